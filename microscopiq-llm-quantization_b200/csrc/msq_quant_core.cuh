@@ -1,0 +1,256 @@
+// msq_quant_core.cuh -- per-block arithmetic of the MX(+outlier) quantizers.
+//
+// A block of `bs` values is held by LPB cooperating lanes, N values each
+// (bs == N * LPB).  Reductions are in-thread over N then xor-butterflies over
+// the LPB lanes (commutative => every lane ends with the identical value).
+//
+// core_outlier : utils/quant.py:23-266 (variant 0) and
+//                number_system/mx/mx_ops.py:210-330 (variant 1, bounds supplied)
+// core_plain   : number_system/mx/mx_ops.py:426-451 (mode 0, incl. the +1e-6 of :444)
+//                and cpp/mx.cuh:37-52 + cpp/shared_exp.cuh:14-53 (mode 1)
+#pragma once
+#include "msq_common.cuh"
+
+namespace msq {
+
+struct QCfg {
+  Fmt fin, fout;
+  int sb_in, sb_out;
+  float std_dev;
+  int flush;
+  int variant;   // outlier: 0 = utils/quant (under -> -20), 1 = mx_ops (bounds external, under -> -S)
+  int mode;      // plain  : 0 = python (+1e-6), 1 = spec/native
+  int rmode;     // Round
+};
+
+template <int LPB> __device__ __forceinline__ double grp_sum(double v) {
+#pragma unroll
+  for (int o = LPB / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int LPB> __device__ __forceinline__ float grp_max(float v) {
+#pragma unroll
+  for (int o = LPB / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int LPB> __device__ __forceinline__ int grp_add(int v) {
+#pragma unroll
+  for (int o = LPB / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int LPB> __device__ __forceinline__ int grp_or(int v) {
+#pragma unroll
+  for (int o = LPB / 2; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float qelem_rt(float v, const Fmt& f, int rmode) {
+  if (rmode == RD_NEAREST) return qelem<RD_NEAREST>(v, f, true, true);
+  if (rmode == RD_FLOOR) return qelem<RD_FLOOR>(v, f, true, true);
+  return qelem<RD_EVEN>(v, f, true, true);
+}
+
+struct BlockOut {
+  uint32_t mask;   // bit i set: x[i] is an outlier
+  int e_in, e_out; // clamped shared exponents (MSQ_EXP_NAN on overflow)
+  int cnt;         // outliers in the whole block (all lanes)
+  int st;          // status bits raised by this block
+};
+
+// x[] in: block values (padding = 0).  x[] out: dequantized values.
+// code[] out (if CODES): element codes, inlier or outlier format according to mask.
+template <int N, int LPB, bool CODES>
+__device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)[N], const QCfg& c,
+                                                 const float* lo_e, const float* hi_e) {
+  constexpr int BS = N * LPB;
+  BlockOut o;
+  o.st = 0;
+  int bad = 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) bad |= !(fabsf(x[i]) <= 3.402823466e38f);
+  bad = grp_or<LPB>(bad);
+
+  float lo[N], hi[N];
+  if (c.variant == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) s += (double)fabsf(x[i]);
+    s = grp_sum<LPB>(s);
+    const double mean64 = s / (double)BS;
+    double q = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double d = (double)fabsf(x[i]) - mean64;
+      q = fma(d, d, q);
+    }
+    q = grp_sum<LPB>(q);
+    const float mean = (float)mean64;
+    const float sd = (float)sqrt(q / (double)BS);
+    const float w = __fmul_rn(c.std_dev, sd);
+    const float l = __fsub_rn(mean, w), h = __fadd_rn(mean, w);
+#pragma unroll
+    for (int i = 0; i < N; ++i) { lo[i] = l; hi[i] = h; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) { lo[i] = lo_e[i]; hi[i] = hi_e[i]; }
+  }
+
+  uint32_t mask = 0;
+  float m_in = 0.0f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    bool isout = (x[i] < lo[i]) | (x[i] > hi[i]);
+    mask |= (isout ? 1u : 0u) << i;
+    m_in = isout ? m_in : fmaxf(m_in, fabsf(x[i]));
+  }
+  o.mask = mask;
+  o.cnt = grp_add<LPB>(__popc(mask));
+  m_in = grp_max<LPB>(m_in);
+
+  const int E_in = (m_in == 0.0f) ? -126 : floor_log2f(m_in);
+  const bool flush = c.flush && (E_in <= -127);
+  o.e_in = clamp_scale_exp(E_in - c.fin.emax, c.sb_in, c.variant == 0);
+  if (bad) o.st |= MSQ_ST_NONFINITE_INPUT;
+  if (o.e_in == MSQ_EXP_NAN) o.st |= MSQ_ST_EXP_IN_OVERFLOW;
+  if (bad || o.e_in == MSQ_EXP_NAN) {
+    o.e_out = MSQ_EXP_NAN;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { x[i] = qnan(); if (CODES) code[i] = 0; }
+    return o;
+  }
+  const float s_in = pow2i(o.e_in), inv_s_in = pow2i(-o.e_in);
+
+  float m_out = 0.0f;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    if ((mask >> i) & 1u) m_out = fmaxf(m_out, fabsf(__fmul_rn(x[i], s_in)));
+  m_out = grp_max<LPB>(m_out);
+  const int E_out = (m_out == 0.0f) ? -126 : floor_log2f(m_out);
+  o.e_out = clamp_scale_exp(E_out - c.fout.emax, c.sb_out, c.variant == 0);
+  if (o.e_out == MSQ_EXP_NAN) {
+    o.st |= MSQ_ST_EXP_OUT_OVERFLOW;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { x[i] = qnan(); if (CODES) code[i] = 0; }
+    return o;
+  }
+  const float s_out = pow2i(o.e_out), inv_s_out = pow2i(-o.e_out);
+
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const bool isout = (mask >> i) & 1u;
+    float v, r, qv;
+    if (isout) {
+      v = __fmul_rn(__fmul_rn(x[i], s_in), inv_s_out);           // quant.py:94,125
+      qv = qelem_rt(v, c.fout, c.rmode);
+      r = __fmul_rn(__fmul_rn(qv, s_out), inv_s_in);             // quant.py:136
+      if (CODES) code[i] = encode_elem(qv, c.fout.ebits, c.fout.bits);
+    } else {
+      v = __fmul_rn(flush ? __fmul_rn(x[i], 0.0f) : x[i], inv_s_in);   // quant.py:80,92
+      qv = qelem_rt(v, c.fin, c.rmode);
+      r = __fmul_rn(qv, s_in);                                    // quant.py:102
+      if (CODES) code[i] = encode_elem(qv, c.fin.ebits, c.fin.bits);
+    }
+    x[i] = __fadd_rn(r, 0.0f);                                    // quant.py:140 (x + 0)
+  }
+  return o;
+}
+
+// cpp/quantize.cuh:88-149 restated: integer-mantissa rounding of one fp32 value.
+__device__ __forceinline__ float qelem_native(float x, int bits, int ebits, float max_norm, int rmode,
+                                              bool saturate, bool allow_denorm) {
+  const uint32_t u = (uint32_t)__float_as_int(x);
+  const uint32_t sign = u >> 31;
+  int be = (int)((u >> 23) & 0xFFu);
+  int man = (int)(u & 0x7FFFFFu);
+  const int mb = bits - 1;                       // magnitude bits incl. implicit one
+  const bool is_int = ebits == 0;
+  const int nbias = is_int ? 1 : (1 << (ebits - 1)) - 1;
+  const int nbe = be - 127 + nbias;
+  if (!is_int && !allow_denorm && nbe < 1) return 0.0f;
+  int ediff = nbe <= 0 ? 1 - nbe : 0;
+  ediff = ediff > 24 ? 24 : ediff;
+  const bool sub = be == 0;
+  const int sig = sub ? 23 : 24;
+  if (!sub) man += (1 << 23);
+  bool tie = false, ev = false;
+  if (rmode == RD_EVEN) {
+    const int tb = ediff + (sig - mb);
+    tie = (man & ((1 << (tb - 1)) - 1)) == 0;
+    ev = (man & (1 << tb)) == 0;
+  }
+  man >>= ediff;
+  man >>= (sig - mb - 1);
+  if (rmode != RD_FLOOR && (!is_int || man != ((1 << (mb + 1)) - 1)) && !(tie && ev)) man += 1;
+  man >>= 1;
+  if (man == 0) return 0.0f;
+  man <<= (sig - mb + ediff);
+  const bool ovf = man >= (1 << sig);
+  if (ovf && !sub) man >>= 1;
+  man &= 0x7FFFFF;
+  if (ovf) be += 1;
+  float out = __int_as_float((int)((sign << 31) | ((uint32_t)be << 23) | (uint32_t)man));
+  if (fabsf(out) > max_norm) {
+    if (is_int || saturate) out = sign ? -max_norm : max_norm;
+    else out = __int_as_float((int)((sign << 31) | 0x7F800000u));
+  }
+  return out;
+}
+
+struct PlainOut { int e; int st; };
+
+template <int N, int LPB>
+__device__ __forceinline__ PlainOut core_plain(float (&x)[N], uint32_t (&code)[N], bool want_codes,
+                                               const QCfg& c, const float* ext_max) {
+  PlainOut o; o.st = 0;
+  int bad = 0;
+  float m = 0.0f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) { bad |= !(fabsf(x[i]) <= 3.402823466e38f); m = fmaxf(m, fabsf(x[i])); }
+  bad = grp_or<LPB>(bad);
+  m = grp_max<LPB>(m);
+  if (ext_max) { m = fabsf(*ext_max); bad = !(m <= 3.402823466e38f); }
+  const Fmt& f = c.fin;
+  if (c.mode == 0) {
+    const int E = (m == 0.0f) ? -126 : floor_log2f(m);
+    const bool flush = c.flush && (E <= -127);
+    int e = bad ? MSQ_EXP_NAN : clamp_scale_exp(E - f.emax, c.sb_in, false);
+    o.e = e;
+    if (e == MSQ_EXP_NAN) {
+      o.st |= bad ? MSQ_ST_NONFINITE_INPUT : MSQ_ST_EXP_IN_OVERFLOW;
+#pragma unroll
+      for (int i = 0; i < N; ++i) { x[i] = qnan(); code[i] = 0; }
+      return o;
+    }
+    const float s = pow2i(e);
+    const float den = __fadd_rn(s, 1e-6f);                       // mx_ops.py:444
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float v = __fdiv_rn(flush ? __fmul_rn(x[i], 0.0f) : x[i], den);
+      float qv = qelem_rt(v, f, c.rmode);
+      if (want_codes) code[i] = encode_elem(qv, f.ebits, f.bits);
+      x[i] = __fmul_rn(qv, s);
+    }
+  } else {
+    int be = bad ? 255 : ((__float_as_int(m) >> 23) & 0xFF);
+    const bool flush = (be == 0) && c.flush;
+    int sh = (be != 255) ? be - f.emax : 255;                     // shared_exp.cuh:39-41
+    const int S = c.sb_in != 0 ? (1 << (c.sb_in - 1)) - 1 : 255;
+    const int ub = sh - 127;
+    sh = ub > S ? 255 : sh;
+    sh = ub < -S ? 127 - S : sh;
+    const int mant = (sh == 0 || sh == 255) ? 0x400000 : 0;
+    const float s = __int_as_float((sh << 23) | mant);
+    o.e = sh == 255 ? MSQ_EXP_NAN : sh - 127;
+    if (sh == 255) o.st |= bad ? MSQ_ST_NONFINITE_INPUT : MSQ_ST_EXP_IN_OVERFLOW;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float v = flush ? 0.0f : __fdiv_rn(x[i], s);
+      float qv = qelem_native(v, f.bits, f.ebits, f.max_norm, c.rmode, true, true);
+      if (want_codes) code[i] = (qv == qv) ? encode_elem(qv, f.ebits, f.bits) : 0;
+      x[i] = __fmul_rn(qv, s);
+    }
+  }
+  return o;
+}
+
+}  // namespace msq

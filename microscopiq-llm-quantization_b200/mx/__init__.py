@@ -1,0 +1,7 @@
+"""`mx` namespace of the reference (number_system/mx/__init__.py): format table, specs and
+quantization entry points, backed by libmsq_b200.so."""
+from .formats import ElemFormat, RoundingMode, _get_format_params  # noqa: F401
+from .specs import (MxSpecs, add_mx_args, apply_mx_specs, finalize_mx_specs, get_backwards_mx_specs,  # noqa: F401
+                    get_default_mx_specs, get_mx_specs, mx_assert_test)
+from .elemwise_ops import quantize_elemwise_op  # noqa: F401
+from .mx_ops import quantize_mx_op, quantize_mx_outlier_op  # noqa: F401
