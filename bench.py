@@ -1,0 +1,245 @@
+#!/usr/bin/env python
+"""bench.py -- MicroScopiQ quantization hot path on B200 (contract: see the task statement).
+
+A *step* = one pass of the MX+outlier quantizer (utils/quant.py:147 quantize_mx_outlier_v1,
+the call the reference's RTN driver makes per linear, llm/llama.py:238-253) over the seven
+linears of one LLaMA-2-7B decoder layer (q,k,v,o 4096x4096; gate,up 11008x4096; down
+4096x11008; fp32), MX-FP4 inliers / FP8-E4M3 outliers, blocks of 16 along the output-row
+axis -- BASELINE.json configs[1].  metric = GB/s of algorithmic bytes (4 B read + 4 B
+written per element), whole job.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+LAYER_SHAPES = [("q_proj", 4096, 4096), ("k_proj", 4096, 4096), ("v_proj", 4096, 4096), ("o_proj", 4096, 4096),
+                ("gate_proj", 11008, 4096), ("up_proj", 11008, 4096), ("down_proj", 4096, 11008)]
+QCFG = dict(in_sb=8, out_sb=8, in_fmt="fp4_e2m1", out_fmt="fp8_e4m3", std_dev=2, axis=0, bs=16)
+WORKLOAD = ("LLaMA-2-7B decoder-layer linears (4x4096x4096, 2x11008x4096, 4096x11008) fp32, "
+            "MX-FP4 inlier / FP8-E4M3 outlier fake-quant, block 16 along rows (quantize_mx_outlier_v1)")
+BYTES_PER_ELEM = 8.0
+METRIC, UNIT = "mx_quant_GBps", "GB/s"
+
+
+def layer_elems():
+    return sum(r * c for _, r, c in LAYER_SHAPES)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_weights(device, seed):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _, r, c in LAYER_SHAPES:
+        out.append((torch.randn(r, c, generator=g) * 0.02))
+    return out
+
+
+def cpu_reference_pass(W):
+    """the reference's CPU implementation of the path = the torch-CPU oracle port"""
+    import msq_oracle as O
+    return O.quantize_mx_outlier(W, QCFG["in_sb"], QCFG["out_sb"], QCFG["in_fmt"], QCFG["out_fmt"], QCFG["std_dev"],
+                                 QCFG["axis"], QCFG["bs"])
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU path on the host cores, bounded sample (one 4096x4096 linear per step)"""
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    W = torch.randn(4096, 4096, generator=torch.Generator().manual_seed(0)) * 0.02
+    for _ in range(args.warmup):
+        cpu_reference_pass(W)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_pass(W)
+    dt = (time.perf_counter() - t0) / args.steps
+    v = W.numel() * BYTES_PER_ELEM / dt / 1e9
+    sample = "one q_proj-sized linear (4096x4096 fp32 = 1/12 of a step's elements) per step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import msq_b200
+    from msq_b200 import _ops
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # each rank owns a different decoder layer (layers quantize independently: no collective)
+    host_w = [w.pin_memory() for w in make_weights(dev, 1000 + rank)]
+    dev_w = [w.to(dev) for w in host_w]
+    dev_out = [torch.empty_like(w) for w in dev_w]
+    host_out = [torch.empty_like(w).pin_memory() for w in host_w]
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    nel = layer_elems()
+
+    def step_device():
+        for w, o in zip(dev_w, dev_out):
+            _ops.mx_outlier(w, QCFG["in_sb"], QCFG["out_sb"], QCFG["in_fmt"], QCFG["out_fmt"], QCFG["std_dev"],
+                            QCFG["axis"], QCFG["bs"], want=("deq",), check=False, out=o, status=status)
+
+    def step_e2e():
+        for hw, ho in zip(host_w, host_out):
+            w = hw.to(dev, non_blocking=True)
+            y = msq_b200.quantize_mx_outlier_v1(w, QCFG["in_sb"], QCFG["out_sb"], QCFG["in_fmt"], QCFG["out_fmt"],
+                                                "max", QCFG["std_dev"], [QCFG["axis"]], QCFG["bs"])
+            ho.copy_(y, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.summary() if rank == 0 else None
+    assert int(status.item()) == 0, "quantizer raised status %d" % int(status.item())
+
+    # end to end through the public API with host buffers
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e2e_steps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+
+    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    ms_step = ms / args.steps
+    bytes_step = nel * BYTES_PER_ELEM
+    value = world * bytes_step / (ms_step * 1e-3) / 1e9
+    peak, peak_src = peaks()
+    per_gpu = bytes_step / (ms_step * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "elements_per_step_per_gpu": nel, "l2": "inputs larger than L2 (810 MB read + 810 MB written per step)",
+                   "sharding": "one decoder layer per rank, no collective"},
+        "clocks": clocks,
+        "e2e": {"value": world * bytes_step / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": nel * 4, "d2h_bytes_per_step": nel * 4,
+                "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": len(LAYER_SHAPES) * args.steps,
+        "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
+                     "traffic": None, "kernel": "k_strided<16,4,outlier>", "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": "8 B x rows x cols"},
+    }
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        line["roofline"]["traffic"] = json.load(open(tr)).get("k_strided_bytes_per_launch")
+    if not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count())
+        W = host_w[0]
+        cpu_reference_pass(W)
+        t0 = time.perf_counter()
+        n = 0
+        while time.perf_counter() - t0 < 10.0 or n < 2:
+            cpu_reference_pass(W)
+            n += 1
+        dt = (time.perf_counter() - t0) / n
+        line["cpu_baseline"] = {"value": W.numel() * BYTES_PER_ELEM / dt / 1e9, "unit": UNIT, "cores": os.cpu_count(),
+                                "kind": "port", "sample": "q_proj 4096x4096 (1/12 of a step), %d passes" % n}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -103,8 +103,10 @@ def across_block_bounds(x, axis, bs, std_dev):
 
 
 def mx_outlier(A, in_sb, out_sb, in_fmt, out_fmt, std_dev, axis, block_size, round="nearest", flush=False,
-               variant=0, want=("deq",), check=None):
-    """MX+outlier fake-quant.  want: subset of {deq, e_in, e_out, blk_cnt, mask}."""
+               variant=0, want=("deq",), check=None, out=None, status=None):
+    """MX+outlier fake-quant.  want: subset of {deq, e_in, e_out, blk_cnt, mask}.
+    out / status: optional preallocated fp32 output and int32[1] status word (no allocation,
+    and with check=False no host synchronisation)."""
     x = _as_f32(A)
     pre, L, post = geometry(x.shape, axis)
     bs = int(block_size) if block_size and block_size > 0 else L
@@ -114,12 +116,12 @@ def mx_outlier(A, in_sb, out_sb, in_fmt, out_fmt, std_dev, axis, block_size, rou
     dev = x.device
     r = OutlierResult()
     r.geom = (pre, L, post, bs, nblk)
-    r.deq = torch.empty_like(x) if "deq" in want else None
+    r.deq = (out if out is not None else torch.empty_like(x)) if "deq" in want else None
     r.e_in = torch.empty(nb, dtype=torch.int8, device=dev) if "e_in" in want else None
     r.e_out = torch.empty(nb, dtype=torch.int8, device=dev) if "e_out" in want else None
     r.blk_cnt = torch.empty(nb, dtype=torch.uint8, device=dev) if "blk_cnt" in want else None
     r.mask = torch.empty(x.shape, dtype=torch.uint8, device=dev) if "mask" in want else None
-    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = status if status is not None else torch.zeros(1, dtype=torch.int32, device=dev)
     lo = hi = None
     if variant == 1:
         lo, hi = across_block_bounds(x, axis, bs, std_dev)

@@ -44,10 +44,56 @@ template <int LPB> __device__ __forceinline__ int grp_or(int v) {
   return v;
 }
 
+// Rounding selected at run time without duplicating the element code:
+// addend = 0.5 (nearest / even) or 0 (floor); `even` subtracts one on exact .5 ties
+// whose floor is even (elemwise_ops.py:59-72).
+struct RoundSel { float addend; bool even; };
+__device__ __forceinline__ RoundSel make_round(int rmode) {
+  RoundSel r; r.addend = (rmode == RD_FLOOR) ? 0.0f : 0.5f; r.even = (rmode == RD_EVEN); return r;
+}
+
+// _quantize_elemwise_core with saturate_normals=True, allow_denorm=True (the only way the MX
+// quantizers call it, quant.py:96-99), format chosen per element by `isf/min_exp/up/down/mx`.
+__device__ __forceinline__ float qelem_mx(float x, bool isf, int min_exp, float up, float down, float mx,
+                                          const RoundSel rs) {
+  const float ax = fabsf(x);
+  const int be = __float_as_int(ax) >> 23;
+  const int p = isf ? min(max(be - 127, min_exp), 127) : 0;
+  float y = __fmul_rn(__fmul_rn(x, pow2i(-p)), up);
+  const float a = fabsf(y);
+  float r = floorf(__fadd_rn(a, rs.addend));
+  if (rs.even) {
+    const float t = __fadd_rn(a, -0.5f);
+    const float h = __fmul_rn(t, 0.5f);
+    if (t >= 0.0f && h == floorf(h)) r = __fadd_rn(r, -1.0f);
+  }
+  y = __fmul_rn(__fmul_rn(copysignf(r, y), down), pow2i(p));
+  y = (y > mx) ? mx : y;
+  y = (y < -mx) ? -mx : y;
+  return (ax == __int_as_float(0x7F800000)) ? x : y;
+}
+
 __device__ __forceinline__ float qelem_rt(float v, const Fmt& f, int rmode) {
-  if (rmode == RD_NEAREST) return qelem<RD_NEAREST>(v, f, true, true);
-  if (rmode == RD_FLOOR) return qelem<RD_FLOOR>(v, f, true, true);
-  return qelem<RD_EVEN>(v, f, true, true);
+  return qelem_mx(v, f.ebits != 0, f.min_exp, f.up, f.down, f.max_norm, make_round(rmode));
+}
+
+// Same arithmetic for FINITE inputs with |x| < 2^127 (true for every scaled block element:
+// |x / 2^e| <= 2^(emax+1)), which lets both powers of two be built with one integer op each
+// and the clamp use min/max.
+__device__ __forceinline__ float qelem_mx_bounded(float x, bool isf, int min_exp, float up, float down, float mx,
+                                                  const RoundSel rs) {
+  const int be = (__float_as_int(x) >> 23) & 0xFF;
+  const int p = isf ? max(be - 127, min_exp) : 0;
+  float y = __fmul_rn(__fmul_rn(x, __int_as_float((127 - p) << 23)), up);
+  const float a = fabsf(y);
+  float r = floorf(__fadd_rn(a, rs.addend));
+  if (rs.even) {
+    const float t = __fadd_rn(a, -0.5f);
+    const float h = __fmul_rn(t, 0.5f);
+    if (t >= 0.0f && h == floorf(h)) r = __fadd_rn(r, -1.0f);
+  }
+  y = __fmul_rn(__fmul_rn(copysignf(r, y), down), __int_as_float((p + 127) << 23));
+  return fminf(fmaxf(y, -mx), mx);
 }
 
 struct BlockOut {
@@ -59,47 +105,48 @@ struct BlockOut {
 
 // x[] in: block values (padding = 0).  x[] out: dequantized values.
 // code[] out (if CODES): element codes, inlier or outlier format according to mask.
-template <int N, int LPB, bool CODES>
+// EXT: detector bounds come from lo_e/hi_e (variant 1) instead of block statistics.
+template <int N, int LPB, bool CODES, bool EXT>
 __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)[N], const QCfg& c,
                                                  const float* lo_e, const float* hi_e) {
   constexpr int BS = N * LPB;
   BlockOut o;
   o.st = 0;
   int bad = 0;
-#pragma unroll
-  for (int i = 0; i < N; ++i) bad |= !(fabsf(x[i]) <= 3.402823466e38f);
-  bad = grp_or<LPB>(bad);
-
-  float lo[N], hi[N];
-  if (c.variant == 0) {
+  float l = 0.0f, h = 0.0f;
+  if (!EXT) {
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) s += (double)fabsf(x[i]);
+    for (int i = 0; i < N; ++i) {
+      const float a = fabsf(x[i]);
+      bad |= !(a <= 3.402823466e38f);
+      s += (double)a;
+    }
     s = grp_sum<LPB>(s);
     const double mean64 = s / (double)BS;
     double q = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      double d = (double)fabsf(x[i]) - mean64;
+      const double d = (double)fabsf(x[i]) - mean64;
       q = fma(d, d, q);
     }
     q = grp_sum<LPB>(q);
     const float mean = (float)mean64;
     const float sd = (float)sqrt(q / (double)BS);
     const float w = __fmul_rn(c.std_dev, sd);
-    const float l = __fsub_rn(mean, w), h = __fadd_rn(mean, w);
-#pragma unroll
-    for (int i = 0; i < N; ++i) { lo[i] = l; hi[i] = h; }
+    l = __fsub_rn(mean, w); h = __fadd_rn(mean, w);
   } else {
 #pragma unroll
-    for (int i = 0; i < N; ++i) { lo[i] = lo_e[i]; hi[i] = hi_e[i]; }
+    for (int i = 0; i < N; ++i) bad |= !(fabsf(x[i]) <= 3.402823466e38f);
   }
+  if (LPB > 1) bad = grp_or<LPB>(bad);
 
   uint32_t mask = 0;
   float m_in = 0.0f;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    bool isout = (x[i] < lo[i]) | (x[i] > hi[i]);
+    const float li = EXT ? lo_e[i] : l, hi_i = EXT ? hi_e[i] : h;
+    const bool isout = (x[i] < li) | (x[i] > hi_i);
     mask |= (isout ? 1u : 0u) << i;
     m_in = isout ? m_in : fmaxf(m_in, fabsf(x[i]));
   }
@@ -112,45 +159,44 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
   o.e_in = clamp_scale_exp(E_in - c.fin.emax, c.sb_in, c.variant == 0);
   if (bad) o.st |= MSQ_ST_NONFINITE_INPUT;
   if (o.e_in == MSQ_EXP_NAN) o.st |= MSQ_ST_EXP_IN_OVERFLOW;
-  if (bad || o.e_in == MSQ_EXP_NAN) {
-    o.e_out = MSQ_EXP_NAN;
-#pragma unroll
-    for (int i = 0; i < N; ++i) { x[i] = qnan(); if (CODES) code[i] = 0; }
-    return o;
-  }
-  const float s_in = pow2i(o.e_in), inv_s_in = pow2i(-o.e_in);
+  const bool dead_in = bad || o.e_in == MSQ_EXP_NAN;
+  const int e_in = dead_in ? 0 : o.e_in;
+  const float s_in = pow2i(e_in), inv_s_in = pow2i(-e_in);
 
   float m_out = 0.0f;
 #pragma unroll
-  for (int i = 0; i < N; ++i)
-    if ((mask >> i) & 1u) m_out = fmaxf(m_out, fabsf(__fmul_rn(x[i], s_in)));
+  for (int i = 0; i < N; ++i) {
+    const float t = fabsf(__fmul_rn(x[i], s_in));
+    m_out = ((mask >> i) & 1u) ? fmaxf(m_out, t) : m_out;
+  }
   m_out = grp_max<LPB>(m_out);
   const int E_out = (m_out == 0.0f) ? -126 : floor_log2f(m_out);
-  o.e_out = clamp_scale_exp(E_out - c.fout.emax, c.sb_out, c.variant == 0);
-  if (o.e_out == MSQ_EXP_NAN) {
-    o.st |= MSQ_ST_EXP_OUT_OVERFLOW;
-#pragma unroll
-    for (int i = 0; i < N; ++i) { x[i] = qnan(); if (CODES) code[i] = 0; }
-    return o;
-  }
-  const float s_out = pow2i(o.e_out), inv_s_out = pow2i(-o.e_out);
+  o.e_out = dead_in ? MSQ_EXP_NAN : clamp_scale_exp(E_out - c.fout.emax, c.sb_out, c.variant == 0);
+  if (!dead_in && o.e_out == MSQ_EXP_NAN) o.st |= MSQ_ST_EXP_OUT_OVERFLOW;
+  const bool dead = dead_in || o.e_out == MSQ_EXP_NAN;
+  const int e_out = dead ? 0 : o.e_out;
+  const float s_out = pow2i(e_out), inv_s_out = pow2i(-e_out);
+  const RoundSel rs = make_round(c.rmode);
+  const bool f_in = c.fin.ebits != 0, f_out = c.fout.ebits != 0;
+  const float in_m1 = flush ? 0.0f : 1.0f;
 
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const bool isout = (mask >> i) & 1u;
-    float v, r, qv;
-    if (isout) {
-      v = __fmul_rn(__fmul_rn(x[i], s_in), inv_s_out);           // quant.py:94,125
-      qv = qelem_rt(v, c.fout, c.rmode);
-      r = __fmul_rn(__fmul_rn(qv, s_out), inv_s_in);             // quant.py:136
-      if (CODES) code[i] = encode_elem(qv, c.fout.ebits, c.fout.bits);
-    } else {
-      v = __fmul_rn(flush ? __fmul_rn(x[i], 0.0f) : x[i], inv_s_in);   // quant.py:80,92
-      qv = qelem_rt(v, c.fin, c.rmode);
-      r = __fmul_rn(qv, s_in);                                    // quant.py:102
-      if (CODES) code[i] = encode_elem(qv, c.fin.ebits, c.fin.bits);
-    }
-    x[i] = __fadd_rn(r, 0.0f);                                    // quant.py:140 (x + 0)
+    // inlier : v = (x*[flush?0:1]) * 2^-e_in ;  r = (q * 2^e_in) * 1          quant.py:80,92,102
+    // outlier: v = (x*2^e_in) * 2^-e_out      ;  r = (q * 2^e_out) * 2^-e_in   quant.py:94,125,136
+    const float m1 = isout ? s_in : in_m1, m2 = isout ? inv_s_out : inv_s_in;
+    const float d1 = isout ? s_out : s_in, d2 = isout ? inv_s_in : 1.0f;
+    const float v = __fmul_rn(__fmul_rn(x[i], m1), m2);
+    const float qv = qelem_mx_bounded(v, isout ? f_out : f_in, isout ? c.fout.min_exp : c.fin.min_exp,
+                                      isout ? c.fout.up : c.fin.up, isout ? c.fout.down : c.fin.down,
+                                      isout ? c.fout.max_norm : c.fin.max_norm, rs);
+    if (CODES) code[i] = encode_elem(qv, isout ? c.fout.ebits : c.fin.ebits, isout ? c.fout.bits : c.fin.bits);
+    x[i] = __fadd_rn(__fmul_rn(__fmul_rn(qv, d1), d2), 0.0f);                   // quant.py:140 (x + 0)
+  }
+  if (dead) {      // NaN/Inf input or a shared exponent above the scale range: the reference asserts
+#pragma unroll
+    for (int i = 0; i < N; ++i) { x[i] = qnan(); if (CODES) code[i] = 0u; }
   }
   return o;
 }

@@ -1,0 +1,66 @@
+// msq_quant_kernels.cuh -- parameter block and launchers shared by the quantizer kernels.
+//
+// Geometry: the tensor is viewed as [pre, L, post]; blocks of `bs` run along L
+// (zero-padded to a multiple of bs, utils/quant.py:563-583).  Block-linear index
+// t = (p*nblk + b)*post + j.  A packed *segment* is MSQ_SEG_BLOCKS consecutive t.
+#pragma once
+#include "msq_quant_core.cuh"
+#include "msq_api_internal.h"
+
+namespace msq {
+
+struct QParams {
+  long long pre, post, nblocks;   // nblocks = pre*nblk*post
+  int L, bs, nblk;
+  QCfg c;
+  const float* in;
+  float* deq;          // optional
+  uint8_t* codes;      // optional (packed, inlier container width)
+  int8_t* e_in;        // optional [nblocks]
+  int8_t* e_out;       // optional [nblocks]
+  uint32_t* bitmap;    // optional, 1 bit / element, linear element order
+  uint8_t* hi;         // optional, segment-compacted high bits of outlier codes
+  int* seg_cnt;        // optional [nseg]
+  uint8_t* blk_cnt;    // optional [nblocks] outliers per block
+  uint8_t* mask;       // optional, 1 byte / element
+  int* status;         // optional, OR of MSQ_ST_*
+  const float* lo_ext; // variant 1: [pre, bs, post]
+  const float* hi_ext;
+  const float* ext_max;// plain: optional external block max [nblocks]
+  long long hi_seg_stride;  // bytes
+  int hi_w;            // container width of one hi field (0 = no hi stream)
+};
+
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  total = __shfl_sync(0xffffffffu, inc, 31);
+  return inc - v;
+}
+
+// exclusive scan over the 256 threads of the CTA; returns offset, *sum = CTA total
+__device__ __forceinline__ int cta_excl_scan(int v, int* s_warp, int* sum) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int wt;
+  int ex = warp_excl_scan(v, lane, wt);
+  __syncthreads();
+  if (lane == 0) s_warp[w] = wt;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { int t = s_warp[i]; if (i < w) base += t; tot += t; }
+  *sum = tot;
+  return ex + base;
+}
+
+
+// launchers (one translation unit each); return false if the geometry is not theirs
+cudaError_t launch_strided(const QParams& P, bool outlier, size_t smem, cudaStream_t stream);
+cudaError_t launch_inner(const QParams& P, bool outlier, size_t smem, cudaStream_t stream);
+cudaError_t launch_generic(const QParams& P, bool outlier, cudaStream_t stream);
+
+}  // namespace msq

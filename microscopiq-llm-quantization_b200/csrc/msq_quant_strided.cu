@@ -1,0 +1,161 @@
+// msq_quant_strided.cu -- blocks strided by `post` (e.g. 16 output rows of one weight column,
+// the layout the reference's GPTQ / RTN drivers use: axes=[0] on [rows, cols]).
+//
+// Lane = column: a warp reads 32 consecutive columns of one row per load (128 B, fully
+// coalesced), a thread keeps its whole block (BS rows) in registers.  256 threads = 256
+// consecutive block-linear indices; 4 sub-iterations cover one packed segment.
+//
+// PACK = false : fake-quant (fp32 out, what the reference API returns) + optional per-block
+//                exponents / outlier counts.
+// PACK = true  : packed planes (codes, bitmap, hi stream, exponents); fp32 out optional.
+// Element offsets are 32-bit (host guarantees numel < 2^31 on this path).
+#include "msq_quant_kernels.cuh"
+
+namespace msq {
+
+template <int BS, bool OUTLIER, bool PACK, bool EXT>
+__global__ void __launch_bounds__(256) k_strided(const QParams P) {
+  extern __shared__ uint32_t s_hi[];
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const long long seg = blockIdx.x;
+  const bool pack_hi = PACK && OUTLIER && P.hi_w > 0;
+  const int wi = P.c.fin.width;
+  const int lane = threadIdx.x & 31;
+  const int post = (int)P.post;
+  if (pack_hi) {
+    const int words = (int)(P.hi_seg_stride >> 2);
+    for (int i = threadIdx.x; i < words; i += 256) s_hi[i] = 0;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+  }
+  int st = 0;
+#pragma unroll 1
+  for (int sub = 0; sub < MSQ_SEG_BLOCKS / 256; ++sub) {
+    const long long t0 = seg * MSQ_SEG_BLOCKS + (long long)sub * 256 + threadIdx.x;
+    const bool active = t0 < P.nblocks;
+    float x[BS];
+    uint32_t code[BS];
+    int base = 0, p = 0, j = 0, b = 0;
+    if (active) {
+      const int pb = (int)(t0 / post);
+      j = (int)(t0 - (long long)pb * post);
+      p = pb / P.nblk; b = pb - p * P.nblk;
+      base = (p * P.L + b * BS) * post + j;
+    }
+    const int nv = active ? min(BS, P.L - b * BS) : 0;       // valid rows, the rest is zero padding
+    const float* pin = P.in + base;
+    if (nv == BS) {
+#pragma unroll
+      for (int i = 0; i < BS; ++i) x[i] = __ldg(pin + i * post);
+    } else {
+#pragma unroll
+      for (int i = 0; i < BS; ++i) x[i] = (i < nv) ? __ldg(pin + i * post) : 0.0f;
+    }
+
+    BlockOut bo;
+    if (OUTLIER) {
+      float lo[BS], hi[BS];
+      if (EXT) {
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+          const int o = active ? (p * BS + i) * post + j : 0;
+          lo[i] = P.lo_ext[o]; hi[i] = P.hi_ext[o];
+        }
+      }
+      bo = core_outlier<BS, 1, PACK, EXT>(x, code, P.c, lo, hi);
+    } else {
+      PlainOut po = core_plain<BS, 1>(x, code, PACK, P.c, (P.ext_max && active) ? P.ext_max + t0 : nullptr);
+      bo.mask = 0; bo.e_in = po.e; bo.e_out = 0; bo.cnt = 0; bo.st = po.st;
+    }
+    if (active) st |= bo.st;
+
+    // ---- stores: lane = column, so every row is one coalesced warp store ----
+    if (!PACK || P.deq) {
+      float* pout = P.deq + base;
+      if (nv == BS) {
+#pragma unroll
+        for (int i = 0; i < BS; ++i) pout[i * post] = x[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < BS; ++i)
+          if (i < nv) pout[i * post] = x[i];
+      }
+    }
+    if (active) {
+      if (P.e_in) P.e_in[t0] = (int8_t)bo.e_in;
+      if (OUTLIER && P.e_out) P.e_out[t0] = (int8_t)bo.e_out;
+      if (OUTLIER && P.blk_cnt) P.blk_cnt[t0] = (uint8_t)bo.cnt;
+    }
+    if (PACK) {
+      // host guarantees post % 32 == 0, so a warp's 32 columns share (p, b) and whole words
+      const int G = 32 / wi;                 // lanes per 32-bit word of codes
+#pragma unroll
+      for (int i = 0; i < BS; ++i) {
+        uint32_t w = (code[i] & ((1u << wi) - 1u)) << ((lane & (G - 1)) * wi);
+        for (int o = 1; o < G; o <<= 1) w |= __shfl_xor_sync(0xffffffffu, w, o);
+        if (i < nv && (lane & (G - 1)) == 0)
+          *reinterpret_cast<uint32_t*>(P.codes + (((long long)(base + i * post) * wi) >> 3)) = w;
+      }
+      if (OUTLIER) {
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+          const uint32_t w = __ballot_sync(0xffffffffu, (bo.mask >> i) & 1u);
+          if (i < nv && lane == 0) P.bitmap[(base + i * post) >> 5] = w;
+        }
+      }
+    }
+    if (pack_hi) {
+      int tot;
+      const int off = cta_excl_scan(active ? bo.cnt : 0, s_warp, &tot);
+      int k = s_base + off;
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+          if ((bo.mask >> i) & 1u) {
+            const int bit = k * P.hi_w;
+            atomicOr(&s_hi[bit >> 5], (code[i] >> wi) << (bit & 31));
+            ++k;
+          }
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) s_base += tot;
+      __syncthreads();
+    }
+  }
+  if (pack_hi) {
+    const int total = s_base;
+    const int words = (total * P.hi_w + 31) >> 5;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(P.hi + seg * P.hi_seg_stride);
+    for (int i = threadIdx.x; i < words; i += 256) dst[i] = s_hi[i];
+    if (threadIdx.x == 0 && P.seg_cnt) P.seg_cnt[seg] = total;
+  } else if (PACK && OUTLIER && P.seg_cnt && threadIdx.x == 0) {
+    P.seg_cnt[seg] = 0;
+  }
+  if (P.status) {
+    st = __reduce_or_sync(0xffffffffu, st);
+    if (lane == 0 && st) atomicOr(P.status, st);
+  }
+}
+
+cudaError_t launch_strided(const QParams& P, bool outlier, size_t smem, cudaStream_t stream) {
+  const long long nseg = (P.nblocks + MSQ_SEG_BLOCKS - 1) / MSQ_SEG_BLOCKS;
+  void (*k)(const QParams) = nullptr;
+  const bool pack = P.codes != nullptr;
+  const bool ext = outlier && P.c.variant != 0;
+#define MSQ_PICK(BS_)                                                                               \
+  if (!outlier) k = pack ? k_strided<BS_, false, true, false> : k_strided<BS_, false, false, false>; \
+  else if (ext) k = pack ? k_strided<BS_, true, true, true> : k_strided<BS_, true, false, true>;     \
+  else k = pack ? k_strided<BS_, true, true, false> : k_strided<BS_, true, false, false>;
+  if (P.bs == 16) { MSQ_PICK(16) }
+  else if (P.bs == 32) { MSQ_PICK(32) }
+  else if (P.bs == 8) { MSQ_PICK(8) }
+  else return cudaErrorInvalidValue;
+#undef MSQ_PICK
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k<<<(unsigned)nseg, 256, smem, stream>>>(P);
+  return cudaGetLastError();
+}
+
+}  // namespace msq

@@ -1,0 +1,281 @@
+"""GPU tier: the CUDA quantizers (through the C ABI / the reference-named Python API)
+against the oracle, the reference fixtures and the reference's known-answer tables."""
+import pytest
+import torch
+
+import golden_core as G
+import msq_oracle as O
+from util import assert_exact, load_json, load_npz, mismatches
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def M():
+    import msq_b200
+    assert torch.cuda.is_available()
+    return msq_b200
+
+
+def dev(x):
+    return torch.as_tensor(x, dtype=torch.float32).cuda()
+
+
+def weights(rows, cols, seed, outliers=True):
+    g = torch.Generator().manual_seed(seed)
+    W = torch.randn(rows, cols, generator=g) * 0.02
+    if outliers:
+        idx = torch.randperm(W.numel(), generator=g)[: max(1, W.numel() // 1000)]
+        W.view(-1)[idx] *= 20
+    return W
+
+
+# ------------------------------------------------------------------ known-answer tables
+@pytest.mark.parametrize("fmt", G.MX_NAN_FORMATS)
+@pytest.mark.parametrize("cc", [False, True])
+def test_mx_nan_poisons_block(M, fmt, cc):
+    for row in G.MX_NAN_INPUTS:
+        y = M._quantize_mx(dev(row), 8, fmt, block_size=4, axes=-1, round="floor", custom_cuda=cc)
+        assert torch.isnan(y).all()
+
+
+@pytest.mark.parametrize("cc", [False, True])
+def test_mx_int4_never_minus_two(M, cc):
+    y = M._quantize_mx(dev(G.MX_INT4_X), 8, "int4", block_size=0, axes=1, custom_cuda=cc)
+    assert_exact(y, dev(G.MX_INT4_Y))
+
+
+def test_mx_hw_table(M):
+    y = M._quantize_mx(dev(G.MX_HW_X), 8, "int8", block_size=10, axes=1, custom_cuda=True)
+    assert_exact(y, dev(G.MX_HW_Y))
+
+
+def test_e5m0_scale(M):
+    x, tt = dev(G.E5M0_X), dev(G.E5M0_T)
+    for sgn in (1.0, -1.0):
+        for ax, xx, t2 in ((-1, x, tt), (0, x.t().contiguous(), tt.t().contiguous())):
+            y = M._quantize_mx(sgn * xx, 5, "int2", axes=[ax], block_size=8, custom_cuda=True)
+            fin = torch.isfinite(t2)
+            assert_exact(y[fin], (sgn * t2)[fin])
+            assert (~torch.isfinite(y[~fin])).all()
+
+
+def test_fp8_e4m3_saturation(M):
+    for pad in (0, 1, 56):
+        x = dev(G.FP8_E4M3_X + [0] * pad)
+        y = M._quantize_mx(x, 8, "fp8_e4m3", block_size=x.shape[-1], axes=[-1], custom_cuda=True)
+        assert_exact(y, dev(G.FP8_E4M3_T + [0] * pad))
+
+
+@pytest.mark.parametrize("rnd", ["nearest", "even"])
+def test_mxfp8_rounding_table(M, rnd):
+    y = M._quantize_mx(dev(G.MXFP8_X), 8, "fp8_e4m3", block_size=32, axes=0, round=rnd, custom_cuda=True)
+    assert_exact(y, dev(G.MXFP8_T))
+    y = M._quantize_mx(dev(G.MXFP8_X), 8, "fp8_e4m3", block_size=32, axes=0, round=rnd, custom_cuda=False)
+    assert_exact(y, O.quantize_mx(torch.tensor(G.MXFP8_X), 8, "fp8_e4m3", 0, 32, rnd, mode="python"))
+
+
+@pytest.mark.parametrize("cc", [False, True])
+def test_bf16_tables(M, cc):
+    from msq_b200.mx.elemwise_ops import _quantize_bfloat, _quantize_fp
+    for ad in (True, False):
+        y = _quantize_bfloat(dev(G.BF16_RNE_X), 16, "even", custom_cuda=cc, allow_denorm=ad)
+        assert float((y.cpu() - torch.tensor(G.BF16_RNE_T)).abs().max()) <= 1e-8
+    y = _quantize_bfloat(dev(G.BF16_MAX_X), 16, "nearest", custom_cuda=cc)
+    assert torch.isfinite(y).tolist() == G.BF16_MAX_FINITE
+    y = _quantize_fp(dev(G.FP16_MAX_X), exp_bits=5, mantissa_bits=10, round="nearest", custom_cuda=cc)
+    assert torch.isfinite(y).tolist() == G.FP16_MAX_FINITE
+    for rnd in ("nearest", "floor", "even"):
+        y = _quantize_bfloat(dev(G.ELEM_NAN_X), 16, rnd, custom_cuda=cc).cpu()
+        assert y[0] == 0 and torch.isnan(y[1]) and torch.isinf(y[2]) and y[3] == 0
+    x = torch.from_numpy(G.all_encodings(8, 9))
+    y = _quantize_bfloat(x.cuda(), 16, "even", custom_cuda=cc).cpu()
+    ref = x.to(torch.bfloat16).float()
+    fin = torch.isfinite(ref)
+    assert_exact(y[fin], ref[fin])
+
+
+@pytest.mark.parametrize("fmt,e,m", [("fp8_e4m3", 4, 3), ("fp8_e5m2", 5, 2), ("fp6_e3m2", 3, 2), ("fp6_e2m3", 2, 3),
+                                     ("fp4_e2m1", 2, 1)])
+@pytest.mark.parametrize("rnd", ["nearest", "floor", "even"])
+@pytest.mark.parametrize("cc", [False, True])
+def test_idempotent_on_own_encodings(M, fmt, e, m, rnd, cc):
+    from msq_b200.mx.elemwise_ops import _quantize_elemwise
+    x = torch.from_numpy(G.all_encodings(e, m, encodes_infs=(fmt == "fp8_e5m2")))
+    y = _quantize_elemwise(x.cuda(), fmt, rnd, custom_cuda=cc, saturate_normals=True)
+    assert_exact(y, x)
+
+
+def test_all_bf16_encodings_through_mx(M):
+    """test_quantize_mx.py:38-65 in spirit: every bf16 encoding through plain MX, GPU == oracle"""
+    x = torch.from_numpy(G.all_encodings(8, 7))
+    x = x[torch.isfinite(x)]
+    x = x[: (x.numel() // 64) * 64].reshape(-1, 64)
+    for fmt in ("fp8_e4m3", "fp6_e3m2", "fp4_e2m1", "int8", "int4"):
+        for bs in (8, 9, 64):
+            for rnd in ("nearest", "floor", "even"):
+                for sb in (8, 5):
+                    y = M._quantize_mx(x.cuda(), sb, fmt, block_size=bs, axes=[-1], round=rnd, custom_cuda=False)
+                    assert_exact(y, O.quantize_mx(x, sb, fmt, -1, bs, rnd, mode="python"), "%s %d %s %d" % (fmt, bs, rnd, sb))
+                    y = M._quantize_mx(x.cuda(), sb, fmt, block_size=bs, axes=[-1], round=rnd, custom_cuda=True)
+                    assert_exact(y, O.quantize_mx(x, sb, fmt, -1, bs, rnd, mode="spec"), "spec %s %d %s %d" % (fmt, bs, rnd, sb))
+
+
+# ------------------------------------------------------------------ fixtures from the reference
+def test_outlier_fixtures(M):
+    z = load_npz("outlier.npz")
+    for c in load_json("outlier_cases.json"):
+        y = M.quantize_mx_outlier_v1(z["x_" + c["name"]].cuda(), c["in_sb"], c["out_sb"], c["in_fmt"], c["out_fmt"],
+                                     "max", c["std_dev"], [c["axis"]], c["bs"], c["round"], False, False)
+        assert_exact(y, z["y_" + c["name"]], c["name"])
+    y = M.quantize_mx_outlier_v1(z["x_flush"].cuda(), 8, 8, "fp4_e2m1", "fp8_e4m3", "max", 2, [0], 16, "nearest", True)
+    assert_exact(y, z["y_flush"], "flush")
+
+
+@pytest.mark.parametrize("rows", [4096, 768, 1000])
+def test_hessian_variant_fixture(M, rows):
+    z = load_npz("outlier.npz")
+    y, n = M.quantize_mx_outlier_hessian(z["hx_%d" % rows].cuda(), 8, 8, "int2", "fp4", "max", 2, [0], 16)
+    assert_exact(y, z["hy_%d" % rows])
+    assert n.dtype == torch.int8 and torch.equal(n.cpu(), z["hn_%d" % rows])
+
+
+def test_mxops_variant_fixtures(M):
+    z = load_npz("mxops_outlier.npz")
+    for n, (f, bs, sb) in enumerate([("fp4_e2m1", 32, 4), ("fp6_e3m2", 32, 4), ("fp4_e2m1", 32, 8), ("int4", 16, 8)]):
+        y = M._quantize_mx_outlier_v1(z["x_%d" % n].cuda(), sb, sb, f, f, block_size=bs, axes=[1])
+        assert_exact(y, z["y_%d" % n], f)
+
+
+def test_plain_mx_fixtures(M):
+    z = load_npz("plain_mx.npz")
+    for n, c in enumerate(load_json("plain_cases.json")):
+        y = M._quantize_mx(z["x_%d" % n].cuda(), c["sb"], c["fmt"], axes=[c["axis"]], block_size=c["bs"], round=c["round"])
+        assert_exact(y, z["y_%d" % n], str(c))
+
+
+def test_elemwise_fixtures(M):
+    z = load_npz("elemwise.npz")
+    x = z["x"].cuda()
+    from msq_b200.mx.elemwise_ops import _quantize_bfloat
+    for rnd in ("nearest", "floor", "even"):
+        assert_exact(_quantize_bfloat(x, 16, rnd), z["bf16_" + rnd])
+        assert_exact(_quantize_bfloat(x, 10, rnd), z["bf10_" + rnd])
+        for f in ("fp8_e4m3", "fp8_e5m2", "fp6_e3m2", "fp6_e2m3", "fp4_e2m1", "int8", "int4", "int2"):
+            eb, mb, _, mn, _ = M._get_format_params(f)
+            assert_exact(M._quantize_elemwise_core(x, mb, eb, mn, rnd, True, True), z["%s_%s_sat" % (f, rnd)], f + rnd)
+            assert_exact(M._quantize_elemwise_core(x, mb, eb, mn, rnd, False, False),
+                         z["%s_%s_nosat_nodenorm" % (f, rnd)], f + rnd)
+
+
+def test_uniform_fixtures(M):
+    z = load_npz("uniform.npz")
+    W = z["w"].cuda()
+    for n, (bits, perch, sym, mse) in enumerate([(4, True, False, False), (4, True, True, False), (3, False, True, False),
+                                                 (2, True, False, True), (8, True, False, False)]):
+        q = M.Quantizer()
+        q.configure(bits, perchannel=perch, sym=sym, mse=mse)
+        q.find_params(W, weight=True)
+        assert q.scale.shape == z["scale_%d" % n].shape
+        if not mse:
+            assert_exact(q.scale, z["scale_%d" % n])
+            assert_exact(q.zero, z["zero_%d" % n])
+            assert_exact(q.quantize(W), z["q_%d" % n])
+        else:   # powf / summation order may pick a neighbouring grid point: compare the objective
+            e_mine = (q.quantize(W).cpu() - z["w"]).abs().pow(2.4).sum(1)
+            e_ref = (z["q_%d" % n] - z["w"]).abs().pow(2.4).sum(1)
+            assert float(((e_mine - e_ref).abs() / e_ref).max()) < 1e-3
+    q = M.Quantizer()
+    q.configure(2, perchannel=True, trits=True)
+    q.find_params(W, weight=True)
+    assert_exact(q.quantize(W), z["q_trits"])
+    q = M.Quantizer()
+    q.configure(4, perchannel=True, sym=False)
+    q.find_params(z["x3"].cuda(), weight=False)
+    assert_exact(q.scale, z["scale_x3"])
+    assert_exact(q.quantize(z["x3"].cuda()), z["q_x3"])
+
+
+# ------------------------------------------------------------------ oracle at larger sizes, every kernel mapping
+CASES = [
+    # in_fmt, out_fmt, bs, axis, shape, expected kernel path (1 strided, 2 innermost, 3 generic)
+    ("int2", "fp4", 16, 0, (1024, 512), 1),
+    ("fp4_e2m1", "fp8_e4m3", 16, 0, (512, 768), 1),
+    ("fp4_e2m1", "fp8_e4m3", 32, 0, (512, 256), 1),
+    ("int2", "fp4", 16, 0, (528, 130), 1),          # ragged rows, post % 4 != 0 -> scalar mapping
+    ("fp4_e2m1", "fp4_e2m1", 32, 1, (256, 1024), 2),
+    ("fp6_e3m2", "fp6_e3m2", 16, 1, (64, 2048), 2),
+    ("int4", "int8", 128, 1, (64, 1024), 2),
+    ("int4", "int8", 64, 1, (64, 1024), 2),
+    ("int8", "fp8_e5m2", 8, 1, (64, 1024), 2),
+    ("fp4_e2m1", "fp8_e4m3", 32, 1, (100, 1000), 3),   # 1000 % 32 != 0
+    ("fp4_e2m1", "fp8_e4m3", 24, 0, (96, 64), 3),
+]
+
+
+@pytest.mark.parametrize("fi,fo,bs,axis,shape,path", CASES)
+@pytest.mark.parametrize("rnd", ["nearest", "even"])
+def test_outlier_vs_oracle(M, fi, fo, bs, axis, shape, path, rnd):
+    from msq_b200 import _ops
+    W = weights(shape[0], shape[1], 11)
+    r = _ops.mx_outlier(W.cuda(), 8, 8, fi, fo, 2, axis, bs, rnd, want=("deq", "e_in", "e_out", "blk_cnt"))
+    assert r.path == path
+    y, art = O.quantize_mx_outlier(W, 8, 8, fi, fo, 2, axis, bs, rnd, artefacts=True)
+    assert_exact(r.deq, y)
+    rm = _ops.mx_outlier(W.cuda(), 8, 8, fi, fo, 2, axis, bs, rnd, want=("deq", "mask"))   # byte mask: generic kernel
+    assert rm.path == 3
+    assert_exact(rm.deq, y)
+    assert_exact(rm.mask, art["mask"])
+    pre, L, post, _, nblk = r.geom
+    assert_exact(r.e_in.view(pre, nblk, post).float(), art["e_in"])
+    assert_exact(r.e_out.view(pre, nblk, post).float(), art["e_out"])
+    X, _ = O.to_blocks(art["mask"], axis, bs)
+    assert_exact(r.blk_cnt.view(pre, nblk, post).float(), X.sum(2))
+
+
+def test_outlier_status_flags(M):
+    W = weights(64, 64, 5)
+    W[3, 3] = float("nan")
+    with pytest.raises(AssertionError):
+        M.quantize_mx_outlier_v1(W.cuda(), 8, 8, "int2", "fp4", "max", 2, [0], 16)
+    with pytest.raises(AssertionError):           # exponent above a 4-bit scale: NaN scale (quant.py:88)
+        M.quantize_mx_outlier_v1((weights(64, 64, 5) * 1e6).cuda(), 4, 4, "fp4", "fp4", "max", 2, [0], 16)
+    with pytest.raises(RuntimeError):             # no CPU fallback
+        M.quantize_mx_outlier_v1(weights(64, 64, 5), 8, 8, "int2", "fp4", "max", 2, [0], 16)
+    assert M.quantize_mx_outlier_v1(W, 8, 8, None, "fp4") is W
+
+
+def test_edge_shapes(M):
+    for shape, axis, bs in (((1, 1), 0, 16), ((16, 1), 0, 16), ((5,), 0, 16), ((3, 7, 5), 1, 4), ((2, 3, 4, 5), 2, 2)):
+        W = weights(1, 1, 1).new_empty(shape).normal_(generator=torch.Generator().manual_seed(2))
+        y = M.quantize_mx_outlier_v1(W.cuda(), 8, 8, "int4", "fp8_e4m3", "max", 2, [axis], bs)
+        assert_exact(y, O.quantize_mx_outlier(W, 8, 8, "int4", "fp8_e4m3", 2, axis, bs))
+        y = M._quantize_mx(W.cuda(), 8, "fp6_e2m3", axes=[axis], block_size=bs)
+        assert_exact(y, O.quantize_mx(W, 8, "fp6_e2m3", axis, bs))
+
+
+def test_full_size_properties(M):
+    """LLaMA-2-7B sized weight: idempotence of the grid + agreement between the strided and
+    the innermost kernels on transposed data (size-independent properties)."""
+    W = weights(4096, 4096, 0).cuda()
+    y = M.quantize_mx_outlier_v1(W, 8, 8, "int2", "fp4", "max", 2, [0], 16)
+    yt = M.quantize_mx_outlier_v1(W.t().contiguous(), 8, 8, "int2", "fp4", "max", 2, [1], 16)
+    assert_exact(y, yt.t())
+    p = M._quantize_mx(W, 8, "fp4_e2m1", axes=[1], block_size=32, custom_cuda=True)
+    assert_exact(M._quantize_mx(p, 8, "fp4_e2m1", axes=[1], block_size=32, custom_cuda=True), p)
+    # against the oracle on a 1/16 slice (rows are independent across 16-row blocks)
+    ref = O.quantize_mx_outlier(W[:256].cpu(), 8, 8, "int2", "fp4", 2, 0, 16)
+    assert_exact(y[:256], ref)
+
+
+def test_helpers(M):
+    from msq_b200.utils.quant import _extract_outlier_indices, _reshape_to_blocks, _shared_exponents, _undo_reshape_to_blocks
+    W = weights(100, 36, 9)
+    A, axes, o, p = _reshape_to_blocks(W.cuda(), [0], 16)
+    assert list(A.shape) == [7, 16, 36] and axes == [0]
+    mask = _extract_outlier_indices(A, 2, [1])
+    X, _ = O.to_blocks(W, 0, 16)
+    assert_exact(mask, O.outlier_mask_block(X, 2)[0].squeeze(0))
+    e = _shared_exponents(A, "max", [1])
+    assert_exact(e, O.shared_exponent(X).squeeze(0))
+    assert_exact(_undo_reshape_to_blocks(A, p, o, axes), W)
