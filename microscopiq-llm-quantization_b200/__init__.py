@@ -12,3 +12,4 @@ from .utils.quant import (quantize_mx_outlier_v1, quantize_mx_outlier_hessian, q
                           MXQuantizer)
 
 __version__ = "0.1.0"
+from .llm.gptq import GPTQ  # noqa: F401,E402

@@ -1,0 +1,60 @@
+"""tcgen05 GEMM / Hessian entry points of the C ABI (csrc/msq_gemm.cu)."""
+import ctypes as C
+
+import torch
+
+from . import _native as N
+
+_p, _ll, _i, _f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
+N.register("msq_gemm_nt_f32out", _i, [_p, _p, _p, _i, _i, _i, _ll, _ll, _ll, _f, _f, _i, _p])
+N.register("msq_hessian_workspace_bytes", _ll, [_i, _i, _i])
+N.register("msq_hessian_accumulate", _i, [_p, _i, _i, _ll, _i, _p, _ll, _f, _f, _p, _ll, _i, _p])
+
+_DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def gemm_nt(A, B, out=None, alpha=1.0, beta=0.0):
+    """out[M,N] (fp32) = alpha * A[M,K] @ B[N,K].T + beta * out ; A, B fp16 or bf16, last dim contiguous"""
+    N.require_cuda(A, "A")
+    N.require_cuda(B, "B")
+    assert A.dtype == B.dtype and A.dtype in (torch.float16, torch.bfloat16)
+    assert A.dim() == 2 and B.dim() == 2 and A.shape[1] == B.shape[1]
+    assert A.stride(1) == 1 and B.stride(1) == 1
+    M, K = A.shape
+    Nn = B.shape[0]
+    if out is None:
+        out = torch.empty(M, Nn, dtype=torch.float32, device=A.device)
+        beta = 0.0
+    assert out.dtype == torch.float32 and out.stride(1) == 1
+    rc = N.lib().msq_gemm_nt_f32out(N.ptr(A), N.ptr(B), N.ptr(out), M, Nn, K, A.stride(0), B.stride(0), out.stride(0),
+                                    float(alpha), float(beta), _DT[A.dtype], N.stream_ptr(A.device))
+    N.check(rc, "msq_gemm_nt_f32out")
+    return out
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def hessian_accumulate(H, X, alpha, beta, symmetric=True):
+    """H <- beta*H + alpha * X^T X  (X [T, K] tokens x features, fp32/fp16/bf16; H [K, K] fp32)"""
+    N.require_cuda(H, "H")
+    N.require_cuda(X, "X")
+    assert X.dim() == 2 and X.stride(1) == 1 and X.dtype in _DT
+    T, K = X.shape
+    assert H.shape == (K, K) and H.dtype == torch.float32 and H.stride(1) == 1
+    dt = _DT[X.dtype]
+    nbytes = int(N.lib().msq_hessian_workspace_bytes(T, K, dt))
+    ws = _workspace(nbytes, X.device)
+    rc = N.lib().msq_hessian_accumulate(N.ptr(X), T, K, X.stride(0), dt, N.ptr(H), H.stride(0), float(alpha), float(beta),
+                                        N.ptr(ws), nbytes, int(bool(symmetric)), N.stream_ptr(X.device))
+    N.check(rc, "msq_hessian_accumulate")
+    return H

@@ -1,0 +1,218 @@
+// msq_gptq.cu -- the column loop of GPTQ.fasterquant (llm/gptq.py:106-165) on B200.
+//
+// Rows are independent inside a 128-column GPTQ block except for the top-k "prune"
+// (gptq.py:146-153), which is a value no-op whenever the column already holds at least k exact
+// zeros (always the case for int2/int4/fp4 inliers).  k_gptq_block therefore runs the whole
+// block without any cross-row synchronisation and records, per column, the number of zeros and
+// the reference's k; msq_gptq_check_prune verifies zeros >= k afterwards.  If that ever fails the
+// host re-runs the linear through the column-synchronous generic path (llm/gptq.py mirror).
+//
+// One warp owns 32 rows (lane = row): the [32 x 128] tile of W lives in shared memory (stride 129,
+// conflict free), column i is quantized with the same block core as the stand-alone quantizer
+// (BS lanes per MX block, xor-butterfly reductions), and the rank-1 update
+// W1[:, j] -= err * Hinv1[i, j] (gptq.py:159) is applied to the remaining columns of the tile.
+#include "msq_quant_core.cuh"
+#include "msq_api_internal.h"
+
+namespace msq {
+
+constexpr int GB = 128;          // GPTQ block width (blocksize of gptq.py:61)
+constexpr int TS = GB + 1;       // smem row stride
+
+struct GptqParams {
+  const float* W; long long ldw;     // [rows, >= i1+count] current weights
+  float* Q; long long ldq;           // quantized weights out
+  const float* Hinv; long long ldh;  // upper Cholesky factor of H^-1
+  float* Err;                        // [rows, 128] (w - q) / d, zero padded
+  double* loss;                      // sum (w-q)^2 / d^2 / 2
+  int* zeros; int* kcnt;             // per column: #(q == 0), reference's k
+  int* status;
+  int rows, i1, count;
+  QCfg c;
+};
+
+template <int BS>
+__global__ void __launch_bounds__(32) k_gptq_block(const GptqParams P) {
+  extern __shared__ float sm[];
+  float* tile = sm;                 // [32][TS]  W1 -> Q1
+  float* etile = sm + 32 * TS;      // [32][TS]  Err1
+  const int lane = threadIdx.x;
+  const int r0 = blockIdx.x * 32;
+  const int row = r0 + lane;
+  const bool active = row < P.rows;
+  const int count = P.count;
+
+  for (int rr = 0; rr < 32; ++rr) {
+    const bool rv = r0 + rr < P.rows;
+    const float* src = P.W + (long long)(r0 + rr) * P.ldw + P.i1;
+#pragma unroll
+    for (int c = 0; c < GB / 32; ++c) {
+      const int j = lane + 32 * c;
+      tile[rr * TS + j] = (rv && j < count) ? __ldg(src + j) : 0.0f;
+      etile[rr * TS + j] = 0.0f;
+    }
+  }
+  __syncwarp();
+
+  double loss = 0.0;
+  int st = 0;
+  const bool counts_for_k = ((row / BS) % BS) == 0;      // quant.py:66  outlier_pos[::block_size]
+#pragma unroll 1
+  for (int i = 0; i < count; ++i) {
+    const float* hrow = P.Hinv + (long long)(P.i1 + i) * P.ldh + P.i1;
+    const float d = __ldg(hrow + i);
+    const float w = tile[lane * TS + i];
+    float x[1] = {active ? w : 0.0f};
+    uint32_t code[1];
+    const BlockOut bo = core_outlier<1, BS, false, false>(x, code, P.c, nullptr, nullptr);
+    const float q = x[0];
+    st |= bo.st;
+    const unsigned zmask = __ballot_sync(0xffffffffu, active && q == 0.0f);
+    if (lane == 0) atomicAdd(P.zeros + P.i1 + i, __popc(zmask));
+    if (active && counts_for_k && (lane % BS) == 0 && bo.cnt) atomicAdd(P.kcnt + P.i1 + i, bo.cnt);
+    const float diff = __fsub_rn(w, q);
+    const float err = __fdiv_rn(diff, d);
+    if (active) loss += (double)__fdiv_rn(__fmul_rn(diff, diff), __fmul_rn(d, d));
+    tile[lane * TS + i] = q;
+    etile[lane * TS + i] = active ? err : 0.0f;
+#pragma unroll 4
+    for (int j = i + 1; j < count; ++j)
+      tile[lane * TS + j] = __fsub_rn(tile[lane * TS + j], __fmul_rn(err, __ldg(hrow + j)));
+  }
+  __syncwarp();
+
+  for (int rr = 0; rr < 32; ++rr) {
+    if (r0 + rr >= P.rows) break;
+    float* qd = P.Q + (long long)(r0 + rr) * P.ldq + P.i1;
+    float* ed = P.Err + (long long)(r0 + rr) * GB;
+#pragma unroll
+    for (int c = 0; c < GB / 32; ++c) {
+      const int j = lane + 32 * c;
+      if (j < count) qd[j] = tile[rr * TS + j];
+      ed[j] = etile[rr * TS + j];
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+  if (lane == 0) atomicAdd(P.loss, loss * 0.5);
+  st = __reduce_or_sync(0xffffffffu, st);
+  if (lane == 0 && st) atomicOr(P.status, st);
+}
+
+// W[:, i2:] -= Err1 @ Hinv[i1:i2, i2:]   (gptq.py:165), strict fp32 FMA accumulation.
+// 64 x 64 output tile per CTA, 4 x 4 outputs per thread, whole K = 128 staged in shared memory.
+__global__ void __launch_bounds__(256) k_gptq_trailing(float* __restrict__ W, long long ldw, const float* __restrict__ Err,
+                                                       const float* __restrict__ Hinv, long long ldh, int rows, int i1,
+                                                       int count, int i2, int cols) {
+  __shared__ float sA[64][64 + 4];     // Err tile  [m][k-chunk]
+  __shared__ float sB[64][64 + 4];     // Hinv tile [k-chunk][n]
+  const int m0 = blockIdx.y * 64, n0 = i2 + blockIdx.x * 64;
+  const int tid = threadIdx.x;
+  const int tm = (tid / 16) * 4, tn = (tid % 16) * 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < count; k0 += 64) {
+    __syncthreads();
+    for (int idx = tid; idx < 64 * 64; idx += 256) {
+      const int m = idx / 64, k = idx - m * 64;
+      sA[m][k] = (m0 + m < rows && k0 + k < count) ? __ldg(Err + (long long)(m0 + m) * GB + k0 + k) : 0.0f;
+      const int kk = idx / 64, n = idx - kk * 64;
+      sB[kk][n] = (k0 + kk < count && n0 + n < cols) ? __ldg(Hinv + (long long)(i1 + k0 + kk) * ldh + n0 + n) : 0.0f;
+    }
+    __syncthreads();
+    const int kend = min(64, count - k0);
+    for (int k = 0; k < kend; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a[u] = sA[tm + u][k]; b[u] = sB[k][tn + u]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(a[u], b[v], acc[u][v]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int m = m0 + tm + u;
+    if (m >= rows) continue;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int n = n0 + tn + v;
+      if (n < cols) W[(long long)m * ldw + n] -= acc[u][v];
+    }
+  }
+}
+
+__global__ void k_gptq_check(const int* __restrict__ zeros, const int* __restrict__ kcnt, int cols, int* violation) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cols) {
+    const int k = (int)(short)kcnt[i];               // .to(torch.int16), gptq.py:147
+    if (zeros[i] < k) atomicAdd(violation, 1);
+  }
+}
+
+// rank-1 update used by the generic (column-synchronous) path: W1[:, i:] -= err (x) h
+__global__ void __launch_bounds__(256) k_rank1_sub(float* __restrict__ W, long long ldw, const float* __restrict__ err,
+                                                   const float* __restrict__ h, int rows, int n) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= (long long)rows * n) return;
+  const int r = (int)(t / n), j = (int)(t - (long long)r * n);
+  float* p = W + (long long)r * ldw + j;
+  *p = __fsub_rn(*p, __fmul_rn(__ldg(err + r), __ldg(h + j)));
+}
+
+}  // namespace msq
+
+using namespace msq;
+
+extern "C" {
+
+// One 128-column GPTQ block [i1, i1+count) for all rows.  zeros/kcnt are [cols] int32 (caller zeroes
+// them once per linear), loss a device double, Err a [rows,128] fp32 scratch, status OR of MSQ_ST_*.
+int msq_gptq_block(const float* W, long long ldw, float* Q, long long ldq, const float* Hinv, long long ldh, int rows, int i1,
+                   int count, float* Err, double* loss, int* zeros, int* kcnt, int* status, int block_size,
+                   int in_scale_bits, int out_scale_bits, int in_ebits, int in_mbits, int in_emax, float in_max_norm,
+                   int out_ebits, int out_mbits, int out_emax, float out_max_norm, float std_dev, int flush_fp32_subnorms,
+                   int rmode, void* stream) {
+  if (!W || !Q || !Hinv || !Err || !loss || !zeros || !kcnt || !status || rows <= 0 || count <= 0 || count > GB)
+    return MSQ_ERR_BAD_ARG;
+  if (in_ebits > 5 || out_ebits > 5) return MSQ_ERR_UNSUPPORTED;
+  GptqParams P;
+  P.W = W; P.ldw = ldw; P.Q = Q; P.ldq = ldq; P.Hinv = Hinv; P.ldh = ldh; P.Err = Err; P.loss = loss; P.zeros = zeros;
+  P.kcnt = kcnt; P.status = status; P.rows = rows; P.i1 = i1; P.count = count;
+  P.c.fin = make_fmt(in_ebits, in_mbits, in_emax, in_max_norm);
+  P.c.fout = make_fmt(out_ebits, out_mbits, out_emax, out_max_norm);
+  P.c.sb_in = in_scale_bits; P.c.sb_out = out_scale_bits; P.c.std_dev = std_dev; P.c.flush = flush_fp32_subnorms;
+  P.c.variant = 0; P.c.mode = 0; P.c.rmode = rmode;
+  const unsigned grid = (unsigned)((rows + 31) / 32);
+  const size_t smem = 2 * 32 * TS * sizeof(float);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (block_size == 16) k_gptq_block<16><<<grid, 32, smem, s>>>(P);
+  else if (block_size == 32) k_gptq_block<32><<<grid, 32, smem, s>>>(P);
+  else if (block_size == 8) k_gptq_block<8><<<grid, 32, smem, s>>>(P);
+  else return MSQ_ERR_UNSUPPORTED;
+  return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+}
+
+int msq_gptq_trailing_update(float* W, long long ldw, const float* Err, const float* Hinv, long long ldh, int rows, int i1,
+                             int count, int i2, int cols, void* stream) {
+  if (!W || !Err || !Hinv || rows <= 0 || count <= 0 || count > GB) return MSQ_ERR_BAD_ARG;
+  if (i2 >= cols) return MSQ_OK;
+  dim3 grid((unsigned)((cols - i2 + 63) / 64), (unsigned)((rows + 63) / 64));
+  k_gptq_trailing<<<grid, 256, 0, (cudaStream_t)stream>>>(W, ldw, Err, Hinv, ldh, rows, i1, count, i2, cols);
+  return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+}
+
+int msq_gptq_check_prune(const int* zeros, const int* kcnt, int cols, int* violation, void* stream) {
+  if (!zeros || !kcnt || !violation || cols <= 0) return MSQ_ERR_BAD_ARG;
+  k_gptq_check<<<(cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(zeros, kcnt, cols, violation);
+  return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+}
+
+int msq_rank1_sub_f32(float* W, long long ldw, const float* err, const float* h, int rows, int n, void* stream) {
+  if (!W || !err || !h || rows <= 0 || n < 0) return MSQ_ERR_BAD_ARG;
+  if (n == 0) return MSQ_OK;
+  const long long tot = (long long)rows * n;
+  k_rank1_sub<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(W, ldw, err, h, rows, n);
+  return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -141,6 +141,9 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
   }
   if (LPB > 1) bad = grp_or<LPB>(bad);
 
+  // outlier split.  A*(1-mask) / A*mask of quant.py:70-71 are exact products with 0/1, so the
+  // maxima below are the reference's maxima.  ALU-pipe work is kept minimal: 0/1 blending and
+  // exponent arithmetic run on the FMA pipe (FMUL / IMAD).
   uint32_t mask = 0;
   float m_in = 0.0f;
 #pragma unroll
@@ -148,7 +151,7 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
     const float li = EXT ? lo_e[i] : l, hi_i = EXT ? hi_e[i] : h;
     const bool isout = (x[i] < li) | (x[i] > hi_i);
     mask |= (isout ? 1u : 0u) << i;
-    m_in = isout ? m_in : fmaxf(m_in, fabsf(x[i]));
+    m_in = fmaxf(m_in, __fmul_rn(fabsf(x[i]), isout ? 0.0f : 1.0f));
   }
   o.mask = mask;
   o.cnt = grp_add<LPB>(__popc(mask));
@@ -167,7 +170,7 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const float t = fabsf(__fmul_rn(x[i], s_in));
-    m_out = ((mask >> i) & 1u) ? fmaxf(m_out, t) : m_out;
+    m_out = fmaxf(m_out, __fmul_rn(t, ((mask >> i) & 1u) ? 1.0f : 0.0f));
   }
   m_out = grp_max<LPB>(m_out);
   const int E_out = (m_out == 0.0f) ? -126 : floor_log2f(m_out);
@@ -177,22 +180,48 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
   const int e_out = dead ? 0 : o.e_out;
   const float s_out = pow2i(e_out), inv_s_out = pow2i(-e_out);
   const RoundSel rs = make_round(c.rmode);
-  const bool f_in = c.fin.ebits != 0, f_out = c.fout.ebits != 0;
-  const float in_m1 = flush ? 0.0f : 1.0f;
+  const float inv_s_in_eff = flush ? 0.0f : inv_s_in;            // quant.py:80 (x*0 keeps the sign of x)
+
+  // Element rounding with the quantum exponent p clamped in the BIASED domain:
+  //   p' = clamp(biased_exp(v), lo', hi')   (floats: lo' = min_exp+127, hi' = 254; ints: 127, 127)
+  //   y  = v * 2^(mant - p)  ->  round  ->  * 2^(p - mant)
+  // (v * 2^-p) * 2^mant == v * 2^(mant-p) exactly here: |v| <= 2^(emax+1) and every element
+  // format on this path has ebits <= 5, so no intermediate leaves the normal range inexactly.
+  const int mant_i = c.fin.bits - 2, mant_o = c.fout.bits - 2;
+  const int lo_i = c.fin.ebits ? c.fin.min_exp + 127 : 127, hi_i = c.fin.ebits ? 254 : 127;
+  const int lo_o = c.fout.ebits ? c.fout.min_exp + 127 : 127, hi_o = c.fout.ebits ? 254 : 127;
+  const int d_lo = lo_o - lo_i, d_hi = hi_o - hi_i;
+  const int c1_i = (254 + mant_i) << 23, d_c1 = (mant_o - mant_i) << 23;   // s1 = c1 - p'<<23
+  const int c2_i = -(mant_i << 23), d_c2 = -((mant_o - mant_i) << 23);     // s2 = c2 + p'<<23
+  const float mx_i = c.fin.max_norm, mx_o = c.fout.max_norm;
 
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const bool isout = (mask >> i) & 1u;
-    // inlier : v = (x*[flush?0:1]) * 2^-e_in ;  r = (q * 2^e_in) * 1          quant.py:80,92,102
-    // outlier: v = (x*2^e_in) * 2^-e_out      ;  r = (q * 2^e_out) * 2^-e_in   quant.py:94,125,136
-    const float m1 = isout ? s_in : in_m1, m2 = isout ? inv_s_out : inv_s_in;
-    const float d1 = isout ? s_out : s_in, d2 = isout ? inv_s_in : 1.0f;
-    const float v = __fmul_rn(__fmul_rn(x[i], m1), m2);
-    const float qv = qelem_mx_bounded(v, isout ? f_out : f_in, isout ? c.fout.min_exp : c.fin.min_exp,
-                                      isout ? c.fout.up : c.fin.up, isout ? c.fout.down : c.fin.down,
-                                      isout ? c.fout.max_norm : c.fin.max_norm, rs);
+    const int mi = isout ? 1 : 0;
+    // inlier : v = x * 2^-e_in               ; r = q * 2^e_in                  quant.py:92,102
+    // outlier: v = (x * 2^e_in) * 2^-e_out   ; r = (q * 2^e_out) * 2^-e_in     quant.py:94,125,136
+    const float vin = __fmul_rn(x[i], inv_s_in_eff);
+    const float vout = __fmul_rn(__fmul_rn(x[i], s_in), inv_s_out);
+    const float v = isout ? vout : vin;
+    const int be = (__float_as_int(v) >> 23) & 0xFF;
+    const int pb = min(max(be, lo_i + mi * d_lo), hi_i + mi * d_hi);
+    const float s1 = __int_as_float((c1_i + mi * d_c1) - (pb << 23));
+    const float s2 = __int_as_float((c2_i + mi * d_c2) + (pb << 23));
+    const float y = __fmul_rn(v, s1);
+    const float a = fabsf(y);
+    float r = floorf(__fadd_rn(a, rs.addend));
+    if (rs.even) {
+      const float t = __fadd_rn(a, -0.5f);
+      const float hh = __fmul_rn(t, 0.5f);
+      if (t >= 0.0f && hh == floorf(hh)) r = __fadd_rn(r, -1.0f);
+    }
+    const float mx = isout ? mx_o : mx_i;
+    const float qv = fminf(fmaxf(__fmul_rn(copysignf(r, y), s2), -mx), mx);
     if (CODES) code[i] = encode_elem(qv, isout ? c.fout.ebits : c.fin.ebits, isout ? c.fout.bits : c.fin.bits);
-    x[i] = __fadd_rn(__fmul_rn(__fmul_rn(qv, d1), d2), 0.0f);                   // quant.py:140 (x + 0)
+    const float rin = __fmul_rn(qv, s_in);
+    const float rout = __fmul_rn(__fmul_rn(qv, s_out), inv_s_in);
+    x[i] = __fadd_rn(isout ? rout : rin, 0.0f);                                 // quant.py:140 (x + 0)
   }
   if (dead) {      // NaN/Inf input or a shared exponent above the scale range: the reference asserts
 #pragma unroll

@@ -1,0 +1,306 @@
+"""GPTQ solver on B200 -- mirror of the reference's llm/gptq.py (class GPTQ: add_batch,
+fasterquant, free; attributes layer, dev, rows, columns, H, nsamples, quantizer).
+
+add_batch   -> tcgen05 Hessian accumulation (csrc/msq_gemm.cu), optionally batched over calls
+fasterquant -> Cholesky trio through torch.linalg (cuSOLVER), then per 128-column block the fused
+               column-loop kernel + fp32 trailing update (csrc/msq_gptq.cu).  When the fused path's
+               "prune is a no-op" check fails, or for quantizer settings it does not cover, the
+               column-synchronous generic path below reproduces gptq.py:116-160 op by op on the GPU.
+"""
+import ctypes as C
+import math
+import time
+
+import torch
+import torch.nn as nn
+
+try:
+    import transformers
+    _Conv1D = transformers.Conv1D
+except Exception:  # pragma: no cover
+    _Conv1D = ()
+
+from .. import _native as N
+from .. import _ops, _tc
+from ..utils.quant import *  # noqa: F401,F403  (the reference re-exports utils.quant from gptq)
+from ..utils.quant import MXQuantizer, Quantizer, quantize, quantize_mx_outlier_hessian
+
+DEBUG = False
+
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+
+_p, _ll, _i, _f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
+N.register("msq_gptq_block", _i, [_p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i,
+                                  _i, _i, _i, _f, _i, _i, _i, _f, _f, _i, _i, _p])
+N.register("msq_gptq_trailing_update", _i, [_p, _ll, _p, _p, _ll, _i, _i, _i, _i, _i, _p])
+N.register("msq_gptq_check_prune", _i, [_p, _p, _i, _p, _p])
+N.register("msq_rank1_sub_f32", _i, [_p, _ll, _p, _p, _i, _i, _p])
+
+
+class GPTQ:
+
+    #: number of add_batch calls whose activations are buffered before one Hessian GEMM
+    #: (1 = accumulate immediately, exactly like gptq.py:53-58)
+    hessian_batch = 1
+    #: print 'time' / 'error' like the reference (gptq.py:174-175)
+    verbose = True
+
+    def __init__(self, layer):
+        self.layer = layer
+        self.dev = self.layer.weight.device
+        W = layer.weight.data.clone()
+        if isinstance(self.layer, nn.Conv2d):
+            W = W.flatten(1)
+        if isinstance(self.layer, _Conv1D):
+            W = W.t()
+        self.rows = W.shape[0]
+        self.columns = W.shape[1]
+        self._H = torch.zeros((self.columns, self.columns), device=self.dev)
+        self.nsamples = 0
+        self._pending = []
+        self._pending_n = 0
+        self.last_path = None
+        self.last_error = None
+
+    # -- Hessian ---------------------------------------------------------------------------
+    @property
+    def H(self):
+        self._flush()
+        return self._H
+
+    @H.setter
+    def H(self, value):
+        self._pending, self._pending_n = [], 0
+        self._H = value
+
+    @H.deleter
+    def H(self):
+        self._pending, self._pending_n = [], 0
+        self._H = None
+
+    def add_batch(self, inp, out):
+        if DEBUG:
+            self.inp1 = inp
+            self.out1 = out
+        if len(inp.shape) == 2:
+            inp = inp.unsqueeze(0)
+        b = inp.shape[0]
+        if isinstance(self.layer, nn.Linear) or isinstance(self.layer, _Conv1D):
+            if len(inp.shape) == 3:
+                inp = inp.reshape((-1, inp.shape[-1]))
+            x = inp                                   # [tokens, features]; the reference transposes (gptq.py:42)
+        elif isinstance(self.layer, nn.Conv2d):
+            unfold = nn.Unfold(self.layer.kernel_size, dilation=self.layer.dilation, padding=self.layer.padding,
+                               stride=self.layer.stride)
+            x = unfold(inp).permute([1, 0, 2]).flatten(1).t()
+        else:
+            raise TypeError("unsupported layer type %s" % type(self.layer))
+        N.require_cuda(x, "inp")
+        if x.dtype not in (torch.float16, torch.bfloat16, torch.float32):
+            x = x.float()
+        self._pending.append((x.detach().contiguous(), b))
+        self._pending_n += 1
+        if self._pending_n >= self.hessian_batch:
+            self._flush()
+
+    def _flush(self):
+        """H <- H * n/(n+b) + (2/(n+b)) X^T X   (gptq.py:53-58) for the buffered calls"""
+        if not self._pending:
+            return
+        xs = [x for x, _ in self._pending]
+        b = sum(bb for _, bb in self._pending)
+        X = xs[0] if len(xs) == 1 else torch.cat(xs, 0)
+        n_new = self.nsamples + b
+        _tc.hessian_accumulate(self._H, X, alpha=2.0 / n_new, beta=self.nsamples / n_new)
+        self.nsamples = n_new
+        self._pending, self._pending_n = [], 0
+
+    # -- solver ----------------------------------------------------------------------------
+    def _fused_ok(self):
+        q = self.quantizer
+        if not isinstance(q, MXQuantizer) or q.inlier_elem_format is None:
+            return False
+        axes = q.axes if isinstance(q.axes, (list, tuple)) else [q.axes]
+        if list(axes) not in ([0], [-2]) or q.block_size not in (8, 16, 32):
+            return False
+        if q.shared_exp_method != "max" or q.round not in ("nearest", "floor", "even"):
+            return False
+        return _ops.fmt4(q.inlier_elem_format)[0] <= 5 and _ops.fmt4(q.outlier_elem_format)[0] <= 5
+
+    def fasterquant(self, blocksize=128, percdamp=.01, groupsize=-1, actorder=False, static_groups=False):
+        W = self.layer.weight.data.clone()
+        if isinstance(self.layer, nn.Conv2d):
+            W = W.flatten(1)
+        if isinstance(self.layer, _Conv1D):
+            W = W.t()
+        W = W.float().contiguous()
+        N.require_cuda(W, "layer.weight")
+
+        tick = time.time()
+
+        if not self.quantizer.ready():
+            self.quantizer.find_params(W, weight=True)
+
+        H = self.H
+        del self.H
+        dead = torch.diag(H) == 0
+        H[dead, dead] = 1
+        W[:, dead] = 0
+
+        groups = None
+        if static_groups:
+            import copy
+            groups = []
+            for i in range(0, self.columns, groupsize):
+                quantizer = copy.deepcopy(self.quantizer)
+                quantizer.find_params(W[:, i:(i + groupsize)], weight=True)
+                groups.append(quantizer)
+
+        perm = invperm = None
+        if actorder:
+            perm = torch.argsort(torch.diag(H), descending=True)
+            W = W[:, perm].contiguous()
+            H = H[perm][:, perm]
+            invperm = torch.argsort(perm)
+
+        damp = percdamp * torch.mean(torch.diag(H))
+        diag = torch.arange(self.columns, device=self.dev)
+        H[diag, diag] += damp
+        H = torch.linalg.cholesky(H)
+        H = torch.cholesky_inverse(H)
+        H = torch.linalg.cholesky(H, upper=True)
+        Hinv = H.contiguous()
+
+        Q = None
+        if self._fused_ok() and blocksize == 128:
+            Q, loss = self._solve_fused(W.clone(), Hinv)
+            self.last_path = "fused"
+        if Q is None:
+            Q, loss = self._solve_generic(W, Hinv, blocksize, groupsize, actorder, static_groups, groups, perm)
+            self.last_path = "generic"
+
+        torch.cuda.synchronize()
+        self.last_error = loss
+        if self.verbose:
+            print('time %.2f' % (time.time() - tick))
+            print('error', loss)
+
+        if actorder:
+            Q = Q[:, invperm]
+        if isinstance(self.layer, _Conv1D):
+            Q = Q.t()
+        self.layer.weight.data = Q.reshape(self.layer.weight.shape).to(self.layer.weight.data.dtype)
+        if DEBUG:
+            print(torch.sum((self.layer(self.inp1) - self.out1) ** 2))
+
+    def _solve_fused(self, W, Hinv):
+        """gptq.py:106-165 with the per-block kernel; returns (Q, loss) or (None, None) when the
+        prune would have changed values (then the generic path must run)."""
+        q = self.quantizer
+        dev = W.device
+        rows, cols = W.shape
+        fi, fo = _ops.fmt4(q.inlier_elem_format), _ops.fmt4(q.outlier_elem_format)
+        Q = torch.empty_like(W)
+        Err = torch.empty(rows, 128, dtype=torch.float32, device=dev)
+        loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        counters = torch.zeros(2 * cols + 2, dtype=torch.int32, device=dev)
+        zeros, kcnt, status, viol = counters[:cols], counters[cols:2 * cols], counters[2 * cols:2 * cols + 1], counters[2 * cols + 1:]
+        L, s = N.lib(), N.stream_ptr(dev)
+        rm = _ops._rmode(q.round)
+        for i1 in range(0, cols, 128):
+            i2 = min(i1 + 128, cols)
+            rc = L.msq_gptq_block(N.ptr(W), W.stride(0), N.ptr(Q), Q.stride(0), N.ptr(Hinv), Hinv.stride(0), rows, i1,
+                                  i2 - i1, N.ptr(Err), N.ptr(loss), N.ptr(zeros), N.ptr(kcnt), N.ptr(status),
+                                  int(q.block_size), int(q.inlier_scale_bits), int(q.outlier_scale_bits),
+                                  fi[0], fi[1], fi[2], fi[3], fo[0], fo[1], fo[2], fo[3], float(q.std_dev),
+                                  int(bool(q.flush_fp32_subnorms)), rm, s)
+            N.check(rc, "msq_gptq_block")
+            rc = L.msq_gptq_trailing_update(N.ptr(W), W.stride(0), N.ptr(Err), N.ptr(Hinv), Hinv.stride(0), rows, i1,
+                                            i2 - i1, i2, cols, s)
+            N.check(rc, "msq_gptq_trailing_update")
+        rc = L.msq_gptq_check_prune(N.ptr(zeros), N.ptr(kcnt), cols, N.ptr(viol), s)
+        N.check(rc, "msq_gptq_check_prune")
+        flags = counters[2 * cols:].tolist()          # one host sync per linear
+        _ops.raise_on_status(flags[0])
+        if flags[1] != 0:
+            return None, None
+        return Q, float(loss.item())
+
+    def _solve_generic(self, W, Hinv, blocksize, groupsize, actorder, static_groups, groups, perm):
+        """column-synchronous path: gptq.py:106-165 statement by statement, on the GPU"""
+        Q = torch.zeros_like(W)
+        loss = torch.zeros((), dtype=torch.float64, device=W.device)
+        L, s = N.lib(), N.stream_ptr(W.device)
+        for i1 in range(0, self.columns, blocksize):
+            i2 = min(i1 + blocksize, self.columns)
+            count = i2 - i1
+            W1 = W[:, i1:i2].clone()
+            Q1 = torch.zeros_like(W1)
+            Err1 = torch.zeros_like(W1)
+            Losses1 = torch.zeros_like(W1)
+            Hinv1 = Hinv[i1:i2, i1:i2].contiguous()
+            for i in range(count):
+                w = W1[:, i]
+                d = Hinv1[i, i]
+                if groupsize != -1:
+                    if not static_groups:
+                        if (i1 + i) % groupsize == 0:
+                            self.quantizer.find_params(W[:, (i1 + i):(i1 + i + groupsize)], weight=True)
+                    else:
+                        idx = i1 + i
+                        if actorder:
+                            idx = perm[idx]
+                        self.quantizer = groups[idx // groupsize]
+                qz = self.quantizer
+                if isinstance(qz, MXQuantizer):
+                    res = quantize_mx_outlier_hessian(w.unsqueeze(1).contiguous(), qz.inlier_scale_bits,
+                                                      qz.outlier_scale_bits, qz.inlier_elem_format,
+                                                      qz.outlier_elem_format, qz.shared_exp_method, qz.std_dev, qz.axes,
+                                                      qz.block_size, qz.round, qz.flush_fp32_subnorms, qz.custom_cuda)
+                    if isinstance(res, tuple):
+                        q, num_outliers_per_block = res
+                        q = q.flatten()
+                        importance = (q ** 2) / d ** 2
+                        num_outliers = int(num_outliers_per_block.sum().to(torch.int16))
+                        if num_outliers > 0:
+                            least = torch.topk(importance, num_outliers, largest=False).indices
+                            q[least] = 0
+                    else:
+                        q = res.flatten()
+                else:   # plain GPTQ quantizer (upstream GPTQ behaviour; the reference's fork cannot reach it)
+                    q = quantize(w.unsqueeze(1), qz.scale, qz.zero, qz.maxq).flatten()
+                Q1[:, i] = q
+                Losses1[:, i] = (w - q) ** 2 / d ** 2
+                err1 = ((w - q) / d).contiguous()
+                rc = L.msq_rank1_sub_f32(N.ptr(W1[:, i:]), W1.stride(0), N.ptr(err1), N.ptr(Hinv1[i, i:]), self.rows,
+                                         count - i, s)
+                N.check(rc, "msq_rank1_sub_f32")
+                Err1[:, i] = err1
+            Q[:, i1:i2] = Q1
+            loss += (Losses1 / 2).double().sum()
+            if i2 < self.columns:
+                E = torch.zeros(self.rows, 128, dtype=torch.float32, device=W.device) if count <= 128 else None
+                if E is not None:
+                    E[:, :count] = Err1
+                    rc = L.msq_gptq_trailing_update(N.ptr(W), W.stride(0), N.ptr(E), N.ptr(Hinv), Hinv.stride(0),
+                                                    self.rows, i1, count, i2, self.columns, s)
+                    N.check(rc, "msq_gptq_trailing_update")
+                else:   # blocksize > 128: chunk the K dimension of the update
+                    for c0 in range(0, count, 128):
+                        c1 = min(c0 + 128, count)
+                        E = torch.zeros(self.rows, 128, dtype=torch.float32, device=W.device)
+                        E[:, :c1 - c0] = Err1[:, c0:c1]
+                        rc = L.msq_gptq_trailing_update(N.ptr(W), W.stride(0), N.ptr(E), N.ptr(Hinv), Hinv.stride(0),
+                                                        self.rows, i1 + c0, c1 - c0, i2, self.columns, s)
+                        N.check(rc, "msq_gptq_trailing_update")
+        return Q, float(loss.item())
+
+    def free(self):
+        if DEBUG:
+            self.inp1 = None
+            self.out1 = None
+        self.H = None
+        self.Losses = None
+        self.Trace = None
+        torch.cuda.empty_cache()
