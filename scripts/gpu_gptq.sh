@@ -1,6 +1,7 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_gptq.py tests/test_gpu_gemm.py -x -q 2>&1 | tail -25
+timeout 900 python -m pytest tests/test_gpu_gptq.py tests/test_gpu_gemm.py -x -q 2>&1 | tail -12
+exit 0
 timeout 600 python - <<'PY'
 import torch, time, sys
 sys.path.insert(0, '.')
