@@ -1,0 +1,200 @@
+// msq_pack.cu -- dequantize ("unpack") the packed MicroScopiQ planes produced by the PACK variants of
+// the quantizer kernels (csrc/msq_quant_strided.cu, msq_quant_inner.cu).  Layout: DESIGN.md "packed layout".
+//   codes   : one inlier-width slot per element, linear element order
+//   bitmap  : 1 bit per element (set = outlier), 32-bit little-endian words
+//   e_in/e_out : int8 shared exponents per block, block-linear order (MSQ_EXP_NAN = NaN scale)
+//   hi      : per segment (MSQ_SEG_BLOCKS blocks) the high bits of the outlier codes, compacted in
+//             block-major order, hi_w bits each, starting at seg * hi_seg_stride
+// unpack(pack(W)) reproduces the reference's dequantized tensor bit for bit (tests/test_gpu_pack.py).
+#include "msq_quant_kernels.cuh"
+
+namespace msq {
+
+struct UParams {
+  long long pre, post, nblocks;
+  int L, bs, nblk;
+  Fmt fin, fout;
+  const uint8_t* codes; const int8_t* e_in; const int8_t* e_out; const uint32_t* bitmap; const uint8_t* hi;
+  long long hi_seg_stride; int hi_w;
+  float* out_f32; __nv_bfloat16* out_bf16;
+  int plain;          // 1: plain MX (no bitmap / outliers)
+};
+
+__device__ __forceinline__ float dq_elem(uint32_t code, bool isout, const UParams& P, float s_in, float inv_s_in, float s_out,
+                                         bool nan_blk) {
+  float q = isout ? decode_elem(code, P.fout.ebits, P.fout.bits) : decode_elem(code, P.fin.ebits, P.fin.bits);
+  float r = isout ? __fmul_rn(__fmul_rn(q, s_out), inv_s_in) : __fmul_rn(q, s_in);
+  r = __fadd_rn(r, 0.0f);
+  return nan_blk ? qnan() : r;
+}
+
+__device__ __forceinline__ uint32_t hi_field(const uint32_t* s_hi, int k, int hw) {
+  const int bit = k * hw;
+  return (s_hi[bit >> 5] >> (bit & 31)) & ((1u << hw) - 1u);
+}
+
+// strided layout: thread = block (column), 256 consecutive block-linear indices per sub-iteration
+__global__ void __launch_bounds__(256) k_unpack_strided(const UParams P) {
+  extern __shared__ uint32_t s_hi[];
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const long long seg = blockIdx.x;
+  const bool has_hi = !P.plain && P.hi_w > 0;
+  const int wi = P.fin.width;
+  const int lane = threadIdx.x & 31;
+  const int post = (int)P.post;
+  if (has_hi) {
+    const int words = (int)(P.hi_seg_stride >> 2);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.hi + seg * P.hi_seg_stride);
+    for (int i = threadIdx.x; i < words; i += 256) s_hi[i] = __ldg(src + i);
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+  }
+  for (int sub = 0; sub < MSQ_SEG_BLOCKS / 256; ++sub) {
+    const long long t0 = seg * MSQ_SEG_BLOCKS + (long long)sub * 256 + threadIdx.x;
+    const bool active = t0 < P.nblocks;
+    int base = 0, b = 0;
+    if (active) {
+      const int pb = (int)(t0 / post);
+      const int j = (int)(t0 - (long long)pb * post);
+      const int p = pb / P.nblk; b = pb - p * P.nblk;
+      base = (p * P.L + b * P.bs) * post + j;
+    }
+    const int nv = active ? min(P.bs, P.L - b * P.bs) : 0;
+    // outlier mask of this block: one bitmap word per row, shared by the warp (post % 32 == 0)
+    uint32_t mask = 0;
+    if (!P.plain) {
+      for (int i = 0; i < nv; ++i) {
+        const uint32_t w = __ldg(P.bitmap + ((base + i * post) >> 5));
+        mask |= ((w >> lane) & 1u) << i;
+      }
+    }
+    int k = 0;
+    if (has_hi) {
+      int tot;
+      const int off = cta_excl_scan(__popc(mask), s_warp, &tot);
+      k = s_base + off;
+      __syncthreads();
+      if (threadIdx.x == 0) s_base += tot;
+      __syncthreads();
+    }
+    if (!active) continue;
+    const int ei = P.e_in[t0], eo = P.plain ? 0 : P.e_out[t0];
+    const bool nan_blk = ei == MSQ_EXP_NAN || eo == MSQ_EXP_NAN;
+    const float s_in = pow2i(nan_blk ? 0 : ei), inv_s_in = pow2i(nan_blk ? 0 : -ei), s_out = pow2i(nan_blk ? 0 : eo);
+    for (int i = 0; i < nv; ++i) {
+      const int lin = base + i * post;
+      const long long bit = (long long)lin * wi;
+      uint32_t code = (P.codes[bit >> 3] >> (bit & 7)) & ((1u << wi) - 1u);
+      const bool isout = (mask >> i) & 1u;
+      if (isout && has_hi) { code |= hi_field(s_hi, k, P.hi_w) << wi; ++k; }
+      const float r = dq_elem(code, isout, P, s_in, inv_s_in, s_out, nan_blk);
+      if (P.out_f32) P.out_f32[lin] = r;
+      if (P.out_bf16) P.out_bf16[lin] = __float2bfloat16_rn(r);
+    }
+  }
+}
+
+// innermost layout: thread = 4 consecutive elements, bs/4 lanes per block
+__global__ void __launch_bounds__(256) k_unpack_inner(const UParams P) {
+  extern __shared__ uint32_t s_hi[];
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const long long seg = blockIdx.x;
+  const bool has_hi = !P.plain && P.hi_w > 0;
+  const int wi = P.fin.width;
+  const int BS = P.bs;
+  if (has_hi) {
+    const int words = (int)(P.hi_seg_stride >> 2);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.hi + seg * P.hi_seg_stride);
+    for (int i = threadIdx.x; i < words; i += 256) s_hi[i] = __ldg(src + i);
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+  }
+  const long long nelem = P.nblocks * BS;
+  const long long seg_e0 = seg * MSQ_SEG_BLOCKS * BS;
+  for (int it = 0; it < BS; ++it) {
+    const long long e0 = seg_e0 + (long long)it * 1024 + threadIdx.x * 4;
+    const bool active = e0 < nelem;
+    uint32_t nib = 0;
+    if (active && !P.plain) nib = (__ldg(P.bitmap + (e0 >> 5)) >> (e0 & 31)) & 15u;
+    int k = 0;
+    if (has_hi) {
+      int tot;
+      const int off = cta_excl_scan(__popc(nib), s_warp, &tot);
+      k = s_base + off;
+      __syncthreads();
+      if (threadIdx.x == 0) s_base += tot;
+      __syncthreads();
+    }
+    if (!active) continue;
+    const long long t = e0 / BS;
+    const int ei = P.e_in[t], eo = P.plain ? 0 : P.e_out[t];
+    const bool nan_blk = ei == MSQ_EXP_NAN || eo == MSQ_EXP_NAN;
+    const float s_in = pow2i(nan_blk ? 0 : ei), inv_s_in = pow2i(nan_blk ? 0 : -ei), s_out = pow2i(nan_blk ? 0 : eo);
+    const long long bit0 = e0 * wi;
+    uint32_t cw;
+    if (wi == 2) cw = P.codes[bit0 >> 3];
+    else if (wi == 4) cw = *reinterpret_cast<const uint16_t*>(P.codes + (bit0 >> 3));
+    else cw = *reinterpret_cast<const uint32_t*>(P.codes + (bit0 >> 3));
+    float r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t code = (cw >> (i * wi)) & ((1u << wi) - 1u);
+      const bool isout = (nib >> i) & 1u;
+      if (isout && has_hi) { code |= hi_field(s_hi, k, P.hi_w) << wi; ++k; }
+      r[i] = dq_elem(code, isout, P, s_in, inv_s_in, s_out, nan_blk);
+    }
+    if (P.out_f32) *reinterpret_cast<float4*>(P.out_f32 + e0) = make_float4(r[0], r[1], r[2], r[3]);
+    if (P.out_bf16) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(r[0], r[1]), b2 = __floats2bfloat162_rn(r[2], r[3]);
+      uint2 v;
+      v.x = *reinterpret_cast<uint32_t*>(&a); v.y = *reinterpret_cast<uint32_t*>(&b2);
+      *reinterpret_cast<uint2*>(P.out_bf16 + e0) = v;
+    }
+  }
+}
+
+}  // namespace msq
+
+using namespace msq;
+
+extern "C" {
+
+// Inverse of the PACK outputs of msq_quantize_mx_outlier_f32 / msq_quantize_mx_f32 (plain != 0: no
+// bitmap / e_out / hi).  Exactly one or both of out_f32 / out_bf16 may be given.
+int msq_unpack_mx(const unsigned char* codes, const signed char* e_in, const signed char* e_out, const unsigned int* bitmap,
+                  const unsigned char* hi, float* out_f32, void* out_bf16, long long pre, long long L, long long post,
+                  int block_size, int in_ebits, int in_mbits, int in_emax, float in_max_norm, int out_ebits, int out_mbits,
+                  int out_emax, float out_max_norm, int plain, void* stream) {
+  if (!codes || !e_in || (!out_f32 && !out_bf16) || pre <= 0 || L <= 0 || post <= 0 || block_size <= 0) return MSQ_ERR_BAD_ARG;
+  if (!plain && (!bitmap || !e_out)) return MSQ_ERR_BAD_ARG;
+  if (pre * L * post >= 0x7fffffffLL) return MSQ_ERR_UNSUPPORTED;
+  UParams P;
+  memset(&P, 0, sizeof(P));
+  P.pre = pre; P.L = (int)L; P.post = post; P.bs = block_size;
+  P.nblk = (int)((L + block_size - 1) / block_size);
+  P.nblocks = pre * P.nblk * post;
+  P.fin = make_fmt(in_ebits, in_mbits, in_emax, in_max_norm);
+  P.fout = plain ? P.fin : make_fmt(out_ebits, out_mbits, out_emax, out_max_norm);
+  P.codes = codes; P.e_in = e_in; P.e_out = e_out; P.bitmap = bitmap; P.hi = hi; P.plain = plain;
+  P.hi_w = plain ? 0 : msq_packed_hi_width(in_ebits, in_mbits, out_ebits, out_mbits);
+  if (P.hi_w > 0 && !hi) return MSQ_ERR_BAD_ARG;
+  P.hi_seg_stride = msq_packed_hi_seg_stride(block_size, P.hi_w);
+  P.out_f32 = out_f32; P.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  const long long nseg = (P.nblocks + MSQ_SEG_BLOCKS - 1) / MSQ_SEG_BLOCKS;
+  const size_t smem = P.hi_w > 0 ? (size_t)P.hi_seg_stride : 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (post == 1 && L % block_size == 0 && block_size % 4 == 0) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_unpack_inner, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_unpack_inner<<<(unsigned)nseg, 256, smem, s>>>(P);
+  } else if (post > 1 && post % 32 == 0 && block_size <= 32) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_unpack_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_unpack_strided<<<(unsigned)nseg, 256, smem, s>>>(P);
+  } else {
+    return MSQ_ERR_UNSUPPORTED;
+  }
+  return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+}
+
+}  // extern "C"

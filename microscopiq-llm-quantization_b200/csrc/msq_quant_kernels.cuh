@@ -7,6 +7,11 @@
 #include "msq_quant_core.cuh"
 #include "msq_api_internal.h"
 
+extern "C" {
+int msq_packed_hi_width(int in_ebits, int in_mbits, int out_ebits, int out_mbits);
+long long msq_packed_hi_seg_stride(int block_size, int hi_w);
+}
+
 namespace msq {
 
 struct QParams {

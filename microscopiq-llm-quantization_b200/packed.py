@@ -1,0 +1,136 @@
+"""Packed MicroScopiQ weights: the artefact the reference never materialises.
+
+    p = pack_mx_outlier(W, 8, 8, "fp4_e2m1", "fp8_e4m3", axes=[0], block_size=16)
+    W_hat = p.dequantize()            # == quantize_mx_outlier_v1(W, ...) bit for bit
+
+Planes (all CUDA tensors, layout in DESIGN.md):
+  codes   uint8   inlier-width slot per element (2/4/8 bits), linear element order
+  bitmap  int32   1 bit per element, set = outlier
+  e_in    int8    inlier shared exponent per block  (-128 = NaN scale)
+  e_out   int8    outlier shared exponent per block
+  hi      uint8   per 1024-block segment, compacted high bits of the outlier codes (when wider)
+  seg_cnt int32   outliers per segment
+"""
+import ctypes as C
+
+import torch
+
+from . import _native as N
+from . import _ops
+
+_p, _ll, _i, _f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
+N.register("msq_unpack_mx", _i, [_p, _p, _p, _p, _p, _p, _p, _ll, _ll, _ll, _i, _i, _i, _i, _f, _i, _i, _i, _f, _i, _p])
+
+
+class PackedMX(object):
+    """container for the packed planes + the metadata needed to decode them"""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    @property
+    def nbytes(self):
+        """bytes a consumer has to read: hi counts only the compacted prefix of every segment"""
+        n = self.codes.numel() + self.e_in.numel()
+        if not self.plain:
+            n += self.bitmap.numel() * 4 + self.e_out.numel()
+            if self.hi is not None:
+                n += (int(self.seg_cnt.sum().item()) * self.hi_w + 7) // 8
+        return n
+
+    def outlier_mask(self):
+        """bool tensor of the original shape (decoded from the bitmap)"""
+        words = self.bitmap.view(torch.int32)
+        bits = (words.unsqueeze(-1) >> torch.arange(32, device=words.device, dtype=torch.int32)) & 1
+        n = 1
+        for s in self.shape:
+            n *= s
+        return bits.reshape(-1)[:n].reshape(self.shape).bool()
+
+    def dequantize(self, dtype=torch.float32):
+        pre, L, post = _ops.geometry(self.shape, self.axis)
+        fi = _ops.fmt4(self.in_fmt)
+        fo = _ops.fmt4(self.out_fmt if not self.plain else self.in_fmt)
+        dev = self.codes.device
+        out32 = torch.empty(self.shape, dtype=torch.float32, device=dev) if dtype == torch.float32 else None
+        out16 = torch.empty(self.shape, dtype=torch.bfloat16, device=dev) if dtype == torch.bfloat16 else None
+        if out32 is None and out16 is None:
+            raise TypeError("dequantize to float32 or bfloat16")
+        rc = N.lib().msq_unpack_mx(N.ptr(self.codes), N.ptr(self.e_in), N.ptr(self.e_out), N.ptr(self.bitmap),
+                                   N.ptr(self.hi), N.ptr(out32), N.ptr(out16), pre, L, post, self.block_size,
+                                   fi[0], fi[1], fi[2], fi[3], fo[0], fo[1], fo[2], fo[3], int(self.plain),
+                                   N.stream_ptr(dev))
+        N.check(rc, "msq_unpack_mx")
+        return out32 if out32 is not None else out16
+
+
+def _alloc_planes(x, pre, L, post, bs, fi, fo, plain):
+    L_ = N.lib()
+    dev = x.device
+    nblk = (L + bs - 1) // bs
+    nb = pre * nblk * post
+    n = x.numel()
+    wi = L_.msq_packed_code_width(fi[0], fi[1])
+    hi_w = 0 if plain else L_.msq_packed_hi_width(fi[0], fi[1], fo[0], fo[1])
+    nseg = (nb + L_.msq_seg_blocks() - 1) // L_.msq_seg_blocks()
+    stride = int(L_.msq_packed_hi_seg_stride(bs, hi_w))
+    planes = dict(
+        codes=torch.empty((n * wi + 7) // 8 + 16, dtype=torch.uint8, device=dev)[: (n * wi + 7) // 8],
+        e_in=torch.empty(nb, dtype=torch.int8, device=dev),
+        e_out=None if plain else torch.empty(nb, dtype=torch.int8, device=dev),
+        bitmap=None if plain else torch.zeros((n + 31) // 32, dtype=torch.int32, device=dev),
+        hi=torch.empty(max(nseg * stride, 16), dtype=torch.uint8, device=dev) if hi_w > 0 else None,
+        seg_cnt=None if plain else torch.zeros(nseg, dtype=torch.int32, device=dev),
+    )
+    return planes, wi, hi_w, stride, nseg
+
+
+def pack_mx_outlier(A, inlier_scale_bits, outlier_scale_bits, inlier_elem_format, outlier_elem_format, std_dev=2,
+                    axes=None, block_size=16, round="nearest", flush_fp32_subnorms=False, variant=0, want_deq=False,
+                    check=True):
+    """quantize + pack in one pass (msq_quantize_mx_outlier_f32 with the packed outputs)."""
+    x = _ops._as_f32(A)
+    axis = _ops._single_axis(axes, x.ndim)
+    pre, L, post = _ops.geometry(x.shape, axis)
+    bs = int(block_size)
+    fi, fo = _ops.fmt4(inlier_elem_format), _ops.fmt4(outlier_elem_format)
+    pl, wi, hi_w, stride, nseg = _alloc_planes(x, pre, L, post, bs, fi, fo, False)
+    deq = torch.empty_like(x) if want_deq else None
+    st = torch.zeros(1, dtype=torch.int32, device=x.device)
+    lo = hi = None
+    if variant == 1:
+        lo, hi = _ops.across_block_bounds(x, axis, bs, std_dev)
+    path = C.c_int(0)
+    rc = N.lib().msq_quantize_mx_outlier_f32(
+        N.ptr(x), N.ptr(deq), pre, L, post, bs, int(inlier_scale_bits), int(outlier_scale_bits),
+        fi[0], fi[1], fi[2], fi[3], fo[0], fo[1], fo[2], fo[3], float(std_dev), int(bool(flush_fp32_subnorms)),
+        _ops._rmode(round), int(variant), N.ptr(lo), N.ptr(hi),
+        N.ptr(pl["codes"]), N.ptr(pl["e_in"]), N.ptr(pl["e_out"]), N.ptr(pl["bitmap"]), N.ptr(pl["hi"]),
+        N.ptr(pl["seg_cnt"]), None, None, N.ptr(st), C.byref(path), N.stream_ptr(x.device))
+    N.check(rc, "msq_quantize_mx_outlier_f32(pack)")
+    if check:
+        _ops.raise_on_status(int(st.item()))
+    p = PackedMX(shape=tuple(x.shape), axis=axis, block_size=bs, in_fmt=inlier_elem_format, out_fmt=outlier_elem_format,
+                 in_scale_bits=inlier_scale_bits, out_scale_bits=outlier_scale_bits, code_width=wi, hi_w=hi_w,
+                 hi_seg_stride=stride, nseg=nseg, plain=False, path=path.value, status=st, **pl)
+    return (p, deq) if want_deq else p
+
+
+def pack_mx(A, scale_bits, elem_format, axes=None, block_size=32, round="nearest", flush_fp32_subnorms=False, mode=1):
+    """plain MX quantize + pack (codes + shared exponents); mode 1 = spec arithmetic (exact 2^e divisor)."""
+    x = _ops._as_f32(A)
+    axis = _ops._single_axis(axes, x.ndim)
+    pre, L, post = _ops.geometry(x.shape, axis)
+    bs = int(block_size)
+    f = _ops.fmt4(elem_format)
+    pl, wi, _, _, nseg = _alloc_planes(x, pre, L, post, bs, f, f, True)
+    st = torch.zeros(1, dtype=torch.int32, device=x.device)
+    path = C.c_int(0)
+    rc = N.lib().msq_quantize_mx_f32(N.ptr(x), None, pre, L, post, bs, int(scale_bits), f[0], f[1], f[2], f[3],
+                                     int(bool(flush_fp32_subnorms)), _ops._rmode(round), int(mode), None,
+                                     N.ptr(pl["codes"]), N.ptr(pl["e_in"]), N.ptr(st), C.byref(path),
+                                     N.stream_ptr(x.device))
+    N.check(rc, "msq_quantize_mx_f32(pack)")
+    return PackedMX(shape=tuple(x.shape), axis=axis, block_size=bs, in_fmt=elem_format, out_fmt=elem_format,
+                    in_scale_bits=scale_bits, out_scale_bits=scale_bits, code_width=wi, hi_w=0, hi_seg_stride=0,
+                    nseg=nseg, plain=True, path=path.value, status=st, **pl)

@@ -1,0 +1,125 @@
+"""GPU tier: quantize+pack and unpack.  Packed planes decode (in pure torch, following the layout
+written in DESIGN.md) to exactly the oracle's mask / exponents / element codes, and the CUDA unpack
+kernel reproduces the reference's dequantized tensor bit for bit."""
+import pytest
+import torch
+
+import msq_oracle as O
+from util import assert_exact
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def M():
+    import msq_b200
+    return msq_b200
+
+
+def weights(rows, cols, seed):
+    g = torch.Generator().manual_seed(seed)
+    W = torch.randn(rows, cols, generator=g) * 0.02
+    idx = torch.randperm(W.numel(), generator=g)[: max(1, W.numel() // 1000)]
+    W.view(-1)[idx] *= 20
+    return W
+
+
+def decode_planes(p, M):
+    """reference decoder of the packed layout, written from the spec (slow, torch on CPU)"""
+    n = 1
+    for s in p.shape:
+        n *= s
+    wi = p.code_width
+    raw = p.codes.cpu().to(torch.int64)
+    bits = ((raw.unsqueeze(-1) >> torch.arange(8)) & 1).reshape(-1)[: n * wi].reshape(n, wi)
+    slot = (bits << torch.arange(wi)).sum(-1)
+    mask = p.outlier_mask().cpu().reshape(-1)
+    code = slot.clone()
+    if p.hi_w:
+        pre, L, post = M._ops.geometry(p.shape, p.axis)
+        bs = p.block_size
+        nblk = (L + bs - 1) // bs
+        lin = torch.arange(n).reshape(pre, L, post)
+        hi_raw = p.hi.cpu().to(torch.int64)
+        segb = M._native.lib().msq_seg_blocks()
+        seg_cnt = p.seg_cnt.cpu()
+        # block-major order inside every segment
+        order = []
+        for pb in range(pre * nblk):
+            pp, b = divmod(pb, nblk)
+            rows = lin[pp, b * bs:(b + 1) * bs, :]          # [<=bs, post]
+            order.append(rows.t())                           # [post, <=bs]: block j, then position i
+        blocks = [blk for o in order for blk in o]           # block-linear order
+        for s in range(p.nseg):
+            k = 0
+            base_bit = s * p.hi_seg_stride * 8
+            for blk in blocks[s * segb:(s + 1) * segb]:
+                for e in blk.tolist():
+                    if mask[e]:
+                        bit = base_bit + k * p.hi_w
+                        v = 0
+                        for t in range(p.hi_w):
+                            v |= ((int(hi_raw[(bit + t) >> 3]) >> ((bit + t) & 7)) & 1) << t
+                        code[e] |= v << wi
+                        k += 1
+            assert k == int(seg_cnt[s])
+    return mask.reshape(p.shape), code.reshape(p.shape)
+
+
+CASES = [
+    # in_fmt, out_fmt, bs, axis, shape, hi_w
+    ("int2", "fp4", 16, 0, (96, 64), 2),
+    ("fp4_e2m1", "fp8_e4m3", 16, 0, (64, 96), 4),
+    ("fp4_e2m1", "fp4_e2m1", 16, 0, (48, 32), 0),
+    ("int2", "fp8_e4m3", 8, 0, (40, 64), 8),
+    ("fp4_e2m1", "fp8_e4m3", 32, 1, (24, 128), 4),
+    ("int2", "fp4", 16, 1, (16, 256), 2),
+    ("fp6_e3m2", "fp6_e3m2", 32, 1, (16, 128), 0),
+    ("int4", "int8", 64, 1, (8, 256), 4),
+    ("fp4_e2m1", "fp8_e4m3", 32, 0, (80, 32), 4),      # ragged rows (80 = 2.5 blocks of 32)
+]
+
+
+@pytest.mark.parametrize("fi,fo,bs,axis,shape,hi_w", CASES)
+def test_pack_layout_and_roundtrip(M, fi, fo, bs, axis, shape, hi_w):
+    W = weights(shape[0], shape[1], 21)
+    p, deq = M.pack_mx_outlier(W.cuda(), 8, 8, fi, fo, 2, [axis], bs, want_deq=True)
+    assert p.hi_w == hi_w
+    y, art = O.quantize_mx_outlier(W, 8, 8, fi, fo, 2, axis, bs, artefacts=True)
+    assert_exact(deq, y, "fused dequant output")
+    assert_exact(p.dequantize(), y, "unpack(pack(W))")
+    assert_exact(p.dequantize(torch.bfloat16).float(), y.to(torch.bfloat16).float(), "bf16 unpack")
+    mask, code = decode_planes(p, M)
+    assert_exact(mask.float(), art["mask"], "outlier bitmap")
+    pre, L, post = M._ops.geometry(shape, axis)
+    nblk = (L + bs - 1) // bs
+    assert_exact(p.e_in.view(pre, nblk, post).float(), art["e_in"], "e_in")
+    assert_exact(p.e_out.view(pre, nblk, post).float(), art["e_out"], "e_out")
+    q = torch.where(art["mask"].bool(), art["qout"], art["qin"])
+    dec = torch.where(art["mask"].bool(), O.decode_elem(code, fo), O.decode_elem(code, fi))
+    assert_exact(dec, q, "element codes")
+
+
+def test_pack_plain_roundtrip(M):
+    W = weights(64, 256, 3)
+    for fmt, bs in (("fp4_e2m1", 32), ("fp6_e2m3", 32), ("int8", 16), ("fp8_e4m3", 64)):
+        p = M.pack_mx(W.cuda(), 8, fmt, axes=[1], block_size=bs)
+        y, art = O.quantize_mx(W, 8, fmt, 1, bs, mode="spec", artefacts=True)
+        assert_exact(p.dequantize(), y, fmt)
+        assert_exact(p.e_in.view(64, -1).float(), art["e"].squeeze(-1), fmt)
+    p = M.pack_mx(W.cuda(), 8, "fp4_e2m1", axes=[0], block_size=16)
+    assert_exact(p.dequantize(), O.quantize_mx(W, 8, "fp4_e2m1", 0, 16, mode="spec"))
+
+
+def test_pack_llama_shape_bytes_and_roundtrip(M):
+    """full-size property: unpack(pack(W)) == fake-quant(W) and the byte count matches DESIGN.md"""
+    W = weights(4096, 4096, 0).cuda()
+    p = M.pack_mx_outlier(W, 8, 8, "fp4_e2m1", "fp8_e4m3", 2, [0], 16)
+    y = M.quantize_mx_outlier_v1(W, 8, 8, "fp4_e2m1", "fp8_e4m3", "max", 2, [0], 16)
+    assert_exact(p.dequantize(), y)
+    rho = float(p.outlier_mask().float().mean())
+    per_elem = p.nbytes / W.numel()
+    expect = 0.5 + 2 / 16 + 1 / 8 + 0.5 * rho           # codes + 2 exponents / 16 + bitmap + 4-bit hi * rho
+    assert abs(per_elem - expect) < 0.01, (per_elem, expect, rho)
+    with pytest.raises(RuntimeError):                   # packed fast path needs 32-column words
+        M.pack_mx_outlier(W[:, :100].contiguous(), 8, 8, "int2", "fp4", 2, [0], 16)
