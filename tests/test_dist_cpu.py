@@ -1,0 +1,79 @@
+"""CPU tier, world_size 2, gloo: the host-side multi-GPU logic (Hessian combine, sharding maps,
+row gather).  The per-rank Hessians are produced by the oracle, so no GPU is needed."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import msq_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from msq_b200 import dist as D
+    torch.manual_seed(0)
+    K, T, nsamp = 48, 32, 7                       # 7 samples over 2 ranks: uneven split on purpose
+    X = torch.randn(nsamp, T, K)
+    lo, hi = D.shard_range(nsamp, rank, world)
+    H, n = torch.zeros(K, K), 0
+    for s in range(lo, hi):
+        H, n = O.hessian_add_batch(H, n, X[s:s + 1])
+    Hg, N = D.combine_hessians(H, n)
+    Hg2, _ = D.combine_hessians(H, n, upper_only=False)
+    Href, nref = torch.zeros(K, K), 0
+    for s in range(nsamp):
+        Href, nref = O.hessian_add_batch(Href, nref, X[s:s + 1])
+    ok = N == nsamp and float((Hg - Href).abs().max()) < 1e-5 * float(Href.abs().max())
+    ok = ok and float((Hg2 - Hg).abs().max()) < 1e-6 * float(Href.abs().max()) and torch.equal(Hg, Hg.t())
+    # row-sharded result gather
+    rows, cols, bs = 1000, 8, 4
+    rr = D.row_shards(rows, bs, world)
+    full = torch.arange(rows * cols, dtype=torch.float32).reshape(rows, cols)
+    got = D.all_gather_rows(full[rr[rank][0]:rr[rank][1]].clone(), rr, rows)
+    ok = ok and torch.equal(got, full)
+    # broadcast of a quantized layer from its owner
+    layer = torch.nn.Linear(4, 4, bias=False)
+    layer.weight.data.fill_(float(rank + 1))
+    D.broadcast_weight(layer, src=1)
+    ok = ok and bool((layer.weight.data == 2.0).all())
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_gloo():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world)), dict(ret)
+
+
+def test_sharding_maps():
+    from msq_b200 import dist as D
+    assert [D.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    shapes = {"q": (4096, 4096), "k": (4096, 4096), "v": (4096, 4096), "o": (4096, 4096), "gate": (11008, 4096),
+              "up": (11008, 4096), "down": (4096, 11008)}
+    a = D.assign_linears(shapes, 8)
+    assert sorted(set(a.values())) == list(range(7))          # 7 linears on 7 of 8 ranks
+    a2 = D.assign_linears(shapes, 2)
+    cost = lambda k: shapes[k][0] * shapes[k][1] ** 2 + shapes[k][1] ** 3
+    loads = [sum(cost(k) for k in a2 if a2[k] == r) for r in range(2)]
+    assert max(loads) / sum(loads) < 0.8
+    rs = D.row_shards(4096, 16, 8)
+    assert rs[0] == (0, 512) and rs[-1][1] == 4096 and all(lo % 256 == 0 for lo, _ in rs)
+    rs = D.row_shards(1000, 16, 3)                            # ragged: last shard shorter, none negative
+    assert rs[-1][1] == 1000 and all(hi >= lo for lo, hi in rs)
