@@ -14,3 +14,4 @@ from .utils.quant import (quantize_mx_outlier_v1, quantize_mx_outlier_hessian, q
 __version__ = "0.1.0"
 from .llm.gptq import GPTQ  # noqa: F401,E402
 from .packed import PackedMX, pack_mx, pack_mx_outlier  # noqa: F401,E402
+from .mx.linear import MXLinear, linear  # noqa: F401,E402

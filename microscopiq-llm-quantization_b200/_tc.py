@@ -58,3 +58,58 @@ def hessian_accumulate(H, X, alpha, beta, symmetric=True):
                                         N.ptr(ws), nbytes, int(bool(symmetric)), N.stream_ptr(X.device))
     N.check(rc, "msq_hessian_accumulate")
     return H
+
+
+N.register("msq_gemm_packed_w_bf16", _i, [_p, _ll, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p])
+
+
+#: activation rows at and above which packed_linear dequantizes the weight to bf16 first
+FUSED_MAX_M = 512
+
+
+def _bf16_terms(x):
+    """split x into bf16 pieces whose sum is x exactly (bf16: 1, fp16: 2, fp32: 3 terms)"""
+    if x.dtype == torch.bfloat16:
+        return [x]
+    xf = x.float()
+    terms = []
+    for _ in range(2 if x.dtype == torch.float16 else 3):
+        t = xf.to(torch.bfloat16)
+        terms.append(t)
+        xf = xf - t.float()
+    return terms
+
+
+def packed_linear(x, pw, bias=None):
+    """y[..., N] (fp32) = x[..., K] @ dequant(pw)[N, K].T (+ bias) with pw a PackedMX blocked along K
+    (block 32).  bf16 activations take one pass; fp16 / fp32 activations are split into exact bf16
+    terms (2 / 3 accumulating passes) so that every product stays exact."""
+    N.require_cuda(x, "x")
+    from . import _ops
+    if len(pw.shape) != 2 or pw.axis != 1 or pw.block_size != 32 or pw.hi_w != 0:
+        raise NotImplementedError("packed_linear needs a [N, K] tensor packed along K with block 32 and equal code widths")
+    Nn, K = pw.shape
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, K)
+    M = x2.shape[0]
+    out = torch.empty(M, Nn, dtype=torch.float32, device=x.device)
+    fi, fo = _ops.fmt4(pw.in_fmt), _ops.fmt4(pw.out_fmt)
+    if M >= FUSED_MAX_M and Nn % 8 == 0:
+        # compute-bound regime: dequantize the weight once to bf16 (exact) and run the dense GEMM
+        wb = pw.dequantize(torch.bfloat16)
+        for i, t in enumerate(_bf16_terms(x2)):
+            gemm_nt(t.contiguous(), wb, out=out, alpha=1.0, beta=1.0 if i else 0.0)
+        if bias is not None:
+            out += bias.float()
+        return out.reshape(*lead, Nn)
+    for i, t in enumerate(_bf16_terms(x2)):
+        t = t.contiguous()
+        if K % 8:
+            raise NotImplementedError("K must be a multiple of 32")
+        rc = N.lib().msq_gemm_packed_w_bf16(N.ptr(t), t.stride(0), N.ptr(pw.codes), N.ptr(pw.bitmap), N.ptr(pw.e_in),
+                                            N.ptr(pw.e_out), N.ptr(out), out.stride(0), M, Nn, K, fi[0], fi[1], fo[0],
+                                            fo[1], int(pw.plain), int(i > 0), N.stream_ptr(x.device))
+        N.check(rc, "msq_gemm_packed_w_bf16")
+    if bias is not None:
+        out += bias.float()
+    return out.reshape(*lead, Nn)

@@ -1,0 +1,261 @@
+// msq_gemm_w4.cu -- packed-weight linear on tcgen05:   C[m, n] (+)= sum_k X[m, k] * W[n, k]
+//
+// W is the packed MicroScopiQ tensor [N, K] blocked along K (block 32, inner layout): codes +
+// outlier bitmap + two int8 shared exponents per block (same code width for inliers and outliers,
+// the w_elem_format/w_elem_format pairing of number_system/mx/linear.py:78-85).  X is bf16.
+//
+// The weight tile is the UMMA *M* operand (128 output features), the activations the UMMA *N*
+// operand (BNX = 16..256 tokens), so a small batch does not waste the tensor core.  Per K-block of 64:
+//   warp 0      : TMA loads the X tile [BNX x 64] (128B swizzle)
+//   warps 8..11 : dequantize the W tile [128 x 64] from the packed planes (LUT + power-of-two scale,
+//                 exact in bf16) and write it to shared memory in the same 128B-swizzled K-major
+//                 layout TMA would produce; fence.proxy.async; arrive
+//   warp 1      : tcgen05.mma.kind::f16 128 x BNX x 16, fp32 accumulators in TMEM (double buffered)
+//   warps 4..7  : epilogue, TMEM -> registers -> C[m, n] (lane = n: coalesced rows of C)
+// Dequantized weight values q * 2^e are exactly representable in bf16, products are exact in the
+// fp32 accumulator: the result differs from the reference's fp32 F.linear on fake-quantized
+// operands (linear.py:91) only by summation order.
+#include "msq_api_internal.h"
+#include "msq_common.cuh"
+#include "msq_tc.cuh"
+
+namespace msq {
+
+constexpr int WM = 128, WBK = 64, WSTAGES = 4, WMAXN = 256;
+constexpr int WA_BYTES = WM * WBK * 2, WB_BYTES = WMAXN * WBK * 2;
+constexpr int W4_SMEM = WSTAGES * (WA_BYTES + WB_BYTES) + 1024 + 256 + 2 * 256 * 2;
+
+struct W4Params {
+  const uint8_t* codes; const uint32_t* bitmap; const int8_t* e_in; const int8_t* e_out;
+  float* C; long long ldc;
+  int M, N, K;              // C is [M, N]; W is [N, K]; X is [M, K]
+  int bnx;                  // activation tile (UMMA N), multiple of 16
+  int tiles_n, tiles_m;
+  int wi;                   // code width: 2, 4 or 8
+  int in_ebits, in_bits, out_ebits, out_bits;
+  int plain;                // no bitmap / outliers
+  int accumulate;           // C += instead of C =
+};
+
+__global__ void __launch_bounds__(384, 1) k_gemm_w4(const __grid_constant__ CUtensorMap tmX, const W4Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                   // W tiles
+  uint8_t* sB = smem + WSTAGES * WA_BYTES;              // X tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WSTAGES * (WA_BYTES + WB_BYTES));
+  uint64_t* full = bars;
+  uint64_t* empty = bars + WSTAGES;
+  uint64_t* acc_full = bars + 2 * WSTAGES;
+  uint64_t* acc_empty = bars + 2 * WSTAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * WSTAGES + 4);
+  __nv_bfloat16* lut_in = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  __nv_bfloat16* lut_out = lut_in + 256;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = P.tiles_n * P.tiles_m;
+  const int kblocks = (P.K + WBK - 1) / WBK;
+
+  if (warp == 0 && lane == 0) tc::tma_prefetch_desc(&tmX);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < WSTAGES; ++i) { tc::mbar_init(&full[i], 1 + 128); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
+    tc::mbar_fence_init();
+  }
+  if (warp == 2) tc::tmem_alloc<512>(tmem_slot);
+  for (int c = threadIdx.x; c < 256; c += blockDim.x) {
+    const bool valid = c < (1 << P.wi);
+    lut_in[c] = __float2bfloat16_rn(valid ? decode_elem((uint32_t)c, P.in_ebits, P.in_bits) : 0.0f);
+    lut_out[c] = __float2bfloat16_rn(valid ? decode_elem((uint32_t)c, P.out_ebits, P.out_bits) : 0.0f);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_coords = [&](int t, int& tn, int& tm) { tm = t / P.tiles_n; tn = t - tm * P.tiles_n; };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int tn, tm; tile_coords(t, tn, tm);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+          tc::mbar_expect_tx(&full[stage], (uint32_t)(P.bnx * WBK * 2));
+          tc::tma_load_2d(sB + stage * WB_BYTES, &tmX, &full[stage], kb * WBK, tm * P.bnx);
+          if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc(1 /*bf16*/, WM, P.bnx);
+      int stage = 0; uint32_t phase = 0;
+      int buf = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        tc::mbar_wait(&acc_empty[buf], acc_phase ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(buf * WMAXN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          tc::mbar_wait(&full[stage], phase);
+          tc::tc_fence_after();
+          const uint64_t ad = tc::make_kmajor_sw128_desc(tc::smem_u32(sA + stage * WA_BYTES));
+          const uint64_t bd = tc::make_kmajor_sw128_desc(tc::smem_u32(sB + stage * WB_BYTES));
+#pragma unroll
+          for (int k = 0; k < WBK / 16; ++k)
+            tc::umma_f16(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          tc::umma_commit(&empty[stage]);
+          if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
+        }
+        tc::umma_commit(&acc_full[buf]);
+        if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ---- weight dequant producers: 128 threads, 8 chunks (of 8 elements = 16 B of bf16) each per stage
+    const int ptid = threadIdx.x - 256;
+    const int wi = P.wi;
+    const long long code_row_bytes = ((long long)P.K * wi) >> 3;
+    const int kblk32 = P.K >> 5;                        // MX blocks per weight row
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int tn, tm; tile_coords(t, tn, tm);
+      const int n0 = tn * WM;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        tc::mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* dst = sA + stage * WA_BYTES;
+#pragma unroll 2
+        for (int i = 0; i < 8; ++i) {
+          const int c = ptid + 128 * i;
+          const int r = c >> 3, kc = c & 7;
+          const int n = n0 + r, k = kb * WBK + kc * 8;
+          uint4 outv = make_uint4(0, 0, 0, 0);
+          if (n < P.N && k < P.K) {
+            // 8 codes
+            uint32_t cw0, cw1 = 0;
+            const uint8_t* cp = P.codes + (long long)n * code_row_bytes + (((long long)k * wi) >> 3);
+            if (wi == 4) cw0 = __ldg(reinterpret_cast<const uint32_t*>(cp));
+            else if (wi == 2) cw0 = __ldg(reinterpret_cast<const uint16_t*>(cp));
+            else { const uint2 v = __ldg(reinterpret_cast<const uint2*>(cp)); cw0 = v.x; cw1 = v.y; }
+            uint32_t ob = 0;
+            const int blk = n * kblk32 + (k >> 5);
+            const int ei = P.e_in[blk];
+            int eo = 0;
+            if (!P.plain) {
+              ob = (__ldg(P.bitmap + (((long long)n * P.K + k) >> 5)) >> (k & 31)) & 0xFFu;
+              eo = P.e_out[blk];
+            }
+            const bool nan_blk = ei == MSQ_EXP_NAN || eo == MSQ_EXP_NAN;
+            // inlier: q * 2^e_in ; outlier: q * 2^(e_out - e_in)   (both exact in bf16)
+            const __nv_bfloat16 s_in = __float2bfloat16_rn(nan_blk ? qnan() : pow2i(ei));
+            const int eoi = max(-126, min(127, eo - ei));
+            const __nv_bfloat16 s_out = __float2bfloat16_rn(nan_blk ? qnan() : pow2i(eoi));
+            uint32_t packed[4];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              uint32_t code;
+              if (wi == 8) code = ((e < 4 ? cw0 : cw1) >> ((e & 3) * 8)) & 0xFFu;
+              else code = (cw0 >> (e * wi)) & ((1u << wi) - 1u);
+              const bool isout = (ob >> e) & 1u;
+              const __nv_bfloat16 q = isout ? lut_out[code] : lut_in[code];
+              const __nv_bfloat16 v = __hmul(q, isout ? s_out : s_in);
+              const uint32_t bits = (uint32_t)__bfloat16_as_ushort(v);
+              if (e & 1) packed[e >> 1] |= bits << 16; else packed[e >> 1] = bits;
+            }
+            outv = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          }
+          *reinterpret_cast<uint4*>(dst + r * 128 + ((kc ^ (r & 7)) << 4)) = outv;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc::mbar_arrive(&full[stage]);
+        if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    int buf = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int tn, tm; tile_coords(t, tn, tm);
+      tc::mbar_wait(&acc_full[buf], acc_phase);
+      tc::tc_fence_after();
+      const int n = tn * WM + q * 32 + lane;
+      for (int c = 0; c < P.bnx / 16; ++c) {
+        uint32_t r[32];
+        // 16 columns per step keeps the tail exact for BNX that are multiples of 16
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * WMAXN + c * 16))
+            : "memory");
+        tc::tmem_ld_wait();
+        if (n < P.N) {
+#pragma unroll
+          for (int v = 0; v < 16; ++v) {
+            const int m = tm * P.bnx + c * 16 + v;
+            if (m < P.M) {
+              float* p = P.C + (long long)m * P.ldc + n;
+              const float val = __uint_as_float(r[v]);
+              *p = P.accumulate ? (*p + val) : val;
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(&acc_empty[buf]);
+      if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace msq
+
+using namespace msq;
+
+extern "C" {
+
+// C[M,N] fp32 (+)= X[M,K] (bf16, K contiguous, ld = ldx) * W[N,K]^T with W given by its packed planes
+// (block 32 along K, inner layout, no hi stream: inlier and outlier codes share one width).
+int msq_gemm_packed_w_bf16(const void* X, long long ldx, const unsigned char* codes, const unsigned int* bitmap,
+                           const signed char* e_in, const signed char* e_out, float* C, long long ldc, int M, int N, int K,
+                           int in_ebits, int in_mbits, int out_ebits, int out_mbits, int plain, int accumulate,
+                           void* stream) {
+  if (!X || !codes || !e_in || !C || M <= 0 || N <= 0 || K <= 0) return MSQ_ERR_BAD_ARG;
+  if (!plain && (!bitmap || !e_out)) return MSQ_ERR_BAD_ARG;
+  if (K % 32 != 0) return MSQ_ERR_UNSUPPORTED;
+  Fmt fi = make_fmt(in_ebits, in_mbits, 0, 1.0f), fo = make_fmt(plain ? in_ebits : out_ebits, plain ? in_mbits : out_mbits, 0, 1.0f);
+  if (fi.width != fo.width) return MSQ_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(X) & 15) || (ldx % 8) || (reinterpret_cast<uintptr_t>(codes) & 15)) return MSQ_ERR_ALIGN;
+  W4Params P;
+  memset(&P, 0, sizeof(P));
+  P.codes = codes; P.bitmap = bitmap; P.e_in = e_in; P.e_out = e_out; P.C = C; P.ldc = ldc; P.M = M; P.N = N; P.K = K;
+  int bnx = M >= WMAXN ? WMAXN : ((M + 15) / 16) * 16;
+  P.bnx = bnx;
+  P.tiles_n = (N + WM - 1) / WM; P.tiles_m = (M + bnx - 1) / bnx;
+  P.wi = fi.width; P.in_ebits = in_ebits; P.in_bits = in_mbits;
+  P.out_ebits = plain ? in_ebits : out_ebits; P.out_bits = plain ? in_mbits : out_mbits;
+  P.plain = plain; P.accumulate = accumulate;
+  CUtensorMap tmX;
+  int rc = make_tmap_2d(&tmX, X, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, ldx, bnx, WBK);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_gemm_w4, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = P.tiles_n * P.tiles_m;
+  if (grid > sms) grid = sms;
+  k_gemm_w4<<<grid, 384, W4_SMEM, (cudaStream_t)stream>>>(tmX, P);
+  return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+}
+
+}  // extern "C"

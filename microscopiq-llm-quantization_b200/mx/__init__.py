@@ -5,3 +5,4 @@ from .specs import (MxSpecs, add_mx_args, apply_mx_specs, finalize_mx_specs, get
                     get_default_mx_specs, get_mx_specs, mx_assert_test)
 from .elemwise_ops import quantize_elemwise_op  # noqa: F401
 from .mx_ops import quantize_mx_op, quantize_mx_outlier_op  # noqa: F401
+from .linear import MXLinear, linear  # noqa: F401,E402

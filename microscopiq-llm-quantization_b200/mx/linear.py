@@ -1,0 +1,107 @@
+"""MX linear layer on B200 -- mirror of number_system/mx/linear.py (forward path).
+
+    linear(input, weight, bias=None, mx_specs=None, name=None)       linear.py:204-217
+    MXLinear(in_features, out_features, bias=True, mx_specs=None)     linear.py:220-254
+
+Forward = the reference's LinearFunction.forward (linear.py:20-108): bfloat/fp rounding of input,
+weight and bias, MX+outlier quantization of both operands along the input-feature axis (axes=[1],
+across-block detector of mx_ops.py), fp32 matmul, rounding of the output, bias add, rounding.
+The matmul runs on the packed weight with tcgen05 (csrc/msq_gemm_w4.cu) whenever the weight is a
+2-D tensor blocked by 32 along K with an element format of at most 8 bits; otherwise on the
+dequantized operands.  The reference's backward is broken as shipped and is not
+part of the contract: this layer is inference-only.
+"""
+import torch
+import torch.nn.functional as F
+
+from .. import _tc
+from ..packed import pack_mx_outlier
+from .elemwise_ops import quantize_elemwise_op
+from .mx_ops import quantize_mx_outlier_op
+from .specs import apply_mx_specs, mx_assert_test
+
+f_linear = F.linear
+torch_matmul = torch.matmul
+
+
+def _pack_weight(bf_weight, mx_specs):
+    fmt = mx_specs["w_elem_format"]
+    sb = mx_specs["scale_bits"] or 4                       # mx_ops.py:519-524
+    return pack_mx_outlier(bf_weight, sb, sb, fmt, fmt, 5, [1], mx_specs["block_size"], round=mx_specs["round_mx_output"],
+                           flush_fp32_subnorms=mx_specs["mx_flush_fp32_subnorms"], variant=1)
+
+
+def _packable(weight, mx_specs):
+    return (mx_specs["w_elem_format"] is not None and weight.dim() == 2 and mx_specs["block_size"] == 32
+            and weight.shape[1] % 32 == 0 and weight.shape[1] // 32 >= 2 and mx_specs["shared_exp_method"] == "max")
+
+
+def linear_forward(input, weight, bias, mx_specs, packed_weight=None):
+    bf_in = quantize_elemwise_op(input, mx_specs=mx_specs, round=mx_specs["round_output"])
+    bf_bias = None
+    if bias is not None:
+        bf_bias = quantize_elemwise_op(bias, mx_specs=mx_specs, round=mx_specs["round_weight"])
+    # MX quantize the activations along the input-feature axis (linear.py:66-73: axes=[1])
+    qis_input = quantize_mx_outlier_op(bf_in, mx_specs, inlier_elem_format=mx_specs["a_elem_format"],
+                                       outlier_elem_format=mx_specs["a_elem_format"], axes=[1],
+                                       round=mx_specs["round_mx_output"])
+    if packed_weight is None and _packable(weight, mx_specs):
+        bf_weight = quantize_elemwise_op(weight, mx_specs=mx_specs, round=mx_specs["round_weight"])
+        packed_weight = _pack_weight(bf_weight, mx_specs)
+    if packed_weight is not None and qis_input.shape[-1] == packed_weight.shape[1]:
+        output = _tc.packed_linear(qis_input, packed_weight).to(input.dtype)
+    else:
+        bf_weight = quantize_elemwise_op(weight, mx_specs=mx_specs, round=mx_specs["round_weight"])
+        qis_weight = quantize_mx_outlier_op(bf_weight, mx_specs, inlier_elem_format=mx_specs["w_elem_format"],
+                                            outlier_elem_format=mx_specs["w_elem_format"], axes=[1],
+                                            round=mx_specs["round_mx_output"])
+        output = f_linear(qis_input, qis_weight)
+    output = quantize_elemwise_op(output, mx_specs=mx_specs, round=mx_specs["round_output"])
+    if bf_bias is not None:
+        output = quantize_elemwise_op(output + bf_bias, mx_specs=mx_specs, round=mx_specs["round_output"])
+    return output
+
+
+def linear(input, weight, bias=None, mx_specs=None, name=None):
+    mx_assert_test(mx_specs)
+    if mx_specs is None:
+        return f_linear(input, weight, bias=bias)
+    mx_specs = apply_mx_specs(mx_specs)
+    with torch.no_grad():
+        return linear_forward(input, weight, bias, mx_specs)
+
+
+class MXLinear(torch.nn.Linear):
+    def __init__(self, in_features, out_features, bias=True, mx_specs=None, name=None):
+        mx_assert_test(mx_specs)
+        self.mx_none = mx_specs is None
+        self.name = name
+        self.mx_specs = apply_mx_specs(mx_specs)
+        self._packed = None
+        self._packed_version = None
+        super().__init__(in_features, out_features, bias)
+
+    def apply_mx_specs(self, mx_specs):
+        mx_assert_test(mx_specs)
+        self.mx_none = mx_specs is None
+        self.mx_specs = apply_mx_specs(mx_specs)
+        self._packed = None
+
+    def append_name(self, postfix):
+        self.name += postfix
+
+    def packed_weight(self):
+        """quantize + pack the weight once; reused until the parameter is modified"""
+        ver = (self.weight._version, self.weight.data_ptr())
+        if self._packed is None or self._packed_version != ver:
+            with torch.no_grad():
+                bf_w = quantize_elemwise_op(self.weight.data, mx_specs=self.mx_specs, round=self.mx_specs["round_weight"])
+                self._packed = _pack_weight(bf_w, self.mx_specs) if _packable(self.weight, self.mx_specs) else None
+            self._packed_version = ver
+        return self._packed
+
+    def forward(self, inputs):
+        if self.mx_none:
+            return super().forward(inputs)
+        with torch.no_grad():
+            return linear_forward(inputs, self.weight, self.bias, self.mx_specs, packed_weight=self.packed_weight())
