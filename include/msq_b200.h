@@ -99,6 +99,73 @@ int msq_outlier_bounds_across_blocks_f32(const float* in, float* lo, float* hi, 
                                          long long L, long long post, int block_size,
                                          float std_dev, void* stream);
 
+/* ---- packed planes -> dense -------------------------------------------------------------
+ * Inverse of the packed outputs of msq_quantize_mx_outlier_f32 / msq_quantize_mx_f32 (plain != 0).
+ * The reference has no packed artefact (llm/opt.py:254-294 is dead code); the invariant checked is
+ * unpack(pack(W)) == quantize_mx_outlier_v1(W) bit for bit (utils/quant.py:147-266).
+ * out_f32 and/or out_bf16 (device, same shape as the original tensor). */
+int msq_unpack_mx(const unsigned char* codes, const signed char* e_in, const signed char* e_out,
+                  const unsigned int* bitmap, const unsigned char* hi, float* out_f32, void* out_bf16,
+                  long long pre, long long L, long long post, int block_size,
+                  int in_ebits, int in_mbits, int in_emax, float in_max_norm,
+                  int out_ebits, int out_mbits, int out_emax, float out_max_norm, int plain, void* stream);
+
+/* ---- GPTQ uniform quantizer -------------------------------------------------------------
+ * replaces quantize(x, scale, zero, maxq)        utils/quant.py:268-272
+ *          Quantizer.find_params                 utils/quant.py:298-357
+ * x is viewed as [pre, C, post] with one (scale, zero) per C; find_params works on rows of x [rows, n]. */
+int msq_uniform_quantize_f32(const float* x, float* out, const float* scale, const float* zero, int maxq,
+                             long long pre, long long C, long long post, void* stream);
+int msq_uniform_find_params_f32(const float* x, float* scale, float* zero, long long rows, long long n,
+                                int maxq, int sym, int mse, float norm, int grid, float maxshrink, void* stream);
+
+/* _shared_exponents(method="max")               utils/quant.py:498-541  (exact floor(log2)) */
+int msq_shared_exponents_f32(const float* x, float* out, long long pre, long long L, long long post,
+                             int ebits, void* stream);
+
+/* ---- tensor-core GEMM / Hessian ---------------------------------------------------------
+ * C[M,N] fp32 = alpha * A[M,K] * B[N,K]^T + beta * C ; A, B 16-bit (dtype 1 fp16, 2 bf16), K contiguous.
+ * replaces the dense contractions the reference sends to cuBLAS SGEMM (llm/gptq.py:58, mx/linear.py:91). */
+int msq_gemm_nt_f32out(const void* A, const void* B, float* C, int M, int N, int K, long long lda,
+                       long long ldb, long long ldc, float alpha, float beta, int dtype, void* stream);
+
+/* GPTQ.add_batch for nn.Linear                  llm/gptq.py:53-58
+ *   H <- beta * H + alpha * X^T X,  X [T, K] tokens x features (dtype 0 fp32, 1 fp16, 2 bf16), H [K,K] fp32.
+ *   caller passes beta = n/(n+b), alpha = 2/(n+b); workspace from msq_hessian_workspace_bytes. */
+long long msq_hessian_workspace_bytes(int T, int K, int dtype);
+int msq_hessian_accumulate(const void* X, int T, int K, long long ldx, int dtype, float* H, long long ldh,
+                           float alpha, float beta, void* workspace, long long workspace_bytes,
+                           int symmetric, void* stream);
+
+/* ---- GPTQ solver ------------------------------------------------------------------------
+ * msq_gptq_block: columns [i1, i1+count) of GPTQ.fasterquant's loop   llm/gptq.py:106-160
+ *   (quantize_mx_outlier_hessian per column, loss, rank-1 updates inside the 128-column block).
+ *   W [rows, ldw] current weights (read), Q out, Hinv upper Cholesky factor of H^-1, Err [rows,128] out,
+ *   loss device double (+=), zeros/kcnt [cols] int32 (+=, caller zeroes once per linear), status OR.
+ * msq_gptq_trailing_update: W[:, i2:] -= Err @ Hinv[i1:i1+count, i2:]   llm/gptq.py:165
+ * msq_gptq_check_prune: *violation += #columns whose zero count is below the reference's k
+ *   (llm/gptq.py:146-153 would then change values -> use the column-synchronous path).
+ * msq_rank1_sub_f32: W[:, :n] -= err (x) h                              llm/gptq.py:159 */
+int msq_gptq_block(const float* W, long long ldw, float* Q, long long ldq, const float* Hinv, long long ldh,
+                   int rows, int i1, int count, float* Err, double* loss, int* zeros, int* kcnt, int* status,
+                   int block_size, int in_scale_bits, int out_scale_bits,
+                   int in_ebits, int in_mbits, int in_emax, float in_max_norm,
+                   int out_ebits, int out_mbits, int out_emax, float out_max_norm,
+                   float std_dev, int flush_fp32_subnorms, int rmode, void* stream);
+int msq_gptq_trailing_update(float* W, long long ldw, const float* Err, const float* Hinv, long long ldh,
+                             int rows, int i1, int count, int i2, int cols, void* stream);
+int msq_gptq_check_prune(const int* zeros, const int* kcnt, int cols, int* violation, void* stream);
+int msq_rank1_sub_f32(float* W, long long ldw, const float* err, const float* h, int rows, int n, void* stream);
+
+/* ---- packed-weight linear ---------------------------------------------------------------
+ * C[M,N] fp32 (+)= X[M,K] (bf16) * dequant(W)[N,K]^T, W = packed planes blocked by 32 along K with equal
+ * inlier/outlier code widths.  replaces LinearFunction.forward's fake-quant + F.linear,
+ * number_system/mx/linear.py:78-91. */
+int msq_gemm_packed_w_bf16(const void* X, long long ldx, const unsigned char* codes, const unsigned int* bitmap,
+                           const signed char* e_in, const signed char* e_out, float* C, long long ldc,
+                           int M, int N, int K, int in_ebits, int in_mbits, int out_ebits, int out_mbits,
+                           int plain, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
