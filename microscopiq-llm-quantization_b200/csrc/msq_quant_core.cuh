@@ -103,26 +103,77 @@ struct BlockOut {
   int st;          // status bits raised by this block
 };
 
+// ---------------------------------------------------------------------------------------------
+// core_outlier: the MX+outlier quantizer on one block.
 // x[] in: block values (padding = 0).  x[] out: dequantized values.
-// code[] out (if CODES): element codes, inlier or outlier format according to mask.
+// code[] out (if CODES): element codes, inlier or outlier format according to o.mask.
 // EXT: detector bounds come from lo_e/hi_e (variant 1) instead of block statistics.
-template <int N, int LPB, bool CODES, bool EXT>
+//
+// Instruction budget matters here (this is the HBM-bound headline kernel), so the element path is
+// written for the Blackwell pipes: pairs of elements go through packed fp32x2 instructions
+// (FMUL2/FFMA2/FADD2, IEEE-rn per lane, so results are identical to scalar code), the
+// inlier/outlier choice is an exact 0/1 blend  a*(1-m) + b*m  on the FMA pipe instead of selects,
+// and the quantum exponent is clamped in the float domain (2^p = clamp(2^E, 2^lo, 2^hi)).
+// Every blend is exact: one operand is multiplied by exactly 0, the other by exactly 1, and the
+// format constants being blended (2^lo, 2^hi, 2^-mant, max_norm) are small dyadic numbers.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
+// a*(1-m) + b*m with m in {0,1}, nm = 1-m
+__device__ __forceinline__ float2 blend2(float2 a, float2 b, float2 m, float2 nm) {
+  return __ffma2_rn(b, m, __fmul2_rn(a, nm));
+}
+// c_i + m*(c_o - c_i) for exactly representable constants
+__device__ __forceinline__ float2 cblend2(float ci, float dco, float2 m) { return __ffma2_rn(f2s(dco), m, f2s(ci)); }
+
+struct ElemConsts {      // per-format constants of the float-domain rounding
+  float L, H;            // 2^lo, 2^hi  (ints: 1, 1)
+  float down;            // 2^-(bits-2)
+  float mx;              // max_norm
+};
+__device__ __forceinline__ ElemConsts elem_consts(const Fmt& f) {
+  ElemConsts e;
+  e.L = f.ebits ? pow2i(f.min_exp) : 1.0f;
+  e.H = f.ebits ? __int_as_float(0x7F000000) : 1.0f;      // 2^127: no upper clamp for floats
+  e.down = f.down; e.mx = f.max_norm;
+  return e;
+}
+
+// scalar version of the bounded element rounding (used for odd N and for round-to-even)
+__device__ __forceinline__ float qelem_pair_scalar(float v, float L, float H, float down, float mx, const RoundSel rs) {
+  const float P2 = fminf(fmaxf(__int_as_float(__float_as_int(v) & 0x7F800000), L), H);
+  const float s2 = __fmul_rn(P2, down);
+  const float s1 = __int_as_float(0x7F000000 - __float_as_int(s2));
+  const float y = __fmul_rn(v, s1);
+  float r;
+  if (!rs.even) {
+    r = truncf(__fadd_rn(y, copysignf(rs.addend, y)));
+  } else {
+    const float a = fabsf(y);
+    r = floorf(__fadd_rn(a, 0.5f));
+    const float t = __fadd_rn(a, -0.5f), hh = __fmul_rn(t, 0.5f);
+    if (t >= 0.0f && hh == floorf(hh)) r = __fadd_rn(r, -1.0f);
+    r = copysignf(r, y);
+  }
+  return fminf(fmaxf(__fmul_rn(r, s2), -mx), mx);
+}
+
+template <int N, int LPB, bool CODES, bool EXT, bool CNT = true>
 __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)[N], const QCfg& c,
                                                  const float* lo_e, const float* hi_e) {
   constexpr int BS = N * LPB;
   BlockOut o;
   o.st = 0;
+  o.mask = 0;
+  o.cnt = 0;
   int bad = 0;
   float l = 0.0f, h = 0.0f;
   if (!EXT) {
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const float a = fabsf(x[i]);
-      bad |= !(a <= 3.402823466e38f);
-      s += (double)a;
-    }
+    for (int i = 0; i < N; ++i) s += (double)fabsf(x[i]);
     s = grp_sum<LPB>(s);
+    bad = !(s <= 1.0e300);            // an Inf or NaN element makes the fp64 sum non-finite
     const double mean64 = s / (double)BS;
     double q = 0.0;
 #pragma unroll
@@ -139,22 +190,22 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
 #pragma unroll
     for (int i = 0; i < N; ++i) bad |= !(fabsf(x[i]) <= 3.402823466e38f);
   }
-  if (LPB > 1) bad = grp_or<LPB>(bad);
+  if (EXT && LPB > 1) bad = grp_or<LPB>(bad);
 
-  // outlier split.  A*(1-mask) / A*mask of quant.py:70-71 are exact products with 0/1, so the
-  // maxima below are the reference's maxima.  ALU-pipe work is kept minimal: 0/1 blending and
-  // exponent arithmetic run on the FMA pipe (FMUL / IMAD).
-  uint32_t mask = 0;
-  float m_in = 0.0f;
+  // outlier split exactly as quant.py:70-71: inlier_val = A*(1-mask), outlier_val = A*mask with an
+  // exact 0/1 float mask.  From here on x[] holds the inlier part and t1[] the outlier part.
+  float mf[N], t1[N];
+  float m_in = 0.0f, fcnt = 0.0f;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const float li = EXT ? lo_e[i] : l, hi_i = EXT ? hi_e[i] : h;
-    const bool isout = (x[i] < li) | (x[i] > hi_i);
-    mask |= (isout ? 1u : 0u) << i;
-    m_in = fmaxf(m_in, __fmul_rn(fabsf(x[i]), isout ? 0.0f : 1.0f));
+    mf[i] = ((x[i] < li) | (x[i] > hi_i)) ? 1.0f : 0.0f;
+    if (CNT) fcnt = __fadd_rn(fcnt, mf[i]);
+    t1[i] = __fmul_rn(x[i], mf[i]);
+    x[i] = __fmul_rn(x[i], __fsub_rn(1.0f, mf[i]));
+    m_in = fmaxf(m_in, fabsf(x[i]));
   }
-  o.mask = mask;
-  o.cnt = grp_add<LPB>(__popc(mask));
+  if (CNT) o.cnt = grp_add<LPB>((int)fcnt);
   m_in = grp_max<LPB>(m_in);
 
   const int E_in = (m_in == 0.0f) ? -126 : floor_log2f(m_in);
@@ -166,11 +217,12 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
   const int e_in = dead_in ? 0 : o.e_in;
   const float s_in = pow2i(e_in), inv_s_in = pow2i(-e_in);
 
+  // level-1 scaling of the outliers, t = outlier_val * 2^e_in (quant.py:94); their maximum gives e_out
   float m_out = 0.0f;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    const float t = fabsf(__fmul_rn(x[i], s_in));
-    m_out = fmaxf(m_out, __fmul_rn(t, ((mask >> i) & 1u) ? 1.0f : 0.0f));
+    t1[i] = __fmul_rn(t1[i], s_in);
+    m_out = fmaxf(m_out, fabsf(t1[i]));
   }
   m_out = grp_max<LPB>(m_out);
   const int E_out = (m_out == 0.0f) ? -126 : floor_log2f(m_out);
@@ -181,47 +233,61 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
   const float s_out = pow2i(e_out), inv_s_out = pow2i(-e_out);
   const RoundSel rs = make_round(c.rmode);
   const float inv_s_in_eff = flush ? 0.0f : inv_s_in;            // quant.py:80 (x*0 keeps the sign of x)
+  const ElemConsts ci = elem_consts(c.fin), co = elem_consts(c.fout);
+  const float dL = __fsub_rn(co.L, ci.L), dH = __fsub_rn(co.H, ci.H), dD = __fsub_rn(co.down, ci.down),
+              dM = __fsub_rn(co.mx, ci.mx);
 
-  // Element rounding with the quantum exponent p clamped in the BIASED domain:
-  //   p' = clamp(biased_exp(v), lo', hi')   (floats: lo' = min_exp+127, hi' = 254; ints: 127, 127)
-  //   y  = v * 2^(mant - p)  ->  round  ->  * 2^(p - mant)
-  // (v * 2^-p) * 2^mant == v * 2^(mant-p) exactly here: |v| <= 2^(emax+1) and every element
-  // format on this path has ebits <= 5, so no intermediate leaves the normal range inexactly.
-  const int mant_i = c.fin.bits - 2, mant_o = c.fout.bits - 2;
-  const int lo_i = c.fin.ebits ? c.fin.min_exp + 127 : 127, hi_i = c.fin.ebits ? 254 : 127;
-  const int lo_o = c.fout.ebits ? c.fout.min_exp + 127 : 127, hi_o = c.fout.ebits ? 254 : 127;
-  const int d_lo = lo_o - lo_i, d_hi = hi_o - hi_i;
-  const int c1_i = (254 + mant_i) << 23, d_c1 = (mant_o - mant_i) << 23;   // s1 = c1 - p'<<23
-  const int c2_i = -(mant_i << 23), d_c2 = -((mant_o - mant_i) << 23);     // s2 = c2 + p'<<23
-  const float mx_i = c.fin.max_norm, mx_o = c.fout.max_norm;
-
+  // inlier : v = in * 2^-e_in           ; r = q * 2^e_in                  quant.py:92,102
+  // outlier: v = t * 2^-e_out           ; r = (q * 2^e_out) * 2^-e_in     quant.py:125,136
+  // exactly one of the two scaled parts is non-zero, so v = vin + vout is exact and one rounding
+  // with the element's own format replaces the reference's two (the other one rounds an exact 0).
+  if ((N % 2 == 0) && !rs.even) {
 #pragma unroll
-  for (int i = 0; i < N; ++i) {
-    const bool isout = (mask >> i) & 1u;
-    const int mi = isout ? 1 : 0;
-    // inlier : v = x * 2^-e_in               ; r = q * 2^e_in                  quant.py:92,102
-    // outlier: v = (x * 2^e_in) * 2^-e_out   ; r = (q * 2^e_out) * 2^-e_in     quant.py:94,125,136
-    const float vin = __fmul_rn(x[i], inv_s_in_eff);
-    const float vout = __fmul_rn(__fmul_rn(x[i], s_in), inv_s_out);
-    const float v = isout ? vout : vin;
-    const int be = (__float_as_int(v) >> 23) & 0xFF;
-    const int pb = min(max(be, lo_i + mi * d_lo), hi_i + mi * d_hi);
-    const float s1 = __int_as_float((c1_i + mi * d_c1) - (pb << 23));
-    const float s2 = __int_as_float((c2_i + mi * d_c2) + (pb << 23));
-    const float y = __fmul_rn(v, s1);
-    const float a = fabsf(y);
-    float r = floorf(__fadd_rn(a, rs.addend));
-    if (rs.even) {
-      const float t = __fadd_rn(a, -0.5f);
-      const float hh = __fmul_rn(t, 0.5f);
-      if (t >= 0.0f && hh == floorf(hh)) r = __fadd_rn(r, -1.0f);
+    for (int i = 0; i < N; i += 2) {
+      const float2 m = f2(mf[i], mf[i + 1]);
+      const float2 vin = __fmul2_rn(f2(x[i], x[i + 1]), f2s(inv_s_in_eff));
+      const float2 vout = __fmul2_rn(f2(t1[i], t1[i + 1]), f2s(inv_s_out));
+      const float2 v = __fadd2_rn(vin, vout);
+      const float2 L2 = cblend2(ci.L, dL, m), H2 = cblend2(ci.H, dH, m), D2 = cblend2(ci.down, dD, m),
+                   M2 = cblend2(ci.mx, dM, m);
+      float2 P2;
+      P2.x = fminf(fmaxf(__int_as_float(__float_as_int(v.x) & 0x7F800000), L2.x), H2.x);
+      P2.y = fminf(fmaxf(__int_as_float(__float_as_int(v.y) & 0x7F800000), L2.y), H2.y);
+      const float2 s2 = __fmul2_rn(P2, D2);
+      float2 s1;
+      s1.x = __int_as_float(0x7F000000 - __float_as_int(s2.x));
+      s1.y = __int_as_float(0x7F000000 - __float_as_int(s2.y));
+      const float2 y = __fmul2_rn(v, s1);
+      const float2 yh = __fadd2_rn(y, f2(copysignf(rs.addend, y.x), copysignf(rs.addend, y.y)));
+      float2 q = __fmul2_rn(f2(truncf(yh.x), truncf(yh.y)), s2);
+      q.x = fminf(fmaxf(q.x, -M2.x), M2.x);
+      q.y = fminf(fmaxf(q.y, -M2.y), M2.y);
+      const bool o0 = mf[i] != 0.0f, o1 = mf[i + 1] != 0.0f;
+      if (CODES) {
+        code[i] = encode_elem(q.x, o0 ? c.fout.ebits : c.fin.ebits, o0 ? c.fout.bits : c.fin.bits);
+        code[i + 1] = encode_elem(q.y, o1 ? c.fout.ebits : c.fin.ebits, o1 ? c.fout.bits : c.fin.bits);
+        o.mask |= (o0 ? 1u : 0u) << i;
+        o.mask |= (o1 ? 1u : 0u) << (i + 1);
+      }
+      const float2 rin = __fmul2_rn(q, f2s(s_in));
+      const float2 rout = __fmul2_rn(__fmul2_rn(q, f2s(s_out)), f2s(inv_s_in));
+      const float2 r = __fadd2_rn(f2(o0 ? rout.x : rin.x, o1 ? rout.y : rin.y), f2s(0.0f));   // quant.py:140 (x + 0)
+      x[i] = r.x; x[i + 1] = r.y;
     }
-    const float mx = isout ? mx_o : mx_i;
-    const float qv = fminf(fmaxf(__fmul_rn(copysignf(r, y), s2), -mx), mx);
-    if (CODES) code[i] = encode_elem(qv, isout ? c.fout.ebits : c.fin.ebits, isout ? c.fout.bits : c.fin.bits);
-    const float rin = __fmul_rn(qv, s_in);
-    const float rout = __fmul_rn(__fmul_rn(qv, s_out), inv_s_in);
-    x[i] = __fadd_rn(isout ? rout : rin, 0.0f);                                 // quant.py:140 (x + 0)
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const bool isout = mf[i] != 0.0f;
+      const float v = __fadd_rn(__fmul_rn(x[i], inv_s_in_eff), __fmul_rn(t1[i], inv_s_out));
+      const float qv = qelem_pair_scalar(v, isout ? co.L : ci.L, isout ? co.H : ci.H, isout ? co.down : ci.down,
+                                         isout ? co.mx : ci.mx, rs);
+      if (CODES) {
+        code[i] = encode_elem(qv, isout ? c.fout.ebits : c.fin.ebits, isout ? c.fout.bits : c.fin.bits);
+        o.mask |= (isout ? 1u : 0u) << i;
+      }
+      const float r = isout ? __fmul_rn(__fmul_rn(qv, s_out), inv_s_in) : __fmul_rn(qv, s_in);
+      x[i] = __fadd_rn(r, 0.0f);
+    }
   }
   if (dead) {      // NaN/Inf input or a shared exponent above the scale range: the reference asserts
 #pragma unroll

@@ -13,7 +13,7 @@
 
 namespace msq {
 
-template <int BS, bool OUTLIER, bool PACK, bool EXT>
+template <int BS, bool OUTLIER, bool PACK, bool EXT, bool CNT>
 __global__ void __launch_bounds__(256, (BS <= 16 ? 3 : 1)) k_strided(const QParams P) {
   extern __shared__ uint32_t s_hi[];
   __shared__ int s_warp[8];
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256, (BS <= 16 ? 3 : 1)) k_strided(const QPara
           lo[i] = P.lo_ext[o]; hi[i] = P.hi_ext[o];
         }
       }
-      bo = core_outlier<BS, 1, PACK, EXT>(x, code, P.c, lo, hi);
+      bo = core_outlier<BS, 1, PACK, EXT, CNT>(x, code, P.c, lo, hi);
     } else {
       PlainOut po = core_plain<BS, 1>(x, code, PACK, P.c, (P.ext_max && active) ? P.ext_max + t0 : nullptr);
       bo.mask = 0; bo.e_in = po.e; bo.e_out = 0; bo.cnt = 0; bo.st = po.st;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256, (BS <= 16 ? 3 : 1)) k_strided(const QPara
     if (active) {
       if (P.e_in) P.e_in[t0] = (int8_t)bo.e_in;
       if (OUTLIER && P.e_out) P.e_out[t0] = (int8_t)bo.e_out;
-      if (OUTLIER && P.blk_cnt) P.blk_cnt[t0] = (uint8_t)bo.cnt;
+      if (OUTLIER && CNT && P.blk_cnt) P.blk_cnt[t0] = (uint8_t)bo.cnt;
     }
     if (PACK) {
       // host guarantees post % 32 == 0, so a warp's 32 columns share (p, b) and whole words
@@ -144,10 +144,12 @@ cudaError_t launch_strided(const QParams& P, bool outlier, size_t smem, cudaStre
   void (*k)(const QParams) = nullptr;
   const bool pack = P.codes != nullptr;
   const bool ext = outlier && P.c.variant != 0;
-#define MSQ_PICK(BS_)                                                                               \
-  if (!outlier) k = pack ? k_strided<BS_, false, true, false> : k_strided<BS_, false, false, false>; \
-  else if (ext) k = pack ? k_strided<BS_, true, true, true> : k_strided<BS_, true, false, true>;     \
-  else k = pack ? k_strided<BS_, true, true, false> : k_strided<BS_, true, false, false>;
+  const bool cnt = pack || P.blk_cnt != nullptr;
+#define MSQ_PICK(BS_)                                                                                             \
+  if (!outlier) k = pack ? k_strided<BS_, false, true, false, false> : k_strided<BS_, false, false, false, false>; \
+  else if (ext) k = pack ? k_strided<BS_, true, true, true, true> : k_strided<BS_, true, false, true, true>;       \
+  else if (pack) k = k_strided<BS_, true, true, false, true>;                                                      \
+  else k = cnt ? k_strided<BS_, true, false, false, true> : k_strided<BS_, true, false, false, false>;
   if (P.bs == 16) { MSQ_PICK(16) }
   else if (P.bs == 32) { MSQ_PICK(32) }
   else if (P.bs == 8) { MSQ_PICK(8) }
