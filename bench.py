@@ -78,6 +78,104 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def _time_ms(fn, iters, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def extras(dev, dev_w, nel):
+    """secondary metrics of BASELINE.json's metric string, rank 0 only, each a few hundred ms:
+    quantize+pack GB/s, GPTQ seconds for one LLaMA-2-7B decoder layer (x32 = model), packed GEMM TFLOP/s."""
+    import msq_b200
+    from msq_b200 import _tc
+    out = {}
+    # (1) quantize + pack, same 7 linears, algorithmic bytes = 4 B read + packed bytes written
+    packed_bytes = [0]
+
+    def pack_all():
+        tot = 0
+        for w in dev_w:
+            p = msq_b200.pack_mx_outlier(w, QCFG["in_sb"], QCFG["out_sb"], QCFG["in_fmt"], QCFG["out_fmt"], QCFG["std_dev"],
+                                         [QCFG["axis"]], QCFG["bs"], check=False)
+            tot += p.codes.numel() + p.e_in.numel() + p.e_out.numel() + p.bitmap.numel() * 4
+        packed_bytes[0] = tot
+    ms = _time_ms(pack_all, 5)
+    p = msq_b200.pack_mx_outlier(dev_w[0], QCFG["in_sb"], QCFG["out_sb"], QCFG["in_fmt"], QCFG["out_fmt"], QCFG["std_dev"],
+                                 [QCFG["axis"]], QCFG["bs"])
+    bpe = p.nbytes / dev_w[0].numel()
+    out["pack"] = {"GBps": nel * (4 + bpe) / (ms * 1e-3) / 1e9, "ms_per_layer": ms, "packed_bytes_per_elem": bpe,
+                   "frac_of_hbm_peak": nel * (4 + bpe) / (ms * 1e-3) / 1e9 / peaks()[0]}
+    del p
+    # (2) GPTQ: Hessian over 128 x 2048 synthetic fp16 tokens + fasterquant for the 7 linears of one layer
+    msq_b200.GPTQ.verbose = False
+    nsamples, seqlen = 128, 2048
+    t_h = t_s = 0.0
+    flops_h = 0.0
+    X = {}
+    for _, r, c in LAYER_SHAPES:
+        if c not in X:
+            X[c] = torch.randn(1, seqlen, c, device=dev, generator=torch.Generator(device=dev).manual_seed(c)).half()
+    for i, (name, r, c) in enumerate(LAYER_SHAPES):
+        layer = torch.nn.Linear(c, r, bias=False, device=dev, dtype=torch.float16)
+        layer.weight.data = dev_w[i].half()
+        g = msq_b200.GPTQ(layer)
+        g.hessian_batch = 8
+        g.quantizer = msq_b200.MXQuantizer()
+        g.quantizer.configure(8, 8, QCFG["in_fmt"], QCFG["out_fmt"], axes=[0], block_size=QCFG["bs"])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(nsamples):
+            g.add_batch(X[c], None)
+        _ = g.H
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        g.fasterquant()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        if i == 0:      # first call pays cuSOLVER initialisation: repeat it
+            layer.weight.data = dev_w[i].half()
+            g = msq_b200.GPTQ(layer)
+            g.hessian_batch = 8
+            g.quantizer = msq_b200.MXQuantizer()
+            g.quantizer.configure(8, 8, QCFG["in_fmt"], QCFG["out_fmt"], axes=[0], block_size=QCFG["bs"])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(nsamples):
+                g.add_batch(X[c], None)
+            _ = g.H
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            g.fasterquant()
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+        t_h += t1 - t0
+        t_s += t2 - t1
+        flops_h += 2.0 * nsamples * seqlen * c * c
+        g.free()
+    out["gptq_layer"] = {"hessian_s": t_h, "solve_s": t_s, "layer_s": t_h + t_s,
+                         "hessian_TFLOPs": flops_h / t_h / 1e12,
+                         "llama2_7b_quantize_s_est": 32 * (t_h + t_s),
+                         "note": "one decoder layer measured (7 linears, 128x2048 fp16 tokens each, layer forward excluded) x 32"}
+    # (3) packed-weight GEMM, K = N = 4096, MX-FP4 + outliers, bf16 activations
+    gemm = {}
+    W = dev_w[0]
+    pw = msq_b200.pack_mx_outlier(W, 8, 8, "fp4_e2m1", "fp4_e2m1", 5, [1], 32, variant=1)
+    for M in (16, 256, 4096, 8192):
+        x = torch.randn(M, 4096, device=dev).to(torch.bfloat16)
+        ms = _time_ms(lambda: _tc.packed_linear(x, pw), 10)
+        gemm["M%d" % M] = {"ms": ms, "TFLOPs": 2.0 * M * 4096 * 4096 / (ms * 1e-3) / 1e12}
+    out["packed_gemm_k4096_n4096"] = gemm
+    return out
+
+
 def make_weights(device, seed):
     g = torch.Generator().manual_seed(seed)
     out = []
@@ -124,6 +222,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary metrics (pack, GPTQ layer, GEMM sweep)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -224,6 +323,8 @@ def main():
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         line["roofline"]["traffic"] = json.load(open(tr)).get("k_strided_bytes_per_launch")
+    if not args.no_extras:
+        line["extra"] = extras(dev, dev_w, nel)
     if not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count())
         W = host_w[0]

@@ -35,9 +35,11 @@ struct W4Params {
   int in_ebits, in_bits, out_ebits, out_bits;
   int plain;                // no bitmap / outliers
   int accumulate;           // C += instead of C =
+  int ksplit;               // K is cut into ksplit slices (atomicAdd epilogue when > 1)
+  int kb_per_split;         // 64-wide K blocks per slice
 };
 
-__global__ void __launch_bounds__(384, 1) k_gemm_w4(const __grid_constant__ CUtensorMap tmX, const W4Params P) {
+__global__ void __launch_bounds__(512, 1) k_gemm_w4(const __grid_constant__ CUtensorMap tmX, const W4Params P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                   // W tiles
@@ -52,12 +54,12 @@ __global__ void __launch_bounds__(384, 1) k_gemm_w4(const __grid_constant__ CUte
   __nv_bfloat16* lut_out = lut_in + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = P.tiles_n * P.tiles_m;
-  const int kblocks = (P.K + WBK - 1) / WBK;
+  const int num_tiles = P.tiles_n * P.tiles_m * P.ksplit;
+  const int kblocks_total = (P.K + WBK - 1) / WBK;
 
   if (warp == 0 && lane == 0) tc::tma_prefetch_desc(&tmX);
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < WSTAGES; ++i) { tc::mbar_init(&full[i], 1 + 128); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < WSTAGES; ++i) { tc::mbar_init(&full[i], 1 + 256); tc::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
     tc::mbar_fence_init();
   }
@@ -72,14 +74,21 @@ __global__ void __launch_bounds__(384, 1) k_gemm_w4(const __grid_constant__ CUte
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto tile_coords = [&](int t, int& tn, int& tm) { tm = t / P.tiles_n; tn = t - tm * P.tiles_n; };
+  // tile index -> (n tile, m tile, first K block, number of K blocks)
+  auto tile_coords = [&](int t, int& tn, int& tm, int& kb0, int& nkb) {
+    const int ks = t % P.ksplit;
+    const int r = t / P.ksplit;
+    tm = r / P.tiles_n; tn = r - tm * P.tiles_n;
+    kb0 = ks * P.kb_per_split;
+    nkb = min(P.kb_per_split, kblocks_total - kb0);
+  };
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int tn, tm; tile_coords(t, tn, tm);
-        for (int kb = 0; kb < kblocks; ++kb) {
+        int tn, tm, kb0, nkb; tile_coords(t, tn, tm, kb0, nkb);
+        for (int kb = kb0; kb < kb0 + nkb; ++kb) {
           tc::mbar_wait(&empty[stage], phase ^ 1);
           tc::mbar_expect_tx(&full[stage], (uint32_t)(P.bnx * WBK * 2));
           tc::tma_load_2d(sB + stage * WB_BYTES, &tmX, &full[stage], kb * WBK, tm * P.bnx);
@@ -93,10 +102,11 @@ __global__ void __launch_bounds__(384, 1) k_gemm_w4(const __grid_constant__ CUte
       int stage = 0; uint32_t phase = 0;
       int buf = 0; uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int tn, tm, kb0, nkb; tile_coords(t, tn, tm, kb0, nkb);
         tc::mbar_wait(&acc_empty[buf], acc_phase ^ 1);
         tc::tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(buf * WMAXN);
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           tc::mbar_wait(&full[stage], phase);
           tc::tc_fence_after();
           const uint64_t ad = tc::make_kmajor_sw128_desc(tc::smem_u32(sA + stage * WA_BYTES));
@@ -112,70 +122,97 @@ __global__ void __launch_bounds__(384, 1) k_gemm_w4(const __grid_constant__ CUte
       }
     }
   } else if (warp >= 8) {
-    // ---- weight dequant producers: 128 threads, 8 chunks (of 8 elements = 16 B of bf16) each per stage
+    // ---- weight dequant producers: 256 threads, 4 chunks (8 elements = 16 B of bf16) each per stage.
+    // The packed bytes of stage s+1 are fetched into registers before stage s is converted, so the
+    // global-load latency overlaps the LUT/scale arithmetic.
     const int ptid = threadIdx.x - 256;
     const int wi = P.wi;
     const long long code_row_bytes = ((long long)P.K * wi) >> 3;
     const int kblk32 = P.K >> 5;                        // MX blocks per weight row
-    int stage = 0; uint32_t phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      int tn, tm; tile_coords(t, tn, tm);
-      const int n0 = tn * WM;
-      for (int kb = 0; kb < kblocks; ++kb) {
-        tc::mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* dst = sA + stage * WA_BYTES;
-#pragma unroll 2
-        for (int i = 0; i < 8; ++i) {
-          const int c = ptid + 128 * i;
-          const int r = c >> 3, kc = c & 7;
-          const int n = n0 + r, k = kb * WBK + kc * 8;
-          uint4 outv = make_uint4(0, 0, 0, 0);
-          if (n < P.N && k < P.K) {
-            // 8 codes
-            uint32_t cw0, cw1 = 0;
-            const uint8_t* cp = P.codes + (long long)n * code_row_bytes + (((long long)k * wi) >> 3);
-            if (wi == 4) cw0 = __ldg(reinterpret_cast<const uint32_t*>(cp));
-            else if (wi == 2) cw0 = __ldg(reinterpret_cast<const uint16_t*>(cp));
-            else { const uint2 v = __ldg(reinterpret_cast<const uint2*>(cp)); cw0 = v.x; cw1 = v.y; }
-            uint32_t ob = 0;
-            const int blk = n * kblk32 + (k >> 5);
-            const int ei = P.e_in[blk];
-            int eo = 0;
-            if (!P.plain) {
-              ob = (__ldg(P.bitmap + (((long long)n * P.K + k) >> 5)) >> (k & 31)) & 0xFFu;
-              eo = P.e_out[blk];
-            }
-            const bool nan_blk = ei == MSQ_EXP_NAN || eo == MSQ_EXP_NAN;
-            // inlier: q * 2^e_in ; outlier: q * 2^(e_out - e_in)   (both exact in bf16)
-            const __nv_bfloat16 s_in = __float2bfloat16_rn(nan_blk ? qnan() : pow2i(ei));
-            const int eoi = max(-126, min(127, eo - ei));
-            const __nv_bfloat16 s_out = __float2bfloat16_rn(nan_blk ? qnan() : pow2i(eoi));
-            uint32_t packed[4];
+    struct Raw { uint32_t c0, c1, ob; int ei, eo; };
+    auto fetch = [&](int n0, int kb, Raw (&raw)[4]) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              uint32_t code;
-              if (wi == 8) code = ((e < 4 ? cw0 : cw1) >> ((e & 3) * 8)) & 0xFFu;
-              else code = (cw0 >> (e * wi)) & ((1u << wi) - 1u);
-              const bool isout = (ob >> e) & 1u;
-              const __nv_bfloat16 q = isout ? lut_out[code] : lut_in[code];
-              const __nv_bfloat16 v = __hmul(q, isout ? s_out : s_in);
-              const uint32_t bits = (uint32_t)__bfloat16_as_ushort(v);
-              if (e & 1) packed[e >> 1] |= bits << 16; else packed[e >> 1] = bits;
-            }
-            outv = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      for (int i = 0; i < 4; ++i) {
+        const int c = ptid + 256 * i;
+        const int r = c >> 3, kc = c & 7;
+        const int n = n0 + r, k = kb * WBK + kc * 8;
+        raw[i].c0 = raw[i].c1 = raw[i].ob = 0; raw[i].ei = 0; raw[i].eo = 0;
+        if (n < P.N && k < P.K) {
+          const uint8_t* cp = P.codes + (long long)n * code_row_bytes + (((long long)k * wi) >> 3);
+          if (wi == 4) raw[i].c0 = __ldg(reinterpret_cast<const uint32_t*>(cp));
+          else if (wi == 2) raw[i].c0 = __ldg(reinterpret_cast<const uint16_t*>(cp));
+          else { const uint2 v = __ldg(reinterpret_cast<const uint2*>(cp)); raw[i].c0 = v.x; raw[i].c1 = v.y; }
+          const int blk = n * kblk32 + (k >> 5);
+          raw[i].ei = P.e_in[blk];
+          if (!P.plain) {
+            raw[i].ob = (__ldg(P.bitmap + (((long long)n * P.K + k) >> 5)) >> (k & 31)) & 0xFFu;
+            raw[i].eo = P.e_out[blk];
           }
-          *reinterpret_cast<uint4*>(dst + r * 128 + ((kc ^ (r & 7)) << 4)) = outv;
+        } else {
+          raw[i].ei = 1 << 20;                          // marker: out of range -> zeros
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        tc::mbar_arrive(&full[stage]);
-        if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
       }
+    };
+    auto convert = [&](uint8_t* dst, const Raw (&raw)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = ptid + 256 * i;
+        const int r = c >> 3, kc = c & 7;
+        uint4 outv = make_uint4(0, 0, 0, 0);
+        if (raw[i].ei != (1 << 20)) {
+          const int ei = raw[i].ei, eo = raw[i].eo;
+          const bool nan_blk = ei == MSQ_EXP_NAN || eo == MSQ_EXP_NAN;
+          // inlier: q * 2^e_in ; outlier: q * 2^(e_out - e_in)   (both exact in bf16)
+          const __nv_bfloat16 s_in = __float2bfloat16_rn(nan_blk ? qnan() : pow2i(ei));
+          const int eoi = max(-126, min(127, eo - ei));
+          const __nv_bfloat16 s_out = __float2bfloat16_rn(nan_blk ? qnan() : pow2i(eoi));
+          uint32_t packed[4];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            uint32_t code;
+            if (wi == 8) code = ((e < 4 ? raw[i].c0 : raw[i].c1) >> ((e & 3) * 8)) & 0xFFu;
+            else code = (raw[i].c0 >> (e * wi)) & ((1u << wi) - 1u);
+            const bool isout = (raw[i].ob >> e) & 1u;
+            const __nv_bfloat16 q = isout ? lut_out[code] : lut_in[code];
+            const __nv_bfloat16 v = __hmul(q, isout ? s_out : s_in);
+            const uint32_t bits = (uint32_t)__bfloat16_as_ushort(v);
+            if (e & 1) packed[e >> 1] |= bits << 16; else packed[e >> 1] = bits;
+          }
+          outv = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+        *reinterpret_cast<uint4*>(dst + r * 128 + ((kc ^ (r & 7)) << 4)) = outv;
+      }
+    };
+    int stage = 0; uint32_t phase = 0;
+    Raw cur[4], nxt[4];
+    int t = blockIdx.x;
+    int tn = 0, tm = 0, kb0 = 0, nkb = 0, kb = 0;
+    bool have = t < num_tiles;
+    if (have) { tile_coords(t, tn, tm, kb0, nkb); fetch(tn * WM, kb0, cur); }
+    while (have) {
+      // locate the next (tile, kb) and prefetch it
+      int t2 = t, tn2 = tn, tm2 = tm, kb02 = kb0, nkb2 = nkb, kb2 = kb + 1;
+      bool have2 = true;
+      if (kb2 >= nkb) {
+        t2 = t + gridDim.x; kb2 = 0;
+        have2 = t2 < num_tiles;
+        if (have2) tile_coords(t2, tn2, tm2, kb02, nkb2);
+      }
+      if (have2) fetch(tn2 * WM, kb02 + kb2, nxt);
+      tc::mbar_wait(&empty[stage], phase ^ 1);
+      convert(sA + stage * WA_BYTES, cur);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc::mbar_arrive(&full[stage]);
+      if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+      t = t2; tn = tn2; tm = tm2; kb0 = kb02; nkb = nkb2; kb = kb2; have = have2;
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
     int buf = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      int tn, tm; tile_coords(t, tn, tm);
+      int tn, tm, kb0, nkb; tile_coords(t, tn, tm, kb0, nkb);
       tc::mbar_wait(&acc_full[buf], acc_phase);
       tc::tc_fence_after();
       const int n = tn * WM + q * 32 + lane;
@@ -196,7 +233,8 @@ __global__ void __launch_bounds__(384, 1) k_gemm_w4(const __grid_constant__ CUte
             if (m < P.M) {
               float* p = P.C + (long long)m * P.ldc + n;
               const float val = __uint_as_float(r[v]);
-              *p = P.accumulate ? (*p + val) : val;
+              if (P.ksplit > 1) atomicAdd(p, val);
+              else *p = P.accumulate ? (*p + val) : val;
             }
           }
         }
@@ -241,6 +279,19 @@ int msq_gemm_packed_w_bf16(const void* X, long long ldx, const unsigned char* co
   P.wi = fi.width; P.in_ebits = in_ebits; P.in_bits = in_mbits;
   P.out_ebits = plain ? in_ebits : out_ebits; P.out_bits = plain ? in_mbits : out_mbits;
   P.plain = plain; P.accumulate = accumulate;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // split K until the grid covers the SMs (each slice keeps at least 8 K-blocks of 64)
+  const int kblocks_total = (K + WBK - 1) / WBK;
+  int ksplit = 1;
+  while (P.tiles_n * P.tiles_m * ksplit * 2 <= sms && kblocks_total / (ksplit * 2) >= 8) ksplit *= 2;
+  P.ksplit = ksplit;
+  P.kb_per_split = (kblocks_total + ksplit - 1) / ksplit;
+  if (ksplit > 1 && !accumulate) {
+    if (ldc == N) cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), (cudaStream_t)stream);
+    else cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, (cudaStream_t)stream);
+  }
   CUtensorMap tmX;
   int rc = make_tmap_2d(&tmX, X, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, ldx, bnx, WBK);
   if (rc) return rc;
@@ -249,12 +300,9 @@ int msq_gemm_packed_w_bf16(const void* X, long long ldx, const unsigned char* co
     if (cudaFuncSetAttribute(k_gemm_w4, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
     attr_set = true;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int grid = P.tiles_n * P.tiles_m;
+  int grid = P.tiles_n * P.tiles_m * P.ksplit;
   if (grid > sms) grid = sms;
-  k_gemm_w4<<<grid, 384, W4_SMEM, (cudaStream_t)stream>>>(tmX, P);
+  k_gemm_w4<<<grid, 512, W4_SMEM, (cudaStream_t)stream>>>(tmX, P);
   return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
 }
 

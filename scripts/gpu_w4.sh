@@ -16,7 +16,7 @@ for K in (4096, 8192):
     W = torch.randn(N, K, device='cuda')*0.02
     pw = msq_b200.pack_mx_outlier(W, 8,8,'fp4_e2m1','fp4_e2m1',5,[1],32, variant=1)
     wb = pw.dequantize(torch.bfloat16)
-    for Mx in (16, 1024, 8192):
+    for Mx in (1, 16, 64, 256, 511):
         x = torch.randn(Mx, K, device='cuda').to(torch.bfloat16)
         ms = timeit(lambda: _tc.packed_linear(x, pw))
         ms2 = timeit(lambda: torch.matmul(x, wb.t()))
