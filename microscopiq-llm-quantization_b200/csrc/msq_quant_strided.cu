@@ -14,7 +14,7 @@
 namespace msq {
 
 template <int BS, bool OUTLIER, bool PACK, bool EXT, bool CNT>
-__global__ void __launch_bounds__(256, (BS <= 16 ? 3 : 1)) k_strided(const QParams P) {
+__global__ void __launch_bounds__(256, (BS <= 16 ? 4 : 1)) k_strided(const QParams P) {
   extern __shared__ uint32_t s_hi[];
   __shared__ int s_warp[8];
   __shared__ int s_base;
