@@ -1,0 +1,217 @@
+"""Layer-sequential GPTQ / RTN drivers and perplexity evaluation -- the callers of the hot path
+(SURVEY 8f rows 1-2): llm/llama.py:62-173 (llama_sequential), :176-284 (llama_eval, incl. the
+`--nearest` RTN branch :226-253), llm/opt.py:26-128 (opt_sequential).
+
+One implementation serves every HF decoder stack: the first decoder layer is wrapped in a Catcher that
+records its positional input and *all* keyword arguments (attention mask, position ids, rotary
+`position_embeddings` of transformers >= 4.48, cache position ...) and those are replayed for every layer,
+so the driver does not depend on one transformers version (the reference's llama.py does: SURVEY 7).
+The quantizer configuration is an argument (the reference hard-codes int2/fp4/block 16, llama.py:130-137).
+"""
+import time
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+from ..utils.modelutils import find_layers
+from ..utils.quant import MXQuantizer, quantize_mx_outlier_v1
+from .gptq import GPTQ
+
+#: the reference's hard-coded quantizer (llm/llama.py:130-137)
+REFERENCE_QCFG = dict(inlier_scale_bits=8, outlier_scale_bits=8, inlier_elem_format="int2", outlier_elem_format="fp4",
+                      axes=[0], block_size=16)
+
+LLAMA_TRUE_SEQUENTIAL = [["self_attn.k_proj", "self_attn.v_proj", "self_attn.q_proj"], ["self_attn.o_proj"],
+                         ["mlp.up_proj", "mlp.gate_proj"], ["mlp.down_proj"]]
+
+
+def decoder_parts(model):
+    """(layers ModuleList, modules that run before layer 0, final norm or None, lm_head)"""
+    if hasattr(model, "model") and hasattr(model.model, "layers"):                       # LLaMA / Mistral
+        pre = [m for m in (model.model.embed_tokens, getattr(model.model, "rotary_emb", None)) if m is not None]
+        return model.model.layers, pre, model.model.norm, model.lm_head
+    if hasattr(model, "model") and hasattr(model.model, "decoder"):                      # OPT
+        d = model.model.decoder
+        pre = [m for m in (d.embed_tokens, d.embed_positions, getattr(d, "project_in", None)) if m is not None]
+        post = [m for m in (getattr(d, "final_layer_norm", None), getattr(d, "project_out", None)) if m is not None]
+        return d.layers, pre, (nn.Sequential(*post) if post else None), model.lm_head
+    raise TypeError("unsupported model type %s" % type(model))
+
+
+class _Stop(Exception):
+    pass
+
+
+class Catcher(nn.Module):
+    def __init__(self, module, store):
+        super().__init__()
+        self.module, self.store = module, store
+
+    def forward(self, inp, *args, **kwargs):
+        self.store["inps"].append(inp.detach())
+        self.store["args"], self.store["kwargs"] = args, kwargs
+        raise _Stop
+
+
+@torch.no_grad()
+def capture_layer_inputs(model, batches, dev):
+    """run the embedding part on every calibration batch and stop at decoder layer 0"""
+    layers, pre, _, _ = decoder_parts(model)
+    for m in pre:
+        m.to(dev)
+    layers[0] = layers[0].to(dev)
+    store = {"inps": [], "args": (), "kwargs": {}}
+    layers[0] = Catcher(layers[0], store)
+    use_cache = model.config.use_cache
+    model.config.use_cache = False
+    try:
+        for batch in batches:
+            ids = batch[0] if isinstance(batch, (tuple, list)) else batch
+            try:
+                model(ids.to(dev))
+            except _Stop:
+                pass
+    finally:
+        layers[0] = layers[0].module
+        model.config.use_cache = use_cache
+    layers[0] = layers[0].cpu()
+    for m in pre:
+        m.cpu()
+    inps = torch.cat(store["inps"], 0)
+    return inps, store["args"], store["kwargs"]
+
+
+def _run_layer(layer, x, args, kwargs):
+    out = layer(x, *args, **kwargs)
+    return out[0] if isinstance(out, (tuple, list)) else out
+
+
+@torch.no_grad()
+def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=.01, groupsize=-1, act_order=False,
+                        static_groups=False, true_sequential=False, hessian_batch=8, verbose=False, stats=None):
+    """llama_sequential / opt_sequential (llm/llama.py:62-173, llm/opt.py:26-128).
+    nearest=True is the RTN branch (llm/llama.py:226-253): every linear is replaced by
+    quantize_mx_outlier_v1(W) without calibration.  Returns {layer name: quantizer}."""
+    qcfg = dict(REFERENCE_QCFG if qcfg is None else qcfg)
+    layers, _, _, _ = decoder_parts(model)
+    stats = stats if stats is not None else {}
+    stats.update(hessian_s=0.0, solve_s=0.0, forward_s=0.0, linears=0)
+    quantizers = {}
+    if nearest:
+        for i in range(len(layers)):
+            layer = layers[i].to(dev)
+            for name, lin in find_layers(layer).items():
+                q = MXQuantizer()
+                q.configure(**qcfg)
+                W = lin.weight.data
+                lin.weight.data = quantize_mx_outlier_v1(W.float(), q.inlier_scale_bits, q.outlier_scale_bits,
+                                                         q.inlier_elem_format, q.outlier_elem_format, q.shared_exp_method,
+                                                         q.std_dev, q.axes, q.block_size, q.round, q.flush_fp32_subnorms,
+                                                         q.custom_cuda).to(W.dtype)
+                quantizers["layers.%d.%s" % (i, name)] = q
+                stats["linears"] += 1
+            layers[i] = layer.cpu()
+        return quantizers
+
+    inps, args, kwargs = capture_layer_inputs(model, batches, dev)
+    outs = torch.zeros_like(inps)
+    nsamples = inps.shape[0]
+    GPTQ.verbose = verbose
+    for i in range(len(layers)):
+        layer = layers[i].to(dev)
+        full = find_layers(layer)
+        if true_sequential and all(n in full for grp in LLAMA_TRUE_SEQUENTIAL for n in grp):
+            sequential = LLAMA_TRUE_SEQUENTIAL
+        else:
+            sequential = [list(full.keys())]
+        for names in sequential:
+            subset = {n: full[n] for n in names}
+            gptq = {}
+            for name in subset:
+                gptq[name] = GPTQ(subset[name])
+                gptq[name].hessian_batch = hessian_batch
+                gptq[name].quantizer = MXQuantizer()
+                gptq[name].quantizer.configure(**qcfg)
+
+            def add_batch(name):
+                def tmp(_, inp, out):
+                    gptq[name].add_batch(inp[0].data, out.data)
+                return tmp
+            handles = [subset[name].register_forward_hook(add_batch(name)) for name in subset]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for j in range(nsamples):
+                outs[j] = _run_layer(layer, inps[j].unsqueeze(0), args, kwargs)
+            for name in subset:
+                _ = gptq[name].H                     # flush buffered activations
+            torch.cuda.synchronize()
+            stats["hessian_s"] += time.perf_counter() - t0
+            for h in handles:
+                h.remove()
+            t0 = time.perf_counter()
+            for name in subset:
+                gptq[name].fasterquant(percdamp=percdamp, groupsize=groupsize, actorder=act_order,
+                                       static_groups=static_groups)
+                quantizers["layers.%d.%s" % (i, name)] = gptq[name].quantizer
+                gptq[name].free()
+                stats["linears"] += 1
+            torch.cuda.synchronize()
+            stats["solve_s"] += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for j in range(nsamples):
+            outs[j] = _run_layer(layer, inps[j].unsqueeze(0), args, kwargs)
+        torch.cuda.synchronize()
+        stats["forward_s"] += time.perf_counter() - t0
+        layers[i] = layer.cpu()
+        del layer, gptq
+        inps, outs = outs, inps
+    return quantizers
+
+
+@torch.no_grad()
+def perplexity(model, token_ids, dev, seqlen=None):
+    """llama_eval's arithmetic (llm/llama.py:266-282): exp(mean token NLL) over consecutive windows of
+    `seqlen` tokens, decoder layers streamed through the device one at a time."""
+    seqlen = seqlen or getattr(model, "seqlen", 2048)
+    token_ids = token_ids.reshape(1, -1)
+    nsamples = token_ids.numel() // seqlen
+    batches = [token_ids[:, i * seqlen:(i + 1) * seqlen] for i in range(nsamples)]
+    layers, _, norm, lm_head = decoder_parts(model)
+    inps, args, kwargs = capture_layer_inputs(model, batches, dev)
+    outs = torch.zeros_like(inps)
+    for i in range(len(layers)):
+        layer = layers[i].to(dev)
+        for j in range(nsamples):
+            outs[j] = _run_layer(layer, inps[j].unsqueeze(0), args, kwargs)
+        layers[i] = layer.cpu()
+        inps, outs = outs, inps
+    if norm is not None:
+        norm.to(dev)
+    lm_head.to(dev)
+    nlls = []
+    for i in range(nsamples):
+        h = inps[i].unsqueeze(0)
+        if norm is not None:
+            h = norm(h)
+        logits = lm_head(h)
+        shift_logits = logits[:, :-1, :].contiguous().float()
+        shift_labels = batches[i][:, 1:].to(dev)
+        loss = nn.CrossEntropyLoss()(shift_logits.view(-1, shift_logits.size(-1)), shift_labels.reshape(-1))
+        nlls.append(loss.float() * seqlen)
+    if norm is not None:
+        norm.cpu()
+    lm_head.cpu()
+    return float(torch.exp(torch.stack(nlls).sum() / (nsamples * seqlen)))
+
+
+def llama_sequential(model, dataloader, dev, args=None):
+    """signature of llm/llama.py:62; `args` replaces the reference's module-global argparse namespace"""
+    a = args or SimpleNamespace()
+    return sequential_quantize(model, dataloader, dev, nearest=getattr(a, "nearest", False),
+                               percdamp=getattr(a, "percdamp", .01), groupsize=getattr(a, "groupsize", -1),
+                               act_order=getattr(a, "act_order", False), static_groups=getattr(a, "static_groups", False),
+                               true_sequential=getattr(a, "true_sequential", False))
+
+
+opt_sequential = llama_sequential
