@@ -17,7 +17,7 @@
 namespace msq {
 
 constexpr int GB = 128;          // GPTQ block width (blocksize of gptq.py:61)
-constexpr int TS = GB + 1;       // smem row stride
+constexpr int TS = GB + 4;       // smem row stride: 16-byte aligned rows, float4 row updates conflict free
 
 struct GptqParams {
   const float* W; long long ldw;     // [rows, >= i1+count] current weights
@@ -33,9 +33,10 @@ struct GptqParams {
 
 template <int BS>
 __global__ void __launch_bounds__(32) k_gptq_block(const GptqParams P) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* tile = sm;                 // [32][TS]  W1 -> Q1
   float* etile = sm + 32 * TS;      // [32][TS]  Err1
+  float* hs = sm + 64 * TS;         // [128][GB] Hinv1 = Hinv[i1:i1+count, i1:i1+count] (zero padded)
   const int lane = threadIdx.x;
   const int r0 = blockIdx.x * 32;
   const int row = r0 + lane;
@@ -52,16 +53,25 @@ __global__ void __launch_bounds__(32) k_gptq_block(const GptqParams P) {
       etile[rr * TS + j] = 0.0f;
     }
   }
+  for (int rr = 0; rr < GB; ++rr) {
+    const float* src = P.Hinv + (long long)(P.i1 + rr) * P.ldh + P.i1;
+#pragma unroll
+    for (int c = 0; c < GB / 32; ++c) {
+      const int j = lane + 32 * c;
+      hs[rr * GB + j] = (rr < count && j < count) ? __ldg(src + j) : 0.0f;
+    }
+  }
   __syncwarp();
 
   double loss = 0.0;
   int st = 0;
   const bool counts_for_k = ((row / BS) % BS) == 0;      // quant.py:66  outlier_pos[::block_size]
+  float* trow = tile + lane * TS;
 #pragma unroll 1
   for (int i = 0; i < count; ++i) {
-    const float* hrow = P.Hinv + (long long)(P.i1 + i) * P.ldh + P.i1;
-    const float d = __ldg(hrow + i);
-    const float w = tile[lane * TS + i];
+    const float* hrow = hs + i * GB;
+    const float d = hrow[i];
+    const float w = trow[i];
     float x[1] = {active ? w : 0.0f};
     uint32_t code[1];
     const BlockOut bo = core_outlier<1, BS, false, false>(x, code, P.c, nullptr, nullptr);
@@ -73,11 +83,22 @@ __global__ void __launch_bounds__(32) k_gptq_block(const GptqParams P) {
     const float diff = __fsub_rn(w, q);
     const float err = __fdiv_rn(diff, d);
     if (active) loss += (double)__fdiv_rn(__fmul_rn(diff, diff), __fmul_rn(d, d));
-    tile[lane * TS + i] = q;
+    trow[i] = q;
     etile[lane * TS + i] = active ? err : 0.0f;
+    // W1[:, j] -= err * Hinv1[i, j] for j > i (gptq.py:159): scalar head up to the next multiple of 4,
+    // then 128-bit row updates (Hinv1 row is a shared-memory broadcast)
+    const int j4 = min((i + 4) & ~3, count);
+    for (int j = i + 1; j < j4; ++j) trow[j] = __fsub_rn(trow[j], __fmul_rn(err, hrow[j]));
 #pragma unroll 4
-    for (int j = i + 1; j < count; ++j)
-      tile[lane * TS + j] = __fsub_rn(tile[lane * TS + j], __fmul_rn(err, __ldg(hrow + j)));
+    for (int j = j4; j < count; j += 4) {
+      float4 t = *reinterpret_cast<float4*>(trow + j);
+      const float4 h = *reinterpret_cast<const float4*>(hrow + j);
+      t.x = __fsub_rn(t.x, __fmul_rn(err, h.x));
+      t.y = __fsub_rn(t.y, __fmul_rn(err, h.y));
+      t.z = __fsub_rn(t.z, __fmul_rn(err, h.z));
+      t.w = __fsub_rn(t.w, __fmul_rn(err, h.w));
+      *reinterpret_cast<float4*>(trow + j) = t;
+    }
   }
   __syncwarp();
 
@@ -183,12 +204,20 @@ int msq_gptq_block(const float* W, long long ldw, float* Q, long long ldq, const
   P.c.sb_in = in_scale_bits; P.c.sb_out = out_scale_bits; P.c.std_dev = std_dev; P.c.flush = flush_fp32_subnorms;
   P.c.variant = 0; P.c.mode = 0; P.c.rmode = rmode;
   const unsigned grid = (unsigned)((rows + 31) / 32);
-  const size_t smem = 2 * 32 * TS * sizeof(float);
+  const size_t smem = (2 * 32 * TS + GB * GB) * sizeof(float);
   cudaStream_t s = (cudaStream_t)stream;
-  if (block_size == 16) k_gptq_block<16><<<grid, 32, smem, s>>>(P);
-  else if (block_size == 32) k_gptq_block<32><<<grid, 32, smem, s>>>(P);
-  else if (block_size == 8) k_gptq_block<8><<<grid, 32, smem, s>>>(P);
+  void (*k)(const GptqParams) = nullptr;
+  if (block_size == 16) k = k_gptq_block<16>;
+  else if (block_size == 32) k = k_gptq_block<32>;
+  else if (block_size == 8) k = k_gptq_block<8>;
   else return MSQ_ERR_UNSUPPORTED;
+  static bool attr_done[3] = {false, false, false};
+  const int ki = block_size == 16 ? 0 : (block_size == 32 ? 1 : 2);
+  if (!attr_done[ki]) {
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MSQ_ERR_CUDA;
+    attr_done[ki] = true;
+  }
+  k<<<grid, 32, smem, s>>>(P);
   return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
 }
 

@@ -28,6 +28,21 @@ template <int LPB> __device__ __forceinline__ double grp_sum(double v) {
   for (int o = LPB / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// fp32 sum over the LPB lanes in canonical tree order: partner distance 1, 2, 4, ... continues the
+// in-thread adjacent pairwise tree (commutativity makes every lane end with the same value)
+template <int LPB> __device__ __forceinline__ float grp_sum_tree(float v) {
+#pragma unroll
+  for (int o = 1; o < LPB; o <<= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// in-thread adjacent pairwise tree over N (power of two) values; destroys t[]
+template <int N> __device__ __forceinline__ float tree_sum_regs(float (&t)[N]) {
+#pragma unroll
+  for (int stride = 1; stride < N; stride <<= 1)
+#pragma unroll
+    for (int i = 0; i + stride < N; i += 2 * stride) t[i] = __fadd_rn(t[i], t[i + stride]);
+  return t[0];
+}
 template <int LPB> __device__ __forceinline__ float grp_max(float v) {
 #pragma unroll
   for (int o = LPB / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -169,21 +184,20 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
   int bad = 0;
   float l = 0.0f, h = 0.0f;
   if (!EXT) {
-    double s = 0.0;
+    // mean(|A|), std(|A|) of utils/quant.py:477-478: fp32, two-pass, canonical pairwise-tree order
+    float t[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) s += (double)fabsf(x[i]);
-    s = grp_sum<LPB>(s);
-    bad = !(s <= 1.0e300);            // an Inf or NaN element makes the fp64 sum non-finite
-    const double mean64 = s / (double)BS;
-    double q = 0.0;
+    for (int i = 0; i < N; ++i) t[i] = fabsf(x[i]);
+    const float s = grp_sum_tree<LPB>(tree_sum_regs<N>(t));
+    bad = !(s <= 3.402823466e38f);    // an Inf/NaN element (or an overflowing sum) makes it non-finite
+    const float mean = __fdiv_rn(s, (float)BS);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const double d = (double)fabsf(x[i]) - mean64;
-      q = fma(d, d, q);
+      const float d = __fsub_rn(fabsf(x[i]), mean);
+      t[i] = __fmul_rn(d, d);
     }
-    q = grp_sum<LPB>(q);
-    const float mean = (float)mean64;
-    const float sd = (float)sqrt(q / (double)BS);
+    const float q = grp_sum_tree<LPB>(tree_sum_regs<N>(t));
+    const float sd = __fsqrt_rn(__fdiv_rn(q, (float)BS));
     const float w = __fmul_rn(c.std_dev, sd);
     l = __fsub_rn(mean, w); h = __fadd_rn(mean, w);
   } else {

@@ -22,12 +22,10 @@ __global__ void __launch_bounds__(256) k_generic(const QParams P) {
   int st = 0;
   int bad = 0;
   float m = 0.0f;
-  double s = 0.0;
   for (int i = 0; i < nv; ++i) {
     float a = fabsf(__ldg(P.in + base + (long long)i * P.post));
     bad |= !(a <= 3.402823466e38f);
     m = fmaxf(m, a);
-    s += (double)a;
   }
   if (!OUTLIER) {
     // plain MX through the shared core, one element at a time
@@ -47,15 +45,30 @@ __global__ void __launch_bounds__(256) k_generic(const QParams P) {
   }
   float lo = 0.f, hi = 0.f;
   if (c.variant == 0) {
-    const double mean64 = s / (double)bs;
-    double q = 0.0;
-    for (int i = 0; i < nv; ++i) {
-      double d = (double)fabsf(__ldg(P.in + base + (long long)i * P.post)) - mean64;
-      q = fma(d, d, q);
-    }
-    for (int i = nv; i < bs; ++i) q = fma(-mean64, -mean64, q);   // padding zeros
-    const float mean = (float)mean64;
-    const float sd = (float)sqrt(q / (double)bs);
+    // canonical fp32 pairwise-tree sums over the bs block entries (binary-counter form: identical
+    // association to the adjacent tree with the summands zero-padded to a power of two)
+    float lvl[32];
+    auto tree_total = [&](auto term) {
+      unsigned cnt = 0;
+      for (int i = 0; i < bs; ++i) {
+        float carry = term(i);
+        int l = 0;
+        for (unsigned cc = cnt; cc & 1u; cc >>= 1, ++l) carry = __fadd_rn(lvl[l], carry);
+        lvl[l] = carry;
+        ++cnt;
+      }
+      float acc = 0.0f;
+      bool have = false;
+      for (int l = 0; l < 32; ++l)
+        if ((cnt >> l) & 1u) { acc = have ? __fadd_rn(lvl[l], acc) : lvl[l]; have = true; }
+      return acc;
+    };
+    auto absval = [&](int i) { return i < nv ? fabsf(__ldg(P.in + base + (long long)i * P.post)) : 0.0f; };
+    const float ssum = tree_total(absval);
+    if (!(ssum <= 3.402823466e38f)) bad = 1;
+    const float mean = __fdiv_rn(ssum, (float)bs);
+    const float q = tree_total([&](int i) { const float d = __fsub_rn(absval(i), mean); return __fmul_rn(d, d); });
+    const float sd = __fsqrt_rn(__fdiv_rn(q, (float)bs));
     const float w = __fmul_rn(c.std_dev, sd);
     lo = __fsub_rn(mean, w); hi = __fadd_rn(mean, w);
   }

@@ -45,6 +45,11 @@ class GPTQ:
     hessian_batch = 1
     #: print 'time' / 'error' like the reference (gptq.py:174-175)
     verbose = True
+    #: how the upper Cholesky factor of H^-1 is obtained.  "reference": cholesky -> cholesky_inverse ->
+    #: cholesky(upper), exactly gptq.py:101-103.  "flip": the same matrix from ONE Cholesky of the
+    #: row/column-reversed H plus a triangular inverse (H = R R^T with R upper => H^-1 = (R^-1)^T R^-1),
+    #: about half the time; agrees with the reference route to ~1e-6..1e-5 relative.
+    hinv_method = "reference"
 
     def __init__(self, layer):
         self.layer = layer
@@ -167,9 +172,13 @@ class GPTQ:
         damp = percdamp * torch.mean(torch.diag(H))
         diag = torch.arange(self.columns, device=self.dev)
         H[diag, diag] += damp
-        H = torch.linalg.cholesky(H)
-        H = torch.cholesky_inverse(H)
-        H = torch.linalg.cholesky(H, upper=True)
+        if self.hinv_method == "flip":
+            R = torch.linalg.cholesky(H.flip(0, 1)).flip(0, 1)          # upper, H = R R^T
+            H = torch.linalg.solve_triangular(R, torch.eye(self.columns, device=self.dev, dtype=R.dtype), upper=True)
+        else:
+            H = torch.linalg.cholesky(H)
+            H = torch.cholesky_inverse(H)
+            H = torch.linalg.cholesky(H, upper=True)
         Hinv = H.contiguous()
 
         Q = None
