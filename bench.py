@@ -97,23 +97,36 @@ def extras(dev, dev_w, nel):
     import msq_b200
     from msq_b200 import _tc
     out = {}
-    # (1) quantize + pack, same 7 linears, algorithmic bytes = 4 B read + packed bytes written
-    packed_bytes = [0]
+    # (1) quantize + pack, same 7 linears, kernel time through the C ABI with preallocated planes;
+    #     algorithmic bytes = 4 B read + packed bytes written (hi stream: compacted prefix only)
+    import ctypes as C
+    from msq_b200 import _native as N, _ops, packed
+    fi, fo = _ops.fmt4(QCFG["in_fmt"]), _ops.fmt4(QCFG["out_fmt"])
+    calls, pbytes = [], 0
+    for w in dev_w:
+        pre, L, post = _ops.geometry(w.shape, QCFG["axis"])
+        pl, wi, hi_w, stride, nseg = packed._alloc_planes(w, pre, L, post, QCFG["bs"], fi, fo, False)
+        st = torch.zeros(1, dtype=torch.int32, device=dev)
+        calls.append((w, pre, L, post, pl, st))
+        p = msq_b200.pack_mx_outlier(w, QCFG["in_sb"], QCFG["out_sb"], QCFG["in_fmt"], QCFG["out_fmt"], QCFG["std_dev"],
+                                     [QCFG["axis"]], QCFG["bs"])
+        pbytes += p.nbytes
+        del p
+    path = C.c_int(0)
 
     def pack_all():
-        tot = 0
-        for w in dev_w:
-            p = msq_b200.pack_mx_outlier(w, QCFG["in_sb"], QCFG["out_sb"], QCFG["in_fmt"], QCFG["out_fmt"], QCFG["std_dev"],
-                                         [QCFG["axis"]], QCFG["bs"], check=False)
-            tot += p.codes.numel() + p.e_in.numel() + p.e_out.numel() + p.bitmap.numel() * 4
-        packed_bytes[0] = tot
-    ms = _time_ms(pack_all, 5)
-    p = msq_b200.pack_mx_outlier(dev_w[0], QCFG["in_sb"], QCFG["out_sb"], QCFG["in_fmt"], QCFG["out_fmt"], QCFG["std_dev"],
-                                 [QCFG["axis"]], QCFG["bs"])
-    bpe = p.nbytes / dev_w[0].numel()
+        for w, pre, L, post, pl, st in calls:
+            rc = N.lib().msq_quantize_mx_outlier_f32(
+                N.ptr(w), None, pre, L, post, QCFG["bs"], QCFG["in_sb"], QCFG["out_sb"], fi[0], fi[1], fi[2], fi[3],
+                fo[0], fo[1], fo[2], fo[3], float(QCFG["std_dev"]), 0, 0, 0, None, None, N.ptr(pl["codes"]), N.ptr(pl["e_in"]),
+                N.ptr(pl["e_out"]), N.ptr(pl["bitmap"]), N.ptr(pl["hi"]), N.ptr(pl["seg_cnt"]), None, None, N.ptr(st),
+                C.byref(path), N.stream_ptr(dev))
+            assert rc == 0
+    ms = _time_ms(pack_all, 10)
+    bpe = pbytes / nel
     out["pack"] = {"GBps": nel * (4 + bpe) / (ms * 1e-3) / 1e9, "ms_per_layer": ms, "packed_bytes_per_elem": bpe,
                    "frac_of_hbm_peak": nel * (4 + bpe) / (ms * 1e-3) / 1e9 / peaks()[0]}
-    del p
+    del calls
     # (2) GPTQ: Hessian over 128 x 2048 synthetic fp16 tokens + fasterquant for the 7 linears of one layer
     msq_b200.GPTQ.verbose = False
     nsamples, seqlen = 128, 2048

@@ -149,6 +149,41 @@ __device__ __forceinline__ float decode_elem(uint32_t code, int ebits, int bits)
   return ((code >> (cw - 1)) & 1u) ? -v : v;
 }
 
+
+// ---- fast element encoder --------------------------------------------------------------------
+// For a value q that already lies on the format grid, the sign-magnitude code is a shifted slice of
+// the fp32 bits of |q| (floats, normal range), of |q| + min_norm (floats, subnormal range) or of
+// |q| + 2 (integer formats):   mag = (bits(|q| + add) >> sh) - bias_const.
+struct EncC {
+  float thresh;   // |q| < thresh -> "small" path (floats: min_norm; ints: +inf)
+  float addc;     // added on the small path (floats: min_norm; ints: 2.0)
+  int sh;         // 23 - trailing mantissa bits of the code
+  int c_norm;     // subtracted on the normal path
+  int c_sub;      // subtracted on the small path
+  int signbit;    // 1 << (code width - 1)
+};
+__host__ __device__ inline EncC make_enc(int ebits, int bits) {
+  EncC e;
+  if (ebits == 0) {
+    e.thresh = 3.0e38f; e.addc = 2.0f; e.sh = 23 - (bits - 1); e.c_norm = 0; e.c_sub = 128 << (bits - 1);
+    e.signbit = 1 << (bits - 1);
+  } else {
+    const int tm = bits - 2, bias = (1 << (ebits - 1)) - 1;
+    float mn = 1.0f;
+    for (int i = 0; i < bias - 1; ++i) mn *= 0.5f;        // 2^(1-bias)
+    e.thresh = mn; e.addc = mn; e.sh = 23 - tm; e.c_norm = (127 - bias) << tm; e.c_sub = (128 - bias) << tm;
+    e.signbit = 1 << (ebits + tm);
+  }
+  return e;
+}
+__device__ __forceinline__ uint32_t encode_fast(float q, const EncC& e) {
+  const float aq = fabsf(q);
+  const bool small = aq < e.thresh;
+  const int u = __float_as_int(__fadd_rn(aq, small ? e.addc : 0.0f));
+  const int mag = (u >> e.sh) - (small ? e.c_sub : e.c_norm);
+  return (uint32_t)mag | ((q < 0.0f) ? (uint32_t)e.signbit : 0u);
+}
+
 // shared-exponent clamp (quant.py:85-89 / mx_ops.py:270-273).  Returns MSQ_EXP_NAN on overflow.
 __device__ __forceinline__ int clamp_scale_exp(int e, int scale_bits, bool under_to_minus20) {
   int S = (1 << (scale_bits - 1)) - 1;

@@ -250,6 +250,14 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
   const ElemConsts ci = elem_consts(c.fin), co = elem_consts(c.fout);
   const float dL = __fsub_rn(co.L, ci.L), dH = __fsub_rn(co.H, ci.H), dD = __fsub_rn(co.down, ci.down),
               dM = __fsub_rn(co.mx, ci.mx);
+  const EncC enc_i = make_enc(c.fin.ebits, c.fin.bits), enc_o = make_enc(c.fout.ebits, c.fout.bits);
+  auto encode_sel = [&](float qv, bool isout) {
+    EncC e;
+    e.thresh = isout ? enc_o.thresh : enc_i.thresh; e.addc = isout ? enc_o.addc : enc_i.addc;
+    e.sh = isout ? enc_o.sh : enc_i.sh; e.c_norm = isout ? enc_o.c_norm : enc_i.c_norm;
+    e.c_sub = isout ? enc_o.c_sub : enc_i.c_sub; e.signbit = isout ? enc_o.signbit : enc_i.signbit;
+    return encode_fast(qv, e);
+  };
 
   // inlier : v = in * 2^-e_in           ; r = q * 2^e_in                  quant.py:92,102
   // outlier: v = t * 2^-e_out           ; r = (q * 2^e_out) * 2^-e_in     quant.py:125,136
@@ -278,8 +286,8 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
       q.y = fminf(fmaxf(q.y, -M2.y), M2.y);
       const bool o0 = mf[i] != 0.0f, o1 = mf[i + 1] != 0.0f;
       if (CODES) {
-        code[i] = encode_elem(q.x, o0 ? c.fout.ebits : c.fin.ebits, o0 ? c.fout.bits : c.fin.bits);
-        code[i + 1] = encode_elem(q.y, o1 ? c.fout.ebits : c.fin.ebits, o1 ? c.fout.bits : c.fin.bits);
+        code[i] = encode_sel(q.x, o0);
+        code[i + 1] = encode_sel(q.y, o1);
         o.mask |= (o0 ? 1u : 0u) << i;
         o.mask |= (o1 ? 1u : 0u) << (i + 1);
       }
@@ -296,7 +304,7 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
       const float qv = qelem_pair_scalar(v, isout ? co.L : ci.L, isout ? co.H : ci.H, isout ? co.down : ci.down,
                                          isout ? co.mx : ci.mx, rs);
       if (CODES) {
-        code[i] = encode_elem(qv, isout ? c.fout.ebits : c.fin.ebits, isout ? c.fout.bits : c.fin.bits);
+        code[i] = encode_sel(qv, isout);
         o.mask |= (isout ? 1u : 0u) << i;
       }
       const float r = isout ? __fmul_rn(__fmul_rn(qv, s_out), inv_s_in) : __fmul_rn(qv, s_in);
@@ -382,7 +390,7 @@ __device__ __forceinline__ PlainOut core_plain(float (&x)[N], uint32_t (&code)[N
     for (int i = 0; i < N; ++i) {
       float v = __fdiv_rn(flush ? __fmul_rn(x[i], 0.0f) : x[i], den);
       float qv = qelem_rt(v, f, c.rmode);
-      if (want_codes) code[i] = encode_elem(qv, f.ebits, f.bits);
+      if (want_codes) code[i] = encode_fast(qv, make_enc(f.ebits, f.bits));
       x[i] = __fmul_rn(qv, s);
     }
   } else {
@@ -401,7 +409,7 @@ __device__ __forceinline__ PlainOut core_plain(float (&x)[N], uint32_t (&code)[N
     for (int i = 0; i < N; ++i) {
       float v = flush ? 0.0f : __fdiv_rn(x[i], s);
       float qv = qelem_native(v, f.bits, f.ebits, f.max_norm, c.rmode, true, true);
-      if (want_codes) code[i] = (qv == qv) ? encode_elem(qv, f.ebits, f.bits) : 0;
+      if (want_codes) code[i] = (qv == qv) ? encode_fast(qv, make_enc(f.ebits, f.bits)) : 0;
       x[i] = __fmul_rn(qv, s);
     }
   }

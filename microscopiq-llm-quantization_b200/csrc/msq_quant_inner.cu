@@ -83,16 +83,19 @@ __global__ void __launch_bounds__(256) k_inner(const QParams P) {
       int tot;
       const int mine = active ? __popc(bo.mask & 15u) : 0;
       int off = cta_excl_scan(mine, s_warp, &tot);
-      int k = s_base + off;
-      if (active) {
+      if (active && mine) {
+        const int bit0 = (s_base + off) * P.hi_w;
+        int w = bit0 >> 5, b = bit0 & 31;
+        uint32_t cur = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if ((bo.mask >> i) & 1u) {
-            int bit = k * P.hi_w;
-            atomicOr(&s_hi[bit >> 5], (code[i] >> wi) << (bit & 31));
-            ++k;
+            cur |= (code[i] >> wi) << b;
+            b += P.hi_w;
+            if (b == 32) { atomicOr(&s_hi[w], cur); cur = 0; b = 0; ++w; }
           }
         }
+        if (b) atomicOr(&s_hi[w], cur);
       }
       __syncthreads();
       if (threadIdx.x == 0) s_base += tot;

@@ -13,6 +13,20 @@
 
 namespace msq {
 
+// one row of 32 codes (a warp's 32 columns) -> 32*WI bits: lanes combine into 32-bit words
+template <int BS, int WI>
+__device__ __forceinline__ void store_codes(uint8_t* codes, const uint32_t (&code)[BS], int base, int post, int nv, int lane) {
+  constexpr int G = 32 / WI;                 // lanes per 32-bit word
+#pragma unroll
+  for (int i = 0; i < BS; ++i) {
+    uint32_t w = (code[i] & ((1u << WI) - 1u)) << ((lane & (G - 1)) * WI);
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) w |= __shfl_xor_sync(0xffffffffu, w, o);
+    if (i < nv && (lane & (G - 1)) == 0)
+      *reinterpret_cast<uint32_t*>(codes + (((long long)(base + i * post) * WI) >> 3)) = w;
+  }
+}
+
 template <int BS, bool OUTLIER, bool PACK, bool EXT, bool CNT>
 __global__ void __launch_bounds__(256, (BS <= 16 ? 4 : 1)) k_strided(const QParams P) {
   extern __shared__ uint32_t s_hi[];
@@ -89,14 +103,9 @@ __global__ void __launch_bounds__(256, (BS <= 16 ? 4 : 1)) k_strided(const QPara
     }
     if (PACK) {
       // host guarantees post % 32 == 0, so a warp's 32 columns share (p, b) and whole words
-      const int G = 32 / wi;                 // lanes per 32-bit word of codes
-#pragma unroll
-      for (int i = 0; i < BS; ++i) {
-        uint32_t w = (code[i] & ((1u << wi) - 1u)) << ((lane & (G - 1)) * wi);
-        for (int o = 1; o < G; o <<= 1) w |= __shfl_xor_sync(0xffffffffu, w, o);
-        if (i < nv && (lane & (G - 1)) == 0)
-          *reinterpret_cast<uint32_t*>(P.codes + (((long long)(base + i * post) * wi) >> 3)) = w;
-      }
+      if (wi == 4) store_codes<BS, 4>(P.codes, code, base, post, nv, lane);
+      else if (wi == 2) store_codes<BS, 2>(P.codes, code, base, post, nv, lane);
+      else store_codes<BS, 8>(P.codes, code, base, post, nv, lane);
       if (OUTLIER) {
 #pragma unroll
         for (int i = 0; i < BS; ++i) {
@@ -108,16 +117,21 @@ __global__ void __launch_bounds__(256, (BS <= 16 ? 4 : 1)) k_strided(const QPara
     if (pack_hi) {
       int tot;
       const int off = cta_excl_scan(active ? bo.cnt : 0, s_warp, &tot);
-      int k = s_base + off;
-      if (active) {
+      if (active && bo.cnt) {
+        // this block's hi fields are contiguous in the stream: assemble whole words locally, one
+        // shared-memory atomic per touched word (fields never straddle words: hi_w divides 32)
+        const int bit0 = (s_base + off) * P.hi_w;
+        int w = bit0 >> 5, b = bit0 & 31;
+        uint32_t cur = 0;
 #pragma unroll
         for (int i = 0; i < BS; ++i) {
           if ((bo.mask >> i) & 1u) {
-            const int bit = k * P.hi_w;
-            atomicOr(&s_hi[bit >> 5], (code[i] >> wi) << (bit & 31));
-            ++k;
+            cur |= (code[i] >> wi) << b;
+            b += P.hi_w;
+            if (b == 32) { atomicOr(&s_hi[w], cur); cur = 0; b = 0; ++w; }
           }
         }
+        if (b) atomicOr(&s_hi[w], cur);
       }
       __syncthreads();
       if (threadIdx.x == 0) s_base += tot;

@@ -78,9 +78,9 @@ def _alloc_planes(x, pre, L, post, bs, fi, fo, plain):
         codes=torch.empty((n * wi + 7) // 8 + 16, dtype=torch.uint8, device=dev)[: (n * wi + 7) // 8],
         e_in=torch.empty(nb, dtype=torch.int8, device=dev),
         e_out=None if plain else torch.empty(nb, dtype=torch.int8, device=dev),
-        bitmap=None if plain else torch.zeros((n + 31) // 32, dtype=torch.int32, device=dev),
+        bitmap=None if plain else torch.empty((n + 31) // 32, dtype=torch.int32, device=dev),
         hi=torch.empty(max(nseg * stride, 16), dtype=torch.uint8, device=dev) if hi_w > 0 else None,
-        seg_cnt=None if plain else torch.zeros(nseg, dtype=torch.int32, device=dev),
+        seg_cnt=None if plain else torch.empty(nseg, dtype=torch.int32, device=dev),
     )
     return planes, wi, hi_w, stride, nseg
 
