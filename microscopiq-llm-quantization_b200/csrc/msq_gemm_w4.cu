@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(512, 1) k_gemm_w4(const __grid_constant__ CUte
 
   if (warp == 0 && lane == 0) tc::tma_prefetch_desc(&tmX);
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < WSTAGES; ++i) { tc::mbar_init(&full[i], 1 + 256); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < WSTAGES; ++i) { tc::mbar_init(&full[i], 1 + 8); tc::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
     tc::mbar_fence_init();
   }
@@ -123,90 +123,147 @@ __global__ void __launch_bounds__(512, 1) k_gemm_w4(const __grid_constant__ CUte
     }
   } else if (warp >= 8) {
     // ---- weight dequant producers: 256 threads, 4 chunks (8 elements = 16 B of bf16) each per stage.
-    // The packed bytes of stage s+1 are fetched into registers before stage s is converted, so the
-    // global-load latency overlaps the LUT/scale arithmetic.
+    // The packed bytes are prefetched PF-1 stages ahead into a register ring (statically indexed:
+    // the stage loop is unrolled by PF), so ~PF stages of global loads per thread are in flight
+    // while the current stage is converted.
+    constexpr int PF = 3;
     const int ptid = threadIdx.x - 256;
     const int wi = P.wi;
     const long long code_row_bytes = ((long long)P.K * wi) >> 3;
     const int kblk32 = P.K >> 5;                        // MX blocks per weight row
-    struct Raw { uint32_t c0, c1, ob; int ei, eo; };
+    // raw loaded words only: nothing is computed from them until convert(), so the loads of the
+    // prefetched stages stay in flight
+    struct Raw { uint32_t c0, c1, bm; int ei, eo; };
     auto fetch = [&](int n0, int kb, Raw (&raw)[4]) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int c = ptid + 256 * i;
         const int r = c >> 3, kc = c & 7;
         const int n = n0 + r, k = kb * WBK + kc * 8;
-        raw[i].c0 = raw[i].c1 = raw[i].ob = 0; raw[i].ei = 0; raw[i].eo = 0;
+        raw[i].c0 = raw[i].c1 = raw[i].bm = 0; raw[i].ei = 0; raw[i].eo = 0;
         if (n < P.N && k < P.K) {
           const uint8_t* cp = P.codes + (long long)n * code_row_bytes + (((long long)k * wi) >> 3);
           if (wi == 4) raw[i].c0 = __ldg(reinterpret_cast<const uint32_t*>(cp));
           else if (wi == 2) raw[i].c0 = __ldg(reinterpret_cast<const uint16_t*>(cp));
           else { const uint2 v = __ldg(reinterpret_cast<const uint2*>(cp)); raw[i].c0 = v.x; raw[i].c1 = v.y; }
           const int blk = n * kblk32 + (k >> 5);
-          raw[i].ei = P.e_in[blk];
+          raw[i].ei = __ldg(P.e_in + blk);
           if (!P.plain) {
-            raw[i].ob = (__ldg(P.bitmap + (((long long)n * P.K + k) >> 5)) >> (k & 31)) & 0xFFu;
-            raw[i].eo = P.e_out[blk];
+            raw[i].bm = __ldg(P.bitmap + (((long long)n * P.K + k) >> 5));
+            raw[i].eo = __ldg(P.e_out + blk);
           }
-        } else {
-          raw[i].ei = 1 << 20;                          // marker: out of range -> zeros
         }
       }
     };
-    auto convert = [&](uint8_t* dst, const Raw (&raw)[4]) {
+    // 4-bit sign-magnitude codes with one format for inliers and outliers (MXLinear's pairing):
+    // magnitude -> bf16 through byte-permute lookups held in registers (8 magnitudes: low-byte and
+    // high-byte tables of 8 bytes each), sign moved to bit 15, one HMUL2 per pair for the block
+    // scale; the rare outlier elements are rescaled afterwards.
+    const bool fast4 = (wi == 4) && (P.plain || (P.in_ebits == P.out_ebits && P.in_bits == P.out_bits));
+    uint32_t tl0 = 0, tl1 = 0, th0 = 0, th1 = 0;
+    if (fast4) {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const uint32_t bb = (uint32_t)__bfloat16_as_ushort(lut_in[m]);
+        if (m < 4) { tl0 |= (bb & 0xFFu) << (8 * m); th0 |= (bb >> 8) << (8 * m); }
+        else { tl1 |= (bb & 0xFFu) << (8 * (m - 4)); th1 |= (bb >> 8) << (8 * (m - 4)); }
+      }
+    }
+    auto convert = [&](uint8_t* dst, const Raw (&raw)[4], int n0, int kb) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int c = ptid + 256 * i;
         const int r = c >> 3, kc = c & 7;
         uint4 outv = make_uint4(0, 0, 0, 0);
-        if (raw[i].ei != (1 << 20)) {
+        const int k = kb * WBK + kc * 8;
+        if (n0 + r < P.N && k < P.K) {
           const int ei = raw[i].ei, eo = raw[i].eo;
+          uint32_t ob = (raw[i].bm >> (k & 31)) & 0xFFu;
           const bool nan_blk = ei == MSQ_EXP_NAN || eo == MSQ_EXP_NAN;
           // inlier: q * 2^e_in ; outlier: q * 2^(e_out - e_in)   (both exact in bf16)
           const __nv_bfloat16 s_in = __float2bfloat16_rn(nan_blk ? qnan() : pow2i(ei));
           const int eoi = max(-126, min(127, eo - ei));
           const __nv_bfloat16 s_out = __float2bfloat16_rn(nan_blk ? qnan() : pow2i(eoi));
-          uint32_t packed[4];
+          uint32_t w[4];
+          if (fast4) {
+            const uint32_t sbits = (uint32_t)__bfloat16_as_ushort(s_in);
+            const uint32_t s2 = sbits | (sbits << 16);
+            const uint32_t cw = raw[i].c0;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            uint32_t code;
-            if (wi == 8) code = ((e < 4 ? raw[i].c0 : raw[i].c1) >> ((e & 3) * 8)) & 0xFFu;
-            else code = (raw[i].c0 >> (e * wi)) & ((1u << wi) - 1u);
-            const bool isout = (raw[i].ob >> e) & 1u;
-            const __nv_bfloat16 q = isout ? lut_out[code] : lut_in[code];
-            const __nv_bfloat16 v = __hmul(q, isout ? s_out : s_in);
-            const uint32_t bits = (uint32_t)__bfloat16_as_ushort(v);
-            if (e & 1) packed[e >> 1] |= bits << 16; else packed[e >> 1] = bits;
+            for (int h = 0; h < 2; ++h) {                      // 4 codes per half
+              const uint32_t c4 = (cw >> (16 * h)) & 0xFFFFu;
+              const uint32_t sel = c4 & 0x7777u;               // magnitudes as permute selectors
+              const uint32_t lo = __byte_perm(tl0, tl1, sel);  // 4 low bytes
+              const uint32_t hi = __byte_perm(th0, th1, sel);  // 4 high bytes
+              uint32_t p0 = __byte_perm(lo, hi, 0x5140);       // (lo0,hi0,lo1,hi1)
+              uint32_t p1 = __byte_perm(lo, hi, 0x7362);       // (lo2,hi2,lo3,hi3)
+              p0 |= ((c4 & 0x8u) << 12) | ((c4 & 0x80u) << 24);
+              p1 |= ((c4 & 0x800u) << 4) | ((c4 & 0x8000u) << 16);
+              __nv_bfloat162 v0 = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&p0), *reinterpret_cast<const __nv_bfloat162*>(&s2));
+              __nv_bfloat162 v1 = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&p1), *reinterpret_cast<const __nv_bfloat162*>(&s2));
+              w[2 * h] = *reinterpret_cast<uint32_t*>(&v0);
+              w[2 * h + 1] = *reinterpret_cast<uint32_t*>(&v1);
+            }
+            while (ob) {                                       // outliers: q * 2^(e_out - e_in)
+              const int e = __ffs(ob) - 1;
+              ob &= ob - 1;
+              const uint32_t code = (cw >> (4 * e)) & 0xFu;
+              const uint32_t bits = (uint32_t)__bfloat16_as_ushort(__hmul(lut_in[code], s_out));
+              const int wsel = e >> 1;
+              w[wsel] = (e & 1) ? ((w[wsel] & 0x0000FFFFu) | (bits << 16)) : ((w[wsel] & 0xFFFF0000u) | bits);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              uint32_t code;
+              if (wi == 8) code = ((e < 4 ? raw[i].c0 : raw[i].c1) >> ((e & 3) * 8)) & 0xFFu;
+              else code = (raw[i].c0 >> (e * wi)) & ((1u << wi) - 1u);
+              const bool isout = (ob >> e) & 1u;
+              const __nv_bfloat16 q = isout ? lut_out[code] : lut_in[code];
+              const __nv_bfloat16 v = __hmul(q, isout ? s_out : s_in);
+              const uint32_t bits = (uint32_t)__bfloat16_as_ushort(v);
+              if (e & 1) w[e >> 1] |= bits << 16; else w[e >> 1] = bits;
+            }
           }
-          outv = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          outv = make_uint4(w[0], w[1], w[2], w[3]);
         }
         *reinterpret_cast<uint4*>(dst + r * 128 + ((kc ^ (r & 7)) << 4)) = outv;
       }
     };
-    int stage = 0; uint32_t phase = 0;
-    Raw cur[4], nxt[4];
-    int t = blockIdx.x;
-    int tn = 0, tm = 0, kb0 = 0, nkb = 0, kb = 0;
-    bool have = t < num_tiles;
-    if (have) { tile_coords(t, tn, tm, kb0, nkb); fetch(tn * WM, kb0, cur); }
-    while (have) {
-      // locate the next (tile, kb) and prefetch it
-      int t2 = t, tn2 = tn, tm2 = tm, kb02 = kb0, nkb2 = nkb, kb2 = kb + 1;
-      bool have2 = true;
-      if (kb2 >= nkb) {
-        t2 = t + gridDim.x; kb2 = 0;
-        have2 = t2 < num_tiles;
-        if (have2) tile_coords(t2, tn2, tm2, kb02, nkb2);
+    // cursor over this CTA's (tile, K-block) sequence
+    struct Cursor { int t, tn, tm, kb0, nkb, kb; bool ok; };
+    auto cur_init = [&](Cursor& c) {
+      c.t = blockIdx.x; c.kb = 0; c.ok = c.t < num_tiles;
+      if (c.ok) tile_coords(c.t, c.tn, c.tm, c.kb0, c.nkb);
+    };
+    auto cur_next = [&](Cursor& c) {
+      if (++c.kb >= c.nkb) {
+        c.t += gridDim.x; c.kb = 0; c.ok = c.t < num_tiles;
+        if (c.ok) tile_coords(c.t, c.tn, c.tm, c.kb0, c.nkb);
       }
-      if (have2) fetch(tn2 * WM, kb02 + kb2, nxt);
-      tc::mbar_wait(&empty[stage], phase ^ 1);
-      convert(sA + stage * WA_BYTES, cur);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      tc::mbar_arrive(&full[stage]);
-      if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
+    };
+    Cursor fc, cc;
+    cur_init(fc); cur_init(cc);
+    Raw ring[PF][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
-      t = t2; tn = tn2; tm = tm2; kb0 = kb02; nkb = nkb2; kb = kb2; have = have2;
+    for (int j = 0; j < PF - 1; ++j) {
+      if (fc.ok) { fetch(fc.tn * WM, fc.kb0 + fc.kb, ring[j]); cur_next(fc); }
+    }
+    int stage = 0; uint32_t phase = 0;
+    while (cc.ok) {
+#pragma unroll
+      for (int j = 0; j < PF; ++j) {
+        if (cc.ok) {
+          if (fc.ok) { fetch(fc.tn * WM, fc.kb0 + fc.kb, ring[(j + PF - 1) % PF]); cur_next(fc); }
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+          convert(sA + stage * WA_BYTES, ring[j], cc.tn * WM, cc.kb0 + cc.kb);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&full[stage]);      // one arrival per producer warp
+          if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
+          cur_next(cc);
+        }
+      }
     }
   } else if (warp >= 4) {
     const int q = warp & 3;

@@ -1,0 +1,2 @@
+cd $GRAFT_REPO_ROOT
+timeout 600 python -m pytest tests/test_gpu_dist.py -x -q 2>&1 | tail -5
