@@ -190,14 +190,17 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
     for (int i = 0; i < N; ++i) t[i] = fabsf(x[i]);
     const float s = grp_sum_tree<LPB>(tree_sum_regs<N>(t));
     bad = !(s <= 3.402823466e38f);    // an Inf/NaN element (or an overflowing sum) makes it non-finite
-    const float mean = __fdiv_rn(s, (float)BS);
+    // BS is a power of two here, so multiplying by 1/BS is the division of utils/quant.py:477 exactly
+    constexpr float inv_bs = 1.0f / (float)BS;
+    static_assert((BS & (BS - 1)) == 0, "fast mappings use power-of-two blocks");
+    const float mean = __fmul_rn(s, inv_bs);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       const float d = __fsub_rn(fabsf(x[i]), mean);
       t[i] = __fmul_rn(d, d);
     }
     const float q = grp_sum_tree<LPB>(tree_sum_regs<N>(t));
-    const float sd = __fsqrt_rn(__fdiv_rn(q, (float)BS));
+    const float sd = __fsqrt_rn(__fmul_rn(q, inv_bs));
     const float w = __fmul_rn(c.std_dev, sd);
     l = __fsub_rn(mean, w); h = __fadd_rn(mean, w);
   } else {
@@ -272,18 +275,22 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
       const float2 v = __fadd2_rn(vin, vout);
       const float2 L2 = cblend2(ci.L, dL, m), H2 = cblend2(ci.H, dH, m), D2 = cblend2(ci.down, dD, m),
                    M2 = cblend2(ci.mx, dM, m);
+      // quantum 2^(p - mant) with p = clamp(exponent(v), lo, hi), done on powers of two in the float
+      // domain.  floor(|v| / quantum + addend) * quantum is computed without leaving the FMA pipe:
+      //   a = |v| + addend*quantum   (the reference's fp32 add, scaled by an exact power of two)
+      //   floor to a multiple of the quantum = (a (+rz) C) - C  with C = 2^23 * quantum
       float2 P2;
       P2.x = fminf(fmaxf(__int_as_float(__float_as_int(v.x) & 0x7F800000), L2.x), H2.x);
       P2.y = fminf(fmaxf(__int_as_float(__float_as_int(v.y) & 0x7F800000), L2.y), H2.y);
-      const float2 s2 = __fmul2_rn(P2, D2);
-      float2 s1;
-      s1.x = __int_as_float(0x7F000000 - __float_as_int(s2.x));
-      s1.y = __int_as_float(0x7F000000 - __float_as_int(s2.y));
-      const float2 y = __fmul2_rn(v, s1);
-      const float2 yh = __fadd2_rn(y, f2(copysignf(rs.addend, y.x), copysignf(rs.addend, y.y)));
-      float2 q = __fmul2_rn(f2(truncf(yh.x), truncf(yh.y)), s2);
-      q.x = fminf(fmaxf(q.x, -M2.x), M2.x);
-      q.y = fminf(fmaxf(q.y, -M2.y), M2.y);
+      const float2 qn = __fmul2_rn(P2, D2);                              // quantum
+      const float2 hq = __fmul2_rn(qn, f2s(rs.addend));                  // 0.5 quantum (nearest) or 0 (floor)
+      const float2 Cq = __fmul2_rn(qn, f2s(8388608.0f));
+      const float ax = __fadd_rn(fabsf(v.x), hq.x), ay = __fadd_rn(fabsf(v.y), hq.y);
+      float2 q;
+      q.x = fminf(__fsub_rn(__fadd_rz(ax, Cq.x), Cq.x), M2.x);
+      q.y = fminf(__fsub_rn(__fadd_rz(ay, Cq.y), Cq.y), M2.y);
+      q.x = copysignf(q.x, v.x);
+      q.y = copysignf(q.y, v.y);
       const bool o0 = mf[i] != 0.0f, o1 = mf[i + 1] != 0.0f;
       if (CODES) {
         code[i] = encode_sel(q.x, o0);

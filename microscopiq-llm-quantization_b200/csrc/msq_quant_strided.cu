@@ -46,14 +46,15 @@ __global__ void __launch_bounds__(256, (BS <= 16 ? 4 : 1)) k_strided(const QPara
   int st = 0;
 #pragma unroll 1
   for (int sub = 0; sub < MSQ_SEG_BLOCKS / 256; ++sub) {
-    const long long t0 = seg * MSQ_SEG_BLOCKS + (long long)sub * 256 + threadIdx.x;
-    const bool active = t0 < P.nblocks;
+    // 32-bit index math: the host routes tensors with >= 2^31 elements to the generic kernel
+    const int t0 = (int)seg * MSQ_SEG_BLOCKS + sub * 256 + (int)threadIdx.x;
+    const bool active = t0 < (int)P.nblocks;
     float x[BS];
     uint32_t code[BS];
     int base = 0, p = 0, j = 0, b = 0;
     if (active) {
-      const int pb = (int)(t0 / post);
-      j = (int)(t0 - (long long)pb * post);
+      const int pb = t0 / post;
+      j = t0 - pb * post;
       p = pb / P.nblk; b = pb - p * P.nblk;
       base = (p * P.L + b * BS) * post + j;
     }
