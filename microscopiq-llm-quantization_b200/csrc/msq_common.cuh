@@ -37,6 +37,7 @@ struct Fmt {
   float max_norm;
   float up;       // 2^(bits-2)
   float down;     // 2^-(bits-2)
+  float L, H;     // float-domain exponent clamp of the element rounding: 2^min_exp, 2^127 (ints: 1, 1)
 };
 
 __host__ inline Fmt make_fmt(int ebits, int mbits, int emax, float max_norm) {
@@ -47,6 +48,12 @@ __host__ inline Fmt make_fmt(int ebits, int mbits, int emax, float max_norm) {
   f.width = cw <= 2 ? 2 : (cw <= 4 ? 4 : 8);
   f.up = 1.0f; f.down = 1.0f;
   for (int i = 0; i < mbits - 2; ++i) { f.up *= 2.0f; f.down *= 0.5f; }
+  f.L = 1.0f; f.H = 1.0f;
+  if (ebits > 0) {
+    for (int i = 0; i < -f.min_exp; ++i) f.L *= 0.5f;
+    for (int i = 0; i < f.min_exp; ++i) f.L *= 2.0f;
+    f.H = 1.70141183e38f;      // 2^127
+  }
   return f;
 }
 

@@ -36,9 +36,9 @@ template <int LPB> __device__ __forceinline__ float grp_sum_tree(float v) {
   return v;
 }
 // in-thread adjacent pairwise tree over N (power of two) values; destroys t[]
-template <int N> __device__ __forceinline__ float tree_sum_regs(float (&t)[N]) {
+template <int N, int START = 1> __device__ __forceinline__ float tree_sum_regs(float (&t)[N]) {
 #pragma unroll
-  for (int stride = 1; stride < N; stride <<= 1)
+  for (int stride = START; stride < N; stride <<= 1)
 #pragma unroll
     for (int i = 0; i + stride < N; i += 2 * stride) t[i] = __fadd_rn(t[i], t[i + stride]);
   return t[0];
@@ -148,9 +148,7 @@ struct ElemConsts {      // per-format constants of the float-domain rounding
 };
 __device__ __forceinline__ ElemConsts elem_consts(const Fmt& f) {
   ElemConsts e;
-  e.L = f.ebits ? pow2i(f.min_exp) : 1.0f;
-  e.H = f.ebits ? __int_as_float(0x7F000000) : 1.0f;      // 2^127: no upper clamp for floats
-  e.down = f.down; e.mx = f.max_norm;
+  e.L = f.L; e.H = f.H; e.down = f.down; e.mx = f.max_norm;    // precomputed on the host (make_fmt)
   return e;
 }
 
@@ -186,9 +184,13 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
   if (!EXT) {
     // mean(|A|), std(|A|) of utils/quant.py:477-478: fp32, two-pass, canonical pairwise-tree order
     float t[N];
+    if (N >= 2) {     // first tree level with |.| as an operand modifier
 #pragma unroll
-    for (int i = 0; i < N; ++i) t[i] = fabsf(x[i]);
-    const float s = grp_sum_tree<LPB>(tree_sum_regs<N>(t));
+      for (int i = 0; i + 1 < N; i += 2) t[i] = __fadd_rn(fabsf(x[i]), fabsf(x[i + 1]));
+    } else {
+      t[0] = fabsf(x[0]);
+    }
+    const float s = grp_sum_tree<LPB>(tree_sum_regs<N, (N >= 2 ? 2 : 1)>(t));
     bad = !(s <= 3.402823466e38f);    // an Inf/NaN element (or an overflowing sum) makes it non-finite
     // BS is a power of two here, so multiplying by 1/BS is the division of utils/quant.py:477 exactly
     constexpr float inv_bs = 1.0f / (float)BS;

@@ -242,7 +242,8 @@ static int launch_quant(QParams& P, bool outlier, cudaStream_t stream, int* path
       (P.bs == 8 || P.bs == 16 || P.bs == 32 || P.bs == 64 || P.bs == 128)) {
     path = 2;
     err = launch_inner(P, outlier, smem, stream);
-  } else if (fast_ok && P.post > 1 && (P.bs == 8 || P.bs == 16 || P.bs == 32) && (!packing || P.post % 32 == 0)) {
+  } else if (fast_ok && P.post > 1 && (P.bs == 8 || P.bs == 16 || P.bs == 32) && (!packing || P.post % 32 == 0) &&
+             (packing || P.pre * (long long)P.nblk <= 65535)) {
     path = 1;
     err = launch_strided(P, outlier, smem, stream);
   } else {

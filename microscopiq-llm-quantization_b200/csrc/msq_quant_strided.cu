@@ -44,20 +44,32 @@ __global__ void __launch_bounds__(256, (BS <= 16 ? 4 : 1)) k_strided(const QPara
     __syncthreads();
   }
   int st = 0;
+  // PACK: one CTA = one packed segment (4 sub-iterations of 256 consecutive block-linear indices).
+  // fake-quant: 2-D grid, blockIdx.y = row of blocks (p, b), blockIdx.x*256 + tid = column: no divisions.
+  constexpr int NSUB = PACK ? MSQ_SEG_BLOCKS / 256 : 1;
 #pragma unroll 1
-  for (int sub = 0; sub < MSQ_SEG_BLOCKS / 256; ++sub) {
+  for (int sub = 0; sub < NSUB; ++sub) {
     // 32-bit index math: the host routes tensors with >= 2^31 elements to the generic kernel
-    const int t0 = (int)seg * MSQ_SEG_BLOCKS + sub * 256 + (int)threadIdx.x;
-    const bool active = t0 < (int)P.nblocks;
+    int t0, base = 0, p = 0, j = 0, b = 0;
+    bool active;
+    if (PACK) {
+      t0 = (int)seg * MSQ_SEG_BLOCKS + sub * 256 + (int)threadIdx.x;
+      active = t0 < (int)P.nblocks;
+      if (active) {
+        const int pb = t0 / post;
+        j = t0 - pb * post;
+        p = pb / P.nblk; b = pb - p * P.nblk;
+      }
+    } else {
+      const int pb = (int)blockIdx.y;
+      j = (int)blockIdx.x * 256 + (int)threadIdx.x;
+      active = j < post;
+      p = pb / P.nblk; b = pb - p * P.nblk;       // uniform per CTA
+      t0 = pb * post + j;
+    }
+    if (active) base = (p * P.L + b * BS) * post + j;
     float x[BS];
     uint32_t code[BS];
-    int base = 0, p = 0, j = 0, b = 0;
-    if (active) {
-      const int pb = t0 / post;
-      j = t0 - pb * post;
-      p = pb / P.nblk; b = pb - p * P.nblk;
-      base = (p * P.L + b * BS) * post + j;
-    }
     const int nv = active ? min(BS, P.L - b * BS) : 0;       // valid rows, the rest is zero padding
     const float* pin = P.in + base;
     if (nv == BS) {
@@ -171,7 +183,16 @@ cudaError_t launch_strided(const QParams& P, bool outlier, size_t smem, cudaStre
   else return cudaErrorInvalidValue;
 #undef MSQ_PICK
   if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k<<<(unsigned)nseg, 256, smem, stream>>>(P);
+  if (pack) {
+    k<<<(unsigned)nseg, 256, smem, stream>>>(P);
+  } else {
+    const long long rows_of_blocks = P.pre * P.nblk;
+    if (rows_of_blocks > 65535) {              // gridDim.y limit: fold into the segment mapping is not needed in
+      return cudaErrorInvalidConfiguration;    // practice (65535 * bs rows); the caller falls back to k_generic
+    }
+    dim3 grid((unsigned)((P.post + 255) / 256), (unsigned)rows_of_blocks);
+    k<<<grid, 256, 0, stream>>>(P);
+  }
   return cudaGetLastError();
 }
 
