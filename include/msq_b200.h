@@ -166,6 +166,17 @@ int msq_gemm_packed_w_bf16(const void* X, long long ldx, const unsigned char* co
                            int M, int N, int K, int in_ebits, int in_mbits, int out_ebits, int out_mbits,
                            int plain, int accumulate, void* stream);
 
+/* native block-scaled tensor-core path: tcgen05.mma kind::mxf8f6f4.block_scale (E4M3 x E4M3, UE8M0 scales
+ * per 32 elements along K).  X: plain MX-FP8 (E4M3) activations, codes [M,K] bytes (ld = ldx) + int8
+ * exponents [M, K/32]; W: packed FP4 (E2M1) weight blocked by 32 along K, outliers folded into the E4M3
+ * element value as q * 2^(e_out - 2 e_in) (caller guarantees -6 <= e_out - 2 e_in <= 6 for outlier blocks).
+ * Same contraction as msq_gemm_packed_w_bf16; replaces number_system/mx/linear.py:66-91 when
+ * a_elem_format = fp8_e4m3 and w_elem_format = fp4_e2m1. */
+int msq_gemm_mxfp8_blockscaled(const unsigned char* xcodes, long long ldx, const signed char* xe,
+                               const unsigned char* wcodes, const unsigned int* wbitmap, const signed char* we_in,
+                               const signed char* we_out, float* C, long long ldc, int M, int N, int K,
+                               int plain, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -113,3 +113,48 @@ def packed_linear(x, pw, bias=None):
     if bias is not None:
         out += bias.float()
     return out.reshape(*lead, Nn)
+
+
+N.register("msq_gemm_mxfp8_blockscaled", _i, [_p, _ll, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _p])
+
+
+def mx8_weight_ok(pw):
+    """can this packed weight go through the native block-scaled FP8 path?  FP4 (E2M1) inliers and
+    outliers, K blocks of 32, and every outlier block's exponent relative to the block scale,
+    e_out - 2 e_in, within the range where q * 2^(e_out - 2 e_in) is still an exact E4M3 value.
+    (One device->host read; the answer is cached on the PackedMX object.)"""
+    from .mx.formats import _get_format_params
+    ok = getattr(pw, "_mx8_ok", None)
+    if ok is not None:
+        return ok
+    ok = (len(pw.shape) == 2 and pw.axis == 1 and pw.block_size == 32 and pw.hi_w == 0 and pw.code_width == 4
+          and _get_format_params(pw.in_fmt)[:2] == (2, 3) and (pw.plain or _get_format_params(pw.out_fmt)[:2] == (2, 3)))
+    if ok and not pw.plain:
+        has_out = pw.bitmap != 0                       # block 32 along K == one bitmap word per block
+        d = (pw.e_out.to(torch.int32) - 2 * pw.e_in.to(torch.int32))[has_out]
+        ok = bool(d.numel() == 0 or (int(d.min()) >= -6 and int(d.max()) <= 6))
+    pw._mx8_ok = ok
+    return ok
+
+
+def packed_linear_mx8(xq, pw, bias=None):
+    """y = dq(xq) @ dq(pw).T on tcgen05 kind::mxf8f6f4.block_scale.  xq: PackedMX of the activations
+    ([..., K], FP8 E4M3, block 32 along the last axis, no outliers); pw: packed FP4 weight (mx8_weight_ok)."""
+    from . import _ops
+    K = pw.shape[1]
+    if xq.shape[-1] != K or xq.block_size != 32 or xq.code_width != 8 or _ops.fmt4(xq.in_fmt)[:2] != (4, 5):
+        raise NotImplementedError("activations must be MX-FP8 (E4M3) packed along K with block 32")
+    if not mx8_weight_ok(pw):
+        raise NotImplementedError("weight is not eligible for the block-scaled FP8 path")
+    M = 1
+    for s_ in xq.shape[:-1]:
+        M *= s_
+    Nn = pw.shape[0]
+    out = torch.empty(M, Nn, dtype=torch.float32, device=pw.codes.device)
+    rc = N.lib().msq_gemm_mxfp8_blockscaled(N.ptr(xq.codes), K, N.ptr(xq.e_in), N.ptr(pw.codes), N.ptr(pw.bitmap),
+                                            N.ptr(pw.e_in), N.ptr(pw.e_out), N.ptr(out), out.stride(0), M, Nn, K,
+                                            int(pw.plain), 0, N.stream_ptr(out.device))
+    N.check(rc, "msq_gemm_mxfp8_blockscaled")
+    if bias is not None:
+        out += bias.float()
+    return out.reshape(*xq.shape[:-1], Nn)

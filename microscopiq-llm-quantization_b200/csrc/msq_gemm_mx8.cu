@@ -1,0 +1,365 @@
+// msq_gemm_mx8.cu -- packed-weight linear on Blackwell's native block-scaled tensor-core path:
+//     C[m, n] (+)= sum_k  dq(X)[m, k] * dq(W)[n, k]
+// with  tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale  (E4M3 x E4M3 elements, one UE8M0 scale per
+// 32 elements along K for both operands, fp32 accumulation in TMEM).
+//
+//   X : plain MX-FP8 (E4M3) activations, block 32 along K: codes [M, K] bytes + int8 exponents [M, K/32]
+//       (what pack_mx(x, 8, "fp8_e4m3", axes=[-1], block_size=32) produces) -- TMA-loaded as bytes.
+//   W : packed MicroScopiQ weight [N, K], FP4 (E2M1) inliers AND outliers, block 32 along K: 4-bit codes,
+//       outlier bitmap, e_in / e_out.  Producer warps widen the 4-bit codes to E4M3 bytes (every E2M1 value
+//       is an E4M3 value) straight into the 128B-swizzled K-major tile; the block scale 2^e_in goes to the
+//       scale-factor operand.  An outlier's value is q * 2^(e_out - e_in) (utils/quant.py:136), i.e.
+//       q * 2^(e_out - 2 e_in) relative to the block scale the hardware applies, so the producer stores
+//       that product as the element's E4M3 value -- exact while -6 <= e_out - 2 e_in <= 6, which the
+//       host checks before choosing this path (otherwise the bf16 kernel of msq_gemm_w4.cu is used).
+//
+// Scale factors: per stage (128 K = 4 blocks) the 128 x 4 UE8M0 bytes of each operand form one 512-byte
+// chunk laid out  byte(r, kb) = (r % 32) * 16 + (r / 32) * 4 + kb,  copied shared -> tensor memory with
+// tcgen05.cp.32x128b.warpx4 (one 32-bit TMEM column per 32 rows, broadcast to the four lane quarters);
+// the MMA for K-block kb selects byte kb through the a_sf_id / b_sf_id fields of the instruction
+// descriptor.  The weight tile is the UMMA M operand (SFA = weight scales), the activations the N operand.
+#include "msq_api_internal.h"
+#include "msq_common.cuh"
+#include "msq_tc.cuh"
+
+namespace msq {
+
+constexpr int XM = 128, XBK = 128, XSTAGES = 4, XMAXN = 256;
+constexpr int XA_BYTES = XM * XBK, XB_BYTES = XMAXN * XBK;          // 1 byte per element
+constexpr int XSF_BYTES = 512 + 1024;                                // SFA chunk + two SFB chunks
+constexpr int MX8_SMEM = XSTAGES * (XA_BYTES + XB_BYTES + XSF_BYTES) + 1024 + 256;
+constexpr uint32_t TM_ACC = 0, TM_SFA = 256, TM_SFB = 260;           // TMEM columns
+
+struct Mx8Params {
+  const uint8_t* wcodes; const uint32_t* wbitmap; const int8_t* we_in; const int8_t* we_out;
+  const int8_t* xe;           // activation shared exponents [M, K/32]
+  float* C; long long ldc;
+  int M, N, K;
+  int bnx, tiles_n, tiles_m, ksplit, kb_per_split;
+  int plain;                  // weight has no outliers
+  int accumulate;
+};
+
+__device__ __forceinline__ uint64_t make_sf_desc(uint32_t smem_addr) {
+  // no swizzle, 8-row x 16-byte core matrices 128 bytes apart (SBO), single 16-byte column (LBO unused)
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(128 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void utccp_32x128b(uint32_t tmem_addr, uint64_t desc) {
+  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(tmem_addr), "l"(desc) : "memory");
+}
+__device__ __forceinline__ void umma_mxf8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                          uint32_t tsfa, uint32_t tsfb) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb)
+      : "memory");
+}
+// block-scaled instruction descriptor: E4M3 x E4M3 -> F32, UE8M0 scales, both K-major
+//   [4,6) b_sf_id  [7,10) A fmt  [10,13) B fmt  [17,23) N>>3  [23] scale fmt (1 = E8M0)  [24,29) M>>4  [29,31) a_sf_id
+__device__ __forceinline__ uint32_t make_idesc_mx8(int M, int N, int sf_id) {
+  return ((uint32_t)sf_id << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | (1u << 23) | ((uint32_t)(M >> 4) << 24) |
+         ((uint32_t)sf_id << 29);
+}
+
+__global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUtensorMap tmX, const Mx8Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                      // W tiles (E4M3 bytes)
+  uint8_t* sB = smem + XSTAGES * XA_BYTES;                 // X tiles
+  uint8_t* sSF = smem + XSTAGES * (XA_BYTES + XB_BYTES);   // per stage: SFA[512] | SFB[1024]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSF + XSTAGES * XSF_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + XSTAGES;
+  uint64_t* acc_full = bars + 2 * XSTAGES;
+  uint64_t* acc_empty = bars + 2 * XSTAGES + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * XSTAGES + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = P.tiles_n * P.tiles_m * P.ksplit;
+  const int kblocks_total = (P.K + XBK - 1) / XBK;
+
+  if (warp == 0 && lane == 0) tc::tma_prefetch_desc(&tmX);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < XSTAGES; ++i) { tc::mbar_init(&full[i], 1 + 8); tc::mbar_init(&empty[i], 1); }
+    tc::mbar_init(acc_full, 1);
+    tc::mbar_init(acc_empty, 128);
+    tc::mbar_fence_init();
+  }
+  if (warp == 2) tc::tmem_alloc<512>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_coords = [&](int t, int& tn, int& tm, int& kb0, int& nkb) {
+    const int ks = t % P.ksplit;
+    const int r = t / P.ksplit;
+    tm = r / P.tiles_n; tn = r - tm * P.tiles_n;
+    kb0 = ks * P.kb_per_split;
+    nkb = min(P.kb_per_split, kblocks_total - kb0);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int tn, tm, kb0, nkb; tile_coords(t, tn, tm, kb0, nkb);
+        for (int kb = kb0; kb < kb0 + nkb; ++kb) {
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+          tc::mbar_expect_tx(&full[stage], (uint32_t)(P.bnx * XBK));
+          tc::tma_load_2d(sB + stage * XB_BYTES, &tmX, &full[stage], kb * XBK, tm * P.bnx);
+          if (++stage == XSTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      uint32_t acc_phase = 0;
+      const int sfb_chunks = (P.bnx + 127) / 128;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int tn, tm, kb0, nkb; tile_coords(t, tn, tm, kb0, nkb);
+        tc::mbar_wait(acc_empty, acc_phase ^ 1);
+        tc::tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb) {
+          tc::mbar_wait(&full[stage], phase);
+          tc::tc_fence_after();
+          const uint32_t sf_addr = tc::smem_u32(sSF + stage * XSF_BYTES);
+          utccp_32x128b(tmem_base + TM_SFA, make_sf_desc(sf_addr));
+          for (int c = 0; c < sfb_chunks; ++c) utccp_32x128b(tmem_base + TM_SFB + 4 * c, make_sf_desc(sf_addr + 512 + 512 * c));
+          const uint64_t ad = tc::make_kmajor_sw128_desc(tc::smem_u32(sA + stage * XA_BYTES));
+          const uint64_t bd = tc::make_kmajor_sw128_desc(tc::smem_u32(sB + stage * XB_BYTES));
+#pragma unroll
+          for (int k = 0; k < XBK / 32; ++k)      // 32 one-byte elements = 32 bytes = 2 descriptor units per UMMA_K
+            umma_mxf8(tmem_base + TM_ACC, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), make_idesc_mx8(XM, P.bnx, k),
+                      (kb | k) != 0, tmem_base + TM_SFA, tmem_base + TM_SFB);
+          tc::umma_commit(&empty[stage]);
+          if (++stage == XSTAGES) { stage = 0; phase ^= 1; }
+        }
+        tc::umma_commit(acc_full);
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 8) {
+    // ---- producers: 256 threads, per stage 128 rows x 128 K of weights = 1024 chunks of 16 elements
+    constexpr int PF = 2;
+    const int ptid = threadIdx.x - 256;
+    const long long code_row_bytes = (long long)P.K >> 1;
+    const int kblk32 = P.K >> 5;
+    struct Raw { uint2 c; uint32_t bm; int ei, eo; };
+    auto fetch = [&](int n0, int kb, Raw (&raw)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = ptid + 256 * i;
+        const int r = c >> 3, kc = c & 7;
+        const int n = n0 + r, k = kb * XBK + kc * 16;
+        raw[i].c = make_uint2(0, 0); raw[i].bm = 0; raw[i].ei = 0; raw[i].eo = 0;
+        if (n < P.N && k < P.K) {
+          raw[i].c = __ldg(reinterpret_cast<const uint2*>(P.wcodes + (long long)n * code_row_bytes + (k >> 1)));
+          const int blk = n * kblk32 + (k >> 5);
+          raw[i].ei = __ldg(P.we_in + blk);
+          if (!P.plain) {
+            raw[i].bm = __ldg(P.wbitmap + (((long long)n * P.K + k) >> 5));
+            raw[i].eo = __ldg(P.we_out + blk);
+          }
+        }
+      }
+    };
+    // E2M1 magnitude (3 bits) -> E4M3 byte: 0, 0.5, 1, 1.5, 2, 3, 4, 6
+    const uint32_t t0 = 0x3C383000u, t1 = 0x4C484440u;     // bytes {00,30,38,3C} {40,44,48,4C}
+    const EncC enc8 = make_enc(4, 5);
+    auto widen4 = [&](uint32_t c4) {     // 4 nibbles -> 4 E4M3 bytes
+      const uint32_t mag = __byte_perm(t0, t1, c4 & 0x7777u);
+      const uint32_t s = c4 & 0x8888u;
+      return mag | ((s << 4) & 0x80u) | ((s << 8) & 0x8000u) | ((s << 12) & 0x800000u) | ((s << 16) & 0x80000000u);
+    };
+    auto convert = [&](int stage, const Raw (&raw)[4], int n0, int kb) {
+      uint8_t* dst = sA + stage * XA_BYTES;
+      uint8_t* sfa = sSF + stage * XSF_BYTES;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = ptid + 256 * i;
+        const int r = c >> 3, kc = c & 7;
+        const int k = kb * XBK + kc * 16;
+        uint4 outv = make_uint4(0, 0, 0, 0);
+        uint32_t sf_byte = 0x7Fu;                    // 2^0 for rows / K-blocks outside the matrix
+        if (n0 + r < P.N && k < P.K) {
+          const int ei = raw[i].ei, eo = raw[i].eo;
+          sf_byte = (uint32_t)(ei + 127) & 0xFFu;    // UE8M0; MSQ_EXP_NAN (-128) maps to 0xFF = NaN
+          uint32_t w[4];
+          w[0] = widen4(raw[i].c.x & 0xFFFFu); w[1] = widen4(raw[i].c.x >> 16);
+          w[2] = widen4(raw[i].c.y & 0xFFFFu); w[3] = widen4(raw[i].c.y >> 16);
+          uint32_t ob = (raw[i].bm >> (k & 31)) & 0xFFFFu;
+          while (ob) {                               // outliers: q * 2^(e_out - 2 e_in) relative to the block scale
+            const int e = __ffs(ob) - 1;
+            ob &= ob - 1;
+            const uint32_t code = ((e < 8 ? raw[i].c.x : raw[i].c.y) >> (4 * (e & 7))) & 0xFu;
+            const float v = __fmul_rn(decode_elem(code, 2, 3), pow2i(max(-60, min(60, eo - 2 * ei))));
+            const uint32_t b8 = (eo == MSQ_EXP_NAN) ? 0x7Fu : (encode_fast(v, enc8) & 0xFFu);
+            const int ws = e >> 2, sh = (e & 3) * 8;
+            w[ws] = (w[ws] & ~(0xFFu << sh)) | (b8 << sh);
+          }
+          outv = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        *reinterpret_cast<uint4*>(dst + r * 128 + ((kc ^ (r & 7)) << 4)) = outv;
+        if ((kc & 1) == 0) sfa[(r & 31) * 16 + (r >> 5) * 4 + (kc >> 1)] = (uint8_t)sf_byte;
+      }
+    };
+    // activation scale chunks: thread t < bnx handles activation row t of the tile (4 K-blocks = one 32-bit word)
+    auto write_sfb = [&](int stage, int m0, int kb) {
+      if (ptid < P.bnx) {
+        const int m = m0 + ptid;
+        uint32_t v = 0x7F7F7F7Fu;
+        if (m < P.M) {
+          uint32_t raw4 = 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int kbq = kb * 4 + q;
+            const uint32_t b = (kbq < kblk32) ? ((uint32_t)(__ldg(P.xe + (long long)m * kblk32 + kbq) + 127) & 0xFFu) : 0x7Fu;
+            raw4 |= b << (8 * q);
+          }
+          v = raw4;
+        }
+        uint8_t* sfb = sSF + stage * XSF_BYTES + 512 + (ptid >> 7) * 512;
+        const int rr = ptid & 127;
+        *reinterpret_cast<uint32_t*>(sfb + (rr & 31) * 16 + (rr >> 5) * 4) = v;
+      }
+    };
+    struct Cursor { int t, tn, tm, kb0, nkb, kb; bool ok; };
+    auto cur_init = [&](Cursor& c) {
+      c.t = blockIdx.x; c.kb = 0; c.ok = c.t < num_tiles;
+      if (c.ok) tile_coords(c.t, c.tn, c.tm, c.kb0, c.nkb);
+    };
+    auto cur_next = [&](Cursor& c) {
+      if (++c.kb >= c.nkb) {
+        c.t += gridDim.x; c.kb = 0; c.ok = c.t < num_tiles;
+        if (c.ok) tile_coords(c.t, c.tn, c.tm, c.kb0, c.nkb);
+      }
+    };
+    Cursor fc, cc;
+    cur_init(fc); cur_init(cc);
+    Raw ring[PF][4];
+#pragma unroll
+    for (int j = 0; j < PF - 1; ++j) {
+      if (fc.ok) { fetch(fc.tn * XM, fc.kb0 + fc.kb, ring[j]); cur_next(fc); }
+    }
+    int stage = 0; uint32_t phase = 0;
+    while (cc.ok) {
+#pragma unroll
+      for (int j = 0; j < PF; ++j) {
+        if (cc.ok) {
+          if (fc.ok) { fetch(fc.tn * XM, fc.kb0 + fc.kb, ring[(j + PF - 1) % PF]); cur_next(fc); }
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+          convert(stage, ring[j], cc.tn * XM, cc.kb0 + cc.kb);
+          write_sfb(stage, cc.tm * P.bnx, cc.kb0 + cc.kb);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&full[stage]);
+          if (++stage == XSTAGES) { stage = 0; phase ^= 1; }
+          cur_next(cc);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int tn, tm, kb0, nkb; tile_coords(t, tn, tm, kb0, nkb);
+      tc::mbar_wait(acc_full, acc_phase);
+      tc::tc_fence_after();
+      const int n = tn * XM + q * 32 + lane;
+      for (int c = 0; c < P.bnx / 16; ++c) {
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + TM_ACC + (uint32_t)(c * 16))
+            : "memory");
+        tc::tmem_ld_wait();
+        if (n < P.N) {
+#pragma unroll
+          for (int v = 0; v < 16; ++v) {
+            const int m = tm * P.bnx + c * 16 + v;
+            if (m < P.M) {
+              float* p = P.C + (long long)m * P.ldc + n;
+              const float val = __uint_as_float(r[v]);
+              if (P.ksplit > 1) atomicAdd(p, val);
+              else *p = P.accumulate ? (*p + val) : val;
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(acc_empty);
+      acc_phase ^= 1;
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace msq
+
+using namespace msq;
+
+extern "C" {
+
+// C[M,N] fp32 (+)= dq(X)[M,K] * dq(W)[N,K]^T on the block-scaled tensor-core path.
+//   xcodes [M, K] E4M3 bytes (ld = ldx bytes), xe int8 [M, K/32]         (plain MX-FP8 activations)
+//   wcodes / wbitmap / we_in / we_out: packed FP4 weight, block 32 along K (plain != 0: no outliers)
+// The caller guarantees that every outlier block satisfies -6 <= e_out - 2 e_in <= 6 (exact E4M3 folding).
+int msq_gemm_mxfp8_blockscaled(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* wcodes,
+                               const unsigned int* wbitmap, const signed char* we_in, const signed char* we_out, float* C,
+                               long long ldc, int M, int N, int K, int plain, int accumulate, void* stream) {
+  if (!xcodes || !xe || !wcodes || !we_in || !C || M <= 0 || N <= 0 || K <= 0) return MSQ_ERR_BAD_ARG;
+  if (!plain && (!wbitmap || !we_out)) return MSQ_ERR_BAD_ARG;
+  if (K % 32 != 0) return MSQ_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(xcodes) & 15) || (ldx % 16) || (reinterpret_cast<uintptr_t>(wcodes) & 15)) return MSQ_ERR_ALIGN;
+  Mx8Params P;
+  memset(&P, 0, sizeof(P));
+  P.wcodes = wcodes; P.wbitmap = wbitmap; P.we_in = we_in; P.we_out = we_out; P.xe = xe; P.C = C; P.ldc = ldc;
+  P.M = M; P.N = N; P.K = K; P.plain = plain; P.accumulate = accumulate;
+  const int bnx = M >= XMAXN ? XMAXN : ((M + 15) / 16) * 16;
+  P.bnx = bnx;
+  P.tiles_n = (N + XM - 1) / XM; P.tiles_m = (M + bnx - 1) / bnx;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int kblocks_total = (K + XBK - 1) / XBK;
+  int ksplit = 1;
+  while (P.tiles_n * P.tiles_m * ksplit * 2 <= sms && kblocks_total / (ksplit * 2) >= 4) ksplit *= 2;
+  P.ksplit = ksplit;
+  P.kb_per_split = (kblocks_total + ksplit - 1) / ksplit;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (ksplit > 1 && !accumulate) {
+    if (ldc == N) cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s);
+    else cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s);
+  }
+  CUtensorMap tmX;
+  int rc = make_tmap_2d(&tmX, xcodes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K, ldx, bnx, XBK);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(k_gemm_mx8, cudaFuncAttributeMaxDynamicSharedMemorySize, MX8_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
+    attr_set = true;
+  }
+  int grid = P.tiles_n * P.tiles_m * P.ksplit;
+  if (grid > sms) grid = sms;
+  k_gemm_mx8<<<grid, 512, MX8_SMEM, s>>>(tmX, P);
+  return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+}
+
+}  // extern "C"
