@@ -206,6 +206,14 @@ def extras(dev, dev_w, nel):
         ms = _time_ms(lambda: _tc.packed_linear(x, pw), 10)
         gemm["M%d" % M] = {"ms": ms, "TFLOPs": 2.0 * M * 4096 * 4096 / (ms * 1e-3) / 1e12}
     out["packed_gemm_k4096_n4096"] = gemm
+    # (4) same weight on the native block-scaled path (tcgen05 kind::mxf8f6f4), MX-FP8 activations
+    mx8 = {}
+    if _tc.mx8_weight_ok(pw):
+        for M in (16, 256, 4096):
+            xq = msq_b200.pack_mx(torch.randn(M, 4096, device=dev), 8, "fp8_e4m3", axes=[-1], block_size=32)
+            ms = _time_ms(lambda: _tc.packed_linear_mx8(xq, pw), 10)
+            mx8["M%d" % M] = {"ms": ms, "TFLOPs": 2.0 * M * 4096 * 4096 / (ms * 1e-3) / 1e12}
+    out["blockscaled_mxfp8_gemm_k4096_n4096"] = mx8
     return out
 
 

@@ -36,6 +36,13 @@ def _packable(weight, mx_specs):
             and weight.shape[1] % 32 == 0 and weight.shape[1] // 32 >= 2 and mx_specs["shared_exp_method"] == "max")
 
 
+def _mx8_activation_ok(x, mx_specs):
+    from .formats import _get_format_params
+    a = mx_specs["a_elem_format"]
+    return (a is not None and x.dim() == 2 and mx_specs["block_size"] == 32 and x.shape[1] % 32 == 0
+            and x.shape[1] // 32 >= 2 and _get_format_params(a)[:2] == (4, 5) and x.dtype == torch.float32)
+
+
 def linear_forward(input, weight, bias, mx_specs, packed_weight=None):
     bf_in = quantize_elemwise_op(input, mx_specs=mx_specs, round=mx_specs["round_output"])
     bf_bias = None
@@ -49,13 +56,17 @@ def linear_forward(input, weight, bias, mx_specs, packed_weight=None):
         bf_weight = quantize_elemwise_op(weight, mx_specs=mx_specs, round=mx_specs["round_weight"])
         packed_weight = _pack_weight(bf_weight, mx_specs)
     if packed_weight is not None and qis_input.shape[-1] == packed_weight.shape[1]:
-        output = _tc.packed_linear(qis_input, packed_weight).to(input.dtype)
-    else:
-        bf_weight = quantize_elemwise_op(weight, mx_specs=mx_specs, round=mx_specs["round_weight"])
-        qis_weight = quantize_mx_outlier_op(bf_weight, mx_specs, inlier_elem_format=mx_specs["w_elem_format"],
-                                            outlier_elem_format=mx_specs["w_elem_format"], axes=[1],
-                                            round=mx_specs["round_mx_output"])
-        output = f_linear(qis_input, qis_weight)
+        output = None
+        if _mx8_activation_ok(bf_in, mx_specs) and _tc.mx8_weight_ok(packed_weight):
+            # native block-scaled path: needs the activations as MX-FP8 codes with no outliers of their own
+            sb = mx_specs["scale_bits"] or 4
+            xq = pack_mx_outlier(bf_in, sb, sb, mx_specs["a_elem_format"], mx_specs["a_elem_format"], 5, [1], 32,
+                                 round=mx_specs["round_mx_output"], flush_fp32_subnorms=mx_specs["mx_flush_fp32_subnorms"],
+                                 variant=1)
+            if not bool((xq.bitmap != 0).any()):
+                output = _tc.packed_linear_mx8(xq, packed_weight).to(input.dtype)
+        if output is None:
+            output = _tc.packed_linear(qis_input, packed_weight).to(input.dtype)
     output = quantize_elemwise_op(output, mx_specs=mx_specs, round=mx_specs["round_output"])
     if bf_bias is not None:
         output = quantize_elemwise_op(output + bf_bias, mx_specs=mx_specs, round=mx_specs["round_output"])
