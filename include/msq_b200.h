@@ -177,6 +177,15 @@ int msq_gemm_mxfp8_blockscaled(const unsigned char* xcodes, long long ldx, const
                                const signed char* we_out, float* C, long long ldc, int M, int N, int K,
                                int plain, int accumulate, void* stream);
 
+/* compute-bound variant of the block-scaled path: widen the packed FP4 weight once to dense MX-FP8
+ * (E4M3 bytes [N,K] + UE8M0 scales [N,K/32]), then run the GEMM with both operands streamed by TMA. */
+int msq_widen_fp4_to_mxfp8(const unsigned char* wcodes, const unsigned int* wbitmap, const signed char* we_in,
+                           const signed char* we_out, unsigned char* out_bytes, unsigned char* out_sf,
+                           int N, int K, int plain, void* stream);
+int msq_gemm_mxfp8_dense(const unsigned char* xcodes, long long ldx, const signed char* xe,
+                         const unsigned char* wbytes, long long ldw, const unsigned char* wsf, float* C,
+                         long long ldc, int M, int N, int K, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,6 +116,11 @@ def packed_linear(x, pw, bias=None):
 
 
 N.register("msq_gemm_mxfp8_blockscaled", _i, [_p, _ll, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _p])
+N.register("msq_widen_fp4_to_mxfp8", _i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p])
+N.register("msq_gemm_mxfp8_dense", _i, [_p, _ll, _p, _p, _ll, _p, _p, _ll, _i, _i, _i, _i, _p])
+
+#: activation rows at and above which the weight is widened once and streamed through TMA
+MX8_DENSE_MIN_M = 512
 
 
 def mx8_weight_ok(pw):
@@ -151,6 +156,19 @@ def packed_linear_mx8(xq, pw, bias=None):
         M *= s_
     Nn = pw.shape[0]
     out = torch.empty(M, Nn, dtype=torch.float32, device=pw.codes.device)
+    if M >= MX8_DENSE_MIN_M and K % 128 == 0:
+        # compute-bound regime: widen the FP4 weight to E4M3 bytes once, then both operands stream through TMA
+        wb = torch.empty(Nn, K, dtype=torch.uint8, device=out.device)
+        wsf = torch.empty(Nn, K // 32, dtype=torch.uint8, device=out.device)
+        rc = N.lib().msq_widen_fp4_to_mxfp8(N.ptr(pw.codes), N.ptr(pw.bitmap), N.ptr(pw.e_in), N.ptr(pw.e_out), N.ptr(wb),
+                                            N.ptr(wsf), Nn, K, int(pw.plain), N.stream_ptr(out.device))
+        N.check(rc, "msq_widen_fp4_to_mxfp8")
+        rc = N.lib().msq_gemm_mxfp8_dense(N.ptr(xq.codes), K, N.ptr(xq.e_in), N.ptr(wb), K, N.ptr(wsf), N.ptr(out),
+                                          out.stride(0), M, Nn, K, 0, N.stream_ptr(out.device))
+        N.check(rc, "msq_gemm_mxfp8_dense")
+        if bias is not None:
+            out += bias.float()
+        return out.reshape(*xq.shape[:-1], Nn)
     rc = N.lib().msq_gemm_mxfp8_blockscaled(N.ptr(xq.codes), K, N.ptr(xq.e_in), N.ptr(pw.codes), N.ptr(pw.bitmap),
                                             N.ptr(pw.e_in), N.ptr(pw.e_out), N.ptr(out), out.stride(0), M, Nn, K,
                                             int(pw.plain), 0, N.stream_ptr(out.device))

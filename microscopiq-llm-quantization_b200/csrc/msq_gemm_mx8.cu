@@ -38,6 +38,8 @@ struct Mx8Params {
   int bnx, tiles_n, tiles_m, ksplit, kb_per_split;
   int plain;                  // weight has no outliers
   int accumulate;
+  int wdense;                 // 1: the weight tile comes pre-widened (E4M3 bytes) through TMA, scales from wsf
+  const uint8_t* wsf;         // dense mode: UE8M0 weight scales [N, K/32]
 };
 
 __device__ __forceinline__ uint64_t make_sf_desc(uint32_t smem_addr) {
@@ -69,7 +71,8 @@ __device__ __forceinline__ uint32_t make_idesc_mx8(int M, int N, int sf_id) {
          ((uint32_t)sf_id << 29);
 }
 
-__global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUtensorMap tmX, const Mx8Params P) {
+__global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                                                      const Mx8Params P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                      // W tiles (E4M3 bytes)
@@ -114,8 +117,9 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
         int tn, tm, kb0, nkb; tile_coords(t, tn, tm, kb0, nkb);
         for (int kb = kb0; kb < kb0 + nkb; ++kb) {
           tc::mbar_wait(&empty[stage], phase ^ 1);
-          tc::mbar_expect_tx(&full[stage], (uint32_t)(P.bnx * XBK));
+          tc::mbar_expect_tx(&full[stage], (uint32_t)(P.bnx * XBK + (P.wdense ? XA_BYTES : 0)));
           tc::tma_load_2d(sB + stage * XB_BYTES, &tmX, &full[stage], kb * XBK, tm * P.bnx);
+          if (P.wdense) tc::tma_load_2d(sA + stage * XA_BYTES, &tmW, &full[stage], kb * XBK, tn * XM);
           if (++stage == XSTAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -246,13 +250,47 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
     };
     Cursor fc, cc;
     cur_init(fc); cur_init(cc);
+    int stage = 0; uint32_t phase = 0;
+    if (P.wdense) {
+      // the weight bytes arrive by TMA; only the two scale-factor chunks are assembled here.  K % 128 == 0 in this
+      // mode, so one K-block's four scales are one aligned 32-bit word; the next stage's words are fetched before
+      // waiting for the current stage to drain.
+      auto ld_sf = [&](const Cursor& c, uint32_t& va, uint32_t& vb) {
+        va = 0x7F7F7F7Fu; vb = 0x7F7F7F7Fu;
+        if (!c.ok) return;
+        const int kb = c.kb0 + c.kb;
+        const int n = c.tn * XM + ptid, m = c.tm * P.bnx + ptid;
+        if (ptid < XM && n < P.N) va = __ldg(reinterpret_cast<const uint32_t*>(P.wsf + (long long)n * kblk32) + kb);
+        if (ptid < P.bnx && m < P.M)
+          vb = __vadd4(__ldg(reinterpret_cast<const uint32_t*>(P.xe + (long long)m * kblk32) + kb), 0x7F7F7F7Fu);
+      };
+      uint32_t va, vb;
+      ld_sf(cc, va, vb);
+      while (cc.ok) {
+        cur_next(fc);
+        uint32_t na, nb;
+        ld_sf(fc, na, nb);
+        tc::mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sf = sSF + stage * XSF_BYTES;
+        if (ptid < XM) *reinterpret_cast<uint32_t*>(sf + (ptid & 31) * 16 + (ptid >> 5) * 4) = va;
+        if (ptid < P.bnx) {
+          const int rr = ptid & 127;
+          *reinterpret_cast<uint32_t*>(sf + 512 + (ptid >> 7) * 512 + (rr & 31) * 16 + (rr >> 5) * 4) = vb;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&full[stage]);
+        if (++stage == XSTAGES) { stage = 0; phase ^= 1; }
+        cur_next(cc);
+        va = na; vb = nb;
+      }
+    }
     Raw ring[PF][4];
 #pragma unroll
     for (int j = 0; j < PF - 1; ++j) {
-      if (fc.ok) { fetch(fc.tn * XM, fc.kb0 + fc.kb, ring[j]); cur_next(fc); }
+      if (!P.wdense && fc.ok) { fetch(fc.tn * XM, fc.kb0 + fc.kb, ring[j]); cur_next(fc); }
     }
-    int stage = 0; uint32_t phase = 0;
-    while (cc.ok) {
+    while (!P.wdense && cc.ok) {
 #pragma unroll
       for (int j = 0; j < PF; ++j) {
         if (cc.ok) {
@@ -311,6 +349,42 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
   }
 }
 
+// packed FP4 weight -> dense E4M3 bytes [N, K] + UE8M0 scales [N, K/32] (outliers folded as in k_gemm_mx8)
+__global__ void __launch_bounds__(256) k_widen_fp4_e4m3(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ bitmap,
+                                                        const int8_t* __restrict__ e_in, const int8_t* __restrict__ e_out,
+                                                        uint8_t* __restrict__ out, uint8_t* __restrict__ sf, long long nchunks,
+                                                        int K, int plain) {
+  const long long c = (long long)blockIdx.x * 256 + threadIdx.x;      // one chunk = 16 consecutive K elements
+  if (c >= nchunks) return;
+  const long long e0 = c * 16;
+  const long long blk = e0 >> 5;
+  const int k = (int)(e0 % K);
+  const uint2 cw = __ldg(reinterpret_cast<const uint2*>(codes + (e0 >> 1)));
+  const int ei = e_in[blk], eo = plain ? 0 : e_out[blk];
+  const uint32_t t0 = 0x3C383000u, t1 = 0x4C484440u;
+  auto widen4 = [&](uint32_t c4) {
+    const uint32_t mag = __byte_perm(t0, t1, c4 & 0x7777u);
+    const uint32_t s = c4 & 0x8888u;
+    return mag | ((s << 4) & 0x80u) | ((s << 8) & 0x8000u) | ((s << 12) & 0x800000u) | ((s << 16) & 0x80000000u);
+  };
+  uint32_t w[4] = {widen4(cw.x & 0xFFFFu), widen4(cw.x >> 16), widen4(cw.y & 0xFFFFu), widen4(cw.y >> 16)};
+  if (!plain) {
+    uint32_t ob = (__ldg(bitmap + (e0 >> 5)) >> (k & 31)) & 0xFFFFu;
+    const EncC enc8 = make_enc(4, 5);
+    while (ob) {
+      const int e = __ffs(ob) - 1;
+      ob &= ob - 1;
+      const uint32_t code = ((e < 8 ? cw.x : cw.y) >> (4 * (e & 7))) & 0xFu;
+      const float v = __fmul_rn(decode_elem(code, 2, 3), pow2i(max(-60, min(60, eo - 2 * ei))));
+      const uint32_t b8 = (eo == MSQ_EXP_NAN) ? 0x7Fu : (encode_fast(v, enc8) & 0xFFu);
+      const int ws = e >> 2, sh = (e & 3) * 8;
+      w[ws] = (w[ws] & ~(0xFFu << sh)) | (b8 << sh);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + e0) = make_uint4(w[0], w[1], w[2], w[3]);
+  if ((e0 & 31) == 0) sf[blk] = (uint8_t)((ei + 127) & 0xFF);
+}
+
 }  // namespace msq
 
 using namespace msq;
@@ -321,17 +395,15 @@ extern "C" {
 //   xcodes [M, K] E4M3 bytes (ld = ldx bytes), xe int8 [M, K/32]         (plain MX-FP8 activations)
 //   wcodes / wbitmap / we_in / we_out: packed FP4 weight, block 32 along K (plain != 0: no outliers)
 // The caller guarantees that every outlier block satisfies -6 <= e_out - 2 e_in <= 6 (exact E4M3 folding).
-int msq_gemm_mxfp8_blockscaled(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* wcodes,
-                               const unsigned int* wbitmap, const signed char* we_in, const signed char* we_out, float* C,
-                               long long ldc, int M, int N, int K, int plain, int accumulate, void* stream) {
-  if (!xcodes || !xe || !wcodes || !we_in || !C || M <= 0 || N <= 0 || K <= 0) return MSQ_ERR_BAD_ARG;
-  if (!plain && (!wbitmap || !we_out)) return MSQ_ERR_BAD_ARG;
-  if (K % 32 != 0) return MSQ_ERR_UNSUPPORTED;
-  if ((reinterpret_cast<uintptr_t>(xcodes) & 15) || (ldx % 16) || (reinterpret_cast<uintptr_t>(wcodes) & 15)) return MSQ_ERR_ALIGN;
+static int launch_mx8(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* wcodes,
+                      const unsigned int* wbitmap, const signed char* we_in, const signed char* we_out,
+                      const unsigned char* wdense, long long ldw, const unsigned char* wsf, float* C, long long ldc, int M,
+                      int N, int K, int plain, int accumulate, cudaStream_t s) {
   Mx8Params P;
   memset(&P, 0, sizeof(P));
   P.wcodes = wcodes; P.wbitmap = wbitmap; P.we_in = we_in; P.we_out = we_out; P.xe = xe; P.C = C; P.ldc = ldc;
   P.M = M; P.N = N; P.K = K; P.plain = plain; P.accumulate = accumulate;
+  P.wdense = wdense != nullptr; P.wsf = wsf;
   const int bnx = M >= XMAXN ? XMAXN : ((M + 15) / 16) * 16;
   P.bnx = bnx;
   P.tiles_n = (N + XM - 1) / XM; P.tiles_m = (M + bnx - 1) / bnx;
@@ -343,14 +415,19 @@ int msq_gemm_mxfp8_blockscaled(const unsigned char* xcodes, long long ldx, const
   while (P.tiles_n * P.tiles_m * ksplit * 2 <= sms && kblocks_total / (ksplit * 2) >= 4) ksplit *= 2;
   P.ksplit = ksplit;
   P.kb_per_split = (kblocks_total + ksplit - 1) / ksplit;
-  cudaStream_t s = (cudaStream_t)stream;
   if (ksplit > 1 && !accumulate) {
     if (ldc == N) cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s);
     else cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s);
   }
-  CUtensorMap tmX;
+  CUtensorMap tmX, tmW;
   int rc = make_tmap_2d(&tmX, xcodes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K, ldx, bnx, XBK);
   if (rc) return rc;
+  if (wdense) {
+    rc = make_tmap_2d(&tmW, wdense, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, ldw, XM, XBK);
+    if (rc) return rc;
+  } else {
+    tmW = tmX;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(k_gemm_mx8, cudaFuncAttributeMaxDynamicSharedMemorySize, MX8_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
@@ -358,8 +435,43 @@ int msq_gemm_mxfp8_blockscaled(const unsigned char* xcodes, long long ldx, const
   }
   int grid = P.tiles_n * P.tiles_m * P.ksplit;
   if (grid > sms) grid = sms;
-  k_gemm_mx8<<<grid, 512, MX8_SMEM, s>>>(tmX, P);
+  k_gemm_mx8<<<grid, 512, MX8_SMEM, s>>>(tmX, tmW, P);
   return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+}
+
+int msq_gemm_mxfp8_blockscaled(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* wcodes,
+                               const unsigned int* wbitmap, const signed char* we_in, const signed char* we_out, float* C,
+                               long long ldc, int M, int N, int K, int plain, int accumulate, void* stream) {
+  if (!xcodes || !xe || !wcodes || !we_in || !C || M <= 0 || N <= 0 || K <= 0) return MSQ_ERR_BAD_ARG;
+  if (!plain && (!wbitmap || !we_out)) return MSQ_ERR_BAD_ARG;
+  if (K % 32 != 0) return MSQ_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(xcodes) & 15) || (ldx % 16) || (reinterpret_cast<uintptr_t>(wcodes) & 15)) return MSQ_ERR_ALIGN;
+  return launch_mx8(xcodes, ldx, xe, wcodes, wbitmap, we_in, we_out, nullptr, 0, nullptr, C, ldc, M, N, K, plain, accumulate,
+                    (cudaStream_t)stream);
+}
+
+// packed FP4 weight -> dense MX-FP8 operand: E4M3 bytes [N, K] + UE8M0 scales [N, K/32]
+int msq_widen_fp4_to_mxfp8(const unsigned char* wcodes, const unsigned int* wbitmap, const signed char* we_in,
+                           const signed char* we_out, unsigned char* out_bytes, unsigned char* out_sf, int N, int K, int plain,
+                           void* stream) {
+  if (!wcodes || !we_in || !out_bytes || !out_sf || N <= 0 || K <= 0 || (K % 32)) return MSQ_ERR_BAD_ARG;
+  if (!plain && (!wbitmap || !we_out)) return MSQ_ERR_BAD_ARG;
+  const long long nchunks = (long long)N * K / 16;
+  k_widen_fp4_e4m3<<<(unsigned)((nchunks + 255) / 256), 256, 0, (cudaStream_t)stream>>>(wcodes, wbitmap, we_in, we_out, out_bytes,
+                                                                                      out_sf, nchunks, K, plain);
+  return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+}
+
+// same contraction with BOTH operands dense MX-FP8 (bytes + UE8M0 scales): a pure TMA-fed block-scaled GEMM
+int msq_gemm_mxfp8_dense(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* wbytes,
+                         long long ldw, const unsigned char* wsf, float* C, long long ldc, int M, int N, int K, int accumulate,
+                         void* stream) {
+  if (!xcodes || !xe || !wbytes || !wsf || !C || M <= 0 || N <= 0 || K <= 0) return MSQ_ERR_BAD_ARG;
+  if (K % 128 != 0) return MSQ_ERR_UNSUPPORTED;          // scale words are read four K-blocks at a time
+  if ((reinterpret_cast<uintptr_t>(xe) & 3) || (reinterpret_cast<uintptr_t>(wsf) & 3)) return MSQ_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(xcodes) & 15) || (ldx % 16) || (reinterpret_cast<uintptr_t>(wbytes) & 15) || (ldw % 16)) return MSQ_ERR_ALIGN;
+  return launch_mx8(xcodes, ldx, xe, nullptr, nullptr, nullptr, nullptr, wbytes, ldw, wsf, C, ldc, M, N, K, 1, accumulate,
+                    (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -15,7 +15,7 @@ for K in (4096, 8192):
     W = torch.randn(K, K, device='cuda')*0.02
     pw = msq_b200.pack_mx_outlier(W, 8,8,'fp4_e2m1','fp4_e2m1',5,[1],32, variant=1)
     print('mx8 ok:', _tc.mx8_weight_ok(pw))
-    for Mx in (16, 256, 1024, 4096):
+    for Mx in (16, 256, 1024, 4096, 8192):
         x = torch.randn(Mx, K, device='cuda')
         xq = msq_b200.pack_mx(x, 8, 'fp8_e4m3', axes=[-1], block_size=32)
         ms = timeit(lambda: _tc.packed_linear_mx8(xq, pw))
