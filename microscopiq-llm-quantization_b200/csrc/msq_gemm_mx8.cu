@@ -218,23 +218,24 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
       }
     };
     // activation scale chunks: thread t < bnx handles activation row t of the tile (4 K-blocks = one 32-bit word)
-    auto write_sfb = [&](int stage, int m0, int kb) {
-      if (ptid < P.bnx) {
-        const int m = m0 + ptid;
-        uint32_t v = 0x7F7F7F7Fu;
-        if (m < P.M) {
-          uint32_t raw4 = 0;
+    const bool sf_words = (kblk32 & 3) == 0 && (reinterpret_cast<uintptr_t>(P.xe) & 3) == 0;
+    auto load_sfb = [&](int m0, int kb) -> uint32_t {
+      const int m = m0 + ptid;
+      if (ptid >= P.bnx || m >= P.M) return 0x7F7F7F7Fu;
+      if (sf_words) return __vadd4(__ldg(reinterpret_cast<const uint32_t*>(P.xe + (long long)m * kblk32) + kb), 0x7F7F7F7Fu);
+      uint32_t raw4 = 0;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int kbq = kb * 4 + q;
-            const uint32_t b = (kbq < kblk32) ? ((uint32_t)(__ldg(P.xe + (long long)m * kblk32 + kbq) + 127) & 0xFFu) : 0x7Fu;
-            raw4 |= b << (8 * q);
-          }
-          v = raw4;
-        }
-        uint8_t* sfb = sSF + stage * XSF_BYTES + 512 + (ptid >> 7) * 512;
+      for (int q = 0; q < 4; ++q) {
+        const int kbq = kb * 4 + q;
+        const uint32_t b = (kbq < kblk32) ? ((uint32_t)(__ldg(P.xe + (long long)m * kblk32 + kbq) + 127) & 0xFFu) : 0x7Fu;
+        raw4 |= b << (8 * q);
+      }
+      return raw4;
+    };
+    auto store_sfb = [&](int stage, uint32_t v) {
+      if (ptid < P.bnx) {
         const int rr = ptid & 127;
-        *reinterpret_cast<uint32_t*>(sfb + (rr & 31) * 16 + (rr >> 5) * 4) = v;
+        *reinterpret_cast<uint32_t*>(sSF + stage * XSF_BYTES + 512 + (ptid >> 7) * 512 + (rr & 31) * 16 + (rr >> 5) * 4) = v;
       }
     };
     struct Cursor { int t, tn, tm, kb0, nkb, kb; bool ok; };
@@ -259,10 +260,9 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
         va = 0x7F7F7F7Fu; vb = 0x7F7F7F7Fu;
         if (!c.ok) return;
         const int kb = c.kb0 + c.kb;
-        const int n = c.tn * XM + ptid, m = c.tm * P.bnx + ptid;
+        const int n = c.tn * XM + ptid;
         if (ptid < XM && n < P.N) va = __ldg(reinterpret_cast<const uint32_t*>(P.wsf + (long long)n * kblk32) + kb);
-        if (ptid < P.bnx && m < P.M)
-          vb = __vadd4(__ldg(reinterpret_cast<const uint32_t*>(P.xe + (long long)m * kblk32) + kb), 0x7F7F7F7Fu);
+        vb = load_sfb(c.tm * P.bnx, kb);
       };
       uint32_t va, vb;
       ld_sf(cc, va, vb);
@@ -273,10 +273,7 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
         tc::mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sf = sSF + stage * XSF_BYTES;
         if (ptid < XM) *reinterpret_cast<uint32_t*>(sf + (ptid & 31) * 16 + (ptid >> 5) * 4) = va;
-        if (ptid < P.bnx) {
-          const int rr = ptid & 127;
-          *reinterpret_cast<uint32_t*>(sf + 512 + (ptid >> 7) * 512 + (rr & 31) * 16 + (rr >> 5) * 4) = vb;
-        }
+        store_sfb(stage, vb);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&full[stage]);
@@ -286,18 +283,27 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
       }
     }
     Raw ring[PF][4];
+    uint32_t sfb_ring[PF];
 #pragma unroll
     for (int j = 0; j < PF - 1; ++j) {
-      if (!P.wdense && fc.ok) { fetch(fc.tn * XM, fc.kb0 + fc.kb, ring[j]); cur_next(fc); }
+      if (!P.wdense && fc.ok) {
+        fetch(fc.tn * XM, fc.kb0 + fc.kb, ring[j]);
+        sfb_ring[j] = load_sfb(fc.tm * P.bnx, fc.kb0 + fc.kb);
+        cur_next(fc);
+      }
     }
     while (!P.wdense && cc.ok) {
 #pragma unroll
       for (int j = 0; j < PF; ++j) {
         if (cc.ok) {
-          if (fc.ok) { fetch(fc.tn * XM, fc.kb0 + fc.kb, ring[(j + PF - 1) % PF]); cur_next(fc); }
+          if (fc.ok) {
+            fetch(fc.tn * XM, fc.kb0 + fc.kb, ring[(j + PF - 1) % PF]);
+            sfb_ring[(j + PF - 1) % PF] = load_sfb(fc.tm * P.bnx, fc.kb0 + fc.kb);
+            cur_next(fc);
+          }
           tc::mbar_wait(&empty[stage], phase ^ 1);
           convert(stage, ring[j], cc.tn * XM, cc.kb0 + cc.kb);
-          write_sfb(stage, cc.tm * P.bnx, cc.kb0 + cc.kb);
+          store_sfb(stage, sfb_ring[j]);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&full[stage]);
