@@ -43,6 +43,23 @@ template <int N, int START = 1> __device__ __forceinline__ float tree_sum_regs(f
     for (int i = 0; i + stride < N; i += 2 * stride) t[i] = __fadd_rn(t[i], t[i + stride]);
   return t[0];
 }
+// the same adjacent pairwise tree with two independent additions per packed FADD2:
+// level `s` adds t[i+s] into t[i] for i = 0, 2s, 4s, ...; additions (i, i+2s) share one instruction
+template <int N, int START = 1> __device__ __forceinline__ float tree_sum_regs2(float (&t)[N]) {
+#pragma unroll
+  for (int stride = START; stride < N; stride <<= 1) {
+#pragma unroll
+    for (int i = 0; i + stride < N; i += 4 * stride) {
+      if (i + 3 * stride < N) {
+        const float2 r = __fadd2_rn(make_float2(t[i], t[i + 2 * stride]), make_float2(t[i + stride], t[i + 3 * stride]));
+        t[i] = r.x; t[i + 2 * stride] = r.y;
+      } else {
+        t[i] = __fadd_rn(t[i], t[i + stride]);
+      }
+    }
+  }
+  return t[0];
+}
 template <int LPB> __device__ __forceinline__ float grp_max(float v) {
 #pragma unroll
   for (int o = LPB / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -111,6 +128,19 @@ __device__ __forceinline__ float qelem_mx_bounded(float x, bool isf, int min_exp
   return fminf(fmaxf(y, -mx), mx);
 }
 
+// floor(log2(a)) for finite a >= 0 with the reference's "0 -> FP32_MIN_NORMAL" (quant.py:520-523), branch-free
+__device__ __forceinline__ int floor_log2_or_min(float a) {
+  const int u = __float_as_int(a);
+  const int be = u >> 23;
+  const int sub = (u ? 31 - __clz(u) : 23) - 149;     // subnormals; u == 0 gives -126
+  return be ? be - 127 : sub;
+}
+// clamp_scale_exp without branches; S = 2^(scale_bits-1) - 1, U = value taken below -S
+__device__ __forceinline__ int clamp_scale_sel(int e, int S, int U) {
+  e = (e < -S) ? U : e;
+  return (e > S) ? MSQ_EXP_NAN : e;
+}
+
 struct BlockOut {
   uint32_t mask;   // bit i set: x[i] is an outlier
   int e_in, e_out; // clamped shared exponents (MSQ_EXP_NAN on overflow)
@@ -140,6 +170,19 @@ __device__ __forceinline__ float2 blend2(float2 a, float2 b, float2 m, float2 nm
 }
 // c_i + m*(c_o - c_i) for exactly representable constants
 __device__ __forceinline__ float2 cblend2(float ci, float dco, float2 m) { return __ffma2_rn(f2s(dco), m, f2s(ci)); }
+
+// comparison straight to a 1.0f / 0.0f value (SASS FSET.BF): keeps the 16 per-block comparisons out of the
+// 7 predicate registers (the compiler otherwise spills them through a bit-mask register)
+__device__ __forceinline__ float fset_gt(float a, float b) {
+  float d;
+  asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ float fset_lt(float a, float b) {
+  float d;
+  asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
 
 struct ElemConsts {      // per-format constants of the float-domain rounding
   float L, H;            // 2^lo, 2^hi  (ints: 1, 1)
@@ -190,18 +233,29 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
     } else {
       t[0] = fabsf(x[0]);
     }
-    const float s = grp_sum_tree<LPB>(tree_sum_regs<N, (N >= 2 ? 2 : 1)>(t));
+    const float s = grp_sum_tree<LPB>(tree_sum_regs2<N, (N >= 2 ? 2 : 1)>(t));
     bad = !(s <= 3.402823466e38f);    // an Inf/NaN element (or an overflowing sum) makes it non-finite
     // BS is a power of two here, so multiplying by 1/BS is the division of utils/quant.py:477 exactly
     constexpr float inv_bs = 1.0f / (float)BS;
     static_assert((BS & (BS - 1)) == 0, "fast mappings use power-of-two blocks");
     const float mean = __fmul_rn(s, inv_bs);
+    if (N % 4 == 0) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const float d = __fsub_rn(fabsf(x[i]), mean);
-      t[i] = __fmul_rn(d, d);
+      for (int i = 0; i < N; i += 4) {      // squares paired the way the first tree level consumes them
+        const float d0 = __fsub_rn(fabsf(x[i]), mean), d1 = __fsub_rn(fabsf(x[i + 1]), mean);
+        const float d2 = __fsub_rn(fabsf(x[i + 2]), mean), d3 = __fsub_rn(fabsf(x[i + 3]), mean);
+        const float2 a = __fmul2_rn(make_float2(d0, d2), make_float2(d0, d2));
+        const float2 b = __fmul2_rn(make_float2(d1, d3), make_float2(d1, d3));
+        t[i] = a.x; t[i + 2] = a.y; t[i + 1] = b.x; t[i + 3] = b.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const float d = __fsub_rn(fabsf(x[i]), mean);
+        t[i] = __fmul_rn(d, d);
+      }
     }
-    const float q = grp_sum_tree<LPB>(tree_sum_regs<N>(t));
+    const float q = grp_sum_tree<LPB>(tree_sum_regs2<N>(t));
     const float sd = __fsqrt_rn(__fmul_rn(q, inv_bs));
     const float w = __fmul_rn(c.std_dev, sd);
     l = __fsub_rn(mean, w); h = __fadd_rn(mean, w);
@@ -218,18 +272,34 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const float li = EXT ? lo_e[i] : l, hi_i = EXT ? hi_e[i] : h;
-    mf[i] = ((x[i] < li) | (x[i] > hi_i)) ? 1.0f : 0.0f;
+    mf[i] = fmaxf(fset_lt(x[i], li), fset_gt(x[i], hi_i));      // 0/1 float mask without predicates
     if (CNT) fcnt = __fadd_rn(fcnt, mf[i]);
-    t1[i] = __fmul_rn(x[i], mf[i]);
-    x[i] = __fmul_rn(x[i], __fsub_rn(1.0f, mf[i]));
-    m_in = fmaxf(m_in, fabsf(x[i]));
+  }
+  if (N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+      const float2 m = f2(mf[i], mf[i + 1]), xv = f2(x[i], x[i + 1]);
+      const float2 nm = __ffma2_rn(m, f2s(-1.0f), f2s(1.0f));       // 1 - mask, exact
+      const float2 to = __fmul2_rn(xv, m), ti = __fmul2_rn(xv, nm);
+      t1[i] = to.x; t1[i + 1] = to.y; x[i] = ti.x; x[i + 1] = ti.y;
+      m_in = fmaxf(m_in, fmaxf(fabsf(ti.x), fabsf(ti.y)));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      t1[i] = __fmul_rn(x[i], mf[i]);
+      x[i] = __fmul_rn(x[i], __fsub_rn(1.0f, mf[i]));
+      m_in = fmaxf(m_in, fabsf(x[i]));
+    }
   }
   if (CNT) o.cnt = grp_add<LPB>((int)fcnt);
   m_in = grp_max<LPB>(m_in);
 
-  const int E_in = (m_in == 0.0f) ? -126 : floor_log2f(m_in);
+  const int S_in = (1 << (c.sb_in - 1)) - 1, S_out = (1 << (c.sb_out - 1)) - 1;
+  const int U_in = (c.variant == 0 && S_in > 20) ? -20 : -S_in, U_out = (c.variant == 0 && S_out > 20) ? -20 : -S_out;
+  const int E_in = floor_log2_or_min(m_in);
   const bool flush = c.flush && (E_in <= -127);
-  o.e_in = clamp_scale_exp(E_in - c.fin.emax, c.sb_in, c.variant == 0);
+  o.e_in = clamp_scale_sel(E_in - c.fin.emax, S_in, U_in);
   if (bad) o.st |= MSQ_ST_NONFINITE_INPUT;
   if (o.e_in == MSQ_EXP_NAN) o.st |= MSQ_ST_EXP_IN_OVERFLOW;
   const bool dead_in = bad || o.e_in == MSQ_EXP_NAN;
@@ -238,14 +308,23 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
 
   // level-1 scaling of the outliers, t = outlier_val * 2^e_in (quant.py:94); their maximum gives e_out
   float m_out = 0.0f;
+  if (N % 2 == 0) {
 #pragma unroll
-  for (int i = 0; i < N; ++i) {
-    t1[i] = __fmul_rn(t1[i], s_in);
-    m_out = fmaxf(m_out, fabsf(t1[i]));
+    for (int i = 0; i < N; i += 2) {
+      const float2 ts = __fmul2_rn(f2(t1[i], t1[i + 1]), f2s(s_in));
+      t1[i] = ts.x; t1[i + 1] = ts.y;
+      m_out = fmaxf(m_out, fmaxf(fabsf(ts.x), fabsf(ts.y)));
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      t1[i] = __fmul_rn(t1[i], s_in);
+      m_out = fmaxf(m_out, fabsf(t1[i]));
+    }
   }
   m_out = grp_max<LPB>(m_out);
-  const int E_out = (m_out == 0.0f) ? -126 : floor_log2f(m_out);
-  o.e_out = dead_in ? MSQ_EXP_NAN : clamp_scale_exp(E_out - c.fout.emax, c.sb_out, c.variant == 0);
+  const int E_out = floor_log2_or_min(m_out);
+  o.e_out = dead_in ? MSQ_EXP_NAN : clamp_scale_sel(E_out - c.fout.emax, S_out, U_out);
   if (!dead_in && o.e_out == MSQ_EXP_NAN) o.st |= MSQ_ST_EXP_OUT_OVERFLOW;
   const bool dead = dead_in || o.e_out == MSQ_EXP_NAN;
   const int e_out = dead ? 0 : o.e_out;
@@ -253,8 +332,12 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
   const RoundSel rs = make_round(c.rmode);
   const float inv_s_in_eff = flush ? 0.0f : inv_s_in;            // quant.py:80 (x*0 keeps the sign of x)
   const ElemConsts ci = elem_consts(c.fin), co = elem_consts(c.fout);
-  const float dL = __fsub_rn(co.L, ci.L), dH = __fsub_rn(co.H, ci.H), dD = __fsub_rn(co.down, ci.down),
-              dM = __fsub_rn(co.mx, ci.mx);
+  const float dM = __fsub_rn(co.mx, ci.mx);
+  // quantum = clamp(2^E(v), L, H) * D.  H = 2^127 never binds for float formats (v is finite), integer formats
+  // have L = H = 1; both cases are  max(2^E(v) * D', L*D)  with D' = D (floats) or 0 (integers).
+  const float Dp_i = c.fin.ebits ? ci.down : 0.0f, Dp_o = c.fout.ebits ? co.down : 0.0f;
+  const float LD_i = __fmul_rn(ci.L, ci.down), LD_o = __fmul_rn(co.L, co.down);
+  const float dDp = __fsub_rn(Dp_o, Dp_i), dLD = __fsub_rn(LD_o, LD_i);
   const EncC enc_i = make_enc(c.fin.ebits, c.fin.bits), enc_o = make_enc(c.fout.ebits, c.fout.bits);
   auto encode_sel = [&](float qv, bool isout) {
     EncC e;
@@ -275,19 +358,18 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
       const float2 vin = __fmul2_rn(f2(x[i], x[i + 1]), f2s(inv_s_in_eff));
       const float2 vout = __fmul2_rn(f2(t1[i], t1[i + 1]), f2s(inv_s_out));
       const float2 v = __fadd2_rn(vin, vout);
-      const float2 L2 = cblend2(ci.L, dL, m), H2 = cblend2(ci.H, dH, m), D2 = cblend2(ci.down, dD, m),
-                   M2 = cblend2(ci.mx, dM, m);
+      const float2 Dp2 = cblend2(Dp_i, dDp, m), LD2 = cblend2(LD_i, dLD, m), M2 = cblend2(ci.mx, dM, m);
       // quantum 2^(p - mant) with p = clamp(exponent(v), lo, hi), done on powers of two in the float
       // domain.  floor(|v| / quantum + addend) * quantum is computed without leaving the FMA pipe:
       //   a = |v| + addend*quantum   (the reference's fp32 add, scaled by an exact power of two)
       //   floor to a multiple of the quantum = (a (+rz) C) - C  with C = 2^23 * quantum
-      float2 P2;
-      P2.x = fminf(fmaxf(__int_as_float(__float_as_int(v.x) & 0x7F800000), L2.x), H2.x);
-      P2.y = fminf(fmaxf(__int_as_float(__float_as_int(v.y) & 0x7F800000), L2.y), H2.y);
-      const float2 qn = __fmul2_rn(P2, D2);                              // quantum
-      const float2 hq = __fmul2_rn(qn, f2s(rs.addend));                  // 0.5 quantum (nearest) or 0 (floor)
+      const float2 PD = __fmul2_rn(f2(__int_as_float(__float_as_int(v.x) & 0x7F800000),
+                                         __int_as_float(__float_as_int(v.y) & 0x7F800000)), Dp2);
+      const float2 qn = f2(fmaxf(PD.x, LD2.x), fmaxf(PD.y, LD2.y));      // quantum
+      // |v| + 0.5 quantum (nearest) or + 0 (floor): the product is an exact power of two, so the fused form is
+      // the reference's separate fp32 add
       const float2 Cq = __fmul2_rn(qn, f2s(8388608.0f));
-      const float ax = __fadd_rn(fabsf(v.x), hq.x), ay = __fadd_rn(fabsf(v.y), hq.y);
+      const float ax = __fmaf_rn(qn.x, rs.addend, fabsf(v.x)), ay = __fmaf_rn(qn.y, rs.addend, fabsf(v.y));
       float2 q;
       q.x = fminf(__fsub_rn(__fadd_rz(ax, Cq.x), Cq.x), M2.x);
       q.y = fminf(__fsub_rn(__fadd_rz(ay, Cq.y), Cq.y), M2.y);

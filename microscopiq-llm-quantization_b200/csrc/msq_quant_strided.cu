@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256, (BS <= 16 ? 4 : 1)) k_strided(const QPara
   }
   int st = 0;
   // PACK: one CTA = one packed segment (4 sub-iterations of 256 consecutive block-linear indices).
-  // fake-quant: 2-D grid, blockIdx.y = row of blocks (p, b), blockIdx.x*256 + tid = column: no divisions.
+  // fake-quant: 3-D grid, blockIdx.z = p, blockIdx.y = b, blockIdx.x*256 + tid = column: no divisions.
   constexpr int NSUB = PACK ? MSQ_SEG_BLOCKS / 256 : 1;
 #pragma unroll 1
   for (int sub = 0; sub < NSUB; ++sub) {
@@ -61,23 +61,26 @@ __global__ void __launch_bounds__(256, (BS <= 16 ? 4 : 1)) k_strided(const QPara
         p = pb / P.nblk; b = pb - p * P.nblk;
       }
     } else {
-      const int pb = (int)blockIdx.y;
+      b = (int)blockIdx.y; p = (int)blockIdx.z;   // uniform per CTA, no divisions
       j = (int)blockIdx.x * 256 + (int)threadIdx.x;
       active = j < post;
-      p = pb / P.nblk; b = pb - p * P.nblk;       // uniform per CTA
-      t0 = pb * post + j;
+      t0 = (p * P.nblk + b) * post + j;
     }
     if (active) base = (p * P.L + b * BS) * post + j;
     float x[BS];
     uint32_t code[BS];
     const int nv = active ? min(BS, P.L - b * BS) : 0;       // valid rows, the rest is zero padding
-    const float* pin = P.in + base;
+    // row addresses as base + (int64)(stride_bytes * i): one IMAD.WIDE per row instead of a 4-instruction
+    // multiply / sign-extend / 64-bit add sequence
+    const int sb = post * 4;
+    const char* pin = reinterpret_cast<const char*>(P.in + base);
+    auto row_in = [&](int i) { return reinterpret_cast<const float*>(pin + (long long)sb * i); };
     if (nv == BS) {
 #pragma unroll
-      for (int i = 0; i < BS; ++i) x[i] = __ldg(pin + i * post);
+      for (int i = 0; i < BS; ++i) x[i] = __ldg(row_in(i));
     } else {
 #pragma unroll
-      for (int i = 0; i < BS; ++i) x[i] = (i < nv) ? __ldg(pin + i * post) : 0.0f;
+      for (int i = 0; i < BS; ++i) x[i] = (i < nv) ? __ldg(row_in(i)) : 0.0f;
     }
 
     BlockOut bo;
@@ -99,14 +102,15 @@ __global__ void __launch_bounds__(256, (BS <= 16 ? 4 : 1)) k_strided(const QPara
 
     // ---- stores: lane = column, so every row is one coalesced warp store ----
     if (!PACK || P.deq) {
-      float* pout = P.deq + base;
+      char* pout = reinterpret_cast<char*>(P.deq + base);
+      auto row_out = [&](int i) { return reinterpret_cast<float*>(pout + (long long)sb * i); };
       if (nv == BS) {
 #pragma unroll
-        for (int i = 0; i < BS; ++i) pout[i * post] = x[i];
+        for (int i = 0; i < BS; ++i) *row_out(i) = x[i];
       } else {
 #pragma unroll
         for (int i = 0; i < BS; ++i)
-          if (i < nv) pout[i * post] = x[i];
+          if (i < nv) *row_out(i) = x[i];
       }
     }
     if (active) {
@@ -186,11 +190,10 @@ cudaError_t launch_strided(const QParams& P, bool outlier, size_t smem, cudaStre
   if (pack) {
     k<<<(unsigned)nseg, 256, smem, stream>>>(P);
   } else {
-    const long long rows_of_blocks = P.pre * P.nblk;
-    if (rows_of_blocks > 65535) {              // gridDim.y limit: fold into the segment mapping is not needed in
-      return cudaErrorInvalidConfiguration;    // practice (65535 * bs rows); the caller falls back to k_generic
+    if (P.nblk > 65535 || P.pre > 65535) {     // gridDim.y/z limits (65535 * bs rows); the caller falls back
+      return cudaErrorInvalidConfiguration;    // to k_generic
     }
-    dim3 grid((unsigned)((P.post + 255) / 256), (unsigned)rows_of_blocks);
+    dim3 grid((unsigned)((P.post + 255) / 256), (unsigned)P.nblk, (unsigned)P.pre);
     k<<<grid, 256, 0, stream>>>(P);
   }
   return cudaGetLastError();
