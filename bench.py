@@ -299,35 +299,15 @@ def main():
             _ops.mx_outlier(w, QCFG["in_sb"], QCFG["out_sb"], QCFG["in_fmt"], QCFG["out_fmt"], QCFG["std_dev"],
                             QCFG["axis"], QCFG["bs"], want=("deq",), check=False, out=o, status=status)
 
-    copy_in, copy_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-
     def step_e2e():
-        """public API (quantize_mx_outlier_v1 on CUDA tensors) fed from pinned host memory and read back
-        to pinned host memory; uploads, kernels and downloads of the 7 linears are pipelined on three
-        streams (PCIe is full duplex), every byte of every step crosses the bus inside the timed region."""
-        cur = torch.cuda.current_stream(dev)
-        staged = []
-        for hw in host_w:
-            with torch.cuda.stream(copy_in):
-                w = hw.to(dev, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_in)
-            staged.append((w, ev))
-        outs = []
-        for (w, ev), ho in zip(staged, host_out):
-            cur.wait_event(ev)
-            y = msq_b200.quantize_mx_outlier_v1(w, QCFG["in_sb"], QCFG["out_sb"], QCFG["in_fmt"], QCFG["out_fmt"],
-                                                "max", QCFG["std_dev"], [QCFG["axis"]], QCFG["bs"])
-            done = torch.cuda.Event()
-            done.record(cur)
-            with torch.cuda.stream(copy_out):
-                copy_out.wait_event(done)
-                ho.copy_(y, non_blocking=True)
-            y.record_stream(copy_out)
-            w.record_stream(cur)
-            outs.append(y)
-        copy_out.synchronize()
-        torch.cuda.synchronize()
+        """public API with HOST buffers: msq_b200.quantize_mx_outlier_host (the reference's quantize_mx_outlier_v1
+        signature on a CPU-resident weight) -> C ABI msq_host_quantize_mx_outlier_f32.  Pinned host tensors in, pinned
+        host tensors out; inside the library every linear is cut into 16 MiB chunks whose upload, kernel and download
+        overlap on three streams.  Every byte of every step crosses PCIe inside the timed region."""
+        for hw, ho in zip(host_w, host_out):
+            msq_b200.quantize_mx_outlier_host(hw, QCFG["in_sb"], QCFG["out_sb"], QCFG["in_fmt"], QCFG["out_fmt"], "max",
+                                              QCFG["std_dev"], [QCFG["axis"]], QCFG["bs"], out=ho, sync=False)
+        msq_b200.host_sync()
 
     sampler = ClockSampler(local)
     if rank == 0:

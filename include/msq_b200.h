@@ -186,6 +186,24 @@ int msq_gemm_mxfp8_dense(const unsigned char* xcodes, long long ldx, const signe
                          const unsigned char* wbytes, long long ldw, const unsigned char* wsf, float* C,
                          long long ldc, int M, int N, int K, int accumulate, void* stream);
 
+/* ---- host-buffer entry points --------------------------------------------------------------
+ * quantize_mx_outlier_v1 (utils/quant.py:147-266) as the reference's drivers call it on CPU-resident
+ * weights (llm/llama.py:94-121): h_in / h_out are HOST pointers (pinned for full PCIe speed), the
+ * tensor is cut into chunks of ~chunk_bytes (0 = 16 MiB) along its outermost blocked dimension and
+ * upload / kernel / download of successive chunks overlap on three streams.  Results are bit-identical
+ * to msq_quantize_mx_outlier_f32 on the whole tensor (MX blocks are independent).
+ * sync = 0 only queues the work: calls may be issued back to back without draining the pipeline;
+ * msq_host_sync waits for everything queued on the current device and returns the OR of the MSQ_ST_*
+ * bits raised since the previous msq_host_sync. */
+int msq_host_quantize_mx_outlier_f32(const float* h_in, float* h_out, long long pre, long long L, long long post,
+                                     int block_size, int in_scale_bits, int out_scale_bits,
+                                     int in_ebits, int in_mbits, int in_emax, float in_max_norm,
+                                     int out_ebits, int out_mbits, int out_emax, float out_max_norm,
+                                     float std_dev, int flush_fp32_subnorms, int rmode,
+                                     long long chunk_bytes, int sync);
+int msq_host_sync(int* status_out);
+int msq_host_release(void);
+
 #ifdef __cplusplus
 }
 #endif

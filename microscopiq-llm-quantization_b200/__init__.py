@@ -9,7 +9,7 @@ from .mx.specs import MxSpecs, finalize_mx_specs, apply_mx_specs, add_mx_args, g
 from .mx.elemwise_ops import quantize_elemwise_op, _quantize_elemwise_core  # noqa: F401
 from .mx.mx_ops import _quantize_mx, quantize_mx_op, _quantize_mx_outlier_v1, quantize_mx_outlier_op  # noqa: F401
 from .utils.quant import (quantize_mx_outlier_v1, quantize_mx_outlier_hessian, quantize, Quantizer,  # noqa: F401
-                          MXQuantizer)
+                          MXQuantizer, quantize_mx_outlier_host, host_sync)
 
 __version__ = "0.1.0"
 from .llm.gptq import GPTQ  # noqa: F401,E402

@@ -12,6 +12,12 @@ CHECK_STATUS = True
 
 _DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 
+_i, _ll, _f, _p = C.c_int, C.c_longlong, C.c_float, C.c_void_p
+N.register("msq_host_quantize_mx_outlier_f32", _i, [_p, _p, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _f,
+                                                     _f, _i, _i, _ll, _i])
+N.register("msq_host_sync", _i, [C.POINTER(C.c_int)])
+N.register("msq_host_release", _i, [])
+
 
 def _rmode(round):
     if isinstance(round, RoundingMode):
@@ -140,6 +146,50 @@ def mx_outlier(A, in_sb, out_sb, in_fmt, out_fmt, std_dev, axis, block_size, rou
     if r.deq is not None:
         r.deq = r.deq.to(A.dtype)
     return r
+
+
+def mx_outlier_host(A, in_sb, out_sb, in_fmt, out_fmt, std_dev, axis, block_size, round="nearest", flush=False,
+                    out=None, sync=True, chunk_bytes=0):
+    """MX+outlier fake-quant of a HOST tensor (utils/quant.py:147-266 called on a CPU-resident weight): chunked
+    upload / kernel / download pipeline inside libmsq_b200.so (csrc/msq_host.cu).  Pinned `A` / `out` run at PCIe
+    speed; with sync=False the call only queues work -- call host_sync() before reading `out`."""
+    if A.is_cuda:
+        raise ValueError("mx_outlier_host takes a host tensor (use mx_outlier for CUDA tensors)")
+    if not torch.cuda.is_available():
+        raise RuntimeError("msq_b200 needs a CUDA device: there is no CPU implementation")
+    x = A.detach().contiguous()
+    if x.dtype != torch.float32:
+        x = x.float()
+    pre, L, post = geometry(x.shape, axis)
+    bs = int(block_size) if block_size and block_size > 0 else L
+    fi, fo = fmt4(in_fmt), fmt4(out_fmt)
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
+    elif out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous() or out.shape != x.shape:
+        raise ValueError("out must be a contiguous fp32 host tensor of the input's shape")
+    rc = N.lib().msq_host_quantize_mx_outlier_f32(
+        x.data_ptr(), out.data_ptr(), pre, L, post, bs, int(in_sb), int(out_sb),
+        fi[0], fi[1], fi[2], fi[3], fo[0], fo[1], fo[2], fo[3],
+        float(std_dev), int(bool(flush)), _rmode(round), int(chunk_bytes), int(bool(sync)))
+    N.check(rc, "msq_host_quantize_mx_outlier_f32")
+    if sync:
+        host_sync()
+    else:
+        _HOST_KEEPALIVE.append((x, out))      # the queued copies read / write these buffers
+    return out if A.dtype == torch.float32 or not sync else out.to(A.dtype)
+
+
+_HOST_KEEPALIVE = []
+
+
+def host_sync(check=None):
+    """wait for the queued host-pipeline work of the current device; raises like the reference on bad blocks"""
+    st = C.c_int(0)
+    N.check(N.lib().msq_host_sync(C.byref(st)), "msq_host_sync")
+    del _HOST_KEEPALIVE[:]
+    if CHECK_STATUS if check is None else check:
+        raise_on_status(st.value)
+    return st.value
 
 
 def raise_on_status(s):

@@ -1,7 +1,9 @@
 """MicroScopiQ quantizers on B200 -- mirror of the reference's utils/quant.py.
 
 Public names, positional order, defaults and return arity follow utils/quant.py:23-454.
-All arithmetic runs in libmsq_b200.so; tensors must be CUDA tensors (no CPU fallback).
+All arithmetic runs in libmsq_b200.so on the GPU (no CPU fallback).  CUDA tensors are quantized in place on
+the device; quantize_mx_outlier_v1 also accepts a HOST tensor, as the reference's drivers pass it
+(llm/llama.py:94-121), and then streams it through the device in chunks (csrc/msq_host.cu).
 """
 import torch
 import torch.nn as nn
@@ -28,8 +30,31 @@ def quantize_mx_outlier_v1(A, inlier_scale_bits, outlier_scale_bits, inlier_elem
     """utils/quant.py:147-266 -- MX inliers + two-level-scaled outliers, dequantized."""
     if inlier_elem_format is None:
         return A
+    if isinstance(A, torch.Tensor) and not A.is_cuda:
+        return quantize_mx_outlier_host(A, inlier_scale_bits, outlier_scale_bits, inlier_elem_format,
+                                        outlier_elem_format, shared_exp_method, std_dev, axes, block_size, round,
+                                        flush_fp32_subnorms)
     return _mx_outlier(A, inlier_scale_bits, outlier_scale_bits, inlier_elem_format, outlier_elem_format,
                        shared_exp_method, std_dev, axes, block_size, round, flush_fp32_subnorms, ("deq",)).deq
+
+
+def quantize_mx_outlier_host(A, inlier_scale_bits, outlier_scale_bits, inlier_elem_format, outlier_elem_format,
+                             shared_exp_method="max", std_dev=2, axes=None, block_size=0, round="nearest",
+                             flush_fp32_subnorms=False, out=None, sync=True):
+    """quantize_mx_outlier_v1 for a host-resident tensor: same arguments, host tensor in, host tensor out
+    (pinned unless `out` is given).  sync=False queues the work and returns immediately; call host_sync()
+    before reading the result (lets consecutive tensors share one upload/compute/download pipeline)."""
+    assert inlier_scale_bits > 0 and outlier_scale_bits > 0
+    if shared_exp_method != "max":
+        raise NotImplementedError("shared_exp_method=%r for the outlier quantizer" % (shared_exp_method,))
+    if round == "dither":
+        raise NotImplementedError("dither rounding is not part of the B200 contract")
+    axis = _ops._single_axis(axes, A.ndim)
+    return _ops.mx_outlier_host(A, inlier_scale_bits, outlier_scale_bits, inlier_elem_format, outlier_elem_format,
+                                std_dev, axis, block_size, round, flush_fp32_subnorms, out=out, sync=sync)
+
+
+host_sync = _ops.host_sync
 
 
 def quantize_mx_outlier_hessian(A, inlier_scale_bits, outlier_scale_bits, inlier_elem_format, outlier_elem_format,
