@@ -53,7 +53,25 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
 
+    def _nvml(self):
+        """NVML (the library behind nvidia-smi) answers in microseconds, so the short timed region gets many samples"""
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            r = get_reasons(h)
+            self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for _, b in bits])
+            time.sleep(0.002)
+
     def run(self):
+        try:
+            return self._nvml()
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
@@ -367,7 +385,7 @@ def main():
                 "ms_per_step": e2e_s * 1e3},
         "gpu_launches": len(LAYER_SHAPES) * args.steps,
         "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
-                     "traffic": None, "kernel": "k_strided<16,4,outlier>", "peak_source": peak_src,
+                     "traffic": None, "kernel": "k_strided<BS=16, OUTLIER, fake-quant>", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": "8 B x rows x cols"},
     }
     tr = os.path.join(ROOT, "profiles", "traffic.json")
