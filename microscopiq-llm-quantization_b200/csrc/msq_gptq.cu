@@ -203,6 +203,7 @@ int msq_gptq_block(const float* W, long long ldw, float* Q, long long ldq, const
   P.c.fout = make_fmt(out_ebits, out_mbits, out_emax, out_max_norm);
   P.c.sb_in = in_scale_bits; P.c.sb_out = out_scale_bits; P.c.std_dev = std_dev; P.c.flush = flush_fp32_subnorms;
   P.c.variant = 0; P.c.mode = 0; P.c.rmode = rmode;
+  finish_cfg(P.c);
   const unsigned grid = (unsigned)((rows + 31) / 32);
   const size_t smem = (2 * 32 * TS + GB * GB) * sizeof(float);
   cudaStream_t s = (cudaStream_t)stream;

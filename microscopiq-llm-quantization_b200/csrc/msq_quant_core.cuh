@@ -15,6 +15,7 @@ namespace msq {
 
 struct QCfg {
   Fmt fin, fout;
+  EncC enc_i, enc_o;   // code encoders of fin / fout, filled by finish_cfg() on the host
   int sb_in, sb_out;
   float std_dev;
   int flush;
@@ -22,6 +23,11 @@ struct QCfg {
   int mode;      // plain  : 0 = python (+1e-6), 1 = spec/native
   int rmode;     // Round
 };
+
+__host__ inline void finish_cfg(QCfg& c) {
+  c.enc_i = make_enc(c.fin.ebits, c.fin.bits);
+  c.enc_o = make_enc(c.fout.ebits, c.fout.bits);
+}
 
 template <int LPB> __device__ __forceinline__ double grp_sum(double v) {
 #pragma unroll
@@ -214,6 +220,40 @@ __device__ __forceinline__ float qelem_pair_scalar(float v, float L, float H, fl
   return fminf(fmaxf(__fmul_rn(r, s2), -mx), mx);
 }
 
+// ---- element rounding of a pair on the packed fp32x2 path -------------------------------------------------
+// quantum = max(2^E(v) * Dp, LD)   (Dp = 2^-mant for float formats, 0 for integer formats; LD = 2^min_exp * 2^-mant)
+__device__ __forceinline__ float2 quantum2(float2 v, float2 Dp, float2 LD) {
+  const float2 PD = __fmul2_rn(f2(__int_as_float(__float_as_int(v.x) & 0x7F800000),
+                                  __int_as_float(__float_as_int(v.y) & 0x7F800000)), Dp);
+  return f2(fmaxf(PD.x, LD.x), fmaxf(PD.y, LD.y));
+}
+// torch-path rounding (elemwise_ops.py:59-72, nearest = floor(|y| + 0.5) with the fp32 add, floor): |q| clamped to M
+__device__ __forceinline__ float2 round_mag2_py(float2 v, float2 qn, float addend, float2 M) {
+  const float2 Cq = __fmul2_rn(qn, f2s(8388608.0f));
+  const float ax = __fmaf_rn(qn.x, addend, fabsf(v.x)), ay = __fmaf_rn(qn.y, addend, fabsf(v.y));
+  return f2(fminf(__fsub_rn(__fadd_rz(ax, Cq.x), Cq.x), M.x), fminf(__fsub_rn(__fadd_rz(ay, Cq.y), Cq.y), M.y));
+}
+// integer-mantissa rounding of cpp/quantize.cuh:88-149 on the exact value: nearest = half away from zero on the
+// truncated half-quantum count, even = ties to even, floor = truncation
+__device__ __forceinline__ float2 round_mag2_native(float2 v, float2 qn, int rmode, float2 M) {
+  const float2 Cq = __fmul2_rn(qn, f2s(8388608.0f));
+  float qx, qy;
+  if (rmode == RD_EVEN) {
+    qx = __fsub_rn(__fadd_rn(fabsf(v.x), Cq.x), Cq.x);
+    qy = __fsub_rn(__fadd_rn(fabsf(v.y), Cq.y), Cq.y);
+  } else if (rmode == RD_FLOOR) {
+    qx = __fsub_rn(__fadd_rz(fabsf(v.x), Cq.x), Cq.x);
+    qy = __fsub_rn(__fadd_rz(fabsf(v.y), Cq.y), Cq.y);
+  } else {
+    const float2 hq = __fmul2_rn(qn, f2s(0.5f)), Ch = __fmul2_rn(qn, f2s(4194304.0f));
+    const float tx = __fadd_rn(__fsub_rn(__fadd_rz(fabsf(v.x), Ch.x), Ch.x), hq.x);    // floor(2a/q) half quanta + one
+    const float ty = __fadd_rn(__fsub_rn(__fadd_rz(fabsf(v.y), Ch.y), Ch.y), hq.y);
+    qx = __fsub_rn(__fadd_rz(tx, Cq.x), Cq.x);
+    qy = __fsub_rn(__fadd_rz(ty, Cq.y), Cq.y);
+  }
+  return f2(fminf(qx, M.x), fminf(qy, M.y));
+}
+
 template <int N, int LPB, bool CODES, bool EXT, bool CNT = true>
 __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)[N], const QCfg& c,
                                                  const float* lo_e, const float* hi_e) {
@@ -338,7 +378,7 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
   const float Dp_i = c.fin.ebits ? ci.down : 0.0f, Dp_o = c.fout.ebits ? co.down : 0.0f;
   const float LD_i = __fmul_rn(ci.L, ci.down), LD_o = __fmul_rn(co.L, co.down);
   const float dDp = __fsub_rn(Dp_o, Dp_i), dLD = __fsub_rn(LD_o, LD_i);
-  const EncC enc_i = make_enc(c.fin.ebits, c.fin.bits), enc_o = make_enc(c.fout.ebits, c.fout.bits);
+  const EncC enc_i = c.enc_i, enc_o = c.enc_o;
   auto encode_sel = [&](float qv, bool isout) {
     EncC e;
     e.thresh = isout ? enc_o.thresh : enc_i.thresh; e.addc = isout ? enc_o.addc : enc_i.addc;
@@ -363,16 +403,8 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
       // domain.  floor(|v| / quantum + addend) * quantum is computed without leaving the FMA pipe:
       //   a = |v| + addend*quantum   (the reference's fp32 add, scaled by an exact power of two)
       //   floor to a multiple of the quantum = (a (+rz) C) - C  with C = 2^23 * quantum
-      const float2 PD = __fmul2_rn(f2(__int_as_float(__float_as_int(v.x) & 0x7F800000),
-                                         __int_as_float(__float_as_int(v.y) & 0x7F800000)), Dp2);
-      const float2 qn = f2(fmaxf(PD.x, LD2.x), fmaxf(PD.y, LD2.y));      // quantum
-      // |v| + 0.5 quantum (nearest) or + 0 (floor): the product is an exact power of two, so the fused form is
-      // the reference's separate fp32 add
-      const float2 Cq = __fmul2_rn(qn, f2s(8388608.0f));
-      const float ax = __fmaf_rn(qn.x, rs.addend, fabsf(v.x)), ay = __fmaf_rn(qn.y, rs.addend, fabsf(v.y));
-      float2 q;
-      q.x = fminf(__fsub_rn(__fadd_rz(ax, Cq.x), Cq.x), M2.x);
-      q.y = fminf(__fsub_rn(__fadd_rz(ay, Cq.y), Cq.y), M2.y);
+      const float2 qn = quantum2(v, Dp2, LD2);
+      float2 q = round_mag2_py(v, qn, rs.addend, M2);
       q.x = copysignf(q.x, v.x);
       q.y = copysignf(q.y, v.y);
       const bool o0 = mf[i] != 0.0f, o1 = mf[i + 1] != 0.0f;
@@ -464,10 +496,13 @@ __device__ __forceinline__ PlainOut core_plain(float (&x)[N], uint32_t (&code)[N
   m = grp_max<LPB>(m);
   if (ext_max) { m = fabsf(*ext_max); bad = !(m <= 3.402823466e38f); }
   const Fmt& f = c.fin;
+  // float-domain constants of the element rounding (see core_outlier)
+  const float Dp = f.ebits ? f.down : 0.0f, LD = __fmul_rn(f.L, f.down);
   if (c.mode == 0) {
-    const int E = (m == 0.0f) ? -126 : floor_log2f(m);
+    const int E = floor_log2_or_min(m);
     const bool flush = c.flush && (E <= -127);
-    int e = bad ? MSQ_EXP_NAN : clamp_scale_exp(E - f.emax, c.sb_in, false);
+    const int S = (1 << (c.sb_in - 1)) - 1;
+    int e = bad ? MSQ_EXP_NAN : clamp_scale_sel(E - f.emax, S, -S);
     o.e = e;
     if (e == MSQ_EXP_NAN) {
       o.st |= bad ? MSQ_ST_NONFINITE_INPUT : MSQ_ST_EXP_IN_OVERFLOW;
@@ -477,12 +512,28 @@ __device__ __forceinline__ PlainOut core_plain(float (&x)[N], uint32_t (&code)[N
     }
     const float s = pow2i(e);
     const float den = __fadd_rn(s, 1e-6f);                       // mx_ops.py:444
+    const float keep = flush ? 0.0f : 1.0f;                      // x * 0 keeps the sign like the reference's flush
+    if ((N % 2 == 0) && c.rmode != RD_EVEN) {
+      const float addend = (c.rmode == RD_FLOOR) ? 0.0f : 0.5f;
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      float v = __fdiv_rn(flush ? __fmul_rn(x[i], 0.0f) : x[i], den);
-      float qv = qelem_rt(v, f, c.rmode);
-      if (want_codes) code[i] = encode_fast(qv, make_enc(f.ebits, f.bits));
-      x[i] = __fmul_rn(qv, s);
+      for (int i = 0; i < N; i += 2) {
+        const float2 xs = __fmul2_rn(f2(x[i], x[i + 1]), f2s(keep));
+        const float2 v = f2(__fdiv_rn(xs.x, den), __fdiv_rn(xs.y, den));
+        const float2 qn = quantum2(v, f2s(Dp), f2s(LD));
+        float2 q = round_mag2_py(v, qn, addend, f2s(f.max_norm));
+        q.x = copysignf(q.x, v.x); q.y = copysignf(q.y, v.y);
+        if (want_codes) { code[i] = encode_fast(q.x, c.enc_i); code[i + 1] = encode_fast(q.y, c.enc_i); }
+        const float2 r = __fmul2_rn(q, f2s(s));
+        x[i] = r.x; x[i + 1] = r.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        float v = __fdiv_rn(flush ? __fmul_rn(x[i], 0.0f) : x[i], den);
+        float qv = qelem_rt(v, f, c.rmode);
+        if (want_codes) code[i] = encode_fast(qv, c.enc_i);
+        x[i] = __fmul_rn(qv, s);
+      }
     }
   } else {
     int be = bad ? 255 : ((__float_as_int(m) >> 23) & 0xFF);
@@ -496,12 +547,29 @@ __device__ __forceinline__ PlainOut core_plain(float (&x)[N], uint32_t (&code)[N
     const float s = __int_as_float((sh << 23) | mant);
     o.e = sh == 255 ? MSQ_EXP_NAN : sh - 127;
     if (sh == 255) o.st |= bad ? MSQ_ST_NONFINITE_INPUT : MSQ_ST_EXP_IN_OVERFLOW;
+    if ((N % 2 == 0) && sh != 255 && sh >= 0) {
+      // x / 2^k == x * 2^-k (both the correctly rounded value of the same real number)
+      const float inv = flush ? 0.0f : pow2i(127 - sh);
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      float v = flush ? 0.0f : __fdiv_rn(x[i], s);
-      float qv = qelem_native(v, f.bits, f.ebits, f.max_norm, c.rmode, true, true);
-      if (want_codes) code[i] = (qv == qv) ? encode_fast(qv, make_enc(f.ebits, f.bits)) : 0;
-      x[i] = __fmul_rn(qv, s);
+      for (int i = 0; i < N; i += 2) {
+        float2 v = __fmul2_rn(f2(x[i], x[i + 1]), f2s(inv));
+        if (flush) v = f2s(0.0f);                                 // mx.cuh:45 (plain zero, not x*0)
+        const float2 qn = quantum2(v, f2s(Dp), f2s(LD));
+        float2 q = round_mag2_native(v, qn, c.rmode, f2s(f.max_norm));
+        q.x = copysignf(q.x, v.x); q.y = copysignf(q.y, v.y);
+        q = __fadd2_rn(q, f2s(0.0f));                             // quantize.cuh returns +0 for a zero mantissa
+        if (want_codes) { code[i] = encode_fast(q.x, c.enc_i); code[i + 1] = encode_fast(q.y, c.enc_i); }
+        const float2 r = __fmul2_rn(q, f2s(s));
+        x[i] = r.x; x[i + 1] = r.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        float v = flush ? 0.0f : __fdiv_rn(x[i], s);
+        float qv = qelem_native(v, f.bits, f.ebits, f.max_norm, c.rmode, true, true);
+        if (want_codes) code[i] = (qv == qv) ? encode_fast(qv, c.enc_i) : 0;
+        x[i] = __fmul_rn(qv, s);
+      }
     }
   }
   return o;

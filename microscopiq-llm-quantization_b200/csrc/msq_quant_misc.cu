@@ -305,6 +305,7 @@ int msq_quantize_mx_outlier_f32(
   P.c.fout = make_fmt(out_ebits, out_mbits, out_emax, out_max_norm);
   P.c.sb_in = in_scale_bits; P.c.sb_out = out_scale_bits;
   P.c.std_dev = std_dev; P.c.flush = flush_fp32_subnorms; P.c.variant = variant; P.c.rmode = rmode; P.c.mode = 0;
+  finish_cfg(P.c);
   P.in = in; P.deq = deq; P.codes = codes; P.e_in = e_in; P.e_out = e_out; P.bitmap = bitmap; P.hi = hi;
   P.seg_cnt = seg_cnt; P.blk_cnt = blk_cnt; P.mask = mask; P.status = status; P.lo_ext = lo_ext; P.hi_ext = hi_ext;
   P.hi_w = msq_packed_hi_width(in_ebits, in_mbits, out_ebits, out_mbits);
@@ -327,6 +328,7 @@ int msq_quantize_mx_f32(
   P.c.fout = P.c.fin;
   P.c.sb_in = P.c.sb_out = scale_bits;
   P.c.flush = flush_fp32_subnorms; P.c.rmode = rmode; P.c.mode = mode;
+  finish_cfg(P.c);
   P.in = in; P.deq = deq; P.codes = codes; P.e_in = e_shared; P.status = status; P.ext_max = ext_max;
   return launch_quant(P, false, (cudaStream_t)stream, path);
 }

@@ -240,8 +240,13 @@ def test_outlier_status_flags(M):
         M.quantize_mx_outlier_v1(W.cuda(), 8, 8, "int2", "fp4", "max", 2, [0], 16)
     with pytest.raises(AssertionError):           # exponent above a 4-bit scale: NaN scale (quant.py:88)
         M.quantize_mx_outlier_v1((weights(64, 64, 5) * 1e6).cuda(), 4, 4, "fp4", "fp4", "max", 2, [0], 16)
-    with pytest.raises(RuntimeError):             # no CPU fallback
-        M.quantize_mx_outlier_v1(weights(64, 64, 5), 8, 8, "int2", "fp4", "max", 2, [0], 16)
+    # a host tensor is streamed through the GPU (csrc/msq_host.cu), never computed on the CPU
+    Wc = weights(64, 64, 5)
+    yc = M.quantize_mx_outlier_v1(Wc, 8, 8, "int2", "fp4", "max", 2, [0], 16)
+    assert not yc.is_cuda
+    assert_exact(yc, M.quantize_mx_outlier_v1(Wc.cuda(), 8, 8, "int2", "fp4", "max", 2, [0], 16))
+    with pytest.raises(RuntimeError):             # the other entry points take CUDA tensors only: no CPU fallback
+        M._quantize_mx(Wc, 8, "fp4_e2m1", block_size=16, axes=[0])
     assert M.quantize_mx_outlier_v1(W, 8, 8, None, "fp4") is W
 
 
