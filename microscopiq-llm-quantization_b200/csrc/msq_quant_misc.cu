@@ -187,15 +187,43 @@ __global__ void __launch_bounds__(256) k_elemwise(const T* __restrict__ in, T* _
     } else {
       for (int k = 0; k < VEC; ++k) v[k] = (i0 + k < n) ? in[i0 + k] : from_f32<T>(0.0f);
     }
+    auto slow = [&](float x) {
+      if (native) return qelem_native(x, f.bits, f.ebits, f.max_norm, rmode, saturate, allow_denorm);
+      if (rmode == RD_NEAREST) return qelem<RD_NEAREST>(x, f, saturate, allow_denorm);
+      if (rmode == RD_FLOOR) return qelem<RD_FLOOR>(x, f, saturate, allow_denorm);
+      return qelem<RD_EVEN>(x, f, saturate, allow_denorm);
+    };
+    if (VEC % 2 == 0 && (native || rmode != RD_EVEN)) {
+      // packed fp32x2 rounding (see core_outlier); values the magic-number rounding cannot hold (|x| >= 2^100,
+      // Inf, NaN) take the literal path
+      const float Dp = f.ebits ? f.down : 0.0f, LD = __fmul_rn(f.L, f.down);
+      const float addend = (rmode == RD_FLOOR) ? 0.0f : 0.5f;
+      const float inf = __int_as_float(0x7F800000);
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      float x = to_f32<T>(v[k]);
-      float y;
-      if (native) y = qelem_native(x, f.bits, f.ebits, f.max_norm, rmode, saturate, allow_denorm);
-      else if (rmode == RD_NEAREST) y = qelem<RD_NEAREST>(x, f, saturate, allow_denorm);
-      else if (rmode == RD_FLOOR) y = qelem<RD_FLOOR>(x, f, saturate, allow_denorm);
-      else y = qelem<RD_EVEN>(x, f, saturate, allow_denorm);
-      v[k] = from_f32<T>(y);
+      for (int k = 0; k < VEC; k += 2) {
+        const float2 x = f2(to_f32<T>(v[k]), to_f32<T>(v[k + 1]));
+        float2 y;
+        if (fabsf(x.x) < 1.2676506e30f && fabsf(x.y) < 1.2676506e30f) {
+          float2 a = x;
+          if (!allow_denorm && f.ebits) {                      // elemwise_ops.py:139-141 / quantize.cuh:104
+            a.x = (fabsf(a.x) >= f.L) ? a.x : (native ? 0.0f : __fmul_rn(0.0f, a.x));
+            a.y = (fabsf(a.y) >= f.L) ? a.y : (native ? 0.0f : __fmul_rn(0.0f, a.y));
+          }
+          const float2 qn = quantum2(a, f2s(Dp), f2s(LD));
+          const float2 big = f2s(3.0e38f);
+          float2 q = native ? round_mag2_native(a, qn, rmode, big) : round_mag2_py(a, qn, addend, big);
+          if (saturate || f.ebits == 0) { q.x = fminf(q.x, f.max_norm); q.y = fminf(q.y, f.max_norm); }
+          else { q.x = q.x > f.max_norm ? inf : q.x; q.y = q.y > f.max_norm ? inf : q.y; }
+          y.x = copysignf(q.x, a.x); y.y = copysignf(q.y, a.y);
+          if (native) y = __fadd2_rn(y, f2s(0.0f));            // quantize.cuh returns +0 for a zero mantissa
+        } else {
+          y.x = slow(x.x); y.y = slow(x.y);
+        }
+        v[k] = from_f32<T>(y.x); v[k + 1] = from_f32<T>(y.y);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) v[k] = from_f32<T>(slow(to_f32<T>(v[k])));
     }
     if (i0 + VEC <= n) {
       if (sizeof(T) * VEC == 16) *reinterpret_cast<uint4*>(out + i0) = *reinterpret_cast<uint4*>(v);

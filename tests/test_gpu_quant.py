@@ -284,3 +284,60 @@ def test_helpers(M):
     e = _shared_exponents(A, "max", [1])
     assert_exact(e, O.shared_exponent(X).squeeze(0))
     assert_exact(_undo_reshape_to_blocks(A, p, o, axes), W)
+
+
+def _adversarial_values():
+    """values that stress the packed rounding path: exact ties, one ulp either side of ties, binade edges,
+    subnormals, huge values, +-0, Inf, NaN"""
+    g = torch.Generator().manual_seed(77)
+    base = torch.randn(4096, generator=g) * torch.exp2(torch.randint(-20, 12, (4096,), generator=g).float())
+    k = torch.arange(0, 64, dtype=torch.float32)
+    ties = torch.cat([(k + 0.5) * s for s in (2.0 ** -9, 2.0 ** -6, 2.0 ** -3, 0.25, 0.5, 1.0, 2.0)])
+    near = torch.cat([torch.nextafter(ties, torch.full_like(ties, 1e30)), torch.nextafter(ties, torch.zeros_like(ties))])
+    pows = torch.exp2(torch.arange(-149, 128, dtype=torch.float32))
+    edge = torch.cat([pows, torch.nextafter(pows, torch.zeros_like(pows)), pows * 1.5, pows * 1.75])
+    special = torch.tensor([0.0, -0.0, float("inf"), float("-inf"), float("nan"), 3.4e38, -3.4e38, 1.3e30, 1.2e30,
+                            0.5 - 2.0 ** -25, 1.5 - 2.0 ** -24, 447.9, 448.0, 449.0, 464.0, 5.9, 6.0, 6.1, 7.0])
+    x = torch.cat([base, ties, -ties, near, -near, edge, -edge, special])
+    return x[: (x.numel() // 8) * 8].contiguous()
+
+
+@pytest.mark.parametrize("fmt", ["fp8_e4m3", "fp8_e5m2", "fp6_e3m2", "fp6_e2m3", "fp4_e2m1", "int8", "int4", "int2"])
+@pytest.mark.parametrize("rnd", ["nearest", "floor", "even"])
+def test_elemwise_adversarial_vs_oracle(M, fmt, rnd):
+    from msq_b200 import _ops
+    x = _adversarial_values()
+    eb, mb, _, mn, _ = M._get_format_params(fmt)
+    for sat in (True, False):
+        for den in (True, False):
+            y = _ops.elemwise(x.cuda(), mb, eb, mn, rnd, sat, den, native=False)
+            assert_exact(y, O.qelem(x, mb, eb, mn, rnd, sat, den), "%s %s sat=%s den=%s" % (fmt, rnd, sat, den))
+            finite = torch.isfinite(x)          # the native code's treatment of NaN/Inf bits is checked in test_ref_native
+            yn = _ops.elemwise(x[finite][: (int(finite.sum()) // 8) * 8].cuda(), mb, eb, mn, rnd, sat, den, native=True)
+            ref = O.qelem_native(x[finite][: (int(finite.sum()) // 8) * 8], mb, eb, mn, rnd, sat, den)
+            assert_exact(yn, ref, "native %s %s sat=%s den=%s" % (fmt, rnd, sat, den))
+
+
+@pytest.mark.parametrize("rnd", ["nearest", "floor", "even"])
+def test_bfloat_adversarial_vs_oracle(M, rnd):
+    from msq_b200.mx.elemwise_ops import _quantize_bfloat
+    x = _adversarial_values()
+    for bits in (16, 12, 10):
+        assert_exact(_quantize_bfloat(x.cuda(), bits, rnd), O.quantize_bfloat(x, bits, rnd), "bf%d %s" % (bits, rnd))
+        # fp16 tensors: the reference rounds |y| + 0.5 in fp16, the kernels compute in fp32 (DESIGN.md section 7):
+        # tolerance-only, a handful of ties may land on the neighbouring grid point
+        n = mismatches(_quantize_bfloat(x.cuda().half(), bits, rnd).float(), O.quantize_bfloat(x.half(), bits, rnd).float())
+        assert n <= x.numel() // 1000, "bf%d %s fp16 in: %d mismatches" % (bits, rnd, n)
+
+
+@pytest.mark.parametrize("fmt", ["fp8_e4m3", "fp6_e2m3", "fp4_e2m1", "int8", "int4"])
+@pytest.mark.parametrize("rnd", ["nearest", "floor", "even"])
+@pytest.mark.parametrize("mode", ["python", "spec"])
+def test_plain_mx_adversarial_vs_oracle(M, fmt, rnd, mode):
+    """block quantizer on values that sit on rounding ties after scaling, both arithmetic modes, both mappings"""
+    x = _adversarial_values()
+    x = x[torch.isfinite(x)]
+    x = x[: (x.numel() // 1024) * 1024].view(-1, 1024)
+    for axis, bs in ((1, 32), (0, 16), (1, 16)):
+        y = M._quantize_mx(x.cuda(), 8, fmt, axes=[axis], block_size=bs, round=rnd, custom_cuda=(mode == "spec"))
+        assert_exact(y, O.quantize_mx(x, 8, fmt, axis, bs, rnd, mode=mode), "%s %s %s axis%d" % (fmt, rnd, mode, axis))
