@@ -95,6 +95,154 @@ __global__ void __launch_bounds__(256) k_unpack_strided(const UParams P) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Fast strided unpack: lane = column, thread = one MX block, BS compile-time.
+//  * decoding is one shared-memory table lookup (2^wi inlier entries followed by 2^(wi+hi_w) outlier entries,
+//    built per CTA from decode_elem);
+//  * code / bitmap rows are fetched as whole 32-bit words shared by the lanes that need them;
+//  * the position of a warp's hi fields inside the segment stream comes from a prologue that popcounts the
+//    segment's bitmap words once (32 groups of 32 blocks), so the main loop has no CTA-wide synchronisation
+//    and its four sub-iterations are independent; inside a warp a shuffle scan gives the block offset and the
+//    popcount of the lower mask bits the element offset (no serial dependency, no branches);
+//  * only the used prefix of the hi stream is staged.
+// ---------------------------------------------------------------------------------------------------------
+// base + stride * i as one IMAD.WIDE
+__device__ __forceinline__ const char* row_at(const void* base, int stride_bytes, int i) {
+  long long a;
+  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(a) : "r"(stride_bytes), "r"(i), "l"(reinterpret_cast<long long>(base)));
+  return reinterpret_cast<const char*>(a);
+}
+
+// HWT: hi field width known at compile time (0 = no hi stream, 4), or -1 = run-time P.hi_w
+template <int BS, int HWT>
+__global__ void __launch_bounds__(256) k_unpack_strided_fast(const UParams P) {
+  constexpr bool HAS_HI = HWT != 0;
+  const int hw = HWT >= 0 ? HWT : P.hi_w;
+  extern __shared__ uint32_t s_dyn[];
+  __shared__ int s_off[MSQ_SEG_BLOCKS / 32 + 1];
+  const int wi = P.fin.width;
+  const int wo = wi + hw;                             // full outlier code width
+  float* lut = reinterpret_cast<float*>(s_dyn);       // [2^wi | 2^wo]
+  const int lut_n = (1 << wi) + (1 << wo);
+  uint32_t* s_hi = s_dyn + lut_n;
+  const int seg = (int)blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int post = (int)P.post;
+  constexpr int NGRP = MSQ_SEG_BLOCKS / 32;           // 32 groups of 32 blocks (= one warp's columns)
+  for (int i = threadIdx.x; i < lut_n; i += 256)
+    lut[i] = (i < (1 << wi)) ? decode_elem((uint32_t)i, P.fin.ebits, P.fin.bits)
+                             : decode_elem((uint32_t)(i - (1 << wi)), P.fout.ebits, P.fout.bits);
+  if (HAS_HI) {
+    // outliers per group: BS bitmap words each, BS consecutive threads reduce with shuffles
+    for (int w = threadIdx.x; w < NGRP * BS; w += 256) {
+      const int g = w / BS, i = w % BS;
+      const int t = seg * MSQ_SEG_BLOCKS + g * 32;
+      int cnt = 0;
+      if (t < (int)P.nblocks) {
+        const int pb = t / post, j = t - pb * post;
+        const int p = pb / P.nblk, b = pb - p * P.nblk;
+        if (i < min(BS, P.L - b * BS)) cnt = __popc(__ldg(P.bitmap + (((p * P.L + b * BS + i) * post + j) >> 5)));
+      }
+#pragma unroll
+      for (int o = BS / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if (i == 0) s_off[g] = cnt;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int tot;
+      const int ex = warp_excl_scan(s_off[lane], lane, tot);
+      s_off[lane] = ex;
+      if (lane == 0) s_off[NGRP] = tot;
+    }
+    __syncthreads();
+    const int words = (s_off[NGRP] * hw + 31) >> 5;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.hi + (long long)seg * P.hi_seg_stride);
+    for (int i = threadIdx.x; i < words; i += 256) s_hi[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const uint32_t cm = (1u << wi) - 1u, hm = (1u << hw) - 1u;
+  const int cshift = (lane * wi) & 31;                // this lane's slot inside the row's code word
+  const uint32_t* codes32 = reinterpret_cast<const uint32_t*>(P.codes) + ((lane * wi) >> 5);
+  const int cstride = (post >> 5) * wi * 4;           // bytes between the code words of consecutive rows
+  const int bstride = (post >> 5) * 4;                // same for bitmap words
+  const int sb = post * 4;
+#pragma unroll 2
+  for (int sub = 0; sub < MSQ_SEG_BLOCKS / 256; ++sub) {
+    const int t0 = seg * MSQ_SEG_BLOCKS + sub * 256 + (int)threadIdx.x;
+    const bool active = t0 < (int)P.nblocks;
+    int base = 0, b = 0;
+    if (active) {
+      const int pb = t0 / post;
+      const int j = t0 - pb * post;
+      const int p = pb / P.nblk; b = pb - p * P.nblk;
+      base = (p * P.L + b * BS) * post + j;
+    }
+    const int nv = active ? min(BS, P.L - b * BS) : 0;
+    const int ei = active ? P.e_in[t0] : 0, eo = (active && !P.plain) ? P.e_out[t0] : 0;
+    const int row32 = (base - lane) >> 5;             // index of this warp's 32-column group in row 0 of the block
+    const char* cp = reinterpret_cast<const char*>(codes32 + (long long)row32 * wi);
+    const char* bp = reinterpret_cast<const char*>(P.bitmap + row32);
+    uint32_t mask = 0, cw[BS];
+    if (nv == BS) {
+#pragma unroll
+      for (int i = 0; i < BS; ++i) {
+        cw[i] = __ldg(reinterpret_cast<const uint32_t*>(row_at(cp, cstride, i)));
+        if (!P.plain) mask |= ((__ldg(reinterpret_cast<const uint32_t*>(row_at(bp, bstride, i))) >> lane) & 1u) << i;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < BS; ++i) {
+        cw[i] = 0;
+        if (i < nv) {
+          cw[i] = __ldg(reinterpret_cast<const uint32_t*>(row_at(cp, cstride, i)));
+          if (!P.plain) mask |= ((__ldg(reinterpret_cast<const uint32_t*>(row_at(bp, bstride, i))) >> lane) & 1u) << i;
+        }
+      }
+    }
+    int k = 0;
+    if (HAS_HI) {
+      int wt;
+      k = s_off[sub * 8 + warp] + warp_excl_scan(__popc(mask), lane, wt);
+    }
+    const bool nan_blk = ei == MSQ_EXP_NAN || eo == MSQ_EXP_NAN;
+    const float s_in = pow2i(nan_blk ? 0 : ei), inv_s_in = pow2i(nan_blk ? 0 : -ei), s_out = pow2i(nan_blk ? 0 : eo);
+    // decode in place: cw[i] becomes the fp32 bits of element i
+#pragma unroll
+    for (int i = 0; i < BS; ++i) {
+      uint32_t c = (cw[i] >> cshift) & cm;
+      const uint32_t isout = (mask >> i) & 1u;
+      if (HAS_HI) {
+        const int bit = (k + __popc(mask & ((1u << i) - 1u))) * hw;
+        const uint32_t f = (s_hi[bit >> 5] >> (bit & 31)) & hm;
+        c |= (f & (0u - isout)) << wi;
+      }
+      const float q = lut[c + (isout << wi)];
+      float r = isout ? __fmul_rn(__fmul_rn(q, s_out), inv_s_in) : __fmul_rn(q, s_in);
+      r = nan_blk ? qnan() : __fadd_rn(r, 0.0f);
+      cw[i] = __float_as_uint(r);
+    }
+    if (P.out_f32) {
+      float* o = P.out_f32 + base;
+      if (nv == BS) {
+#pragma unroll
+        for (int i = 0; i < BS; ++i) *reinterpret_cast<uint32_t*>(const_cast<char*>(row_at(o, sb, i))) = cw[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < BS; ++i)
+          if (i < nv) *reinterpret_cast<uint32_t*>(const_cast<char*>(row_at(o, sb, i))) = cw[i];
+      }
+    }
+    if (P.out_bf16) {
+      __nv_bfloat16* o = P.out_bf16 + base;
+#pragma unroll
+      for (int i = 0; i < BS; ++i)
+        if (i < nv)
+          *reinterpret_cast<__nv_bfloat16*>(const_cast<char*>(row_at(o, sb >> 1, i))) = __float2bfloat16_rn(__uint_as_float(cw[i]));
+    }
+  }
+}
+
 // innermost layout: thread = 4 consecutive elements, bs/4 lanes per block
 __global__ void __launch_bounds__(256) k_unpack_inner(const UParams P) {
   extern __shared__ uint32_t s_hi[];
@@ -188,6 +336,21 @@ int msq_unpack_mx(const unsigned char* codes, const signed char* e_in, const sig
   if (post == 1 && L % block_size == 0 && block_size % 4 == 0) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_unpack_inner, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_unpack_inner<<<(unsigned)nseg, 256, smem, s>>>(P);
+  } else if (post > 1 && post % 32 == 0 && (block_size == 8 || block_size == 16 || block_size == 32) &&
+             P.fin.width + P.hi_w <= 8) {
+    const size_t lut_bytes = ((size_t)(1 << P.fin.width) + ((size_t)1 << (P.fin.width + P.hi_w))) * sizeof(float);
+    const size_t sm = lut_bytes + smem;
+    void (*k)(const UParams) = nullptr;
+    const bool hh = P.hi_w > 0;
+    const int hwt = P.hi_w == 0 ? 0 : (P.hi_w == 4 ? 4 : -1);
+#define MSQ_PICK_U(BS_) k = hwt == 0 ? k_unpack_strided_fast<BS_, 0> : (hwt == 4 ? k_unpack_strided_fast<BS_, 4> : k_unpack_strided_fast<BS_, -1>)
+    if (block_size == 16) MSQ_PICK_U(16);
+    else if (block_size == 32) MSQ_PICK_U(32);
+    else MSQ_PICK_U(8);
+#undef MSQ_PICK_U
+    (void)hh;
+    if (sm > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    k<<<(unsigned)nseg, 256, sm, s>>>(P);
   } else if (post > 1 && post % 32 == 0 && block_size <= 32) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_unpack_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_unpack_strided<<<(unsigned)nseg, 256, smem, s>>>(P);
