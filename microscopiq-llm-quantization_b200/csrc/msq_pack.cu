@@ -303,6 +303,104 @@ __global__ void __launch_bounds__(256) k_unpack_inner(const UParams P) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fast innermost unpack (blocks along the contiguous axis, the layout of GEMM weight operands): thread = 8
+// consecutive elements (one 32-bit code word for 4-bit slots, one bitmap byte, one 16/32-byte store), LUT
+// decode, hi offsets from a prologue prefix sum over the segment's bitmap words (no synchronisation in the
+// main loop).
+// ---------------------------------------------------------------------------------------------------------
+template <int HWT>
+__global__ void __launch_bounds__(256) k_unpack_inner_fast(const UParams P) {
+  constexpr bool HAS_HI = HWT != 0;
+  const int hw = HWT >= 0 ? HWT : P.hi_w;
+  extern __shared__ uint32_t s_dyn[];
+  __shared__ int s_warp[8];
+  const int wi = P.fin.width;
+  const int wo = wi + hw;
+  const int BS = P.bs;
+  float* lut = reinterpret_cast<float*>(s_dyn);
+  const int lut_n = (1 << wi) + (1 << wo);
+  int* s_pref = reinterpret_cast<int*>(s_dyn + lut_n);          // exclusive outlier count before each bitmap word
+  const int nwords = (MSQ_SEG_BLOCKS * BS) >> 5;                // bitmap words per segment (BS % 8 == 0 => integer)
+  uint32_t* s_hi = s_dyn + lut_n + (HAS_HI ? nwords + 1 : 0);
+  const long long seg = blockIdx.x;
+  const long long nelem = P.nblocks * BS;
+  const long long seg_e0 = seg * MSQ_SEG_BLOCKS * BS;
+  for (int i = threadIdx.x; i < lut_n; i += 256)
+    lut[i] = (i < (1 << wi)) ? decode_elem((uint32_t)i, P.fin.ebits, P.fin.bits)
+                             : decode_elem((uint32_t)(i - (1 << wi)), P.fout.ebits, P.fout.bits);
+  if (HAS_HI) {
+    // each thread owns nwords/256 consecutive words (nwords is a multiple of 256: 32*BS words, BS % 8 == 0)
+    const int per = nwords >> 8;
+    const uint32_t* bm = P.bitmap + (seg_e0 >> 5);
+    const long long words_total = (nelem + 31) >> 5;
+    int sum = 0;
+    for (int j = 0; j < per; ++j) {
+      const int w = threadIdx.x * per + j;
+      sum += ((seg_e0 >> 5) + w < words_total) ? __popc(__ldg(bm + w)) : 0;
+    }
+    int tot;
+    int run = cta_excl_scan(sum, s_warp, &tot);
+    for (int j = 0; j < per; ++j) {
+      const int w = threadIdx.x * per + j;
+      s_pref[w] = run;
+      run += ((seg_e0 >> 5) + w < words_total) ? __popc(__ldg(bm + w)) : 0;
+    }
+    const int words = (tot * hw + 31) >> 5;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.hi + seg * P.hi_seg_stride);
+    for (int i = threadIdx.x; i < words; i += 256) s_hi[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const uint32_t cm = (1u << wi) - 1u, hm = (1u << hw) - 1u;
+  const int iters = (MSQ_SEG_BLOCKS * BS) >> 11;                // 2048 elements per CTA iteration
+#pragma unroll 2
+  for (int it = 0; it < iters; ++it) {
+    const long long e0 = seg_e0 + (long long)it * 2048 + threadIdx.x * 8;
+    if (e0 >= nelem) continue;
+    uint32_t bword = 0;
+    if (!P.plain) bword = __ldg(P.bitmap + (e0 >> 5));
+    const int sh = (int)(e0 & 31);
+    const uint32_t byte = (bword >> sh) & 0xFFu;
+    uint64_t cw;
+    if (wi == 4) cw = __ldg(reinterpret_cast<const uint32_t*>(P.codes + (e0 >> 1)));
+    else if (wi == 2) cw = __ldg(reinterpret_cast<const uint16_t*>(P.codes + (e0 >> 2)));
+    else { const uint2 v = __ldg(reinterpret_cast<const uint2*>(P.codes + e0)); cw = (uint64_t)v.x | ((uint64_t)v.y << 32); }
+    const long long t = e0 / BS;
+    const int ei = P.e_in[t], eo = P.plain ? 0 : P.e_out[t];
+    const bool nan_blk = ei == MSQ_EXP_NAN || eo == MSQ_EXP_NAN;
+    const float s_in = pow2i(nan_blk ? 0 : ei), inv_s_in = pow2i(nan_blk ? 0 : -ei), s_out = pow2i(nan_blk ? 0 : eo);
+    int k = 0;
+    if (HAS_HI) k = s_pref[(int)((e0 - seg_e0) >> 5)] + __popc(bword & ((1u << sh) - 1u));
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t c = (uint32_t)(cw >> (j * wi)) & cm;
+      const uint32_t isout = (byte >> j) & 1u;
+      if (HAS_HI) {
+        const int bit = (k + __popc(byte & ((1u << j) - 1u))) * hw;
+        const uint32_t f = (s_hi[bit >> 5] >> (bit & 31)) & hm;
+        c |= (f & (0u - isout)) << wi;
+      }
+      const float q = lut[c + (isout << wi)];
+      const float v = isout ? __fmul_rn(__fmul_rn(q, s_out), inv_s_in) : __fmul_rn(q, s_in);
+      r[j] = nan_blk ? qnan() : __fadd_rn(v, 0.0f);
+    }
+    if (P.out_f32) {
+      float4* o = reinterpret_cast<float4*>(P.out_f32 + e0);
+      o[0] = make_float4(r[0], r[1], r[2], r[3]);
+      o[1] = make_float4(r[4], r[5], r[6], r[7]);
+    }
+    if (P.out_bf16) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(r[0], r[1]), b2 = __floats2bfloat162_rn(r[2], r[3]);
+      __nv_bfloat162 c2 = __floats2bfloat162_rn(r[4], r[5]), d2 = __floats2bfloat162_rn(r[6], r[7]);
+      uint4 v;
+      v.x = *reinterpret_cast<uint32_t*>(&a); v.y = *reinterpret_cast<uint32_t*>(&b2);
+      v.z = *reinterpret_cast<uint32_t*>(&c2); v.w = *reinterpret_cast<uint32_t*>(&d2);
+      *reinterpret_cast<uint4*>(P.out_bf16 + e0) = v;
+    }
+  }
+}
+
 }  // namespace msq
 
 using namespace msq;
@@ -333,7 +431,15 @@ int msq_unpack_mx(const unsigned char* codes, const signed char* e_in, const sig
   const long long nseg = (P.nblocks + MSQ_SEG_BLOCKS - 1) / MSQ_SEG_BLOCKS;
   const size_t smem = P.hi_w > 0 ? (size_t)P.hi_seg_stride : 0;
   cudaStream_t s = (cudaStream_t)stream;
-  if (post == 1 && L % block_size == 0 && block_size % 4 == 0) {
+  if (post == 1 && L % block_size == 0 && block_size % 8 == 0 && P.fin.width + P.hi_w <= 8) {
+    // blocks of 8k elements: every 8-element group sits inside one block and one bitmap word
+    const size_t lut_bytes = ((size_t)(1 << P.fin.width) + ((size_t)1 << (P.fin.width + P.hi_w))) * sizeof(float);
+    const size_t pref_bytes = P.hi_w > 0 ? ((size_t)((MSQ_SEG_BLOCKS * block_size) >> 5) + 1) * sizeof(int) : 0;
+    const size_t sm = lut_bytes + pref_bytes + smem;
+    void (*k)(const UParams) = P.hi_w == 0 ? k_unpack_inner_fast<0> : (P.hi_w == 4 ? k_unpack_inner_fast<4> : k_unpack_inner_fast<-1>);
+    if (sm > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    k<<<(unsigned)nseg, 256, sm, s>>>(P);
+  } else if (post == 1 && L % block_size == 0 && block_size % 4 == 0) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(k_unpack_inner, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_unpack_inner<<<(unsigned)nseg, 256, smem, s>>>(P);
   } else if (post > 1 && post % 32 == 0 && (block_size == 8 || block_size == 16 || block_size == 32) &&

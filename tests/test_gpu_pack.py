@@ -123,3 +123,24 @@ def test_pack_llama_shape_bytes_and_roundtrip(M):
     assert abs(per_elem - expect) < 0.01, (per_elem, expect, rho)
     with pytest.raises(RuntimeError):                   # packed fast path needs 32-column words
         M.pack_mx_outlier(W[:, :100].contiguous(), 8, 8, "int2", "fp4", 2, [0], 16)
+
+
+@pytest.mark.parametrize("fi,fo,bs,axis,shape", [
+    ("fp4_e2m1", "fp8_e4m3", 16, 0, (1000, 1056)),     # many segments, ragged last block row, strided layout
+    ("fp4_e2m1", "fp8_e4m3", 32, 1, (520, 2048)),      # many segments, innermost layout with a hi stream
+    ("fp4_e2m1", "fp4_e2m1", 32, 1, (768, 4096)),      # GEMM weight operand layout (no hi stream)
+    ("int2", "fp8_e4m3", 8, 0, (264, 2080)),           # 8-bit... 6-bit hi field (run-time hi width), bs 8
+    ("int2", "fp4", 16, 1, (300, 1024)),               # 2-bit slots, 2-bit hi field, innermost
+    ("fp6_e3m2", "fp6_e3m2", 32, 0, (640, 1024)),      # 8-bit containers
+    ("int4", "int8", 64, 1, (96, 4096)),               # 64-element blocks, innermost
+])
+def test_multi_segment_roundtrip(M, fi, fo, bs, axis, shape):
+    """unpack(pack(W)) == fake-quant(W) bit for bit across segment boundaries, both unpack layouts, fp32 and bf16"""
+    W = weights(shape[0], shape[1], 33).cuda()
+    p = M.pack_mx_outlier(W, 8, 8, fi, fo, 2, [axis], bs)
+    y = M.quantize_mx_outlier_v1(W, 8, 8, fi, fo, "max", 2, [axis], bs)
+    assert_exact(p.dequantize(), y, "fp32")
+    assert_exact(p.dequantize(torch.bfloat16).float(), y.to(torch.bfloat16).float(), "bf16")
+    # the oracle on a slice that crosses the first segment boundary
+    ref = O.quantize_mx_outlier(W.cpu()[:, :64] if axis == 0 else W.cpu()[:8], 8, 8, fi, fo, 2, axis, bs)
+    assert_exact(y[:, :64] if axis == 0 else y[:8], ref, "oracle slice")
