@@ -414,10 +414,31 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
         o.mask |= (o0 ? 1u : 0u) << i;
         o.mask |= (o1 ? 1u : 0u) << (i + 1);
       }
-      const float2 rin = __fmul2_rn(q, f2s(s_in));
-      const float2 rout = __fmul2_rn(__fmul2_rn(q, f2s(s_out)), f2s(inv_s_in));
-      const float2 r = __fadd2_rn(f2(o0 ? rout.x : rin.x, o1 ? rout.y : rin.y), f2s(0.0f));   // quant.py:140 (x + 0)
-      x[i] = r.x; x[i + 1] = r.y;
+      x[i] = q.x; x[i + 1] = q.y;
+    }
+    // scale back: inlier q * 2^e_in, outlier (q * 2^e_out) * 2^-e_in, then the "+ 0" of quant.py:140.
+    // When all exponents are far from the fp32 range limits both products are exact, so the outlier's two
+    // multiplications equal one multiplication by 2^(e_out - e_in) and the "+ 0" folds into an FMA.
+    // With the two scales within 22 binades of each other the per-element scale is an exact 0/1 blend as well.
+    const bool safe = (abs(e_in) <= 100) & (abs(e_out) <= 100) & (abs(e_out - e_in) <= 100) & (abs(e_out - 2 * e_in) <= 22);
+    if (safe) {
+      const float s_oi = pow2i(e_out - e_in);
+      const float dS = __fsub_rn(s_oi, s_in);
+#pragma unroll
+      for (int i = 0; i < N; i += 2) {
+        const float2 A = cblend2(s_in, dS, f2(mf[i], mf[i + 1]));
+        const float2 r = __ffma2_rn(f2(x[i], x[i + 1]), A, f2s(0.0f));
+        x[i] = r.x; x[i + 1] = r.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; i += 2) {
+        const float2 q = f2(x[i], x[i + 1]);
+        const float2 rin = __fmul2_rn(q, f2s(s_in));
+        const float2 rout = __fmul2_rn(__fmul2_rn(q, f2s(s_out)), f2s(inv_s_in));
+        const float2 r = __fadd2_rn(f2(mf[i] != 0.0f ? rout.x : rin.x, mf[i + 1] != 0.0f ? rout.y : rin.y), f2s(0.0f));
+        x[i] = r.x; x[i + 1] = r.y;
+      }
     }
   } else {
 #pragma unroll

@@ -11,6 +11,12 @@
 // Element offsets are 32-bit (host guarantees numel < 2^31 on this path).
 #include "msq_quant_kernels.cuh"
 
+#ifndef MSQ_FQ_THREADS
+#define MSQ_FQ_THREADS 256     // CTA size of the fake-quant (non-packing) launches
+#endif
+#ifndef MSQ_STRIDED_MINB
+#define MSQ_STRIDED_MINB 4
+#endif
 namespace msq {
 
 // one row of 32 codes (a warp's 32 columns) -> 32*WI bits: lanes combine into 32-bit words
@@ -28,7 +34,7 @@ __device__ __forceinline__ void store_codes(uint8_t* codes, const uint32_t (&cod
 }
 
 template <int BS, bool OUTLIER, bool PACK, bool EXT, bool CNT>
-__global__ void __launch_bounds__(256, (BS <= 16 ? 4 : 1)) k_strided(const QParams P) {
+__global__ void __launch_bounds__(256, (BS <= 16 ? MSQ_STRIDED_MINB : 1)) k_strided(const QParams P) {
   extern __shared__ uint32_t s_hi[];
   __shared__ int s_warp[8];
   __shared__ int s_base;
@@ -62,7 +68,7 @@ __global__ void __launch_bounds__(256, (BS <= 16 ? 4 : 1)) k_strided(const QPara
       }
     } else {
       b = (int)blockIdx.y; p = (int)blockIdx.z;   // uniform per CTA, no divisions
-      j = (int)blockIdx.x * 256 + (int)threadIdx.x;
+      j = (int)(blockIdx.x * blockDim.x + threadIdx.x);
       active = j < post;
       t0 = (p * P.nblk + b) * post + j;
     }
@@ -193,8 +199,8 @@ cudaError_t launch_strided(const QParams& P, bool outlier, size_t smem, cudaStre
     if (P.nblk > 65535 || P.pre > 65535) {     // gridDim.y/z limits (65535 * bs rows); the caller falls back
       return cudaErrorInvalidConfiguration;    // to k_generic
     }
-    dim3 grid((unsigned)((P.post + 255) / 256), (unsigned)P.nblk, (unsigned)P.pre);
-    k<<<grid, 256, 0, stream>>>(P);
+    dim3 grid((unsigned)((P.post + MSQ_FQ_THREADS - 1) / MSQ_FQ_THREADS), (unsigned)P.nblk, (unsigned)P.pre);
+    k<<<grid, MSQ_FQ_THREADS, 0, stream>>>(P);
   }
   return cudaGetLastError();
 }
