@@ -96,6 +96,33 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and therefore its pinned-host allocations, first touch) to the CPUs of the NUMA node the GPU
+    hangs off: with one rank per GPU the host side of the e2e copies otherwise crosses the socket interconnect."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:          # nvml prints an 8-digit domain, sysfs uses 4
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def _time_ms(fn, iters, warm=2):
     for _ in range(warm):
         fn()
@@ -295,6 +322,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -379,7 +407,7 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "elements_per_step_per_gpu": nel, "l2": "inputs larger than L2 (810 MB read + 810 MB written per step)",
-                   "sharding": "one decoder layer per rank, no collective"},
+                   "sharding": "one decoder layer per rank, no collective", "host_numa_node_rank0": numa},
         "clocks": clocks,
         "e2e": {"value": world * bytes_step / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": nel * 4, "d2h_bytes_per_step": nel * 4,
                 "ms_per_step": e2e_s * 1e3},
@@ -393,7 +421,7 @@ def main():
         line["roofline"]["traffic"] = json.load(open(tr)).get("k_strided_bytes_per_launch")
     if not args.no_extras:
         line["extra"] = extras(dev, dev_w, nel)
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N=1 only
         torch.set_num_threads(os.cpu_count())
         W = host_w[0]
         cpu_reference_pass(W)

@@ -14,6 +14,7 @@ from types import SimpleNamespace
 import torch
 import torch.nn as nn
 
+from .. import dist as D
 from ..utils.modelutils import find_layers
 from ..utils.quant import MXQuantizer, quantize_mx_outlier_v1
 from .gptq import GPTQ
@@ -92,25 +93,44 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
                         static_groups=False, true_sequential=False, hessian_batch=8, verbose=False, stats=None):
     """llama_sequential / opt_sequential (llm/llama.py:62-173, llm/opt.py:26-128).
     nearest=True is the RTN branch (llm/llama.py:226-253): every linear is replaced by
-    quantize_mx_outlier_v1(W) without calibration.  Returns {layer name: quantizer}."""
+    quantize_mx_outlier_v1(W) without calibration.  Returns {layer name: quantizer}.
+
+    Under torch.distributed (one process per GPU, every rank holding the same model and the same `batches`)
+    the path shards where it shards naturally: each rank runs ITS share of the calibration samples through the
+    layer, the per-rank Hessians are combined by one sum-allreduce per linear (dist.combine_hessians), the
+    independent solves of a layer are spread over the ranks (dist.assign_linears) and the quantized weights are
+    broadcast from their owners; RTN spreads the linears of a layer the same way."""
     qcfg = dict(REFERENCE_QCFG if qcfg is None else qcfg)
     layers, _, _, _ = decoder_parts(model)
     stats = stats if stats is not None else {}
-    stats.update(hessian_s=0.0, solve_s=0.0, forward_s=0.0, linears=0)
+    stats.update(hessian_s=0.0, solve_s=0.0, forward_s=0.0, comm_s=0.0, linears=0)
     quantizers = {}
+    world, rank = 1, 0
+    if D.is_dist():
+        world, rank = D.dist.get_world_size(), D.dist.get_rank()
+        lo, hi = D.shard_range(len(batches), rank, world)
+        if not nearest:
+            assert hi > lo, "fewer calibration batches than ranks"
+            batches = batches[lo:hi]
     if nearest:
         for i in range(len(layers)):
             layer = layers[i].to(dev)
-            for name, lin in find_layers(layer).items():
+            found = find_layers(layer)
+            owners = D.assign_linears({n: tuple(m.weight.shape) for n, m in found.items()}, world)
+            for name, lin in found.items():
                 q = MXQuantizer()
                 q.configure(**qcfg)
+                quantizers["layers.%d.%s" % (i, name)] = q
+                if owners[name] != rank:
+                    continue
                 W = lin.weight.data
                 lin.weight.data = quantize_mx_outlier_v1(W.float(), q.inlier_scale_bits, q.outlier_scale_bits,
                                                          q.inlier_elem_format, q.outlier_elem_format, q.shared_exp_method,
                                                          q.std_dev, q.axes, q.block_size, q.round, q.flush_fp32_subnorms,
                                                          q.custom_cuda).to(W.dtype)
-                quantizers["layers.%d.%s" % (i, name)] = q
                 stats["linears"] += 1
+            for name, lin in found.items():
+                D.broadcast_weight(lin, owners[name])
             layers[i] = layer.cpu()
         return quantizers
 
@@ -149,15 +169,30 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
             stats["hessian_s"] += time.perf_counter() - t0
             for h in handles:
                 h.remove()
+            owners = D.assign_linears({n: tuple(m.weight.shape) for n, m in subset.items()}, world)
+            if world > 1:
+                t0 = time.perf_counter()
+                for name in subset:                  # every rank needs N; only the owner needs H, but one
+                    H, N = D.combine_hessians(gptq[name].H, gptq[name].nsamples, upper_only=False)   # allreduce is cheapest
+                    gptq[name].H, gptq[name].nsamples = H, N
+                torch.cuda.synchronize()
+                stats["comm_s"] += time.perf_counter() - t0
             t0 = time.perf_counter()
             for name in subset:
-                gptq[name].fasterquant(percdamp=percdamp, groupsize=groupsize, actorder=act_order,
-                                       static_groups=static_groups)
                 quantizers["layers.%d.%s" % (i, name)] = gptq[name].quantizer
+                if owners[name] == rank:
+                    gptq[name].fasterquant(percdamp=percdamp, groupsize=groupsize, actorder=act_order,
+                                           static_groups=static_groups)
+                    stats["linears"] += 1
                 gptq[name].free()
-                stats["linears"] += 1
             torch.cuda.synchronize()
             stats["solve_s"] += time.perf_counter() - t0
+            if world > 1:
+                t0 = time.perf_counter()
+                for name in subset:
+                    D.broadcast_weight(subset[name], owners[name])
+                torch.cuda.synchronize()
+                stats["comm_s"] += time.perf_counter() - t0
         t0 = time.perf_counter()
         for j in range(nsamples):
             outs[j] = _run_layer(layer, inps[j].unsqueeze(0), args, kwargs)

@@ -18,7 +18,12 @@ ap.add_argument("--nearest", action="store_true")
 a = ap.parse_args()
 
 from msq_b200.llm import sequential as S
-dev = torch.device("cuda:0")
+rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
 t0 = time.time()
 cfg = transformers.LlamaConfig(hidden_size=4096, intermediate_size=11008, num_hidden_layers=a.layers, num_attention_heads=32,
                                num_key_value_heads=32, vocab_size=32000, max_position_embeddings=4096)
@@ -46,10 +51,26 @@ qcfg = dict(inlier_scale_bits=8, outlier_scale_bits=8, inlier_elem_format=a.in_f
             axes=[0], block_size=16)
 stats = {}
 torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
 t0 = time.time()
 S.sequential_quantize(model, calib, dev, qcfg=qcfg, nearest=a.nearest, stats=stats)
 torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
 t_q = time.time() - t0
-print(json.dumps({"model": "LLaMA-2-7B shape, random init, %d layers" % a.layers, "nsamples": a.nsamples, "seqlen": a.seqlen,
+if world > 1:
+    # every rank must end with the same quantized model
+    w = model.model.layers[-1].mlp.down_proj.weight.data.to(dev).float()
+    chk = torch.stack([w.sum(), w.abs().sum()])
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    stats["ranks_agree"] = bool(torch.equal(lo, hi))
+    tt = torch.tensor([t_q], device=dev, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_q = float(tt)
+    dist.destroy_process_group()
+if rank == 0:
+  print(json.dumps({"n_gpus": world, "model": "LLaMA-2-7B shape, random init, %d layers" % a.layers, "nsamples": a.nsamples, "seqlen": a.seqlen,
                   "quantizer": "%s/%s block 16 axes=[0]" % (a.in_fmt, a.out_fmt), "mode": "rtn" if a.nearest else "gptq",
                   "quantize_s": t_q, "build_model_s": t_build, **stats}))

@@ -52,3 +52,58 @@ def test_hessian_allreduce_nccl():
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert all(ret[r] for r in range(world)), dict(ret)
+
+
+def _seq_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    import transformers
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from msq_b200.llm import sequential as S
+    torch.manual_seed(0)
+    cfg = transformers.LlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                                   num_key_value_heads=4, vocab_size=512, max_position_embeddings=256)
+    model = transformers.LlamaForCausalLM(cfg).half().eval()
+    model.seqlen = 128
+    before = {n: p.detach().clone() for n, p in model.named_parameters() if "proj" in n}
+    g = torch.Generator().manual_seed(1)
+    calib = [torch.randint(0, 512, (1, 128), generator=g) for _ in range(6)]
+    qcfg = dict(inlier_scale_bits=8, outlier_scale_bits=8, inlier_elem_format="fp4_e2m1", outlier_elem_format="fp8_e4m3",
+                axes=[0], block_size=16)
+    stats = {}
+    S.sequential_quantize(model, calib, dev, qcfg=qcfg, stats=stats)
+    ok = True
+    rel = []
+    for n, p in model.named_parameters():
+        if "proj" not in n:
+            continue
+        w = p.detach().to(dev).float()
+        ok &= bool(torch.isfinite(w).all())
+        lo, hi = w.clone(), w.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ok &= bool(torch.equal(lo, hi))                      # every rank holds the same quantized weight
+        b = before[n].to(dev).float()
+        rel.append(float((w - b).norm() / b.norm()))
+    ok &= 0.0 < max(rel) < 0.5                               # quantized (changed) but close to the original
+    # the linears of a layer were spread over the ranks, and every calibration sample was used exactly once
+    tot = torch.tensor([float(stats["linears"])], device=dev)
+    dist.all_reduce(tot)
+    ok &= int(tot.item()) == 2 * 7
+    ret[rank] = ok
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_sequential_driver_data_parallel():
+    """llm/llama.py:62-173 under torch.distributed: samples sharded, Hessians allreduced, solves spread over ranks"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_seq_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world)), dict(ret)
