@@ -34,7 +34,22 @@ struct QParams {
   const float* ext_max;// plain: optional external block max [nblocks]
   long long hi_seg_stride;  // bytes
   int hi_w;            // container width of one hi field (0 = no hi stream)
+  // exact division of a 31-bit index by post / nblk: q = (n * m) >> k   (fill_geometry)
+  unsigned int post_m, nblk_m;
+  int post_k, nblk_k;
 };
+
+// floor(n / d) for 0 <= n < 2^31 with the (m, k) pair of magic_div()
+__device__ __forceinline__ int fast_div(int n, unsigned int m, int k) {
+  return (int)(((unsigned long long)(unsigned int)n * m) >> k);
+}
+__host__ inline void magic_div(long long d, unsigned int* m, int* k) {
+  // k = 31 + ceil(log2 d), m = floor(2^k / d) + 1: the error term n*e/2^k stays below 1/d for n < 2^31
+  int l = 0;
+  while ((1LL << l) < d) ++l;
+  *k = 31 + l;
+  *m = (unsigned int)((((unsigned __int128)1) << *k) / (unsigned __int128)d + 1);
+}
 
 __device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
   int inc = v;

@@ -292,6 +292,9 @@ static int fill_geometry(QParams& P, long long pre, long long L, long long post,
   P.pre = pre; P.L = (int)L; P.post = post; P.bs = bs;
   P.nblk = (int)((L + bs - 1) / bs);
   P.nblocks = pre * P.nblk * post;
+  P.post_m = P.nblk_m = 0; P.post_k = P.nblk_k = 0;
+  if (post < 0x7fffffffLL) magic_div(post, &P.post_m, &P.post_k);
+  magic_div(P.nblk, &P.nblk_m, &P.nblk_k);
   return MSQ_OK;
 }
 

@@ -33,6 +33,48 @@ __device__ __forceinline__ void store_codes(uint8_t* codes, const uint32_t (&cod
   }
 }
 
+// 4-bit slots, 16 rows: an 8x8 byte transpose across each group of 8 lanes (3 shuffle + PRMT stages instead of
+// 3 shuffles per row) leaves lane g of a group with rows 2g and 2g+1 of the group's 8 columns; two word stores
+// per lane.  c[] = the 16 codes of this lane's column, rows r0 .. r0+15 of the block.
+__device__ __forceinline__ void store_codes4_16(uint8_t* codes, const uint32_t* c, int rowbase, int r0, int post, int nv,
+                                                int lane) {
+  const int g = lane & 7;
+  uint32_t W0, W1;
+  {
+    uint32_t B[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) B[k] = (c[2 * k] & 0xFu) | ((c[2 * k + 1] << 4) & 0xF0u);
+    W0 = __byte_perm(__byte_perm(B[0], B[1], 0x0040), __byte_perm(B[2], B[3], 0x0040), 0x5410);
+    W1 = __byte_perm(__byte_perm(B[4], B[5], 0x0040), __byte_perm(B[6], B[7], 0x0040), 0x5410);
+  }
+  // stage A: swap the off-diagonal 4x4 blocks (lanes g and g^4 exchange one word)
+  {
+    const uint32_t r = __shfl_xor_sync(0xffffffffu, (g & 4) ? W0 : W1, 4);
+    if (g & 4) W0 = r; else W1 = r;
+  }
+  // stage B: swap 2x2 sub-blocks (16-bit halves of both words travel in one shuffle)
+  {
+    const uint32_t r = __shfl_xor_sync(0xffffffffu, __byte_perm(W0, W1, (g & 2) ? 0x5410 : 0x7632), 2);
+    W0 = __byte_perm(W0, r, (g & 2) ? 0x3254 : 0x5410);
+    W1 = __byte_perm(W1, r, (g & 2) ? 0x3276 : 0x7610);
+  }
+  // stage C: swap single bytes
+  {
+    const uint32_t r = __shfl_xor_sync(0xffffffffu, __byte_perm(W0, W1, (g & 1) ? 0x6420 : 0x7531), 1);
+    W0 = __byte_perm(W0, r, (g & 1) ? 0x3514 : 0x5240);
+    W1 = __byte_perm(W1, r, (g & 1) ? 0x3716 : 0x7260);
+  }
+  // byte k of (W0, W1) = column k of the group; low nibble = row 2g, high nibble = row 2g+1
+  const uint32_t a0 = W0 & 0x0F0F0F0Fu, a1 = W1 & 0x0F0F0F0Fu;
+  const uint32_t b0 = (W0 >> 4) & 0x0F0F0F0Fu, b1 = (W1 >> 4) & 0x0F0F0F0Fu;
+  const uint32_t row_lo = __byte_perm(a0 | (a0 >> 4), a1 | (a1 >> 4), 0x6420);
+  const uint32_t row_hi = __byte_perm(b0 | (b0 >> 4), b1 | (b1 >> 4), 0x6420);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(codes) + (lane >> 3);
+  const int r = r0 + 2 * g;
+  if (r < nv) dst[(rowbase + r * post) >> 3] = row_lo;
+  if (r + 1 < nv) dst[(rowbase + (r + 1) * post) >> 3] = row_hi;
+}
+
 template <int BS, bool OUTLIER, bool PACK, bool EXT, bool CNT>
 __global__ void __launch_bounds__(256, (BS <= 16 ? MSQ_STRIDED_MINB : 2)) k_strided(const QParams P) {
   extern __shared__ uint32_t s_hi[];
@@ -62,9 +104,9 @@ __global__ void __launch_bounds__(256, (BS <= 16 ? MSQ_STRIDED_MINB : 2)) k_stri
       t0 = (int)seg * MSQ_SEG_BLOCKS + sub * 256 + (int)threadIdx.x;
       active = t0 < (int)P.nblocks;
       if (active) {
-        const int pb = t0 / post;
+        const int pb = fast_div(t0, P.post_m, P.post_k);
         j = t0 - pb * post;
-        p = pb / P.nblk; b = pb - p * P.nblk;
+        p = fast_div(pb, P.nblk_m, P.nblk_k); b = pb - p * P.nblk;
       }
     } else {
       b = (int)blockIdx.y; p = (int)blockIdx.z;   // uniform per CTA, no divisions
@@ -126,7 +168,10 @@ __global__ void __launch_bounds__(256, (BS <= 16 ? MSQ_STRIDED_MINB : 2)) k_stri
     }
     if (PACK) {
       // host guarantees post % 32 == 0, so a warp's 32 columns share (p, b) and whole words
-      if (wi == 4) store_codes<BS, 4>(P.codes, code, base, post, nv, lane);
+      if (wi == 4 && BS % 16 == 0) {
+#pragma unroll
+        for (int h = 0; h < BS / 16; ++h) store_codes4_16(P.codes, code + 16 * h, base - lane, 16 * h, post, nv, lane);
+      } else if (wi == 4) store_codes<BS, 4>(P.codes, code, base, post, nv, lane);
       else if (wi == 2) store_codes<BS, 2>(P.codes, code, base, post, nv, lane);
       else store_codes<BS, 8>(P.codes, code, base, post, nv, lane);
       if (OUTLIER) {
@@ -141,20 +186,36 @@ __global__ void __launch_bounds__(256, (BS <= 16 ? MSQ_STRIDED_MINB : 2)) k_stri
       int tot;
       const int off = cta_excl_scan(active ? bo.cnt : 0, s_warp, &tot);
       if (active && bo.cnt) {
-        // this block's hi fields are contiguous in the stream: assemble whole words locally, one
-        // shared-memory atomic per touched word (fields never straddle words: hi_w divides 32)
+        // this block's hi fields are contiguous in the stream, first outlier in the lowest bits
         const int bit0 = (s_base + off) * P.hi_w;
-        int w = bit0 >> 5, b = bit0 & 31;
-        uint32_t cur = 0;
+        if (BS * P.hi_w <= 64) {
+          // branch-free: walk the block backwards, shifting the accumulator by hi_w for every outlier
+          // (an inlier's code has no bits above the slot width, so its field is zero and needs no masking)
+          unsigned long long acc = 0;
 #pragma unroll
-        for (int i = 0; i < BS; ++i) {
-          if ((bo.mask >> i) & 1u) {
-            cur |= (code[i] >> wi) << b;
-            b += P.hi_w;
-            if (b == 32) { atomicOr(&s_hi[w], cur); cur = 0; b = 0; ++w; }
+          for (int i = BS - 1; i >= 0; --i) {
+            const int sh = ((bo.mask >> i) & 1u) ? P.hi_w : 0;
+            acc = (acc << sh) | (unsigned long long)(code[i] >> wi);
           }
+          const int w = bit0 >> 5, b = bit0 & 31;
+          const unsigned long long lo = acc << b;
+          const uint32_t top = b ? (uint32_t)(acc >> (64 - b)) : 0u;
+          atomicOr(&s_hi[w], (uint32_t)lo);
+          if ((uint32_t)(lo >> 32)) atomicOr(&s_hi[w + 1], (uint32_t)(lo >> 32));
+          if (top) atomicOr(&s_hi[w + 2], top);
+        } else {
+          int w = bit0 >> 5, b = bit0 & 31;
+          uint32_t cur = 0;
+#pragma unroll
+          for (int i = 0; i < BS; ++i) {
+            if ((bo.mask >> i) & 1u) {
+              cur |= (code[i] >> wi) << b;
+              b += P.hi_w;
+              if (b == 32) { atomicOr(&s_hi[w], cur); cur = 0; b = 0; ++w; }
+            }
+          }
+          if (b) atomicOr(&s_hi[w], cur);
         }
-        if (b) atomicOr(&s_hi[w], cur);
       }
       __syncthreads();
       if (threadIdx.x == 0) s_base += tot;
