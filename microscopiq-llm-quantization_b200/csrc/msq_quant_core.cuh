@@ -16,6 +16,10 @@ namespace msq {
 struct QCfg {
   Fmt fin, fout;
   EncC enc_i, enc_o;   // code encoders of fin / fout, filled by finish_cfg() on the host
+  // integer-domain encoder of the fused rounding (core_outlier): code = min(k + (exponent steps << tm), cmax) | sign
+  int ksh_i, ksh_o;    // 23 - trailing mantissa bits
+  int cmax_i, cmax_o;  // magnitude code of max_norm
+  int sgn_i, sgn_o;    // sign bit of the code
   int sb_in, sb_out;
   float std_dev;
   int flush;
@@ -24,9 +28,22 @@ struct QCfg {
   int rmode;     // Round
 };
 
+__host__ inline void enc_consts(const Fmt& f, int* ksh, int* cmax, int* sgn) {
+  const int tm = f.bits - 2;                       // trailing mantissa bits (ints: fractional bits)
+  if (f.ebits == 0) {
+    *ksh = 23; *cmax = (1 << (f.bits - 1)) - 1; *sgn = 1 << (f.bits - 1);
+  } else {
+    float q = f.max_norm;                          // k = max_norm / 2^(emax - tm), exact
+    for (int i = 0; i < f.emax - tm; ++i) q *= 0.5f;
+    for (int i = 0; i < tm - f.emax; ++i) q *= 2.0f;
+    *ksh = 23 - tm; *cmax = (int)q + ((f.emax - f.min_exp) << tm); *sgn = 1 << (f.ebits + tm);
+  }
+}
 __host__ inline void finish_cfg(QCfg& c) {
   c.enc_i = make_enc(c.fin.ebits, c.fin.bits);
   c.enc_o = make_enc(c.fout.ebits, c.fout.bits);
+  enc_consts(c.fin, &c.ksh_i, &c.cmax_i, &c.sgn_i);
+  enc_consts(c.fout, &c.ksh_o, &c.cmax_o, &c.sgn_o);
 }
 
 template <int LPB> __device__ __forceinline__ double grp_sum(double v) {
@@ -228,10 +245,27 @@ __device__ __forceinline__ float2 quantum2(float2 v, float2 Dp, float2 LD) {
   return f2(fmaxf(PD.x, LD.x), fmaxf(PD.y, LD.y));
 }
 // torch-path rounding (elemwise_ops.py:59-72, nearest = floor(|y| + 0.5) with the fp32 add, floor): |q| clamped to M
-__device__ __forceinline__ float2 round_mag2_py(float2 v, float2 qn, float addend, float2 M) {
+// t = 2^23*quantum + k*quantum: the low mantissa bits of t are the integer k = floor(|v|/quantum + addend)
+__device__ __forceinline__ float2 round_mag2_py_t(float2 v, float2 qn, float addend, float2 M, float2& t) {
   const float2 Cq = __fmul2_rn(qn, f2s(8388608.0f));
   const float ax = __fmaf_rn(qn.x, addend, fabsf(v.x)), ay = __fmaf_rn(qn.y, addend, fabsf(v.y));
-  return f2(fminf(__fsub_rn(__fadd_rz(ax, Cq.x), Cq.x), M.x), fminf(__fsub_rn(__fadd_rz(ay, Cq.y), Cq.y), M.y));
+  t = f2(__fadd_rz(ax, Cq.x), __fadd_rz(ay, Cq.y));
+  return f2(fminf(__fsub_rn(t.x, Cq.x), M.x), fminf(__fsub_rn(t.y, Cq.y), M.y));
+}
+__device__ __forceinline__ float2 round_mag2_py(float2 v, float2 qn, float addend, float2 M) {
+  float2 t;
+  return round_mag2_py_t(v, qn, addend, M, t);
+}
+// Sign-magnitude code straight from the rounding's integers (no float re-analysis of q):
+//   k          = bits(t) - bits(2^23 * quantum)
+//   exponent   = (bits(quantum) - bits(smallest quantum)) >> (23 - tm)      = (p - min_exp) << tm
+//   magnitude  = min(k + exponent, code(max_norm))          (codes are monotonic in |q|, so this is the clamp)
+// k = 2^(tm+1) carries into the exponent field by itself; subnormals and integer formats have exponent = 0.
+__device__ __forceinline__ uint32_t encode_k(float t, float qn, float LD, float q, int ksh, int cmax, int sgn) {
+  const int k = __float_as_int(t) - __float_as_int(qn) - (23 << 23);
+  const int e = (__float_as_int(qn) - __float_as_int(LD)) >> ksh;
+  const int mag = min(k + e, cmax);
+  return (uint32_t)(mag | ((q < 0.0f) ? sgn : 0));
 }
 // integer-mantissa rounding of cpp/quantize.cuh:88-149 on the exact value: nearest = half away from zero on the
 // truncated half-quantum count, even = ties to even, floor = truncation
@@ -404,13 +438,14 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
       //   a = |v| + addend*quantum   (the reference's fp32 add, scaled by an exact power of two)
       //   floor to a multiple of the quantum = (a (+rz) C) - C  with C = 2^23 * quantum
       const float2 qn = quantum2(v, Dp2, LD2);
-      float2 q = round_mag2_py(v, qn, rs.addend, M2);
+      float2 t;
+      float2 q = round_mag2_py_t(v, qn, rs.addend, M2, t);
       q.x = copysignf(q.x, v.x);
       q.y = copysignf(q.y, v.y);
-      const bool o0 = mf[i] != 0.0f, o1 = mf[i + 1] != 0.0f;
       if (CODES) {
-        code[i] = encode_sel(q.x, o0);
-        code[i + 1] = encode_sel(q.y, o1);
+        const bool o0 = mf[i] != 0.0f, o1 = mf[i + 1] != 0.0f;
+        code[i] = encode_k(t.x, qn.x, LD2.x, q.x, o0 ? c.ksh_o : c.ksh_i, o0 ? c.cmax_o : c.cmax_i, o0 ? c.sgn_o : c.sgn_i);
+        code[i + 1] = encode_k(t.y, qn.y, LD2.y, q.y, o1 ? c.ksh_o : c.ksh_i, o1 ? c.cmax_o : c.cmax_i, o1 ? c.sgn_o : c.sgn_i);
         o.mask |= (o0 ? 1u : 0u) << i;
         o.mask |= (o1 ? 1u : 0u) << (i + 1);
       }

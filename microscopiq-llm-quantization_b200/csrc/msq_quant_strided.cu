@@ -175,10 +175,22 @@ __global__ void __launch_bounds__(256, (BS <= 16 ? MSQ_STRIDED_MINB : 2)) k_stri
       else if (wi == 2) store_codes<BS, 2>(P.codes, code, base, post, nv, lane);
       else store_codes<BS, 8>(P.codes, code, base, post, nv, lane);
       if (OUTLIER) {
+        // one ballot per row; lane 0 stores the row's word (address = first word + row * words per row)
+        char* bp = reinterpret_cast<char*>(P.bitmap + ((base - lane) >> 5));
+        const int bstride = (post >> 5) * 4;
+        const bool l0 = lane == 0;
+        if (nv == BS) {
 #pragma unroll
-        for (int i = 0; i < BS; ++i) {
-          const uint32_t w = __ballot_sync(0xffffffffu, (bo.mask >> i) & 1u);
-          if (i < nv && lane == 0) P.bitmap[(base + i * post) >> 5] = w;
+          for (int i = 0; i < BS; ++i) {
+            const uint32_t w = __ballot_sync(0xffffffffu, bo.mask & (1u << i));
+            if (l0) *reinterpret_cast<uint32_t*>(bp + (long long)bstride * i) = w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < BS; ++i) {
+            const uint32_t w = __ballot_sync(0xffffffffu, bo.mask & (1u << i));
+            if (i < nv && l0) *reinterpret_cast<uint32_t*>(bp + (long long)bstride * i) = w;
+          }
         }
       }
     }
