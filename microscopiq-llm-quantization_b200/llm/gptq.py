@@ -43,6 +43,8 @@ class GPTQ:
     #: number of add_batch calls whose activations are buffered before one Hessian GEMM
     #: (1 = accumulate immediately, exactly like gptq.py:53-58)
     hessian_batch = 1
+    #: where the tie order of the prune's torch.topk (gptq.py:150) comes from: "cuda" (default) or "cpu"
+    prune_topk_device = "cuda"
     #: print 'time' / 'error' like the reference (gptq.py:174-175)
     verbose = True
     #: how the upper Cholesky factor of H^-1 is obtained.  "reference": cholesky -> cholesky_inverse ->
@@ -273,7 +275,14 @@ class GPTQ:
                         importance = (q ** 2) / d ** 2
                         num_outliers = int(num_outliers_per_block.sum().to(torch.int16))
                         if num_outliers > 0:
-                            least = torch.topk(importance, num_outliers, largest=False).indices
+                            # gptq.py:150: torch.topk leaves the order of tied entries unspecified, and on the coarse
+                            # MX grid most of a column's q^2/d^2 values are tied.  The default is the CUDA tie order
+                            # (what the reference itself gets on a GPU); prune_topk_device = "cpu" reproduces a
+                            # CPU run of the reference (the committed fixtures) entry for entry.
+                            if self.prune_topk_device == "cpu":
+                                least = torch.topk(importance.cpu(), num_outliers, largest=False).indices.to(q.device)
+                            else:
+                                least = torch.topk(importance, num_outliers, largest=False).indices
                             q[least] = 0
                     else:
                         q = res.flatten()

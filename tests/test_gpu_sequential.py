@@ -70,3 +70,74 @@ def test_gptq_and_rtn_drivers(make):
     w0 = dict(base.named_parameters())
     changed = [n for n, p in m_g.named_parameters() if "proj" in n or "fc" in n]
     assert any(not torch.equal(dict(m_g.named_parameters())[n].cpu(), w0[n].cpu()) for n in changed)
+
+
+def _fixture_model():
+    import numpy as np
+    import os
+    from util import GOLD
+    z = np.load(os.path.join(GOLD, "ppl_tiny_llama.npz"))
+    cfg = transformers.LlamaConfig(hidden_size=64, intermediate_size=176, num_hidden_layers=2, num_attention_heads=4,
+                                   num_key_value_heads=4, vocab_size=256, max_position_embeddings=128)
+    m = transformers.LlamaForCausalLM(cfg).float().eval()
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd__")}
+    m.load_state_dict(sd)
+    m.seqlen = 32
+    return m, z
+
+
+@pytest.mark.timeout(600)
+def test_perplexity_against_the_reference_fixture():
+    """north star: "tolerance validated against the reference's perplexity on synthetic calibration data".
+    tests/golden/ppl_tiny_llama.npz holds a tiny LLaMA, synthetic tokens, and the perplexities obtained by running the
+    REFERENCE's GPTQ / MXQuantizer / quantize_mx_outlier_v1 on it (tests/golden/make_golden_ppl.py, int2 inliers / fp4
+    outliers / block 16 = llm/llama.py:130-137).  fp32 9.82, reference GPTQ 25.09, reference RTN 32.39."""
+    from msq_b200.llm import sequential as S
+    dev = torch.device("cuda:0")
+    base, z = _fixture_model()
+    calib = [torch.from_numpy(z["calib"][i:i + 1]) for i in range(z["calib"].shape[0])]
+    test_ids = torch.from_numpy(z["test"])
+    ppl_fp = S.perplexity(copy.deepcopy(base), test_ids, dev, 32)
+    assert abs(ppl_fp - float(z["ppl_fp"])) <= 1e-3 * float(z["ppl_fp"])          # same model, same arithmetic
+
+    # RTN: bit-exact weights, so the perplexity differs only by the fp32 forward's summation order (CPU vs GPU)
+    m_r = copy.deepcopy(base)
+    S.sequential_quantize(m_r, None, dev, qcfg=S.REFERENCE_QCFG, nearest=True)
+    for li, layer in enumerate(m_r.model.layers):
+        for name, lin in S.find_layers(layer).items():
+            assert torch.equal(lin.weight.detach().cpu(), torch.from_numpy(z["rtn__%d.%s" % (li, name)])), (li, name)
+    ppl_r = S.perplexity(m_r, test_ids, dev, 32)
+    assert abs(ppl_r - float(z["ppl_rtn"])) <= 1e-3 * float(z["ppl_rtn"]), (ppl_r, float(z["ppl_rtn"]))
+
+    def gptq_run(topk_device):
+        import msq_b200
+        old = msq_b200.GPTQ.prune_topk_device
+        msq_b200.GPTQ.prune_topk_device = topk_device
+        try:
+            m_g = copy.deepcopy(base)
+            S.sequential_quantize(m_g, calib, dev, qcfg=S.REFERENCE_QCFG, hessian_batch=1)
+        finally:
+            msq_b200.GPTQ.prune_topk_device = old
+        diff = {}
+        for li, layer in enumerate(m_g.model.layers):
+            for name, lin in S.find_layers(layer).items():
+                ref = torch.from_numpy(z["gptq__%d.%s" % (li, name)])
+                diff["%d.%s" % (li, name)] = float((lin.weight.detach().cpu() != ref).float().mean())
+        return S.perplexity(m_g, test_ids, dev, 32), diff
+
+    # GPTQ, tie order of the prune's torch.topk taken from the CPU like in the fixture's (CPU) run of the reference:
+    # the six single-block linears of layer 0 are bit-identical to the reference's, later ones see inputs that differ in
+    # the last bits (tensor-core Hessian, GPU forward) and stay within 2 % differing entries; perplexity within 2 %.
+    ppl_c, diff_c = gptq_run("cpu")
+    # GPTQ as shipped (CUDA tie order = what the reference itself gets when it runs on a GPU): same algorithm, other
+    # arbitrary choice among tied prune candidates; the perplexity must stay in the reference's range (better than RTN).
+    ppl_g, diff_g = gptq_run("cuda")
+    print("perplexity fp32 %.4f | RTN ours %.4f ref %.4f | GPTQ ref %.4f, ours cpu-ties %.4f (max differing %.4f), "
+          "ours cuda-ties %.4f (max differing %.4f)" % (ppl_fp, ppl_r, float(z["ppl_rtn"]), float(z["ppl_gptq"]), ppl_c,
+                                                        max(diff_c.values()), ppl_g, max(diff_g.values())))
+    for name in ("0.self_attn.q_proj", "0.self_attn.k_proj", "0.self_attn.v_proj", "0.self_attn.o_proj", "0.mlp.gate_proj",
+                 "0.mlp.up_proj"):
+        assert diff_c[name] == 0.0 and diff_g[name] == 0.0, (name, diff_c[name], diff_g[name])
+    assert max(diff_c.values()) <= 0.02, diff_c
+    assert abs(ppl_c - float(z["ppl_gptq"])) <= 0.02 * float(z["ppl_gptq"]), (ppl_c, float(z["ppl_gptq"]))
+    assert ppl_fp < ppl_g < ppl_r and abs(ppl_g - float(z["ppl_gptq"])) <= 0.25 * float(z["ppl_gptq"])
