@@ -1,2 +1,4 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests/test_gpu_dist.py -x -q 2>&1 | tail -5
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_dist.py -x -q 2>&1 | tail -15
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 scripts/llama7b_e2e.py --layers 2 --nsamples 16 2>&1 | tail -3
