@@ -195,25 +195,26 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
         const int k = kb * XBK + kc * 16;
         uint4 outv = make_uint4(0, 0, 0, 0);
         uint32_t sf_byte = 0x7Fu;                    // 2^0 for rows / K-blocks outside the matrix
-        if (n0 + r < P.N && k < P.K) {
-          const int ei = raw[i].ei, eo = raw[i].eo;
-          sf_byte = (uint32_t)(ei + 127) & 0xFFu;    // UE8M0; MSQ_EXP_NAN (-128) maps to 0xFF = NaN
-          uint32_t w[4];
-          w[0] = widen4(raw[i].c.x & 0xFFFFu); w[1] = widen4(raw[i].c.x >> 16);
-          w[2] = widen4(raw[i].c.y & 0xFFFFu); w[3] = widen4(raw[i].c.y >> 16);
-          uint32_t ob = (raw[i].bm >> (k & 31)) & 0xFFFFu;
-          while (ob) {                               // outliers: q * 2^(e_out - 2 e_in) relative to the block scale
-            const int e = __ffs(ob) - 1;
-            ob &= ob - 1;
-            const uint32_t code = ((e < 8 ? raw[i].c.x : raw[i].c.y) >> (4 * (e & 7))) & 0xFu;
-            const float v = __fmul_rn(decode_elem(code, 2, 3), pow2i(max(-60, min(60, eo - 2 * ei))));
-            const uint32_t b8 = (eo == MSQ_EXP_NAN) ? 0x7Fu : (encode_fast(v, enc8) & 0xFFu);
-            const int ws = e >> 2, sh = (e & 3) * 8;
-            w[ws] = (w[ws] & ~(0xFFu << sh)) | (b8 << sh);
-          }
-          outv = make_uint4(w[0], w[1], w[2], w[3]);
+        uint32_t ob = 0;
+        const bool inside = n0 + r < P.N && k < P.K;
+        if (inside) {
+          sf_byte = (uint32_t)(raw[i].ei + 127) & 0xFFu;    // UE8M0; MSQ_EXP_NAN (-128) maps to 0xFF = NaN
+          outv = make_uint4(widen4(raw[i].c.x & 0xFFFFu), widen4(raw[i].c.x >> 16), widen4(raw[i].c.y & 0xFFFFu),
+                            widen4(raw[i].c.y >> 16));
+          ob = (raw[i].bm >> (k & 31)) & 0xFFFFu;
         }
-        *reinterpret_cast<uint4*>(dst + r * 128 + ((kc ^ (r & 7)) << 4)) = outv;
+        uint8_t* piece = dst + r * 128 + ((kc ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(piece) = outv;
+        // outliers (rare): q * 2^(e_out - 2 e_in) relative to the block scale, patched byte by byte in shared memory
+        // (no register-array indexing, so nothing spills to local memory and the code stays small)
+        while (ob) {
+          const int e = __ffs(ob) - 1;
+          ob &= ob - 1;
+          const int ei = raw[i].ei, eo = raw[i].eo;
+          const uint32_t code = ((e < 8 ? raw[i].c.x : raw[i].c.y) >> (4 * (e & 7))) & 0xFu;
+          const float v = __fmul_rn(decode_elem(code, 2, 3), pow2i(max(-60, min(60, eo - 2 * ei))));
+          piece[e] = (uint8_t)((eo == MSQ_EXP_NAN) ? 0x7Fu : (encode_fast(v, enc8) & 0xFFu));
+        }
         if ((kc & 1) == 0) sfa[(r & 31) * 16 + (r >> 5) * 4 + (kc >> 1)] = (uint8_t)sf_byte;
       }
     };
@@ -374,20 +375,18 @@ __global__ void __launch_bounds__(256) k_widen_fp4_e4m3(const uint8_t* __restric
     return mag | ((s << 4) & 0x80u) | ((s << 8) & 0x8000u) | ((s << 12) & 0x800000u) | ((s << 16) & 0x80000000u);
   };
   uint32_t w[4] = {widen4(cw.x & 0xFFFFu), widen4(cw.x >> 16), widen4(cw.y & 0xFFFFu), widen4(cw.y >> 16)};
+  *reinterpret_cast<uint4*>(out + e0) = make_uint4(w[0], w[1], w[2], w[3]);
   if (!plain) {
     uint32_t ob = (__ldg(bitmap + (e0 >> 5)) >> (k & 31)) & 0xFFFFu;
     const EncC enc8 = make_enc(4, 5);
-    while (ob) {
+    while (ob) {                                   // rare: patch the byte in place (same thread, program order)
       const int e = __ffs(ob) - 1;
       ob &= ob - 1;
       const uint32_t code = ((e < 8 ? cw.x : cw.y) >> (4 * (e & 7))) & 0xFu;
       const float v = __fmul_rn(decode_elem(code, 2, 3), pow2i(max(-60, min(60, eo - 2 * ei))));
-      const uint32_t b8 = (eo == MSQ_EXP_NAN) ? 0x7Fu : (encode_fast(v, enc8) & 0xFFu);
-      const int ws = e >> 2, sh = (e & 3) * 8;
-      w[ws] = (w[ws] & ~(0xFFu << sh)) | (b8 << sh);
+      out[e0 + e] = (uint8_t)((eo == MSQ_EXP_NAN) ? 0x7Fu : (encode_fast(v, enc8) & 0xFFu));
     }
   }
-  *reinterpret_cast<uint4*>(out + e0) = make_uint4(w[0], w[1], w[2], w[3]);
   if ((e0 & 31) == 0) sf[blk] = (uint8_t)((ei + 127) & 0xFF);
 }
 
@@ -417,8 +416,20 @@ static int launch_mx8(const unsigned char* xcodes, long long ldx, const signed c
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int kblocks_total = (K + XBK - 1) / XBK;
+  // split K so that the persistent grid stays busy: cost = rounds over the SMs x (K-blocks per item + a fixed
+  // per-item charge for the TMEM drain and the atomics)
   int ksplit = 1;
-  while (P.tiles_n * P.tiles_m * ksplit * 2 <= sms && kblocks_total / (ksplit * 2) >= 4) ksplit *= 2;
+  {
+    const int tiles = P.tiles_n * P.tiles_m;
+    double best = 1e30;
+    for (int ks = 1; ks <= 16; ks *= 2) {
+      const int per = (kblocks_total + ks - 1) / ks;
+      if (ks > 1 && (per < 2 || (ks - 1) * per >= kblocks_total)) break;      // every split must own K-blocks
+      const int rounds = (tiles * ks + sms - 1) / sms;
+      const double cost = (double)rounds * (per + 2.0) + (ks > 1 ? 1.0 : 0.0);
+      if (cost < best - 1e-9) { best = cost; ksplit = ks; }
+    }
+  }
   P.ksplit = ksplit;
   P.kb_per_split = (kblocks_total + ksplit - 1) / ksplit;
   if (ksplit > 1 && !accumulate) {
