@@ -422,7 +422,8 @@ static int launch_mx8(const unsigned char* xcodes, long long ldx, const signed c
   {
     const int tiles = P.tiles_n * P.tiles_m;
     double best = 1e30;
-    for (int ks = 1; ks <= 16; ks *= 2) {
+    // only when the un-split grid cannot fill the machine: split-K pays a memset and fp32 atomics on the whole output
+    for (int ks = 1; ks <= (tiles < sms ? 16 : 1); ks *= 2) {
       const int per = (kblocks_total + ks - 1) / ks;
       if (ks > 1 && (per < 2 || (ks - 1) * per >= kblocks_total)) break;      // every split must own K-blocks
       const int rounds = (tiles * ks + sms - 1) / sms;
