@@ -341,8 +341,20 @@ int msq_gemm_packed_w_bf16(const void* X, long long ldx, const unsigned char* co
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // split K until the grid covers the SMs (each slice keeps at least 8 K-blocks of 64)
   const int kblocks_total = (K + WBK - 1) / WBK;
+  // split K when the un-split grid cannot fill the machine: cost = rounds over the SMs x (K-blocks per item + a
+  // fixed per-item charge for the TMEM drain and the atomics)
   int ksplit = 1;
-  while (P.tiles_n * P.tiles_m * ksplit * 2 <= sms && kblocks_total / (ksplit * 2) >= 8) ksplit *= 2;
+  {
+    const int tiles = P.tiles_n * P.tiles_m;
+    double best = 1e30;
+    for (int ks = 1; ks <= (tiles < sms ? 16 : 1); ks *= 2) {
+      const int per = (kblocks_total + ks - 1) / ks;
+      if (ks > 1 && (per < 4 || (ks - 1) * per >= kblocks_total)) break;      // every split must own K-blocks
+      const int rounds = (tiles * ks + sms - 1) / sms;
+      const double cost = (double)rounds * (per + 4.0) + (ks > 1 ? 2.0 : 0.0);
+      if (cost < best - 1e-9) { best = cost; ksplit = ks; }
+    }
+  }
   P.ksplit = ksplit;
   P.kb_per_split = (kblocks_total + ksplit - 1) / ksplit;
   if (ksplit > 1 && !accumulate) {
