@@ -11,4 +11,4 @@ for _ in range(3):
 torch.cuda.synchronize()
 PY
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_strided|k_unpack' -s 2 -c 2 -o gpurun_out/prof_pack_cur -f python /tmp/pk.py > gpurun_out/ncu_pack.log 2>&1
-bash scripts/gpu_packtime.sh 2>&1 | tail -5
+bash scripts/gpu_packtime.sh 2>&1 | tail -6
