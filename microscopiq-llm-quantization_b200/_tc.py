@@ -142,9 +142,25 @@ def mx8_weight_ok(pw):
     return ok
 
 
-def packed_linear_mx8(xq, pw, bias=None):
+def widen_weight_mx8(pw):
+    """packed FP4(+outliers) weight -> dense MX-FP8 operand (E4M3 bytes [N, K], UE8M0 scales [N, K/32]),
+    outliers folded in exactly as the fused kernel does (msq_widen_fp4_to_mxfp8)."""
+    Nn, K = pw.shape
+    dev = pw.codes.device
+    wb = torch.empty(Nn, K, dtype=torch.uint8, device=dev)
+    wsf = torch.empty(Nn, K // 32, dtype=torch.uint8, device=dev)
+    rc = N.lib().msq_widen_fp4_to_mxfp8(N.ptr(pw.codes), N.ptr(pw.bitmap), N.ptr(pw.e_in), N.ptr(pw.e_out), N.ptr(wb),
+                                        N.ptr(wsf), Nn, K, int(pw.plain), N.stream_ptr(dev))
+    N.check(rc, "msq_widen_fp4_to_mxfp8")
+    return wb, wsf
+
+
+def packed_linear_mx8(xq, pw, bias=None, cache_dense=False):
     """y = dq(xq) @ dq(pw).T on tcgen05 kind::mxf8f6f4.block_scale.  xq: PackedMX of the activations
-    ([..., K], FP8 E4M3, block 32 along the last axis, no outliers); pw: packed FP4 weight (mx8_weight_ok)."""
+    ([..., K], FP8 E4M3, block 32 along the last axis, no outliers); pw: packed FP4 weight (mx8_weight_ok).
+    cache_dense=True keeps the widened E4M3 copy of the weight (1 byte per element, on top of the 0.56-byte packed
+    planes) on `pw` and runs the TMA-fed kernel at every M: at decode sizes the fused kernel is bound by its
+    dequantizing producer warps, the cached operand streams at HBM speed (still half the bytes of bf16)."""
     from . import _ops
     K = pw.shape[1]
     if xq.shape[-1] != K or xq.block_size != 32 or xq.code_width != 8 or _ops.fmt4(xq.in_fmt)[:2] != (4, 5):
@@ -156,13 +172,15 @@ def packed_linear_mx8(xq, pw, bias=None):
         M *= s_
     Nn = pw.shape[0]
     out = torch.empty(M, Nn, dtype=torch.float32, device=pw.codes.device)
-    if M >= MX8_DENSE_MIN_M and K % 128 == 0:
-        # compute-bound regime: widen the FP4 weight to E4M3 bytes once, then both operands stream through TMA
-        wb = torch.empty(Nn, K, dtype=torch.uint8, device=out.device)
-        wsf = torch.empty(Nn, K // 32, dtype=torch.uint8, device=out.device)
-        rc = N.lib().msq_widen_fp4_to_mxfp8(N.ptr(pw.codes), N.ptr(pw.bitmap), N.ptr(pw.e_in), N.ptr(pw.e_out), N.ptr(wb),
-                                            N.ptr(wsf), Nn, K, int(pw.plain), N.stream_ptr(out.device))
-        N.check(rc, "msq_widen_fp4_to_mxfp8")
+    dense = getattr(pw, "_mx8_dense", None)
+    if K % 128 == 0 and (dense is not None or cache_dense or M >= MX8_DENSE_MIN_M):
+        # widen the FP4 weight to E4M3 bytes (once per call in the compute-bound regime, once per weight when
+        # cached), then both operands stream through TMA
+        if dense is None:
+            dense = widen_weight_mx8(pw)
+            if cache_dense:
+                pw._mx8_dense = dense
+        wb, wsf = dense
         rc = N.lib().msq_gemm_mxfp8_dense(N.ptr(xq.codes), K, N.ptr(xq.e_in), N.ptr(wb), K, N.ptr(wsf), N.ptr(out),
                                           out.stride(0), M, Nn, K, 0, N.stream_ptr(out.device))
         N.check(rc, "msq_gemm_mxfp8_dense")

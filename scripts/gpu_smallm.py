@@ -28,8 +28,14 @@ for K, Nn in ((4096, 4096), (4096, 11008), (11008, 4096), (8192, 8192)):
         x = torch.randn(Mx, K, device='cuda')
         xb = x.to(torch.bfloat16)
         xq = msq_b200.pack_mx(x, 8, 'fp8_e4m3', axes=[-1], block_size=32)
+        pw._mx8_dense = None
         t8 = graph_time(lambda: _tc.packed_linear_mx8(xq, pw))
+        _tc.packed_linear_mx8(xq, pw, cache_dense=True)
+        t8d = graph_time(lambda: _tc.packed_linear_mx8(xq, pw))
+        y_d = _tc.packed_linear_mx8(xq, pw); pw._mx8_dense = None
+        y_f = _tc.packed_linear_mx8(xq, pw)
+        assert float((y_d - y_f).abs().max()) <= 1e-3 * float(y_f.abs().max()) + 1e-6
         t4 = graph_time(lambda: _tc.packed_linear(xb, pw))
         tc = graph_time(lambda: torch.matmul(xb, Wd.t()))
-        print('K=%5d N=%5d M=%3d | mx8 %.1f us (%.0f GB/s of packed W) | w4-bf16 %.1f us (%.0f GB/s) | cuBLAS bf16 dense %.1f us (%.0f GB/s of bf16 W)'
-              % (K, Nn, Mx, t8 * 1e3, wbytes / t8 / 1e6, t4 * 1e3, wbytes / t4 / 1e6, tc * 1e3, 2 * K * Nn / tc / 1e6)); sys.stdout.flush()
+        print('K=%5d N=%5d M=%3d | mx8 cached-dense %.1f us (%.0f GB/s of E4M3 W) | mx8 %.1f us (%.0f GB/s of packed W) | w4-bf16 %.1f us (%.0f GB/s) | cuBLAS bf16 dense %.1f us (%.0f GB/s of bf16 W)'
+              % (K, Nn, Mx, t8d * 1e3, (K * Nn * 33 / 32) / t8d / 1e6, t8 * 1e3, wbytes / t8 / 1e6, t4 * 1e3, wbytes / t4 / 1e6, tc * 1e3, 2 * K * Nn / tc / 1e6)); sys.stdout.flush()
