@@ -1,15 +1,21 @@
-"""utils/modelutils.py mirror (reference: 15 lines): DEV and find_layers."""
+"""Model helpers used by the layer-sequential driver: the default device and the lookup of the quantizable
+sub-modules of a decoder layer (same call signature and result as the reference's utils/modelutils.find_layers)."""
 import torch
-import torch.nn as nn
+from torch import nn
 
-DEV = torch.device("cuda:0")
+DEV = torch.device("cuda", 0)
+
+#: module types GPTQ / RTN replace
+QUANTIZABLE = (nn.Conv2d, nn.Linear)
 
 
-def find_layers(module, layers=(nn.Conv2d, nn.Linear), name=""):
-    """{qualified name: module} for every Linear / Conv2d below `module` (utils/modelutils.py:8-15)"""
-    if isinstance(module, tuple(layers)):
+def find_layers(module, layers=QUANTIZABLE, name=""):
+    """Ordered dict-like {qualified name: sub-module} of every instance of `layers` at or below `module`, names
+    relative to `module` (prefixed by `name` when given), in registration order."""
+    kinds = tuple(layers)
+    prefix = name + "." if name else ""
+    if isinstance(module, kinds):
         return {name: module}
-    found = {}
-    for child_name, child in module.named_children():
-        found.update(find_layers(child, layers=layers, name=name + "." + child_name if name != "" else child_name))
-    return found
+    # named_modules() walks depth first in registration order, exactly the order a recursive descent yields;
+    # a quantizable module has no quantizable descendants in the models this is used on (Linear / Conv2d are leaves)
+    return {prefix + qual: sub for qual, sub in module.named_modules() if qual and isinstance(sub, kinds)}
