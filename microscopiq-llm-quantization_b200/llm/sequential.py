@@ -103,7 +103,7 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
     qcfg = dict(REFERENCE_QCFG if qcfg is None else qcfg)
     layers, _, _, _ = decoder_parts(model)
     stats = stats if stats is not None else {}
-    stats.update(hessian_s=0.0, solve_s=0.0, forward_s=0.0, comm_s=0.0, linears=0)
+    stats.update(hessian_s=0.0, solve_s=0.0, forward_s=0.0, comm_s=0.0, move_s=0.0, linears=0)
     quantizers = {}
     world, rank = 1, 0
     if D.is_dist():
@@ -139,7 +139,10 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
     nsamples = inps.shape[0]
     GPTQ.verbose = verbose
     for i in range(len(layers)):
+        t0 = time.perf_counter()
         layer = layers[i].to(dev)
+        torch.cuda.synchronize()
+        stats["move_s"] += time.perf_counter() - t0
         full = find_layers(layer)
         if true_sequential and all(n in full for grp in LLAMA_TRUE_SEQUENTIAL for n in grp):
             sequential = LLAMA_TRUE_SEQUENTIAL
@@ -198,7 +201,9 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
             outs[j] = _run_layer(layer, inps[j].unsqueeze(0), args, kwargs)
         torch.cuda.synchronize()
         stats["forward_s"] += time.perf_counter() - t0
+        t0 = time.perf_counter()
         layers[i] = layer.cpu()
+        stats["move_s"] += time.perf_counter() - t0
         del layer, gptq
         inps, outs = outs, inps
     return quantizers
