@@ -204,6 +204,11 @@ int msq_host_quantize_mx_outlier_f32(const float* h_in, float* h_out, long long 
 int msq_host_sync(int* status_out);
 int msq_host_release(void);
 
+/* (m, k) such that floor(n / d) == ((unsigned long long)n * m) >> k for all 0 <= n < 2^31 -- the exact
+ * divider behind the kernels' block-linear index arithmetic (replaces the integer divisions of the
+ * [pre, L, post] view, utils/quant.py:544-616); exported for host-side testing. */
+int msq_magic_div(long long d, unsigned int* m, int* k);
+
 #ifdef __cplusplus
 }
 #endif

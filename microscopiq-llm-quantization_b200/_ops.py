@@ -17,6 +17,7 @@ N.register("msq_host_quantize_mx_outlier_f32", _i, [_p, _p, _ll, _ll, _ll, _i, _
                                                      _f, _i, _i, _ll, _i])
 N.register("msq_host_sync", _i, [C.POINTER(C.c_int)])
 N.register("msq_host_release", _i, [])
+N.register("msq_magic_div", _i, [_ll, C.POINTER(C.c_uint), C.POINTER(C.c_int)])
 
 
 def _rmode(round):

@@ -315,6 +315,14 @@ long long msq_packed_hi_seg_stride(int block_size, int hi_w) {
 
 int msq_seg_blocks(void) { return MSQ_SEG_BLOCKS; }
 
+// (m, k) with floor(n / d) == (n * m) >> k for every 0 <= n < 2^31: the divider the packing kernels use for their
+// block-linear index arithmetic (exported so that the host-side construction can be tested without a GPU)
+int msq_magic_div(long long d, unsigned int* m, int* k) {
+  if (d <= 0 || d >= 0x7fffffffLL || !m || !k) return MSQ_ERR_BAD_ARG;
+  magic_div(d, m, k);
+  return MSQ_OK;
+}
+
 int msq_quantize_mx_outlier_f32(
     const float* in, float* deq, long long pre, long long L, long long post, int block_size,
     int in_scale_bits, int out_scale_bits,

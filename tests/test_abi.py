@@ -98,3 +98,24 @@ def test_api_surface_matches_reference_names():
     specs = msq_b200.finalize_mx_specs({"w_elem_format": "fp6_e3m2", "a_elem_format": "fp6_e3m2", "block_size": 32})
     assert specs["w_elem_format_bp"] == "fp6_e3m2" and specs["round_mx_output"] == "nearest"
     assert msq_b200.finalize_mx_specs({}) is None
+
+
+def test_magic_divider_is_exact():
+    """host-side construction of the kernels' exact divider: floor(n / d) == (n * m) >> k for 0 <= n < 2^31"""
+    import ctypes as C
+    import random
+    import msq_b200  # noqa: F401  (registers the signatures)
+    from msq_b200 import _native as N
+    L = N.lib()
+    rnd = random.Random(7)
+    ds = [1, 2, 3, 5, 7, 16, 31, 32, 33, 4096, 11008, 4095, 4097, 65535, 65536, 65537, 2 ** 30, 2 ** 31 - 2]
+    ds += [rnd.randrange(1, 2 ** 31 - 1) for _ in range(200)] + [rnd.randrange(1, 100000) for _ in range(200)]
+    for d in ds:
+        m, k = C.c_uint(0), C.c_int(0)
+        assert L.msq_magic_div(d, C.byref(m), C.byref(k)) == 0
+        ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, 2 ** 31 - 1, 2 ** 31 - 2, (2 ** 31 - 1) // d * d, (2 ** 31 - 1) // d * d - 1]
+        ns += [rnd.randrange(0, 2 ** 31) for _ in range(50)]
+        for n in ns:
+            if 0 <= n < 2 ** 31:
+                assert (n * m.value) >> k.value == n // d, (n, d, m.value, k.value)
+    assert L.msq_magic_div(0, C.byref(m), C.byref(k)) != 0
