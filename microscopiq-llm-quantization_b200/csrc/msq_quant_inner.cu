@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256) k_inner(const QParams P) {
   int st = 0;
   const long long nelem = P.nblocks * BS;
   const long long seg_e0 = seg * MSQ_SEG_BLOCKS * BS;
-#pragma unroll 1
+#pragma unroll ((OUTLIER && !PACK) ? 2 : 1)
   for (int it = 0; it < (MSQ_SEG_BLOCKS * BS) / (256 * N); ++it) {
     const long long e0 = seg_e0 + (long long)it * (256 * N) + threadIdx.x * N;
     const bool active = e0 < nelem;
