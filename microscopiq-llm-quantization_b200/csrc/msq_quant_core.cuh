@@ -46,11 +46,6 @@ __host__ inline void finish_cfg(QCfg& c) {
   enc_consts(c.fout, &c.ksh_o, &c.cmax_o, &c.sgn_o);
 }
 
-template <int LPB> __device__ __forceinline__ double grp_sum(double v) {
-#pragma unroll
-  for (int o = LPB / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 // fp32 sum over the LPB lanes in canonical tree order: partner distance 1, 2, 4, ... continues the
 // in-thread adjacent pairwise tree (commutativity makes every lane end with the same value)
 template <int LPB> __device__ __forceinline__ float grp_sum_tree(float v) {
@@ -130,25 +125,6 @@ __device__ __forceinline__ float qelem_mx(float x, bool isf, int min_exp, float 
 
 __device__ __forceinline__ float qelem_rt(float v, const Fmt& f, int rmode) {
   return qelem_mx(v, f.ebits != 0, f.min_exp, f.up, f.down, f.max_norm, make_round(rmode));
-}
-
-// Same arithmetic for FINITE inputs with |x| < 2^127 (true for every scaled block element:
-// |x / 2^e| <= 2^(emax+1)), which lets both powers of two be built with one integer op each
-// and the clamp use min/max.
-__device__ __forceinline__ float qelem_mx_bounded(float x, bool isf, int min_exp, float up, float down, float mx,
-                                                  const RoundSel rs) {
-  const int be = (__float_as_int(x) >> 23) & 0xFF;
-  const int p = isf ? max(be - 127, min_exp) : 0;
-  float y = __fmul_rn(__fmul_rn(x, __int_as_float((127 - p) << 23)), up);
-  const float a = fabsf(y);
-  float r = floorf(__fadd_rn(a, rs.addend));
-  if (rs.even) {
-    const float t = __fadd_rn(a, -0.5f);
-    const float h = __fmul_rn(t, 0.5f);
-    if (t >= 0.0f && h == floorf(h)) r = __fadd_rn(r, -1.0f);
-  }
-  y = __fmul_rn(__fmul_rn(copysignf(r, y), down), __int_as_float((p + 127) << 23));
-  return fminf(fmaxf(y, -mx), mx);
 }
 
 // floor(log2(a)) for finite a >= 0 with the reference's "0 -> FP32_MIN_NORMAL" (quant.py:520-523), branch-free
