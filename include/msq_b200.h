@@ -4,8 +4,13 @@
  *
  * Boundary rules:
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
- *   - the caller owns every buffer, nothing is allocated behind its back and there is no
- *     global state; `stream` is the caller's cudaStream_t (NULL = legacy default stream);
+ *   - the device-pointer entry points own nothing: the caller allocates every buffer, nothing is
+ *     allocated behind its back and they keep no state between calls; they run on the device that
+ *     owns their first buffer (the calling thread's current device is restored on return) and on
+ *     the caller's `stream` (a cudaStream_t of that device; NULL = legacy default stream);
+ *   - the ONE exception is the host-buffer pipeline (msq_host_*, at the end of this header): it
+ *     keeps, per device, three streams, staging buffers sized to the largest chunk seen and a status
+ *     word, created on first use, guarded by a mutex and freed by msq_host_release();
  *   - every function returns MSQ_OK (0) or a negative MSQ_ERR_*; nothing calls exit()
  *     (the reference's gpuErrchk does: number_system/mx/cpp/common.cuh:211-219);
  *   - there is no CPU fallback behind any of these symbols.
@@ -98,6 +103,14 @@ int msq_quantize_mx_outlier_f32(
 int msq_outlier_bounds_across_blocks_f32(const float* in, float* lo, float* hi, long long pre,
                                          long long L, long long post, int block_size,
                                          float std_dev, void* stream);
+
+/* ---- innermost-dimension reductions ------------------------------------------------------
+ * replaces reduce_sum_inner_dim / reduce_max_inner_dim   number_system/mx/cpp/funcs.cpp:197-211
+ *          (kernels cpp/reduce.cuh:150-210).  in [rows, inner] fp32 contiguous, out [rows];
+ * op 0 = sum, 1 = max (start value -65504, cpp/reduce.cuh:87); 32 <= inner <= 1024, inner % 32 == 0
+ * (the reference's AT_ASSERTM, reduce.cu:34-35), else MSQ_ERR_UNSUPPORTED.  The fp32 sum uses the
+ * reference's two-level shuffle-tree association order. */
+int msq_reduce_inner_dim_f32(const float* in, float* out, long long rows, int inner, int op, void* stream);
 
 /* ---- packed planes -> dense -------------------------------------------------------------
  * Inverse of the packed outputs of msq_quantize_mx_outlier_f32 / msq_quantize_mx_f32 (plain != 0).

@@ -86,8 +86,9 @@ def packed_linear(x, pw, bias=None):
     terms (2 / 3 accumulating passes) so that every product stays exact."""
     N.require_cuda(x, "x")
     from . import _ops
-    if len(pw.shape) != 2 or pw.axis != 1 or pw.block_size != 32 or pw.hi_w != 0:
-        raise NotImplementedError("packed_linear needs a [N, K] tensor packed along K with block 32 and equal code widths")
+    if len(pw.shape) != 2 or pw.axis != 1 or pw.block_size != 32 or pw.hi_w != 0 or pw.shape[1] % 32:
+        raise NotImplementedError("packed_linear needs a [N, K] tensor packed along K with block 32, K a multiple "
+                                  "of 32 and equal code widths")
     Nn, K = pw.shape
     lead = x.shape[:-1]
     x2 = x.reshape(-1, K)
@@ -104,14 +105,54 @@ def packed_linear(x, pw, bias=None):
         return out.reshape(*lead, Nn)
     for i, t in enumerate(_bf16_terms(x2)):
         t = t.contiguous()
-        if K % 8:
-            raise NotImplementedError("K must be a multiple of 32")
         rc = N.lib().msq_gemm_packed_w_bf16(N.ptr(t), t.stride(0), N.ptr(pw.codes), N.ptr(pw.bitmap), N.ptr(pw.e_in),
                                             N.ptr(pw.e_out), N.ptr(out), out.stride(0), M, Nn, K, fi[0], fi[1], fo[0],
                                             fo[1], int(pw.plain), int(i > 0), N.stream_ptr(x.device))
         N.check(rc, "msq_gemm_packed_w_bf16")
     if bias is not None:
         out += bias.float()
+    return out.reshape(*lead, Nn)
+
+
+def dense_linear(x, w, x_terms=None, w_terms=None, bias=None):
+    """y[..., N] (fp32) = x[..., K] @ w[N, K].T on tcgen05 for operands that have no packed form (the reference's
+    `f_linear(qis_input, qis_weight)`, number_system/mx/linear.py:91, when the weight is not packable).
+    Each operand is split into bf16 terms whose sum is the operand exactly (1 term for MX-quantized values -- every
+    element format has at most 8 significand bits --, 3 for arbitrary fp32); products of terms are exact in the fp32
+    accumulator, term pairs below 2^-24 of the leading product are dropped."""
+    N.require_cuda(x, "x")
+    N.require_cuda(w, "w")
+    K = x.shape[-1]
+    assert w.dim() == 2 and w.shape[1] == K
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, K)
+    M, Nn = x2.shape[0], w.shape[0]
+    Kp = (K + 7) // 8 * 8                          # TMA row pitch: multiples of 16 bytes
+
+    def terms(t, n):
+        t = t.float()
+        if Kp != K:
+            t = torch.nn.functional.pad(t, (0, Kp - K))
+        if n is None:
+            return _bf16_terms(t)
+        out = []
+        for _ in range(n):
+            b = t.to(torch.bfloat16)
+            out.append(b)
+            t = t - b.float()
+        return out
+    xt, wt = terms(x2, x_terms), terms(w, w_terms)
+    out = torch.empty(M, (Nn + 3) // 4 * 4, dtype=torch.float32, device=x.device)
+    first = True
+    for i, a in enumerate(xt):
+        for j, b in enumerate(wt):
+            if i + j > 2:
+                continue
+            gemm_nt(a.contiguous(), b.contiguous(), out=out, alpha=1.0, beta=0.0 if first else 1.0)
+            first = False
+    out = out[:, :Nn]
+    if bias is not None:
+        out = out + bias.float()
     return out.reshape(*lead, Nn)
 
 

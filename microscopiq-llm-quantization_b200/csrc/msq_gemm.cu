@@ -269,11 +269,8 @@ static int gemm_nt_16(const void* A, const void* B, float* C, int M, int N, int 
   GemmParams P;
   P.C = C; P.ldc = ldc; P.M = M; P.N = N; P.K = K; P.alpha = alpha; P.beta = beta; P.ab_format = ab_format;
   P.tiles_m = (M + BM - 1) / BM; P.tiles_n = (N + BN - 1) / BN; P.upper_only = upper_only;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(k_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
-    attr_set = true;
-  }
+  // the opt-in is per device: set it on every launch (microseconds) instead of once per process
+  if (cudaFuncSetAttribute(k_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
   int grid = P.tiles_m * P.tiles_n;
   if (grid > sm_count()) grid = sm_count();
   k_gemm_nt<<<grid, 256, GEMM_SMEM, stream>>>(tmA, tmB, P);
@@ -289,6 +286,7 @@ extern "C" {
 // C[M,N] fp32 = alpha * A[M,K] * B[N,K]^T + beta * C ; A, B 16-bit (dtype 1 = fp16, 2 = bf16), K contiguous
 int msq_gemm_nt_f32out(const void* A, const void* B, float* C, int M, int N, int K, long long lda, long long ldb,
                        long long ldc, float alpha, float beta, int dtype, void* stream) {
+  msq::DevGuard dev_guard_(A);
   if (dtype != 1 && dtype != 2) return MSQ_ERR_BAD_ARG;
   return gemm_nt_16(A, B, C, M, N, K, lda, ldb, ldc, alpha, beta, dtype == 2 ? 1 : 0, 0, (cudaStream_t)stream);
 }
@@ -306,6 +304,7 @@ long long msq_hessian_workspace_bytes(int T, int K, int dtype) {
 // symmetric != 0: only tiles touching the upper triangle are computed, then mirrored.
 int msq_hessian_accumulate(const void* X, int T, int K, long long ldx, int dtype, float* H, long long ldh, float alpha,
                            float beta, void* workspace, long long workspace_bytes, int symmetric, void* stream) {
+  msq::DevGuard dev_guard_(X);
   if (!X || !H || !workspace || T <= 0 || K <= 0 || dtype < 0 || dtype > 2) return MSQ_ERR_BAD_ARG;
   if (workspace_bytes < msq_hessian_workspace_bytes(T, K, dtype)) return MSQ_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;

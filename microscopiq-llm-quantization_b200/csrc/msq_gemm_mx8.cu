@@ -446,11 +446,8 @@ static int launch_mx8(const unsigned char* xcodes, long long ldx, const signed c
   } else {
     tmW = tmX;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(k_gemm_mx8, cudaFuncAttributeMaxDynamicSharedMemorySize, MX8_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
-    attr_set = true;
-  }
+  // the opt-in is per device: set it on every launch (microseconds) instead of once per process
+  if (cudaFuncSetAttribute(k_gemm_mx8, cudaFuncAttributeMaxDynamicSharedMemorySize, MX8_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
   int grid = P.tiles_n * P.tiles_m * P.ksplit;
   if (grid > sms) grid = sms;
   k_gemm_mx8<<<grid, 512, MX8_SMEM, s>>>(tmX, tmW, P);
@@ -460,6 +457,7 @@ static int launch_mx8(const unsigned char* xcodes, long long ldx, const signed c
 int msq_gemm_mxfp8_blockscaled(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* wcodes,
                                const unsigned int* wbitmap, const signed char* we_in, const signed char* we_out, float* C,
                                long long ldc, int M, int N, int K, int plain, int accumulate, void* stream) {
+  msq::DevGuard dev_guard_(xcodes);
   if (!xcodes || !xe || !wcodes || !we_in || !C || M <= 0 || N <= 0 || K <= 0) return MSQ_ERR_BAD_ARG;
   if (!plain && (!wbitmap || !we_out)) return MSQ_ERR_BAD_ARG;
   if (K % 32 != 0) return MSQ_ERR_UNSUPPORTED;
@@ -472,6 +470,7 @@ int msq_gemm_mxfp8_blockscaled(const unsigned char* xcodes, long long ldx, const
 int msq_widen_fp4_to_mxfp8(const unsigned char* wcodes, const unsigned int* wbitmap, const signed char* we_in,
                            const signed char* we_out, unsigned char* out_bytes, unsigned char* out_sf, int N, int K, int plain,
                            void* stream) {
+  msq::DevGuard dev_guard_(wcodes);
   if (!wcodes || !we_in || !out_bytes || !out_sf || N <= 0 || K <= 0 || (K % 32)) return MSQ_ERR_BAD_ARG;
   if (!plain && (!wbitmap || !we_out)) return MSQ_ERR_BAD_ARG;
   const long long nchunks = (long long)N * K / 16;
@@ -484,6 +483,7 @@ int msq_widen_fp4_to_mxfp8(const unsigned char* wcodes, const unsigned int* wbit
 int msq_gemm_mxfp8_dense(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* wbytes,
                          long long ldw, const unsigned char* wsf, float* C, long long ldc, int M, int N, int K, int accumulate,
                          void* stream) {
+  msq::DevGuard dev_guard_(xcodes);
   if (!xcodes || !xe || !wbytes || !wsf || !C || M <= 0 || N <= 0 || K <= 0) return MSQ_ERR_BAD_ARG;
   if (K % 128 != 0) return MSQ_ERR_UNSUPPORTED;          // scale words are read four K-blocks at a time
   if ((reinterpret_cast<uintptr_t>(xe) & 3) || (reinterpret_cast<uintptr_t>(wsf) & 3)) return MSQ_ERR_ALIGN;

@@ -321,6 +321,7 @@ int msq_gemm_packed_w_bf16(const void* X, long long ldx, const unsigned char* co
                            const signed char* e_in, const signed char* e_out, float* C, long long ldc, int M, int N, int K,
                            int in_ebits, int in_mbits, int out_ebits, int out_mbits, int plain, int accumulate,
                            void* stream) {
+  msq::DevGuard dev_guard_(X);
   if (!X || !codes || !e_in || !C || M <= 0 || N <= 0 || K <= 0) return MSQ_ERR_BAD_ARG;
   if (!plain && (!bitmap || !e_out)) return MSQ_ERR_BAD_ARG;
   if (K % 32 != 0) return MSQ_ERR_UNSUPPORTED;
@@ -364,11 +365,8 @@ int msq_gemm_packed_w_bf16(const void* X, long long ldx, const unsigned char* co
   CUtensorMap tmX;
   int rc = make_tmap_2d(&tmX, X, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, ldx, bnx, WBK);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(k_gemm_w4, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
-    attr_set = true;
-  }
+  // the opt-in is per device: set it on every launch (microseconds) instead of once per process
+  if (cudaFuncSetAttribute(k_gemm_w4, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
   int grid = P.tiles_n * P.tiles_m * P.ksplit;
   if (grid > sms) grid = sms;
   k_gemm_w4<<<grid, 512, W4_SMEM, (cudaStream_t)stream>>>(tmX, P);

@@ -193,6 +193,7 @@ int msq_gptq_block(const float* W, long long ldw, float* Q, long long ldq, const
                    int in_scale_bits, int out_scale_bits, int in_ebits, int in_mbits, int in_emax, float in_max_norm,
                    int out_ebits, int out_mbits, int out_emax, float out_max_norm, float std_dev, int flush_fp32_subnorms,
                    int rmode, void* stream) {
+  msq::DevGuard dev_guard_(W);
   if (!W || !Q || !Hinv || !Err || !loss || !zeros || !kcnt || !status || rows <= 0 || count <= 0 || count > GB)
     return MSQ_ERR_BAD_ARG;
   if (in_ebits > 5 || out_ebits > 5) return MSQ_ERR_UNSUPPORTED;
@@ -212,18 +213,15 @@ int msq_gptq_block(const float* W, long long ldw, float* Q, long long ldq, const
   else if (block_size == 32) k = k_gptq_block<32>;
   else if (block_size == 8) k = k_gptq_block<8>;
   else return MSQ_ERR_UNSUPPORTED;
-  static bool attr_done[3] = {false, false, false};
-  const int ki = block_size == 16 ? 0 : (block_size == 32 ? 1 : 2);
-  if (!attr_done[ki]) {
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MSQ_ERR_CUDA;
-    attr_done[ki] = true;
-  }
+  // the opt-in is per device: set it on every launch instead of once per process
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MSQ_ERR_CUDA;
   k<<<grid, 32, smem, s>>>(P);
   return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
 }
 
 int msq_gptq_trailing_update(float* W, long long ldw, const float* Err, const float* Hinv, long long ldh, int rows, int i1,
                              int count, int i2, int cols, void* stream) {
+  msq::DevGuard dev_guard_(W);
   if (!W || !Err || !Hinv || rows <= 0 || count <= 0 || count > GB) return MSQ_ERR_BAD_ARG;
   if (i2 >= cols) return MSQ_OK;
   dim3 grid((unsigned)((cols - i2 + 63) / 64), (unsigned)((rows + 63) / 64));
@@ -232,12 +230,14 @@ int msq_gptq_trailing_update(float* W, long long ldw, const float* Err, const fl
 }
 
 int msq_gptq_check_prune(const int* zeros, const int* kcnt, int cols, int* violation, void* stream) {
+  msq::DevGuard dev_guard_(zeros);
   if (!zeros || !kcnt || !violation || cols <= 0) return MSQ_ERR_BAD_ARG;
   k_gptq_check<<<(cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(zeros, kcnt, cols, violation);
   return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
 }
 
 int msq_rank1_sub_f32(float* W, long long ldw, const float* err, const float* h, int rows, int n, void* stream) {
+  msq::DevGuard dev_guard_(W);
   if (!W || !err || !h || rows <= 0 || n < 0) return MSQ_ERR_BAD_ARG;
   if (n == 0) return MSQ_OK;
   const long long tot = (long long)rows * n;

@@ -413,6 +413,7 @@ int msq_unpack_mx(const unsigned char* codes, const signed char* e_in, const sig
                   const unsigned char* hi, float* out_f32, void* out_bf16, long long pre, long long L, long long post,
                   int block_size, int in_ebits, int in_mbits, int in_emax, float in_max_norm, int out_ebits, int out_mbits,
                   int out_emax, float out_max_norm, int plain, void* stream) {
+  msq::DevGuard dev_guard_(codes);
   if (!codes || !e_in || (!out_f32 && !out_bf16) || pre <= 0 || L <= 0 || post <= 0 || block_size <= 0) return MSQ_ERR_BAD_ARG;
   if (!plain && (!bitmap || !e_out)) return MSQ_ERR_BAD_ARG;
   if (pre * L * post >= 0x7fffffffLL) return MSQ_ERR_UNSUPPORTED;

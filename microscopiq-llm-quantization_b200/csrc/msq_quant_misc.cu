@@ -333,6 +333,7 @@ int msq_quantize_mx_outlier_f32(
     unsigned char* codes, signed char* e_in, signed char* e_out, unsigned int* bitmap,
     unsigned char* hi, int* seg_cnt, unsigned char* blk_cnt, unsigned char* mask,
     int* status, int* path, void* stream) {
+  msq::DevGuard dev_guard_(in);
   if (!in || in_scale_bits <= 0 || out_scale_bits <= 0 || in_scale_bits > 8 || out_scale_bits > 8) return MSQ_ERR_BAD_ARG;
   if (rmode < 0 || rmode > 2 || (variant != 0 && variant != 1)) return MSQ_ERR_BAD_ARG;
   if (variant == 1 && (!lo_ext || !hi_ext)) return MSQ_ERR_BAD_ARG;
@@ -358,6 +359,7 @@ int msq_quantize_mx_f32(
     int scale_bits, int ebits, int mbits, int emax, float max_norm,
     int flush_fp32_subnorms, int rmode, int mode, const float* ext_max,
     unsigned char* codes, signed char* e_shared, int* status, int* path, void* stream) {
+  msq::DevGuard dev_guard_(in);
   if (!in || scale_bits <= 0 || scale_bits > 8 || rmode < 0 || rmode > 2 || (mode != 0 && mode != 1)) return MSQ_ERR_BAD_ARG;
   QParams P;
   memset(&P, 0, sizeof(P));
@@ -374,6 +376,7 @@ int msq_quantize_mx_f32(
 
 int msq_outlier_bounds_across_blocks_f32(const float* in, float* lo, float* hi, long long pre, long long L,
                                          long long post, int block_size, float std_dev, void* stream) {
+  msq::DevGuard dev_guard_(in);
   if (!in || !lo || !hi || block_size <= 0) return MSQ_ERR_BAD_ARG;
   const int nblk = (int)((L + block_size - 1) / block_size);
   if (nblk < 2) return MSQ_ERR_BAD_ARG;    // reference asserts: std of a single sample is NaN (mx_ops.py:66)
@@ -391,6 +394,7 @@ static int elemwise_grid(long long n, int vec) {
 
 int msq_quantize_elemwise(const void* in, void* out, long long n, int dtype, int bits, int exp_bits, float max_norm,
                           int rmode, int saturate_normals, int allow_denorm, int native, void* stream) {
+  msq::DevGuard dev_guard_(in);
   if (!in || !out || n < 0 || bits < 2 || bits > 25 || rmode < 0 || rmode > 2) return MSQ_ERR_BAD_ARG;
   if (n == 0) return MSQ_OK;
   Fmt f = make_fmt(exp_bits, bits, 0, max_norm);

@@ -131,6 +131,7 @@ extern "C" {
 
 int msq_uniform_quantize_f32(const float* x, float* out, const float* scale, const float* zero, int maxq,
                              long long pre, long long Cn, long long post, void* stream) {
+  msq::DevGuard dev_guard_(x);
   if (!x || !out || !scale || !zero || pre <= 0 || Cn <= 0 || post <= 0) return MSQ_ERR_BAD_ARG;
   const long long n = pre * Cn * post;
   long long blocks = (n + 255) / 256;
@@ -141,6 +142,7 @@ int msq_uniform_quantize_f32(const float* x, float* out, const float* scale, con
 
 int msq_uniform_find_params_f32(const float* x, float* scale, float* zero, long long rows, long long n, int maxq,
                                 int sym, int mse, float norm, int grid, float maxshrink, void* stream) {
+  msq::DevGuard dev_guard_(x);
   if (!x || !scale || !zero || rows <= 0 || n <= 0 || rows > 0x7fffffffLL) return MSQ_ERR_BAD_ARG;
   const int ncand = (int)(maxshrink * grid);             // range(int(maxshrink * grid)), quant.py:342
   k_uniform_find_params<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, scale, zero, n, maxq, sym, mse, norm, grid, ncand);
@@ -149,6 +151,7 @@ int msq_uniform_find_params_f32(const float* x, float* scale, float* zero, long 
 
 int msq_shared_exponents_f32(const float* x, float* out, long long pre, long long L, long long post, int ebits,
                              void* stream) {
+  msq::DevGuard dev_guard_(x);
   if (!x || !out || pre <= 0 || L <= 0 || post <= 0) return MSQ_ERR_BAD_ARG;
   const long long n = pre * post;
   k_shared_exponents<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, out, pre, L, post, ebits);

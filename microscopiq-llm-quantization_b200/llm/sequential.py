@@ -202,7 +202,6 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
     inps, args, kwargs = capture_layer_inputs(model, batches, dev)
     outs = torch.zeros_like(inps)
     nsamples = inps.shape[0]
-    GPTQ.verbose = verbose
     for i in range(len(layers)):
         t0 = time.perf_counter()
         layer = mover.fetch(i)
@@ -219,6 +218,7 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
             for name in subset:
                 gptq[name] = GPTQ(subset[name])
                 gptq[name].hessian_batch = hessian_batch
+                gptq[name].verbose = verbose
                 gptq[name].quantizer = MXQuantizer()
                 gptq[name].quantizer.configure(**qcfg)
 

@@ -6,3 +6,4 @@ from .specs import (MxSpecs, add_mx_args, apply_mx_specs, finalize_mx_specs, get
 from .elemwise_ops import quantize_elemwise_op  # noqa: F401
 from .mx_ops import quantize_mx_op, quantize_mx_outlier_op  # noqa: F401
 from .linear import MXLinear, linear  # noqa: F401,E402
+from . import custom_extensions  # noqa: F401,E402  (custom_extensions.funcs: the reference's seven pybind names)

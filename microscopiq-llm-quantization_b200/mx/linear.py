@@ -6,9 +6,10 @@
 Forward = the reference's LinearFunction.forward (linear.py:20-108): bfloat/fp rounding of input,
 weight and bias, MX+outlier quantization of both operands along the input-feature axis (axes=[1],
 across-block detector of mx_ops.py), fp32 matmul, rounding of the output, bias add, rounding.
-The matmul runs on the packed weight with tcgen05 (csrc/msq_gemm_w4.cu) whenever the weight is a
-2-D tensor blocked by 32 along K with an element format of at most 8 bits; otherwise on the
-dequantized operands.  The reference's backward is broken as shipped and is not
+The matmul runs on the packed weight with tcgen05 (csrc/msq_gemm_w4.cu, csrc/msq_gemm_mx8.cu) whenever the
+weight is a 2-D tensor blocked by 32 along K with an element format of at most 8 bits; otherwise
+(block size 128 of llm/opt_direct.py:98-105, ragged K, w_elem_format None ...) on the dequantized operands
+with the dense tcgen05 GEMM (_tc.dense_linear).  The reference's backward is broken as shipped and is not
 part of the contract: this layer is inference-only.
 """
 import torch
@@ -67,6 +68,15 @@ def linear_forward(input, weight, bias, mx_specs, packed_weight=None):
                 output = _tc.packed_linear_mx8(xq, packed_weight).to(input.dtype)
         if output is None:
             output = _tc.packed_linear(qis_input, packed_weight).to(input.dtype)
+    else:
+        # not packable (block size other than 32, ragged K, w_elem_format None, ...): linear.py:78-91 on the
+        # dequantized operands -- fake-quantize the weight, then the dense tcgen05 contraction
+        bf_weight = quantize_elemwise_op(weight, mx_specs=mx_specs, round=mx_specs["round_weight"])
+        qis_weight = quantize_mx_outlier_op(bf_weight, mx_specs, inlier_elem_format=mx_specs["w_elem_format"],
+                                            outlier_elem_format=mx_specs["w_elem_format"], axes=[1],
+                                            round=mx_specs["round_mx_output"])
+        output = _tc.dense_linear(qis_input, qis_weight, x_terms=None if mx_specs["a_elem_format"] is None else 1,
+                                  w_terms=None if mx_specs["w_elem_format"] is None else 1).to(input.dtype)
     output = quantize_elemwise_op(output, mx_specs=mx_specs, round=mx_specs["round_output"])
     if bf_bias is not None:
         output = quantize_elemwise_op(output + bf_bias, mx_specs=mx_specs, round=mx_specs["round_output"])

@@ -10,12 +10,18 @@ QUANTIZABLE = (nn.Conv2d, nn.Linear)
 
 
 def find_layers(module, layers=QUANTIZABLE, name=""):
-    """Ordered dict-like {qualified name: sub-module} of every instance of `layers` at or below `module`, names
-    relative to `module` (prefixed by `name` when given), in registration order."""
+    """{qualified name: sub-module} of every sub-module whose type is EXACTLY one of `layers` (utils/modelutils.py:8-16:
+    `type(module) in layers`, so subclasses such as NonDynamicallyQuantizableLinear or MXLinear are skipped, as in
+    the reference), in registration order; matched modules are not descended into and a module shared between two
+    parents is listed under both names."""
     kinds = tuple(layers)
-    prefix = name + "." if name else ""
-    if isinstance(module, kinds):
-        return {name: module}
-    # named_modules() walks depth first in registration order, exactly the order a recursive descent yields;
-    # a quantizable module has no quantizable descendants in the models this is used on (Linear / Conv2d are leaves)
-    return {prefix + qual: sub for qual, sub in module.named_modules() if qual and isinstance(sub, kinds)}
+    found = {}
+    stack = [(name, module)]
+    while stack:
+        qual, mod = stack.pop()
+        if type(mod) in kinds:
+            found[qual] = mod
+            continue
+        children = [((qual + "." + n) if qual else n, c) for n, c in mod.named_children()]
+        stack.extend(reversed(children))
+    return found

@@ -201,7 +201,13 @@ def make_linear():
     d = {}
     cases = [dict(w_elem_format="fp4_e2m1", a_elem_format=None, block_size=32),
              dict(w_elem_format="fp6_e3m2", a_elem_format="fp6_e3m2", block_size=32, scale_bits=4, bfloat=16),
-             dict(w_elem_format="fp4_e2m1", a_elem_format="fp8_e4m3", block_size=32, scale_bits=8)]
+             dict(w_elem_format="fp4_e2m1", a_elem_format="fp8_e4m3", block_size=32, scale_bits=8),
+             # not packable by the B200 path -> dense fallback: the spec of llm/opt_direct.py:98-105 (block 128),
+             # a small block, and the weight / the activations left unquantized
+             dict(w_elem_format="fp4", a_elem_format="int4", block_size=128, custom_cuda=False, quantize_backprop=False),
+             dict(w_elem_format="fp4_e2m1", a_elem_format="fp8_e4m3", block_size=16, scale_bits=8),
+             dict(w_elem_format=None, a_elem_format="fp8_e4m3", block_size=32, scale_bits=8),
+             dict(w_elem_format="int8", a_elem_format=None, block_size=64, scale_bits=8, bfloat=16)]
     for n, spec in enumerate(cases):
         g = torch.Generator().manual_seed(800 + n)
         x = torch.randn(64, 256, generator=g)

@@ -73,3 +73,63 @@ def test_reference_cuda_kernels_vs_ours(fmt, bs, axis):
         ref = REF.quantize_elemwise_func_cuda(x, mb, eb, mx, rmode, True, True)
         ours = msq_b200._quantize_elemwise_core(x, mb, eb, mx, rnd, True, True, custom_cuda=True)
         assert_exact(ours, ref, "elemwise %s %s" % (fmt, rnd))
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_custom_extensions_funcs_shim_vs_reference_module():
+    """the seven names of the reference's pybind module (cpp/funcs.cpp:218-226) behind `custom_extensions.funcs`,
+    each called exactly like mx_ops.py:371-422 / elemwise_ops.py:120-129 call it, against the reference's own
+    compiled module on the same tensors"""
+    from msq_b200.mx import custom_extensions as ce
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(6, 96, 320, generator=g) * torch.logspace(-5, 3, 96).reshape(1, 96, 1)).cuda()
+    for fmt, tile in (("fp4_e2m1", 32), ("fp6_e3m2", 16), ("int8", 10), ("fp8_e4m3", 64)):
+        eb, mb, _, mx, _ = O.format_params(fmt)
+        for rmode in (0, 1, 2):
+            for axis in (0, 1, 2):
+                ref = REF.quantize_mx_by_tile_func_cuda(x, 8, eb, mb, mx, tile, axis, False, rmode)
+                assert_exact(ce.funcs.quantize_mx_by_tile_func_cuda(x, 8, eb, mb, mx, tile, axis, False, rmode), ref,
+                             "by_tile %s axis %d rmode %d" % (fmt, axis, rmode))
+                mv = x.abs().max(dim=axis, keepdim=True).values.contiguous()
+                ref = REF.quantize_mx_func_cuda(x, 8, eb, mb, mx, mv, axis, True, rmode)
+                assert_exact(ce.funcs.quantize_mx_func_cuda(x, 8, eb, mb, mx, mv, axis, True, rmode), ref,
+                             "mx_func %s axis %d rmode %d" % (fmt, axis, rmode))
+            ref = REF.quantize_elemwise_func_cuda(x, mb, eb, mx, rmode, False, True)
+            assert_exact(ce.funcs.quantize_elemwise_func_cuda(x, mb, eb, mx, rmode, False, True), ref)
+            xh = x.half()
+            ref = REF.quantize_elemwise_func_cuda(xh, mb, eb, mx, rmode, True, False)
+            assert_exact(ce.funcs.quantize_elemwise_func_cuda(xh, mb, eb, mx, rmode, True, False).float(), ref.float())
+    # host-tensor names: same results as the reference's CPU loops
+    xc = x[:2].cpu().contiguous()
+    eb, mb, _, mx, _ = O.format_params("fp6_e2m3")
+    mv = xc.abs().max(dim=2, keepdim=True).values
+    assert_exact(ce.funcs.quantize_mx_func_cpp(xc, 8, eb, mb, mx, mv, 2, False, 0),
+                 REF.quantize_mx_func_cpp(xc, 8, eb, mb, mx, mv, 2, False, 0))
+    assert_exact(ce.funcs.quantize_elemwise_func_cpp(xc, mb, eb, mx, 2, True, True),
+                 REF.quantize_elemwise_func_cpp(xc, mb, eb, mx, 2, True, True))
+    # reductions: bit-identical sums (same association order), maxima with the -65504 floor
+    for inner in (32, 64, 320, 1024):
+        a = (torch.randn(37, 5, inner, generator=g) * 100).cuda()
+        assert_exact(ce.funcs.reduce_sum_inner_dim(a), REF.reduce_sum_inner_dim(a), "sum %d" % inner)
+        assert_exact(ce.funcs.reduce_max_inner_dim(a), REF.reduce_max_inner_dim(a), "max %d" % inner)
+    a = torch.full((3, 64), -1.0e5).cuda()
+    assert_exact(ce.funcs.reduce_max_inner_dim(a), REF.reduce_max_inner_dim(a))
+    with pytest.raises(RuntimeError):
+        ce.funcs.reduce_sum_inner_dim(torch.zeros(4, 48).cuda())
+    with pytest.raises(RuntimeError):
+        ce.funcs.quantize_elemwise_func_cuda(x, 25, 8, 1.0)
+    with pytest.raises(RuntimeError):
+        ce.funcs.quantize_mx_by_tile_func_cuda(x.transpose(0, 1), 8, 2, 3, 6.0, 32, 0)
+
+
+def test_custom_extensions_funcs_names():
+    """CPU tier: the shim exposes exactly the reference's seven names and refuses host tensors on the *_cuda names"""
+    from msq_b200.mx import custom_extensions as ce
+    names = ["quantize_mx_func_cpp", "quantize_elemwise_func_cpp", "quantize_mx_func_cuda", "quantize_mx_by_tile_func_cuda",
+             "quantize_elemwise_func_cuda", "reduce_sum_inner_dim", "reduce_max_inner_dim"]
+    assert sorted(n for n in dir(ce.funcs) if not n.startswith("_")) == sorted(names)
+    with pytest.raises(RuntimeError):
+        ce.funcs.quantize_mx_by_tile_func_cuda(torch.zeros(4, 32), 8, 2, 3, 6.0, 32, 1)
+    with pytest.raises(RuntimeError):
+        ce.funcs.reduce_max_inner_dim(torch.zeros(4, 32))
