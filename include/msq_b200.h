@@ -165,10 +165,50 @@ int msq_gptq_block(const float* W, long long ldw, float* Q, long long ldq, const
                    int in_ebits, int in_mbits, int in_emax, float in_max_norm,
                    int out_ebits, int out_mbits, int out_emax, float out_max_norm,
                    float std_dev, int flush_fp32_subnorms, int rmode, void* stream);
+/* msq_gptq_solve_f32: the whole column loop of one linear (llm/gptq.py:106-165) queued on `stream` without host
+ *   round trips: per 128-column block the two-warp column kernel (rank-1 updates off the critical path, same fp32
+ *   operation order per weight as the reference), then the trailing update on tcgen05 when ut_planes (from
+ *   msq_cholinv_ut_planes, or msq_split3_planes_f32 of Hinv^T) is given, else in fp32 SIMT; then the prune check. */
+long long msq_gptq_solve_workspace_bytes(int rows);
+int msq_gptq_solve_f32(float* W, long long ldw, float* Q, long long ldq, const float* Hinv, long long ldh,
+                       const void* ut_planes, long long ut_ld, int ut_plane_rows, int rows, int cols,
+                       void* workspace, long long workspace_bytes, double* loss, int* zeros, int* kcnt,
+                       int* status, int* violation, int block_size, int in_scale_bits, int out_scale_bits,
+                       int in_ebits, int in_mbits, int in_emax, float in_max_norm,
+                       int out_ebits, int out_mbits, int out_emax, float out_max_norm,
+                       float std_dev, int flush_fp32_subnorms, int rmode, void* stream);
 int msq_gptq_trailing_update(float* W, long long ldw, const float* Err, const float* Hinv, long long ldh,
                              int rows, int i1, int count, int i2, int cols, void* stream);
 int msq_gptq_check_prune(const int* zeros, const int* kcnt, int cols, int* violation, void* stream);
 int msq_rank1_sub_f32(float* W, long long ldw, const float* err, const float* h, int rows, int n, void* stream);
+
+/* ---- fp32-accurate tensor-core contraction (bf16 plane stacks) ------------------------------
+ * x = p0 + p1 + p2 exactly with bf16 planes; the six significant plane pairs are accumulated by
+ * tcgen05.mma kind::f16 into the fp32 TMEM accumulator (every product exact), so the result has
+ * fp32-level error.  replaces the fp32 cuBLAS/cuSOLVER contractions of llm/gptq.py:101-103,165 and
+ * number_system/mx/linear.py:91.
+ * msq_split3_planes_f32: src fp32 [rows, cols] -> planes[(p * plane_rows + r) * ldp + c], columns
+ *   zero-filled up to the next multiple of 64 (ldp >= that, ldp % 8 == 0).
+ * msq_gemm_split3_f32:   C[M,N] = alpha * A[M,K] B[N,K]^T + beta * C. */
+int msq_split3_planes_f32(const float* src, long long ld, int rows, int cols, void* planes, long long ldp,
+                          int plane_rows, void* stream);
+int msq_gemm_split3_f32(const void* a_planes, long long a_ld, int a_plane_rows, const void* b_planes,
+                        long long b_ld, int b_plane_rows, float* C, long long ldc, int M, int N, int K,
+                        float alpha, float beta, void* stream);
+
+/* ---- Cholesky trio of GPTQ.fasterquant -------------------------------------------------------
+ * replaces  H = cholesky(H); H = cholesky_inverse(H); H = cholesky(H, upper=True)   llm/gptq.py:101-103
+ * H fp32 [n, n] (ld = ldh, % 4), symmetric positive definite, upper triangle read, DESTROYED;
+ * U fp32 [n, n] (ld = ldu, % 4) receives the upper-triangular factor with U^T U = H^-1 (zeros below
+ * the diagonal).  One reverse Cholesky H = R R^T (R upper) + one triangular inverse U = R^-1, blocked
+ * recursively with every panel product on tcgen05 (split-plane GEMM).  info: device int32 zeroed by
+ * the caller, receives 1 + index of the first non-positive pivot (LAPACK's info), U then holds NaNs.
+ * The workspace keeps bf16 planes of U^T afterwards (msq_cholinv_ut_planes): operand of
+ * msq_gptq_solve_f32's tensor-core trailing update. */
+long long msq_cholinv_workspace_bytes(int n);
+int msq_cholinv_upper_f32(float* H, long long ldh, float* U, long long ldu, int n, void* workspace,
+                          long long workspace_bytes, int* info, void* stream);
+int msq_cholinv_ut_planes(void* workspace, int n, void** planes, long long* ld, int* plane_rows);
 
 /* ---- packed-weight linear ---------------------------------------------------------------
  * C[M,N] fp32 (+)= X[M,K] (bf16) * dequant(W)[N,K]^T, W = packed planes blocked by 32 along K with equal

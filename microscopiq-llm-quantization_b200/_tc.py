@@ -60,6 +60,95 @@ def hessian_accumulate(H, X, alpha, beta, symmetric=True):
     return H
 
 
+N.register("msq_split3_planes_f32", _i, [_p, _ll, _i, _i, _p, _ll, _i, _p])
+N.register("msq_gemm_split3_f32", _i, [_p, _ll, _i, _p, _ll, _i, _p, _ll, _i, _i, _i, _f, _f, _p])
+N.register("msq_cholinv_workspace_bytes", _ll, [_i])
+N.register("msq_cholinv_upper_f32", _i, [_p, _ll, _p, _ll, _i, _p, _ll, _p, _p])
+N.register("msq_cholinv_ut_planes", _i, [_p, _i, C.POINTER(_p), C.POINTER(_ll), C.POINTER(_i)])
+
+
+class Planes(object):
+    """three bf16 planes whose sum is an fp32 matrix exactly (operand format of the split-plane tensor-core GEMM):
+    plane p of element (r, c) at data[(p * plane_rows + r) * ld + c]"""
+
+    def __init__(self, data, ld, plane_rows, rows, cols, keepalive=None, ptr=None):
+        self.data, self.ld, self.plane_rows, self.rows, self.cols = data, ld, plane_rows, rows, cols
+        self.keepalive = keepalive
+        self._ptr = ptr
+
+    @property
+    def ptr(self):
+        return C.c_void_p(self._ptr if self._ptr is not None else self.data.data_ptr())
+
+
+def split3_planes(x):
+    """fp32 [rows, cols] CUDA matrix -> Planes (msq_split3_planes_f32)"""
+    N.require_cuda(x, "x")
+    assert x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1
+    rows, cols = x.shape
+    ld = (cols + 63) // 64 * 64
+    pr = (rows + 127) // 128 * 128
+    data = torch.empty(3 * pr * ld, dtype=torch.bfloat16, device=x.device)
+    rc = N.lib().msq_split3_planes_f32(N.ptr(x), x.stride(0), rows, cols, N.ptr(data), ld, pr, N.stream_ptr(x.device))
+    N.check(rc, "msq_split3_planes_f32")
+    return Planes(data, ld, pr, rows, cols)
+
+
+def gemm_split3(A, B, out=None, alpha=1.0, beta=0.0):
+    """out[M,N] (fp32) = alpha * A[M,K] @ B[N,K].T + beta * out with fp32-level accuracy on tcgen05.
+    A, B: fp32 CUDA matrices or Planes (msq_gemm_split3_f32)."""
+    pa = A if isinstance(A, Planes) else split3_planes(A)
+    pb = B if isinstance(B, Planes) else split3_planes(B)
+    assert pa.cols == pb.cols
+    M, Nn, K = pa.rows, pb.rows, pa.cols
+    dev = pa.data.device
+    if out is None:
+        out = torch.empty(M, (Nn + 3) // 4 * 4, dtype=torch.float32, device=dev)[:, :Nn]
+        beta = 0.0
+    assert out.dtype == torch.float32 and out.stride(1) == 1 and out.shape == (M, Nn)
+    rc = N.lib().msq_gemm_split3_f32(pa.ptr, pa.ld, pa.plane_rows, pb.ptr, pb.ld, pb.plane_rows, N.ptr(out), out.stride(0),
+                                     M, Nn, K, float(alpha), float(beta), N.stream_ptr(dev))
+    N.check(rc, "msq_gemm_split3_f32")
+    return out
+
+
+class CholInv(object):
+    """result of cholinv_upper: U (fp32 [n, n], upper, U^T U = H^-1), the bf16 planes of U^T that the routine leaves
+    in its workspace (operand of the tensor-core trailing update) and the device info word"""
+
+    def __init__(self, U, ut, info, ws):
+        self.U, self.ut, self.info, self.ws = U, ut, info, ws
+
+
+def cholinv_upper(H, check=True):
+    """llm/gptq.py:101-103 (cholesky -> cholesky_inverse -> cholesky(upper)) as one native routine
+    (msq_cholinv_upper_f32).  H: fp32 [n, n] SPD CUDA matrix, DESTROYED.  check=True reads the info word back
+    (one host sync) and raises torch.linalg.LinAlgError like torch.linalg.cholesky does."""
+    N.require_cuda(H, "H")
+    assert H.dim() == 2 and H.shape[0] == H.shape[1] and H.dtype == torch.float32
+    n = H.shape[0]
+    if H.stride(1) != 1 or H.stride(0) % 4 or H.data_ptr() % 16:
+        Hp = torch.zeros(n, (n + 3) // 4 * 4, dtype=torch.float32, device=H.device)
+        Hp[:, :n] = H
+        H = Hp[:, :n]
+    dev = H.device
+    U = torch.empty(n, (n + 3) // 4 * 4, dtype=torch.float32, device=dev)[:, :n]
+    nbytes = int(N.lib().msq_cholinv_workspace_bytes(n))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    rc = N.lib().msq_cholinv_upper_f32(N.ptr(H), H.stride(0), N.ptr(U), U.stride(0), n, N.ptr(ws), nbytes, N.ptr(info),
+                                       N.stream_ptr(dev))
+    N.check(rc, "msq_cholinv_upper_f32")
+    pp, ld, pr = _p(), _ll(), _i()
+    N.check(N.lib().msq_cholinv_ut_planes(N.ptr(ws), n, C.byref(pp), C.byref(ld), C.byref(pr)), "msq_cholinv_ut_planes")
+    ut = Planes(ws, ld.value, pr.value, n, n, keepalive=ws, ptr=pp.value)
+    if check:
+        bad = int(info.item())
+        if bad:
+            raise torch.linalg.LinAlgError("cholinv_upper: the leading minor ending at %d is not positive-definite" % bad)
+    return CholInv(U, ut, info, ws)
+
+
 N.register("msq_gemm_packed_w_bf16", _i, [_p, _ll, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p])
 
 
@@ -114,46 +203,20 @@ def packed_linear(x, pw, bias=None):
     return out.reshape(*lead, Nn)
 
 
-def dense_linear(x, w, x_terms=None, w_terms=None, bias=None):
+def dense_linear(x, w, bias=None):
     """y[..., N] (fp32) = x[..., K] @ w[N, K].T on tcgen05 for operands that have no packed form (the reference's
-    `f_linear(qis_input, qis_weight)`, number_system/mx/linear.py:91, when the weight is not packable).
-    Each operand is split into bf16 terms whose sum is the operand exactly (1 term for MX-quantized values -- every
-    element format has at most 8 significand bits --, 3 for arbitrary fp32); products of terms are exact in the fp32
-    accumulator, term pairs below 2^-24 of the leading product are dropped."""
+    `f_linear(qis_input, qis_weight)`, number_system/mx/linear.py:91, when the weight is not packable): both operands
+    are split into three bf16 planes whose sum is the operand exactly and contracted by the split-plane GEMM
+    (fp32-level accuracy; csrc/msq_gemm_split3.cu)."""
     N.require_cuda(x, "x")
     N.require_cuda(w, "w")
     K = x.shape[-1]
     assert w.dim() == 2 and w.shape[1] == K
     lead = x.shape[:-1]
-    x2 = x.reshape(-1, K)
-    M, Nn = x2.shape[0], w.shape[0]
-    Kp = (K + 7) // 8 * 8                          # TMA row pitch: multiples of 16 bytes
-
-    def terms(t, n):
-        t = t.float()
-        if Kp != K:
-            t = torch.nn.functional.pad(t, (0, Kp - K))
-        if n is None:
-            return _bf16_terms(t)
-        out = []
-        for _ in range(n):
-            b = t.to(torch.bfloat16)
-            out.append(b)
-            t = t - b.float()
-        return out
-    xt, wt = terms(x2, x_terms), terms(w, w_terms)
-    out = torch.empty(M, (Nn + 3) // 4 * 4, dtype=torch.float32, device=x.device)
-    first = True
-    for i, a in enumerate(xt):
-        for j, b in enumerate(wt):
-            if i + j > 2:
-                continue
-            gemm_nt(a.contiguous(), b.contiguous(), out=out, alpha=1.0, beta=0.0 if first else 1.0)
-            first = False
-    out = out[:, :Nn]
+    out = gemm_split3(x.reshape(-1, K).float().contiguous(), w.float().contiguous())
     if bias is not None:
         out = out + bias.float()
-    return out.reshape(*lead, Nn)
+    return out.reshape(*lead, w.shape[0])
 
 
 N.register("msq_gemm_mxfp8_blockscaled", _i, [_p, _ll, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _p])

@@ -107,3 +107,61 @@ def all_gather_rows(Q_local, row_ranges, rows, group=None):
     for (lo, hi), p in zip(row_ranges, parts):
         out[lo:hi] = p[: hi - lo]
     return out
+
+
+def fasterquant_row_sharded(gq, percdamp=.01, group=None, solve_fn=None):
+    """GPTQ.fasterquant (llm/gptq.py:60-193, blocksize 128, no act-order / groups) with the ROWS of one linear sharded over
+    the ranks.  Every rank holds the same weight and the same (allreduced) Hessian, factors it
+    (identical inputs => identical Hinv on every rank; the factorization is small next to the solve of a 70B-sized
+    linear), runs the fused column loop on ITS row range -- boundaries are multiples of block_size^2, so MX blocks and
+    the `outlier_pos[::block_size]` count stay rank-local -- and the quantized rows are all-gathered.
+    The only coupling between rows is the top-k prune (llm/gptq.py:146-153): it is a no-op when every column holds at
+    least k exact zeros, which needs the per-column counts of ALL rows: one int32 sum-allreduce of [2 * cols]
+    counters.  If the check fails (or the quantizer has no fused path) every rank runs the unsharded solver instead.
+    solve_fn(W_rows, fac) -> (Q_rows, loss[1], counters[2*cols+3]) replaces the CUDA solve in the CPU (gloo) tests.
+    Returns the path taken: "row-sharded" or "replicated"."""
+    import torch.nn as nn
+    world = dist.get_world_size(group) if is_dist() else 1
+    rank = dist.get_rank(group) if is_dist() else 0
+    q = gq.quantizer
+    bs = int(getattr(q, "block_size", 16) or 16)
+    fused = solve_fn is not None or gq._fused_ok()
+    if world == 1 or not fused:
+        gq.fasterquant(percdamp=percdamp)
+        return "replicated"
+    W = gq.layer.weight.data.clone()
+    if isinstance(gq.layer, nn.Conv2d):
+        W = W.flatten(1)
+    W = W.float().contiguous()
+    fac = gq._factorize(percdamp, False)
+    W.masked_fill_(fac["dead"].unsqueeze(0), 0)
+    ranges = row_shards(gq.rows, bs, world)
+    lo, hi = ranges[rank]
+    cols = gq.columns
+    if hi > lo:
+        Wl = W[lo:hi].contiguous()
+        Ql, loss, counters = solve_fn(Wl, fac) if solve_fn is not None else gq._solve_fused_raw(Wl, fac["Hinv"], fac["ut"])
+    else:
+        Ql = W[0:0]
+        loss = torch.zeros(1, dtype=torch.float64, device=W.device)
+        counters = torch.zeros(2 * cols + 3, dtype=torch.int32, device=W.device)
+    if fac.get("info") is not None:
+        counters[2 * cols + 2:] = fac["info"]
+    dist.all_reduce(counters, group=group)            # zeros / k per column over all rows; status / info: any rank
+    dist.all_reduce(loss, group=group)
+    zeros, kcnt = counters[:cols], counters[cols:2 * cols]
+    flags = counters[2 * cols:].tolist()
+    if flags[2]:
+        raise torch.linalg.LinAlgError("GPTQ: the damped Hessian is not positive-definite")
+    from . import _ops
+    _ops.raise_on_status(1 if (flags[0] & 1) else 0)
+    violated = bool((zeros < kcnt.to(torch.int16).to(torch.int32)).any()) and getattr(gq, "prune", True)
+    if violated:
+        gq._share.factor[(float(percdamp), False, gq.hinv_method)] = fac       # reuse the factorization
+        gq.fasterquant(percdamp=percdamp)
+        return "replicated"
+    Q = all_gather_rows(Ql, ranges, gq.rows, group=group)
+    gq.last_error = float(loss.item())
+    gq.last_path = "row-sharded"
+    gq.layer.weight.data = Q.reshape(gq.layer.weight.shape).to(gq.layer.weight.data.dtype)
+    return "row-sharded"

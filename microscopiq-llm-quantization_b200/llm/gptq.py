@@ -36,6 +36,22 @@ N.register("msq_gptq_block", _i, [_p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _p, _p,
 N.register("msq_gptq_trailing_update", _i, [_p, _ll, _p, _p, _ll, _i, _i, _i, _i, _i, _p])
 N.register("msq_gptq_check_prune", _i, [_p, _p, _i, _p, _p])
 N.register("msq_rank1_sub_f32", _i, [_p, _ll, _p, _p, _i, _i, _p])
+N.register("msq_gptq_solve_workspace_bytes", _ll, [_i])
+N.register("msq_gptq_solve_f32", _i, [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _p, _ll, _p, _p, _p, _p, _p,
+                                      _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _f, _f, _i, _i, _p])
+
+
+class _Shared(object):
+    """Hessian state that several GPTQ objects may share: linears fed by the SAME activations (q/k/v, gate/up) have
+    identical Hessians, so one accumulation and one factorization serve all of them (identical inputs => identical
+    bits; llm/llama.py:139-159 builds and factors each of them separately)."""
+
+    def __init__(self, columns, dev):
+        self.H = torch.zeros((columns, columns), device=dev)
+        self.nsamples = 0
+        self.pending, self.pending_n = [], 0
+        self.users = 1
+        self.factor = {}            # (percdamp, actorder, method) -> dict(Hinv, ut, dead, perm, invperm)
 
 
 class GPTQ:
@@ -50,13 +66,20 @@ class GPTQ:
     prune_topk_device = "cuda"
     #: print 'time' / 'error' like the reference (gptq.py:174-175)
     verbose = True
-    #: how the upper Cholesky factor of H^-1 is obtained.  "reference": cholesky -> cholesky_inverse ->
-    #: cholesky(upper), exactly gptq.py:101-103.  "flip": the same matrix from ONE Cholesky of the
-    #: row/column-reversed H plus a triangular inverse (H = R R^T with R upper => H^-1 = (R^-1)^T R^-1),
-    #: about half the time; agrees with the reference route to ~1e-6..1e-5 relative.
-    hinv_method = "reference"
+    #: how the upper Cholesky factor of H^-1 (gptq.py:101-103) is obtained.
+    #:   "native"    (default) msq_cholinv_upper_f32: one reverse Cholesky H = R R^T + one triangular inverse, blocked,
+    #:               every panel product on tcgen05 (fp32-accurate split-plane GEMM); no library call.  Same matrix as
+    #:               the reference's three calls up to fp32 rounding (tests/test_gpu_cholinv.py states the bound).
+    #:   "reference" torch.linalg.cholesky -> torch.cholesky_inverse -> torch.linalg.cholesky(upper) (cuSOLVER)
+    #:   "flip"      torch: one Cholesky of the index-reversed matrix + one triangular solve (the algebra of "native")
+    hinv_method = "native"
+    #: trailing update W[:, i2:] -= Err1 Hinv[i1:i2, i2:] (gptq.py:165) on tcgen05 (True) or in fp32 SIMT (False)
+    trailing_tc = True
 
-    def __init__(self, layer):
+    def __init__(self, layer, prune=True):
+        #: prune=False is the reference's vlm/gptq.py:130-144 variant: the column quantizer is quantize_mx_outlier_v1
+        #: and no inlier is zeroed afterwards (llm/gptq.py:146-153 is skipped), so rows never interact
+        self.prune = prune
         self.layer = layer
         self.dev = self.layer.weight.device
         W = layer.weight.data.clone()
@@ -66,10 +89,7 @@ class GPTQ:
             W = W.t()
         self.rows = W.shape[0]
         self.columns = W.shape[1]
-        self._H = torch.zeros((self.columns, self.columns), device=self.dev)
-        self.nsamples = 0
-        self._pending = []
-        self._pending_n = 0
+        self._share = _Shared(self.columns, self.dev)
         self.last_path = None
         self.last_error = None
 
@@ -77,19 +97,40 @@ class GPTQ:
     @property
     def H(self):
         self._flush()
-        return self._H
+        return self._share.H
 
     @H.setter
     def H(self, value):
-        self._pending, self._pending_n = [], 0
-        self._H = value
+        self._share.pending, self._share.pending_n = [], 0
+        self._share.H = value
 
     @H.deleter
     def H(self):
-        self._pending, self._pending_n = [], 0
-        self._H = None
+        self._share.pending, self._share.pending_n = [], 0
+        self._share.H = None
+
+    @property
+    def nsamples(self):
+        return self._share.nsamples
+
+    @nsamples.setter
+    def nsamples(self, value):
+        self._share.nsamples = value
+
+    def share_hessian_with(self, owner):
+        """use `owner`'s Hessian (and its factorization) instead of an own one: for linears that receive the same
+        input tensor.  After this call only the owner's add_batch accumulates; this object's add_batch is a no-op."""
+        if owner is self or self._share is owner._share:
+            return
+        assert owner.columns == self.columns, "shared Hessians need the same number of input features"
+        self._share.users -= 1
+        self._share = owner._share
+        self._share.users += 1
+        self._hessian_owner = owner
 
     def add_batch(self, inp, out):
+        if getattr(self, "_hessian_owner", None) is not None:
+            return                                    # the owner accumulates for the whole group
         if DEBUG:
             self.inp1 = inp
             self.out1 = out
@@ -109,22 +150,24 @@ class GPTQ:
         N.require_cuda(x, "inp")
         if x.dtype not in (torch.float16, torch.bfloat16, torch.float32):
             x = x.float()
-        self._pending.append((x.detach().contiguous(), b))
-        self._pending_n += 1
-        if self._pending_n >= self.hessian_batch:
+        sh = self._share
+        sh.pending.append((x.detach().contiguous(), b))
+        sh.pending_n += 1
+        if sh.pending_n >= self.hessian_batch:
             self._flush()
 
     def _flush(self):
         """H <- H * n/(n+b) + (2/(n+b)) X^T X   (gptq.py:53-58) for the buffered calls"""
-        if not self._pending:
+        sh = self._share
+        if not sh.pending:
             return
-        xs = [x for x, _ in self._pending]
-        b = sum(bb for _, bb in self._pending)
+        xs = [x for x, _ in sh.pending]
+        b = sum(bb for _, bb in sh.pending)
         X = xs[0] if len(xs) == 1 else torch.cat(xs, 0)
-        n_new = self.nsamples + b
-        _tc.hessian_accumulate(self._H, X, alpha=2.0 / n_new, beta=self.nsamples / n_new)
-        self.nsamples = n_new
-        self._pending, self._pending_n = [], 0
+        n_new = sh.nsamples + b
+        _tc.hessian_accumulate(sh.H, X, alpha=2.0 / n_new, beta=sh.nsamples / n_new)
+        sh.nsamples = n_new
+        sh.pending, sh.pending_n = [], 0
 
     # -- solver ----------------------------------------------------------------------------
     def _fused_ok(self):
@@ -152,11 +195,9 @@ class GPTQ:
         if not self.quantizer.ready():
             self.quantizer.find_params(W, weight=True)
 
-        H = self.H
-        del self.H
-        dead = torch.diag(H) == 0
-        H[dead, dead] = 1
-        W[:, dead] = 0
+        fac = self._factorize(percdamp, actorder)
+        dead, perm, invperm, Hinv = fac["dead"], fac["perm"], fac["invperm"], fac["Hinv"]
+        W.masked_fill_(dead.unsqueeze(0), 0)               # W[:, dead] = 0
 
         groups = None
         if static_groups:
@@ -167,30 +208,17 @@ class GPTQ:
                 quantizer.find_params(W[:, i:(i + groupsize)], weight=True)
                 groups.append(quantizer)
 
-        perm = invperm = None
         if actorder:
-            perm = torch.argsort(torch.diag(H), descending=True)
             W = W[:, perm].contiguous()
-            H = H[perm][:, perm]
-            invperm = torch.argsort(perm)
-
-        damp = percdamp * torch.mean(torch.diag(H))
-        diag = torch.arange(self.columns, device=self.dev)
-        H[diag, diag] += damp
-        if self.hinv_method == "flip":
-            R = torch.linalg.cholesky(H.flip(0, 1)).flip(0, 1)          # upper, H = R R^T
-            H = torch.linalg.solve_triangular(R, torch.eye(self.columns, device=self.dev, dtype=R.dtype), upper=True)
-        else:
-            H = torch.linalg.cholesky(H)
-            H = torch.cholesky_inverse(H)
-            H = torch.linalg.cholesky(H, upper=True)
-        Hinv = H.contiguous()
 
         Q = None
         if self._fused_ok() and blocksize == 128:
-            Q, loss = self._solve_fused(W.clone(), Hinv)
+            Q, loss = self._solve_fused(W.clone(), Hinv, fac["ut"], fac["info"])
             self.last_path = "fused"
         if Q is None:
+            if fac["info"] is not None and int(fac["info"].item()):
+                raise torch.linalg.LinAlgError("GPTQ: the damped Hessian is not positive-definite (leading minor %d)"
+                                               % int(fac["info"].item()))
             Q, loss = self._solve_generic(W, Hinv, blocksize, groupsize, actorder, static_groups, groups, perm)
             self.last_path = "generic"
 
@@ -208,36 +236,88 @@ class GPTQ:
         if DEBUG:
             print(torch.sum((self.layer(self.inp1) - self.out1) ** 2))
 
-    def _solve_fused(self, W, Hinv):
-        """gptq.py:106-165 with the per-block kernel; returns (Q, loss) or (None, None) when the
-        prune would have changed values (then the generic path must run)."""
+    def _factorize(self, percdamp, actorder):
+        """gptq.py:78-103: dead columns, act-order permutation, damping and the Cholesky trio.  The result is cached on
+        the shared Hessian state, so the members of a share group factor once."""
+        sh = self._share
+        key = (float(percdamp), bool(actorder), self.hinv_method)
+        fac = sh.factor.get(key)
+        if fac is not None:
+            return fac
+        H = self.H
+        if H is None:
+            raise RuntimeError("GPTQ.fasterquant: the Hessian has already been consumed with different settings")
+        del self.H
+        dead = torch.diag(H) == 0
+        H.diagonal().masked_fill_(dead, 1)                 # H[dead, dead] = 1 without the host sync of mask indexing
+        perm = invperm = None
+        if actorder:
+            perm = torch.argsort(torch.diag(H), descending=True)
+            H = H[perm][:, perm]
+            invperm = torch.argsort(perm)
+        damp = percdamp * torch.mean(torch.diag(H))
+        diag = torch.arange(self.columns, device=self.dev)
+        H[diag, diag] += damp
+        ut = None
+        if self.hinv_method == "native":
+            ci = _tc.cholinv_upper(H, check=False)
+            Hinv, ut = ci.U, ci.ut
+            fac = dict(info=ci.info)
+        else:
+            if self.hinv_method == "flip":
+                R = torch.linalg.cholesky(H.flip(0, 1)).flip(0, 1)          # upper, H = R R^T
+                H = torch.linalg.solve_triangular(R, torch.eye(self.columns, device=self.dev, dtype=R.dtype), upper=True)
+            else:
+                H = torch.linalg.cholesky(H)
+                H = torch.cholesky_inverse(H)
+                H = torch.linalg.cholesky(H, upper=True)
+            Hinv = H.contiguous()
+            fac = dict(info=None)
+        fac.update(dead=dead, perm=perm, invperm=invperm, Hinv=Hinv, ut=ut)
+        sh.factor[key] = fac
+        return fac
+
+    def _solve_fused_raw(self, W, Hinv, ut=None):
+        """queue gptq.py:106-165 for the rows in W (msq_gptq_solve_f32); returns device tensors, no host sync:
+        (Q, loss[1] fp64, counters int32 [2*cols + 3] = zeros[cols] | kcnt[cols] | status | violation | info)"""
         q = self.quantizer
         dev = W.device
         rows, cols = W.shape
         fi, fo = _ops.fmt4(q.inlier_elem_format), _ops.fmt4(q.outlier_elem_format)
         Q = torch.empty_like(W)
-        Err = torch.empty(rows, 128, dtype=torch.float32, device=dev)
-        loss = torch.zeros(1, dtype=torch.float64, device=dev)
-        counters = torch.zeros(2 * cols + 2, dtype=torch.int32, device=dev)
-        zeros, kcnt, status, viol = counters[:cols], counters[cols:2 * cols], counters[2 * cols:2 * cols + 1], counters[2 * cols + 1:]
         L, s = N.lib(), N.stream_ptr(dev)
-        rm = _ops._rmode(q.round)
-        for i1 in range(0, cols, 128):
-            i2 = min(i1 + 128, cols)
-            rc = L.msq_gptq_block(N.ptr(W), W.stride(0), N.ptr(Q), Q.stride(0), N.ptr(Hinv), Hinv.stride(0), rows, i1,
-                                  i2 - i1, N.ptr(Err), N.ptr(loss), N.ptr(zeros), N.ptr(kcnt), N.ptr(status),
-                                  int(q.block_size), int(q.inlier_scale_bits), int(q.outlier_scale_bits),
-                                  fi[0], fi[1], fi[2], fi[3], fo[0], fo[1], fo[2], fo[3], float(q.std_dev),
-                                  int(bool(q.flush_fp32_subnorms)), rm, s)
-            N.check(rc, "msq_gptq_block")
-            rc = L.msq_gptq_trailing_update(N.ptr(W), W.stride(0), N.ptr(Err), N.ptr(Hinv), Hinv.stride(0), rows, i1,
-                                            i2 - i1, i2, cols, s)
-            N.check(rc, "msq_gptq_trailing_update")
-        rc = L.msq_gptq_check_prune(N.ptr(zeros), N.ptr(kcnt), cols, N.ptr(viol), s)
-        N.check(rc, "msq_gptq_check_prune")
+        nws = int(L.msq_gptq_solve_workspace_bytes(rows))
+        ws = _tc._workspace(nws, dev)
+        loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        counters = torch.zeros(2 * cols + 3, dtype=torch.int32, device=dev)
+        zeros, kcnt, status, viol = counters[:cols], counters[cols:2 * cols], counters[2 * cols:2 * cols + 1], counters[2 * cols + 1:2 * cols + 2]
+        if ut is None and self.trailing_tc and cols % 8 == 0:
+            ut = _tc.split3_planes(Hinv.t().contiguous())      # Hinv from a library route: build the operand planes
+        if not self.trailing_tc or cols % 8:
+            ut = None
+        rc = L.msq_gptq_solve_f32(N.ptr(W), W.stride(0), N.ptr(Q), Q.stride(0), N.ptr(Hinv), Hinv.stride(0),
+                                  ut.ptr if ut is not None else None, ut.ld if ut is not None else 0,
+                                  ut.plane_rows if ut is not None else 0, rows, cols, N.ptr(ws), nws, N.ptr(loss),
+                                  N.ptr(zeros), N.ptr(kcnt), N.ptr(status), N.ptr(viol), int(q.block_size),
+                                  int(q.inlier_scale_bits), int(q.outlier_scale_bits), fi[0], fi[1], fi[2], fi[3],
+                                  fo[0], fo[1], fo[2], fo[3], float(q.std_dev), int(bool(q.flush_fp32_subnorms)),
+                                  _ops._rmode(q.round), s)
+        N.check(rc, "msq_gptq_solve_f32")
+        return Q, loss, counters
+
+    def _solve_fused(self, W, Hinv, ut=None, info=None):
+        """gptq.py:106-165 as ONE queued call (msq_gptq_solve_f32): per 128-column block the two-warp column kernel and
+        the trailing update; returns (Q, loss) or (None, None) when the prune would have changed values (then the
+        generic path must run)."""
+        cols = W.shape[1]
+        Q, loss, counters = self._solve_fused_raw(W, Hinv, ut)
+        if info is not None:                          # pivot check of the native factorization rides on the same read
+            counters[2 * cols + 2:] = info
         flags = counters[2 * cols:].tolist()          # one host sync per linear
+        if flags[2]:
+            raise torch.linalg.LinAlgError("GPTQ: the damped Hessian is not positive-definite (leading minor %d)" % flags[2])
         _ops.raise_on_status(flags[0])
-        if flags[1] != 0:
+        if flags[1] != 0 and self.prune:
             return None, None
         return Q, float(loss.item())
 
@@ -276,7 +356,7 @@ class GPTQ:
                         q, num_outliers_per_block = res
                         q = q.flatten()
                         importance = (q ** 2) / d ** 2
-                        num_outliers = int(num_outliers_per_block.sum().to(torch.int16))
+                        num_outliers = int(num_outliers_per_block.sum().to(torch.int16)) if self.prune else 0
                         if num_outliers > 0:
                             # gptq.py:150: torch.topk leaves the order of tied entries unspecified, and on the coarse
                             # MX grid most of a column's q^2/d^2 values are tied.  The default is the CUDA tie order
@@ -321,7 +401,15 @@ class GPTQ:
         if DEBUG:
             self.inp1 = None
             self.out1 = None
-        self.H = None
+        sh = self._share
+        sh.users -= 1
+        if sh.users <= 0:
+            sh.H = None
+            sh.pending, sh.pending_n = [], 0
+            sh.factor = {}
+        self._share = _Shared.__new__(_Shared)
+        self._share.H, self._share.nsamples, self._share.pending, self._share.pending_n = None, 0, [], 0
+        self._share.users, self._share.factor = 1, {}
         self.Losses = None
         self.Trace = None
         if self.release_cache_on_free:

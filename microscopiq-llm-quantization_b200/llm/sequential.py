@@ -152,7 +152,8 @@ def _run_layer(layer, x, args, kwargs):
 
 @torch.no_grad()
 def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=.01, groupsize=-1, act_order=False,
-                        static_groups=False, true_sequential=False, hessian_batch=8, verbose=False, stats=None, overlap_moves=False):
+                        static_groups=False, true_sequential=False, hessian_batch=8, verbose=False, stats=None, overlap_moves=False,
+                        share_hessians=True, forward_batch=8, release_cache=False):
     """llama_sequential / opt_sequential (llm/llama.py:62-173, llm/opt.py:26-128).
     nearest=True is the RTN branch (llm/llama.py:226-253): every linear is replaced by
     quantize_mx_outlier_v1(W) without calibration.  Returns {layer name: quantizer}.
@@ -161,7 +162,12 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
     the path shards where it shards naturally: each rank runs ITS share of the calibration samples through the
     layer, the per-rank Hessians are combined by one sum-allreduce per linear (dist.combine_hessians), the
     independent solves of a layer are spread over the ranks (dist.assign_linears) and the quantized weights are
-    broadcast from their owners; RTN spreads the linears of a layer the same way."""
+    broadcast from their owners; RTN spreads the linears of a layer the same way.
+
+    forward_batch: calibration samples pushed through the layer per call (the reference uses 1, llm/llama.py:147;
+    the Hessian is a sum over tokens, so batching only changes how many kernels are launched).  share_hessians: one
+    Hessian + one factorization for linears that receive the same tensor (q/k/v, gate/up).  release_cache: call
+    torch.cuda.empty_cache() after every linear like gptq.py:191 (off: the solver workspaces are reused)."""
     qcfg = dict(REFERENCE_QCFG if qcfg is None else qcfg)
     layers, _, _, _ = decoder_parts(model)
     stats = stats if stats is not None else {}
@@ -217,20 +223,41 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
             gptq = {}
             for name in subset:
                 gptq[name] = GPTQ(subset[name])
-                gptq[name].hessian_batch = hessian_batch
+                gptq[name].hessian_batch = max(1, hessian_batch // forward_batch)
                 gptq[name].verbose = verbose
+                gptq[name].release_cache_on_free = release_cache
                 gptq[name].quantizer = MXQuantizer()
                 gptq[name].quantizer.configure(**qcfg)
 
+            # linears fed by the SAME tensor (q/k/v, gate/up) have identical Hessians: the first one seen in a forward
+            # accumulates, the others share its state (GPTQ.share_hessian_with).  `seen` holds a reference to the
+            # input for the duration of one forward, so equal (pointer, shape, version) means equal contents.
+            seen = {}
+
             def add_batch(name):
                 def tmp(_, inp, out):
-                    gptq[name].add_batch(inp[0].data, out.data)
+                    x = inp[0].data
+                    if share_hessians:
+                        key = (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x.dtype, x._version)
+                        hit = seen.get(key)
+                        if hit is None:
+                            seen[key] = (name, x)
+                        elif hit[0] != name:
+                            owner = shared_with.setdefault(name, hit[0])
+                            assert owner == hit[0], "input sharing changed between samples"
+                            gptq[name].share_hessian_with(gptq[owner])
+                            return
+                    assert name not in shared_with, "input sharing changed between samples"
+                    gptq[name].add_batch(x, out.data)
                 return tmp
+            shared_with = {}
             handles = [subset[name].register_forward_hook(add_batch(name)) for name in subset]
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            for j in range(nsamples):
-                outs[j] = _run_layer(layer, inps[j].unsqueeze(0), args, kwargs)
+            for j in range(0, nsamples, forward_batch):
+                seen.clear()
+                outs[j:j + forward_batch] = _run_layer(layer, inps[j:j + forward_batch], args, kwargs)
+            seen.clear()
             for name in subset:
                 _ = gptq[name].H                     # flush buffered activations
             torch.cuda.synchronize()
@@ -240,8 +267,10 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
             owners = D.assign_linears({n: tuple(m.weight.shape) for n, m in subset.items()}, world)
             if world > 1:
                 t0 = time.perf_counter()
-                for name in subset:                  # every rank needs N; only the owner needs H, but one
-                    H, N = D.combine_hessians(gptq[name].H, gptq[name].nsamples, upper_only=False)   # allreduce is cheapest
+                for name in subset:                  # one collective per DISTINCT Hessian (share groups: the owner's)
+                    if name in shared_with:
+                        continue
+                    H, N = D.combine_hessians(gptq[name].H, gptq[name].nsamples, upper_only=False)
                     gptq[name].H, gptq[name].nsamples = H, N
                 torch.cuda.synchronize()
                 stats["comm_s"] += time.perf_counter() - t0
@@ -262,8 +291,8 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
                 torch.cuda.synchronize()
                 stats["comm_s"] += time.perf_counter() - t0
         t0 = time.perf_counter()
-        for j in range(nsamples):
-            outs[j] = _run_layer(layer, inps[j].unsqueeze(0), args, kwargs)
+        for j in range(0, nsamples, forward_batch):
+            outs[j:j + forward_batch] = _run_layer(layer, inps[j:j + forward_batch], args, kwargs)
         torch.cuda.synchronize()
         stats["forward_s"] += time.perf_counter() - t0
         t0 = time.perf_counter()

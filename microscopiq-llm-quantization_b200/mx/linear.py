@@ -75,8 +75,7 @@ def linear_forward(input, weight, bias, mx_specs, packed_weight=None):
         qis_weight = quantize_mx_outlier_op(bf_weight, mx_specs, inlier_elem_format=mx_specs["w_elem_format"],
                                             outlier_elem_format=mx_specs["w_elem_format"], axes=[1],
                                             round=mx_specs["round_mx_output"])
-        output = _tc.dense_linear(qis_input, qis_weight, x_terms=None if mx_specs["a_elem_format"] is None else 1,
-                                  w_terms=None if mx_specs["w_elem_format"] is None else 1).to(input.dtype)
+        output = _tc.dense_linear(qis_input, qis_weight).to(input.dtype)
     output = quantize_elemwise_op(output, mx_specs=mx_specs, round=mx_specs["round_output"])
     if bf_bias is not None:
         output = quantize_elemwise_op(output + bf_bias, mx_specs=mx_specs, round=mx_specs["round_output"])
@@ -102,17 +101,44 @@ class MXLinear(torch.nn.Linear):
         self._packed_version = None
         super().__init__(in_features, out_features, bias)
 
+    @classmethod
+    def from_packed(cls, pw, bias=None, mx_specs=None, name=None, keep_dense=False):
+        """inference module over a packed weight (PackedMX [out_features, in_features], e.g. loaded from an MSQPACK
+        checkpoint or emitted by GPTQ / pack_mx_outlier): the stored planes ARE the weight -- nothing is re-quantized,
+        the forward multiplies the (MX-quantized) activations with the packed planes on tcgen05.
+        keep_dense=True also materialises the dequantized fp32 weight in `.weight` (state_dict compatibility);
+        otherwise `.weight` is an empty placeholder."""
+        out_f, in_f = pw.shape
+        specs = dict(mx_specs) if mx_specs is not None else {}
+        specs.setdefault("block_size", 32)
+        self = cls.__new__(cls)
+        torch.nn.Module.__init__(self)
+        self.in_features, self.out_features = in_f, out_f
+        dev = pw.codes.device
+        w = pw.dequantize() if keep_dense else torch.empty(0, device=dev)
+        self.weight = torch.nn.Parameter(w, requires_grad=False)
+        self.bias = None if bias is None else torch.nn.Parameter(bias.detach().to(dev).float(), requires_grad=False)
+        self.mx_none = False
+        self.name = name
+        mx_assert_test(specs)
+        self.mx_specs = apply_mx_specs(specs)
+        self._packed, self._packed_version, self._frozen = pw, None, True
+        return self
+
     def apply_mx_specs(self, mx_specs):
         mx_assert_test(mx_specs)
         self.mx_none = mx_specs is None
         self.mx_specs = apply_mx_specs(mx_specs)
-        self._packed = None
+        if not getattr(self, "_frozen", False):
+            self._packed = None
 
     def append_name(self, postfix):
         self.name += postfix
 
     def packed_weight(self):
         """quantize + pack the weight once; reused until the parameter is modified"""
+        if getattr(self, "_frozen", False):
+            return self._packed
         ver = (self.weight._version, self.weight.data_ptr())
         if self._packed is None or self._packed_version != ver:
             with torch.no_grad():

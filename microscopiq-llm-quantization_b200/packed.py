@@ -134,3 +134,118 @@ def pack_mx(A, scale_bits, elem_format, axes=None, block_size=32, round="nearest
     return PackedMX(shape=tuple(x.shape), axis=axis, block_size=bs, in_fmt=elem_format, out_fmt=elem_format,
                     in_scale_bits=scale_bits, out_scale_bits=scale_bits, code_width=wi, hi_w=0, hi_seg_stride=0,
                     nseg=nseg, plain=True, path=path.value, status=st, **pl)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# On-disk format (replaces the reference's dead opt_pack3 / load_quant3, llm/opt.py:254-294)
+#
+#   bytes 0..7     magic  b"MSQPACK1"
+#   bytes 8..15    little-endian uint64: length H of the JSON header
+#   bytes 16..16+H JSON (utf-8): {"version": 1, "metadata": {...}, "tensors": {name: entry}}
+#   then the raw planes, each starting on a 64-byte boundary (offsets in the header are relative to the first one)
+#
+# entry of a packed tensor: {"kind": "packed", "meta": {shape, axis, block_size, in_fmt, out_fmt, in_scale_bits,
+#   out_scale_bits, code_width, hi_w, hi_seg_stride, nseg, plain}, "planes": {plane: {dtype, shape, offset, nbytes}}}
+# entry of a dense tensor (biases, norms, embeddings ...): {"kind": "dense", "planes": {"data": {...}}}
+# Only the used prefix layout is NOT compacted: the hi plane is stored with its segment stride, as in HBM, so a
+# loaded tensor is usable by the kernels without any re-layout.
+# ---------------------------------------------------------------------------------------------------------------
+import json as _json
+import struct as _struct
+
+MAGIC = b"MSQPACK1"
+FORMAT_VERSION = 1
+_PLANES = ("codes", "bitmap", "e_in", "e_out", "hi", "seg_cnt")
+_META = ("shape", "axis", "block_size", "in_fmt", "out_fmt", "in_scale_bits", "out_scale_bits", "code_width", "hi_w",
+         "hi_seg_stride", "nseg", "plain")
+_DTYPES = {"uint8": torch.uint8, "int8": torch.int8, "int32": torch.int32, "float32": torch.float32,
+           "float16": torch.float16, "bfloat16": torch.bfloat16, "int64": torch.int64}
+
+
+def _fmt_name(f):
+    return f if isinstance(f, str) or f is None else getattr(f, "name", str(f))
+
+
+def _plane_entry(t, blobs, cursor):
+    t = t.detach().contiguous().cpu()
+    name = str(t.dtype).replace("torch.", "")
+    if name not in _DTYPES:
+        raise TypeError("cannot store dtype %s" % t.dtype)
+    raw = t.view(torch.uint8).reshape(-1) if t.numel() else torch.empty(0, dtype=torch.uint8)
+    if t.dtype in (torch.bfloat16,):
+        raw = t.view(torch.int16).reshape(-1).view(torch.uint8)
+    off = (cursor + 63) // 64 * 64
+    blobs.append((off, raw))
+    return {"dtype": name, "shape": list(t.shape), "offset": off, "nbytes": int(raw.numel())}, off + int(raw.numel())
+
+
+def save_packed(path, tensors, metadata=None):
+    """write {name: PackedMX | torch.Tensor} to one file; returns the number of bytes written"""
+    entries, blobs, cursor = {}, [], 0
+    for name, t in tensors.items():
+        if isinstance(t, PackedMX):
+            meta = {k: getattr(t, k) for k in _META}
+            meta["shape"] = list(meta["shape"])
+            meta["in_fmt"], meta["out_fmt"] = _fmt_name(meta["in_fmt"]), _fmt_name(meta["out_fmt"])
+            planes = {}
+            for pn in _PLANES:
+                pl = getattr(t, pn, None)
+                if pl is not None:
+                    planes[pn], cursor = _plane_entry(pl, blobs, cursor)
+            entries[name] = {"kind": "packed", "meta": meta, "planes": planes}
+        else:
+            e, cursor = _plane_entry(t, blobs, cursor)
+            entries[name] = {"kind": "dense", "planes": {"data": e}}
+    header = _json.dumps({"version": FORMAT_VERSION, "metadata": metadata or {}, "tensors": entries}).encode("utf-8")
+    base = (16 + len(header) + 63) // 64 * 64
+    with open(path, "wb") as f:
+        f.write(MAGIC)
+        f.write(_struct.pack("<Q", len(header)))
+        f.write(header)
+        f.write(b"\0" * (base - 16 - len(header)))
+        pos = 0
+        for off, raw in blobs:
+            f.write(b"\0" * (off - pos))
+            f.write(raw.numpy().tobytes())
+            pos = off + raw.numel()
+    return base + cursor
+
+
+def read_packed_header(path):
+    with open(path, "rb") as f:
+        if f.read(8) != MAGIC:
+            raise ValueError("%s is not an MSQPACK1 file" % path)
+        (hlen,) = _struct.unpack("<Q", f.read(8))
+        header = _json.loads(f.read(hlen).decode("utf-8"))
+    if header.get("version") != FORMAT_VERSION:
+        raise ValueError("unsupported MSQPACK version %r" % (header.get("version"),))
+    return header, (16 + hlen + 63) // 64 * 64
+
+
+def load_packed(path, device="cuda", names=None):
+    """read a file written by save_packed: {name: PackedMX | torch.Tensor} with the planes on `device`"""
+    import numpy as np
+    header, base = read_packed_header(path)
+    mm = np.memmap(path, dtype=np.uint8, mode="r")
+
+    def plane(e):
+        raw = torch.from_numpy(np.array(mm[base + e["offset"]: base + e["offset"] + e["nbytes"]]))
+        dt = _DTYPES[e["dtype"]]
+        t = (raw.view(torch.int16).view(torch.bfloat16) if dt == torch.bfloat16 else raw.view(dt)) if raw.numel() else \
+            torch.empty(0, dtype=dt)
+        return t.reshape(e["shape"]).to(device)
+
+    out = {}
+    for name, e in header["tensors"].items():
+        if names is not None and name not in names:
+            continue
+        if e["kind"] == "dense":
+            out[name] = plane(e["planes"]["data"])
+            continue
+        kw = dict(e["meta"])
+        kw["shape"] = tuple(kw["shape"])
+        for pn in _PLANES:
+            kw[pn] = plane(e["planes"][pn]) if pn in e["planes"] else None
+        kw["path"], kw["status"] = 0, None
+        out[name] = PackedMX(**kw)
+    return out
