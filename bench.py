@@ -218,9 +218,9 @@ def extras(dev, dev_w, nel):
         t_s += t2 - t1
         flops_h += 2.0 * nsamples * seqlen * c * c
         g.free()
-    # same solves with the one-Cholesky route to the identical factor (GPTQ.hinv_method = "flip")
-    t_flip = 0.0
-    msq_b200.GPTQ.hinv_method = "flip"
+    # same solves with the reference's own route to Hinv (three cuSOLVER calls through torch.linalg) for comparison
+    t_lib = 0.0
+    msq_b200.GPTQ.hinv_method = "reference"
     for i, (name, r, c) in enumerate(LAYER_SHAPES):
         layer = torch.nn.Linear(c, r, bias=False, device=dev, dtype=torch.float16)
         layer.weight.data = dev_w[i].half()
@@ -235,13 +235,14 @@ def extras(dev, dev_w, nel):
         t1 = time.perf_counter()
         g.fasterquant()
         torch.cuda.synchronize()
-        t_flip += time.perf_counter() - t1
+        t_lib += time.perf_counter() - t1
         g.free()
-    msq_b200.GPTQ.hinv_method = "reference"
-    out["gptq_layer"] = {"hessian_s": t_h, "solve_s": t_s, "layer_s": t_h + t_s, "solve_s_flip_cholesky": t_flip,
+    msq_b200.GPTQ.hinv_method = "native"
+    out["gptq_layer"] = {"hessian_s": t_h, "solve_s": t_s, "layer_s": t_h + t_s, "solve_s_cusolver_route": t_lib,
                          "hessian_TFLOPs": flops_h / t_h / 1e12,
-                         "llama2_7b_quantize_s_est": 32 * (t_h + t_s),
-                         "note": "one decoder layer measured (7 linears, 128x2048 fp16 tokens each, layer forward excluded) x 32"}
+                         "note": "kernel-level view of one decoder layer: 7 linears solved one by one, each with its own "
+                                 "Hessian (128x2048 fp16 tokens) and its own native factorization; the driver-level number "
+                                 "(shared Hessians, forwards, moves) is extra.gptq_model"}
     # (3) packed-weight GEMM, K = N = 4096, MX-FP4 + outliers, bf16 activations
     gemm = {}
     W = dev_w[0]
@@ -262,6 +263,200 @@ def extras(dev, dev_w, nel):
     return out
 
 
+def _dist_max(dist, dev, *vals):
+    t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t]
+
+
+def build_llama(layers, dev, hidden=4096, inter=11008, heads=32, vocab=32000, seed=0):
+    """random-init LLaMA-2-7B-shaped HF model in fp16 on the host (no checkpoint available), same weights on every rank"""
+    import transformers
+    cfg = transformers.LlamaConfig(hidden_size=hidden, intermediate_size=inter, num_hidden_layers=layers, num_attention_heads=heads,
+                                   num_key_value_heads=heads, vocab_size=vocab, max_position_embeddings=4096)
+    skip = lambda *x, **k: None
+    saved = (torch.nn.init.kaiming_uniform_, torch.nn.init.uniform_, torch.nn.init.normal_)
+    torch.nn.init.kaiming_uniform_ = torch.nn.init.uniform_ = torch.nn.init.normal_ = skip
+    torch.set_default_dtype(torch.float16)
+    try:
+        model = transformers.LlamaForCausalLM(cfg)
+    finally:
+        torch.set_default_dtype(torch.float32)
+        torch.nn.init.kaiming_uniform_, torch.nn.init.uniform_, torch.nn.init.normal_ = saved
+    g = torch.Generator(device=dev).manual_seed(seed)
+    with torch.no_grad():
+        for _, p in model.named_parameters():
+            if p.dim() >= 2:
+                p.data = (torch.randn(p.shape, device=dev, generator=g) * 0.02).half().cpu()
+            else:
+                p.data = torch.ones_like(p.data)
+    model.eval()
+    return model
+
+
+def leg_gptq_model(dev, rank, world, dist, layers=4, nsamples=128, seqlen=2048, qcfg=None, tag="fp4_e2m1/fp8_e4m3 block 16"):
+    """STRONG scaling of the real calibration path (llm/llama.py:62-173 through msq_b200.llm.sequential): `layers`
+    LLaMA-2-7B decoder layers, 128 x 2048 synthetic tokens split over the ranks, per-rank tcgen05 Hessians, NCCL
+    allreduce, solves spread over the ranks, quantized weights broadcast.  Wall time, max over ranks."""
+    from msq_b200.llm import sequential as S
+    model = build_llama(layers, dev)
+    model.seqlen = seqlen
+    gc = torch.Generator().manual_seed(3)
+    calib = [torch.randint(0, 32000, (1, seqlen), generator=gc) for _ in range(nsamples)]
+    qcfg = qcfg or dict(inlier_scale_bits=8, outlier_scale_bits=8, inlier_elem_format=QCFG["in_fmt"],
+                        outlier_elem_format=QCFG["out_fmt"], axes=[0], block_size=QCFG["bs"])
+    stats = {}
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    S.sequential_quantize(model, calib, dev, qcfg=qcfg, stats=stats)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    tq = time.perf_counter() - t0
+    agree = True
+    if dist is not None:
+        w = model.model.layers[-1].mlp.down_proj.weight.data.to(dev).float()
+        chk = torch.stack([w.sum(), w.abs().sum()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        agree = bool(torch.equal(lo, hi))
+    keys = ["hessian_s", "solve_s", "forward_s", "comm_s", "move_s"]
+    mx = _dist_max(dist, dev, tq, *[stats.get(k, 0.0) for k in keys])
+    del model
+    out = {"quantizer": tag, "layers": layers, "nsamples": nsamples, "seqlen": seqlen, "quantize_s": mx[0],
+           "layer_s": mx[0] / layers, "llama2_7b_quantize_s": mx[0] / layers * 32,
+           "note": "%d decoder layers measured end to end (capture, forwards, Hessians, collectives, solves, host<->device "
+                   "layer moves), x %g = 32-layer model" % (layers, 32.0 / layers), "ranks_agree": agree}
+    for k, v in zip(keys, mx[1:]):
+        out[k] = v
+    out["allreduce_s"] = out.pop("comm_s")
+    nbytes = stats.get("comm_bytes", 0)
+    out["allreduce_GBps"] = (nbytes / out["allreduce_s"] / 1e9) if out["allreduce_s"] > 0 and world > 1 else None
+    out["linears_solved_rank0"] = stats.get("linears")
+    return out
+
+
+def leg_cfg3(dev, rank, world, dist, dev_w):
+    """BASELINE configs[2]: MX-FP6 (fp6_e3m2 in/out, scale_bits 4, block 32, the run_mx_fp6.sh element format) on the
+    LLaMA-2-7B linears + the Hessian allreduce across the ranks."""
+    import msq_b200
+    from msq_b200 import _ops, dist as D
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    outs = [torch.empty_like(w) for w in dev_w]
+
+    def step():
+        for w, o in zip(dev_w, outs):
+            _ops.mx_outlier(w, 4, 4, "fp6_e3m2", "fp6_e3m2", 2, 0, 32, want=("deq",), check=False, out=o, status=st)
+    ms = _time_ms(step, 10)
+    nel = sum(w.numel() for w in dev_w)
+    res = {"quant_GBps_per_gpu": nel * 8 / (ms * 1e-3) / 1e9, "quantizer": "fp6_e3m2/fp6_e3m2 scale_bits 4 block 32 axes=[0]"}
+    del outs
+    if dist is not None:
+        ar = {}
+        for K in (4096, 11008):
+            H = torch.randn(K, K, device=dev)
+            for _ in range(2):
+                D.combine_hessians(H, 16, upper_only=False)
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                D.combine_hessians(H, 16, upper_only=False)
+            e1.record()
+            torch.cuda.synchronize()
+            (ms_ar,) = _dist_max(dist, dev, e0.elapsed_time(e1) / 5)
+            ar["K%d" % K] = {"ms": ms_ar, "algo_GBps": K * K * 4 / (ms_ar * 1e-3) / 1e9,
+                             "bus_GBps": K * K * 4 * 2 * (world - 1) / world / (ms_ar * 1e-3) / 1e9}
+            del H
+        res["hessian_allreduce"] = ar
+    return res
+
+
+def leg_cfg4(dev, rank, world, dist):
+    """BASELINE configs[3]: LLaMA-3-70B linears, one of each big shape, rows sharded over the ranks
+    (dist.fasterquant_row_sharded): 8192x8192 and 28672x8192 (K = 8192) and 8192x28672 (K = 28672)."""
+    import msq_b200
+    from msq_b200 import dist as D
+    res = {}
+    tokens = 128 * 2048
+    for name, rows, cols in (("q_proj", 8192, 8192), ("gate_proj", 28672, 8192), ("down_proj", 8192, 28672)):
+        g = torch.Generator(device=dev).manual_seed(rows + cols)
+        layer = torch.nn.Linear(cols, rows, bias=False, device=dev, dtype=torch.float16)
+        layer.weight.data = (torch.randn(rows, cols, device=dev, generator=g) * 0.02).half()
+        gq = msq_b200.GPTQ(layer)
+        gq.verbose = False
+        gq.release_cache_on_free = False
+        gq.quantizer = msq_b200.MXQuantizer()
+        gq.quantizer.configure(8, 8, QCFG["in_fmt"], QCFG["out_fmt"], axes=[0], block_size=QCFG["bs"])
+        per_rank = tokens // world
+        X = torch.randn(1, 8192, cols, device=dev, generator=torch.Generator(device=dev).manual_seed(rank)).half()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(per_rank // 8192):
+            gq.add_batch(X, None)
+        _ = gq.H
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        if dist is not None:
+            H, n = D.combine_hessians(gq.H, gq.nsamples, upper_only=False)
+            gq.H, gq.nsamples = H, n
+            torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        path = D.fasterquant_row_sharded(gq)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        th, ta, ts = _dist_max(dist, dev, t1 - t0, t2 - t1, t3 - t2)
+        res["%s_%dx%d" % (name, rows, cols)] = {"hessian_s": th, "allreduce_s": ta, "solve_s": ts, "path": path,
+                                               "hessian_TFLOPs_aggregate": 2.0 * tokens * cols * cols / th / 1e12,
+                                               "error": gq.last_error}
+        gq.free()
+        del layer, gq, X
+        torch.cuda.empty_cache()
+    return res
+
+
+def leg_cfg5(dev, rank, world, dist):
+    """BASELINE configs[4]: packed MX-FP4 + outlier GEMM sweep, output features split over the ranks (no collective).
+    W is packed along K with block 32 (the mx.linear operand layout); A = bf16 (W4A16) and MX-FP8 (block-scaled)."""
+    import msq_b200
+    from msq_b200 import _tc, dist as D
+    res = {}
+    for KN in (4096, 8192, 14336, 28672):
+        lo, hi = D.shard_range(KN // 128, rank, world)
+        n_loc = (hi - lo) * 128
+        if n_loc == 0:
+            continue
+        g = torch.Generator(device=dev).manual_seed(KN + rank)
+        W = torch.randn(n_loc, KN, device=dev, generator=g) * 0.02
+        pw = msq_b200.pack_mx_outlier(W, 8, 8, "fp4_e2m1", "fp4_e2m1", 5, [1], 32, variant=1)
+        del W
+        ok8 = _tc.mx8_weight_ok(pw)
+        row = {}
+        for M in (1, 16, 256, 4096):
+            x = torch.randn(M, KN, device=dev, generator=g).to(torch.bfloat16)
+            ms = _time_ms(lambda: _tc.packed_linear(x, pw), 5)
+            ent = {"a16_ms": None, "a16_TFLOPs": None}
+            (ms,) = _dist_max(dist, dev, ms)
+            ent["a16_ms"], ent["a16_TFLOPs"] = ms, 2.0 * M * KN * KN / (ms * 1e-3) / 1e12
+            if ok8:
+                xq = msq_b200.pack_mx(x.float(), 8, "fp8_e4m3", axes=[-1], block_size=32)
+                ms8 = _time_ms(lambda: _tc.packed_linear_mx8(xq, pw), 5)
+                (ms8,) = _dist_max(dist, dev, ms8)
+                ent["mxfp8_ms"], ent["mxfp8_TFLOPs"] = ms8, 2.0 * M * KN * KN / (ms8 * 1e-3) / 1e12
+            row["M%d" % M] = ent
+        res["KN%d" % KN] = row
+        del pw
+        torch.cuda.empty_cache()
+    return res
+
+
 def make_weights(device, seed):
     g = torch.Generator().manual_seed(seed)
     out = []
@@ -278,24 +473,26 @@ def cpu_reference_pass(W):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the CPU path on the host cores, bounded sample (one 4096x4096 linear per step)"""
+    """--impl reference: the reference's CPU implementation of the path (the torch-CPU oracle port, all host threads) on
+    the SAME config as the B200 arm: one step = the seven linears of one decoder layer (202 M elements)."""
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count())
-    W = torch.randn(4096, 4096, generator=torch.Generator().manual_seed(0)) * 0.02
+    Ws = make_weights(None, 1000)
     for _ in range(args.warmup):
-        cpu_reference_pass(W)
+        cpu_reference_pass(Ws[0])                 # warm-up on one q_proj-sized linear (a full step takes seconds)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_pass(W)
+        for W in Ws:
+            cpu_reference_pass(W)
     dt = (time.perf_counter() - t0) / args.steps
-    v = W.numel() * BYTES_PER_ELEM / dt / 1e9
-    sample = "one q_proj-sized linear (4096x4096 fp32 = 1/12 of a step's elements) per step"
+    v = layer_elems() * BYTES_PER_ELEM / dt / 1e9
+    sample = "the full step: all seven linears of the layer, %d steps" % args.steps
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": {"workload": WORKLOAD, "elements_per_step_per_gpu": layer_elems(), "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -309,6 +506,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary metrics (pack, GPTQ layer, GEMM sweep)")
+    ap.add_argument("--gptq-layers", type=int, default=4, help="decoder layers of the LLaMA-2-7B-shaped model the GPTQ leg quantizes")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -340,7 +538,14 @@ def main():
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     nel = layer_elems()
 
+    # the seven linears go through ONE launch (msq_quantize_mx_outlier_multi_f32: the RTN driver's per-layer call)
+    plan = _ops.MultiQuantPlan(dev_w, dev_out, QCFG["in_sb"], QCFG["out_sb"], QCFG["in_fmt"], QCFG["out_fmt"],
+                               QCFG["std_dev"], QCFG["bs"], status=status)
+
     def step_device():
+        plan.launch()
+
+    def step_device_per_tensor():
         for w, o in zip(dev_w, dev_out):
             _ops.mx_outlier(w, QCFG["in_sb"], QCFG["out_sb"], QCFG["in_fmt"], QCFG["out_fmt"], QCFG["std_dev"],
                             QCFG["axis"], QCFG["bs"], want=("deq",), check=False, out=o, status=status)
@@ -376,6 +581,7 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.summary() if rank == 0 else None
+    ms_per_tensor = _time_ms(step_device_per_tensor, args.steps) if rank == 0 else 0.0     # seven launches, for comparison
     assert int(status.item()) == 0, "quantizer raised status %d" % int(status.item())
 
     # end to end through the public API with host buffers
@@ -393,6 +599,13 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_s = float(t[0]), float(t[1])
+    legs = {}
+    if not args.no_extras:
+        # every rank takes part in these: they time the paths that shard with their collectives inside
+        legs["gptq_model"] = leg_gptq_model(dev, rank, world, dist, layers=args.gptq_layers)
+        legs["cfg3_mxfp6"] = leg_cfg3(dev, rank, world, dist, dev_w)
+        legs["cfg4_llama3_70b_row_sharded"] = leg_cfg4(dev, rank, world, dist)
+        legs["cfg5_gemm_sweep_n_split"] = leg_cfg5(dev, rank, world, dist)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -411,16 +624,18 @@ def main():
         "clocks": clocks,
         "e2e": {"value": world * bytes_step / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": nel * 4, "d2h_bytes_per_step": nel * 4,
                 "ms_per_step": e2e_s * 1e3},
-        "gpu_launches": len(LAYER_SHAPES) * args.steps,
+        "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
-                     "traffic": None, "kernel": "k_strided<BS=16, OUTLIER, fake-quant>", "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": "8 B x rows x cols"},
+                     "traffic": None, "kernel": "k_strided_multi<BS=16> (one launch = the seven linears)", "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": "8 B x 202 375 168 elements = 1.619 GB",
+                     "seven_separate_launches_GBps": bytes_step / (ms_per_tensor * 1e-3) / 1e9},
     }
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
-        line["roofline"]["traffic"] = json.load(open(tr)).get("k_strided_bytes_per_launch")
+        line["roofline"]["traffic"] = json.load(open(tr)).get("k_strided_multi_bytes_per_launch")
     if not args.no_extras:
         line["extra"] = extras(dev, dev_w, nel)
+        line["extra"].update(legs)
     if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N=1 only
         torch.set_num_threads(os.cpu_count())
         W = host_w[0]

@@ -98,6 +98,15 @@ int msq_quantize_mx_outlier_f32(
     unsigned char* hi, int* seg_cnt, unsigned char* blk_cnt, unsigned char* mask,
     int* status, int* host_path, void* stream);
 
+/* The same quantizer (variant 0, blocks along the rows: axes=[0]) for up to 16 weight matrices [rows[i], cols[i]]
+ * in ONE launch: what llm/llama.py:238-253 does linear by linear for a decoder layer.  in / out are HOST arrays of
+ * n DEVICE pointers; bit-identical to n calls of msq_quantize_mx_outlier_f32(pre = 1, L = rows[i], post = cols[i]). */
+int msq_quantize_mx_outlier_multi_f32(int n, const float* const* in, float* const* out, const long long* rows,
+                                      const long long* cols, int block_size, int in_scale_bits, int out_scale_bits,
+                                      int in_ebits, int in_mbits, int in_emax, float in_max_norm,
+                                      int out_ebits, int out_mbits, int out_emax, float out_max_norm,
+                                      float std_dev, int flush_fp32_subnorms, int rmode, int* status, void* stream);
+
 /* detector statistics of number_system/mx/mx_ops.py:49-83 as called at :248 (mean / unbiased
  * std of signed A over the block-count axis).  lo, hi: fp32 [pre, block_size, post]. */
 int msq_outlier_bounds_across_blocks_f32(const float* in, float* lo, float* hi, long long pre,
@@ -218,6 +227,21 @@ int msq_gemm_packed_w_bf16(const void* X, long long ldx, const unsigned char* co
                            const signed char* e_in, const signed char* e_out, float* C, long long ldc,
                            int M, int N, int K, int in_ebits, int in_mbits, int out_ebits, int out_mbits,
                            int plain, int accumulate, void* stream);
+
+/* Same contraction for the artefact the quantizers emit (utils/quant.py:147-266 with axes=[0]; what GPTQ.fasterquant
+ * leaves, llm/llama.py:130-137): W packed in ROW blocks of block_size (16 or 32) output rows per input column,
+ * inlier-width slots + bitmap + e_in/e_out [N/block_size, K] + the segment-compacted hi stream.
+ * msq_packed_build_hi_index: rank index over the bitmap (stream offset of every 8th block inside its segment),
+ *   built once per weight; hi_off8 holds ceil(nblocks / 8) uint32.
+ * msq_gemm_packed_rowblock_bf16: N % block_size == 0, K % 64 == 0, slot width 2 or 4 bits (else
+ *   MSQ_ERR_UNSUPPORTED -> msq_unpack_mx + msq_gemm_nt_f32out). */
+int msq_packed_build_hi_index(const unsigned int* bitmap, long long pre, long long L, long long post, int block_size,
+                              unsigned int* hi_off8, void* stream);
+int msq_gemm_packed_rowblock_bf16(const void* X, long long ldx, const unsigned char* codes, const unsigned int* bitmap,
+                                  const signed char* e_in, const signed char* e_out, const unsigned char* hi,
+                                  const unsigned int* hi_off8, long long hi_seg_stride, float* C, long long ldc,
+                                  int M, int N, int K, int block_size, int in_ebits, int in_mbits, int out_ebits,
+                                  int out_mbits, int accumulate, void* stream);
 
 /* native block-scaled tensor-core path: tcgen05.mma kind::mxf8f6f4.block_scale (E4M3 x E4M3, UE8M0 scales
  * per 32 elements along K).  X: plain MX-FP8 (E4M3) activations, codes [M,K] bytes (ld = ldx) + int8

@@ -15,6 +15,8 @@ _DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 _i, _ll, _f, _p = C.c_int, C.c_longlong, C.c_float, C.c_void_p
 N.register("msq_host_quantize_mx_outlier_f32", _i, [_p, _p, _ll, _ll, _ll, _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _f,
                                                      _f, _i, _i, _ll, _i])
+N.register("msq_quantize_mx_outlier_multi_f32", _i, [_i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _f, _f,
+                                                      _i, _i, _p, _p])
 N.register("msq_host_sync", _i, [C.POINTER(C.c_int)])
 N.register("msq_host_release", _i, [])
 N.register("msq_magic_div", _i, [_ll, C.POINTER(C.c_uint), C.POINTER(C.c_int)])
@@ -201,3 +203,47 @@ def raise_on_status(s):
         raise AssertionError("inlier_val contains NaN values")
     if s & N.ST_EXP_OUT_OVERFLOW:
         raise AssertionError("shared_exp_out contains NaN values")
+
+
+class MultiQuantPlan(object):
+    """argument block of msq_quantize_mx_outlier_multi_f32 for a fixed list of weight matrices (built once, launched
+    many times: no per-call host work beyond the ctypes call)"""
+
+    def __init__(self, tensors, outs, in_sb, out_sb, in_fmt, out_fmt, std_dev, block_size, round="nearest", flush=False,
+                 status=None):
+        n = len(tensors)
+        assert 0 < n <= 16 and len(outs) == n
+        for t, o in zip(tensors, outs):
+            N.require_cuda(t, "input")
+            assert t.dim() == 2 and t.dtype == torch.float32 and t.is_contiguous()
+            assert o.shape == t.shape and o.dtype == torch.float32 and o.is_contiguous() and o.device == t.device
+        self.keep = (list(tensors), list(outs))
+        self.n = n
+        self.inp = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+        self.out = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+        self.rows = (C.c_longlong * n)(*[t.shape[0] for t in tensors])
+        self.cols = (C.c_longlong * n)(*[t.shape[1] for t in tensors])
+        self.fi, self.fo = fmt4(in_fmt), fmt4(out_fmt)
+        self.args = (int(block_size), int(in_sb), int(out_sb))
+        self.tail = (float(std_dev), int(bool(flush)), _rmode(round))
+        self.status = status if status is not None else torch.zeros(1, dtype=torch.int32, device=tensors[0].device)
+        self.device = tensors[0].device
+
+    def launch(self):
+        fi, fo = self.fi, self.fo
+        rc = N.lib().msq_quantize_mx_outlier_multi_f32(self.n, self.inp, self.out, self.rows, self.cols, *self.args,
+                                                       fi[0], fi[1], fi[2], fi[3], fo[0], fo[1], fo[2], fo[3], *self.tail,
+                                                       N.ptr(self.status), N.stream_ptr(self.device))
+        N.check(rc, "msq_quantize_mx_outlier_multi_f32")
+
+
+def mx_outlier_multi(tensors, in_sb, out_sb, in_fmt, out_fmt, std_dev, block_size, round="nearest", flush=False,
+                     outs=None, check=None):
+    """quantize_mx_outlier_v1(axes=[0]) of several 2-D fp32 CUDA weights in one launch; returns the list of outputs"""
+    xs = [_as_f32(t) for t in tensors]
+    outs = outs if outs is not None else [torch.empty_like(x) for x in xs]
+    plan = MultiQuantPlan(xs, outs, in_sb, out_sb, in_fmt, out_fmt, std_dev, block_size, round, flush)
+    plan.launch()
+    if CHECK_STATUS if check is None else check:
+        raise_on_status(int(plan.status.item()))
+    return outs

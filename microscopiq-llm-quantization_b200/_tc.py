@@ -169,12 +169,61 @@ def _bf16_terms(x):
     return terms
 
 
+N.register("msq_gemm_packed_rowblock_bf16", _i, [_p, _ll, _p, _p, _p, _p, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _i, _i,
+                                                  _i, _i, _i, _p])
+
+
+def rowblock_ok(pw):
+    """can this packed weight go through the row-block GEMM (the layout the quantizers emit: axes=[0])?"""
+    return (len(pw.shape) == 2 and pw.axis == 0 and not pw.plain and pw.block_size in (16, 32)
+            and pw.shape[0] % pw.block_size == 0 and pw.shape[1] % 64 == 0 and pw.code_width in (2, 4)
+            and pw.hi_w in (0, 2, 4))
+
+
+def _packed_linear_rowblock(x2, pw, out):
+    from . import _ops
+    Nn, K = pw.shape
+    M = x2.shape[0]
+    fi, fo = _ops.fmt4(pw.in_fmt), _ops.fmt4(pw.out_fmt)
+    idx = pw.hi_index() if pw.hi_w else None
+    for i, t in enumerate(_bf16_terms(x2)):
+        t = t.contiguous()
+        rc = N.lib().msq_gemm_packed_rowblock_bf16(N.ptr(t), t.stride(0), N.ptr(pw.codes), N.ptr(pw.bitmap), N.ptr(pw.e_in),
+                                                   N.ptr(pw.e_out), N.ptr(pw.hi), N.ptr(idx), int(pw.hi_seg_stride),
+                                                   N.ptr(out), out.stride(0), M, Nn, K, int(pw.block_size), fi[0], fi[1],
+                                                   fo[0], fo[1], int(i > 0), N.stream_ptr(x2.device))
+        N.check(rc, "msq_gemm_packed_rowblock_bf16")
+    return out
+
+
 def packed_linear(x, pw, bias=None):
     """y[..., N] (fp32) = x[..., K] @ dequant(pw)[N, K].T (+ bias) with pw a PackedMX blocked along K
     (block 32).  bf16 activations take one pass; fp16 / fp32 activations are split into exact bf16
     terms (2 / 3 accumulating passes) so that every product stays exact."""
     N.require_cuda(x, "x")
     from . import _ops
+    if len(pw.shape) == 2 and pw.axis == 0:
+        # the quantizers' own artefact (row blocks along the output features, hi stream): row-block GEMM, or -- for
+        # geometries it does not cover -- unpack once to bf16 (exact) and the dense tcgen05 GEMM
+        Nn, K = pw.shape
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, K)
+        out = torch.empty(x2.shape[0], (Nn + 3) // 4 * 4, dtype=torch.float32, device=x.device)[:, :Nn]
+        if rowblock_ok(pw) and x2.shape[0] < FUSED_MAX_M:
+            _packed_linear_rowblock(x2, pw, out)
+        else:
+            wb = getattr(pw, "_dense_bf16", None)
+            if wb is None:
+                wb = pw.dequantize(torch.bfloat16)
+                if K % 8:
+                    wb = torch.nn.functional.pad(wb, (0, 8 - K % 8))
+                pw._dense_bf16 = wb if x2.shape[0] >= FUSED_MAX_M else None      # large-M callers reuse it
+            for i, t in enumerate(_bf16_terms(x2)):
+                t = t.contiguous() if K % 8 == 0 else torch.nn.functional.pad(t, (0, 8 - K % 8)).contiguous()
+                gemm_nt(t, wb, out=out, alpha=1.0, beta=1.0 if i else 0.0)
+        if bias is not None:
+            out = out + bias.float()
+        return out.reshape(*lead, Nn)
     if len(pw.shape) != 2 or pw.axis != 1 or pw.block_size != 32 or pw.hi_w != 0 or pw.shape[1] % 32:
         raise NotImplementedError("packed_linear needs a [N, K] tensor packed along K with block 32, K a multiple "
                                   "of 32 and equal code widths")
@@ -185,8 +234,11 @@ def packed_linear(x, pw, bias=None):
     out = torch.empty(M, Nn, dtype=torch.float32, device=x.device)
     fi, fo = _ops.fmt4(pw.in_fmt), _ops.fmt4(pw.out_fmt)
     if M >= FUSED_MAX_M and Nn % 8 == 0:
-        # compute-bound regime: dequantize the weight once to bf16 (exact) and run the dense GEMM
-        wb = pw.dequantize(torch.bfloat16)
+        # compute-bound regime: dequantize the weight to bf16 (exact) ONCE per weight -- kept on the PackedMX
+        # object, 2 B per weight next to the packed planes -- and run the dense GEMM
+        wb = getattr(pw, "_dense_bf16", None)
+        if wb is None:
+            wb = pw._dense_bf16 = pw.dequantize(torch.bfloat16)
         for i, t in enumerate(_bf16_terms(x2)):
             gemm_nt(t.contiguous(), wb, out=out, alpha=1.0, beta=1.0 if i else 0.0)
         if bias is not None:

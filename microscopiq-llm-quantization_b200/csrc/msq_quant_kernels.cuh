@@ -78,6 +78,19 @@ __device__ __forceinline__ int cta_excl_scan(int v, int* s_warp, int* sum) {
 }
 
 
+// several [rows, cols] matrices quantized along the rows by one launch (k_strided_multi)
+constexpr int MSQ_MULTI_MAX = 16;
+struct MultiQParams {
+  int n;
+  QCfg c;
+  int* status;
+  const float* in[MSQ_MULTI_MAX];
+  float* deq[MSQ_MULTI_MAX];
+  int L[MSQ_MULTI_MAX], post[MSQ_MULTI_MAX], gx[MSQ_MULTI_MAX];
+  unsigned int cta_start[MSQ_MULTI_MAX + 1];
+};
+cudaError_t launch_strided_multi(const MultiQParams& MP, int bs, unsigned total_ctas, cudaStream_t stream);
+
 // launchers (one translation unit each); return false if the geometry is not theirs
 cudaError_t launch_strided(const QParams& P, bool outlier, size_t smem, cudaStream_t stream);
 cudaError_t launch_inner(const QParams& P, bool outlier, size_t smem, cudaStream_t stream);

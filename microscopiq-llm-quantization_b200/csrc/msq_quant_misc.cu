@@ -354,6 +354,43 @@ int msq_quantize_mx_outlier_f32(
   return launch_quant(P, true, (cudaStream_t)stream, path);
 }
 
+// quantize_mx_outlier_v1 (utils/quant.py:147-266, axes=[0]) for up to 16 weight matrices [rows[i], cols[i]] in ONE
+// launch -- what the reference's RTN driver does linear by linear for a decoder layer (llm/llama.py:238-253).
+// in / out: HOST arrays of n DEVICE pointers (fp32, contiguous, 16-byte aligned); results are bit-identical to n calls
+// of msq_quantize_mx_outlier_f32(pre = 1, L = rows, post = cols).  block_size 8, 16 or 32; each matrix < 2^31 elements.
+int msq_quantize_mx_outlier_multi_f32(int n, const float* const* in, float* const* out, const long long* rows,
+                                      const long long* cols, int block_size, int in_scale_bits, int out_scale_bits,
+                                      int in_ebits, int in_mbits, int in_emax, float in_max_norm, int out_ebits,
+                                      int out_mbits, int out_emax, float out_max_norm, float std_dev,
+                                      int flush_fp32_subnorms, int rmode, int* status, void* stream) {
+  if (n <= 0 || n > MSQ_MULTI_MAX || !in || !out || !rows || !cols) return MSQ_ERR_BAD_ARG;
+  msq::DevGuard dev_guard_(in[0]);
+  if (in_scale_bits <= 0 || out_scale_bits <= 0 || in_scale_bits > 8 || out_scale_bits > 8 || rmode < 0 || rmode > 2)
+    return MSQ_ERR_BAD_ARG;
+  if (block_size != 8 && block_size != 16 && block_size != 32) return MSQ_ERR_UNSUPPORTED;
+  MultiQParams MP;
+  memset(&MP, 0, sizeof(MP));
+  MP.n = n; MP.status = status;
+  MP.c.fin = make_fmt(in_ebits, in_mbits, in_emax, in_max_norm);
+  MP.c.fout = make_fmt(out_ebits, out_mbits, out_emax, out_max_norm);
+  MP.c.sb_in = in_scale_bits; MP.c.sb_out = out_scale_bits;
+  MP.c.std_dev = std_dev; MP.c.flush = flush_fp32_subnorms; MP.c.variant = 0; MP.c.rmode = rmode; MP.c.mode = 0;
+  finish_cfg(MP.c);
+  unsigned long long total = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!in[i] || !out[i] || rows[i] <= 0 || cols[i] <= 0 || rows[i] * cols[i] >= 0x7fffffffLL) return MSQ_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(in[i]) & 15) || (reinterpret_cast<uintptr_t>(out[i]) & 15)) return MSQ_ERR_ALIGN;
+    MP.in[i] = in[i]; MP.deq[i] = out[i];
+    MP.L[i] = (int)rows[i]; MP.post[i] = (int)cols[i];
+    MP.gx[i] = (int)((cols[i] + 255) / 256);
+    MP.cta_start[i] = (unsigned)total;
+    total += (unsigned long long)MP.gx[i] * (unsigned long long)((rows[i] + block_size - 1) / block_size);
+    if (total >= 0x7fffffffULL) return MSQ_ERR_UNSUPPORTED;
+  }
+  MP.cta_start[n] = (unsigned)total;
+  return launch_strided_multi(MP, block_size, (unsigned)total, (cudaStream_t)stream) == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+}
+
 int msq_quantize_mx_f32(
     const float* in, float* deq, long long pre, long long L, long long post, int block_size,
     int scale_bits, int ebits, int mbits, int emax, float max_norm,

@@ -249,6 +249,59 @@ __global__ void __launch_bounds__(256, (BS <= 16 ? MSQ_STRIDED_MINB : 2)) k_stri
   }
 }
 
+// ---- several weight matrices in ONE launch (fake-quant, blocks along the rows) -----------------------------------
+// The drivers quantize the linears of a decoder layer back to back (llm/llama.py:238-253); one launch over all of
+// them removes the launch gaps and the partially filled last wave of every matrix.  Same per-block arithmetic as
+// k_strided (core_outlier), CTA -> (matrix, row block, 256 columns) through a table in the parameter block.
+template <int BS>
+__global__ void __launch_bounds__(256, (BS <= 16 ? MSQ_STRIDED_MINB : 2)) k_strided_multi(const __grid_constant__ MultiQParams MP) {
+  int t = 0;
+#pragma unroll 1
+  while (t + 1 < MP.n && blockIdx.x >= MP.cta_start[t + 1]) ++t;
+  const int local = (int)(blockIdx.x - MP.cta_start[t]);
+  const int gx = MP.gx[t];
+  const int b = local / gx;
+  const int post = MP.post[t], L = MP.L[t];
+  const int j = (local - b * gx) * 256 + (int)threadIdx.x;
+  const bool active = j < post;
+  const int base = active ? b * BS * post + j : 0;
+  const int nv = active ? min(BS, L - b * BS) : 0;
+  float x[BS];
+  uint32_t code[BS];
+  const int sb = post * 4;
+  const char* pin = reinterpret_cast<const char*>(MP.in[t] + base);
+  if (nv == BS) {
+#pragma unroll
+    for (int i = 0; i < BS; ++i) x[i] = __ldg(reinterpret_cast<const float*>(pin + (long long)sb * i));
+  } else {
+#pragma unroll
+    for (int i = 0; i < BS; ++i) x[i] = (i < nv) ? __ldg(reinterpret_cast<const float*>(pin + (long long)sb * i)) : 0.0f;
+  }
+  const BlockOut bo = core_outlier<BS, 1, false, false, false>(x, code, MP.c, nullptr, nullptr);
+  char* pout = reinterpret_cast<char*>(MP.deq[t] + base);
+  if (nv == BS) {
+#pragma unroll
+    for (int i = 0; i < BS; ++i) *reinterpret_cast<float*>(pout + (long long)sb * i) = x[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < BS; ++i)
+      if (i < nv) *reinterpret_cast<float*>(pout + (long long)sb * i) = x[i];
+  }
+  if (MP.status) {
+    int st = active ? bo.st : 0;
+    st = __reduce_or_sync(0xffffffffu, st);
+    if ((threadIdx.x & 31) == 0 && st) atomicOr(MP.status, st);
+  }
+}
+
+cudaError_t launch_strided_multi(const MultiQParams& MP, int bs, unsigned total_ctas, cudaStream_t stream) {
+  if (bs == 16) k_strided_multi<16><<<total_ctas, 256, 0, stream>>>(MP);
+  else if (bs == 32) k_strided_multi<32><<<total_ctas, 256, 0, stream>>>(MP);
+  else if (bs == 8) k_strided_multi<8><<<total_ctas, 256, 0, stream>>>(MP);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_strided(const QParams& P, bool outlier, size_t smem, cudaStream_t stream) {
   const long long nseg = (P.nblocks + MSQ_SEG_BLOCKS - 1) / MSQ_SEG_BLOCKS;
   void (*k)(const QParams) = nullptr;

@@ -14,6 +14,7 @@ from types import SimpleNamespace
 import torch
 import torch.nn as nn
 
+from .. import _ops
 from .. import dist as D
 from ..utils.modelutils import find_layers
 from ..utils.quant import MXQuantizer, quantize_mx_outlier_v1
@@ -171,7 +172,7 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
     qcfg = dict(REFERENCE_QCFG if qcfg is None else qcfg)
     layers, _, _, _ = decoder_parts(model)
     stats = stats if stats is not None else {}
-    stats.update(hessian_s=0.0, solve_s=0.0, forward_s=0.0, comm_s=0.0, move_s=0.0, linears=0)
+    stats.update(hessian_s=0.0, solve_s=0.0, forward_s=0.0, comm_s=0.0, move_s=0.0, linears=0, comm_bytes=0)
     quantizers = {}
     world, rank = 1, 0
     if D.is_dist():
@@ -187,18 +188,34 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
             mover.prefetch(i + 1)
             found = find_layers(layer)
             owners = D.assign_linears({n: tuple(m.weight.shape) for n, m in found.items()}, world)
+            mine = []
             for name, lin in found.items():
                 q = MXQuantizer()
                 q.configure(**qcfg)
                 quantizers["layers.%d.%s" % (i, name)] = q
-                if owners[name] != rank:
-                    continue
-                W = lin.weight.data
-                lin.weight.data = quantize_mx_outlier_v1(W.float(), q.inlier_scale_bits, q.outlier_scale_bits,
-                                                         q.inlier_elem_format, q.outlier_elem_format, q.shared_exp_method,
-                                                         q.std_dev, q.axes, q.block_size, q.round, q.flush_fp32_subnorms,
-                                                         q.custom_cuda).to(W.dtype)
-                stats["linears"] += 1
+                if owners[name] == rank:
+                    mine.append((lin, q))
+            axes = qcfg.get("axes", [0])
+            axes = [axes] if isinstance(axes, int) else list(axes)
+            one_launch = (len(mine) > 0 and axes in ([0], [-2]) and qcfg.get("block_size", 16) in (8, 16, 32)
+                          and qcfg.get("inlier_elem_format") is not None and len(mine) <= 16
+                          and all(l.weight.dim() == 2 and l.weight.is_cuda for l, _ in mine)
+                          and mine[0][1].shared_exp_method == "max" and mine[0][1].round in ("nearest", "floor", "even"))
+            if one_launch:          # every linear of the layer this rank owns in ONE launch (k_strided_multi)
+                q = mine[0][1]
+                outs = _ops.mx_outlier_multi([l.weight.data.float() for l, _ in mine], q.inlier_scale_bits,
+                                             q.outlier_scale_bits, q.inlier_elem_format, q.outlier_elem_format, q.std_dev,
+                                             q.block_size, q.round, q.flush_fp32_subnorms)
+                for (lin, _), o in zip(mine, outs):
+                    lin.weight.data = o.to(lin.weight.dtype)
+            else:
+                for lin, q in mine:
+                    W = lin.weight.data
+                    lin.weight.data = quantize_mx_outlier_v1(W.float(), q.inlier_scale_bits, q.outlier_scale_bits,
+                                                             q.inlier_elem_format, q.outlier_elem_format, q.shared_exp_method,
+                                                             q.std_dev, q.axes, q.block_size, q.round, q.flush_fp32_subnorms,
+                                                             q.custom_cuda).to(W.dtype)
+            stats["linears"] += len(mine)
             for name, lin in found.items():
                 D.broadcast_weight(lin, owners[name])
             mover.offload(i, layer)
@@ -272,6 +289,7 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
                         continue
                     H, N = D.combine_hessians(gptq[name].H, gptq[name].nsamples, upper_only=False)
                     gptq[name].H, gptq[name].nsamples = H, N
+                    stats["comm_bytes"] += H.numel() * 4
                 torch.cuda.synchronize()
                 stats["comm_s"] += time.perf_counter() - t0
             t0 = time.perf_counter()
@@ -288,6 +306,7 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
                 t0 = time.perf_counter()
                 for name in subset:
                     D.broadcast_weight(subset[name], owners[name])
+                    stats["comm_bytes"] += subset[name].weight.numel() * subset[name].weight.element_size()
                 torch.cuda.synchronize()
                 stats["comm_s"] += time.perf_counter() - t0
         t0 = time.perf_counter()

@@ -19,6 +19,7 @@ from . import _native as N
 from . import _ops
 
 _p, _ll, _i, _f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
+N.register("msq_packed_build_hi_index", _i, [_p, _ll, _ll, _ll, _i, _p, _p])
 N.register("msq_unpack_mx", _i, [_p, _p, _p, _p, _p, _p, _p, _ll, _ll, _ll, _i, _i, _i, _i, _f, _i, _i, _i, _f, _i, _p])
 
 
@@ -46,6 +47,22 @@ class PackedMX(object):
         for s in self.shape:
             n *= s
         return bits.reshape(-1)[:n].reshape(self.shape).bool()
+
+    def hi_index(self):
+        """rank index over the bitmap (msq_packed_build_hi_index): stream offset of every 8th block inside its segment.
+        Gives the row-block GEMM random access into the compacted hi stream; built once, cached (and stored by
+        save_packed as a derived plane)."""
+        idx = getattr(self, "hi_off8", None)
+        if idx is None:
+            pre, L, post = _ops.geometry(self.shape, self.axis)
+            nblk = (L + self.block_size - 1) // self.block_size
+            nb = pre * nblk * post
+            idx = torch.empty((nb + 7) // 8, dtype=torch.int32, device=self.codes.device)
+            rc = N.lib().msq_packed_build_hi_index(N.ptr(self.bitmap), pre, L, post, self.block_size, N.ptr(idx),
+                                                   N.stream_ptr(idx.device))
+            N.check(rc, "msq_packed_build_hi_index")
+            self.hi_off8 = idx
+        return idx
 
     def dequantize(self, dtype=torch.float32):
         pre, L, post = _ops.geometry(self.shape, self.axis)
@@ -155,7 +172,7 @@ import struct as _struct
 
 MAGIC = b"MSQPACK1"
 FORMAT_VERSION = 1
-_PLANES = ("codes", "bitmap", "e_in", "e_out", "hi", "seg_cnt")
+_PLANES = ("codes", "bitmap", "e_in", "e_out", "hi", "seg_cnt", "hi_off8")
 _META = ("shape", "axis", "block_size", "in_fmt", "out_fmt", "in_scale_bits", "out_scale_bits", "code_width", "hi_w",
          "hi_seg_stride", "nseg", "plain")
 _DTYPES = {"uint8": torch.uint8, "int8": torch.int8, "int32": torch.int32, "float32": torch.float32,

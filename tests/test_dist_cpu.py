@@ -77,3 +77,83 @@ def test_sharding_maps():
     assert rs[0] == (0, 512) and rs[-1][1] == 4096 and all(lo % 256 == 0 for lo, _ in rs)
     rs = D.row_shards(1000, 16, 3)                            # ragged: last shard shorter, none negative
     assert rs[-1][1] == 1000 and all(hi >= lo for lo, hi in rs)
+
+
+class _OracleGPTQ(object):
+    """stand-in for msq_b200.GPTQ on the CPU tier: same attributes, factorization and solves done by the oracle"""
+
+    def __init__(self, layer, H, cfg):
+        from types import SimpleNamespace
+        self.layer, self.rows, self.columns = layer, layer.weight.shape[0], layer.weight.shape[1]
+        self.quantizer = SimpleNamespace(block_size=cfg["block_size"])
+        self.H, self.cfg, self.prune, self.hinv_method = H, cfg, True, "oracle"
+        self._share = SimpleNamespace(factor={})
+        self.last_path = self.last_error = None
+        self.replicated_calls = 0
+
+    def _fused_ok(self):
+        return True
+
+    def _factorize(self, percdamp, actorder):
+        W0 = self.layer.weight.data.clone().float()
+        Hinv, _ = O.hessian_inverse_factor(self.H.clone(), W0, percdamp)
+        return dict(Hinv=Hinv, ut=None, info=None, dead=torch.diag(self.H) == 0, perm=None, invperm=None)
+
+    def fasterquant(self, percdamp=.01):
+        self.replicated_calls += 1
+
+
+def _rowshard_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from msq_b200 import dist as D
+    g = torch.Generator().manual_seed(5)
+    rows, cols = 768, 160                                     # 3 units of 16^2 rows over 2 ranks: uneven on purpose
+    W = torch.randn(rows, cols, generator=g) * 0.02
+    X = torch.randn(4, 64, cols, generator=g)
+    H, n = torch.zeros(cols, cols), 0
+    for b in range(4):
+        H, n = O.hessian_add_batch(H, n, X[b:b + 1])
+    cfg = dict(inlier_scale_bits=8, outlier_scale_bits=8, inlier_elem_format="int2", outlier_elem_format="fp4", block_size=16)
+    layer = torch.nn.Linear(cols, rows, bias=False)
+    layer.weight.data = W.clone()
+    gq = _OracleGPTQ(layer, H, cfg)
+
+    def solve(Wl, fac):
+        Q, loss, info = O.fasterquant(Wl, fac["Hinv"], cfg, 128)
+        cnt = torch.zeros(2 * cols + 3, dtype=torch.int32)
+        cnt[:cols] = (Q == 0).sum(0).to(torch.int32)
+        cnt[cols:2 * cols] = torch.tensor(info["k"], dtype=torch.int32)
+        return Q, torch.tensor([loss], dtype=torch.float64), cnt
+    path = D.fasterquant_row_sharded(gq, solve_fn=solve)
+    Hinv, _ = O.hessian_inverse_factor(H.clone(), W.clone(), .01)
+    Qref, loss_ref, info = O.fasterquant(W, Hinv, cfg, 128)
+    ok = path == "row-sharded" and info["columns_with_zeros_lt_k"] == 0 and gq.replicated_calls == 0
+    ok = ok and torch.equal(layer.weight.data, Qref) and abs(gq.last_error - loss_ref) <= 1e-9 * loss_ref
+    # a quantizer whose prune is NOT a no-op must fall back to the replicated solver on every rank
+    layer2 = torch.nn.Linear(cols, rows, bias=False)
+    layer2.weight.data = W.clone()
+    gq2 = _OracleGPTQ(layer2, H, cfg)
+
+    def solve_bad(Wl, fac):
+        Q, loss, cnt = solve(Wl, fac)
+        if rank == 1:
+            cnt[3] = 0                                        # column 3: no zeros on this rank's rows ...
+            cnt[cols + 3] = 30000                             # ... and a k nobody can satisfy
+        return Q, loss, cnt
+    path2 = D.fasterquant_row_sharded(gq2, solve_fn=solve_bad)
+    ok = ok and path2 == "replicated" and gq2.replicated_calls == 1
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_row_sharded_fasterquant_two_rank_gloo():
+    """rows of one linear over 2 ranks == the unsharded oracle solve, bit for bit; counters are reduced before the
+    prune check; a violated check sends every rank to the replicated solver"""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_rowshard_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world)), dict(ret)
