@@ -185,7 +185,17 @@ int msq_gptq_solve_f32(float* W, long long ldw, float* Q, long long ldq, const f
                        int* status, int* violation, int block_size, int in_scale_bits, int out_scale_bits,
                        int in_ebits, int in_mbits, int in_emax, float in_max_norm,
                        int out_ebits, int out_mbits, int out_emax, float out_max_norm,
-                       float std_dev, int flush_fp32_subnorms, int rmode, void* stream);
+                       float std_dev, int flush_fp32_subnorms, int rmode,
+                       unsigned char* codes8, unsigned int* bitmap, signed char* e_in, signed char* e_out,
+                       void* stream);
+/* codes8 .. e_out (optional, all or none; cols % 32 == 0, rows % block_size == 0): the quantizer's own artefact of the
+ * GPTQ result -- one code byte per weight (inlier or outlier format by its bitmap bit), the outlier bitmap and the
+ * block exponents [rows / block_size, cols].  msq_pack_from_codes turns code bytes + bitmap into the standard packed
+ * planes (inlier-width slots, segment-compacted hi stream, seg_cnt) of ANY [pre, L, post] geometry, so that
+ * msq_unpack_mx(planes) == Q bit for bit and msq_gemm_packed_rowblock_bf16 can run the GPTQ result directly. */
+int msq_pack_from_codes(const unsigned char* codes8, const unsigned int* bitmap, long long pre, long long L,
+                        long long post, int block_size, int in_ebits, int in_mbits, int out_ebits, int out_mbits,
+                        unsigned char* slots, unsigned char* hi, int* seg_cnt, void* stream);
 int msq_gptq_trailing_update(float* W, long long ldw, const float* Err, const float* Hinv, long long ldh,
                              int rows, int i1, int count, int i2, int cols, void* stream);
 int msq_gptq_check_prune(const int* zeros, const int* kcnt, int cols, int* violation, void* stream);

@@ -12,6 +12,7 @@
 #include "msq_api_internal.h"
 #include "msq_common.cuh"
 #include "msq_tc.cuh"
+#include "msq_split3.cuh"
 
 namespace msq {
 
@@ -122,7 +123,7 @@ k_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         tc::tmem_ld_wait();
         const int col0 = tn * BN + c * 32;
         if (row < P.M) {
-          if (col0 + 32 <= P.N) {
+          if (col0 + 32 <= P.N && ((P.ldc & 3) == 0)) {
 #pragma unroll
             for (int v = 0; v < 8; ++v) {
               float4 o;
@@ -219,6 +220,33 @@ __global__ void __launch_bounds__(256) k_transpose_to16(const TIN* __restrict__ 
   }
 }
 
+// X [T, K] fp32 -> three bf16 planes of X^T, each [Kpad, Tpad] (x = p0 + p1 + p2 exactly, zero padded): the operand
+// of the split-plane GEMM.  bf16 keeps fp32's exponent range, so -- unlike a two-term fp16 split -- nothing
+// overflows at |x| >= 65504 and small features keep their relative accuracy.
+__global__ void __launch_bounds__(256) k_transpose_split3(const float* __restrict__ X, __nv_bfloat16* __restrict__ P, int T,
+                                                          int K, long long ldx, int Tpad, int Kpad) {
+  __shared__ float tile[32][33];
+  const int t0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r, k = k0 + tx;
+    tile[r][tx] = (t < T && k < K) ? X[(long long)t * ldx + k] : 0.0f;
+  }
+  __syncthreads();
+  const long long ps = (long long)Kpad * Tpad;
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, t = t0 + tx;
+    if (k >= Kpad || t >= Tpad) continue;
+    const float v = tile[tx][r];
+    const __nv_bfloat16 p0 = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(p0);
+    const __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 p2 = __float2bfloat16_rn(r1 - __bfloat162float(p1));
+    __nv_bfloat16* dst = P + (long long)k * Tpad + t;
+    dst[0] = p0; dst[ps] = p1; dst[2 * ps] = p2;
+  }
+}
+
 EncodeTiledFn get_encode_tiled() {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
@@ -258,7 +286,7 @@ static int gemm_nt_16(const void* A, const void* B, float* C, int M, int N, int 
                       long long ldc, float alpha, float beta, int ab_format, int upper_only, cudaStream_t stream) {
   if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return MSQ_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (reinterpret_cast<uintptr_t>(C) & 15) ||
-      (lda % 8) || (ldb % 8) || (ldc % 4))
+      (lda % 8) || (ldb % 8))
     return MSQ_ERR_ALIGN;
   CUtensorMap tmA, tmB;
   const CUtensorMapDataType dt = ab_format == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -294,13 +322,14 @@ int msq_gemm_nt_f32out(const void* A, const void* B, float* C, int M, int N, int
 // workspace bytes for msq_hessian_accumulate
 long long msq_hessian_workspace_bytes(int T, int K, int dtype) {
   const long long Tpad = ((long long)T + 63) / 64 * 64;
-  return dtype == 0 ? 2LL * 3 * Tpad * K * 2 : Tpad * (long long)K * 2;
+  const long long Kpad = ((long long)K + 127) / 128 * 128;
+  return dtype == 0 ? 3LL * Kpad * Tpad * 2 : Tpad * (long long)K * 2;
 }
 
 // GPTQ.add_batch (llm/gptq.py:53-58) for nn.Linear:   H <- beta * H + alpha * X^T X
 // with X [T, K] row-major tokens x features (dtype 0 fp32, 1 fp16, 2 bf16), H [K, K] fp32 (ld = ldh).
 // The caller passes beta = n/(n+b), alpha = 2/(n+b).  fp16/bf16 products are exact in the fp32
-// accumulator; fp32 input is split into two fp16 terms (relative error ~2^-21).
+// accumulator; fp32 input is split into three bf16 planes (full fp32 range, error ~2^-24 |x||x|^T per product).
 // symmetric != 0: only tiles touching the upper triangle are computed, then mirrored.
 int msq_hessian_accumulate(const void* X, int T, int K, long long ldx, int dtype, float* H, long long ldh, float alpha,
                            float beta, void* workspace, long long workspace_bytes, int symmetric, void* stream) {
@@ -314,9 +343,29 @@ int msq_hessian_accumulate(const void* X, int T, int K, long long ldx, int dtype
   dim3 g((Tpad + 31) / 32, (K + 31) / 32);
   int Keff = Tpad;
   if (dtype == 0) {
-    XtB = XtA + 3LL * Tpad * K;
-    k_transpose_to16<float><<<g, 256, 0, s>>>(reinterpret_cast<const float*>(X), XtA, XtB, T, K, ldx, Tpad, 1);
-    Keff = 3 * Tpad;
+    // fp32 activations: three bf16 planes of X^T and the fp32-accurate split-plane GEMM (six plane pairs)
+    const int Kpad = (K + 127) / 128 * 128;
+    __nv_bfloat16* PL = reinterpret_cast<__nv_bfloat16*>(workspace);
+    dim3 g3((Tpad + 31) / 32, (Kpad + 31) / 32);
+    k_transpose_split3<<<g3, 256, 0, s>>>(reinterpret_cast<const float*>(X), PL, T, K, ldx, Tpad, Kpad);
+    if (cudaGetLastError() != cudaSuccess) return MSQ_ERR_CUDA;
+    CUtensorMap mA, mB;
+    if (split3_make_tmap(&mA, PL, 3LL * Kpad, Tpad, Tpad, 128)) return MSQ_ERR_CUDA;
+    if (split3_make_tmap(&mB, PL, 3LL * Kpad, Tpad, Tpad, 256)) return MSQ_ERR_CUDA;
+    Split3Params SP;
+    memset(&SP, 0, sizeof(SP));
+    SP.M = K; SP.N = K; SP.K = Tpad;
+    SP.a_plane_rows = Kpad; SP.b_plane_rows = Kpad;
+    SP.alpha = alpha; SP.beta = beta; SP.C = H; SP.ldc = ldh;
+    SP.upper_only = symmetric ? 1 : 0;
+    int rc3 = split3_gemm(mA, mB, SP, s);
+    if (rc3) return rc3;
+    if (symmetric) {
+      dim3 gs((K + 31) / 32, (K + 31) / 32);
+      k_symmetrize_lower<<<gs, 256, 0, s>>>(H, K, ldh);
+      if (cudaGetLastError() != cudaSuccess) return MSQ_ERR_CUDA;
+    }
+    return MSQ_OK;
   } else {
     k_transpose_to16<uint16_t><<<g, 256, 0, s>>>(reinterpret_cast<const uint16_t*>(X), XtA, XtB, T, K, ldx, Tpad, dtype == 2 ? 2 : 0);
   }

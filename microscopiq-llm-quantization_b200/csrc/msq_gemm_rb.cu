@@ -195,9 +195,12 @@ __global__ void __launch_bounds__(512, 1) k_gemm_rb(const __grid_constant__ CUte
             const bool isout = (m >> j) & 1u;
             const uint32_t hv = hi_w ? ((hib >> (hi_w * j)) & ((1u << hi_w) - 1u)) : 0u;
             const float q = isout ? lut_out[(hv << wi) | slot] : lut_in[slot];
-            const uint32_t ew = isout ? (j < 4 ? eo[it].x : eo[it].y) : (j < 4 ? ei[it].x : ei[it].y);
-            const int e = (int)(signed char)((ew >> (8 * (j & 3))) & 0xFFu);
-            const float sc = e == MSQ_EXP_NAN ? qnan() : pow2i(e);
+            // inlier: q * 2^e_in ; outlier: (q * 2^e_out) * 2^-e_in  (utils/quant.py:136: the outlier was scaled by 2^e_in first)
+            const int e_i = (int)(signed char)(((j < 4 ? ei[it].x : ei[it].y) >> (8 * (j & 3))) & 0xFFu);
+            const int e_o = (int)(signed char)(((j < 4 ? eo[it].x : eo[it].y) >> (8 * (j & 3))) & 0xFFu);
+            const bool nan_blk = e_i == MSQ_EXP_NAN || e_o == MSQ_EXP_NAN;
+            const int e = isout ? max(-126, min(127, e_o - e_i)) : e_i;
+            const float sc = nan_blk ? qnan() : pow2i(e);
             const uint32_t bits = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(q * sc));
             if (j & 1) w[j >> 1] |= bits << 16; else w[j >> 1] = bits;
           }

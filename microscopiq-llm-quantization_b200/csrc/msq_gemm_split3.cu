@@ -148,7 +148,7 @@ k_gemm_split3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         tc::tmem_ld_wait();
         const int col0 = tn * BN + c * 32;
         if (col0 >= P.N) continue;                       // warp-uniform
-        const bool full32 = col0 + 32 <= P.N;
+        const bool full32 = col0 + 32 <= P.N && ((P.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);    // float4 rows need a 16-byte row pitch
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = P.alpha * __uint_as_float(r[j]);
@@ -179,7 +179,7 @@ k_gemm_split3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           if (P.out_planes) {      // row-major bf16 planes of the result (operand of a later contraction)
             __nv_bfloat16* p0 = P.out_planes + (long long)(P.op_row0 + row) * P.ldp + P.op_col0 + col0;
             const long long ps = (long long)P.op_plane_rows * P.ldp;
-            if (full32) {
+            if (col0 + 32 <= P.N) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 __align__(16) __nv_bfloat16 a0[8], a1[8], a2[8];
@@ -262,7 +262,7 @@ static int sm_count_s3() {
 
 int split3_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Split3Params& P, cudaStream_t stream) {
   if (P.M <= 0 || P.N <= 0 || P.K <= 0) return MSQ_OK;
-  if (P.C && ((reinterpret_cast<uintptr_t>(P.C) & 15) || (P.ldc % 4))) return MSQ_ERR_ALIGN;
+  if (P.C && (reinterpret_cast<uintptr_t>(P.C) & 3)) return MSQ_ERR_ALIGN;
   if (cudaFuncSetAttribute(s3::k_gemm_split3, cudaFuncAttributeMaxDynamicSharedMemorySize, s3::SMEM) != cudaSuccess)
     return MSQ_ERR_CUDA;
   const int tiles = ((P.M + s3::BM - 1) / s3::BM) * ((P.N + s3::BN - 1) / s3::BN);

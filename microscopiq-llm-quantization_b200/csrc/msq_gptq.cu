@@ -28,6 +28,11 @@ struct GptqParams {
   float* Err;                        // [rows, 128] (w - q) / d, zero padded (optional for k_gptq_block2)
   __nv_bfloat16* ErrPlanes;          // optional: the same values as three bf16 planes [3 * err_plane_rows, 128]
   int err_plane_rows;                //           (operand of the tensor-core trailing update)
+  // optional packed-artefact outputs of k_gptq_block2<BS, true> (all or none; cols % 32 == 0):
+  uint8_t* codes8; long long ldcodes;   // [rows, ldcodes] full element code (inlier or outlier format by the mask bit)
+  uint32_t* bitmap;                  // 1 bit per element, row-major [rows, cols]
+  int8_t* e_in; int8_t* e_out;       // [rows / BS, cols]
+  int cols;
   double* loss;                      // sum (w-q)^2 / d^2 / 2
   int* zeros; int* kcnt;             // per column: #(q == 0), reference's k
   int* status;
@@ -141,12 +146,17 @@ constexpr int MBK = 8;
 
 __device__ __forceinline__ void bar_pair() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 
-template <int BS>
+template <int BS, bool EMIT>
 __global__ void __launch_bounds__(64) k_gptq_block2(const GptqParams P) {
   extern __shared__ __align__(16) float sm[];
   float* tile = sm;                 // [32][TS]  W1 -> Q1
   float* etile = sm + 32 * TS;      // [32][TS]  Err1
   float* hs = sm + 64 * TS;         // [128][GB] Hinv1
+  // EMIT: element codes, outlier bits and block exponents of the quantized columns (the packed artefact)
+  uint8_t* ctile = reinterpret_cast<uint8_t*>(hs + GB * GB);          // [32][GB] codes
+  uint32_t* mtile = reinterpret_cast<uint32_t*>(ctile + 32 * GB);      // [32][4]  outlier bits
+  int8_t* eitile = reinterpret_cast<int8_t*>(mtile + 32 * 4);          // [32 / BS][GB]
+  int8_t* eotile = eitile + (32 / BS) * GB;                            // [32 / BS][GB]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r0 = blockIdx.x * 32;
   const int row = r0 + lane;
@@ -162,6 +172,7 @@ __global__ void __launch_bounds__(64) k_gptq_block2(const GptqParams P) {
       tile[rr * TS + j] = (rv && j < count) ? __ldg(src + j) : 0.0f;
       etile[rr * TS + j] = 0.0f;
     }
+    if (EMIT && lane < 4) mtile[rr * 4 + lane] = 0;
   }
   for (int rr = warp; rr < GB; rr += 2) {
     const float* src = P.Hinv + (long long)(P.i1 + rr) * P.ldh + P.i1;
@@ -216,7 +227,7 @@ __global__ void __launch_bounds__(64) k_gptq_block2(const GptqParams P) {
           const float wv = w[c];
           float x[1] = {active ? wv : 0.0f};
           uint32_t code[1];
-          const BlockOut bo = core_outlier<1, BS, false, false>(x, code, P.c, nullptr, nullptr);
+          const BlockOut bo = core_outlier<1, BS, EMIT, false>(x, code, P.c, nullptr, nullptr);
           const float q = x[0];
           st |= bo.st;
           const unsigned zmask = __ballot_sync(0xffffffffu, active && q == 0.0f);
@@ -227,6 +238,14 @@ __global__ void __launch_bounds__(64) k_gptq_block2(const GptqParams P) {
           if (active) loss += (double)__fdiv_rn(__fmul_rn(diff, diff), __fmul_rn(d, d));
           ep[c] = active ? err : 0.0f;
           trow[i] = q;
+          if (EMIT) {
+            ctile[lane * GB + i] = (uint8_t)code[0];
+            if (bo.mask & 1u) mtile[lane * 4 + (i >> 5)] |= 1u << (i & 31);
+            if ((lane % BS) == 0) {
+              eitile[(lane / BS) * GB + i] = (int8_t)bo.e_in;
+              eotile[(lane / BS) * GB + i] = (int8_t)bo.e_out;
+            }
+          }
 #pragma unroll
           for (int c2 = c + 1; c2 < MBK; ++c2) w[c2] = __fsub_rn(w[c2], __fmul_rn(err, h[c2]));
         } else {
@@ -289,6 +308,17 @@ __global__ void __launch_bounds__(64) k_gptq_block2(const GptqParams P) {
         const __nv_bfloat16 p2 = __float2bfloat16_rn(r1 - __bfloat162float(p1));
         __nv_bfloat16* ep = P.ErrPlanes + (long long)(r0 + rr) * GB + j;
         ep[0] = p0; ep[eps] = p1; ep[2 * eps] = p2;
+      }
+      if (EMIT && j < count) P.codes8[(long long)(r0 + rr) * P.ldcodes + P.i1 + j] = ctile[rr * GB + j];
+    }
+    if (EMIT && lane < 4 && P.i1 + lane * 32 < P.cols)
+      P.bitmap[(((long long)(r0 + rr) * P.cols + P.i1) >> 5) + lane] = mtile[rr * 4 + lane];
+    if (EMIT && (rr % BS) == 0) {
+      const long long eb = (long long)((r0 + rr) / BS) * P.cols + P.i1;
+#pragma unroll
+      for (int c = 0; c < GB / 32; ++c) {
+        const int j = lane + 32 * c;
+        if (j < count) { P.e_in[eb + j] = eitile[(rr / BS) * GB + j]; P.e_out[eb + j] = eotile[(rr / BS) * GB + j]; }
       }
     }
   }
@@ -375,6 +405,7 @@ int msq_gptq_block(const float* W, long long ldw, float* Q, long long ldq, const
   GptqParams P;
   P.W = W; P.ldw = ldw; P.Q = Q; P.ldq = ldq; P.Hinv = Hinv; P.ldh = ldh; P.Err = Err; P.loss = loss; P.zeros = zeros;
   P.ErrPlanes = nullptr; P.err_plane_rows = 0;
+  P.codes8 = nullptr; P.ldcodes = 0; P.bitmap = nullptr; P.e_in = nullptr; P.e_out = nullptr; P.cols = 0;
   P.kcnt = kcnt; P.status = status; P.rows = rows; P.i1 = i1; P.count = count;
   P.c.fin = make_fmt(in_ebits, in_mbits, in_emax, in_max_norm);
   P.c.fout = make_fmt(out_ebits, out_mbits, out_emax, out_max_norm);
@@ -439,16 +470,19 @@ int msq_gptq_solve_f32(float* W, long long ldw, float* Q, long long ldq, const f
                        long long workspace_bytes, double* loss, int* zeros, int* kcnt, int* status, int* violation,
                        int block_size, int in_scale_bits, int out_scale_bits, int in_ebits, int in_mbits, int in_emax,
                        float in_max_norm, int out_ebits, int out_mbits, int out_emax, float out_max_norm, float std_dev,
-                       int flush_fp32_subnorms, int rmode, void* stream) {
+                       int flush_fp32_subnorms, int rmode, unsigned char* codes8, unsigned int* bitmap,
+                       signed char* e_in, signed char* e_out, void* stream) {
   msq::DevGuard dev_guard_(W);
   if (!W || !Q || !Hinv || !workspace || !loss || !zeros || !kcnt || !status || !violation || rows <= 0 || cols <= 0)
     return MSQ_ERR_BAD_ARG;
+  const bool emit = codes8 != nullptr;
+  if (emit && (!bitmap || !e_in || !e_out || (cols % 32) || (rows % block_size))) return MSQ_ERR_BAD_ARG;
   if (workspace_bytes < msq_gptq_solve_workspace_bytes(rows)) return MSQ_ERR_BAD_ARG;
   if (in_ebits > 5 || out_ebits > 5) return MSQ_ERR_UNSUPPORTED;
   void (*k)(const GptqParams) = nullptr;
-  if (block_size == 16) k = k_gptq_block2<16>;
-  else if (block_size == 32) k = k_gptq_block2<32>;
-  else if (block_size == 8) k = k_gptq_block2<8>;
+  if (block_size == 16) k = emit ? k_gptq_block2<16, true> : k_gptq_block2<16, false>;
+  else if (block_size == 32) k = emit ? k_gptq_block2<32, true> : k_gptq_block2<32, false>;
+  else if (block_size == 8) k = emit ? k_gptq_block2<8, true> : k_gptq_block2<8, false>;
   else return MSQ_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream;
   const int rp = (rows + 127) / 128 * 128;
@@ -460,12 +494,13 @@ int msq_gptq_solve_f32(float* W, long long ldw, float* Q, long long ldq, const f
   P.W = W; P.ldw = ldw; P.Q = Q; P.ldq = ldq; P.Hinv = Hinv; P.ldh = ldh; P.loss = loss; P.zeros = zeros;
   P.kcnt = kcnt; P.status = status; P.rows = rows;
   P.Err = tc ? nullptr : Err; P.ErrPlanes = tc ? EP : nullptr; P.err_plane_rows = rp;
+  P.codes8 = codes8; P.ldcodes = cols; P.bitmap = bitmap; P.e_in = e_in; P.e_out = e_out; P.cols = cols;
   P.c.fin = make_fmt(in_ebits, in_mbits, in_emax, in_max_norm);
   P.c.fout = make_fmt(out_ebits, out_mbits, out_emax, out_max_norm);
   P.c.sb_in = in_scale_bits; P.c.sb_out = out_scale_bits; P.c.std_dev = std_dev; P.c.flush = flush_fp32_subnorms;
   P.c.variant = 0; P.c.mode = 0; P.c.rmode = rmode;
   finish_cfg(P.c);
-  const size_t smem = (2 * 32 * TS + GB * GB) * sizeof(float);
+  const size_t smem = (2 * 32 * TS + GB * GB) * sizeof(float) + (emit ? 32 * GB + 32 * 16 + 2 * (32 / block_size) * GB : 0);
   if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MSQ_ERR_CUDA;
   CUtensorMap mE, mUT;
   if (tc) {

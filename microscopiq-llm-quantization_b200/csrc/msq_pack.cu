@@ -468,3 +468,110 @@ int msq_unpack_mx(const unsigned char* codes, const signed char* e_in, const sig
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Packed planes from per-element codes: the GPTQ column kernel (msq_gptq_solve_f32) emits one code byte per weight
+// (inlier or outlier format according to the bitmap) -- the quantizer's own integers, not a re-quantization of the
+// dequantized values.  This pass lays them out as the standard planes: inlier-width slots + segment-compacted hi
+// stream, so that unpack(planes) == GPTQ's Q bit for bit and the row-block GEMM can consume them.
+// ---------------------------------------------------------------------------------------------------------------
+namespace msq {
+
+__global__ void __launch_bounds__(256) k_slots_from_codes(const uint8_t* __restrict__ codes8, long long n, int wi,
+                                                          uint8_t* __restrict__ slots) {
+  const long long g = (long long)blockIdx.x * 256 + threadIdx.x;      // group of 8 elements
+  const long long e0 = g * 8;
+  if (e0 >= n) return;
+  uint32_t w = 0;
+  const uint32_t m = (1u << wi) - 1u;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (e0 + i < n) w |= ((uint32_t)codes8[e0 + i] & m) << (wi * i);
+  uint8_t* dst = slots + ((e0 * wi) >> 3);
+  const int nbytes = wi;                                               // 8 elements * wi bits
+  for (int b = 0; b < nbytes; ++b)
+    if (((e0 * wi) >> 3) + b < ((n * wi + 7) >> 3)) dst[b] = (uint8_t)(w >> (8 * b));
+}
+
+__global__ void __launch_bounds__(256) k_hi_from_codes(const uint8_t* __restrict__ codes8, const uint32_t* __restrict__ bitmap,
+                                                       long long pre, long long L, long long post, int bs, long long nb, int wi,
+                                                       int hi_w, uint8_t* __restrict__ hi, long long hi_seg_stride,
+                                                       int* __restrict__ seg_cnt) {
+  __shared__ uint32_t wsum[8];
+  const long long nblk = (L + bs - 1) / bs;
+  const long long t0 = (long long)blockIdx.x * MSQ_SEG_BLOCKS + threadIdx.x * 4;
+  uint32_t c[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const long long t = t0 + u;
+    c[u] = 0;
+    if (t < nb) {
+      const long long j = t % post, pb = t / post, b = pb % nblk, p = pb / nblk;
+      for (int i = 0; i < bs; ++i) {
+        const long long l = b * bs + i;
+        if (l >= L) break;
+        const long long e = (p * L + l) * post + j;
+        c[u] += (__ldg(bitmap + (e >> 5)) >> (e & 31)) & 1u;
+      }
+    }
+  }
+  const uint32_t mine = c[0] + c[1] + c[2] + c[3];
+  uint32_t incl = mine;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  uint32_t base = 0, total = 0;
+  for (int w = 0; w < 8; ++w) { if (w < warp) base += wsum[w]; total += wsum[w]; }
+  if (threadIdx.x == 0 && seg_cnt) seg_cnt[blockIdx.x] = hi_w ? (int)total : 0;
+  if (!hi_w) return;
+  uint32_t off = base + incl - mine;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(hi + (long long)blockIdx.x * hi_seg_stride);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const long long t = t0 + u;
+    if (t >= nb || !c[u]) continue;
+    const long long j = t % post, pb = t / post, b = pb % nblk, p = pb / nblk;
+    for (int i = 0; i < bs; ++i) {
+      const long long l = b * bs + i;
+      if (l >= L) break;
+      const long long e = (p * L + l) * post + j;
+      if ((__ldg(bitmap + (e >> 5)) >> (e & 31)) & 1u) {
+        const uint32_t field = ((uint32_t)codes8[e] >> wi) & ((1u << hi_w) - 1u);
+        const uint32_t bit = off * hi_w;
+        atomicOr(dst + (bit >> 5), field << (bit & 31));            // hi_w divides 32: a field never straddles words
+        ++off;
+      }
+    }
+  }
+}
+
+}  // namespace msq
+
+extern "C" int msq_pack_from_codes(const unsigned char* codes8, const unsigned int* bitmap, long long pre, long long L,
+                                   long long post, int block_size, int in_ebits, int in_mbits, int out_ebits, int out_mbits,
+                                   unsigned char* slots, unsigned char* hi, int* seg_cnt, void* stream) {
+  msq::DevGuard dev_guard_(codes8);
+  if (!codes8 || !bitmap || !slots || pre <= 0 || L <= 0 || post <= 0 || block_size <= 0) return MSQ_ERR_BAD_ARG;
+  using namespace msq;
+  const Fmt fi = make_fmt(in_ebits, in_mbits, 0, 1.0f);
+  const int wi = fi.width, hi_w = msq_packed_hi_width(in_ebits, in_mbits, out_ebits, out_mbits);
+  if (hi_w && !hi) return MSQ_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long n = pre * L * post;
+  const long long nblk = (L + block_size - 1) / block_size, nb = pre * nblk * post;
+  const long long nseg = (nb + MSQ_SEG_BLOCKS - 1) / MSQ_SEG_BLOCKS;
+  const long long stride = msq_packed_hi_seg_stride(block_size, hi_w);
+  if (hi_w && cudaMemsetAsync(hi, 0, (size_t)(nseg * stride), s) != cudaSuccess) return MSQ_ERR_CUDA;
+  if (wi == 8) {
+    if (cudaMemcpyAsync(slots, codes8, (size_t)n, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return MSQ_ERR_CUDA;
+  } else {
+    k_slots_from_codes<<<(unsigned)((n / 8 + 256) / 256), 256, 0, s>>>(codes8, n, wi, slots);
+    if (cudaGetLastError() != cudaSuccess) return MSQ_ERR_CUDA;
+  }
+  k_hi_from_codes<<<(unsigned)nseg, 256, 0, s>>>(codes8, bitmap, pre, L, post, block_size, nb, wi, hi_w, hi, stride, seg_cnt);
+  return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+}

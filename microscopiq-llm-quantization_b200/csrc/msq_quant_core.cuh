@@ -290,13 +290,13 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
     static_assert((BS & (BS - 1)) == 0, "fast mappings use power-of-two blocks");
     const float mean = __fmul_rn(s, inv_bs);
     if (N % 4 == 0) {
+      // The squares are SCALAR mul.rn.f32: ptxas (12.9) contracts mul.rn.f32x2 feeding add.rn.f32x2 into FFMA2 even
+      // with -fmad=false, which would make the first tree level fma(d0, d0, d1*d1) -- one rounding less than the
+      // canonical order, and a different detector bound in ~1 block out of 10^7 (found by the full-size parity test).
 #pragma unroll
-      for (int i = 0; i < N; i += 4) {      // squares paired the way the first tree level consumes them
-        const float d0 = __fsub_rn(fabsf(x[i]), mean), d1 = __fsub_rn(fabsf(x[i + 1]), mean);
-        const float d2 = __fsub_rn(fabsf(x[i + 2]), mean), d3 = __fsub_rn(fabsf(x[i + 3]), mean);
-        const float2 a = __fmul2_rn(make_float2(d0, d2), make_float2(d0, d2));
-        const float2 b = __fmul2_rn(make_float2(d1, d3), make_float2(d1, d3));
-        t[i] = a.x; t[i + 2] = a.y; t[i + 1] = b.x; t[i + 3] = b.y;
+      for (int i = 0; i < N; ++i) {
+        const float d = __fsub_rn(fabsf(x[i]), mean);
+        t[i] = __fmul_rn(d, d);
       }
     } else {
 #pragma unroll

@@ -38,7 +38,8 @@ N.register("msq_gptq_check_prune", _i, [_p, _p, _i, _p, _p])
 N.register("msq_rank1_sub_f32", _i, [_p, _ll, _p, _p, _i, _i, _p])
 N.register("msq_gptq_solve_workspace_bytes", _ll, [_i])
 N.register("msq_gptq_solve_f32", _i, [_p, _ll, _p, _ll, _p, _ll, _p, _ll, _i, _i, _i, _p, _ll, _p, _p, _p, _p, _p,
-                                      _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _f, _f, _i, _i, _p])
+                                      _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _f, _f, _i, _i, _p, _p, _p, _p, _p])
+N.register("msq_pack_from_codes", _i, [_p, _p, _ll, _ll, _ll, _i, _i, _i, _i, _i, _p, _p, _p, _p])
 
 
 class _Shared(object):
@@ -75,6 +76,10 @@ class GPTQ:
     hinv_method = "native"
     #: trailing update W[:, i2:] -= Err1 Hinv[i1:i2, i2:] (gptq.py:165) on tcgen05 (True) or in fp32 SIMT (False)
     trailing_tc = True
+    #: keep the packed artefact of the result (self.packed: PackedMX whose dequantize() is the new weight bit for bit,
+    #: built from the column kernel's own codes) -- what save_packed / MXLinear.from_packed / the row-block GEMM consume.
+    #: Available on the fused path without act-order (None otherwise).
+    emit_packed = False
 
     def __init__(self, layer, prune=True):
         #: prune=False is the reference's vlm/gptq.py:130-144 variant: the column quantizer is quantize_mx_outlier_v1
@@ -90,6 +95,8 @@ class GPTQ:
         self.rows = W.shape[0]
         self.columns = W.shape[1]
         self._share = _Shared(self.columns, self.dev)
+        self.packed = None
+        self._emitted = None
         self.last_path = None
         self.last_error = None
 
@@ -230,6 +237,7 @@ class GPTQ:
 
         if actorder:
             Q = Q[:, invperm]
+            self.packed = None                             # the artefact is in permuted column order
         if isinstance(self.layer, _Conv1D):
             Q = Q.t()
         self.layer.weight.data = Q.reshape(self.layer.weight.shape).to(self.layer.weight.data.dtype)
@@ -277,14 +285,22 @@ class GPTQ:
         sh.factor[key] = fac
         return fac
 
-    def _solve_fused_raw(self, W, Hinv, ut=None):
+    def _solve_fused_raw(self, W, Hinv, ut=None, emit=False):
         """queue gptq.py:106-165 for the rows in W (msq_gptq_solve_f32); returns device tensors, no host sync:
-        (Q, loss[1] fp64, counters int32 [2*cols + 3] = zeros[cols] | kcnt[cols] | status | violation | info)"""
+        (Q, loss[1] fp64, counters int32 [2*cols + 3] = zeros[cols] | kcnt[cols] | status | violation | info).
+        emit=True also keeps the quantizer's own artefact (code bytes, bitmap, block exponents) in self._emitted."""
         q = self.quantizer
         dev = W.device
         rows, cols = W.shape
         fi, fo = _ops.fmt4(q.inlier_elem_format), _ops.fmt4(q.outlier_elem_format)
         Q = torch.empty_like(W)
+        em = None
+        if emit and cols % 32 == 0 and rows % int(q.block_size) == 0:
+            nbk = (rows // int(q.block_size)) * cols
+            em = dict(codes8=torch.empty(rows, cols, dtype=torch.uint8, device=dev),
+                      bitmap=torch.empty(rows * cols // 32, dtype=torch.int32, device=dev),
+                      e_in=torch.empty(nbk, dtype=torch.int8, device=dev), e_out=torch.empty(nbk, dtype=torch.int8, device=dev))
+        self._emitted = em
         L, s = N.lib(), N.stream_ptr(dev)
         nws = int(L.msq_gptq_solve_workspace_bytes(rows))
         ws = _tc._workspace(nws, dev)
@@ -301,16 +317,39 @@ class GPTQ:
                                   N.ptr(zeros), N.ptr(kcnt), N.ptr(status), N.ptr(viol), int(q.block_size),
                                   int(q.inlier_scale_bits), int(q.outlier_scale_bits), fi[0], fi[1], fi[2], fi[3],
                                   fo[0], fo[1], fo[2], fo[3], float(q.std_dev), int(bool(q.flush_fp32_subnorms)),
-                                  _ops._rmode(q.round), s)
+                                  _ops._rmode(q.round), N.ptr(em["codes8"]) if em else None,
+                                  N.ptr(em["bitmap"]) if em else None, N.ptr(em["e_in"]) if em else None,
+                                  N.ptr(em["e_out"]) if em else None, s)
         N.check(rc, "msq_gptq_solve_f32")
         return Q, loss, counters
+
+    def _packed_from_emitted(self, rows, cols):
+        """PackedMX of the GPTQ result from the column kernel's own codes (msq_pack_from_codes): dequantize() == Q"""
+        from ..packed import PackedMX, _alloc_planes
+        em, q = self._emitted, self.quantizer
+        if em is None:
+            return None
+        fi, fo = _ops.fmt4(q.inlier_elem_format), _ops.fmt4(q.outlier_elem_format)
+        bs = int(q.block_size)
+        ref = em["codes8"]
+        pl, wi, hi_w, stride, nseg = _alloc_planes(ref, 1, rows, cols, bs, fi, fo, False)
+        rc = N.lib().msq_pack_from_codes(N.ptr(em["codes8"]), N.ptr(em["bitmap"]), 1, rows, cols, bs, fi[0], fi[1], fo[0],
+                                         fo[1], N.ptr(pl["codes"]), N.ptr(pl["hi"]), N.ptr(pl["seg_cnt"]),
+                                         N.stream_ptr(ref.device))
+        N.check(rc, "msq_pack_from_codes")
+        pl["bitmap"], pl["e_in"], pl["e_out"] = em["bitmap"], em["e_in"], em["e_out"]
+        self._emitted = None
+        return PackedMX(shape=(rows, cols), axis=0, block_size=bs, in_fmt=q.inlier_elem_format,
+                        out_fmt=q.outlier_elem_format, in_scale_bits=q.inlier_scale_bits,
+                        out_scale_bits=q.outlier_scale_bits, code_width=wi, hi_w=hi_w, hi_seg_stride=stride, nseg=nseg,
+                        plain=False, path=4, status=None, **pl)
 
     def _solve_fused(self, W, Hinv, ut=None, info=None):
         """gptq.py:106-165 as ONE queued call (msq_gptq_solve_f32): per 128-column block the two-warp column kernel and
         the trailing update; returns (Q, loss) or (None, None) when the prune would have changed values (then the
         generic path must run)."""
-        cols = W.shape[1]
-        Q, loss, counters = self._solve_fused_raw(W, Hinv, ut)
+        rows, cols = W.shape
+        Q, loss, counters = self._solve_fused_raw(W, Hinv, ut, emit=self.emit_packed)
         if info is not None:                          # pivot check of the native factorization rides on the same read
             counters[2 * cols + 2:] = info
         flags = counters[2 * cols:].tolist()          # one host sync per linear
@@ -318,7 +357,9 @@ class GPTQ:
             raise torch.linalg.LinAlgError("GPTQ: the damped Hessian is not positive-definite (leading minor %d)" % flags[2])
         _ops.raise_on_status(flags[0])
         if flags[1] != 0 and self.prune:
+            self._emitted = None
             return None, None
+        self.packed = self._packed_from_emitted(rows, cols)
         return Q, float(loss.item())
 
     def _solve_generic(self, W, Hinv, blocksize, groupsize, actorder, static_groups, groups, perm):

@@ -154,7 +154,7 @@ def _run_layer(layer, x, args, kwargs):
 @torch.no_grad()
 def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=.01, groupsize=-1, act_order=False,
                         static_groups=False, true_sequential=False, hessian_batch=8, verbose=False, stats=None, overlap_moves=False,
-                        share_hessians=True, forward_batch=8, release_cache=False):
+                        share_hessians=True, forward_batch=8, release_cache=False, packed_out=None):
     """llama_sequential / opt_sequential (llm/llama.py:62-173, llm/opt.py:26-128).
     nearest=True is the RTN branch (llm/llama.py:226-253): every linear is replaced by
     quantize_mx_outlier_v1(W) without calibration.  Returns {layer name: quantizer}.
@@ -168,7 +168,9 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
     forward_batch: calibration samples pushed through the layer per call (the reference uses 1, llm/llama.py:147;
     the Hessian is a sum over tokens, so batching only changes how many kernels are launched).  share_hessians: one
     Hessian + one factorization for linears that receive the same tensor (q/k/v, gate/up).  release_cache: call
-    torch.cuda.empty_cache() after every linear like gptq.py:191 (off: the solver workspaces are reused)."""
+    torch.cuda.empty_cache() after every linear like gptq.py:191 (off: the solver workspaces are reused).
+    packed_out: a dict that receives {"layers.<i>.<name>": PackedMX} -- the packed artefact of every linear this rank
+    solved on the fused path (packed.save_packed writes them to disk, MXLinear.from_packed runs them)."""
     qcfg = dict(REFERENCE_QCFG if qcfg is None else qcfg)
     layers, _, _, _ = decoder_parts(model)
     stats = stats if stats is not None else {}
@@ -243,6 +245,7 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
                 gptq[name].hessian_batch = max(1, hessian_batch // forward_batch)
                 gptq[name].verbose = verbose
                 gptq[name].release_cache_on_free = release_cache
+                gptq[name].emit_packed = packed_out is not None
                 gptq[name].quantizer = MXQuantizer()
                 gptq[name].quantizer.configure(**qcfg)
 
@@ -299,6 +302,8 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
                     gptq[name].fasterquant(percdamp=percdamp, groupsize=groupsize, actorder=act_order,
                                            static_groups=static_groups)
                     stats["linears"] += 1
+                    if packed_out is not None and gptq[name].packed is not None:
+                        packed_out["layers.%d.%s" % (i, name)] = gptq[name].packed
                 gptq[name].free()
             torch.cuda.synchronize()
             stats["solve_s"] += time.perf_counter() - t0

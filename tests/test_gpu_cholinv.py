@@ -35,8 +35,8 @@ def test_split_gemm_against_fp64(M, m, n, k):
     bound = 4 * k * 2.0 ** -24 * (A.double().abs() @ B.double().abs().t()) + 1e-30
     assert bool(((Cm.double() - ref).abs() <= bound).all()), float(((Cm.double() - ref).abs() / bound).max())
     # alpha / beta epilogue
-    C0 = torch.randn(m, (n + 3) // 4 * 4, generator=g).cuda()[:, :n]
-    C1 = C0.clone()
+    Cfull = torch.randn(m, (n + 3) // 4 * 4, generator=g).cuda()          # rows stay 16-byte aligned
+    C0, C1 = Cfull[:, :n].clone(), Cfull[:, :n]
     _tc.gemm_split3(A, B, out=C1, alpha=-1.0, beta=1.0)
     assert bool(((C1.double() - (C0.double() - ref)).abs() <= bound + 2.0 ** -23 * C0.double().abs()).all())
 
@@ -125,8 +125,9 @@ def test_two_warp_column_kernel_is_bit_identical_to_the_one_warp_kernel(M, rows,
     assert abs(loss - lr) <= 1e-9 * abs(lr)
 
 
-@pytest.mark.parametrize("rows,cols", [(512, 384), (4096, 1024), (300, 1160)])
-def test_tensor_core_trailing_update_against_oracle(M, rows, cols):
+@pytest.mark.parametrize("rows,cols,fi,fo", [(512, 384, "int2", "fp4"), (4096, 1024, "fp4_e2m1", "fp8_e4m3"),
+                                            (300, 1160, "int2", "fp4")])
+def test_tensor_core_trailing_update_against_oracle(M, rows, cols, fi, fo):
     """trailing update on tcgen05 (split planes): first GPTQ block bit-exact (no trailing update involved), whole
     matrix within the GPTQ tolerance of DESIGN.md (<= 1 % differing entries, loss within 1 %) of the oracle fed the
     same Hinv; and the update itself within 4 K 2^-24 |Err||Hinv| of fp64."""
@@ -137,10 +138,9 @@ def test_tensor_core_trailing_update_against_oracle(M, rows, cols):
     layer = torch.nn.Linear(cols, rows, bias=False).cuda()
     gq = M.GPTQ(layer)
     gq.quantizer = M.MXQuantizer()
-    gq.quantizer.configure(8, 8, "fp4_e2m1", "fp8_e4m3", axes=[0], block_size=16)
+    gq.quantizer.configure(8, 8, fi, fo, axes=[0], block_size=16)
     Q, loss = gq._solve_fused(W.cuda().clone(), Hinv)
-    cfg = dict(inlier_scale_bits=8, outlier_scale_bits=8, inlier_elem_format="fp4_e2m1", outlier_elem_format="fp8_e4m3",
-               block_size=16)
+    cfg = dict(inlier_scale_bits=8, outlier_scale_bits=8, inlier_elem_format=fi, outlier_elem_format=fo, block_size=16)
     Qo, loss_o, info = O.fasterquant(W, Hinv.cpu(), cfg, 128)
     assert Q is not None and info["columns_with_zeros_lt_k"] == 0
     assert_exact(Q[:, :128], Qo[:, :128], "first block")
@@ -205,3 +205,37 @@ def test_shared_hessian_gives_identical_weights(M):
     a, b = run(False), run(True)
     for x, y in zip(a, b):
         assert_exact(x, y)
+
+
+@pytest.mark.parametrize("rows,cols,fi,fo,bs", [(512, 384, "fp4_e2m1", "fp8_e4m3", 16), (1024, 1280, "int2", "fp4", 16),
+                                               (256, 1056, "fp4_e2m1", "fp8_e4m3", 32)])
+def test_gptq_emits_its_own_packed_artefact(M, rows, cols, fi, fo, bs):
+    """quantize -> GEMM without a detour: fasterquant(emit_packed) keeps the column kernel's codes, bitmap and block
+    exponents; msq_pack_from_codes lays them out as the standard planes.  unpack(planes) must be the GPTQ result bit for
+    bit (it is NOT a re-quantization of Q) and the row-block GEMM must run on it."""
+    from msq_b200 import _tc
+    g = torch.Generator().manual_seed(rows + cols)
+    W = torch.randn(rows, cols, generator=g) * 0.02
+    X = torch.randn(2, 512, cols, generator=g).half()
+    layer = torch.nn.Linear(cols, rows, bias=False).cuda()
+    layer.weight.data = W.clone().cuda()
+    gq = M.GPTQ(layer)
+    gq.emit_packed = True
+    gq.quantizer = M.MXQuantizer()
+    gq.quantizer.configure(8, 8, fi, fo, axes=[0], block_size=bs)
+    for b in range(2):
+        gq.add_batch(X[b:b + 1].cuda(), None)
+    gq.fasterquant()
+    if gq.last_path != "fused":
+        pytest.skip("prune is not a no-op for this configuration")
+    pw = gq.packed
+    assert pw is not None and pw.axis == 0 and pw.block_size == bs
+    assert_exact(pw.dequantize(), layer.weight.data.float(), "unpack(GPTQ artefact)")
+    # seg_cnt / hi stream are consistent with the bitmap
+    assert int(pw.seg_cnt.sum()) == (int(pw.outlier_mask().sum()) if pw.hi_w else 0)
+    x = torch.randn(24, cols, generator=g).to(torch.bfloat16).cuda()
+    y = _tc.packed_linear(x, pw).double().cpu()
+    Wd = layer.weight.data.double().cpu()
+    bound = 4 * cols * 2.0 ** -24 * (x.double().cpu().abs() @ Wd.abs().t()) + 1e-30
+    assert bool(((y - x.double().cpu() @ Wd.t()).abs() <= bound).all())
+    gq.free()

@@ -72,9 +72,9 @@ def test_rowblock_gemm_other_dtypes_large_m_and_fallback(M):
         bound = 4 * K * 2.0 ** -24 * (x.double().cpu().abs() @ Wd.abs().t()) + 1e-6
         assert bool(((y - ref).abs() <= bound).all())
     # a geometry the kernel does not cover (rows not a multiple of the block, ragged K) goes through unpack + dense GEMM
-    pw2 = M.pack_mx_outlier(weights(200, 72, 3).cuda(), 8, 8, "fp4_e2m1", "fp8_e4m3", 2, [0], 16)
+    pw2 = M.pack_mx_outlier(weights(200, 96, 3).cuda(), 8, 8, "fp4_e2m1", "fp8_e4m3", 2, [0], 16)
     assert not _tc.rowblock_ok(pw2)
-    x = torch.randn(5, 72, generator=g).to(torch.bfloat16).cuda()
+    x = torch.randn(5, 96, generator=g).to(torch.bfloat16).cuda()
     y = _tc.packed_linear(x, pw2).double().cpu()
     Wd2 = pw2.dequantize().double().cpu()
     assert float((y - x.double().cpu() @ Wd2.t()).abs().max()) <= 1e-4
