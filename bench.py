@@ -221,6 +221,8 @@ def extras(dev, dev_w, nel):
     # same solves with the reference's own route to Hinv (three cuSOLVER calls through torch.linalg) for comparison
     t_lib = 0.0
     msq_b200.GPTQ.hinv_method = "reference"
+    _w = torch.eye(512, device=dev)
+    torch.linalg.cholesky(torch.cholesky_inverse(torch.linalg.cholesky(_w)), upper=True)        # cuSOLVER handles, untimed
     for i, (name, r, c) in enumerate(LAYER_SHAPES):
         layer = torch.nn.Linear(c, r, bias=False, device=dev, dtype=torch.float16)
         layer.weight.data = dev_w[i].half()
@@ -300,12 +302,19 @@ def leg_gptq_model(dev, rank, world, dist, layers=4, nsamples=128, seqlen=2048, 
     LLaMA-2-7B decoder layers, 128 x 2048 synthetic tokens split over the ranks, per-rank tcgen05 Hessians, NCCL
     allreduce, solves spread over the ranks, quantized weights broadcast.  Wall time, max over ranks."""
     from msq_b200.llm import sequential as S
+    qcfg = qcfg or dict(inlier_scale_bits=8, outlier_scale_bits=8, inlier_elem_format=QCFG["in_fmt"],
+                        outlier_elem_format=QCFG["out_fmt"], axes=[0], block_size=QCFG["bs"])
+    # untimed warm-up on one layer / 8 samples per rank: CUDA module loading, cuBLAS / NCCL initialisation and the
+    # allocator's first growth would otherwise be multiplied by 32 / layers in the extrapolation
+    warm = build_llama(1, dev)
+    warm.seqlen = seqlen
+    gw = torch.Generator().manual_seed(4)
+    S.sequential_quantize(warm, [torch.randint(0, 32000, (1, seqlen), generator=gw) for _ in range(8 * world)], dev, qcfg=qcfg)
+    del warm
     model = build_llama(layers, dev)
     model.seqlen = seqlen
     gc = torch.Generator().manual_seed(3)
     calib = [torch.randint(0, 32000, (1, seqlen), generator=gc) for _ in range(nsamples)]
-    qcfg = qcfg or dict(inlier_scale_bits=8, outlier_scale_bits=8, inlier_elem_format=QCFG["in_fmt"],
-                        outlier_elem_format=QCFG["out_fmt"], axes=[0], block_size=QCFG["bs"])
     stats = {}
     torch.cuda.synchronize()
     if dist is not None:

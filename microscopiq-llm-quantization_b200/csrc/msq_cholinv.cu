@@ -26,8 +26,6 @@ namespace msq {
 namespace ci {
 
 constexpr int LB = 128;        // leaf size
-constexpr int LS = LB + 1;     // shared-memory row stride (conflict-free column walks)
-constexpr int LEAF_SMEM = 2 * LB * LS * (int)sizeof(float);
 
 __device__ __forceinline__ void split3(float v, __nv_bfloat16& p0, __nv_bfloat16& p1, __nv_bfloat16& p2) {
   p0 = __float2bfloat16_rn(v);
@@ -75,71 +73,120 @@ struct LeafParams {
   int* info;
 };
 
+// acc[a][j] = sum_{k < K} A[(tr + 32 a) * lda + k] * B[(tc + 8 j) * ldb + k]     (tr = tid / 8, tc = tid % 8)
+// A . B^T from shared memory with both operands contiguous in k: 7 LDS.128 feed 48 FMAs per 4 k; the row -> thread
+// maps keep the 16-byte accesses of a quarter warp on distinct banks (row pitch 132 words).
+__device__ __forceinline__ void nt_tile(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int M,
+                                        int K, int tr, int tc, float (&acc)[3][4]) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[a][j] = 0.0f;
+  const bool r1 = tr + 32 < M, r2 = tr + 64 < M;
+  if (tr >= M) return;
+  for (int k = 0; k < K; k += 4) {
+    float4 av[3], bv[4];
+    av[0] = *reinterpret_cast<const float4*>(A + tr * lda + k);
+    av[1] = r1 ? *reinterpret_cast<const float4*>(A + (tr + 32) * lda + k) : make_float4(0, 0, 0, 0);
+    av[2] = r2 ? *reinterpret_cast<const float4*>(A + (tr + 64) * lda + k) : make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(B + (tc + 8 * j) * ldb + k);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[a][j] = fmaf(av[a].x, bv[j].x, acc[a][j]);
+        acc[a][j] = fmaf(av[a].y, bv[j].y, acc[a][j]);
+        acc[a][j] = fmaf(av[a].z, bv[j].z, acc[a][j]);
+        acc[a][j] = fmaf(av[a].w, bv[j].w, acc[a][j]);
+      }
+  }
+}
+
+constexpr int UTS = 36;    // row pitch of the transposed 32 x 32 diagonal inverse
+constexpr int TTS = 100;   // row pitch of T^T (32 x <= 96)
+constexpr int LEAF_SMEM2 = (2 * LB * 132 + 32 * UTS + 32 * TTS) * (int)sizeof(float);
+
 __global__ void __launch_bounds__(256, 1) k_chol_leaf(const LeafParams P) {
-  extern __shared__ float sm_leaf[];
-  float* As = sm_leaf;
-  float* Us = sm_leaf + LB * LS;
+  extern __shared__ __align__(16) float sm_leaf[];
+  constexpr int S = 132;             // row pitch: 16-byte aligned rows
+  float* As = sm_leaf;               // [128][S]  A -> R
+  float* Us = sm_leaf + LB * S;      // [128][S]  U = R^-1
+  float* UTd = Us + LB * S;          // [32][UTS] transpose of the current diagonal block of U
+  float* TT = UTd + 32 * UTS;        // [32][TTS] (R12 U22)^T
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tr = tid >> 3, tc = tid & 7;
   const int m = P.m;
   for (int idx = tid; idx < LB * LB; idx += 256) {
     const int i = idx >> 7, k = idx & 127;
     float v = 0.0f;
     if (i < m && k < m && i <= k) v = P.A[(long long)(P.o + i) * P.lda + P.o + k];
     else if (i == k) v = 1.0f;                           // identity padding
-    As[i * LS + k] = v;
-    Us[i * LS + k] = 0.0f;
+    As[i * S + k] = v;
+    Us[i * S + k] = 0.0f;
   }
   __syncthreads();
 
-  // phase 1: A = R R^T, diagonal sub-blocks also inverted
+  // phase 1: A = R R^T from the last 32-column block to the first; diagonal blocks are inverted on the way
   for (int jb = 3; jb >= 0; --jb) {
     const int c0 = jb * 32;
     if (warp == 0) {
       float a[32], u[32];
 #pragma unroll
-      for (int k = 0; k < 32; ++k) { a[k] = k >= lane ? As[(c0 + lane) * LS + c0 + k] : 0.0f; u[k] = 0.0f; }
+      for (int k = 0; k < 32; ++k) { a[k] = k >= lane ? As[(c0 + lane) * S + c0 + k] : 0.0f; u[k] = 0.0f; }
       const int bad = warp_chol_inv_32(a, u, lane);
       if (bad && lane == 0 && c0 + bad - 1 < m) atomicCAS(P.info, 0, P.o + c0 + bad);
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
-        As[(c0 + lane) * LS + c0 + k] = k >= lane ? a[k] : 0.0f;
-        Us[(c0 + lane) * LS + c0 + k] = u[k];
+        As[(c0 + lane) * S + c0 + k] = k >= lane ? a[k] : 0.0f;
+        Us[(c0 + lane) * S + c0 + k] = u[k];
       }
     }
     __syncthreads();
-    // panel: R[i][c0 + c] = sum_{k >= c} A[i][c0 + k] U_d[c][k]        (R12 = A12 U22^T), one warp per row
-    for (int i = warp; i < c0; i += 8) {
-      float s = 0.0f;
-      for (int k = 0; k < 32; ++k) s = fmaf(As[i * LS + c0 + k], Us[(c0 + lane) * LS + c0 + k], s);
-      __syncwarp();
-      As[i * LS + c0 + lane] = s;
-    }
+    if (c0 == 0) break;
+    // panel: R12 = A12 U22^T   ([c0 x 32], K = 32), buffered in registers (it overwrites its own A operand)
+    float acc[3][4];
+    nt_tile(As + c0, S, Us + c0 * S + c0, S, c0, 32, tr, tc, acc);
     __syncthreads();
-    // trailing: A[i][k] -= sum_c R[i][c0 + c] R[k][c0 + c]   for i <= k < c0
-    for (int idx = tid; idx < c0 * c0; idx += 256) {
-      const int i = idx / c0, k = idx - i * c0;
-      if (i > k) continue;
-      float s = 0.0f;
-      for (int c = 0; c < 32; ++c) s = fmaf(As[i * LS + c0 + c], As[k * LS + c0 + c], s);
-      As[i * LS + k] -= s;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      if (tr + 32 * a < c0)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) As[(tr + 32 * a) * S + c0 + tc + 8 * j] = acc[a][j];
+    __syncthreads();
+    // trailing: A11 -= R12 R12^T, 32-column groups on or above the diagonal
+    for (int g = 0; g < jb; ++g) {
+      nt_tile(As + c0, S, As + (32 * g) * S + c0, S, 32 * (g + 1), 32, tr, tc, acc);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        if (tr + 32 * a < 32 * (g + 1))
+#pragma unroll
+          for (int j = 0; j < 4; ++j) As[(tr + 32 * a) * S + 32 * g + tc + 8 * j] -= acc[a][j];
     }
     __syncthreads();
   }
-  // phase 2: off-diagonal blocks of U = R^-1:  U12 = -U11 (R12 U22)
+  // phase 2: off-diagonal blocks of U = R^-1:  U12 = -U11 (R12 U22), block column by block column
   for (int jb = 1; jb < 4; ++jb) {
     const int c0 = jb * 32;
-    for (int i = warp; i < c0; i += 8) {                 // T[i][c] = sum_{k <= c} R[i][c0 + k] U_d[k][c]
-      float s = 0.0f;
-      for (int k = 0; k < 32; ++k) s = fmaf(As[i * LS + c0 + k], Us[(c0 + k) * LS + c0 + lane], s);
-      __syncwarp();
-      As[i * LS + c0 + lane] = s;
+    for (int idx = tid; idx < 32 * 32; idx += 256) {     // transpose of the diagonal inverse: K-contiguous B operand
+      const int r = idx >> 5, c = idx & 31;
+      UTd[c * UTS + r] = Us[(c0 + r) * S + c0 + c];
     }
     __syncthreads();
-    for (int i = warp; i < c0; i += 8) {                 // U[i][c0 + c] = -sum_{k >= i} U[i][k] T[k][c]
-      float s = 0.0f;
-      for (int k = i; k < c0; ++k) s = fmaf(Us[i * LS + k], As[k * LS + c0 + lane], s);
-      Us[i * LS + c0 + lane] = -s;
-    }
+    float acc[3][4];
+    nt_tile(As + c0, S, UTd, UTS, c0, 32, tr, tc, acc);  // T = R12 U22, stored transposed
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      if (tr + 32 * a < c0)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) TT[(tc + 8 * j) * TTS + tr + 32 * a] = acc[a][j];
+    __syncthreads();
+    nt_tile(Us, S, TT, TTS, c0, c0, tr, tc, acc);        // U12 = -U11 T   (K = c0; U11 is upper triangular)
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      if (tr + 32 * a < c0)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Us[(tr + 32 * a) * S + c0 + tc + 8 * j] = -acc[a][j];
     __syncthreads();
   }
   // phase 3: results -- fp32 block of U, planes of U and of U^T (full block, zeros below the diagonal)
@@ -147,13 +194,13 @@ __global__ void __launch_bounds__(256, 1) k_chol_leaf(const LeafParams P) {
   for (int idx = tid; idx < LB * LB; idx += 256) {
     const int i = idx >> 7, k = idx & 127;
     if (i >= m || k >= m) continue;
-    const float v = Us[i * LS + k];                      // 0 for i > k
+    const float v = Us[i * S + k];                       // 0 for i > k
     P.U[(long long)(P.o + i) * P.ldu + P.o + k] = v;
     __nv_bfloat16 b0, b1, b2;
     split3(v, b0, b1, b2);
     __nv_bfloat16* p = P.PU + (long long)(P.o + i) * P.ldp + P.o + k;
     p[0] = b0; p[ps] = b1; p[2 * ps] = b2;
-    const float vt = Us[k * LS + i];                     // U^T[i][k]
+    const float vt = Us[k * S + i];                      // U^T[i][k]
     split3(vt, b0, b1, b2);
     __nv_bfloat16* q = P.PUT + (long long)(P.o + i) * P.ldp + P.o + k;
     q[0] = b0; q[ps] = b1; q[2 * ps] = b2;
@@ -203,7 +250,7 @@ static void rec(Ctx& c, int lo_b, int hi_b) {
     LeafParams P;
     P.A = c.A; P.lda = c.lda; P.U = c.U; P.ldu = c.ldu; P.PU = c.PU; P.PUT = c.PUT; P.ldp = c.L.ldp;
     P.plane_rows = c.L.nA; P.o = lo_b * LB; P.m = min(LB, n - P.o); P.info = c.info;
-    k_chol_leaf<<<1, 256, LEAF_SMEM, c.s>>>(P);
+    k_chol_leaf<<<1, 256, LEAF_SMEM2, c.s>>>(P);
     if (cudaGetLastError() != cudaSuccess) c.rc = MSQ_ERR_CUDA;
     return;
   }
@@ -303,7 +350,7 @@ int msq_cholinv_upper_f32(float* H, long long ldh, float* U, long long ldu, int 
   // blocks strictly below the diagonal are read as part of 256-wide tiles: they must hold zeros
   if (cudaMemsetAsync(c.PU, 0, c.L.stack_elems * 2, c.s) != cudaSuccess) return MSQ_ERR_CUDA;
   if (cudaMemsetAsync(c.PUT, 0, c.L.stack_elems * 2, c.s) != cudaSuccess) return MSQ_ERR_CUDA;
-  if (cudaFuncSetAttribute(ci::k_chol_leaf, cudaFuncAttributeMaxDynamicSharedMemorySize, ci::LEAF_SMEM) != cudaSuccess)
+  if (cudaFuncSetAttribute(ci::k_chol_leaf, cudaFuncAttributeMaxDynamicSharedMemorySize, ci::LEAF_SMEM2) != cudaSuccess)
     return MSQ_ERR_CUDA;
   int rc = 0;
   rc |= split3_make_tmap(&c.mPU_a, c.PU, 3LL * c.L.nA, n, c.L.ldp, 128);

@@ -189,6 +189,14 @@ class GPTQ:
         return _ops.fmt4(q.inlier_elem_format)[0] <= 5 and _ops.fmt4(q.outlier_elem_format)[0] <= 5
 
     def fasterquant(self, blocksize=128, percdamp=.01, groupsize=-1, actorder=False, static_groups=False):
+        st = self._fq_launch(blocksize, percdamp, groupsize, actorder, static_groups)
+        self._fq_finish(st)
+        torch.cuda.synchronize()                           # gptq.py:173
+
+    def _fq_launch(self, blocksize=128, percdamp=.01, groupsize=-1, actorder=False, static_groups=False):
+        """first half of fasterquant: everything up to the queued fused solve (no host synchronisation), on the
+        current stream.  _fq_finish completes it.  The layer-sequential driver launches the independent linears of a
+        layer on separate streams this way (the column kernel is latency bound and fills a fraction of the SMs)."""
         W = self.layer.weight.data.clone()
         if isinstance(self.layer, nn.Conv2d):
             W = W.flatten(1)
@@ -203,7 +211,7 @@ class GPTQ:
             self.quantizer.find_params(W, weight=True)
 
         fac = self._factorize(percdamp, actorder)
-        dead, perm, invperm, Hinv = fac["dead"], fac["perm"], fac["invperm"], fac["Hinv"]
+        dead, perm = fac["dead"], fac["perm"]
         W.masked_fill_(dead.unsqueeze(0), 0)               # W[:, dead] = 0
 
         groups = None
@@ -218,21 +226,32 @@ class GPTQ:
         if actorder:
             W = W[:, perm].contiguous()
 
-        Q = None
+        raw = None
         if self._fused_ok() and blocksize == 128:
-            Q, loss = self._solve_fused(W.clone(), Hinv, fac["ut"], fac["info"])
+            raw = self._solve_fused_raw(W.clone(), fac["Hinv"], fac["ut"], emit=self.emit_packed)
+        return dict(tick=tick, W=W, fac=fac, raw=raw, groups=groups,
+                    args=(blocksize, groupsize, actorder, static_groups))
+
+    def _fq_finish(self, st):
+        """second half of fasterquant: read the flags of the fused solve (one host sync), fall back to the
+        column-synchronous path if the prune was not a no-op, write the weight back"""
+        W, fac = st["W"], st["fac"]
+        blocksize, groupsize, actorder, static_groups = st["args"]
+        perm, invperm, Hinv = fac["perm"], fac["invperm"], fac["Hinv"]
+        Q = None
+        if st["raw"] is not None:
+            Q, loss = self._solve_fused_check(st["raw"], W.shape, fac["info"])
             self.last_path = "fused"
         if Q is None:
             if fac["info"] is not None and int(fac["info"].item()):
                 raise torch.linalg.LinAlgError("GPTQ: the damped Hessian is not positive-definite (leading minor %d)"
                                                % int(fac["info"].item()))
-            Q, loss = self._solve_generic(W, Hinv, blocksize, groupsize, actorder, static_groups, groups, perm)
+            Q, loss = self._solve_generic(W, Hinv, blocksize, groupsize, actorder, static_groups, st["groups"], perm)
             self.last_path = "generic"
 
-        torch.cuda.synchronize()
         self.last_error = loss
         if self.verbose:
-            print('time %.2f' % (time.time() - tick))
+            print('time %.2f' % (time.time() - st["tick"]))
             print('error', loss)
 
         if actorder:
@@ -344,12 +363,10 @@ class GPTQ:
                         out_scale_bits=q.outlier_scale_bits, code_width=wi, hi_w=hi_w, hi_seg_stride=stride, nseg=nseg,
                         plain=False, path=4, status=None, **pl)
 
-    def _solve_fused(self, W, Hinv, ut=None, info=None):
-        """gptq.py:106-165 as ONE queued call (msq_gptq_solve_f32): per 128-column block the two-warp column kernel and
-        the trailing update; returns (Q, loss) or (None, None) when the prune would have changed values (then the
-        generic path must run)."""
-        rows, cols = W.shape
-        Q, loss, counters = self._solve_fused_raw(W, Hinv, ut, emit=self.emit_packed)
+    def _solve_fused_check(self, raw, shape, info=None):
+        """host side of the fused solve: one read of (status, violation, info); (Q, loss) or (None, None)"""
+        Q, loss, counters = raw
+        rows, cols = shape
         if info is not None:                          # pivot check of the native factorization rides on the same read
             counters[2 * cols + 2:] = info
         flags = counters[2 * cols:].tolist()          # one host sync per linear
@@ -361,6 +378,13 @@ class GPTQ:
             return None, None
         self.packed = self._packed_from_emitted(rows, cols)
         return Q, float(loss.item())
+
+    def _solve_fused(self, W, Hinv, ut=None, info=None):
+        """gptq.py:106-165 as ONE queued call (msq_gptq_solve_f32): per 128-column block the two-warp column kernel and
+        the trailing update; returns (Q, loss) or (None, None) when the prune would have changed values (then the
+        generic path must run)."""
+        raw = self._solve_fused_raw(W, Hinv, ut, emit=self.emit_packed)
+        return self._solve_fused_check(raw, W.shape, info)
 
     def _solve_generic(self, W, Hinv, blocksize, groupsize, actorder, static_groups, groups, perm):
         """column-synchronous path: gptq.py:106-165 statement by statement, on the GPU"""

@@ -46,27 +46,69 @@ class _Stop(Exception):
 
 
 class LayerMover(object):
-    """Streams decoder layers between host and device around the per-layer work (the reference moves them
-    synchronously, llm/llama.py:94 / :168): layer i+1 is uploaded and layer i-1 downloaded by a background thread on
-    a side stream while layer i is being quantized.  Ordering is by CUDA events: the compute stream waits for an
-    upload before touching the layer, a download waits for the layer's last use.
-    Opt-in (sequential_quantize(overlap_moves=True)): on a LLaMA-2-7B-shaped run it hides the 7.3 s of layer moves
-    (move_s 7.4 -> 0.3 s) but the launch-bound solves of the same run were slower (36.8 s against 19.7-23.9 s in the
-    synchronous runs; boxes differ, so this is unconfirmed), so the net effect is not established."""
+    """Moves decoder layers between host and device around the per-layer work (the reference does `layer.to(dev)` /
+    `layer.cpu()`, llm/llama.py:94 / :168, which allocates -- and page-faults -- a fresh host copy of every layer).
+    Here the host tensors stay where they are: `fetch` uploads them (through one reusable pinned staging buffer, so
+    the copy runs at PCIe speed) and `offload` copies the device values back INTO the original host storage.
+    With enabled=True (sequential_quantize(overlap_moves=True)) layer i+1 is uploaded and layer i-1 downloaded by a
+    background thread on a side stream while layer i is being quantized; ordering is by CUDA events."""
 
     def __init__(self, layers, dev, enabled=True):
         self.layers, self.dev = layers, dev
-        self.enabled = enabled and dev.type == "cuda"
+        self.cuda = dev.type == "cuda"
+        self.enabled = enabled and self.cuda
         self.pending, self.offloads = {}, []
+        self.host = {}             # layer index -> {param/buffer name: host tensor} (the original storage)
+        self.stage = None
         if self.enabled:
             from concurrent.futures import ThreadPoolExecutor
             self.stream = torch.cuda.Stream(dev)
             self.pool = ThreadPoolExecutor(max_workers=1)
 
+    def _staging(self, nbytes):
+        if self.stage is None or self.stage.numel() < nbytes:
+            self.stage = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        return self.stage
+
+    def _to_device(self, i):
+        layer = self.layers[i]
+        if not self.cuda:
+            return layer.to(self.dev)
+        host = {}
+        tensors = [(n, p) for n, p in list(layer.named_parameters()) + list(layer.named_buffers()) if not p.is_cuda]
+        total = sum((p.numel() * p.element_size() + 255) // 256 * 256 for _, p in tensors)
+        stage = self._staging(max(total, 1))
+        off = 0
+        with torch.no_grad():
+            for n, p in tensors:
+                nb = p.numel() * p.element_size()
+                view = stage[off: off + nb].view(p.dtype).reshape(p.shape)
+                view.copy_(p.data)                                   # host -> pinned
+                host[n] = p.data
+                p.data = view.to(self.dev, non_blocking=True)        # pinned -> device at PCIe speed
+                off += (nb + 255) // 256 * 256
+        torch.cuda.current_stream(self.dev).synchronize()             # the staging buffer is reused by the next layer
+        self.host[i] = host
+        return layer
+
+    def _to_host(self, i, layer):
+        host = self.host.pop(i, None)
+        if host is None or not self.cuda:
+            return layer.cpu()
+        with torch.no_grad():
+            for n, p in list(layer.named_parameters()) + list(layer.named_buffers()):
+                h = host.get(n)
+                if h is None or h.shape != p.shape:
+                    p.data = p.data.cpu()
+                    continue
+                h.copy_(p.data.to(h.dtype))                          # back into the ORIGINAL host storage
+                p.data = h
+        return layer
+
     def _upload(self, i):
         torch.cuda.set_device(self.dev)
         with torch.cuda.stream(self.stream):
-            layer = self.layers[i].to(self.dev)
+            layer = self._to_device(i)
             ev = torch.cuda.Event()
             ev.record(self.stream)
         return layer, ev
@@ -78,7 +120,7 @@ class LayerMover(object):
     def fetch(self, i):
         """layer i on the device, usable on the current stream"""
         if not self.enabled:
-            return self.layers[i].to(self.dev)
+            return self._to_device(i)
         self.prefetch(i)
         layer, ev = self.pending.pop(i).result()
         torch.cuda.current_stream(self.dev).wait_event(ev)
@@ -88,12 +130,12 @@ class LayerMover(object):
         torch.cuda.set_device(self.dev)
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ev)
-            self.layers[i] = layer.cpu()
+            self.layers[i] = self._to_host(i, layer)
 
     def offload(self, i, layer):
         """send layer i back to the host once everything queued on the current stream has used it"""
         if not self.enabled:
-            self.layers[i] = layer.cpu()
+            self.layers[i] = self._to_host(i, layer)
             return
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.dev))
@@ -154,7 +196,8 @@ def _run_layer(layer, x, args, kwargs):
 @torch.no_grad()
 def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=.01, groupsize=-1, act_order=False,
                         static_groups=False, true_sequential=False, hessian_batch=8, verbose=False, stats=None, overlap_moves=False,
-                        share_hessians=True, forward_batch=8, release_cache=False, packed_out=None):
+                        share_hessians=True, forward_batch=8, release_cache=False, packed_out=None,
+                        solve_streams_n=3):
     """llama_sequential / opt_sequential (llm/llama.py:62-173, llm/opt.py:26-128).
     nearest=True is the RTN branch (llm/llama.py:226-253): every linear is replaced by
     quantize_mx_outlier_v1(W) without calibration.  Returns {layer name: quantizer}.
@@ -169,6 +212,7 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
     the Hessian is a sum over tokens, so batching only changes how many kernels are launched).  share_hessians: one
     Hessian + one factorization for linears that receive the same tensor (q/k/v, gate/up).  release_cache: call
     torch.cuda.empty_cache() after every linear like gptq.py:191 (off: the solver workspaces are reused).
+    solve_streams_n: side streams the independent column loops of a layer are queued on (0 = one after the other).
     packed_out: a dict that receives {"layers.<i>.<name>": PackedMX} -- the packed artefact of every linear this rank
     solved on the fused path (packed.save_packed writes them to disk, MXLinear.from_packed runs them)."""
     qcfg = dict(REFERENCE_QCFG if qcfg is None else qcfg)
@@ -184,6 +228,7 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
             assert hi > lo, "fewer calibration batches than ranks"
             batches = batches[lo:hi]
     mover = LayerMover(layers, dev, overlap_moves)
+    solve_streams = [torch.cuda.Stream(dev) for _ in range(max(0, solve_streams_n))] if dev.type == "cuda" else []
     if nearest:
         for i in range(len(layers)):
             layer = mover.fetch(i)
@@ -296,14 +341,29 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
                 torch.cuda.synchronize()
                 stats["comm_s"] += time.perf_counter() - t0
             t0 = time.perf_counter()
+            mine = [n for n in subset if owners[n] == rank]
+            # factor every distinct Hessian once on the main stream, then queue the independent column loops on side
+            # streams (a column kernel keeps one or two warps per SM busy: several of them overlap) and collect them
+            main = torch.cuda.current_stream(dev)
+            for name in mine:
+                gptq[name]._factorize(percdamp, act_order)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            launched = []
+            for k, name in enumerate(mine):
+                sstream = solve_streams[k % len(solve_streams)] if solve_streams else main
+                sstream.wait_event(ready)
+                with torch.cuda.stream(sstream):
+                    launched.append((name, sstream, gptq[name]._fq_launch(128, percdamp, groupsize, act_order, static_groups)))
+            for name, sstream, st in launched:
+                with torch.cuda.stream(sstream):
+                    gptq[name]._fq_finish(st)
+                main.wait_stream(sstream)
+                stats["linears"] += 1
+                if packed_out is not None and gptq[name].packed is not None:
+                    packed_out["layers.%d.%s" % (i, name)] = gptq[name].packed
             for name in subset:
                 quantizers["layers.%d.%s" % (i, name)] = gptq[name].quantizer
-                if owners[name] == rank:
-                    gptq[name].fasterquant(percdamp=percdamp, groupsize=groupsize, actorder=act_order,
-                                           static_groups=static_groups)
-                    stats["linears"] += 1
-                    if packed_out is not None and gptq[name].packed is not None:
-                        packed_out["layers.%d.%s" % (i, name)] = gptq[name].packed
                 gptq[name].free()
             torch.cuda.synchronize()
             stats["solve_s"] += time.perf_counter() - t0
