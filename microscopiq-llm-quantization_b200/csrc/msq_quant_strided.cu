@@ -76,7 +76,7 @@ __device__ __forceinline__ void store_codes4_16(uint8_t* codes, const uint32_t* 
 }
 
 template <int BS, bool OUTLIER, bool PACK, bool EXT, bool CNT>
-__global__ void __launch_bounds__(256, (BS <= 16 ? MSQ_STRIDED_MINB : 2)) k_strided(const QParams P) {
+__global__ void __launch_bounds__(256, (BS <= 16 ? (PACK ? 4 : MSQ_STRIDED_MINB) : 2)) k_strided(const QParams P) {
   extern __shared__ uint32_t s_hi[];
   __shared__ int s_warp[8];
   __shared__ int s_base;
