@@ -264,6 +264,17 @@ int msq_gemm_mxfp8_blockscaled(const unsigned char* xcodes, long long ldx, const
                                const signed char* we_out, float* C, long long ldc, int M, int N, int K,
                                int plain, int accumulate, void* stream);
 
+/* FP4-by-TMA variant (decode sizes): the packed 4-bit codes of the weight ARE the tensor-core operand -- TMA expands
+ * 16 codes into a 16-byte chunk (CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B, the layout kind::mxf8f6f4 reads E2M1 from), the
+ * block scale is we_in, no thread touches an inlier -- and the outlier contribution is a fused sparse correction in the
+ * epilogue: CSR over output features (o_ptr [N+1], o_k, o_dw = q * (2^(e_out - e_in) - 2^e_in)); o_ptr NULL = none.
+ * Same contraction and operands as msq_gemm_mxfp8_blockscaled, without its -6 <= e_out - 2 e_in <= 6 restriction.
+ * Needs K % 128 == 0, wcodes 32-byte aligned. */
+int msq_gemm_mxfp4w_blockscaled(const unsigned char* xcodes, long long ldx, const signed char* xe,
+                                const unsigned char* wcodes, const signed char* we_in, const int* o_ptr,
+                                const int* o_k, const float* o_dw, float* C, long long ldc, int M, int N, int K,
+                                int accumulate, void* stream);
+
 /* compute-bound variant of the block-scaled path: widen the packed FP4 weight once to dense MX-FP8
  * (E4M3 bytes [N,K] + UE8M0 scales [N,K/32]), then run the GEMM with both operands streamed by TMA. */
 int msq_widen_fp4_to_mxfp8(const unsigned char* wcodes, const unsigned int* wbitmap, const signed char* we_in,

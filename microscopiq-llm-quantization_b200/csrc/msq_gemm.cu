@@ -271,6 +271,22 @@ int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int
   return r == CUDA_SUCCESS ? MSQ_OK : MSQ_ERR_CUDA;
 }
 
+// packed 4-bit matrix [rows, cols elements] (row pitch in bytes) loaded as CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B: every 16 codes
+// (8 bytes in global memory) land in a 16-byte chunk of shared memory -- the layout tcgen05.mma kind::mxf8f6f4 expects
+// for 4-bit operands.  box = [box_rows, 128 elements]; cols % 128 == 0, base 32-byte aligned, pitch % 32 == 0.
+int make_tmap_2d_u4(CUtensorMap* out, const void* base, long long rows, long long cols, long long row_bytes, int box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return MSQ_ERR_CUDA;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+  cuuint32_t box[2] = {128u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MSQ_OK : MSQ_ERR_CUDA;
+}
+
 static int sm_count() {
   static int n = 0;
   if (!n) {

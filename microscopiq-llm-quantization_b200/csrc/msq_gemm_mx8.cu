@@ -40,6 +40,15 @@ struct Mx8Params {
   int accumulate;
   int wdense;                 // 1: the weight tile comes pre-widened (E4M3 bytes) through TMA, scales from wsf
   const uint8_t* wsf;         // dense mode: UE8M0 weight scales [N, K/32]
+  // FP4-by-TMA mode: the packed 4-bit codes are the A operand as they are (TMA type 16U4_ALIGN16B expands 16 codes
+  // into a 16-byte chunk, the layout kind::mxf8f6f4 reads E2M1 from); scales = we_in; no thread touches a weight.
+  // Outliers (value q * 2^(e_out - e_in) instead of the q * 2^e_in the hardware computes) are a sparse CSR
+  // correction applied by the epilogue warps:  C[m, n] += sum_e x[m, o_k[e]] * o_dw[e]  for e in row n.
+  int wfp4;
+  int w_fmt;                  // tensor-core format code of the weight operand (0 = E4M3, 5 = E2M1)
+  int w_tx_bytes;             // bytes the weight TMA load reports to the mbarrier
+  const int* o_ptr; const int* o_k; const float* o_dw;      // CSR over output features (NULL: no outliers)
+  const uint8_t* xcodes; long long ldx;                     // activation codes as plain memory (for the correction)
 };
 
 __device__ __forceinline__ uint64_t make_sf_desc(uint32_t smem_addr) {
@@ -117,9 +126,9 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
         int tn, tm, kb0, nkb; tile_coords(t, tn, tm, kb0, nkb);
         for (int kb = kb0; kb < kb0 + nkb; ++kb) {
           tc::mbar_wait(&empty[stage], phase ^ 1);
-          tc::mbar_expect_tx(&full[stage], (uint32_t)(P.bnx * XBK + (P.wdense ? XA_BYTES : 0)));
+          tc::mbar_expect_tx(&full[stage], (uint32_t)(P.bnx * XBK + P.w_tx_bytes));
+          if (P.wdense || P.wfp4) tc::tma_load_2d(sA + stage * XA_BYTES, &tmW, &full[stage], kb * XBK, tn * XM);
           tc::tma_load_2d(sB + stage * XB_BYTES, &tmX, &full[stage], kb * XBK, tm * P.bnx);
-          if (P.wdense) tc::tma_load_2d(sA + stage * XA_BYTES, &tmW, &full[stage], kb * XBK, tn * XM);
           if (++stage == XSTAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -143,7 +152,8 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
           const uint64_t bd = tc::make_kmajor_sw128_desc(tc::smem_u32(sB + stage * XB_BYTES));
 #pragma unroll
           for (int k = 0; k < XBK / 32; ++k)      // 32 one-byte elements = 32 bytes = 2 descriptor units per UMMA_K
-            umma_mxf8(tmem_base + TM_ACC, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), make_idesc_mx8(XM, P.bnx, k),
+            umma_mxf8(tmem_base + TM_ACC, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k),
+                      make_idesc_mx8(XM, P.bnx, k) | ((uint32_t)P.w_fmt << 7) /* A format: 5 = E2M1 */,
                       (kb | k) != 0, tmem_base + TM_SFA, tmem_base + TM_SFB);
           tc::umma_commit(&empty[stage]);
           if (++stage == XSTAGES) { stage = 0; phase ^= 1; }
@@ -253,7 +263,8 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
     Cursor fc, cc;
     cur_init(fc); cur_init(cc);
     int stage = 0; uint32_t phase = 0;
-    if (P.wdense) {
+    const bool wtma = P.wdense || P.wfp4;
+    if (wtma) {
       // the weight bytes arrive by TMA; only the two scale-factor chunks are assembled here.  K % 128 == 0 in this
       // mode, so one K-block's four scales are one aligned 32-bit word; the next stage's words are fetched before
       // waiting for the current stage to drain.
@@ -262,7 +273,9 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
         if (!c.ok) return;
         const int kb = c.kb0 + c.kb;
         const int n = c.tn * XM + ptid;
-        if (ptid < XM && n < P.N) va = __ldg(reinterpret_cast<const uint32_t*>(P.wsf + (long long)n * kblk32) + kb);
+        if (ptid < XM && n < P.N)
+          va = P.wfp4 ? __vadd4(__ldg(reinterpret_cast<const uint32_t*>(P.we_in + (long long)n * kblk32) + kb), 0x7F7F7F7Fu)
+                      : __ldg(reinterpret_cast<const uint32_t*>(P.wsf + (long long)n * kblk32) + kb);
         vb = load_sfb(c.tm * P.bnx, kb);
       };
       uint32_t va, vb;
@@ -287,13 +300,13 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
     uint32_t sfb_ring[PF];
 #pragma unroll
     for (int j = 0; j < PF - 1; ++j) {
-      if (!P.wdense && fc.ok) {
+      if (!wtma && fc.ok) {
         fetch(fc.tn * XM, fc.kb0 + fc.kb, ring[j]);
         sfb_ring[j] = load_sfb(fc.tm * P.bnx, fc.kb0 + fc.kb);
         cur_next(fc);
       }
     }
-    while (!P.wdense && cc.ok) {
+    while (!wtma && cc.ok) {
 #pragma unroll
       for (int j = 0; j < PF; ++j) {
         if (cc.ok) {
@@ -318,9 +331,12 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int tn, tm, kb0, nkb; tile_coords(t, tn, tm, kb0, nkb);
+      const int n = tn * XM + q * 32 + lane;
+      // sparse outlier correction: this feature's CSR range is fetched before the accumulator is waited for
+      int oe0 = 0, oe1 = 0;
+      if (P.o_ptr && n < P.N) { oe0 = __ldg(P.o_ptr + n); oe1 = __ldg(P.o_ptr + n + 1); }
       tc::mbar_wait(acc_full, acc_phase);
       tc::tc_fence_after();
-      const int n = tn * XM + q * 32 + lane;
       for (int c = 0; c < P.bnx / 16; ++c) {
         uint32_t r[16];
         asm volatile(
@@ -331,6 +347,25 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
             : "memory");
         tc::tmem_ld_wait();
         if (n < P.N) {
+          if (oe1 > oe0) {    // sparse outlier correction for this (feature, 16 tokens, K slice)
+            const int klo = kb0 * XBK, khi = (kb0 + nkb) * XBK;
+            const int kblk32 = P.K >> 5;
+            for (int e = oe0; e < oe1; ++e) {
+              const int k = __ldg(P.o_k + e);
+              if (k < klo || k >= khi) continue;
+              const float dw = __ldg(P.o_dw + e);
+#pragma unroll
+              for (int v = 0; v < 16; ++v) {
+                const int m = tm * P.bnx + c * 16 + v;
+                if (m < P.M) {
+                  const int xe = P.xe[(long long)m * kblk32 + (k >> 5)];
+                  const float xs = xe == MSQ_EXP_NAN ? qnan() : pow2i(xe);
+                  const float xv = __fmul_rn(decode_elem((uint32_t)P.xcodes[(long long)m * P.ldx + k], 4, 5), xs);
+                  r[v] = __float_as_uint(fmaf(xv, dw, __uint_as_float(r[v])));
+                }
+              }
+            }
+          }
 #pragma unroll
           for (int v = 0; v < 16; ++v) {
             const int m = tm * P.bnx + c * 16 + v;
@@ -400,12 +435,18 @@ extern "C" {
 //   xcodes [M, K] E4M3 bytes (ld = ldx bytes), xe int8 [M, K/32]         (plain MX-FP8 activations)
 //   wcodes / wbitmap / we_in / we_out: packed FP4 weight, block 32 along K (plain != 0: no outliers)
 // The caller guarantees that every outlier block satisfies -6 <= e_out - 2 e_in <= 6 (exact E4M3 folding).
+struct Mx4Sparse { const int* o_ptr; const int* o_k; const float* o_dw; };
+
 static int launch_mx8(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* wcodes,
                       const unsigned int* wbitmap, const signed char* we_in, const signed char* we_out,
                       const unsigned char* wdense, long long ldw, const unsigned char* wsf, float* C, long long ldc, int M,
-                      int N, int K, int plain, int accumulate, cudaStream_t s) {
+                      int N, int K, int plain, int accumulate, cudaStream_t s, const Mx4Sparse* fp4 = nullptr) {
   Mx8Params P;
   memset(&P, 0, sizeof(P));
+  P.w_tx_bytes = wdense ? XA_BYTES : 0;
+  // a 16U4_ALIGN16B load reports the bytes it READ (8 per 16-byte chunk written) to the mbarrier [measured: expecting
+  // the 16 KB it writes never completes; 8 KB does]
+  if (fp4) { P.w_tx_bytes = XA_BYTES / 2; P.wfp4 = 1; P.w_fmt = 5; P.o_ptr = fp4->o_ptr; P.o_k = fp4->o_k; P.o_dw = fp4->o_dw; P.xcodes = xcodes; P.ldx = ldx; }
   P.wcodes = wcodes; P.wbitmap = wbitmap; P.we_in = we_in; P.we_out = we_out; P.xe = xe; P.C = C; P.ldc = ldc;
   P.M = M; P.N = N; P.K = K; P.plain = plain; P.accumulate = accumulate;
   P.wdense = wdense != nullptr; P.wsf = wsf;
@@ -442,6 +483,9 @@ static int launch_mx8(const unsigned char* xcodes, long long ldx, const signed c
   if (rc) return rc;
   if (wdense) {
     rc = make_tmap_2d(&tmW, wdense, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, ldw, XM, XBK);
+    if (rc) return rc;
+  } else if (fp4) {
+    rc = make_tmap_2d_u4(&tmW, wcodes, N, K, (long long)K / 2, XM);
     if (rc) return rc;
   } else {
     tmW = tmX;
@@ -490,6 +534,25 @@ int msq_gemm_mxfp8_dense(const unsigned char* xcodes, long long ldx, const signe
   if ((reinterpret_cast<uintptr_t>(xcodes) & 15) || (ldx % 16) || (reinterpret_cast<uintptr_t>(wbytes) & 15) || (ldw % 16)) return MSQ_ERR_ALIGN;
   return launch_mx8(xcodes, ldx, xe, nullptr, nullptr, nullptr, nullptr, wbytes, ldw, wsf, C, ldc, M, N, K, 1, accumulate,
                     (cudaStream_t)stream);
+}
+
+// FP4-by-TMA mode: the packed 4-bit codes of the weight (block 32 along K, E2M1, equal inlier / outlier width) feed
+// tcgen05.mma kind::mxf8f6f4 directly -- TMA expands 16 codes into a 16-byte chunk (CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B),
+// the block scale is we_in, no thread widens anything -- and the outliers are a sparse correction in the epilogue:
+// CSR over output features, o_dw = q * (2^(e_out - e_in) - 2^e_in) (what the true weight differs from q * 2^e_in by).
+// o_ptr may be NULL (no outliers).  Needs K % 128 == 0 and wcodes 32-byte aligned.
+int msq_gemm_mxfp4w_blockscaled(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* wcodes,
+                                const signed char* we_in, const int* o_ptr, const int* o_k, const float* o_dw, float* C,
+                                long long ldc, int M, int N, int K, int accumulate, void* stream) {
+  msq::DevGuard dev_guard_(xcodes);
+  if (!xcodes || !xe || !wcodes || !we_in || !C || M <= 0 || N <= 0 || K <= 0) return MSQ_ERR_BAD_ARG;
+  if (o_ptr && (!o_k || !o_dw)) return MSQ_ERR_BAD_ARG;
+  if (K % 128 != 0) return MSQ_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(xe) & 3) || (reinterpret_cast<uintptr_t>(we_in) & 3)) return MSQ_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(xcodes) & 15) || (ldx % 16) || (reinterpret_cast<uintptr_t>(wcodes) & 31)) return MSQ_ERR_ALIGN;
+  Mx4Sparse sp{o_ptr, o_k, o_dw};
+  return launch_mx8(xcodes, ldx, xe, wcodes, nullptr, we_in, nullptr, nullptr, 0, nullptr, C, ldc, M, N, K, 1, accumulate,
+                    (cudaStream_t)stream, &sp);
 }
 
 }  // extern "C"

@@ -139,5 +139,6 @@ EncodeTiledFn get_encode_tiled();
 // row-major [rows, cols] matrix with leading dimension ld (elements); box = [box_rows, box_cols], 128B swizzle
 int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int elem_bytes, long long rows, long long cols,
                  long long ld, int box_rows, int box_cols);
+int make_tmap_2d_u4(CUtensorMap* out, const void* base, long long rows, long long cols, long long row_bytes, int box_rows);
 
 }  // namespace msq

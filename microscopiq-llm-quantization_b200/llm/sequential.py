@@ -195,7 +195,7 @@ def _run_layer(layer, x, args, kwargs):
 
 @torch.no_grad()
 def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=.01, groupsize=-1, act_order=False,
-                        static_groups=False, true_sequential=False, hessian_batch=8, verbose=False, stats=None, overlap_moves=False,
+                        static_groups=False, true_sequential=False, hessian_batch=8, verbose=False, stats=None, overlap_moves=True,
                         share_hessians=True, forward_batch=8, release_cache=False, packed_out=None,
                         solve_streams_n=3):
     """llama_sequential / opt_sequential (llm/llama.py:62-173, llm/opt.py:26-128).
