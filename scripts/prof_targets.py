@@ -42,7 +42,12 @@ if what in ("all", "gemm"):
     pw.hi_index()
     for M in (16, 256):
         x = torch.randn(M, 4096, device=dev, generator=g).to(torch.bfloat16)
-        for _ in range(3):
+        for _ in range(2):
             _tc.packed_linear(x, pw)
+    torch.cuda.synchronize()
+    pk = msq_b200.pack_mx_outlier(W, 8, 8, "fp4_e2m1", "fp4_e2m1", 5, [1], 32, variant=1)
+    for M in (16, 256):
+        xq = msq_b200.pack_mx(torch.randn(M, 4096, device=dev, generator=g), 8, "fp8_e4m3", axes=[-1], block_size=32)
+        _tc.packed_linear_mx8(xq, pk)
     torch.cuda.synchronize()
 print("done", what)
