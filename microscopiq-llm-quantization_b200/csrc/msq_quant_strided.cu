@@ -80,8 +80,13 @@ __global__ void __launch_bounds__(256, (BS <= 16 ? (PACK ? 4 : MSQ_STRIDED_MINB)
   extern __shared__ uint32_t s_hi[];
   __shared__ int s_warp[8];
   __shared__ int s_base;
+  // deferred hi placement (blocks whose hi fields fit 64 bits): every block stashes its compacted fields and its count,
+  // ONE scan over the segment's 1024 counts places them afterwards -- instead of a CTA scan + 3 barriers per 256 blocks
+  __shared__ unsigned long long s_acc[PACK && OUTLIER ? MSQ_SEG_BLOCKS : 1];
+  __shared__ unsigned char s_cnt[PACK && OUTLIER ? MSQ_SEG_BLOCKS : 1];
   const long long seg = blockIdx.x;
   const bool pack_hi = PACK && OUTLIER && P.hi_w > 0;
+  const bool deferred = pack_hi && BS * P.hi_w <= 64;
   const int wi = P.c.fin.width;
   const int lane = threadIdx.x & 31;
   const int post = (int)P.post;
@@ -194,7 +199,20 @@ __global__ void __launch_bounds__(256, (BS <= 16 ? (PACK ? 4 : MSQ_STRIDED_MINB)
         }
       }
     }
-    if (pack_hi) {
+    if (deferred) {
+      unsigned long long acc = 0;
+      if (active && bo.cnt) {
+        // walk the block backwards, shifting the accumulator by hi_w for every outlier (an inlier's code has no bits
+        // above the slot width, so its field is zero and needs no masking): first outlier ends in the lowest bits
+#pragma unroll
+        for (int i = BS - 1; i >= 0; --i) {
+          const int sh = ((bo.mask >> i) & 1u) ? P.hi_w : 0;
+          acc = (acc << sh) | (unsigned long long)(code[i] >> wi);
+        }
+      }
+      s_acc[sub * 256 + threadIdx.x] = acc;
+      s_cnt[sub * 256 + threadIdx.x] = (unsigned char)(active ? bo.cnt : 0);
+    } else if (pack_hi) {
       int tot;
       const int off = cta_excl_scan(active ? bo.cnt : 0, s_warp, &tot);
       if (active && bo.cnt) {
@@ -233,6 +251,31 @@ __global__ void __launch_bounds__(256, (BS <= 16 ? (PACK ? 4 : MSQ_STRIDED_MINB)
       if (threadIdx.x == 0) s_base += tot;
       __syncthreads();
     }
+  }
+  if (deferred) {
+    __syncthreads();
+    // thread t places the four consecutive blocks 4t .. 4t+3 of the segment
+    int c4[4], mine = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { c4[u] = s_cnt[4 * threadIdx.x + u]; mine += c4[u]; }
+    int tot;
+    int off = cta_excl_scan(mine, s_warp, &tot);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (c4[u]) {
+        const unsigned long long acc = s_acc[4 * threadIdx.x + u];
+        const int bit0 = off * P.hi_w;
+        const int w = bit0 >> 5, b = bit0 & 31;
+        const unsigned long long lo = acc << b;
+        const uint32_t top = b ? (uint32_t)(acc >> (64 - b)) : 0u;
+        atomicOr(&s_hi[w], (uint32_t)lo);
+        if ((uint32_t)(lo >> 32)) atomicOr(&s_hi[w + 1], (uint32_t)(lo >> 32));
+        if (top) atomicOr(&s_hi[w + 2], top);
+        off += c4[u];
+      }
+    }
+    if (threadIdx.x == 0) s_base = tot;
+    __syncthreads();
   }
   if (pack_hi) {
     const int total = s_base;
