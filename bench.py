@@ -172,79 +172,66 @@ def extras(dev, dev_w, nel):
     out["pack"] = {"GBps": nel * (4 + bpe) / (ms * 1e-3) / 1e9, "ms_per_layer": ms, "packed_bytes_per_elem": bpe,
                    "frac_of_hbm_peak": nel * (4 + bpe) / (ms * 1e-3) / 1e9 / peaks()[0]}
     del calls
-    # (2) GPTQ: Hessian over 128 x 2048 synthetic fp16 tokens + fasterquant for the 7 linears of one layer
+    # (2) GPTQ: Hessians over 128 x 2048 synthetic fp16 tokens + fasterquant for the 7 linears of one layer, the way the
+    #     driver runs them: linears fed by the same activations (q/k/v, gate/up) share ONE Hessian and ONE factorization
     msq_b200.GPTQ.verbose = False
     nsamples, seqlen = 128, 2048
-    t_h = t_s = 0.0
-    flops_h = 0.0
     X = {}
     for _, r, c in LAYER_SHAPES:
         if c not in X:
             X[c] = torch.randn(1, seqlen, c, device=dev, generator=torch.Generator(device=dev).manual_seed(c)).half()
-    for i, (name, r, c) in enumerate(LAYER_SHAPES):
-        layer = torch.nn.Linear(c, r, bias=False, device=dev, dtype=torch.float16)
-        layer.weight.data = dev_w[i].half()
-        g = msq_b200.GPTQ(layer)
-        g.hessian_batch = 8
-        g.quantizer = msq_b200.MXQuantizer()
-        g.quantizer.configure(8, 8, QCFG["in_fmt"], QCFG["out_fmt"], axes=[0], block_size=QCFG["bs"])
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(nsamples):
-            g.add_batch(X[c], None)
-        _ = g.H
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        g.fasterquant()
-        torch.cuda.synchronize()
-        t2 = time.perf_counter()
-        if i == 0:      # first call pays cuSOLVER initialisation: repeat it
-            layer.weight.data = dev_w[i].half()
-            g = msq_b200.GPTQ(layer)
-            g.hessian_batch = 8
-            g.quantizer = msq_b200.MXQuantizer()
-            g.quantizer.configure(8, 8, QCFG["in_fmt"], QCFG["out_fmt"], axes=[0], block_size=QCFG["bs"])
+    GROUPS = [[0, 1, 2], [3], [4, 5], [6]]          # indices into LAYER_SHAPES: (q, k, v) (o) (gate, up) (down)
+
+    def gptq_layer(share, method):
+        msq_b200.GPTQ.hinv_method = method
+        t_h = t_s = 0.0
+        flops = 0.0
+        for grp in (GROUPS if share else [[i] for i in range(len(LAYER_SHAPES))]):
+            gs = []
+            for i in grp:
+                _, r, c = LAYER_SHAPES[i]
+                layer = torch.nn.Linear(c, r, bias=False, device=dev, dtype=torch.float16)
+                layer.weight.data = dev_w[i].half()
+                g = msq_b200.GPTQ(layer)
+                g.hessian_batch = 8
+                g.release_cache_on_free = False
+                g.quantizer = msq_b200.MXQuantizer()
+                g.quantizer.configure(8, 8, QCFG["in_fmt"], QCFG["out_fmt"], axes=[0], block_size=QCFG["bs"])
+                if gs:
+                    g.share_hessian_with(gs[0])
+                gs.append(g)
+            c = LAYER_SHAPES[grp[0]][2]
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for _ in range(nsamples):
-                g.add_batch(X[c], None)
-            _ = g.H
+                gs[0].add_batch(X[c], None)
+            _ = gs[0].H
             torch.cuda.synchronize()
             t1 = time.perf_counter()
-            g.fasterquant()
+            for g in gs:
+                g.fasterquant()
             torch.cuda.synchronize()
             t2 = time.perf_counter()
-        t_h += t1 - t0
-        t_s += t2 - t1
-        flops_h += 2.0 * nsamples * seqlen * c * c
-        g.free()
-    # same solves with the reference's own route to Hinv (three cuSOLVER calls through torch.linalg) for comparison
-    t_lib = 0.0
-    msq_b200.GPTQ.hinv_method = "reference"
+            for g in gs:
+                g.free()
+            t_h += t1 - t0
+            t_s += t2 - t1
+            flops += 2.0 * nsamples * seqlen * c * c
+        msq_b200.GPTQ.hinv_method = "native"
+        return t_h, t_s, flops
+    gptq_layer(True, "native")                                            # warm-up (allocator, module loading)
+    t_h, t_s, flops_h = gptq_layer(True, "native")
+    t_h7, t_s7, flops_h7 = gptq_layer(False, "native")
     _w = torch.eye(512, device=dev)
     torch.linalg.cholesky(torch.cholesky_inverse(torch.linalg.cholesky(_w)), upper=True)        # cuSOLVER handles, untimed
-    for i, (name, r, c) in enumerate(LAYER_SHAPES):
-        layer = torch.nn.Linear(c, r, bias=False, device=dev, dtype=torch.float16)
-        layer.weight.data = dev_w[i].half()
-        g = msq_b200.GPTQ(layer)
-        g.hessian_batch = 8
-        g.quantizer = msq_b200.MXQuantizer()
-        g.quantizer.configure(8, 8, QCFG["in_fmt"], QCFG["out_fmt"], axes=[0], block_size=QCFG["bs"])
-        for _ in range(8):
-            g.add_batch(X[c], None)
-        _ = g.H
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        g.fasterquant()
-        torch.cuda.synchronize()
-        t_lib += time.perf_counter() - t1
-        g.free()
-    msq_b200.GPTQ.hinv_method = "native"
-    out["gptq_layer"] = {"hessian_s": t_h, "solve_s": t_s, "layer_s": t_h + t_s, "solve_s_cusolver_route": t_lib,
+    _, t_lib, _ = gptq_layer(False, "reference")
+    out["gptq_layer"] = {"hessian_s": t_h, "solve_s": t_s, "layer_s": t_h + t_s,
+                         "solve_s_unshared": t_s7, "hessian_s_unshared": t_h7, "solve_s_cusolver_route_unshared": t_lib,
                          "hessian_TFLOPs": flops_h / t_h / 1e12,
-                         "note": "kernel-level view of one decoder layer: 7 linears solved one by one, each with its own "
-                                 "Hessian (128x2048 fp16 tokens) and its own native factorization; the driver-level number "
-                                 "(shared Hessians, forwards, moves) is extra.gptq_model"}
+                         "note": "kernel-level view of one decoder layer (7 linears, 128x2048 fp16 tokens): 4 distinct Hessians and "
+                                 "factorizations (q/k/v and gate/up share theirs, as in the driver), 7 column loops one after the "
+                                 "other; *_unshared = 7 Hessians / factorizations as llm/llama.py:139-159 builds them; the "
+                                 "driver-level number incl. forwards and moves is extra.gptq_model"}
     # (3) packed-weight GEMM, K = N = 4096, MX-FP4 + outliers, bf16 activations
     gemm = {}
     W = dev_w[0]
