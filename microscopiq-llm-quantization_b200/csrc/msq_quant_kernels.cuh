@@ -90,6 +90,9 @@ struct MultiQParams {
   unsigned int cta_start[MSQ_MULTI_MAX + 1];
 };
 cudaError_t launch_strided_multi(const MultiQParams& MP, int bs, unsigned total_ctas, cudaStream_t stream);
+// persistent TMA-staged variant (msq_quant_tma.cu); MSQ_ERR_UNSUPPORTED = geometry not addressable by a tensor map
+int launch_strided_tma(int n, const float* const* in, float* const* out, const long long* rows, const long long* cols,
+                       int bs, const QCfg& c, int* status, cudaStream_t stream);
 
 // launchers (one translation unit each); return false if the geometry is not theirs
 cudaError_t launch_strided(const QParams& P, bool outlier, size_t smem, cudaStream_t stream);

@@ -376,6 +376,18 @@ int msq_quantize_mx_outlier_multi_f32(int n, const float* const* in, float* cons
   MP.c.sb_in = in_scale_bits; MP.c.sb_out = out_scale_bits;
   MP.c.std_dev = std_dev; MP.c.flush = flush_fp32_subnorms; MP.c.variant = 0; MP.c.rmode = rmode; MP.c.mode = 0;
   finish_cfg(MP.c);
+  {
+    // persistent TMA-staged kernel when every matrix can be addressed by a tensor map (cols % 4 == 0);
+    // MSQ_QUANT_TMA=0 keeps the direct-load kernel (A/B measurements)
+    const char* e = getenv("MSQ_QUANT_TMA");
+    if (!(e && e[0] == '0')) {
+      bool ok = true;
+      for (int i = 0; i < n && ok; ++i) ok = in[i] && out[i] && rows[i] > 0 && cols[i] > 0 && rows[i] * cols[i] < 0x7fffffffLL;
+      if (!ok) return MSQ_ERR_BAD_ARG;
+      const int rc = launch_strided_tma(n, in, out, rows, cols, block_size, MP.c, status, (cudaStream_t)stream);
+      if (rc != MSQ_ERR_UNSUPPORTED) return rc;
+    }
+  }
   unsigned long long total = 0;
   for (int i = 0; i < n; ++i) {
     if (!in[i] || !out[i] || rows[i] <= 0 || cols[i] <= 0 || rows[i] * cols[i] >= 0x7fffffffLL) return MSQ_ERR_BAD_ARG;
