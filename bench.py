@@ -578,6 +578,11 @@ def main():
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.summary() if rank == 0 else None
     ms_per_tensor = _time_ms(step_device_per_tensor, args.steps) if rank == 0 else 0.0     # seven launches, for comparison
+    ms_direct = 0.0
+    if rank == 0:      # the round-1/early-round-2 direct-load kernel (k_strided_multi) on the same step, for comparison
+        os.environ["MSQ_QUANT_TMA"] = "0"
+        ms_direct = _time_ms(step_device, args.steps)
+        os.environ.pop("MSQ_QUANT_TMA")
     assert int(status.item()) == 0, "quantizer raised status %d" % int(status.item())
 
     # end to end through the public API with host buffers
@@ -622,13 +627,16 @@ def main():
                 "ms_per_step": e2e_s * 1e3},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
-                     "traffic": None, "kernel": "k_strided_multi<BS=16> (one launch = the seven linears)", "peak_source": peak_src,
+                     "traffic": None,
+                     "kernel": "k_strided_tma<BS=16, TW=256> (persistent, TMA-staged; one launch = the seven linears)",
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": "8 B x 202 375 168 elements = 1.619 GB",
-                     "seven_separate_launches_GBps": bytes_step / (ms_per_tensor * 1e-3) / 1e9},
+                     "seven_separate_launches_GBps": bytes_step / (ms_per_tensor * 1e-3) / 1e9,
+                     "direct_load_kernel_k_strided_multi_GBps": bytes_step / (ms_direct * 1e-3) / 1e9},
     }
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
-        line["roofline"]["traffic"] = json.load(open(tr)).get("k_strided_multi_bytes_per_launch")
+        line["roofline"]["traffic"] = json.load(open(tr)).get("k_strided_tma_bytes_per_launch")
     if not args.no_extras:
         line["extra"] = extras(dev, dev_w, nel)
         line["extra"].update(legs)

@@ -86,7 +86,8 @@ int msq_quantize_mx_f32(const float* in, float* deq, long long pre, long long L,
  *   bitmap   1 bit per element, linear element order, 32-bit little-endian words
  *   hi       segment-compacted high bits of outlier codes (see DESIGN.md "packed layout")
  *   seg_cnt  outliers per segment;  blk_cnt  outliers per block (uint8);  mask  1 byte/element
- *   status   OR of MSQ_ST_*;  host_path  which kernel ran (1 strided, 2 innermost, 3 generic) */
+ *   status   OR of MSQ_ST_*;  host_path  which kernel ran (1 strided, 2 innermost, 3 generic, 4 strided through the
+ *            persistent TMA-staged kernel: 2-D input, values only; 5 = its quantize+pack sibling) */
 int msq_quantize_mx_outlier_f32(
     const float* in, float* deq, long long pre, long long L, long long post, int block_size,
     int in_scale_bits, int out_scale_bits,

@@ -94,6 +94,9 @@ cudaError_t launch_strided_multi(const MultiQParams& MP, int bs, unsigned total_
 int launch_strided_tma(int n, const float* const* in, float* const* out, const long long* rows, const long long* cols,
                        int bs, const QCfg& c, int* status, cudaStream_t stream);
 
+// quantize + pack of one 2-D weight through the TMA-staged kernel; MSQ_ERR_UNSUPPORTED = not its geometry / formats
+int launch_pack_tma(const QParams& Q, cudaStream_t stream);
+
 // launchers (one translation unit each); return false if the geometry is not theirs
 cudaError_t launch_strided(const QParams& P, bool outlier, size_t smem, cudaStream_t stream);
 cudaError_t launch_inner(const QParams& P, bool outlier, size_t smem, cudaStream_t stream);

@@ -266,6 +266,33 @@ static int launch_quant(QParams& P, bool outlier, cudaStream_t stream, int* path
   const bool fast_ok = small && !P.mask && (packing || P.deq);
   int path = 0;
   cudaError_t err;
+  // 2-D weight blocked along its rows, dequantized values only (what MXQuantizer.quantize asks for): persistent
+  // TMA-staged kernel (msq_quant_tma.cu); path 4
+  if (outlier && fast_ok && !packing && P.pre == 1 && P.post > 1 && (P.post & 3) == 0 && inout_al && P.c.variant == 0 &&
+      !P.e_in && !P.e_out && !P.blk_cnt && (P.bs == 8 || P.bs == 16 || P.bs == 32)) {
+    const char* e = getenv("MSQ_QUANT_TMA");
+    if (!(e && e[0] == '0')) {
+      const float* in1[1] = {P.in};
+      float* out1[1] = {P.deq};
+      const long long rows1[1] = {P.L}, cols1[1] = {P.post};
+      const int rc = launch_strided_tma(1, in1, out1, rows1, cols1, P.bs, P.c, P.status, stream);
+      if (rc != MSQ_ERR_UNSUPPORTED) {
+        if (path_out) *path_out = 4;
+        return rc;
+      }
+    }
+  }
+  // quantize + pack of a 2-D weight (16-row blocks, 4-bit slots): TMA-staged segment kernel; path 5
+  if (outlier && packing && fast_ok && P.pre == 1 && P.post > 1) {
+    const char* e = getenv("MSQ_QUANT_TMA");
+    if (!(e && e[0] == '0')) {
+      const int rc = launch_pack_tma(P, stream);
+      if (rc != MSQ_ERR_UNSUPPORTED) {
+        if (path_out) *path_out = 5;
+        return rc;
+      }
+    }
+  }
   if (fast_ok && P.post == 1 && P.L % P.bs == 0 && inout_al && !P.ext_max &&
       (P.bs == 8 || P.bs == 16 || P.bs == 32 || P.bs == 64 || P.bs == 128)) {
     path = 2;

@@ -127,6 +127,246 @@ __global__ void __launch_bounds__(TW + 32, MINB) k_strided_tma(const __grid_cons
   }
 }
 
+
+// ---- quantize + pack (codes, bitmap, exponents, hi stream) in the same TMA-staged style ---------------------------
+// Work unit = one packed SEGMENT (MSQ_SEG_BLOCKS = 1024 consecutive block-linear indices = 4 tiles of 256 columns; with
+// post % 256 == 0 every tile lies inside one row block, a segment may cross into the next one).  Per tile the consumers
+// leave the tile's slice of every plane in a staging area of shared memory -- 4-bit codes through the 8x8 byte transpose
+// across lanes, one ballot per row for the bitmap, one byte per block for each exponent -- and the producer thread
+// writes them with two tensor stores and two linear bulk stores: the compute threads do no global address arithmetic.
+// The hi fields of a block (<= 64 bits) are compacted in registers and stashed; one scan per segment places them.
+struct TmaPackParams {
+  CUtensorMap tin, tcodes, tbitmap;
+  QCfg c;
+  int* status;
+  int8_t* e_in;
+  int8_t* e_out;
+  uint8_t* hi;
+  int* seg_cnt;
+  long long hi_seg_stride;
+  int hi_w;
+  unsigned int ntiles, nseg;
+  int gx;
+  unsigned int gx_m;
+  int gx_k;
+};
+
+__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(tc::smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// exclusive scan over the 256 consumer threads (named barrier 1: the producer warp does not take part)
+__device__ __forceinline__ int cons_excl_scan(int v, int* s_warp, int* sum) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int wt;
+  const int ex = warp_excl_scan(v, lane, wt);
+  cons_bar();
+  if (lane == 0) s_warp[w] = wt;
+  cons_bar();
+  int basev = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const int t = s_warp[i]; if (i < w) basev += t; tot += t; }
+  *sum = tot;
+  return ex + basev;
+}
+
+// store_codes4_16 (msq_quant_strided.cu) with the destination in shared memory: cd = the tile's code image, 16 rows of
+// 128 bytes; this warp's 32 columns are bytes [16*warp, 16*warp + 16) of every row
+__device__ __forceinline__ void stage_codes4_16(uint32_t* cd, const uint32_t* c, int lane, int warp) {
+  const int g = lane & 7;
+  uint32_t W0, W1;
+  {
+    uint32_t B[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) B[k] = (c[2 * k] & 0xFu) | ((c[2 * k + 1] << 4) & 0xF0u);
+    W0 = __byte_perm(__byte_perm(B[0], B[1], 0x0040), __byte_perm(B[2], B[3], 0x0040), 0x5410);
+    W1 = __byte_perm(__byte_perm(B[4], B[5], 0x0040), __byte_perm(B[6], B[7], 0x0040), 0x5410);
+  }
+  {
+    const uint32_t r = __shfl_xor_sync(0xffffffffu, (g & 4) ? W0 : W1, 4);
+    if (g & 4) W0 = r; else W1 = r;
+  }
+  {
+    const uint32_t r = __shfl_xor_sync(0xffffffffu, __byte_perm(W0, W1, (g & 2) ? 0x5410 : 0x7632), 2);
+    W0 = __byte_perm(W0, r, (g & 2) ? 0x3254 : 0x5410);
+    W1 = __byte_perm(W1, r, (g & 2) ? 0x3276 : 0x7610);
+  }
+  {
+    const uint32_t r = __shfl_xor_sync(0xffffffffu, __byte_perm(W0, W1, (g & 1) ? 0x6420 : 0x7531), 1);
+    W0 = __byte_perm(W0, r, (g & 1) ? 0x3514 : 0x5240);
+    W1 = __byte_perm(W1, r, (g & 1) ? 0x3716 : 0x7260);
+  }
+  const uint32_t a0 = W0 & 0x0F0F0F0Fu, a1 = W1 & 0x0F0F0F0Fu;
+  const uint32_t b0 = (W0 >> 4) & 0x0F0F0F0Fu, b1 = (W1 >> 4) & 0x0F0F0F0Fu;
+  const uint32_t row_lo = __byte_perm(a0 | (a0 >> 4), a1 | (a1 >> 4), 0x6420);
+  const uint32_t row_hi = __byte_perm(b0 | (b0 >> 4), b1 | (b1 >> 4), 0x6420);
+  uint32_t* dst = cd + (2 * g) * 32 + warp * 4 + (lane >> 3);      // 32 words per row
+  dst[0] = row_lo;
+  dst[32] = row_hi;
+}
+
+constexpr int TP_NST = 4;
+constexpr int TP_TW = 256;
+
+template <int BS>
+__global__ void __launch_bounds__(TP_TW + 32, 2) k_pack_tma(const __grid_constant__ TmaPackParams P) {
+  static_assert(BS == 16, "4-bit slots, 16-row blocks");
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int STAGE_FLOATS = BS * TP_TW;
+  constexpr uint32_t STAGE_BYTES = STAGE_FLOATS * 4;
+  constexpr int CD_BYTES = BS * (TP_TW / 2), BM_BYTES = BS * (TP_TW / 8), EX_BYTES = TP_TW;
+  constexpr int OUT_BYTES = CD_BYTES + BM_BYTES + 2 * EX_BYTES;      // staging per stage (3 KB)
+  float* tiles = reinterpret_cast<float*>(smem_raw);
+  unsigned char* outs = smem_raw + (size_t)TP_NST * STAGE_BYTES;
+  unsigned long long* s_acc = reinterpret_cast<unsigned long long*>(outs + (size_t)TP_NST * OUT_BYTES);
+  uint32_t* s_hi = reinterpret_cast<uint32_t*>(s_acc + MSQ_SEG_BLOCKS);          // MSQ_SEG_BLOCKS * BS * 4 / 8 bytes max
+  unsigned char* s_cnt = reinterpret_cast<unsigned char*>(s_hi + MSQ_SEG_BLOCKS * BS * 4 / 32);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_cnt + MSQ_SEG_BLOCKS);
+  uint64_t* done = full + TP_NST;
+  int* s_warp = reinterpret_cast<int*>(done + TP_NST);
+  const int tid = (int)threadIdx.x;
+  const int hi_w = P.hi_w;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < TP_NST; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&done[s], TP_TW); }
+    tc::mbar_fence_init();
+  }
+  for (int i = tid; i < MSQ_SEG_BLOCKS * BS * 4 / 32; i += TP_TW + 32) s_hi[i] = 0;
+  for (int i = tid; i < MSQ_SEG_BLOCKS; i += TP_TW + 32) s_cnt[i] = 0;
+  __syncthreads();
+  const unsigned int G = gridDim.x, first = blockIdx.x;
+  const int nseg_mine = first < P.nseg ? (int)((P.nseg - first + G - 1) / G) : 0;
+  int n_mine = 4 * nseg_mine;
+  if (nseg_mine > 0 && first + (unsigned)(nseg_mine - 1) * G == P.nseg - 1) n_mine -= (int)(4u * P.nseg - P.ntiles);
+
+  if (tid >= TP_TW) {
+    if (tid == TP_TW) {
+      auto tile_of = [&](int k) { return 4u * (first + (unsigned)(k >> 2) * G) + (unsigned)(k & 3); };
+      auto coords = [&](unsigned int q, int& cx, int& r0) {
+        const int b = fast_div((int)q, P.gx_m, P.gx_k);
+        cx = (int)q - b * P.gx;
+        r0 = b * BS;
+      };
+      auto load = [&](int k) {
+        int cx, r0;
+        coords(tile_of(k), cx, r0);
+        const int s = k % TP_NST;
+        tc::mbar_expect_tx(&full[s], STAGE_BYTES);
+        tc::tma_load_2d(tiles + (size_t)s * STAGE_FLOATS, &P.tin, &full[s], cx * TP_TW, r0);
+      };
+      const int pre = n_mine < TP_NST ? n_mine : TP_NST;
+      for (int k = 0; k < pre; ++k) load(k);
+      for (int k = 0; k < n_mine; ++k) {
+        const int s = k % TP_NST;
+        tc::mbar_wait(&done[s], (uint32_t)(k / TP_NST) & 1u);
+        const unsigned int q = tile_of(k);
+        int cx, r0;
+        coords(q, cx, r0);
+        const unsigned char* o = outs + (size_t)s * OUT_BYTES;
+        tma_store_2d(&P.tcodes, o, cx * (TP_TW / 2), r0);
+        tma_store_2d(&P.tbitmap, o + CD_BYTES, cx * (TP_TW / 8), r0);
+        bulk_store_1d(P.e_in + (size_t)q * TP_TW, o + CD_BYTES + BM_BYTES, EX_BYTES);
+        bulk_store_1d(P.e_out + (size_t)q * TP_TW, o + CD_BYTES + BM_BYTES + EX_BYTES, EX_BYTES);
+        bulk_commit();
+        if (k >= 1 && k - 1 + TP_NST < n_mine) {
+          bulk_wait_read<1>();
+          load(k - 1 + TP_NST);
+        }
+      }
+      bulk_wait_all();
+    }
+    return;
+  }
+
+  const int lane = tid & 31, warp = tid >> 5;
+  int st = 0;
+#pragma unroll 1
+  for (int k = 0; k < n_mine; ++k) {
+    const int s = k % TP_NST, u = k & 3;
+    tc::mbar_wait(&full[s], (uint32_t)(k / TP_NST) & 1u);
+    const float* tp = tiles + (size_t)s * STAGE_FLOATS + tid;
+    float x[BS];
+    uint32_t code[BS];
+#pragma unroll
+    for (int i = 0; i < BS; ++i) x[i] = tp[i * TP_TW];
+    const BlockOut bo = core_outlier<BS, 1, true, false, true>(x, code, P.c, nullptr, nullptr);
+    st |= bo.st;
+    unsigned char* o = outs + (size_t)s * OUT_BYTES;
+    stage_codes4_16(reinterpret_cast<uint32_t*>(o), code, lane, warp);
+    {
+      uint32_t* bm = reinterpret_cast<uint32_t*>(o + CD_BYTES) + warp;       // 8 words per row
+#pragma unroll
+      for (int i = 0; i < BS; ++i) {
+        const uint32_t w = __ballot_sync(0xffffffffu, bo.mask & (1u << i));
+        if (lane == 0) bm[i * (TP_TW / 32)] = w;
+      }
+    }
+    o[CD_BYTES + BM_BYTES + tid] = (unsigned char)(int8_t)bo.e_in;
+    o[CD_BYTES + BM_BYTES + EX_BYTES + tid] = (unsigned char)(int8_t)bo.e_out;
+    if (hi_w > 0) {
+      // hi fields of the block, first outlier in the lowest bits: two 32-bit halves built by predicated
+      // multiply-adds (walking backwards), joined by the number of outliers in the low half
+      uint32_t a0 = 0, a1 = 0;
+      const uint32_t mul = 1u << hi_w;
+      if (bo.cnt) {
+#pragma unroll
+        for (int i = 7; i >= 0; --i)
+          if (bo.mask & (1u << i)) a0 = a0 * mul + (code[i] >> 4);
+#pragma unroll
+        for (int i = 15; i >= 8; --i)
+          if (bo.mask & (1u << i)) a1 = a1 * mul + (code[i] >> 4);
+      }
+      const int sh = __popc(bo.mask & 0xFFu) * hi_w;                       // <= 32
+      const unsigned long long acc = (unsigned long long)a0 | (sh < 32 ? ((unsigned long long)a1 << sh) : ((unsigned long long)a1 << 32));
+      s_acc[u * TP_TW + tid] = acc;
+      s_cnt[u * TP_TW + tid] = (unsigned char)bo.cnt;
+    }
+    fence_proxy_async_smem();
+    tc::mbar_arrive(&done[s]);
+
+    if (u == 3 || k == n_mine - 1) {
+      const unsigned int sg = first + (unsigned)(k >> 2) * G;
+      if (hi_w > 0) {
+        if (u < 3)
+          for (int i = (u + 1) * TP_TW + tid; i < MSQ_SEG_BLOCKS; i += TP_TW) s_cnt[i] = 0;
+        cons_bar();
+        int c4[4], mine = 0;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { c4[v] = s_cnt[4 * tid + v]; mine += c4[v]; }
+        int tot;
+        int off = cons_excl_scan(mine, s_warp, &tot);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          if (c4[v]) {
+            const unsigned long long acc = s_acc[4 * tid + v];
+            const int bit0 = off * hi_w;
+            const int w = bit0 >> 5, b = bit0 & 31;
+            const unsigned long long lo = acc << b;
+            const uint32_t top = b ? (uint32_t)(acc >> (64 - b)) : 0u;
+            atomicOr(&s_hi[w], (uint32_t)lo);
+            if ((uint32_t)(lo >> 32)) atomicOr(&s_hi[w + 1], (uint32_t)(lo >> 32));
+            if (top) atomicOr(&s_hi[w + 2], top);
+            off += c4[v];
+          }
+        }
+        cons_bar();
+        const int words = (tot * hi_w + 31) >> 5;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(P.hi + (size_t)sg * P.hi_seg_stride);
+        for (int i = tid; i < words; i += TP_TW) { dst[i] = s_hi[i]; s_hi[i] = 0; }
+        if (tid == 0 && P.seg_cnt) P.seg_cnt[sg] = tot;
+      } else if (tid == 0 && P.seg_cnt) {
+        P.seg_cnt[sg] = 0;
+      }
+    }
+  }
+  if (P.status) {
+    st = __reduce_or_sync(0xffffffffu, st);
+    if (lane == 0 && st) atomicOr(P.status, st);
+  }
+}
+
 static int make_tmap_plain_f32(CUtensorMap* out, const void* basep, long long rows, long long cols, int box_rows, int box_cols) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return MSQ_ERR_CUDA;
@@ -184,6 +424,58 @@ int launch_strided_tma(int n, const float* const* in, float* const* out, const l
   if (bs == 16) return launch_one<16, 256, 3>(P, stream);
   if (bs == 32) return launch_one<32, 128, 3>(P, stream);
   return launch_one<8, 256, 4>(P, stream);
+}
+
+
+static int make_tmap_bytes(CUtensorMap* out, const void* basep, long long rows, long long row_bytes, int box_rows, int box_bytes) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return MSQ_ERR_CUDA;
+  cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_bytes, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(basep), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MSQ_OK : MSQ_ERR_CUDA;
+}
+
+// quantize + pack of ONE 2-D weight [L, post] blocked along its rows: 16-row blocks, 4-bit slots, hi fields of a block
+// within 64 bits, post % 256 == 0, no dequantized output.  MSQ_ERR_UNSUPPORTED -> the caller uses k_strided<.., PACK>.
+int launch_pack_tma(const QParams& Q, cudaStream_t stream) {
+  if (Q.pre != 1 || Q.bs != 16 || Q.c.fin.width != 4 || (Q.post & 255) || Q.deq || Q.mask || Q.blk_cnt || Q.c.variant != 0 ||
+      Q.bs * Q.hi_w > 64 || Q.hi_w == 8 || !Q.codes || !Q.bitmap || !Q.e_in || !Q.e_out || (Q.hi_w > 0 && !Q.hi))
+    return MSQ_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(Q.in) & 15) || (reinterpret_cast<uintptr_t>(Q.codes) & 15) ||
+      (reinterpret_cast<uintptr_t>(Q.bitmap) & 15) || (reinterpret_cast<uintptr_t>(Q.e_in) & 15) ||
+      (reinterpret_cast<uintptr_t>(Q.e_out) & 15) || (reinterpret_cast<uintptr_t>(Q.hi) & 3))
+    return MSQ_ERR_UNSUPPORTED;
+  if (Q.nblocks >= 0x7fffffffLL || (long long)Q.L * Q.post >= 0x7fffffffLL) return MSQ_ERR_UNSUPPORTED;
+  TmaPackParams P;
+  memset(&P, 0, sizeof(P));
+  if (make_tmap_plain_f32(&P.tin, Q.in, Q.L, Q.post, 16, TP_TW)) return MSQ_ERR_UNSUPPORTED;
+  if (make_tmap_bytes(&P.tcodes, Q.codes, Q.L, Q.post / 2, 16, TP_TW / 2)) return MSQ_ERR_UNSUPPORTED;
+  if (make_tmap_bytes(&P.tbitmap, Q.bitmap, Q.L, Q.post / 8, 16, TP_TW / 8)) return MSQ_ERR_UNSUPPORTED;
+  P.c = Q.c; P.status = Q.status; P.e_in = Q.e_in; P.e_out = Q.e_out; P.hi = Q.hi; P.seg_cnt = Q.seg_cnt;
+  P.hi_seg_stride = Q.hi_seg_stride; P.hi_w = Q.hi_w;
+  P.ntiles = (unsigned)(Q.nblocks / TP_TW);
+  P.nseg = (unsigned)((Q.nblocks + MSQ_SEG_BLOCKS - 1) / MSQ_SEG_BLOCKS);
+  P.gx = (int)(Q.post / TP_TW);
+  magic_div(P.gx, &P.gx_m, &P.gx_k);
+  auto k = k_pack_tma<16>;
+  const size_t smem = (size_t)TP_NST * (16 * TP_TW * 4 + 16 * (TP_TW / 2) + 16 * (TP_TW / 8) + 2 * TP_TW) +
+                      (size_t)MSQ_SEG_BLOCKS * 8 + (size_t)MSQ_SEG_BLOCKS * 16 * 4 / 8 + MSQ_SEG_BLOCKS +
+                      2 * TP_NST * sizeof(uint64_t) + 8 * sizeof(int) + 64;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MSQ_ERR_CUDA;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, TP_TW + 32, smem) != cudaSuccess || occ < 1) return MSQ_ERR_CUDA;
+  unsigned long long g = (unsigned long long)sms * (unsigned)occ;
+  if (g > P.nseg) g = P.nseg;
+  k<<<(unsigned)g, TP_TW + 32, smem, stream>>>(P);
+  return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
 }
 
 }  // namespace msq

@@ -213,6 +213,44 @@ CASES = [
 ]
 
 
+TMA_CASES = [
+    # 2-D weights blocked along the rows, values only -> the persistent TMA-staged kernel (path 4)
+    ("fp4_e2m1", "fp8_e4m3", 16, (512, 768)),
+    ("int2", "fp4", 16, (528, 132)),              # ragged rows and a ragged column tile (zero fill / clipped store)
+    ("fp4_e2m1", "fp8_e4m3", 32, (100, 1028)),
+    ("fp6_e3m2", "fp6_e3m2", 8, (8, 4)),
+    ("fp4_e2m1", "fp8_e4m3", 16, (1, 2052)),
+    ("fp4_e2m1", "fp8_e4m3", 16, (4096, 4096)),
+]
+
+
+@pytest.mark.parametrize("fi,fo,bs,shape", TMA_CASES)
+@pytest.mark.parametrize("rnd", ["nearest", "even", "floor"])
+def test_tma_staged_kernel_vs_oracle(M, fi, fo, bs, shape, rnd, monkeypatch):
+    """k_strided_tma (msq_quant_tma.cu): the values-only call on a 2-D weight == the oracle, == the direct-load kernel"""
+    from msq_b200 import _ops
+    W = weights(shape[0], shape[1], 23)
+    r = _ops.mx_outlier(W.cuda(), 8, 8, fi, fo, 2, 0, bs, rnd)
+    assert r.path == 4
+    if shape[0] * shape[1] <= 1 << 20:
+        assert_exact(r.deq, O.quantize_mx_outlier(W, 8, 8, fi, fo, 2, 0, bs, rnd))
+    monkeypatch.setenv("MSQ_QUANT_TMA", "0")
+    r0 = _ops.mx_outlier(W.cuda(), 8, 8, fi, fo, 2, 0, bs, rnd)
+    assert r0.path == 1
+    assert torch.equal(r.deq.view(torch.int32), r0.deq.view(torch.int32))
+
+
+def test_tma_staged_kernel_status_and_nonfinite(M):
+    """a NaN / Inf block raises the same status bit and the same NaN block as the direct-load kernel"""
+    from msq_b200 import _ops
+    W = weights(64, 512, 5)
+    W[17, 300] = float("inf")
+    st = torch.zeros(1, dtype=torch.int32, device="cuda")
+    r = _ops.mx_outlier(W.cuda(), 8, 8, "fp4_e2m1", "fp8_e4m3", 2, 0, 16, check=False, status=st)
+    assert r.path == 4 and int(st.item()) & _ops.N.ST_NONFINITE_INPUT
+    assert torch.isnan(r.deq[16:32, 300]).all() and not torch.isnan(r.deq[:, :300]).any()
+
+
 @pytest.mark.parametrize("fi,fo,bs,axis,shape,path", CASES)
 @pytest.mark.parametrize("rnd", ["nearest", "even"])
 def test_outlier_vs_oracle(M, fi, fo, bs, axis, shape, path, rnd):
