@@ -10,16 +10,13 @@
 //                and cpp/mx.cuh:37-52 + cpp/shared_exp.cuh:14-53 (mode 1)
 #pragma once
 #include "msq_common.cuh"
+#include <string.h>
 
 namespace msq {
 
 struct QCfg {
   Fmt fin, fout;
   EncC enc_i, enc_o;   // code encoders of fin / fout, filled by finish_cfg() on the host
-  // integer-domain encoder of the fused rounding (core_outlier): code = min(k + (exponent steps << tm), cmax) | sign
-  int ksh_i, ksh_o;    // 23 - trailing mantissa bits
-  int cmax_i, cmax_o;  // magnitude code of max_norm
-  int sgn_i, sgn_o;    // sign bit of the code
   int sb_in, sb_out;
   float std_dev;
   int flush;
@@ -27,25 +24,42 @@ struct QCfg {
   int mode;      // plain  : 0 = python (+1e-6), 1 = spec/native
   int rmode;     // Round
   float fzero;   // 0.0f the compiler cannot see (finish_cfg): addend that keeps a product an FFMA of its own
+  // float-domain encoder (core_outlier, packed path): code = (bits(|q| * sc) | sign bit at tb) >> (bits(ka) & 31).
+  // Each constant is chosen so that an exact 0/1 FFMA blend of the inlier and the outlier value yields the element's
+  // own constant as a BIT PATTERN (enc2_consts)
+  float sc_i, sc_o, ka_i, ka_o, tb_i, tb_o;
+  int enc2_ok;   // both formats representable (code width <= 8, ebits <= 5)
 };
 
-__host__ inline void enc_consts(const Fmt& f, int* ksh, int* cmax, int* sgn) {
-  const int tm = f.bits - 2;                       // trailing mantissa bits (ints: fractional bits)
+// |q| on the format grid times sc lands in fp32's own subnormal / lowest-normal range in such a way that the fp32 bit
+// pattern, shifted right by ksh2, IS the magnitude code: floats: sc = 2^(-126 - min_exp) maps the format's smallest
+// normal onto fp32's (exponent field 1, subnormals onto subnormals), ksh2 = 23 - trailing mantissa bits; integers:
+// sc = 2^-127 puts k = |q| / 2^-(bits-2) into the mantissa at bit 24 - bits.  The sign goes to bit ksh2 + width - 1 of the
+// unshifted pattern (an exponent bit that is always zero there).
+__host__ inline bool enc2_consts(const Fmt& f, float* sc, float* ka, float* tb) {
+  int ksh2, tbit, e2;
   if (f.ebits == 0) {
-    *ksh = 23; *cmax = (1 << (f.bits - 1)) - 1; *sgn = 1 << (f.bits - 1);
+    if (f.bits < 2 || f.bits > 8) return false;
+    ksh2 = 24 - f.bits; tbit = 23; e2 = -127;
   } else {
-    float q = f.max_norm;                          // k = max_norm / 2^(emax - tm), exact
-    for (int i = 0; i < f.emax - tm; ++i) q *= 0.5f;
-    for (int i = 0; i < tm - f.emax; ++i) q *= 2.0f;
-    *ksh = 23 - tm; *cmax = (int)q + ((f.emax - f.min_exp) << tm); *sgn = 1 << (f.ebits + tm);
+    const int tm = f.bits - 2;
+    if (f.ebits > 5 || 1 + f.ebits + tm > 8 || tm < 0) return false;
+    ksh2 = 23 - tm; tbit = 23 + f.ebits; e2 = -126 - f.min_exp;
   }
+  float v = 1.0f;
+  for (int i = 0; i < -e2; ++i) v *= 0.5f;
+  *sc = v;
+  *ka = 8388608.0f + (float)ksh2;
+  const uint32_t tb_bits = 1u << tbit;
+  memcpy(tb, &tb_bits, 4);
+  return true;
 }
 __host__ inline void finish_cfg(QCfg& c) {
   c.enc_i = make_enc(c.fin.ebits, c.fin.bits);
   c.enc_o = make_enc(c.fout.ebits, c.fout.bits);
-  enc_consts(c.fin, &c.ksh_i, &c.cmax_i, &c.sgn_i);
-  enc_consts(c.fout, &c.ksh_o, &c.cmax_o, &c.sgn_o);
   c.fzero = 0.0f;
+  const bool a = enc2_consts(c.fin, &c.sc_i, &c.ka_i, &c.tb_i), b = enc2_consts(c.fout, &c.sc_o, &c.ka_o, &c.tb_o);
+  c.enc2_ok = (a && b) ? 1 : 0;
 }
 
 // fp32 sum over the LPB lanes in canonical tree order: partner distance 1, 2, 4, ... continues the
@@ -179,6 +193,12 @@ __device__ __forceinline__ float fset_gt(float a, float b) {
   asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
   return d;
 }
+// comparison to an all-ones / all-zeros integer mask (SASS FSET without .BF)
+__device__ __forceinline__ uint32_t fset_lt_u32(float a, float b) {
+  uint32_t d;
+  asm("set.lt.u32.f32 %0, %1, %2;" : "=r"(d) : "f"(a), "f"(b));
+  return d;
+}
 __device__ __forceinline__ float fset_lt(float a, float b) {
   float d;
   asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
@@ -233,17 +253,6 @@ __device__ __forceinline__ float2 round_mag2_py_t(float2 v, float2 qn, float add
 __device__ __forceinline__ float2 round_mag2_py(float2 v, float2 qn, float addend, float2 M) {
   float2 t;
   return round_mag2_py_t(v, qn, addend, M, t);
-}
-// Sign-magnitude code straight from the rounding's integers (no float re-analysis of q):
-//   k          = bits(t) - bits(2^23 * quantum)
-//   exponent   = (bits(quantum) - bits(smallest quantum)) >> (23 - tm)      = (p - min_exp) << tm
-//   magnitude  = min(k + exponent, code(max_norm))          (codes are monotonic in |q|, so this is the clamp)
-// k = 2^(tm+1) carries into the exponent field by itself; subnormals and integer formats have exponent = 0.
-__device__ __forceinline__ uint32_t encode_k(float t, float qn, float LD, float q, int ksh, int cmax, int sgn) {
-  const int k = __float_as_int(t) - __float_as_int(qn) - (23 << 23);
-  const int e = (__float_as_int(qn) - __float_as_int(LD)) >> ksh;
-  const int mag = min(k + e, cmax);
-  return (uint32_t)(mag | ((q < 0.0f) ? sgn : 0));
 }
 // integer-mantissa rounding of cpp/quantize.cuh:88-149 on the exact value: nearest = half away from zero on the
 // truncated half-quantum count, even = ties to even, floor = truncation
@@ -331,7 +340,22 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
   for (int i = 0; i < N; ++i) {
     const float li = EXT ? lo_e[i] : l, hi_i = EXT ? hi_e[i] : h;
     mf[i] = fmaxf(fset_lt(x[i], li), fset_gt(x[i], hi_i));      // 0/1 float mask without predicates
-    if (CNT) fcnt = __fadd_rn(fcnt, mf[i]);
+    if (CNT && !(CODES && N % 2 == 0)) fcnt = __fadd_rn(fcnt, mf[i]);
+  }
+  if (CODES && N % 2 == 0) {
+    // the block's outlier bits as an integer: sum of mask_i * 2^i, exact in fp32 for 16 bits at a time, on the FMA
+    // pipe (two elements per FFMA2); the count is its popcount
+    static_assert(N <= 32, "mask is one 32-bit word");
+    float2 lo2 = f2s(0.0f), hi2 = f2s(0.0f);
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+      const int sh = i & 15;
+      const float2 wgt = f2((float)(1u << sh), (float)(2u << sh));
+      if (i < 16) lo2 = __ffma2_rn(f2(mf[i], mf[i + 1]), wgt, lo2);
+      else hi2 = __ffma2_rn(f2(mf[i], mf[i + 1]), wgt, hi2);
+    }
+    o.mask = __float2uint_rz(__fadd_rn(lo2.x, lo2.y));
+    if (N > 16) o.mask |= __float2uint_rz(__fadd_rn(hi2.x, hi2.y)) << 16;
   }
   if (N % 2 == 0) {
 #pragma unroll
@@ -350,7 +374,7 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
       m_in = fmaxf(m_in, fabsf(x[i]));
     }
   }
-  if (CNT) o.cnt = grp_add<LPB>((int)fcnt);
+  if (CNT) o.cnt = grp_add<LPB>((CODES && N % 2 == 0) ? __popc(o.mask) : (int)fcnt);
   m_in = grp_max<LPB>(m_in);
 
   const int S_in = (1 << (c.sb_in - 1)) - 1, S_out = (1 << (c.sb_out - 1)) - 1;
@@ -396,6 +420,7 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
   const float Dp_i = c.fin.ebits ? ci.down : 0.0f, Dp_o = c.fout.ebits ? co.down : 0.0f;
   const float LD_i = __fmul_rn(ci.L, ci.down), LD_o = __fmul_rn(co.L, co.down);
   const float dDp = __fsub_rn(Dp_o, Dp_i), dLD = __fsub_rn(LD_o, LD_i);
+  const float dSC = __fsub_rn(c.sc_o, c.sc_i), dKA = __fsub_rn(c.ka_o, c.ka_i), dTB = __fsub_rn(c.tb_o, c.tb_i);
   const EncC enc_i = c.enc_i, enc_o = c.enc_o;
   auto encode_sel = [&](float qv, bool isout) {
     EncC e;
@@ -427,11 +452,17 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
       q.x = copysignf(q.x, v.x);
       q.y = copysignf(q.y, v.y);
       if (CODES) {
-        const bool o0 = mf[i] != 0.0f, o1 = mf[i + 1] != 0.0f;
-        code[i] = encode_k(t.x, qn.x, LD2.x, q.x, o0 ? c.ksh_o : c.ksh_i, o0 ? c.cmax_o : c.cmax_i, o0 ? c.sgn_o : c.sgn_i);
-        code[i + 1] = encode_k(t.y, qn.y, LD2.y, q.y, o1 ? c.ksh_o : c.ksh_i, o1 ? c.cmax_o : c.cmax_i, o1 ? c.sgn_o : c.sgn_i);
-        o.mask |= (o0 ? 1u : 0u) << i;
-        o.mask |= (o1 ? 1u : 0u) << (i + 1);
+        // float-domain encoder (enc2_consts): the element's own scale / shift / sign-bit constants are exact 0/1 blends
+        // on the FMA pipe, |q| (already clamped to max_norm) is scaled into fp32's lowest binades where its bit
+        // pattern is the magnitude code; the sign is set only for q < 0 (a rounded-to-zero negative keeps code 0)
+        const float2 aq = f2(fabsf(q.x), fabsf(q.y));
+        const float2 y = __fmul2_rn(aq, cblend2(c.sc_i, dSC, m));
+        const float2 KA = cblend2(c.ka_i, dKA, m), TB = cblend2(c.tb_i, dTB, m);
+        const uint32_t s0 = fset_lt_u32(q.x, 0.0f), s1 = fset_lt_u32(q.y, 0.0f);
+        const uint32_t p0 = (uint32_t)__float_as_int(y.x) | (s0 & (uint32_t)__float_as_int(TB.x));
+        const uint32_t p1 = (uint32_t)__float_as_int(y.y) | (s1 & (uint32_t)__float_as_int(TB.y));
+        code[i] = __funnelshift_r(p0, 0u, (uint32_t)__float_as_int(KA.x));          // shift count = low 5 bits
+        code[i + 1] = __funnelshift_r(p1, 0u, (uint32_t)__float_as_int(KA.y));
       }
       x[i] = q.x; x[i + 1] = q.y;
     }

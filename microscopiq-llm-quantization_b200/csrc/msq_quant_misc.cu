@@ -257,6 +257,7 @@ static int launch_quant(QParams& P, bool outlier, cudaStream_t stream, int* path
     if (!P.codes || !P.e_in) return MSQ_ERR_BAD_ARG;
     if (outlier && (!P.bitmap || !P.e_out || (P.hi_w > 0 && !P.hi))) return MSQ_ERR_BAD_ARG;
     if (!aligned16(P.codes) || !aligned16(P.bitmap) || !aligned16(P.hi)) return MSQ_ERR_ALIGN;
+    if (outlier && !P.c.enc2_ok) return MSQ_ERR_UNSUPPORTED;     // codes wider than 8 bits have no packed form
   } else if (!P.deq && !P.mask && !P.e_in && !P.blk_cnt) {
     return MSQ_ERR_BAD_ARG;
   }
