@@ -29,6 +29,11 @@ struct QCfg {
   // own constant as a BIT PATTERN (enc2_consts)
   float sc_i, sc_o, ka_i, ka_o, tb_i, tb_o;
   int enc2_ok;   // both formats representable (code width <= 8, ebits <= 5)
+  // hi-field accumulation of the packing kernels (HI template flag of core_outlier): bit patterns 1 (inlier) and
+  // 1 << hi_w (outlier) blended per element like the constants above; hi_mulhi = 2^(32 - slot width) turns
+  // "code >> slot width" into a multiply-high
+  float mu_i, mu_o;
+  unsigned int hi_mulhi;
 };
 
 // |q| on the format grid times sc lands in fp32's own subnormal / lowest-normal range in such a way that the fp32 bit
@@ -60,6 +65,14 @@ __host__ inline void finish_cfg(QCfg& c) {
   c.fzero = 0.0f;
   const bool a = enc2_consts(c.fin, &c.sc_i, &c.ka_i, &c.tb_i), b = enc2_consts(c.fout, &c.sc_o, &c.ka_o, &c.tb_o);
   c.enc2_ok = (a && b) ? 1 : 0;
+  {
+    const int d = c.fout.width - c.fin.width;
+    const int hi_w = d <= 0 ? 0 : (d <= 2 ? 2 : (d <= 4 ? 4 : 8));
+    const uint32_t one = 1u, mo = 1u << hi_w;
+    memcpy(&c.mu_i, &one, 4);
+    memcpy(&c.mu_o, &mo, 4);
+    c.hi_mulhi = 1u << (32 - c.fin.width);
+  }
 }
 
 // fp32 sum over the LPB lanes in canonical tree order: partner distance 1, 2, 4, ... continues the
@@ -161,6 +174,8 @@ struct BlockOut {
   int e_in, e_out; // clamped shared exponents (MSQ_EXP_NAN on overflow)
   int cnt;         // outliers in the whole block (all lanes)
   int st;          // status bits raised by this block
+  // HI: compacted hi fields (outlier code >> slot width) of elements 8g .. 8g+7, first outlier in the lowest bits
+  uint32_t hacc[4];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -275,7 +290,7 @@ __device__ __forceinline__ float2 round_mag2_native(float2 v, float2 qn, int rmo
   return f2(fminf(qx, M.x), fminf(qy, M.y));
 }
 
-template <int N, int LPB, bool CODES, bool EXT, bool CNT = true>
+template <int N, int LPB, bool CODES, bool EXT, bool CNT = true, bool HI = false>
 __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)[N], const QCfg& c,
                                                  const float* lo_e, const float* hi_e) {
   constexpr int BS = N * LPB;
@@ -421,6 +436,9 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
   const float LD_i = __fmul_rn(ci.L, ci.down), LD_o = __fmul_rn(co.L, co.down);
   const float dDp = __fsub_rn(Dp_o, Dp_i), dLD = __fsub_rn(LD_o, LD_i);
   const float dSC = __fsub_rn(c.sc_o, c.sc_i), dKA = __fsub_rn(c.ka_o, c.ka_i), dTB = __fsub_rn(c.tb_o, c.tb_i);
+  const float dMU = __fsub_rn(c.mu_o, c.mu_i);
+  uint32_t hw = 1u;          // HI: weight of the next hi field inside its group of eight elements
+  if (HI) { o.hacc[0] = o.hacc[1] = o.hacc[2] = o.hacc[3] = 0u; }
   const EncC enc_i = c.enc_i, enc_o = c.enc_o;
   auto encode_sel = [&](float qv, bool isout) {
     EncC e;
@@ -458,11 +476,25 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
         const float2 aq = f2(fabsf(q.x), fabsf(q.y));
         const float2 y = __fmul2_rn(aq, cblend2(c.sc_i, dSC, m));
         const float2 KA = cblend2(c.ka_i, dKA, m), TB = cblend2(c.tb_i, dTB, m);
-        const uint32_t s0 = fset_lt_u32(q.x, 0.0f), s1 = fset_lt_u32(q.y, 0.0f);
-        const uint32_t p0 = (uint32_t)__float_as_int(y.x) | (s0 & (uint32_t)__float_as_int(TB.x));
-        const uint32_t p1 = (uint32_t)__float_as_int(y.y) | (s1 & (uint32_t)__float_as_int(TB.y));
+        // sign bit: q + 0 turns a -0 into +0, so the sign of the sum is "q < 0"; bit 31 -> 0/1 by a multiply-high
+        // and into place by a multiply-add (FMA pipe; the logic pipe is the busy one in the packing kernels)
+        const float2 qz = __fadd2_rn(q, f2s(0.0f));
+        const uint32_t s0 = __umulhi((uint32_t)__float_as_int(qz.x), 2u), s1 = __umulhi((uint32_t)__float_as_int(qz.y), 2u);
+        const uint32_t p0 = s0 * (uint32_t)__float_as_int(TB.x) + (uint32_t)__float_as_int(y.x);
+        const uint32_t p1 = s1 * (uint32_t)__float_as_int(TB.y) + (uint32_t)__float_as_int(y.y);
         code[i] = __funnelshift_r(p0, 0u, (uint32_t)__float_as_int(KA.x));          // shift count = low 5 bits
         code[i + 1] = __funnelshift_r(p1, 0u, (uint32_t)__float_as_int(KA.y));
+        if (HI) {
+          // compacted hi fields without predicates or variable shifts: field * weight summed, the weight multiplied by
+          // 2^hi_w after every outlier and by 1 after an inlier (whose field is zero); all on the FMA pipe
+          if ((i & 7) == 0) hw = 1u;
+          const float2 MU = cblend2(c.mu_i, dMU, m);
+          uint32_t& acc = o.hacc[(i >> 3) & 3];
+          acc = __umulhi(code[i], c.hi_mulhi) * hw + acc;
+          hw *= (uint32_t)__float_as_int(MU.x);
+          acc = __umulhi(code[i + 1], c.hi_mulhi) * hw + acc;
+          hw *= (uint32_t)__float_as_int(MU.y);
+        }
       }
       x[i] = q.x; x[i + 1] = q.y;
     }
@@ -500,6 +532,11 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
       if (CODES) {
         code[i] = encode_sel(qv, isout);
         o.mask |= (isout ? 1u : 0u) << i;
+        if (HI) {
+          if ((i & 7) == 0) hw = 1u;
+          o.hacc[(i >> 3) & 3] += __umulhi(code[i], c.hi_mulhi) * hw;
+          hw *= isout ? (uint32_t)__float_as_int(c.mu_o) : 1u;
+        }
       }
       const float r = isout ? __fmul_rn(__fmul_rn(qv, s_out), inv_s_in) : __fmul_rn(qv, s_in);
       x[i] = __fadd_rn(r, 0.0f);
@@ -508,6 +545,7 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
   if (dead) {      // NaN/Inf input or a shared exponent above the scale range: the reference asserts
 #pragma unroll
     for (int i = 0; i < N; ++i) { x[i] = qnan(); if (CODES) code[i] = 0u; }
+    if (HI) { o.hacc[0] = o.hacc[1] = o.hacc[2] = o.hacc[3] = 0u; }
   }
   return o;
 }

@@ -44,6 +44,26 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() {
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the time is up, so the
+// producer warp does not take issue slots from the compute warps of its scheduler while it waits (a plain try_wait
+// loop was measured at 14 % of all issued instructions)
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(tc::smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {}
+}
+
 template <int BS, int TW, int MINB>
 __global__ void __launch_bounds__(TW + 32, MINB) k_strided_tma(const __grid_constant__ TmaQParams P) {
   // stages first (the only shared memory of the kernel, so the declared alignment holds), barriers behind them
@@ -87,7 +107,7 @@ __global__ void __launch_bounds__(TW + 32, MINB) k_strided_tma(const __grid_cons
       for (int k = 0; k < pre; ++k) load(k);
       for (int k = 0; k < n_mine; ++k) {
         const int s = k % TQ_NST;
-        tc::mbar_wait(&done[s], (uint32_t)(k / TQ_NST) & 1u);     // every consumer has written its column back
+        mbar_wait_sleep(&done[s], (uint32_t)(k / TQ_NST) & 1u);   // every consumer has written its column back
         int t, c0, c1;
         decode(k, t, c0, c1);
         tma_store_2d(&P.tout[t], tiles + (size_t)s * STAGE_FLOATS, c0, c1);
@@ -178,11 +198,17 @@ __device__ __forceinline__ void stage_codes4_16(uint32_t* cd, const uint32_t* c,
   const int g = lane & 7;
   uint32_t W0, W1;
   {
-    uint32_t B[8];
+    // four codes (<= 8 bits each) per word by multiply-adds (sums of disjoint bytes), low nibbles kept, adjacent
+    // nibbles merged: byte 0 / byte 2 of t = rows (4j, 4j+1) / (4j+2, 4j+3)
+    uint32_t t[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) B[k] = (c[2 * k] & 0xFu) | ((c[2 * k + 1] << 4) & 0xF0u);
-    W0 = __byte_perm(__byte_perm(B[0], B[1], 0x0040), __byte_perm(B[2], B[3], 0x0040), 0x5410);
-    W1 = __byte_perm(__byte_perm(B[4], B[5], 0x0040), __byte_perm(B[6], B[7], 0x0040), 0x5410);
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t w = ((c[4 * j + 3] * 256u + c[4 * j + 2]) * 256u + c[4 * j + 1]) * 256u + c[4 * j];
+      const uint32_t l = w & 0x0F0F0F0Fu;
+      t[j] = l | (l >> 4);
+    }
+    W0 = __byte_perm(t[0], t[1], 0x6420);
+    W1 = __byte_perm(t[2], t[3], 0x6420);
   }
   {
     const uint32_t r = __shfl_xor_sync(0xffffffffu, (g & 4) ? W0 : W1, 4);
@@ -207,7 +233,29 @@ __device__ __forceinline__ void stage_codes4_16(uint32_t* cd, const uint32_t* c,
   dst[32] = row_hi;
 }
 
-constexpr int TP_NST = 4;
+// bitmap of a tile without ballots: the 32 x 16 bit matrix (lane = column, bit = row) is transposed by a 5-stage
+// butterfly -- lanes j and j^16 first share one 32-bit word [M_(j|16) : M_(j&15)], then four swap stages on the two
+// 16 x 16 halves at once (one shuffle, one rotate, one bitwise select each) -- after which lane r < 16 holds row r's word
+template <int D>
+__device__ __forceinline__ uint32_t bfly_stage(uint32_t v, int lane) {
+  constexpr uint32_t m = D == 8 ? 0x00FF00FFu : (D == 4 ? 0x0F0F0F0Fu : (D == 2 ? 0x33333333u : 0x55555555u));
+  const uint32_t t = __shfl_xor_sync(0xffffffffu, v, D);
+  const bool up = (lane & D) != 0;
+  // upper lane: its left columns take the partner's right columns (t >> D); lower lane: the mirror image
+  return up ? ((v & ~m) | ((t >> D) & m)) : ((v & m) | ((t << D) & ~m));
+}
+__device__ __forceinline__ void stage_bitmap16(uint32_t* bm_row0, uint32_t M, int lane) {
+  const uint32_t o = __shfl_xor_sync(0xffffffffu, M, 16);
+  uint32_t v = (lane & 16) ? (o | (M << 16)) : (M | (o << 16));
+  v = bfly_stage<8>(v, lane);
+  v = bfly_stage<4>(v, lane);
+  v = bfly_stage<2>(v, lane);
+  v = bfly_stage<1>(v, lane);
+  if (lane < 16) bm_row0[lane * (256 / 32)] = v;
+}
+
+constexpr int TP_NST = 5;      // input ring
+constexpr int TP_NOUT = 3;     // staging buffers of the output planes (a freed buffer is needed one whole tile later)
 constexpr int TP_TW = 256;
 
 template <int BS>
@@ -217,20 +265,24 @@ __global__ void __launch_bounds__(TP_TW + 32, 2) k_pack_tma(const __grid_constan
   constexpr int STAGE_FLOATS = BS * TP_TW;
   constexpr uint32_t STAGE_BYTES = STAGE_FLOATS * 4;
   constexpr int CD_BYTES = BS * (TP_TW / 2), BM_BYTES = BS * (TP_TW / 8), EX_BYTES = TP_TW;
-  constexpr int OUT_BYTES = CD_BYTES + BM_BYTES + 2 * EX_BYTES;      // staging per stage (3 KB)
+  constexpr int OUT_BYTES = CD_BYTES + BM_BYTES + 2 * EX_BYTES;      // staging per tile (3 KB), double-buffered
   float* tiles = reinterpret_cast<float*>(smem_raw);
   unsigned char* outs = smem_raw + (size_t)TP_NST * STAGE_BYTES;
-  unsigned long long* s_acc = reinterpret_cast<unsigned long long*>(outs + (size_t)TP_NST * OUT_BYTES);
+  unsigned long long* s_acc = reinterpret_cast<unsigned long long*>(outs + TP_NOUT * OUT_BYTES);
   uint32_t* s_hi = reinterpret_cast<uint32_t*>(s_acc + MSQ_SEG_BLOCKS);          // MSQ_SEG_BLOCKS * BS * 4 / 8 bytes max
   unsigned char* s_cnt = reinterpret_cast<unsigned char*>(s_hi + MSQ_SEG_BLOCKS * BS * 4 / 32);
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_cnt + MSQ_SEG_BLOCKS);
-  uint64_t* done = full + TP_NST;
-  int* s_warp = reinterpret_cast<int*>(done + TP_NST);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_cnt + MSQ_SEG_BLOCKS);   // producer -> consumers: tile landed
+  uint64_t* empty = full + TP_NST;                                         // consumers -> producer: tile is in registers
+  uint64_t* sdone = empty + TP_NST;                                        // consumers -> producer: staging written
+  uint64_t* sfree = sdone + TP_NOUT;                                       // producer -> consumers: staging read out
+  int* s_warp = reinterpret_cast<int*>(sfree + TP_NOUT);
   const int tid = (int)threadIdx.x;
   const int hi_w = P.hi_w;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < TP_NST; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&done[s], TP_TW); }
+    for (int s = 0; s < TP_NST; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], TP_TW); }
+#pragma unroll
+    for (int s = 0; s < TP_NOUT; ++s) { tc::mbar_init(&sdone[s], TP_TW); tc::mbar_init(&sfree[s], 1); }
     tc::mbar_fence_init();
   }
   for (int i = tid; i < MSQ_SEG_BLOCKS * BS * 4 / 32; i += TP_TW + 32) s_hi[i] = 0;
@@ -258,22 +310,30 @@ __global__ void __launch_bounds__(TP_TW + 32, 2) k_pack_tma(const __grid_constan
       };
       const int pre = n_mine < TP_NST ? n_mine : TP_NST;
       for (int k = 0; k < pre; ++k) load(k);
+      int si = 0, so = 0;                    // input stage / staging buffer of tile k
+      uint32_t pi = 0, po = 0;               // their phase parities
       for (int k = 0; k < n_mine; ++k) {
-        const int s = k % TP_NST;
-        tc::mbar_wait(&done[s], (uint32_t)(k / TP_NST) & 1u);
+        // the input stage is free as soon as every consumer holds its block in registers: refill it right away
+        if (k + TP_NST < n_mine) {
+          mbar_wait_sleep(&empty[si], pi);
+          load(k + TP_NST);
+        }
+        mbar_wait_sleep(&sdone[so], po);
         const unsigned int q = tile_of(k);
         int cx, r0;
         coords(q, cx, r0);
-        const unsigned char* o = outs + (size_t)s * OUT_BYTES;
+        const unsigned char* o = outs + (size_t)so * OUT_BYTES;
         tma_store_2d(&P.tcodes, o, cx * (TP_TW / 2), r0);
         tma_store_2d(&P.tbitmap, o + CD_BYTES, cx * (TP_TW / 8), r0);
         bulk_store_1d(P.e_in + (size_t)q * TP_TW, o + CD_BYTES + BM_BYTES, EX_BYTES);
         bulk_store_1d(P.e_out + (size_t)q * TP_TW, o + CD_BYTES + BM_BYTES + EX_BYTES, EX_BYTES);
         bulk_commit();
-        if (k >= 1 && k - 1 + TP_NST < n_mine) {
+        if (k >= 1) {                     // the stores of tile k-1 have left their staging buffer
           bulk_wait_read<1>();
-          load(k - 1 + TP_NST);
+          tc::mbar_arrive(&sfree[so == 0 ? TP_NOUT - 1 : so - 1]);
         }
+        if (++si == TP_NST) { si = 0; pi ^= 1u; }
+        if (++so == TP_NOUT) { so = 0; po ^= 1u; }
       }
       bulk_wait_all();
     }
@@ -282,49 +342,38 @@ __global__ void __launch_bounds__(TP_TW + 32, 2) k_pack_tma(const __grid_constan
 
   const int lane = tid & 31, warp = tid >> 5;
   int st = 0;
+  int s = 0, b2 = 0;                       // input stage / staging buffer of tile k
+  uint32_t ph = 0, pf = 1;                 // parity of full[s]; parity that makes the first sfree wait pass at once
 #pragma unroll 1
   for (int k = 0; k < n_mine; ++k) {
-    const int s = k % TP_NST, u = k & 3;
-    tc::mbar_wait(&full[s], (uint32_t)(k / TP_NST) & 1u);
+    const int u = k & 3;
+    tc::mbar_wait(&full[s], ph);
     const float* tp = tiles + (size_t)s * STAGE_FLOATS + tid;
     float x[BS];
     uint32_t code[BS];
 #pragma unroll
     for (int i = 0; i < BS; ++i) x[i] = tp[i * TP_TW];
-    const BlockOut bo = core_outlier<BS, 1, true, false, true>(x, code, P.c, nullptr, nullptr);
+    tc::mbar_arrive(&empty[s]);
+    const BlockOut bo = core_outlier<BS, 1, true, false, true, true>(x, code, P.c, nullptr, nullptr);
     st |= bo.st;
-    unsigned char* o = outs + (size_t)s * OUT_BYTES;
+    // staging buffer b2 was last used by tile k - TP_NOUT: wait until its stores have read it
+    tc::mbar_wait(&sfree[b2], pf);
+    unsigned char* o = outs + (size_t)b2 * OUT_BYTES;
     stage_codes4_16(reinterpret_cast<uint32_t*>(o), code, lane, warp);
-    {
-      uint32_t* bm = reinterpret_cast<uint32_t*>(o + CD_BYTES) + warp;       // 8 words per row
-#pragma unroll
-      for (int i = 0; i < BS; ++i) {
-        const uint32_t w = __ballot_sync(0xffffffffu, bo.mask & (1u << i));
-        if (lane == 0) bm[i * (TP_TW / 32)] = w;
-      }
-    }
+    stage_bitmap16(reinterpret_cast<uint32_t*>(o + CD_BYTES) + warp, bo.mask, lane);
     o[CD_BYTES + BM_BYTES + tid] = (unsigned char)(int8_t)bo.e_in;
     o[CD_BYTES + BM_BYTES + EX_BYTES + tid] = (unsigned char)(int8_t)bo.e_out;
     if (hi_w > 0) {
-      // hi fields of the block, first outlier in the lowest bits: two 32-bit halves built by predicated
-      // multiply-adds (walking backwards), joined by the number of outliers in the low half
-      uint32_t a0 = 0, a1 = 0;
-      const uint32_t mul = 1u << hi_w;
-      if (bo.cnt) {
-#pragma unroll
-        for (int i = 7; i >= 0; --i)
-          if (bo.mask & (1u << i)) a0 = a0 * mul + (code[i] >> 4);
-#pragma unroll
-        for (int i = 15; i >= 8; --i)
-          if (bo.mask & (1u << i)) a1 = a1 * mul + (code[i] >> 4);
-      }
+      // the two 32-bit halves of the block's compacted hi fields (core_outlier<.., HI>), joined by the number of
+      // outliers in the low half
       const int sh = __popc(bo.mask & 0xFFu) * hi_w;                       // <= 32
-      const unsigned long long acc = (unsigned long long)a0 | (sh < 32 ? ((unsigned long long)a1 << sh) : ((unsigned long long)a1 << 32));
-      s_acc[u * TP_TW + tid] = acc;
+      s_acc[u * TP_TW + tid] = (unsigned long long)bo.hacc[0] | ((unsigned long long)bo.hacc[1] << sh);
       s_cnt[u * TP_TW + tid] = (unsigned char)bo.cnt;
     }
     fence_proxy_async_smem();
-    tc::mbar_arrive(&done[s]);
+    tc::mbar_arrive(&sdone[b2]);
+    if (++s == TP_NST) { s = 0; ph ^= 1u; }
+    if (++b2 == TP_NOUT) { b2 = 0; pf ^= 1u; }
 
     if (u == 3 || k == n_mine - 1) {
       const unsigned int sg = first + (unsigned)(k >> 2) * G;
@@ -463,9 +512,9 @@ int launch_pack_tma(const QParams& Q, cudaStream_t stream) {
   P.gx = (int)(Q.post / TP_TW);
   magic_div(P.gx, &P.gx_m, &P.gx_k);
   auto k = k_pack_tma<16>;
-  const size_t smem = (size_t)TP_NST * (16 * TP_TW * 4 + 16 * (TP_TW / 2) + 16 * (TP_TW / 8) + 2 * TP_TW) +
+  const size_t smem = (size_t)TP_NST * (16 * TP_TW * 4) + TP_NOUT * (16 * (TP_TW / 2) + 16 * (TP_TW / 8) + 2 * TP_TW) +
                       (size_t)MSQ_SEG_BLOCKS * 8 + (size_t)MSQ_SEG_BLOCKS * 16 * 4 / 8 + MSQ_SEG_BLOCKS +
-                      2 * TP_NST * sizeof(uint64_t) + 8 * sizeof(int) + 64;
+                      (2 * TP_NST + 2 * TP_NOUT) * sizeof(uint64_t) + 8 * sizeof(int) + 64;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
