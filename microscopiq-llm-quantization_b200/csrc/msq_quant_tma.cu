@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(TW + 32, MINB) k_strided_tma(const __grid_cons
 #pragma unroll 1
   for (int k = 0; k < n_mine; ++k) {
     const int s = k % TQ_NST;
-    tc::mbar_wait(&full[s], (uint32_t)(k / TQ_NST) & 1u);
+    mbar_wait_sleep(&full[s], (uint32_t)(k / TQ_NST) & 1u);
     float* tp = tiles + (size_t)s * STAGE_FLOATS + tid;
     float x[BS];
     uint32_t code[BS];
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(TP_TW + 32, 2) k_pack_tma(const __grid_constan
 #pragma unroll 1
   for (int k = 0; k < n_mine; ++k) {
     const int u = k & 3;
-    tc::mbar_wait(&full[s], ph);
+    mbar_wait_sleep(&full[s], ph);
     const float* tp = tiles + (size_t)s * STAGE_FLOATS + tid;
     float x[BS];
     uint32_t code[BS];
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(TP_TW + 32, 2) k_pack_tma(const __grid_constan
     const BlockOut bo = core_outlier<BS, 1, true, false, true, true>(x, code, P.c, nullptr, nullptr);
     st |= bo.st;
     // staging buffer b2 was last used by tile k - TP_NOUT: wait until its stores have read it
-    tc::mbar_wait(&sfree[b2], pf);
+    mbar_wait_sleep(&sfree[b2], pf);
     unsigned char* o = outs + (size_t)b2 * OUT_BYTES;
     stage_codes4_16(reinterpret_cast<uint32_t*>(o), code, lane, warp);
     stage_bitmap16(reinterpret_cast<uint32_t*>(o + CD_BYTES) + warp, bo.mask, lane);
