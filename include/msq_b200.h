@@ -276,6 +276,18 @@ int msq_gemm_mxfp4w_blockscaled(const unsigned char* xcodes, long long ldx, cons
                                 const int* o_k, const float* o_dw, float* C, long long ldc, int M, int N, int K,
                                 int accumulate, void* stream);
 
+/* GEMM-ready layout of a K-blocked FP4 weight for the decode sizes: per (128-row tile, 128-wide K block) one contiguous
+ * 8 KB chunk of codes and one 512-byte chunk of UE8M0 scales in the tcgen05.cp layout, so that a pipeline stage is two
+ * contiguous DRAM reads instead of 128 64-byte row segments and 128 scattered scale words.  Built once per weight
+ * (the reference has no packed inference path: number_system/mx/linear.py:66-91 multiplies fake-quantized tensors).
+ *   codes_tiled: ceil(N/128) * (K/128) * 8192 bytes, 32-byte aligned;  sf_tiled: ceil(N/128) * (K/128) * 512 bytes. */
+int msq_tile_fp4_weight(const unsigned char* wcodes, const signed char* we_in, unsigned char* codes_tiled,
+                        unsigned char* sf_tiled, int N, int K, void* stream);
+int msq_gemm_mxfp4w_tiled_blockscaled(const unsigned char* xcodes, long long ldx, const signed char* xe,
+                                      const unsigned char* codes_tiled, const unsigned char* sf_tiled,
+                                      const int* o_ptr, const int* o_k, const float* o_dw, float* C, long long ldc,
+                                      int M, int N, int K, int accumulate, void* stream);
+
 /* compute-bound variant of the block-scaled path: widen the packed FP4 weight once to dense MX-FP8
  * (E4M3 bytes [N,K] + UE8M0 scales [N,K/32]), then run the GEMM with both operands streamed by TMA. */
 int msq_widen_fp4_to_mxfp8(const unsigned char* wcodes, const unsigned int* wbitmap, const signed char* we_in,

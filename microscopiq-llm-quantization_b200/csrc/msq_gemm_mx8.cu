@@ -18,16 +18,20 @@
 // tcgen05.cp.32x128b.warpx4 (one 32-bit TMEM column per 32 rows, broadcast to the four lane quarters);
 // the MMA for K-block kb selects byte kb through the a_sf_id / b_sf_id fields of the instruction
 // descriptor.  The weight tile is the UMMA M operand (SFA = weight scales), the activations the N operand.
+#include <stdlib.h>
 #include "msq_api_internal.h"
 #include "msq_common.cuh"
 #include "msq_tc.cuh"
 
 namespace msq {
 
-constexpr int XM = 128, XBK = 128, XSTAGES = 4, XMAXN = 256;
+constexpr int XM = 128, XBK = 128, XSTAGES = 4, XMAXST = 8, XMAXN = 256;   // XSTAGES: ring at full activation tiles; XMAXST: at small ones
 constexpr int XA_BYTES = XM * XBK, XB_BYTES = XMAXN * XBK;          // 1 byte per element
 constexpr int XSF_BYTES = 512 + 1024;                                // SFA chunk + two SFB chunks
-constexpr int MX8_SMEM = XSTAGES * (XA_BYTES + XB_BYTES + XSF_BYTES) + 1024 + 256;
+constexpr int XRAW_BYTES = XM * XBK / 2;                             // packed FP4 codes of one (128-row, 128-k) chunk
+constexpr int MX8_SMEM = 225 * 1024;   // one CTA per SM: XSTAGES full stages, or XMAXST small ones + the staged activation scales
+static_assert(XSTAGES * (XA_BYTES + XB_BYTES + XSF_BYTES) + 1024 + 256 <= MX8_SMEM, "ring");
+static_assert(XMAXST * (XA_BYTES + 4096 + XSF_BYTES) + 1024 + 256 <= MX8_SMEM, "ring");
 constexpr uint32_t TM_ACC = 0, TM_SFA = 256, TM_SFB = 260;           // TMEM columns
 
 struct Mx8Params {
@@ -44,6 +48,13 @@ struct Mx8Params {
   // into a 16-byte chunk, the layout kind::mxf8f6f4 reads E2M1 from); scales = we_in; no thread touches a weight.
   // Outliers (value q * 2^(e_out - e_in) instead of the q * 2^e_in the hardware computes) are a sparse CSR
   // correction applied by the epilogue warps:  C[m, n] += sum_e x[m, o_k[e]] * o_dw[e]  for e in row n.
+  int nst;                    // ring depth (XSTAGES, or up to XMAXST when the activation tile is small: decode sizes are latency-bound)
+  int xb_bytes;               // bytes of one activation stage
+  int sfb_pre;                // tiled mode, one tile per CTA: the activation scale chunks of the CTA's whole K slice are staged
+                              // once before the main loop (the per-stage generic-proxy store + proxy fence -- which also waits
+                              // for the prefetch loads in flight: ~1000 cycles per stage -- leaves the pipeline)
+  int wtiled;                 // FP4-by-TMA with the weight re-laid out tile by tile (msq_tile_fp4_weight): every stage is ONE
+  const uint8_t* wsf_tiled;   // contiguous 8 KB code chunk + ONE 512-byte scale chunk already in the tcgen05.cp layout
   int wfp4;
   int w_fmt;                  // tensor-core format code of the weight operand (0 = E4M3, 5 = E2M1)
   int w_tx_bytes;             // bytes the weight TMA load reports to the mbarrier
@@ -59,6 +70,11 @@ __device__ __forceinline__ uint64_t make_sf_desc(uint32_t smem_addr) {
   d |= (uint64_t)1 << 46;
   return d;
 }
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(tc::smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void utccp_32x128b(uint32_t tmem_addr, uint64_t desc) {
   asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(tmem_addr), "l"(desc) : "memory");
 }
@@ -73,6 +89,20 @@ __device__ __forceinline__ void umma_mxf8(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb)
       : "memory");
 }
+// one lane of a converged warp (elect.sync): the compiler knows that a region guarded by it runs on exactly one lane and
+// moves the (warp-uniform) operands of the tcgen05 instructions to uniform registers with a single R2UR each -- guarded by
+// `lane == 0` it emits an ELECT / R2UR.BROADCAST loop per operand instead
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 // block-scaled instruction descriptor: E4M3 x E4M3 -> F32, UE8M0 scales, both K-major
 //   [4,6) b_sf_id  [7,10) A fmt  [10,13) B fmt  [17,23) N>>3  [23] scale fmt (1 = E8M0)  [24,29) M>>4  [29,31) a_sf_id
 __device__ __forceinline__ uint32_t make_idesc_mx8(int M, int N, int sf_id) {
@@ -85,32 +115,29 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                      // W tiles (E4M3 bytes)
-  uint8_t* sB = smem + XSTAGES * XA_BYTES;                 // X tiles
-  uint8_t* sSF = smem + XSTAGES * (XA_BYTES + XB_BYTES);   // per stage: SFA[512] | SFB[1024]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sSF + XSTAGES * XSF_BYTES);
+  const int NST = P.nst, XBB = P.xb_bytes;
+  uint8_t* sB = smem + NST * XA_BYTES;                     // X tiles
+  uint8_t* sSF = smem + NST * (XA_BYTES + XBB);            // per stage: SFA[512] | SFB[1024]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSF + NST * XSF_BYTES);
   uint64_t* full = bars;
-  uint64_t* empty = bars + XSTAGES;
-  uint64_t* acc_full = bars + 2 * XSTAGES;
-  uint64_t* acc_empty = bars + 2 * XSTAGES + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * XSTAGES + 2);
+  uint64_t* empty = bars + XMAXST;
+  uint64_t* acc_full = bars + 2 * XMAXST;
+  uint64_t* acc_empty = bars + 2 * XMAXST + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * XMAXST + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = P.tiles_n * P.tiles_m * P.ksplit;
   const int kblocks_total = (P.K + XBK - 1) / XBK;
 
+  uint8_t* presf = reinterpret_cast<uint8_t*>(bars) + 256;   // sfb_pre: one 512-byte chunk per K block of this CTA's slice
   if (warp == 0 && lane == 0) tc::tma_prefetch_desc(&tmX);
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < XSTAGES; ++i) { tc::mbar_init(&full[i], 1 + 8); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < NST; ++i) { tc::mbar_init(&full[i], P.sfb_pre ? 1 : 1 + 8); tc::mbar_init(&empty[i], 1); }
     tc::mbar_init(acc_full, 1);
     tc::mbar_init(acc_empty, 128);
     tc::mbar_fence_init();
   }
   if (warp == 2) tc::tmem_alloc<512>(tmem_slot);
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
   auto tile_coords = [&](int t, int& tn, int& tm, int& kb0, int& nkb) {
     const int ks = t % P.ksplit;
     const int r = t / P.ksplit;
@@ -118,6 +145,24 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
     kb0 = ks * P.kb_per_split;
     nkb = min(P.kb_per_split, kblocks_total - kb0);
   };
+  if (P.sfb_pre && (int)blockIdx.x < num_tiles) {
+    // activation scales of this CTA's (single) tile: word (m, kb) = the four UE8M0 bytes of K block kb, in the chunk layout
+    int tn, tm, kb0, nkb; tile_coords(blockIdx.x, tn, tm, kb0, nkb);
+    const int kblk32 = P.K >> 5;
+    for (int i = threadIdx.x; i < nkb * 128; i += blockDim.x) {
+      const int kbl = i >> 7, rr = i & 127;
+      const int m = tm * P.bnx + rr;
+      uint32_t w = 0x7F7F7F7Fu;
+      if (rr < P.bnx && m < P.M)
+        w = __vadd4(__ldg(reinterpret_cast<const uint32_t*>(P.xe + (long long)m * kblk32) + kb0 + kbl), 0x7F7F7F7Fu);
+      *reinterpret_cast<uint32_t*>(presf + kbl * 512 + (rr & 31) * 16 + (rr >> 5) * 4) = w;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);     // warp-uniform for the compiler, too
 
   if (warp == 0) {
     if (lane == 0) {
@@ -126,41 +171,57 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
         int tn, tm, kb0, nkb; tile_coords(t, tn, tm, kb0, nkb);
         for (int kb = kb0; kb < kb0 + nkb; ++kb) {
           tc::mbar_wait(&empty[stage], phase ^ 1);
-          tc::mbar_expect_tx(&full[stage], (uint32_t)(P.bnx * XBK + P.w_tx_bytes));
-          if (P.wdense || P.wfp4) tc::tma_load_2d(sA + stage * XA_BYTES, &tmW, &full[stage], kb * XBK, tn * XM);
-          tc::tma_load_2d(sB + stage * XB_BYTES, &tmX, &full[stage], kb * XBK, tm * P.bnx);
-          if (++stage == XSTAGES) { stage = 0; phase ^= 1; }
+          tc::mbar_expect_tx(&full[stage], (uint32_t)(P.bnx * XBK + P.w_tx_bytes + (P.wtiled ? 512 : 0)));
+          if (P.wtiled) {
+            const long long chunk = (long long)tn * kblocks_total + kb;
+            tc::tma_load_2d(sA + stage * XA_BYTES, &tmW, &full[stage], 0, (int)(chunk * XM));
+            bulk_load_1d(sSF + stage * XSF_BYTES, P.wsf_tiled + chunk * 512, 512, &full[stage]);
+          } else if (P.wdense || P.wfp4) tc::tma_load_2d(sA + stage * XA_BYTES, &tmW, &full[stage], kb * XBK, tn * XM);
+          tc::tma_load_2d(sB + stage * XBB, &tmX, &full[stage], kb * XBK, tm * P.bnx);
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      uint32_t acc_phase = 0;
-      const int sfb_chunks = (P.bnx + 127) / 128;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int tn, tm, kb0, nkb; tile_coords(t, tn, tm, kb0, nkb);
-        tc::mbar_wait(acc_empty, acc_phase ^ 1);
+    // ---- MMA issue.  The WHOLE warp runs the loop and only the tcgen05 instructions are predicated on lane 0: everything
+    // around them is then warp-uniform, lives in uniform registers and needs no R2UR transfers -- written under
+    // `if (lane == 0)` the body of this loop was 278 SASS instructions per stage, which at decode sizes (four 128x16x32
+    // MMAs per stage, ~30 cycles of tensor work) WAS the per-stage time of the kernel (~800 cycles, whatever the ring depth,
+    // the load path or the number of CTAs).  Descriptors are base + stage * constant (the address field cannot carry).
+    int stage = 0; uint32_t phase = 0;
+    uint32_t acc_phase = 0;
+    const int sfb_chunks = (P.bnx + 127) / 128;
+    const uint64_t ad0 = tc::make_kmajor_sw128_desc(tc::smem_u32(sA)), bd0 = tc::make_kmajor_sw128_desc(tc::smem_u32(sB));
+    const uint64_t sfd0 = make_sf_desc(tc::smem_u32(sSF)), psd0 = make_sf_desc(tc::smem_u32(presf));
+    const uint32_t a_step = (uint32_t)(XA_BYTES >> 4), b_step = (uint32_t)(XBB >> 4), sf_step = (uint32_t)(XSF_BYTES >> 4);
+    const uint32_t idesc0 = make_idesc_mx8(XM, P.bnx, 0) | ((uint32_t)P.w_fmt << 7);      // A format: 5 = E2M1
+    const uint32_t idesc_k = (1u << 4) | (1u << 29);                                       // next scale-factor id (both operands)
+    const uint32_t tacc = tmem_base + TM_ACC, tsfa = tmem_base + TM_SFA, tsfb = tmem_base + TM_SFB;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int tn, tm, kb0, nkb; tile_coords(t, tn, tm, kb0, nkb);
+      tc::mbar_wait(acc_empty, acc_phase ^ 1);
+      tc::tc_fence_after();
+      for (int kb = 0; kb < nkb; ++kb) {
+        tc::mbar_wait(&full[stage], phase);
         tc::tc_fence_after();
-        for (int kb = 0; kb < nkb; ++kb) {
-          tc::mbar_wait(&full[stage], phase);
-          tc::tc_fence_after();
-          const uint32_t sf_addr = tc::smem_u32(sSF + stage * XSF_BYTES);
-          utccp_32x128b(tmem_base + TM_SFA, make_sf_desc(sf_addr));
-          for (int c = 0; c < sfb_chunks; ++c) utccp_32x128b(tmem_base + TM_SFB + 4 * c, make_sf_desc(sf_addr + 512 + 512 * c));
-          const uint64_t ad = tc::make_kmajor_sw128_desc(tc::smem_u32(sA + stage * XA_BYTES));
-          const uint64_t bd = tc::make_kmajor_sw128_desc(tc::smem_u32(sB + stage * XB_BYTES));
+        const uint64_t ad = ad0 + (uint64_t)((uint32_t)stage * a_step), bd = bd0 + (uint64_t)((uint32_t)stage * b_step);
+        const uint64_t sfd = sfd0 + (uint64_t)((uint32_t)stage * sf_step);
+        if (elect_one()) {
+          utccp_32x128b(tsfa, sfd);
+          if (P.sfb_pre) utccp_32x128b(tsfb, psd0 + (uint64_t)((uint32_t)kb * 32u));
+          else
+            for (int c = 0; c < sfb_chunks; ++c) utccp_32x128b(tsfb + 4 * c, sfd + (uint64_t)(32u + 32u * (uint32_t)c));
 #pragma unroll
           for (int k = 0; k < XBK / 32; ++k)      // 32 one-byte elements = 32 bytes = 2 descriptor units per UMMA_K
-            umma_mxf8(tmem_base + TM_ACC, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k),
-                      make_idesc_mx8(XM, P.bnx, k) | ((uint32_t)P.w_fmt << 7) /* A format: 5 = E2M1 */,
-                      (kb | k) != 0, tmem_base + TM_SFA, tmem_base + TM_SFB);
+            umma_mxf8(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc0 + (uint32_t)k * idesc_k, (kb | k) != 0, tsfa, tsfb);
           tc::umma_commit(&empty[stage]);
-          if (++stage == XSTAGES) { stage = 0; phase ^= 1; }
         }
-        tc::umma_commit(acc_full);
-        acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == NST) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) tc::umma_commit(acc_full);
+      __syncwarp();
+      acc_phase ^= 1;
     }
   } else if (warp >= 8) {
     // ---- producers: 256 threads, per stage 128 rows x 128 K of weights = 1024 chunks of 16 elements
@@ -264,7 +325,7 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
     cur_init(fc); cur_init(cc);
     int stage = 0; uint32_t phase = 0;
     const bool wtma = P.wdense || P.wfp4;
-    if (wtma) {
+    if (wtma && !P.sfb_pre) {
       // the weight bytes arrive by TMA; only the two scale-factor chunks are assembled here.  K % 128 == 0 in this
       // mode, so one K-block's four scales are one aligned 32-bit word; the next stage's words are fetched before
       // waiting for the current stage to drain.
@@ -273,27 +334,37 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
         if (!c.ok) return;
         const int kb = c.kb0 + c.kb;
         const int n = c.tn * XM + ptid;
-        if (ptid < XM && n < P.N)
+        if (ptid < XM && n < P.N && !P.wtiled)
           va = P.wfp4 ? __vadd4(__ldg(reinterpret_cast<const uint32_t*>(P.we_in + (long long)n * kblk32) + kb), 0x7F7F7F7Fu)
                       : __ldg(reinterpret_cast<const uint32_t*>(P.wsf + (long long)n * kblk32) + kb);
         vb = load_sfb(c.tm * P.bnx, kb);
       };
-      uint32_t va, vb;
-      ld_sf(cc, va, vb);
+      // scale words of the next SFD stages are kept in registers: their global-load latency is off the per-stage chain
+      constexpr int SFD = 4;
+      uint32_t ra[SFD], rb[SFD];
+#pragma unroll
+      for (int j = 0; j < SFD; ++j) {
+        ld_sf(fc, ra[j], rb[j]);
+        if (j + 1 < SFD) cur_next(fc);
+      }
       while (cc.ok) {
-        cur_next(fc);
-        uint32_t na, nb;
-        ld_sf(fc, na, nb);
-        tc::mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* sf = sSF + stage * XSF_BYTES;
-        if (ptid < XM) *reinterpret_cast<uint32_t*>(sf + (ptid & 31) * 16 + (ptid >> 5) * 4) = va;
-        store_sfb(stage, vb);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&full[stage]);
-        if (++stage == XSTAGES) { stage = 0; phase ^= 1; }
-        cur_next(cc);
-        va = na; vb = nb;
+#pragma unroll
+        for (int j = 0; j < SFD; ++j) {
+          if (cc.ok) {
+            const uint32_t va = ra[j], vb = rb[j];
+            cur_next(fc);
+            ld_sf(fc, ra[j], rb[j]);                 // the stage SFD ahead takes this slot
+            tc::mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sf = sSF + stage * XSF_BYTES;
+            if (ptid < XM && !P.wtiled) *reinterpret_cast<uint32_t*>(sf + (ptid & 31) * 16 + (ptid >> 5) * 4) = va;
+            store_sfb(stage, vb);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&full[stage]);
+            if (++stage == NST) { stage = 0; phase ^= 1; }
+            cur_next(cc);
+          }
+        }
       }
     }
     Raw ring[PF][4];
@@ -321,7 +392,7 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&full[stage]);
-          if (++stage == XSTAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
           cur_next(cc);
         }
       }
@@ -335,6 +406,33 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
       // sparse outlier correction: this feature's CSR range is fetched before the accumulator is waited for
       int oe0 = 0, oe1 = 0;
       if (P.o_ptr && n < P.N) { oe0 = __ldg(P.o_ptr + n); oe1 = __ldg(P.o_ptr + n + 1); }
+      // decode sizes: the whole correction of this feature (<= 32 tokens) is summed into registers WHILE the main loop
+      // runs -- the epilogue warps have nothing else to do until the accumulator is complete -- and added afterwards
+      constexpr int CORR_MAX = 32;
+      float corr[CORR_MAX];
+      const bool pre_corr = P.bnx <= CORR_MAX;
+      if (pre_corr) {
+#pragma unroll
+        for (int v = 0; v < CORR_MAX; ++v) corr[v] = 0.0f;
+        const int klo = kb0 * XBK, khi = (kb0 + nkb) * XBK;
+        const int kblk32 = P.K >> 5;
+        for (int e = oe0; e < oe1; ++e) {
+          const int k = __ldg(P.o_k + e);
+          if (k < klo || k >= khi) continue;
+          const float dw = __ldg(P.o_dw + e);
+#pragma unroll
+          for (int v = 0; v < CORR_MAX; ++v) {
+            const int m = tm * P.bnx + v;
+            if (v < P.bnx && m < P.M) {
+              const int xe = P.xe[(long long)m * kblk32 + (k >> 5)];
+              const float xs = xe == MSQ_EXP_NAN ? qnan() : pow2i(xe);
+              const float xv = __fmul_rn(decode_elem((uint32_t)P.xcodes[(long long)m * P.ldx + k], 4, 5), xs);
+              corr[v] = fmaf(xv, dw, corr[v]);
+            }
+          }
+        }
+        oe1 = oe0;                       // nothing left for the in-loop correction below
+      }
       tc::mbar_wait(acc_full, acc_phase);
       tc::tc_fence_after();
       for (int c = 0; c < P.bnx / 16; ++c) {
@@ -371,7 +469,8 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
             const int m = tm * P.bnx + c * 16 + v;
             if (m < P.M) {
               float* p = P.C + (long long)m * P.ldc + n;
-              const float val = __uint_as_float(r[v]);
+              float val = __uint_as_float(r[v]);
+              if (pre_corr) val += (c == 0 ? corr[v] : corr[16 + v]);
               if (P.ksplit > 1) atomicAdd(p, val);
               else *p = P.accumulate ? (*p + val) : val;
             }
@@ -388,6 +487,35 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
   if (warp == 2) {
     tc::tc_fence_after();
     tc::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// FP4 weight [N, K] (codes row-major, K/2 bytes per row; e_in [N, K/32]) -> GEMM-ready tiles: for every (128-row tile tn,
+// 128-wide K block kb) one contiguous 8 KB chunk of codes (row r at r * 64 bytes) and one 512-byte scale chunk in the
+// tcgen05.cp layout (UE8M0 = e + 127).  A stage of k_gemm_mx8 then reads two contiguous pieces of DRAM instead of 128
+// 64-byte row segments 4 KB apart and 128 scattered scale words (measured: 1.3 TB/s of DRAM reads with the row-major planes)
+__global__ void __launch_bounds__(256) k_tile_fp4_weight(const uint8_t* __restrict__ codes, const int8_t* __restrict__ e_in,
+                                                         uint8_t* __restrict__ codes_t, uint8_t* __restrict__ sf_t, int N, int K,
+                                                         int kblocks) {
+  const int kb = blockIdx.x, tn = blockIdx.y;
+  const long long chunk = (long long)tn * kblocks + kb;
+  const int t = threadIdx.x;
+  {
+    const int r = t >> 1, h = t & 1;                       // row, 32-byte half of its 64 bytes
+    const int n = tn * XM + r;
+    uint4 a = make_uint4(0, 0, 0, 0), b = a;
+    if (n < N) {
+      const uint4* src = reinterpret_cast<const uint4*>(codes + (long long)n * (K >> 1) + kb * 64 + h * 32);
+      a = __ldg(src); b = __ldg(src + 1);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(codes_t + chunk * XRAW_BYTES + r * 64 + h * 32);
+    dst[0] = a; dst[1] = b;
+  }
+  if (t < XM) {
+    const int n = tn * XM + t;
+    uint32_t w = 0x7F7F7F7Fu;
+    if (n < N) w = __vadd4(__ldg(reinterpret_cast<const uint32_t*>(e_in + (long long)n * (K >> 5)) + kb), 0x7F7F7F7Fu);
+    *reinterpret_cast<uint32_t*>(sf_t + chunk * 512 + (t & 31) * 16 + (t >> 5) * 4) = w;
   }
 }
 
@@ -435,7 +563,7 @@ extern "C" {
 //   xcodes [M, K] E4M3 bytes (ld = ldx bytes), xe int8 [M, K/32]         (plain MX-FP8 activations)
 //   wcodes / wbitmap / we_in / we_out: packed FP4 weight, block 32 along K (plain != 0: no outliers)
 // The caller guarantees that every outlier block satisfies -6 <= e_out - 2 e_in <= 6 (exact E4M3 folding).
-struct Mx4Sparse { const int* o_ptr; const int* o_k; const float* o_dw; };
+struct Mx4Sparse { const int* o_ptr; const int* o_k; const float* o_dw; const unsigned char* codes_tiled; const unsigned char* sf_tiled; };
 
 static int launch_mx8(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* wcodes,
                       const unsigned int* wbitmap, const signed char* we_in, const signed char* we_out,
@@ -446,7 +574,10 @@ static int launch_mx8(const unsigned char* xcodes, long long ldx, const signed c
   P.w_tx_bytes = wdense ? XA_BYTES : 0;
   // a 16U4_ALIGN16B load reports the bytes it READ (8 per 16-byte chunk written) to the mbarrier [measured: expecting
   // the 16 KB it writes never completes; 8 KB does]
-  if (fp4) { P.w_tx_bytes = XA_BYTES / 2; P.wfp4 = 1; P.w_fmt = 5; P.o_ptr = fp4->o_ptr; P.o_k = fp4->o_k; P.o_dw = fp4->o_dw; P.xcodes = xcodes; P.ldx = ldx; }
+  if (fp4) {
+    P.w_tx_bytes = XA_BYTES / 2; P.wfp4 = 1; P.w_fmt = 5; P.o_ptr = fp4->o_ptr; P.o_k = fp4->o_k; P.o_dw = fp4->o_dw; P.xcodes = xcodes; P.ldx = ldx;
+    if (fp4->codes_tiled) { P.wtiled = 1; P.wsf_tiled = fp4->sf_tiled; }
+  }
   P.wcodes = wcodes; P.wbitmap = wbitmap; P.we_in = we_in; P.we_out = we_out; P.xe = xe; P.C = C; P.ldc = ldc;
   P.M = M; P.N = N; P.K = K; P.plain = plain; P.accumulate = accumulate;
   P.wdense = wdense != nullptr; P.wsf = wsf;
@@ -474,6 +605,15 @@ static int launch_mx8(const unsigned char* xcodes, long long ldx, const signed c
   }
   P.ksplit = ksplit;
   P.kb_per_split = (kblocks_total + ksplit - 1) / ksplit;
+  // ring: at decode sizes a stage is one 8-16 KB weight tile and a 2-4 KB activation tile, and the kernel is bound by the
+  // latency of the per-stage hand-offs: twice the depth keeps twice the bytes in flight
+  P.xb_bytes = bnx <= 32 ? ((bnx * XBK + 1023) / 1024) * 1024 : XB_BYTES;
+  P.nst = bnx <= 32 ? XMAXST : XSTAGES;
+  {
+    const bool one_tile = P.tiles_n * P.tiles_m * ksplit <= sms;
+    const long long ring = (long long)P.nst * (XA_BYTES + P.xb_bytes + XSF_BYTES);
+    P.sfb_pre = (P.wtiled && bnx <= 128 && one_tile && (long long)P.kb_per_split * 512 <= (long long)MX8_SMEM - 1024 - 256 - ring) ? 1 : 0;
+  }
   if (ksplit > 1 && !accumulate) {
     if (ldc == N) cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s);
     else cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s);
@@ -483,6 +623,9 @@ static int launch_mx8(const unsigned char* xcodes, long long ldx, const signed c
   if (rc) return rc;
   if (wdense) {
     rc = make_tmap_2d(&tmW, wdense, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, ldw, XM, XBK);
+    if (rc) return rc;
+  } else if (fp4 && fp4->codes_tiled) {
+    rc = make_tmap_2d_u4(&tmW, fp4->codes_tiled, (long long)P.tiles_n * kblocks_total * XM, XBK, XBK / 2, XM);
     if (rc) return rc;
   } else if (fp4) {
     rc = make_tmap_2d_u4(&tmW, wcodes, N, K, (long long)K / 2, XM);
@@ -550,9 +693,41 @@ int msq_gemm_mxfp4w_blockscaled(const unsigned char* xcodes, long long ldx, cons
   if (K % 128 != 0) return MSQ_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(xe) & 3) || (reinterpret_cast<uintptr_t>(we_in) & 3)) return MSQ_ERR_ALIGN;
   if ((reinterpret_cast<uintptr_t>(xcodes) & 15) || (ldx % 16) || (reinterpret_cast<uintptr_t>(wcodes) & 31)) return MSQ_ERR_ALIGN;
-  Mx4Sparse sp{o_ptr, o_k, o_dw};
+  Mx4Sparse sp{o_ptr, o_k, o_dw, nullptr, nullptr};
   return launch_mx8(xcodes, ldx, xe, wcodes, nullptr, we_in, nullptr, nullptr, 0, nullptr, C, ldc, M, N, K, 1, accumulate,
                     (cudaStream_t)stream, &sp);
+}
+
+// GEMM-ready layout of a K-blocked FP4 weight (see k_tile_fp4_weight): codes_tiled [ceil(N/128) * (K/128) * 8192] bytes,
+// sf_tiled [ceil(N/128) * (K/128) * 512] bytes.  K % 128 == 0; codes 16-byte aligned; outputs 32- / 16-byte aligned.
+int msq_tile_fp4_weight(const unsigned char* wcodes, const signed char* we_in, unsigned char* codes_tiled,
+                        unsigned char* sf_tiled, int N, int K, void* stream) {
+  msq::DevGuard dev_guard_(wcodes);
+  if (!wcodes || !we_in || !codes_tiled || !sf_tiled || N <= 0 || K <= 0) return MSQ_ERR_BAD_ARG;
+  if (K % 128 != 0) return MSQ_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(wcodes) & 15) || (reinterpret_cast<uintptr_t>(we_in) & 3) ||
+      (reinterpret_cast<uintptr_t>(codes_tiled) & 31) || (reinterpret_cast<uintptr_t>(sf_tiled) & 15))
+    return MSQ_ERR_ALIGN;
+  dim3 grid((unsigned)(K / XBK), (unsigned)((N + XM - 1) / XM));
+  k_tile_fp4_weight<<<grid, 256, 0, (cudaStream_t)stream>>>(wcodes, we_in, codes_tiled, sf_tiled, N, K, K / XBK);
+  return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+}
+
+// msq_gemm_mxfp4w_blockscaled on the tiled layout: every pipeline stage is one contiguous 8 KB + one 512 B read
+int msq_gemm_mxfp4w_tiled_blockscaled(const unsigned char* xcodes, long long ldx, const signed char* xe,
+                                      const unsigned char* codes_tiled, const unsigned char* sf_tiled, const int* o_ptr,
+                                      const int* o_k, const float* o_dw, float* C, long long ldc, int M, int N, int K,
+                                      int accumulate, void* stream) {
+  msq::DevGuard dev_guard_(xcodes);
+  if (!xcodes || !xe || !codes_tiled || !sf_tiled || !C || M <= 0 || N <= 0 || K <= 0) return MSQ_ERR_BAD_ARG;
+  if (o_ptr && (!o_k || !o_dw)) return MSQ_ERR_BAD_ARG;
+  if (K % 128 != 0) return MSQ_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(xe) & 3) || (reinterpret_cast<uintptr_t>(xcodes) & 15) || (ldx % 16) ||
+      (reinterpret_cast<uintptr_t>(codes_tiled) & 31) || (reinterpret_cast<uintptr_t>(sf_tiled) & 15))
+    return MSQ_ERR_ALIGN;
+  Mx4Sparse sp{o_ptr, o_k, o_dw, codes_tiled, sf_tiled};
+  return launch_mx8(xcodes, ldx, xe, codes_tiled, nullptr, reinterpret_cast<const signed char*>(sf_tiled), nullptr, nullptr, 0,
+                    nullptr, C, ldc, M, N, K, 1, accumulate, (cudaStream_t)stream, &sp);
 }
 
 }  // extern "C"
