@@ -65,46 +65,52 @@ k_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   auto tile_coords = [&](int t, int& tm, int& tn) { tn = t / P.tiles_m; tm = t - tn * P.tiles_m; };
   auto tile_skipped = [&](int tm, int tn) { return P.upper_only && (tm * BM >= (tn + 1) * BN); };
 
+  // role loops on the whole warp, TMA / tcgen05 instructions under tc::elect_one() (see msq_tc.cuh)
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int tm, tn; tile_coords(t, tm, tn);
-        if (tile_skipped(tm, tn)) continue;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          tc::mbar_wait(&empty[stage], phase ^ 1);
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int tm, tn; tile_coords(t, tm, tn);
+      if (tile_skipped(tm, tn)) continue;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        tc::mbar_wait(&empty[stage], phase ^ 1);
+        if (tc::elect_one()) {
           tc::mbar_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
           tc::tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], kb * BK, tm * BM);
           tc::tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, &full[stage], kb * BK, tn * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc(P.ab_format, BM, BN);
-      int stage = 0; uint32_t phase = 0;
-      int buf = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int tm, tn; tile_coords(t, tm, tn);
-        if (tile_skipped(tm, tn)) continue;
-        tc::mbar_wait(&acc_empty[buf], acc_phase ^ 1);
+    const uint32_t idesc = tc::make_idesc(P.ab_format, BM, BN);
+    const uint64_t ad0 = tc::make_kmajor_sw128_desc(tc::smem_u32(sA)), bd0 = tc::make_kmajor_sw128_desc(tc::smem_u32(sB));
+    int stage = 0; uint32_t phase = 0;
+    int buf = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int tm, tn; tile_coords(t, tm, tn);
+      if (tile_skipped(tm, tn)) continue;
+      tc::mbar_wait(&acc_empty[buf], acc_phase ^ 1);
+      tc::tc_fence_after();
+      const uint32_t d = tmem_base + (uint32_t)(buf * BN);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        tc::mbar_wait(&full[stage], phase);
         tc::tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)(buf * BN);
-        for (int kb = 0; kb < kblocks; ++kb) {
-          tc::mbar_wait(&full[stage], phase);
-          tc::tc_fence_after();
-          const uint64_t ad = tc::make_kmajor_sw128_desc(tc::smem_u32(sA + stage * A_STAGE_BYTES));
-          const uint64_t bd = tc::make_kmajor_sw128_desc(tc::smem_u32(sB + stage * B_STAGE_BYTES));
+        // descriptor = base + stage * (stage bytes >> 4): the 14-bit address field cannot carry (shared memory < 256 KB)
+        const uint64_t ad = ad0 + (uint64_t)((uint32_t)stage * (uint32_t)(A_STAGE_BYTES >> 4));
+        const uint64_t bd = bd0 + (uint64_t)((uint32_t)stage * (uint32_t)(B_STAGE_BYTES >> 4));
+        if (tc::elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)      // 16 elements = 32 bytes = 2 descriptor address units per UMMA_K
             tc::umma_f16(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           tc::umma_commit(&empty[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc::umma_commit(&acc_full[buf]);
-        if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (tc::elect_one()) tc::umma_commit(&acc_full[buf]);
+      __syncwarp();
+      if (++buf == 2) { buf = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     const int q = warp & 3;                       // TMEM lane quarter this warp may read

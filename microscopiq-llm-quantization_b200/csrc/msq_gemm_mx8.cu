@@ -89,20 +89,6 @@ __device__ __forceinline__ void umma_mxf8(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb)
       : "memory");
 }
-// one lane of a converged warp (elect.sync): the compiler knows that a region guarded by it runs on exactly one lane and
-// moves the (warp-uniform) operands of the tcgen05 instructions to uniform registers with a single R2UR each -- guarded by
-// `lane == 0` it emits an ELECT / R2UR.BROADCAST loop per operand instead
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n"
-      ".reg .pred P;\n"
-      "elect.sync _|P, 0xffffffff;\n"
-      "selp.u32 %0, 1, 0, P;\n"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
 // block-scaled instruction descriptor: E4M3 x E4M3 -> F32, UE8M0 scales, both K-major
 //   [4,6) b_sf_id  [7,10) A fmt  [10,13) B fmt  [17,23) N>>3  [23] scale fmt (1 = E8M0)  [24,29) M>>4  [29,31) a_sf_id
 __device__ __forceinline__ uint32_t make_idesc_mx8(int M, int N, int sf_id) {
@@ -165,12 +151,12 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);     // warp-uniform for the compiler, too
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int tn, tm, kb0, nkb; tile_coords(t, tn, tm, kb0, nkb);
-        for (int kb = kb0; kb < kb0 + nkb; ++kb) {
-          tc::mbar_wait(&empty[stage], phase ^ 1);
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int tn, tm, kb0, nkb; tile_coords(t, tn, tm, kb0, nkb);
+      for (int kb = kb0; kb < kb0 + nkb; ++kb) {
+        tc::mbar_wait(&empty[stage], phase ^ 1);
+        if (tc::elect_one()) {
           tc::mbar_expect_tx(&full[stage], (uint32_t)(P.bnx * XBK + P.w_tx_bytes + (P.wtiled ? 512 : 0)));
           if (P.wtiled) {
             const long long chunk = (long long)tn * kblocks_total + kb;
@@ -178,8 +164,9 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
             bulk_load_1d(sSF + stage * XSF_BYTES, P.wsf_tiled + chunk * 512, 512, &full[stage]);
           } else if (P.wdense || P.wfp4) tc::tma_load_2d(sA + stage * XA_BYTES, &tmW, &full[stage], kb * XBK, tn * XM);
           tc::tma_load_2d(sB + stage * XBB, &tmX, &full[stage], kb * XBK, tm * P.bnx);
-          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == NST) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -206,7 +193,7 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
         tc::tc_fence_after();
         const uint64_t ad = ad0 + (uint64_t)((uint32_t)stage * a_step), bd = bd0 + (uint64_t)((uint32_t)stage * b_step);
         const uint64_t sfd = sfd0 + (uint64_t)((uint32_t)stage * sf_step);
-        if (elect_one()) {
+        if (tc::elect_one()) {
           utccp_32x128b(tsfa, sfd);
           if (P.sfb_pre) utccp_32x128b(tsfb, psd0 + (uint64_t)((uint32_t)kb * 32u));
           else
@@ -219,7 +206,7 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
         __syncwarp();
         if (++stage == NST) { stage = 0; phase ^= 1; }
       }
-      if (elect_one()) tc::umma_commit(acc_full);
+      if (tc::elect_one()) tc::umma_commit(acc_full);
       __syncwarp();
       acc_phase ^= 1;
     }

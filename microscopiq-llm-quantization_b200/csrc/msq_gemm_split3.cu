@@ -80,57 +80,61 @@ k_gemm_split3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   };
   constexpr int npairs = 6;      // plane pairs (pa, pb) in accumulation order
 
+  // role loops on the whole warp, TMA / tcgen05 instructions under tc::elect_one() (see msq_tc.cuh)
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int tm, tn; tile_coords(t, tm, tn);
-        if (tile_skipped(tm, tn)) continue;
-        int kb0, kb1; k_range(tm, tn, kb0, kb1);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          for (int pr = 0; pr < npairs; ++pr) {
-            const int pa = (0x211000 >> (4 * pr)) & 0xF;        // 0,0,0,1,1,2
-            const int pb = (0x010210 >> (4 * pr)) & 0xF;        // 0,1,2,0,1,0
-            tc::mbar_wait(&empty[stage], phase ^ 1);
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int tm, tn; tile_coords(t, tm, tn);
+      if (tile_skipped(tm, tn)) continue;
+      int kb0, kb1; k_range(tm, tn, kb0, kb1);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        for (int pr = 0; pr < npairs; ++pr) {
+          const int pa = (0x211000 >> (4 * pr)) & 0xF;        // 0,0,0,1,1,2
+          const int pb = (0x010210 >> (4 * pr)) & 0xF;        // 0,1,2,0,1,0
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+          if (tc::elect_one()) {
             tc::mbar_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
             tc::tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], P.a_col0 + kb * BK,
                             P.a_row0 + pa * P.a_plane_rows + tm * BM);
             tc::tma_load_2d(sB + stage * B_STAGE_BYTES, &tmB, &full[stage], P.b_col0 + kb * BK,
                             P.b_row0 + pb * P.b_plane_rows + tn * BN);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc(1 /*bf16*/, BM, BN);
-      int stage = 0; uint32_t phase = 0;
-      int buf = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int tm, tn; tile_coords(t, tm, tn);
-        if (tile_skipped(tm, tn)) continue;
-        int kb0, kb1; k_range(tm, tn, kb0, kb1);
-        tc::mbar_wait(&acc_empty[buf], acc_phase ^ 1);
+    const uint32_t idesc = tc::make_idesc(1 /*bf16*/, BM, BN);
+    const uint64_t ad0 = tc::make_kmajor_sw128_desc(tc::smem_u32(sA)), bd0 = tc::make_kmajor_sw128_desc(tc::smem_u32(sB));
+    int stage = 0; uint32_t phase = 0;
+    int buf = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int tm, tn; tile_coords(t, tm, tn);
+      if (tile_skipped(tm, tn)) continue;
+      int kb0, kb1; k_range(tm, tn, kb0, kb1);
+      tc::mbar_wait(&acc_empty[buf], acc_phase ^ 1);
+      tc::tc_fence_after();
+      const uint32_t d = tmem_base + (uint32_t)(buf * BN);
+      uint32_t first = 1;
+      for (int u = (kb1 - kb0) * npairs; u > 0; --u) {
+        tc::mbar_wait(&full[stage], phase);
         tc::tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)(buf * BN);
-        uint32_t first = 1;
-        for (int u = (kb1 - kb0) * npairs; u > 0; --u) {
-          tc::mbar_wait(&full[stage], phase);
-          tc::tc_fence_after();
-          const uint64_t ad = tc::make_kmajor_sw128_desc(tc::smem_u32(sA + stage * A_STAGE_BYTES));
-          const uint64_t bd = tc::make_kmajor_sw128_desc(tc::smem_u32(sB + stage * B_STAGE_BYTES));
+        const uint64_t ad = ad0 + (uint64_t)((uint32_t)stage * (uint32_t)(A_STAGE_BYTES >> 4));
+        const uint64_t bd = bd0 + (uint64_t)((uint32_t)stage * (uint32_t)(B_STAGE_BYTES >> 4));
+        if (tc::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            tc::umma_f16(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
-            first = 0;
-          }
+          for (int k = 0; k < BK / 16; ++k)
+            tc::umma_f16(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
           tc::umma_commit(&empty[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc::umma_commit(&acc_full[buf]);
-        if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+        __syncwarp();
+        first = 0;
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (tc::elect_one()) tc::umma_commit(&acc_full[buf]);
+      __syncwarp();
+      if (++buf == 2) { buf = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     const int q = warp & 3;

@@ -83,43 +83,48 @@ __global__ void __launch_bounds__(512, 1) k_gemm_w4(const __grid_constant__ CUte
     nkb = min(P.kb_per_split, kblocks_total - kb0);
   };
 
+  // role loops on the whole warp, TMA / tcgen05 instructions under tc::elect_one() (see msq_tc.cuh)
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int tn, tm, kb0, nkb; tile_coords(t, tn, tm, kb0, nkb);
-        for (int kb = kb0; kb < kb0 + nkb; ++kb) {
-          tc::mbar_wait(&empty[stage], phase ^ 1);
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int tn, tm, kb0, nkb; tile_coords(t, tn, tm, kb0, nkb);
+      for (int kb = kb0; kb < kb0 + nkb; ++kb) {
+        tc::mbar_wait(&empty[stage], phase ^ 1);
+        if (tc::elect_one()) {
           tc::mbar_expect_tx(&full[stage], (uint32_t)(P.bnx * WBK * 2));
           tc::tma_load_2d(sB + stage * WB_BYTES, &tmX, &full[stage], kb * WBK, tm * P.bnx);
-          if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc(1 /*bf16*/, WM, P.bnx);
-      int stage = 0; uint32_t phase = 0;
-      int buf = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int tn, tm, kb0, nkb; tile_coords(t, tn, tm, kb0, nkb);
-        tc::mbar_wait(&acc_empty[buf], acc_phase ^ 1);
+    const uint32_t idesc = tc::make_idesc(1 /*bf16*/, WM, P.bnx);
+    const uint64_t ad0 = tc::make_kmajor_sw128_desc(tc::smem_u32(sA)), bd0 = tc::make_kmajor_sw128_desc(tc::smem_u32(sB));
+    int stage = 0; uint32_t phase = 0;
+    int buf = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int tn, tm, kb0, nkb; tile_coords(t, tn, tm, kb0, nkb);
+      tc::mbar_wait(&acc_empty[buf], acc_phase ^ 1);
+      tc::tc_fence_after();
+      const uint32_t d = tmem_base + (uint32_t)(buf * WMAXN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        tc::mbar_wait(&full[stage], phase);
         tc::tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)(buf * WMAXN);
-        for (int kb = 0; kb < nkb; ++kb) {
-          tc::mbar_wait(&full[stage], phase);
-          tc::tc_fence_after();
-          const uint64_t ad = tc::make_kmajor_sw128_desc(tc::smem_u32(sA + stage * WA_BYTES));
-          const uint64_t bd = tc::make_kmajor_sw128_desc(tc::smem_u32(sB + stage * WB_BYTES));
+        const uint64_t ad = ad0 + (uint64_t)((uint32_t)stage * (uint32_t)(WA_BYTES >> 4));
+        const uint64_t bd = bd0 + (uint64_t)((uint32_t)stage * (uint32_t)(WB_BYTES >> 4));
+        if (tc::elect_one()) {
 #pragma unroll
           for (int k = 0; k < WBK / 16; ++k)
             tc::umma_f16(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           tc::umma_commit(&empty[stage]);
-          if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
         }
-        tc::umma_commit(&acc_full[buf]);
-        if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == WSTAGES) { stage = 0; phase ^= 1; }
       }
+      if (tc::elect_one()) tc::umma_commit(&acc_full[buf]);
+      __syncwarp();
+      if (++buf == 2) { buf = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 8) {
     // ---- weight dequant producers: 256 threads, 4 chunks (8 elements = 16 B of bf16) each per stage.

@@ -37,6 +37,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// one lane of a converged warp.  The role loops of the tcgen05 kernels run on the WHOLE warp with only the TMA / tcgen05
+// instructions guarded by elect_one(): the compiler knows such a region runs on exactly one lane and moves the (warp-uniform)
+// operands into uniform registers with one R2UR each.  Guarded by `lane == 0` it emits an ELECT / R2UR.BROADCAST loop per
+// operand: the MMA issue loop of k_gemm_mx8 was 278 SASS instructions per stage that way (~800 cycles for four MMAs --
+// more than the tensor time of four 128x256x16 MMAs, so it bounded the large GEMMs too).  elect.sync is deterministic for a
+// given member mask, so every tcgen05.commit is issued by the thread that issued the MMAs it tracks.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
