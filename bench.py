@@ -136,6 +136,34 @@ def _time_ms(fn, iters, warm=2):
     return e0.elapsed_time(e1) / iters
 
 
+def _time_ms_device(fn, iters=20, reps=5):
+    """device time per call for calls SHORTER than the host side of their own launch (decode-size GEMMs: ~8 us of GPU
+    work behind ~20 us of Python + ctypes): `iters` calls are captured into one CUDA graph and the replays timed with
+    events.  Falls back to the plain event timing if the capture is refused."""
+    try:
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(iters):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / (iters * reps)
+        del g
+        return ms
+    except Exception:
+        torch.cuda.synchronize()
+        return _time_ms(fn, iters)
+
+
 def extras(dev, dev_w, nel):
     """secondary metrics of BASELINE.json's metric string, rank 0 only, each a few hundred ms:
     quantize+pack GB/s, GPTQ seconds for one LLaMA-2-7B decoder layer (x32 = model), packed GEMM TFLOP/s."""
@@ -238,7 +266,7 @@ def extras(dev, dev_w, nel):
     pw = msq_b200.pack_mx_outlier(W, 8, 8, "fp4_e2m1", "fp4_e2m1", 5, [1], 32, variant=1)
     for M in (16, 256, 4096, 8192):
         x = torch.randn(M, 4096, device=dev).to(torch.bfloat16)
-        ms = _time_ms(lambda: _tc.packed_linear(x, pw), 10)
+        ms = (_time_ms_device if M <= 256 else _time_ms)(lambda: _tc.packed_linear(x, pw), 10)
         gemm["M%d" % M] = {"ms": ms, "TFLOPs": 2.0 * M * 4096 * 4096 / (ms * 1e-3) / 1e12}
     out["packed_gemm_k4096_n4096"] = gemm
     # (4) same weight on the native block-scaled path (tcgen05 kind::mxf8f6f4), MX-FP8 activations
@@ -246,8 +274,13 @@ def extras(dev, dev_w, nel):
     if _tc.mx8_weight_ok(pw):
         for M in (16, 256, 4096):
             xq = msq_b200.pack_mx(torch.randn(M, 4096, device=dev), 8, "fp8_e4m3", axes=[-1], block_size=32)
-            ms = _time_ms(lambda: _tc.packed_linear_mx8(xq, pw), 10)
+            ms = (_time_ms_device if M <= 256 else _time_ms)(lambda: _tc.packed_linear_mx8(xq, pw), 10)
             mx8["M%d" % M] = {"ms": ms, "TFLOPs": 2.0 * M * 4096 * 4096 / (ms * 1e-3) / 1e12}
+        # decode size against the library GEMM on the dequantized weight (bf16, 4x the bytes), both as device time
+        wb = pw.dequantize(torch.bfloat16)
+        xb = torch.randn(16, 4096, device=dev).to(torch.bfloat16)
+        mx8["M16_cublas_bf16_ms"] = _time_ms_device(lambda: torch.matmul(xb, wb.t()), 10)
+        del wb
     out["blockscaled_mxfp8_gemm_k4096_n4096"] = mx8
     return out
 
@@ -437,13 +470,14 @@ def leg_cfg5(dev, rank, world, dist):
         row = {}
         for M in (1, 16, 256, 4096):
             x = torch.randn(M, KN, device=dev, generator=g).to(torch.bfloat16)
-            ms = _time_ms(lambda: _tc.packed_linear(x, pw), 5)
+            tfn = _time_ms_device if M <= 256 else _time_ms      # decode sizes: device time (CUDA graph), not launch overhead
+            ms = tfn(lambda: _tc.packed_linear(x, pw), 5)
             ent = {"a16_ms": None, "a16_TFLOPs": None}
             (ms,) = _dist_max(dist, dev, ms)
             ent["a16_ms"], ent["a16_TFLOPs"] = ms, 2.0 * M * KN * KN / (ms * 1e-3) / 1e12
             if ok8:
                 xq = msq_b200.pack_mx(x.float(), 8, "fp8_e4m3", axes=[-1], block_size=32)
-                ms8 = _time_ms(lambda: _tc.packed_linear_mx8(xq, pw), 5)
+                ms8 = tfn(lambda: _tc.packed_linear_mx8(xq, pw), 5)
                 (ms8,) = _dist_max(dist, dev, ms8)
                 ent["mxfp8_ms"], ent["mxfp8_TFLOPs"] = ms8, 2.0 * M * KN * KN / (ms8 * 1e-3) / 1e12
             row["M%d" % M] = ent
