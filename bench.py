@@ -281,6 +281,25 @@ def extras(dev, dev_w, nel):
         xb = torch.randn(16, 4096, device=dev).to(torch.bfloat16)
         mx8["M16_cublas_bf16_ms"] = _time_ms_device(lambda: torch.matmul(xb, wb.t()), 10)
         del wb
+        # compute-bound shape the north star quotes the tensor-core fraction on: 8192^3 on the TMA-fed kernel
+        # (msq_gemm_mxfp8_tma), against the nominal dense kind::mxf8f6f4 peak and against 2x the measured cuBLAS bf16 rate
+        W8 = torch.randn(8192, 8192, device=dev) * 0.02
+        pw8 = msq_b200.pack_mx_outlier(W8, 8, 8, "fp4_e2m1", "fp4_e2m1", 5, [1], 32, variant=1)
+        del W8
+        if _tc.mx8_weight_ok(pw8):
+            xq8 = msq_b200.pack_mx(torch.randn(8192, 8192, device=dev), 8, "fp8_e4m3", axes=[-1], block_size=32)
+            ms = _time_ms(lambda: _tc.packed_linear_mx8(xq8, pw8), 10)
+            tf = 2.0 * 8192.0 ** 3 / (ms * 1e-3) / 1e12
+            bf16 = 1357.9                   # B200_PROFILING.md fallback (sustained cuBLAS bf16)
+            _pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            if os.path.exists(_pp):
+                bf16 = float(json.load(open(_pp)).get("bf16_tflops_sustained", bf16))
+            mx8["M8192_K8192_N8192"] = {"ms": ms, "TFLOPs": tf, "frac_of_nominal_4500_TFLOPs": tf / 4500.0,
+                                        "frac_of_2x_measured_bf16": tf / (2.0 * bf16),
+                                        "kernel": "k_gemm_mx8_tma (token tile %d)" % _tc.N.lib().msq_gemm_mxfp8_tma_tile_tokens(8192, 8192, 8192)}
+            del xq8
+        del pw8
+        torch.cuda.empty_cache()
     out["blockscaled_mxfp8_gemm_k4096_n4096"] = mx8
     return out
 

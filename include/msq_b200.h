@@ -297,6 +297,25 @@ int msq_gemm_mxfp8_dense(const unsigned char* xcodes, long long ldx, const signe
                          const unsigned char* wbytes, long long ldw, const unsigned char* wsf, float* C,
                          long long ldc, int M, int N, int K, int accumulate, void* stream);
 
+/* compute-bound shape of the same path with NO thread on an operand: element tiles by tensor loads, the UE8M0 scales of
+ * BOTH operands by bulk copies from copies already in the tcgen05.cp chunk layout, two accumulators in tensor memory
+ * (the epilogue of a tile overlaps the MMAs of the next), persistent CTAs over an L2-friendly tile raster.
+ * Replaces number_system/mx/linear.py:66-91 (f_linear on fake-quantized operands) at prefill / calibration sizes.
+ *   msq_tile_scales_ue8m0: scales [rows, K/32] (int8 shared exponents when is_int8_exponent, else UE8M0 bytes) ->
+ *     ceil(rows / rows_per_tile) * (K/128) * ceil(rows_per_tile/128) chunks of 512 bytes.  The weight's copy uses
+ *     rows_per_tile = 128 and is built once per weight.
+ *   msq_gemm_mxfp8_tma: w = dense E4M3 bytes [N, K] (ld = ldw bytes; msq_widen_fp4_to_mxfp8) or, w_is_fp4 != 0, the packed
+ *     4-bit codes of a plain FP4 weight [N, K/2 bytes]; wsf_tiled = its tiled scales; xe = int8 activation exponents
+ *     [M, K/32], tiled into `workspace` (msq_gemm_mxfp8_tma_workspace_bytes) by a launch in front of the GEMM.
+ *     K % 128 == 0; w 32-byte aligned.  msq_gemm_mxfp8_tma_tile_tokens reports the token-tile width it will use. */
+int msq_tile_scales_ue8m0(const void* scales, int is_int8_exponent, int rows, int K, int rows_per_tile,
+                          unsigned char* out, void* stream);
+int msq_gemm_mxfp8_tma_tile_tokens(int M, int N, int K);
+long long msq_gemm_mxfp8_tma_workspace_bytes(int M, int N, int K);
+int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* w,
+                       long long ldw, int w_is_fp4, const unsigned char* wsf_tiled, float* C, long long ldc, int M,
+                       int N, int K, int accumulate, void* workspace, long long workspace_bytes, void* stream);
+
 /* ---- host-buffer entry points --------------------------------------------------------------
  * quantize_mx_outlier_v1 (utils/quant.py:147-266) as the reference's drivers call it on CPU-resident
  * weights (llm/llama.py:94-121): h_in / h_out are HOST pointers (pinned for full PCIe speed), the

@@ -378,12 +378,60 @@ def widen_weight_mx8(pw):
     return wb, wsf
 
 
+N.register("msq_tile_scales_ue8m0", _i, [_p, _i, _i, _i, _i, _p, _p])
+N.register("msq_gemm_mxfp8_tma_tile_tokens", _i, [_i, _i, _i])
+N.register("msq_gemm_mxfp8_tma_workspace_bytes", _ll, [_i, _i, _i])
+N.register("msq_gemm_mxfp8_tma", _i, [_p, _ll, _p, _p, _ll, _i, _p, _p, _ll, _i, _i, _i, _i, _p, _ll, _p])
+
+#: compute-bound sizes (M >= MX8_DENSE_MIN_M): fully TMA-fed kernel (csrc/msq_gemm_mx8_tma.cu)
+MX8_TMA = True
+#: ... with the packed 4-bit codes themselves as the operand when the weight has no outliers (half the L2 -> SMEM bytes)
+MX8_TMA_FP4 = True
+
+
+def tile_scales(scales, rows_per_tile=128):
+    """[rows, K/32] int8 shared exponents (or uint8 UE8M0 bytes) -> tcgen05.cp chunk layout (msq_tile_scales_ue8m0)"""
+    rows, kb32 = scales.shape
+    K = kb32 * 32
+    chunks = (rows_per_tile + 127) // 128
+    out = torch.empty(((rows + rows_per_tile - 1) // rows_per_tile) * (K // 128) * chunks * 512, dtype=torch.uint8,
+                      device=scales.device)
+    rc = N.lib().msq_tile_scales_ue8m0(N.ptr(scales), int(scales.dtype == torch.int8), rows, K, rows_per_tile, N.ptr(out),
+                                       N.stream_ptr(scales.device))
+    N.check(rc, "msq_tile_scales_ue8m0")
+    return out
+
+
+def mx8_tma_weight(pw, allow_copy=True):
+    """operand of the TMA-fed kernel, built once per weight and kept on the PackedMX:
+    (bytes, row pitch, is_fp4, tiled scales) -- the packed codes themselves for a plain FP4 weight (nothing is copied but
+    the scales), else, when allow_copy, the widened E4M3 copy with the outliers folded in (1 byte per weight; needs
+    mx8_weight_ok; shared with cache_dense=True); None when neither applies"""
+    Nn, K = pw.shape
+    if MX8_TMA_FP4 and pw.plain and mx4_weight_ok(pw):
+        op = getattr(pw, "_mx8_tma_fp4", None)
+        if op is None:
+            op = pw._mx8_tma_fp4 = (pw.codes, K // 2, 1, tile_scales(pw.e_in.reshape(Nn, K // 32)))
+        return op
+    dense = getattr(pw, "_mx8_dense", None)
+    if dense is None:
+        if not allow_copy or not mx8_weight_ok(pw):
+            return None
+        dense = pw._mx8_dense = widen_weight_mx8(pw)
+    sf_t = getattr(pw, "_mx8_dense_sf_tiled", None)
+    if sf_t is None or sf_t[0] is not dense[1]:
+        sf_t = pw._mx8_dense_sf_tiled = (dense[1], tile_scales(dense[1]))
+    return (dense[0], K, 0, sf_t[1])
+
+
 def packed_linear_mx8(xq, pw, bias=None, cache_dense=False):
     """y = dq(xq) @ dq(pw).T on tcgen05 kind::mxf8f6f4.block_scale.  xq: PackedMX of the activations
     ([..., K], FP8 E4M3, block 32 along the last axis, no outliers); pw: packed FP4 weight (mx8_weight_ok).
-    cache_dense=True keeps the widened E4M3 copy of the weight (1 byte per element, on top of the 0.56-byte packed
-    planes) on `pw` and runs the TMA-fed kernel at every M: at decode sizes the fused kernel is bound by its
-    dequantizing producer warps, the cached operand streams at HBM speed (still half the bytes of bf16)."""
+    Routing: M <= 32 -> the packed codes by TMA + sparse outlier epilogue (msq_gemm_mxfp4w_tiled_blockscaled);
+    M > 32 -> the fully TMA-fed kernel (msq_gemm_mxfp8_tma): a plain FP4 weight feeds its packed codes, a weight with
+    outliers its widened E4M3 copy (1 byte per element next to the 0.56-byte planes), which is built and kept on `pw`
+    from M >= MX8_DENSE_MIN_M (compute-bound) or when cache_dense=True; otherwise the producer-widen kernel
+    (msq_gemm_mxfp8_blockscaled) reads the packed planes."""
     from . import _ops
     K = pw.shape[1]
     if xq.shape[-1] != K or xq.block_size != 32 or xq.code_width != 8 or _ops.fmt4(xq.in_fmt)[:2] != (4, 5):
@@ -393,7 +441,23 @@ def packed_linear_mx8(xq, pw, bias=None, cache_dense=False):
         M *= s_
     Nn = pw.shape[0]
     dense = getattr(pw, "_mx8_dense", None)
-    if FP4_TMA and dense is None and not cache_dense and M <= FP4_TMA_MAX_M and mx4_weight_ok(pw):
+    if MX8_TMA and M > FP4_TMA_MAX_M and K % 128 == 0 and Nn % 4 == 0:
+        # everything above the decode sizes: both operands and both scale streams by TMA, double-buffered accumulators.
+        # A plain FP4 weight feeds its packed codes; a weight with outliers its widened E4M3 copy -- built (and kept) only
+        # in the compute-bound regime or on request, below that the producer-widen kernel reads the packed planes
+        op = mx8_tma_weight(pw, allow_copy=cache_dense or dense is not None or M >= MX8_DENSE_MIN_M)
+        if op is not None:
+            out = torch.empty(M, Nn, dtype=torch.float32, device=pw.codes.device)
+            w, ldw, is_fp4, wsf_t = op
+            nbytes = int(N.lib().msq_gemm_mxfp8_tma_workspace_bytes(M, Nn, K))
+            ws = _workspace(nbytes, out.device)
+            rc = N.lib().msq_gemm_mxfp8_tma(N.ptr(xq.codes), K, N.ptr(xq.e_in), N.ptr(w), ldw, is_fp4, N.ptr(wsf_t), N.ptr(out),
+                                            out.stride(0), M, Nn, K, 0, N.ptr(ws), nbytes, N.stream_ptr(out.device))
+            N.check(rc, "msq_gemm_mxfp8_tma")
+            if bias is not None:
+                out += bias.float()
+            return out.reshape(*xq.shape[:-1], Nn)
+    if FP4_TMA and not cache_dense and M <= FP4_TMA_MAX_M and mx4_weight_ok(pw):
         # decode sizes: the packed 4-bit codes are the tensor-core operand (TMA-expanded), outliers = sparse epilogue
         o_ptr, o_k, o_dw = mx4_sparse_outliers(pw)
         out = torch.empty(M, Nn, dtype=torch.float32, device=pw.codes.device)

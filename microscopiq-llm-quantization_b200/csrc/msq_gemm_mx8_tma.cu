@@ -1,0 +1,321 @@
+// msq_gemm_mx8_tma.cu -- the compute-bound (large-M) shape of the block-scaled linear
+//     C[m, n] (+)= sum_k dq(X)[m, k] * dq(W)[n, k]          tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale
+// in which NO thread touches an operand: the element tiles arrive by tensor loads, the UE8M0 scale factors of BOTH operands
+// arrive by linear bulk copies from copies that are already in the tcgen05.cp chunk layout (msq_tile_scales_ue8m0: the
+// weight's once per weight, the activations' by one small launch in front of the GEMM).  k_gemm_mx8 (msq_gemm_mx8.cu)
+// assembles the scale chunks with producer warps through the generic proxy -- a store, a proxy fence and an mbarrier
+// arrive per stage, which at decode sizes hides behind the weight stream but at M = 4096 was the per-stage time of the
+// kernel (~2700 cycles per 128-K stage against 512 cycles of tensor work).
+//
+// Tile = 128 weight rows (UMMA M operand, so C's features sit on the TMEM lanes and one register of a warp is 128
+// contiguous bytes of C) x BN tokens (UMMA N operand), BN <= 240 with TWO accumulators in tensor memory (2 x 240 fp32
+// columns + 4 + 8 scale-factor columns <= 512): the four epilogue warps drain tile i while the MMAs of tile i + 1 run.
+// BN = 256 (one accumulator) is used only when the token count makes it cheaper.  Persistent CTAs, tiles rastered in
+// bands of 8 token tiles so that the CTAs running at the same time share weight AND activation tiles in L2.
+//
+// Weight operand: dense E4M3 bytes [N, K] (the widened copy, outliers folded: msq_widen_fp4_to_mxfp8), or the packed 4-bit
+// codes themselves (plain FP4 weight; CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B expands 16 codes into a 16-byte chunk).
+#include <stdlib.h>
+#include "msq_api_internal.h"
+#include "msq_common.cuh"
+#include "msq_tc.cuh"
+
+namespace msq {
+namespace {
+
+constexpr int YM = 128, YBK = 128, YST = 4, YMAXN = 256, YGROUP = 8;
+constexpr int YA_BYTES = YM * YBK, YB_BYTES = YMAXN * YBK, YSF_BYTES = 512 + 1024;
+constexpr int Y_SMEM = YST * (YA_BYTES + YB_BYTES + YSF_BYTES) + 1024 + 256;
+static_assert(Y_SMEM <= 227 * 1024, "shared memory");
+
+struct YParams {
+  const uint8_t* wsf_t;       // weight scales, tiled:     chunk (tn, kb)    at (tn * kblocks + kb) * 512
+  const uint8_t* xsf_t;       // activation scales, tiled: chunks (tm, kb)   at (tm * kblocks + kb) * 512 * sfb_chunks
+  float* C; long long ldc;
+  int M, N, K, bn, nacc, tiles_n, tiles_m, kblocks, sfb_chunks, accumulate, w_fmt, w_tx_bytes;
+};
+
+__device__ __forceinline__ uint64_t sf_desc(uint32_t smem_addr) {     // see make_sf_desc in msq_gemm_mx8.cu
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(128 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void bulk_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void cp_sf(uint32_t tmem_addr, uint64_t desc) {
+  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(tmem_addr), "l"(desc) : "memory");
+}
+__device__ __forceinline__ void mma_bs(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                       uint32_t tsfa, uint32_t tsfb) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                                                          const YParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + YST * YA_BYTES;
+  uint8_t* sSF = smem + YST * (YA_BYTES + YB_BYTES);       // per stage: SFA[512] | SFB[1024]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSF + YST * YSF_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + YST;
+  uint64_t* acc_full = bars + 2 * YST;
+  uint64_t* acc_empty = bars + 2 * YST + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * YST + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = P.tiles_n * P.tiles_m;
+  const int band_tiles = YGROUP * P.tiles_n;
+  auto tile_coords = [&](int t, int& tn, int& tm) {
+    const int band = t / band_tiles;
+    const int first = band * YGROUP;
+    const int rows = min(YGROUP, P.tiles_m - first);
+    const int r = t - band * band_tiles;
+    tn = r / rows;
+    tm = first + (r - tn * rows);
+  };
+
+  if (warp == 0 && lane == 0) { tc::tma_prefetch_desc(&tmX); tc::tma_prefetch_desc(&tmW); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < YST; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
+    tc::mbar_fence_init();
+  }
+  if (warp == 2) tc::tmem_alloc<512>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == 0) {
+    // ---- loads: per stage one weight tile, one activation tile, one + sfb_chunks scale chunks, all on one mbarrier
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t tx = (uint32_t)(P.w_tx_bytes + P.bn * YBK + 512 + 512 * P.sfb_chunks);
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int tn, tm; tile_coords(t, tn, tm);
+      const uint8_t* wsf = P.wsf_t + (long long)tn * P.kblocks * 512;
+      const uint8_t* xsf = P.xsf_t + (long long)tm * P.kblocks * 512 * P.sfb_chunks;
+      for (int kb = 0; kb < P.kblocks; ++kb) {
+        tc::mbar_wait(&empty[stage], phase ^ 1);
+        if (tc::elect_one()) {
+          tc::mbar_expect_tx(&full[stage], tx);
+          tc::tma_load_2d(sA + stage * YA_BYTES, &tmW, &full[stage], kb * YBK, tn * YM);
+          tc::tma_load_2d(sB + stage * YB_BYTES, &tmX, &full[stage], kb * YBK, tm * P.bn);
+          bulk_1d(sSF + stage * YSF_BYTES, wsf + (long long)kb * 512, 512, &full[stage]);
+          bulk_1d(sSF + stage * YSF_BYTES + 512, xsf + (long long)kb * 512 * P.sfb_chunks, 512u * (uint32_t)P.sfb_chunks, &full[stage]);
+        }
+        __syncwarp();
+        if (++stage == YST) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issue (whole warp in the loop, the tcgen05 instructions under elect.sync: see msq_tc.cuh)
+    int stage = 0; uint32_t phase = 0;
+    int as = 0; uint32_t acc_phase = 0;           // bit `as` = phase of accumulator `as`
+    const uint64_t ad0 = tc::make_kmajor_sw128_desc(tc::smem_u32(sA)), bd0 = tc::make_kmajor_sw128_desc(tc::smem_u32(sB));
+    const uint64_t sfd0 = sf_desc(tc::smem_u32(sSF));
+    const uint32_t a_step = (uint32_t)(YA_BYTES >> 4), b_step = (uint32_t)(YB_BYTES >> 4), sf_step = (uint32_t)(YSF_BYTES >> 4);
+    // [4,6) b_sf_id  [7,10) A fmt  [10,13) B fmt  [17,23) N>>3  [23] scale fmt (1 = E8M0)  [24,29) M>>4  [29,31) a_sf_id
+    const uint32_t idesc0 = ((uint32_t)P.w_fmt << 7) | ((uint32_t)(P.bn >> 3) << 17) | (1u << 23) | ((uint32_t)(YM >> 4) << 24);
+    const uint32_t idesc_k = (1u << 4) | (1u << 29);
+    const uint32_t tsfa = tmem_base + (uint32_t)(P.nacc * P.bn), tsfb = tsfa + 4;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      tc::mbar_wait(&acc_empty[as], ((acc_phase >> as) & 1u) ^ 1u);
+      tc::tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(as * P.bn);
+      for (int kb = 0; kb < P.kblocks; ++kb) {
+        tc::mbar_wait(&full[stage], phase);
+        tc::tc_fence_after();
+        const uint64_t ad = ad0 + (uint64_t)((uint32_t)stage * a_step), bd = bd0 + (uint64_t)((uint32_t)stage * b_step);
+        const uint64_t sfd = sfd0 + (uint64_t)((uint32_t)stage * sf_step);
+        if (tc::elect_one()) {
+          cp_sf(tsfa, sfd);
+          cp_sf(tsfb, sfd + 32u);
+          if (P.sfb_chunks > 1) cp_sf(tsfb + 4, sfd + 64u);
+#pragma unroll
+          for (int k = 0; k < YBK / 32; ++k)
+            mma_bs(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc0 + (uint32_t)k * idesc_k, (kb | k) != 0, tsfa, tsfb);
+          tc::umma_commit(&empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == YST) { stage = 0; phase ^= 1; }
+      }
+      if (tc::elect_one()) tc::umma_commit(&acc_full[as]);
+      __syncwarp();
+      acc_phase ^= 1u << as;
+      if (P.nacc == 2) as ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ---- epilogue: TMEM lane = output feature, register = token; one register of a warp = 128 contiguous bytes of C
+    const int q = warp & 3;
+    int as = 0; uint32_t acc_phase = 0;           // bit `as` = phase of accumulator `as`
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int tn, tm; tile_coords(t, tn, tm);
+      const int n = tn * YM + q * 32 + lane;
+      const int m0 = tm * P.bn;
+      tc::mbar_wait(&acc_full[as], (acc_phase >> as) & 1u);
+      tc::tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * P.bn);
+      float* crow = P.C + (long long)m0 * P.ldc + n;
+      for (int c = 0; c < P.bn; c += 16) {
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(tacc + (uint32_t)c)
+            : "memory");
+        tc::tmem_ld_wait();
+        if (n < P.N) {
+#pragma unroll
+          for (int v = 0; v < 16; ++v) {
+            if (m0 + c + v < P.M) {
+              float* p = crow + (long long)(c + v) * P.ldc;
+              const float val = __uint_as_float(r[v]);
+              *p = P.accumulate ? (*p + val) : val;
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(&acc_empty[as]);
+      acc_phase ^= 1u << as;
+      if (P.nacc == 2) as ^= 1;
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// scales [rows, K/32] (int8 shared exponents, or UE8M0 bytes) -> tcgen05.cp chunks: for every (tile of rows_per_tile rows,
+// 128-wide K block) `chunks` = ceil(rows_per_tile / 128) pieces of 512 bytes, byte(r, j) = (r % 32) * 16 + (r / 32) * 4 + j
+// for row r of the piece and 32-block j of the K block; rows outside the matrix get 2^0
+__global__ void __launch_bounds__(256) k_tile_scales(const uint8_t* __restrict__ src, int add127, int rows, int kblk32,
+                                                     int rows_per_tile, int chunks, int kblocks, uint8_t* __restrict__ out) {
+  const int kb = blockIdx.x, tile = blockIdx.y;
+  const int r = threadIdx.x;
+  if (r >= chunks * 128) return;
+  const long long row = (long long)tile * rows_per_tile + r;
+  uint32_t w = 0x7F7F7F7Fu;
+  if (r < rows_per_tile && row < rows) {
+    w = __ldg(reinterpret_cast<const uint32_t*>(src + row * kblk32) + kb);
+    if (add127) w = __vadd4(w, 0x7F7F7F7Fu);            // e + 127; MSQ_EXP_NAN (-128) becomes 0xFF = NaN
+  }
+  const int rr = r & 127;
+  *reinterpret_cast<uint32_t*>(out + (((long long)tile * kblocks + kb) * chunks + (r >> 7)) * 512 + (rr & 31) * 16 + (rr >> 5) * 4) = w;
+}
+
+// token-tile width: fewest (waves over the SMs) x (bytes a tile pulls into shared memory) -- the kernel is bound by the
+// L2 -> shared-memory fill, not by the tensor pipe; one accumulator (BN = 256) pays its exposed epilogue
+static void choose_bn(int M, int N, int K, int sms, int& bn, int& nacc) {
+  if (const char* e = getenv("MSQ_MX8T_BN")) {
+    const int v = atoi(e);
+    if (v >= 16 && v <= 256 && v % 16 == 0) { bn = v; nacc = v <= 240 ? 2 : 1; return; }
+  }
+  const int tiles_n = (N + YM - 1) / YM;
+  const double kblocks = (K + YBK - 1) / YBK;
+  double best = 1e300;
+  bn = 240; nacc = 2;
+  const int cand[] = {256, 240, 224, 208, 192, 176, 160, 144, 128, 112, 96, 80, 64, 48, 32, 16};
+  for (int c : cand) {
+    if (c > 16 && c - 16 >= M) continue;                 // a narrower tile already holds every token
+    const long long tiles = (long long)tiles_n * ((M + c - 1) / c);
+    const double waves = (double)((tiles + sms - 1) / sms);
+    const double cost = waves * (kblocks * (YA_BYTES + c * YBK + 4096.0) + (c > 240 ? 135000.0 : 0.0));
+    if (cost < best - 1e-6) { best = cost; bn = c; nacc = c <= 240 ? 2 : 1; }
+  }
+}
+
+}  // namespace
+}  // namespace msq
+
+using namespace msq;
+
+extern "C" {
+
+int msq_tile_scales_ue8m0(const void* scales, int is_int8_exponent, int rows, int K, int rows_per_tile, unsigned char* out,
+                          void* stream) {
+  msq::DevGuard dev_guard_(scales);
+  if (!scales || !out || rows <= 0 || K <= 0 || rows_per_tile <= 0 || rows_per_tile > 256) return MSQ_ERR_BAD_ARG;
+  if (K % 128 != 0) return MSQ_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(scales) & 3) || (reinterpret_cast<uintptr_t>(out) & 15)) return MSQ_ERR_ALIGN;
+  const int chunks = (rows_per_tile + 127) / 128;
+  dim3 grid((unsigned)(K / YBK), (unsigned)((rows + rows_per_tile - 1) / rows_per_tile));
+  k_tile_scales<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(scales), is_int8_exponent ? 1 : 0, rows,
+                                                        K / 32, rows_per_tile, chunks, K / YBK, out);
+  return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+}
+
+int msq_gemm_mxfp8_tma_tile_tokens(int M, int N, int K) {
+  int dev = 0, sms = 148, bn, nacc;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 148; }
+  choose_bn(M, N, K, sms, bn, nacc);
+  return bn;
+}
+
+long long msq_gemm_mxfp8_tma_workspace_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  const int bn = msq_gemm_mxfp8_tma_tile_tokens(M, N, K);
+  const long long tiles_m = (M + bn - 1) / bn, kblocks = (K + YBK - 1) / YBK, chunks = (bn + 127) / 128;
+  return tiles_m * kblocks * chunks * 512;
+}
+
+int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* w, long long ldw,
+                       int w_is_fp4, const unsigned char* wsf_tiled, float* C, long long ldc, int M, int N, int K, int accumulate,
+                       void* workspace, long long workspace_bytes, void* stream) {
+  msq::DevGuard dev_guard_(xcodes);
+  if (!xcodes || !xe || !w || !wsf_tiled || !C || !workspace || M <= 0 || N <= 0 || K <= 0) return MSQ_ERR_BAD_ARG;
+  if (K % 128 != 0) return MSQ_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(xe) & 3) || (reinterpret_cast<uintptr_t>(xcodes) & 15) || (ldx % 16) ||
+      (reinterpret_cast<uintptr_t>(w) & 31) || (ldw % 16) || (reinterpret_cast<uintptr_t>(wsf_tiled) & 15) ||
+      (reinterpret_cast<uintptr_t>(workspace) & 15))
+    return MSQ_ERR_ALIGN;
+  if (w_is_fp4 && (ldw % 32)) return MSQ_ERR_ALIGN;
+  if (workspace_bytes < msq_gemm_mxfp8_tma_workspace_bytes(M, N, K)) return MSQ_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  YParams P;
+  memset(&P, 0, sizeof(P));
+  choose_bn(M, N, K, sms, P.bn, P.nacc);
+  P.wsf_t = wsf_tiled; P.xsf_t = reinterpret_cast<const uint8_t*>(workspace); P.C = C; P.ldc = ldc;
+  P.M = M; P.N = N; P.K = K; P.accumulate = accumulate;
+  P.tiles_n = (N + YM - 1) / YM; P.tiles_m = (M + P.bn - 1) / P.bn; P.kblocks = K / YBK; P.sfb_chunks = (P.bn + 127) / 128;
+  P.w_fmt = w_is_fp4 ? 5 : 0;
+  // a 16U4_ALIGN16B load reports the bytes it READ to the mbarrier (see msq_gemm_mx8.cu)
+  P.w_tx_bytes = w_is_fp4 ? YA_BYTES / 2 : YA_BYTES;
+  int rc = msq_tile_scales_ue8m0(xe, 1, M, K, P.bn, reinterpret_cast<unsigned char*>(workspace), stream);
+  if (rc) return rc;
+  CUtensorMap tmX, tmW;
+  rc = make_tmap_2d(&tmX, xcodes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K, ldx, P.bn, YBK);
+  if (rc) return rc;
+  if (w_is_fp4) rc = make_tmap_2d_u4(&tmW, w, N, K, ldw, YM);
+  else rc = make_tmap_2d(&tmW, w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, ldw, YM, YBK);
+  if (rc) return rc;
+  if (cudaFuncSetAttribute(k_gemm_mx8_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, Y_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
+  int grid = P.tiles_n * P.tiles_m;
+  if (grid > sms) grid = sms;
+  k_gemm_mx8_tma<<<grid, 256, Y_SMEM, s>>>(tmX, tmW, P);
+  return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+}
+
+}  // extern "C"
