@@ -307,14 +307,17 @@ int msq_gemm_mxfp8_dense(const unsigned char* xcodes, long long ldx, const signe
  *   msq_gemm_mxfp8_tma: w = dense E4M3 bytes [N, K] (ld = ldw bytes; msq_widen_fp4_to_mxfp8) or, w_is_fp4 != 0, the packed
  *     4-bit codes of a plain FP4 weight [N, K/2 bytes]; wsf_tiled = its tiled scales; xe = int8 activation exponents
  *     [M, K/32], tiled into `workspace` (msq_gemm_mxfp8_tma_workspace_bytes) by a launch in front of the GEMM.
+ *     o_ptr / o_k / o_dw (may be NULL): CSR of the outlier corrections of an FP4 weight, as in
+ *     msq_gemm_mxfp4w_blockscaled, applied by the epilogue warps to the accumulator tile they hold in registers.
  *     K % 128 == 0; w 32-byte aligned.  msq_gemm_mxfp8_tma_tile_tokens reports the token-tile width it will use. */
 int msq_tile_scales_ue8m0(const void* scales, int is_int8_exponent, int rows, int K, int rows_per_tile,
                           unsigned char* out, void* stream);
 int msq_gemm_mxfp8_tma_tile_tokens(int M, int N, int K);
 long long msq_gemm_mxfp8_tma_workspace_bytes(int M, int N, int K);
 int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* w,
-                       long long ldw, int w_is_fp4, const unsigned char* wsf_tiled, float* C, long long ldc, int M,
-                       int N, int K, int accumulate, void* workspace, long long workspace_bytes, void* stream);
+                       long long ldw, int w_is_fp4, const unsigned char* wsf_tiled, const int* o_ptr, const int* o_k,
+                       const float* o_dw, float* C, long long ldc, int M, int N, int K, int accumulate,
+                       void* workspace, long long workspace_bytes, void* stream);
 
 /* ---- host-buffer entry points --------------------------------------------------------------
  * quantize_mx_outlier_v1 (utils/quant.py:147-266) as the reference's drivers call it on CPU-resident

@@ -381,7 +381,7 @@ def widen_weight_mx8(pw):
 N.register("msq_tile_scales_ue8m0", _i, [_p, _i, _i, _i, _i, _p, _p])
 N.register("msq_gemm_mxfp8_tma_tile_tokens", _i, [_i, _i, _i])
 N.register("msq_gemm_mxfp8_tma_workspace_bytes", _ll, [_i, _i, _i])
-N.register("msq_gemm_mxfp8_tma", _i, [_p, _ll, _p, _p, _ll, _i, _p, _p, _ll, _i, _i, _i, _i, _p, _ll, _p])
+N.register("msq_gemm_mxfp8_tma", _i, [_p, _ll, _p, _p, _ll, _i, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p, _ll, _p])
 
 #: compute-bound sizes (M >= MX8_DENSE_MIN_M): fully TMA-fed kernel (csrc/msq_gemm_mx8_tma.cu)
 MX8_TMA = True
@@ -402,17 +402,37 @@ def tile_scales(scales, rows_per_tile=128):
     return out
 
 
-def mx8_tma_weight(pw, allow_copy=True):
+#: a weight WITH outliers still feeds its packed codes to the TMA-fed kernel, the outliers being the fused sparse epilogue
+#: correction, while it has at most this many outliers per output feature on average.  The correction is a gather of
+#: activation bytes by the four epilogue warps whose latency is exposed once per (outlier, 16 tokens): measured at 8192^2,
+#: 0.85 outliers per row: M = 64: 16.4 -> 26.9 us (producer-widen kernel 51.7), M = 4096: 241 -> 658 us (widened copy 245);
+#: so below the compute-bound sizes up to one per row, at them only a weight without outliers (or one whose exponents
+#: the E4M3 folding cannot represent); denser weights use the widened E4M3 copy / the producer-widen kernel
+MX8_TMA_SPARSE_MAX_PER_ROW = 1.0
+MX8_TMA_SPARSE_MAX_PER_ROW_LARGE_M = 0.0
+
+
+def mx8_tma_weight(pw, allow_copy=True, sparse_limit=None):
     """operand of the TMA-fed kernel, built once per weight and kept on the PackedMX:
-    (bytes, row pitch, is_fp4, tiled scales) -- the packed codes themselves for a plain FP4 weight (nothing is copied but
-    the scales), else, when allow_copy, the widened E4M3 copy with the outliers folded in (1 byte per weight; needs
-    mx8_weight_ok; shared with cache_dense=True); None when neither applies"""
+    (bytes, row pitch, is_fp4, tiled scales, o_ptr, o_k, o_dw) -- the packed codes themselves for an FP4 weight without
+    or with few outliers (nothing is copied but the scales; outliers = CSR correction in the epilogue), else, when
+    allow_copy, the widened E4M3 copy with the outliers folded in (1 byte per weight; needs mx8_weight_ok; shared with
+    cache_dense=True); None when neither applies"""
     Nn, K = pw.shape
-    if MX8_TMA_FP4 and pw.plain and mx4_weight_ok(pw):
+    if sparse_limit is None:
+        sparse_limit = MX8_TMA_SPARSE_MAX_PER_ROW
+    if MX8_TMA_FP4 and mx4_weight_ok(pw) and getattr(pw, "_mx8_dense", None) is None:
         op = getattr(pw, "_mx8_tma_fp4", None)
         if op is None:
-            op = pw._mx8_tma_fp4 = (pw.codes, K // 2, 1, tile_scales(pw.e_in.reshape(Nn, K // 32)))
-        return op
+            sp = mx4_sparse_outliers(pw)
+            op = pw._mx8_tma_fp4 = (pw.codes, K // 2, 1, tile_scales(pw.e_in.reshape(Nn, K // 32))) + tuple(sp)
+        nnz = 0 if op[5] is None else op[5].numel()
+        if nnz <= sparse_limit * Nn or not mx8_weight_ok(pw):
+            return op                  # few outliers -- or no other kernel can take this weight's exponents
+        if not allow_copy:
+            # below the compute-bound sizes no copy is made: the sparse epilogue up to 4x the limit, beyond that the
+            # producer-widen kernel (whose cost does not depend on the number of outliers)
+            return op if nnz <= 4 * sparse_limit * Nn else None
     dense = getattr(pw, "_mx8_dense", None)
     if dense is None:
         if not allow_copy or not mx8_weight_ok(pw):
@@ -421,7 +441,7 @@ def mx8_tma_weight(pw, allow_copy=True):
     sf_t = getattr(pw, "_mx8_dense_sf_tiled", None)
     if sf_t is None or sf_t[0] is not dense[1]:
         sf_t = pw._mx8_dense_sf_tiled = (dense[1], tile_scales(dense[1]))
-    return (dense[0], K, 0, sf_t[1])
+    return (dense[0], K, 0, sf_t[1], None, None, None)
 
 
 def packed_linear_mx8(xq, pw, bias=None, cache_dense=False):
@@ -445,14 +465,17 @@ def packed_linear_mx8(xq, pw, bias=None, cache_dense=False):
         # everything above the decode sizes: both operands and both scale streams by TMA, double-buffered accumulators.
         # A plain FP4 weight feeds its packed codes; a weight with outliers its widened E4M3 copy -- built (and kept) only
         # in the compute-bound regime or on request, below that the producer-widen kernel reads the packed planes
-        op = mx8_tma_weight(pw, allow_copy=cache_dense or dense is not None or M >= MX8_DENSE_MIN_M)
+        op = mx8_tma_weight(pw, allow_copy=cache_dense or dense is not None or M >= MX8_DENSE_MIN_M,
+                            sparse_limit=-1.0 if cache_dense else (MX8_TMA_SPARSE_MAX_PER_ROW_LARGE_M if M >= MX8_DENSE_MIN_M
+                                                                   else None))
         if op is not None:
             out = torch.empty(M, Nn, dtype=torch.float32, device=pw.codes.device)
-            w, ldw, is_fp4, wsf_t = op
+            w, ldw, is_fp4, wsf_t, o_ptr, o_k, o_dw = op
             nbytes = int(N.lib().msq_gemm_mxfp8_tma_workspace_bytes(M, Nn, K))
             ws = _workspace(nbytes, out.device)
-            rc = N.lib().msq_gemm_mxfp8_tma(N.ptr(xq.codes), K, N.ptr(xq.e_in), N.ptr(w), ldw, is_fp4, N.ptr(wsf_t), N.ptr(out),
-                                            out.stride(0), M, Nn, K, 0, N.ptr(ws), nbytes, N.stream_ptr(out.device))
+            rc = N.lib().msq_gemm_mxfp8_tma(N.ptr(xq.codes), K, N.ptr(xq.e_in), N.ptr(w), ldw, is_fp4, N.ptr(wsf_t),
+                                            N.ptr(o_ptr), N.ptr(o_k), N.ptr(o_dw), N.ptr(out), out.stride(0), M, Nn, K, 0,
+                                            N.ptr(ws), nbytes, N.stream_ptr(out.device))
             N.check(rc, "msq_gemm_mxfp8_tma")
             if bias is not None:
                 out += bias.float()

@@ -56,6 +56,8 @@ struct Mx8Params {
   int wtiled;                 // FP4-by-TMA with the weight re-laid out tile by tile (msq_tile_fp4_weight): every stage is ONE
   const uint8_t* wsf_tiled;   // contiguous 8 KB code chunk + ONE 512-byte scale chunk already in the tcgen05.cp layout
   int wfp4;
+  int pdl;                    // launched as a programmatic dependent of the zero-fill kernel: C may be touched only after
+                              // griddepcontrol.wait (the main loop overlaps the zero-fill and the launch gap behind it)
   int w_fmt;                  // tensor-core format code of the weight operand (0 = E4M3, 5 = E2M1)
   int w_tx_bytes;             // bytes the weight TMA load reports to the mbarrier
   const int* o_ptr; const int* o_k; const float* o_dw;      // CSR over output features (NULL: no outliers)
@@ -422,6 +424,7 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
       }
       tc::mbar_wait(acc_full, acc_phase);
       tc::tc_fence_after();
+      if (P.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
       for (int c = 0; c < P.bnx / 16; ++c) {
         uint32_t r[16];
         asm volatile(
@@ -474,6 +477,18 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
   if (warp == 2) {
     tc::tc_fence_after();
     tc::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// zero-fill of C in front of a split-K launch.  It releases its dependent (the GEMM, launched with programmatic stream
+// serialization) at once: the GEMM's prologue and main loop run while C is being cleared, its epilogue waits
+// (griddepcontrol.wait) for this grid to have completed before the first atomicAdd.
+__global__ void __launch_bounds__(256) k_zero_c(float* __restrict__ C, long long ldc, int M, int N) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const long long n4 = N >> 2;                       // N % 4 == 0 and ldc % 4 == 0 (checked by the launcher)
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < (long long)M * n4; i += (long long)gridDim.x * 256) {
+    const long long m = i / n4, c = i - m * n4;
+    *reinterpret_cast<float4*>(C + m * ldc + c * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -602,7 +617,14 @@ static int launch_mx8(const unsigned char* xcodes, long long ldx, const signed c
     P.sfb_pre = (P.wtiled && bnx <= 128 && one_tile && (long long)P.kb_per_split * 512 <= (long long)MX8_SMEM - 1024 - 256 - ring) ? 1 : 0;
   }
   if (ksplit > 1 && !accumulate) {
-    if (ldc == N) cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s);
+    const bool no_pdl = getenv("MSQ_MX8_NO_PDL") != nullptr;
+    if (!no_pdl && (N % 4) == 0 && (ldc % 4) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
+      const long long n4 = (long long)M * (N >> 2);
+      int zb = (int)((n4 + 255) / 256);
+      if (zb > 4 * sms) zb = 4 * sms;
+      k_zero_c<<<zb, 256, 0, s>>>(C, ldc, M, N);
+      P.pdl = 1;
+    } else if (ldc == N) cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s);
     else cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s);
   }
   CUtensorMap tmX, tmW;
@@ -624,6 +646,16 @@ static int launch_mx8(const unsigned char* xcodes, long long ldx, const signed c
   if (cudaFuncSetAttribute(k_gemm_mx8, cudaFuncAttributeMaxDynamicSharedMemorySize, MX8_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
   int grid = P.tiles_n * P.tiles_m * P.ksplit;
   if (grid > sms) grid = sms;
+  if (P.pdl) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = MX8_SMEM; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_gemm_mx8, tmX, tmW, P) == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+  }
   k_gemm_mx8<<<grid, 512, MX8_SMEM, s>>>(tmX, tmW, P);
   return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
 }

@@ -32,7 +32,11 @@ struct YParams {
   const uint8_t* wsf_t;       // weight scales, tiled:     chunk (tn, kb)    at (tn * kblocks + kb) * 512
   const uint8_t* xsf_t;       // activation scales, tiled: chunks (tm, kb)   at (tm * kblocks + kb) * 512 * sfb_chunks
   float* C; long long ldc;
-  int M, N, K, bn, nacc, tiles_n, tiles_m, kblocks, sfb_chunks, accumulate, w_fmt, w_tx_bytes;
+  int M, N, K, bn, nacc, tiles_n, tiles_m, kblocks, sfb_chunks, accumulate, w_fmt, w_tx_bytes, pdl;
+  // sparse outlier correction fused into the epilogue (FP4 operand whose outlier slots the tensor core reads as
+  // q * 2^e_in):  C[m, n] += sum_e x[m, o_k[e]] * o_dw[e]  over the CSR row of feature n; o_ptr NULL = none
+  const int* o_ptr; const int* o_k; const float* o_dw;
+  const uint8_t* xcodes; long long ldx; const int8_t* xe;
 };
 
 __device__ __forceinline__ uint64_t sf_desc(uint32_t smem_addr) {     // see make_sf_desc in msq_gemm_mx8.cu
@@ -104,6 +108,8 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__
     // ---- loads: per stage one weight tile, one activation tile, one + sfb_chunks scale chunks, all on one mbarrier
     int stage = 0; uint32_t phase = 0;
     const uint32_t tx = (uint32_t)(P.w_tx_bytes + P.bn * YBK + 512 + 512 * P.sfb_chunks);
+    // programmatic dependent of k_tile_scales (which releases us at once): everything up to here overlapped it
+    if (P.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int tn, tm; tile_coords(t, tn, tm);
       const uint8_t* wsf = P.wsf_t + (long long)tn * P.kblocks * 512;
@@ -166,6 +172,8 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__
       int tn, tm; tile_coords(t, tn, tm);
       const int n = tn * YM + q * 32 + lane;
       const int m0 = tm * P.bn;
+      int oe0 = 0, oe1 = 0;
+      if (P.o_ptr && n < P.N) { oe0 = __ldg(P.o_ptr + n); oe1 = __ldg(P.o_ptr + n + 1); }
       tc::mbar_wait(&acc_full[as], (acc_phase >> as) & 1u);
       tc::tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * P.bn);
@@ -180,6 +188,29 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__
             : "memory");
         tc::tmem_ld_wait();
         if (n < P.N) {
+          if (oe1 > oe0) {      // this feature's outliers against the 16 tokens in registers
+            const int kblk32 = P.K >> 5;
+            for (int e = oe0; e < oe1; ++e) {
+              const int k = __ldg(P.o_k + e);
+              const float dw = __ldg(P.o_dw + e);
+              // all 32 gathers are issued before the first use (rows clamped instead of predicated): one load latency
+              // per (outlier, 16 tokens) instead of sixteen
+              uint32_t cb[16];
+              int eb[16];
+#pragma unroll
+              for (int v = 0; v < 16; ++v) {
+                const long long m = min(m0 + c + v, P.M - 1);
+                cb[v] = __ldg(P.xcodes + m * P.ldx + k);
+                eb[v] = __ldg(P.xe + m * kblk32 + (k >> 5));
+              }
+#pragma unroll
+              for (int v = 0; v < 16; ++v) {
+                const float xs = eb[v] == MSQ_EXP_NAN ? qnan() : pow2i(eb[v]);
+                const float xv = __fmul_rn(decode_elem(cb[v], 4, 5), xs);
+                r[v] = __float_as_uint(fmaf(xv, dw, __uint_as_float(r[v])));
+              }
+            }
+          }
 #pragma unroll
           for (int v = 0; v < 16; ++v) {
             if (m0 + c + v < P.M) {
@@ -209,6 +240,7 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__
 // for row r of the piece and 32-block j of the K block; rows outside the matrix get 2^0
 __global__ void __launch_bounds__(256) k_tile_scales(const uint8_t* __restrict__ src, int add127, int rows, int kblk32,
                                                      int rows_per_tile, int chunks, int kblocks, uint8_t* __restrict__ out) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // the GEMM behind us waits before it reads `out`
   const int kb = blockIdx.x, tile = blockIdx.y;
   const int r = threadIdx.x;
   if (r >= chunks * 128) return;
@@ -279,8 +311,8 @@ long long msq_gemm_mxfp8_tma_workspace_bytes(int M, int N, int K) {
 }
 
 int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* w, long long ldw,
-                       int w_is_fp4, const unsigned char* wsf_tiled, float* C, long long ldc, int M, int N, int K, int accumulate,
-                       void* workspace, long long workspace_bytes, void* stream) {
+                       int w_is_fp4, const unsigned char* wsf_tiled, const int* o_ptr, const int* o_k, const float* o_dw, float* C,
+                       long long ldc, int M, int N, int K, int accumulate, void* workspace, long long workspace_bytes, void* stream) {
   msq::DevGuard dev_guard_(xcodes);
   if (!xcodes || !xe || !w || !wsf_tiled || !C || !workspace || M <= 0 || N <= 0 || K <= 0) return MSQ_ERR_BAD_ARG;
   if (K % 128 != 0) return MSQ_ERR_UNSUPPORTED;
@@ -289,6 +321,7 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
       (reinterpret_cast<uintptr_t>(workspace) & 15))
     return MSQ_ERR_ALIGN;
   if (w_is_fp4 && (ldw % 32)) return MSQ_ERR_ALIGN;
+  if (o_ptr && (!o_k || !o_dw)) return MSQ_ERR_BAD_ARG;
   if (workspace_bytes < msq_gemm_mxfp8_tma_workspace_bytes(M, N, K)) return MSQ_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   int dev = 0, sms = 148;
@@ -299,6 +332,7 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
   choose_bn(M, N, K, sms, P.bn, P.nacc);
   P.wsf_t = wsf_tiled; P.xsf_t = reinterpret_cast<const uint8_t*>(workspace); P.C = C; P.ldc = ldc;
   P.M = M; P.N = N; P.K = K; P.accumulate = accumulate;
+  P.o_ptr = o_ptr; P.o_k = o_k; P.o_dw = o_dw; P.xcodes = xcodes; P.ldx = ldx; P.xe = xe;
   P.tiles_n = (N + YM - 1) / YM; P.tiles_m = (M + P.bn - 1) / P.bn; P.kblocks = K / YBK; P.sfb_chunks = (P.bn + 127) / 128;
   P.w_fmt = w_is_fp4 ? 5 : 0;
   // a 16U4_ALIGN16B load reports the bytes it READ to the mbarrier (see msq_gemm_mx8.cu)
@@ -314,6 +348,17 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
   if (cudaFuncSetAttribute(k_gemm_mx8_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, Y_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
   int grid = P.tiles_n * P.tiles_m;
   if (grid > sms) grid = sms;
+  if (getenv("MSQ_MX8_NO_PDL") == nullptr) {
+    P.pdl = 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Y_SMEM; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_gemm_mx8_tma, tmX, tmW, P) == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+  }
   k_gemm_mx8_tma<<<grid, 256, Y_SMEM, s>>>(tmX, tmW, P);
   return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
 }
