@@ -319,6 +319,18 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
                        const float* o_dw, float* C, long long ldc, int M, int N, int K, int accumulate,
                        void* workspace, long long workspace_bytes, void* stream);
 
+/* W4A16 on the block-scaled tensor-core path: 16-bit activations as a sum of three block-scaled E4M3 terms
+ *     x[m, k] = sum_{t<3} a_t[m, k] * 2^(e_t[m, k/32]),  e_t = e_1 - 3 (t - 1),  e_1 = exponent(block max) - 7,
+ * each term the truncation of the remainder onto the E4M3 grid (exact fp32 steps).  bf16 elements within 2^15 of their
+ * block's maximum (fp16: 2^11) are reproduced exactly; smaller ones are truncated at 2^-22 of the block maximum.
+ * The terms are stacked along the token dimension (row t * M + m of codes [3M, K] / e [3M, K/32]): the block-scaled
+ * GEMMs above run once with 3M tokens -- the packed 4-bit weight codes are the other operand, read once -- and the caller
+ * adds the three M-row slabs.  Replaces the bf16 fake-quant matmul of number_system/mx/linear.py:78-91 for
+ * a_elem_format = None (16-bit activations) without dequantizing the weight.
+ * dtype: 1 = fp16, 2 = bf16; K % 32 == 0; x 16-byte aligned, ldx % 8 == 0. */
+int msq_split_a16_e4m3x3(const void* x, long long ldx, int dtype, int M, int K, unsigned char* codes, signed char* e,
+                         void* stream);
+
 /* ---- host-buffer entry points --------------------------------------------------------------
  * quantize_mx_outlier_v1 (utils/quant.py:147-266) as the reference's drivers call it on CPU-resident
  * weights (llm/llama.py:94-121): h_in / h_out are HOST pointers (pinned for full PCIe speed), the

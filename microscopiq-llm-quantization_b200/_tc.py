@@ -196,6 +196,33 @@ def _packed_linear_rowblock(x2, pw, out):
     return out
 
 
+N.register("msq_split_a16_e4m3x3", _i, [_p, _ll, _i, _i, _i, _p, _p, _p])
+
+#: 16-bit activations against a K-blocked FP4 weight below FUSED_MAX_M rows: three block-scaled E4M3 terms on the
+#: block-scaled tensor-core path (the packed codes are the operand) instead of the producer-dequantizing bf16 kernel
+SPLIT_A16 = True
+
+
+class _SplitActs(object):
+    """the stacked E4M3 terms of a 16-bit activation matrix, shaped like the PackedMX that packed_linear_mx8 takes"""
+    block_size, code_width, in_fmt, plain = 32, 8, "fp8_e4m3", True
+
+    def __init__(self, codes, e_in, shape):
+        self.codes, self.e_in, self.shape = codes, e_in, shape
+
+
+def split_a16(x2):
+    """x2 [M, K] bf16 / fp16 -> _SplitActs with 3 M rows (msq_split_a16_e4m3x3)"""
+    M, K = x2.shape
+    x2 = x2 if x2.stride(1) == 1 and x2.stride(0) % 8 == 0 and x2.data_ptr() % 16 == 0 else x2.contiguous()
+    codes = torch.empty(3 * M, K, dtype=torch.uint8, device=x2.device)
+    e = torch.empty(3 * M, K // 32, dtype=torch.int8, device=x2.device)
+    rc = N.lib().msq_split_a16_e4m3x3(N.ptr(x2), x2.stride(0), _DT[x2.dtype], M, K, N.ptr(codes), N.ptr(e),
+                                      N.stream_ptr(x2.device))
+    N.check(rc, "msq_split_a16_e4m3x3")
+    return _SplitActs(codes, e, (3 * M, K))
+
+
 def packed_linear(x, pw, bias=None):
     """y[..., N] (fp32) = x[..., K] @ dequant(pw)[N, K].T (+ bias) with pw a PackedMX blocked along K
     (block 32).  bf16 activations take one pass; fp16 / fp32 activations are split into exact bf16
@@ -241,6 +268,15 @@ def packed_linear(x, pw, bias=None):
             wb = pw._dense_bf16 = pw.dequantize(torch.bfloat16)
         for i, t in enumerate(_bf16_terms(x2)):
             gemm_nt(t.contiguous(), wb, out=out, alpha=1.0, beta=1.0 if i else 0.0)
+        if bias is not None:
+            out += bias.float()
+        return out.reshape(*lead, Nn)
+    if (SPLIT_A16 and x2.dtype in (torch.bfloat16, torch.float16) and K % 128 == 0 and Nn % 4 == 0 and mx4_weight_ok(pw)
+            and (3 * M <= FP4_TMA_MAX_M or mx8_tma_weight(pw, allow_copy=False) is not None)):
+        # W4A16 without dequantizing the weight: the activations become three block-scaled E4M3 terms stacked along the
+        # token dimension, the packed codes feed the block-scaled tensor-core kernels, the three slabs are added
+        y3 = packed_linear_mx8(split_a16(x2), pw)
+        out = y3.view(3, M, Nn).sum(0)
         if bias is not None:
             out += bias.float()
         return out.reshape(*lead, Nn)

@@ -70,3 +70,65 @@ def test_mx_linear_matches_reference_fixtures(M):
         assert torch.equal(y2, y)
         assert lin.packed_weight() is lin.packed_weight()          # cached
     assert torch.equal(M.linear(x, w, b, None), torch.nn.functional.linear(x, w, b))
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_split_a16_terms_reproduce_the_activations(M, dt):
+    """msq_split_a16_e4m3x3: sum_t a_t * 2^e_t == x EXACTLY while an element is within 2^15 (bf16) / 2^11 (fp16) of its
+    block's maximum; below that the truncation error is < 2^-22 of the block maximum.  Inf / NaN poison their block."""
+    from msq_b200 import _tc
+    g = torch.Generator().manual_seed(3)
+    Mx, K = 37, 512
+    spread = 15 if dt == torch.bfloat16 else 11
+    x = torch.randn(Mx, K, generator=g) * torch.exp2(torch.randint(-spread // 2, spread // 2 + 1, (Mx, K), generator=g).float())
+    x[0, :32] = 0.0                                        # an all-zero block
+    x[1, 5] = 0.0
+    x = x.to(dt)
+    x[2, 40:48] = torch.tensor([2.0 ** -i for i in range(8)], dtype=dt) * x[2, 40:48].abs().max() + 0    # exact powers of two
+    sa = _tc.split_a16(x.cuda())
+    terms = sa.codes.view(torch.float8_e4m3fn).float().view(3, Mx, K // 32, 32) * torch.exp2(sa.e_in.float()).view(3, Mx, K // 32, 1)
+    rec = terms.sum(0).view(Mx, K)
+    xf = x.float().cuda()
+    blockmax = xf.abs().view(Mx, K // 32, 32).amax(-1, keepdim=True).expand(Mx, K // 32, 32).reshape(Mx, K)
+    near = xf.abs() * 2.0 ** spread >= blockmax
+    assert torch.equal(rec[near], xf[near])
+    assert bool(((rec - xf).abs() <= blockmax * 2.0 ** -22).all())
+    # wide dynamic range inside a block: truncation at 2^-22 of the block maximum, never more
+    y = (torch.randn(8, 256, generator=g) * torch.exp2(torch.randint(-30, 1, (8, 256), generator=g).float())).to(dt).cuda()
+    sb = _tc.split_a16(y)
+    rec = (sb.codes.view(torch.float8_e4m3fn).float().view(3, 8, 8, 32) * torch.exp2(sb.e_in.float()).view(3, 8, 8, 1)).sum(0).view(8, 256)
+    bm = y.float().abs().view(8, 8, 32).amax(-1, keepdim=True).expand(8, 8, 32).reshape(8, 256)
+    assert bool(((rec - y.float()).abs() <= bm * 2.0 ** -22).all()) and bool((rec.abs() <= y.float().abs()).all())
+    z = torch.ones(2, 64, dtype=dt).cuda()
+    z[1, 3] = float("inf")
+    sz = _tc.split_a16(z)
+    assert int(sz.e_in[1, 0]) == -128 and int(sz.e_in[3, 0]) == -128 and int(sz.e_in[5, 0]) == -128 and int(sz.e_in[1, 1]) != -128
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("Mx,N,K", [(1, 256, 128), (8, 512, 1024), (16, 4096, 4096), (48, 384, 256), (200, 1024, 2048), (500, 256, 512)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("outliers", [False, True])
+def test_w4a16_on_the_block_scaled_path(M, monkeypatch, Mx, N, K, dt, outliers):
+    """16-bit activations x K-blocked FP4 weight: packed_linear splits the activations into three block-scaled E4M3 terms
+    and runs the block-scaled kernels on the packed codes (no bf16 copy of the weight, no producer dequantization).
+    Same tolerance as the bf16 kernel: the split is exact for these inputs, products are exact, fp32 accumulation."""
+    from msq_b200 import _tc
+    g = torch.Generator().manual_seed(N + K + Mx)
+    W = torch.randn(N, K, generator=g) * 0.02
+    if outliers:
+        W.view(-1)[torch.randperm(W.numel(), generator=g)[: W.numel() // 2000]] *= 20
+        pw = M.pack_mx_outlier(W.cuda(), 8, 8, "fp4_e2m1", "fp4_e2m1", 5, [1], 32, variant=1)
+    else:
+        pw = M.pack_mx(W.cuda(), 8, "fp4_e2m1", axes=[1], block_size=32)
+    x = (torch.randn(Mx, K, generator=g) * torch.logspace(-2, 1, Mx).unsqueeze(1)).to(dt)
+    calls = []
+    real = _tc.split_a16
+    monkeypatch.setattr(_tc, "split_a16", lambda t: (calls.append(1), real(t))[1])
+    y = _tc.packed_linear(x.cuda(), pw)
+    assert calls, "packed_linear did not take the split-activation path"
+    check(y.cpu(), x.float(), pw.dequantize().cpu())
+    monkeypatch.setattr(_tc, "SPLIT_A16", False)           # the producer-dequantizing bf16 kernel agrees
+    y0 = _tc.packed_linear(x.cuda(), pw)
+    check(y0.cpu(), x.float(), pw.dequantize().cpu())
