@@ -17,7 +17,7 @@ LIB = os.path.join(HERE, "libmsq_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 # per-file extra flags: the quantizers mirror the reference's op-by-op fp32 arithmetic
-EXTRA = {"msq_quant_strided.cu": ["-fmad=false"], "msq_quant_inner.cu": ["-fmad=false"], "msq_quant_misc.cu": ["-fmad=false"], "msq_pack.cu": ["-fmad=false"], "msq_gptq.cu": ["-fmad=false"],
+EXTRA = {"msq_quant_strided.cu": ["-fmad=false"], "msq_quant_strided_big.cu": ["-fmad=false"], "msq_quant_inner.cu": ["-fmad=false"], "msq_quant_misc.cu": ["-fmad=false"], "msq_pack.cu": ["-fmad=false"], "msq_gptq.cu": ["-fmad=false"],
          "msq_uniform.cu": ["-fmad=false"]}
 
 

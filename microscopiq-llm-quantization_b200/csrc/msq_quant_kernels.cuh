@@ -101,5 +101,7 @@ int launch_pack_tma(const QParams& Q, cudaStream_t stream);
 cudaError_t launch_strided(const QParams& P, bool outlier, size_t smem, cudaStream_t stream);
 cudaError_t launch_inner(const QParams& P, bool outlier, size_t smem, cudaStream_t stream);
 cudaError_t launch_generic(const QParams& P, bool outlier, cudaStream_t stream);
+// long blocks (64 / 128) along a strided axis, values (+ exponents / counts) only: msq_quant_strided_big.cu, path 6
+cudaError_t launch_strided_big(const QParams& P, bool outlier, cudaStream_t stream);
 
 }  // namespace msq

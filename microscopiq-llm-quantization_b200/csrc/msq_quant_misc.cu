@@ -302,6 +302,10 @@ static int launch_quant(QParams& P, bool outlier, cudaStream_t stream, int* path
              (packing || P.pre * (long long)P.nblk <= 65535)) {
     path = 1;
     err = launch_strided(P, outlier, smem, stream);
+  } else if (fast_ok && !packing && P.post > 1 && (P.post & 3) == 0 && inout_al && (P.bs == 64 || P.bs == 128) &&
+             !(outlier && P.c.variant != 0) && P.pre * (long long)P.nblk * ((P.post + 63) / 64) < 0x7fffffffLL) {
+    path = 6;
+    err = launch_strided_big(P, outlier, stream);
   } else {
     if (packing) return MSQ_ERR_UNSUPPORTED;
     path = 3;

@@ -208,6 +208,12 @@ CASES = [
     ("int4", "int8", 128, 1, (64, 1024), 2),
     ("int4", "int8", 64, 1, (64, 1024), 2),
     ("int8", "fp8_e5m2", 8, 1, (64, 1024), 2),
+    # long blocks along the rows ("group 128"): shared-memory staged kernel, 8 / 4 lanes per block (path 6)
+    ("fp4_e2m1", "fp8_e4m3", 128, 0, (512, 768), 6),
+    ("int4", "int8", 64, 0, (200, 132), 6),             # ragged rows (200 = 3 x 64 + 8) and a 4-column last tile
+    ("fp6_e3m2", "fp6_e3m2", 128, 0, (1000, 260), 6),
+    ("fp4_e2m1", "fp4_e2m1", 128, 0, (128, 4), 6),
+    ("fp4_e2m1", "fp8_e4m3", 128, 0, (256, 130), 3),    # post % 4 != 0 -> generic
     ("fp4_e2m1", "fp8_e4m3", 32, 1, (100, 1000), 3),   # 1000 % 32 != 0
     ("fp4_e2m1", "fp8_e4m3", 24, 0, (96, 64), 3),
 ]
@@ -376,7 +382,7 @@ def test_plain_mx_adversarial_vs_oracle(M, fmt, rnd, mode):
     x = _adversarial_values()
     x = x[torch.isfinite(x)]
     x = x[: (x.numel() // 1024) * 1024].view(-1, 1024)
-    for axis, bs in ((1, 32), (0, 16), (1, 16)):
+    for axis, bs in ((1, 32), (0, 16), (1, 16), (0, 128), (0, 64)):
         y = M._quantize_mx(x.cuda(), 8, fmt, axes=[axis], block_size=bs, round=rnd, custom_cuda=(mode == "spec"))
         assert_exact(y, O.quantize_mx(x, 8, fmt, axis, bs, rnd, mode=mode), "%s %s %s axis%d" % (fmt, rnd, mode, axis))
 
@@ -422,3 +428,27 @@ def test_full_size_deviation_set_of_the_bench_workload(M):
         assert torch.equal(W.reshape(-1)[idx], torch.tensor(m["x"]))      # same inputs as the authoring run
         assert torch.equal(flat[idx], torch.tensor(m["oracle"]))
         assert bool((flat[idx] != torch.tensor(m["reference"])).all())    # ... and these are the reference's deviations
+
+
+def test_long_block_strided_kernel(M):
+    """path 6 (msq_quant_strided_big.cu): block 64 / 128 along the rows of a 2-D weight and along the middle axis of a 3-D
+    tensor == oracle; status word and NaN block like the other mappings; plain MX takes the same kernel"""
+    from msq_b200 import _ops
+    W = weights(384, 512, 3)
+    for bs in (64, 128):
+        r = _ops.mx_outlier(W.cuda(), 8, 8, "fp4_e2m1", "fp8_e4m3", 2, 0, bs)
+        assert r.path == 6
+        assert_exact(r.deq, O.quantize_mx_outlier(W, 8, 8, "fp4_e2m1", "fp8_e4m3", 2, 0, bs))
+        yp, ep, path = _ops.mx_plain(W.cuda(), 8, "fp4_e2m1", 0, bs, want_exp=True)
+        assert path == 6
+        assert_exact(yp, O.quantize_mx(W, 8, "fp4_e2m1", 0, bs, "nearest", mode="python"))
+    X = weights(3 * 256, 64, 4).view(3, 256, 64)
+    r = _ops.mx_outlier(X.cuda(), 8, 8, "int4", "fp8_e4m3", 2, 1, 128)
+    assert r.path == 6
+    assert_exact(r.deq, O.quantize_mx_outlier(X, 8, 8, "int4", "fp8_e4m3", 2, 1, 128))
+    W2 = W.clone()
+    W2[200, 77] = float("inf")
+    st = torch.zeros(1, dtype=torch.int32, device="cuda")
+    r = _ops.mx_outlier(W2.cuda(), 8, 8, "fp4_e2m1", "fp8_e4m3", 2, 0, 128, check=False, status=st)
+    assert r.path == 6 and int(st.item()) & _ops.N.ST_NONFINITE_INPUT
+    assert torch.isnan(r.deq[128:256, 77]).all() and not torch.isnan(r.deq[:, :77]).any() and not torch.isnan(r.deq[:128]).any()
