@@ -288,6 +288,14 @@ int msq_gemm_mxfp4w_tiled_blockscaled(const unsigned char* xcodes, long long ldx
                                       const int* o_ptr, const int* o_k, const float* o_dw, float* C, long long ldc,
                                       int M, int N, int K, int accumulate, void* stream);
 
+/* msq_gemm_mxfp4w_tiled_blockscaled over STACKED activation terms (msq_split_a16_e4m3 below: M = terms * fold_m rows):
+ * row m is added into C[m % fold_m, :] by the epilogue (C [fold_m, N] is zero-filled by the call), so a W4A16 linear at
+ * decode sizes is the split launch + this call. */
+int msq_gemm_mxfp4w_tiled_folded(const unsigned char* xcodes, long long ldx, const signed char* xe,
+                                 const unsigned char* codes_tiled, const unsigned char* sf_tiled, const int* o_ptr,
+                                 const int* o_k, const float* o_dw, float* C, long long ldc, int M, int fold_m, int N,
+                                 int K, void* stream);
+
 /* compute-bound variant of the block-scaled path: widen the packed FP4 weight once to dense MX-FP8
  * (E4M3 bytes [N,K] + UE8M0 scales [N,K/32]), then run the GEMM with both operands streamed by TMA. */
 int msq_widen_fp4_to_mxfp8(const unsigned char* wcodes, const unsigned int* wbitmap, const signed char* we_in,
@@ -319,17 +327,18 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
                        const float* o_dw, float* C, long long ldc, int M, int N, int K, int accumulate,
                        void* workspace, long long workspace_bytes, void* stream);
 
-/* W4A16 on the block-scaled tensor-core path: 16-bit activations as a sum of three block-scaled E4M3 terms
- *     x[m, k] = sum_{t<3} a_t[m, k] * 2^(e_t[m, k/32]),  e_t = e_1 - 3 (t - 1),  e_1 = exponent(block max) - 7,
- * each term the truncation of the remainder onto the E4M3 grid (exact fp32 steps).  bf16 elements within 2^15 of their
- * block's maximum (fp16: 2^11) are reproduced exactly; smaller ones are truncated at 2^-22 of the block maximum.
- * The terms are stacked along the token dimension (row t * M + m of codes [3M, K] / e [3M, K/32]): the block-scaled
- * GEMMs above run once with 3M tokens -- the packed 4-bit weight codes are the other operand, read once -- and the caller
- * adds the three M-row slabs.  Replaces the bf16 fake-quant matmul of number_system/mx/linear.py:78-91 for
+/* W4A16 on the block-scaled tensor-core path: 16-bit activations as a sum of T = 2 or 3 block-scaled E4M3 terms
+ *     x[m, k] = sum_{t<T} a_t[m, k] * 2^(e_t[m, k/32]),  e_t = e_1 - 3 (t - 1),  e_1 = exponent(block max) - 7,
+ * each term the truncation of the remainder onto the E4M3 grid (exact fp32 steps).  T = 2 (8 significant bits): bf16
+ * elements within 2^12 of their block's maximum are reproduced exactly, smaller ones are truncated at 2^-19 of the block
+ * maximum; T = 3 (12 bits): bf16 within 2^15, fp16 within 2^11, truncation at 2^-22.
+ * The terms are stacked along the token dimension (row t * M + m of codes [T M, K] / e [T M, K/32]): the block-scaled
+ * GEMMs above run once with T M tokens -- the packed 4-bit weight codes are the other operand, read once -- and the caller
+ * adds the T M-row slabs.  Replaces the bf16 fake-quant matmul of number_system/mx/linear.py:78-91 for
  * a_elem_format = None (16-bit activations) without dequantizing the weight.
  * dtype: 1 = fp16, 2 = bf16; K % 32 == 0; x 16-byte aligned, ldx % 8 == 0. */
-int msq_split_a16_e4m3x3(const void* x, long long ldx, int dtype, int M, int K, unsigned char* codes, signed char* e,
-                         void* stream);
+int msq_split_a16_e4m3(const void* x, long long ldx, int dtype, int M, int K, int terms, unsigned char* codes,
+                       signed char* e, void* stream);
 
 /* ---- host-buffer entry points --------------------------------------------------------------
  * quantize_mx_outlier_v1 (utils/quant.py:147-266) as the reference's drivers call it on CPU-resident

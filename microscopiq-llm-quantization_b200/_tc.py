@@ -196,9 +196,10 @@ def _packed_linear_rowblock(x2, pw, out):
     return out
 
 
-N.register("msq_split_a16_e4m3x3", _i, [_p, _ll, _i, _i, _i, _p, _p, _p])
+N.register("msq_gemm_mxfp4w_tiled_folded", _i, [_p, _ll, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p])
+N.register("msq_split_a16_e4m3", _i, [_p, _ll, _i, _i, _i, _i, _p, _p, _p])
 
-#: 16-bit activations against a K-blocked FP4 weight below FUSED_MAX_M rows: three block-scaled E4M3 terms on the
+#: 16-bit activations against a K-blocked FP4 weight below FUSED_MAX_M rows: two / three block-scaled E4M3 terms on the
 #: block-scaled tensor-core path (the packed codes are the operand) instead of the producer-dequantizing bf16 kernel
 SPLIT_A16 = True
 
@@ -211,16 +212,24 @@ class _SplitActs(object):
         self.codes, self.e_in, self.shape = codes, e_in, shape
 
 
-def split_a16(x2):
-    """x2 [M, K] bf16 / fp16 -> _SplitActs with 3 M rows (msq_split_a16_e4m3x3)"""
+#: E4M3 terms per 16-bit activation: 2 hold bf16's 8 significant bits (exact within 2^12 of the block maximum, truncation
+#: at 2^-19 of it below), fp16's 11 bits need 3
+SPLIT_A16_TERMS = {torch.bfloat16: 2, torch.float16: 3}
+
+
+def split_a16(x2, terms=None):
+    """x2 [M, K] bf16 / fp16 -> _SplitActs with terms * M rows (msq_split_a16_e4m3)"""
     M, K = x2.shape
+    T = int(terms or SPLIT_A16_TERMS[x2.dtype])
     x2 = x2 if x2.stride(1) == 1 and x2.stride(0) % 8 == 0 and x2.data_ptr() % 16 == 0 else x2.contiguous()
-    codes = torch.empty(3 * M, K, dtype=torch.uint8, device=x2.device)
-    e = torch.empty(3 * M, K // 32, dtype=torch.int8, device=x2.device)
-    rc = N.lib().msq_split_a16_e4m3x3(N.ptr(x2), x2.stride(0), _DT[x2.dtype], M, K, N.ptr(codes), N.ptr(e),
-                                      N.stream_ptr(x2.device))
-    N.check(rc, "msq_split_a16_e4m3x3")
-    return _SplitActs(codes, e, (3 * M, K))
+    codes = torch.empty(T * M, K, dtype=torch.uint8, device=x2.device)
+    e = torch.empty(T * M, K // 32, dtype=torch.int8, device=x2.device)
+    rc = N.lib().msq_split_a16_e4m3(N.ptr(x2), x2.stride(0), _DT[x2.dtype], M, K, T, N.ptr(codes), N.ptr(e),
+                                    N.stream_ptr(x2.device))
+    N.check(rc, "msq_split_a16_e4m3")
+    sa = _SplitActs(codes, e, (T * M, K))
+    sa.terms = T
+    return sa
 
 
 def packed_linear(x, pw, bias=None):
@@ -271,12 +280,23 @@ def packed_linear(x, pw, bias=None):
         if bias is not None:
             out += bias.float()
         return out.reshape(*lead, Nn)
-    if (SPLIT_A16 and x2.dtype in (torch.bfloat16, torch.float16) and K % 128 == 0 and Nn % 4 == 0 and mx4_weight_ok(pw)
-            and (3 * M <= FP4_TMA_MAX_M or mx8_tma_weight(pw, allow_copy=False) is not None)):
-        # W4A16 without dequantizing the weight: the activations become three block-scaled E4M3 terms stacked along the
-        # token dimension, the packed codes feed the block-scaled tensor-core kernels, the three slabs are added
-        y3 = packed_linear_mx8(split_a16(x2), pw)
-        out = y3.view(3, M, Nn).sum(0)
+    if (SPLIT_A16 and x2.dtype in SPLIT_A16_TERMS and K % 128 == 0 and Nn % 4 == 0 and mx4_weight_ok(pw)
+            and (SPLIT_A16_TERMS[x2.dtype] * M <= FP4_TMA_MAX_M or mx8_tma_weight(pw, allow_copy=False) is not None)):
+        # W4A16 without dequantizing the weight: the activations become two / three block-scaled E4M3 terms stacked along
+        # the token dimension, the packed codes feed the block-scaled tensor-core kernels, the slabs are added
+        sa = split_a16(x2)
+        if FP4_TMA and FP4_TILED and sa.shape[0] <= FP4_TMA_MAX_M:
+            # decode sizes: the slabs are summed by the split-K atomics of the GEMM itself
+            o_ptr, o_k, o_dw = mx4_sparse_outliers(pw)
+            ct, st = mx4_tiled_weight(pw)
+            out = torch.empty(M, Nn, dtype=torch.float32, device=x2.device)
+            rc = N.lib().msq_gemm_mxfp4w_tiled_folded(N.ptr(sa.codes), K, N.ptr(sa.e_in), N.ptr(ct), N.ptr(st), N.ptr(o_ptr),
+                                                      N.ptr(o_k), N.ptr(o_dw), N.ptr(out), out.stride(0), sa.shape[0], M, Nn, K,
+                                                      N.stream_ptr(out.device))
+            N.check(rc, "msq_gemm_mxfp4w_tiled_folded")
+        else:
+            y3 = packed_linear_mx8(sa, pw)
+            out = y3.view(sa.terms, M, Nn).sum(0)
         if bias is not None:
             out += bias.float()
         return out.reshape(*lead, Nn)

@@ -56,6 +56,8 @@ struct Mx8Params {
   int wtiled;                 // FP4-by-TMA with the weight re-laid out tile by tile (msq_tile_fp4_weight): every stage is ONE
   const uint8_t* wsf_tiled;   // contiguous 8 KB code chunk + ONE 512-byte scale chunk already in the tcgen05.cp layout
   int wfp4;
+  int fold_m;                 // > 0: the M rows are fold slabs of fold_m tokens each (stacked activation terms of a 16-bit
+                              // operand, msq_split_a16_e4m3): row m is ADDED into output row m % fold_m (atomics, C zero-filled)
   int pdl;                    // launched as a programmatic dependent of the zero-fill kernel: C may be touched only after
                               // griddepcontrol.wait (the main loop overlaps the zero-fill and the launch gap behind it)
   int w_fmt;                  // tensor-core format code of the weight operand (0 = E4M3, 5 = E2M1)
@@ -399,7 +401,66 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
       // runs -- the epilogue warps have nothing else to do until the accumulator is complete -- and added afterwards
       constexpr int CORR_MAX = 32;
       float corr[CORR_MAX];
-      const bool pre_corr = P.bnx <= CORR_MAX;
+      // C is accumulated by atomics (split K / folded slabs): the correction does not have to pass through the thread that
+      // owns the accumulator row.  The whole warp works on one outlier at a time -- lane = token, one gather per lane
+      // instead of one lane gathering every token -- and adds x * dw straight into C, WHILE the main loop runs.
+      const bool atomic_corr = P.o_ptr != nullptr && (P.ksplit > 1 || P.fold_m) && !P.accumulate;
+      if (atomic_corr) {
+        if (P.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");       // C has been zero-filled from here on
+        const int klo = kb0 * XBK, khi = (kb0 + nkb) * XBK;
+        const int kblk32 = P.K >> 5;
+        uint32_t have = __ballot_sync(0xffffffffu, oe1 > oe0);
+        while (have) {
+          const int L = __ffs(have) - 1;
+          have &= have - 1;
+          const int b0 = __shfl_sync(0xffffffffu, oe0, L), b1 = __shfl_sync(0xffffffffu, oe1, L);
+          float* ccol = P.C + (tn * XM + q * 32 + L);
+          for (int eb = b0; eb < b1; eb += 32) {
+            // this batch's (k, dw) pairs: one coalesced load, then broadcast by shuffles
+            int kk = -1; float dd = 0.0f;
+            if (eb + lane < b1) { kk = __ldg(P.o_k + eb + lane); dd = __ldg(P.o_dw + eb + lane); }
+            if (kk < klo || kk >= khi) kk = -1;                       // another K slice's outlier
+            uint32_t todo = __ballot_sync(0xffffffffu, kk >= 0);
+            while (todo) {
+              // up to four outliers in flight: all gathers are issued before the first atomic
+              int ks[4]; float ds[4]; uint32_t cb[4]; int xb[4];
+              int cnt = 0;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                ks[u] = -1; ds[u] = 0.0f;
+                if (todo) {
+                  const int j = __ffs(todo) - 1;
+                  todo &= todo - 1;
+                  ks[u] = __shfl_sync(0xffffffffu, kk, j); ds[u] = __shfl_sync(0xffffffffu, dd, j);
+                  ++cnt;
+                }
+              }
+              for (int v = lane; v < P.bnx; v += 32) {
+                const int m = tm * P.bnx + v;
+                const long long mc = min(m, P.M - 1);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int k = max(ks[u], 0);
+                  cb[u] = __ldg(P.xcodes + mc * P.ldx + k);
+                  xb[u] = __ldg(P.xe + mc * kblk32 + (k >> 5));
+                }
+                if (m < P.M) {
+                  float* p = ccol + (long long)(P.fold_m ? m % P.fold_m : m) * P.ldc;
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    if (u < cnt) {
+                      const float xs = xb[u] == MSQ_EXP_NAN ? qnan() : pow2i(xb[u]);
+                      atomicAdd(p, __fmul_rn(__fmul_rn(decode_elem(cb[u], 4, 5), xs), ds[u]));
+                    }
+                  }
+                }
+              }
+            }
+          }
+        }
+        oe1 = oe0;                         // nothing left for the accumulator-side corrections below
+      }
+      const bool pre_corr = P.bnx <= CORR_MAX && !atomic_corr;
       if (pre_corr) {
 #pragma unroll
         for (int v = 0; v < CORR_MAX; ++v) corr[v] = 0.0f;
@@ -458,10 +519,10 @@ __global__ void __launch_bounds__(512, 1) k_gemm_mx8(const __grid_constant__ CUt
           for (int v = 0; v < 16; ++v) {
             const int m = tm * P.bnx + c * 16 + v;
             if (m < P.M) {
-              float* p = P.C + (long long)m * P.ldc + n;
+              float* p = P.C + (long long)(P.fold_m ? m % P.fold_m : m) * P.ldc + n;
               float val = __uint_as_float(r[v]);
               if (pre_corr) val += (c == 0 ? corr[v] : corr[16 + v]);
-              if (P.ksplit > 1) atomicAdd(p, val);
+              if (P.ksplit > 1 || P.fold_m) atomicAdd(p, val);
               else *p = P.accumulate ? (*p + val) : val;
             }
           }
@@ -570,7 +631,7 @@ struct Mx4Sparse { const int* o_ptr; const int* o_k; const float* o_dw; const un
 static int launch_mx8(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* wcodes,
                       const unsigned int* wbitmap, const signed char* we_in, const signed char* we_out,
                       const unsigned char* wdense, long long ldw, const unsigned char* wsf, float* C, long long ldc, int M,
-                      int N, int K, int plain, int accumulate, cudaStream_t s, const Mx4Sparse* fp4 = nullptr) {
+                      int N, int K, int plain, int accumulate, cudaStream_t s, const Mx4Sparse* fp4 = nullptr, int fold_m = 0) {
   Mx8Params P;
   memset(&P, 0, sizeof(P));
   P.w_tx_bytes = wdense ? XA_BYTES : 0;
@@ -616,16 +677,18 @@ static int launch_mx8(const unsigned char* xcodes, long long ldx, const signed c
     const long long ring = (long long)P.nst * (XA_BYTES + P.xb_bytes + XSF_BYTES);
     P.sfb_pre = (P.wtiled && bnx <= 128 && one_tile && (long long)P.kb_per_split * 512 <= (long long)MX8_SMEM - 1024 - 256 - ring) ? 1 : 0;
   }
-  if (ksplit > 1 && !accumulate) {
+  P.fold_m = fold_m;
+  const int M_out = fold_m ? fold_m : M;
+  if ((ksplit > 1 || fold_m) && !accumulate) {
     const bool no_pdl = getenv("MSQ_MX8_NO_PDL") != nullptr;
     if (!no_pdl && (N % 4) == 0 && (ldc % 4) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
-      const long long n4 = (long long)M * (N >> 2);
+      const long long n4 = (long long)M_out * (N >> 2);
       int zb = (int)((n4 + 255) / 256);
       if (zb > 4 * sms) zb = 4 * sms;
-      k_zero_c<<<zb, 256, 0, s>>>(C, ldc, M, N);
+      k_zero_c<<<zb, 256, 0, s>>>(C, ldc, M_out, N);
       P.pdl = 1;
-    } else if (ldc == N) cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s);
-    else cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s);
+    } else if (ldc == N) cudaMemsetAsync(C, 0, (size_t)M_out * N * sizeof(float), s);
+    else cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M_out, s);
   }
   CUtensorMap tmX, tmW;
   int rc = make_tmap_2d(&tmX, xcodes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K, ldx, bnx, XBK);
@@ -747,6 +810,24 @@ int msq_gemm_mxfp4w_tiled_blockscaled(const unsigned char* xcodes, long long ldx
   Mx4Sparse sp{o_ptr, o_k, o_dw, codes_tiled, sf_tiled};
   return launch_mx8(xcodes, ldx, xe, codes_tiled, nullptr, reinterpret_cast<const signed char*>(sf_tiled), nullptr, nullptr, 0,
                     nullptr, C, ldc, M, N, K, 1, accumulate, (cudaStream_t)stream, &sp);
+}
+
+// the same GEMM over STACKED activation terms (msq_split_a16_e4m3: M = terms * fold_m rows): the slabs are summed into
+// C [fold_m, N] by the epilogue's atomics instead of by a pass over a [M, N] result
+int msq_gemm_mxfp4w_tiled_folded(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* codes_tiled,
+                                 const unsigned char* sf_tiled, const int* o_ptr, const int* o_k, const float* o_dw, float* C,
+                                 long long ldc, int M, int fold_m, int N, int K, void* stream) {
+  msq::DevGuard dev_guard_(xcodes);
+  if (!xcodes || !xe || !codes_tiled || !sf_tiled || !C || M <= 0 || N <= 0 || K <= 0) return MSQ_ERR_BAD_ARG;
+  if (fold_m <= 0 || M % fold_m != 0) return MSQ_ERR_BAD_ARG;
+  if (o_ptr && (!o_k || !o_dw)) return MSQ_ERR_BAD_ARG;
+  if (K % 128 != 0) return MSQ_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(xe) & 3) || (reinterpret_cast<uintptr_t>(xcodes) & 15) || (ldx % 16) ||
+      (reinterpret_cast<uintptr_t>(codes_tiled) & 31) || (reinterpret_cast<uintptr_t>(sf_tiled) & 15))
+    return MSQ_ERR_ALIGN;
+  Mx4Sparse sp{o_ptr, o_k, o_dw, codes_tiled, sf_tiled};
+  return launch_mx8(xcodes, ldx, xe, codes_tiled, nullptr, reinterpret_cast<const signed char*>(sf_tiled), nullptr, nullptr, 0,
+                    nullptr, C, ldc, M, N, K, 1, 0, (cudaStream_t)stream, &sp, fold_m == M ? 0 : fold_m);
 }
 
 }  // extern "C"

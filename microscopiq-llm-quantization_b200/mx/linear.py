@@ -44,6 +44,17 @@ def _mx8_activation_ok(x, mx_specs):
             and x.shape[1] // 32 >= 2 and _get_format_params(a)[:2] == (4, 5) and x.dtype == torch.float32)
 
 
+def _bf16_exact_activations(mx_specs):
+    """are the (fake-quantized) activations exactly representable in bfloat16?  MX element formats with at most 8
+    significant bits times a power of two are (fp32 subnormals aside); unquantized activations are when the spec rounds
+    them to bfloat16 first (quantize_elemwise_op, number_system/mx/linear.py:57)."""
+    from .formats import _get_format_params
+    a = mx_specs["a_elem_format"]
+    if a is None:
+        return mx_specs["bfloat"] == 16
+    return _get_format_params(a)[1] - 1 <= 8
+
+
 def linear_forward(input, weight, bias, mx_specs, packed_weight=None):
     bf_in = quantize_elemwise_op(input, mx_specs=mx_specs, round=mx_specs["round_output"])
     bf_bias = None
@@ -67,7 +78,12 @@ def linear_forward(input, weight, bias, mx_specs, packed_weight=None):
             if not bool((xq.bitmap != 0).any()):
                 output = _tc.packed_linear_mx8(xq, packed_weight).to(input.dtype)
         if output is None:
-            output = _tc.packed_linear(qis_input, packed_weight).to(input.dtype)
+            xg = qis_input
+            if xg.dtype == torch.float32 and _bf16_exact_activations(mx_specs):
+                # every value is q * 2^e with <= 8 significant bits (or already rounded to bfloat16): the bf16 cast is
+                # exact, one GEMM pass instead of three bf16 terms, and the W4A16 block-scaled path applies
+                xg = xg.to(torch.bfloat16)
+            output = _tc.packed_linear(xg, packed_weight).to(input.dtype)
     else:
         # not packable (block size other than 32, ragged K, w_elem_format None, ...): linear.py:78-91 on the
         # dequantized operands -- fake-quantize the weight, then the dense tcgen05 contraction

@@ -73,37 +73,45 @@ def test_mx_linear_matches_reference_fixtures(M):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
-def test_split_a16_terms_reproduce_the_activations(M, dt):
-    """msq_split_a16_e4m3x3: sum_t a_t * 2^e_t == x EXACTLY while an element is within 2^15 (bf16) / 2^11 (fp16) of its
-    block's maximum; below that the truncation error is < 2^-22 of the block maximum.  Inf / NaN poison their block."""
+@pytest.mark.parametrize("dt,T", [(torch.bfloat16, 2), (torch.bfloat16, 3), (torch.float16, 3)])
+def test_split_a16_terms_reproduce_the_activations(M, dt, T):
+    """msq_split_a16_e4m3: sum_t a_t * 2^e_t == x EXACTLY while an element is within 2^12 (bf16, two terms) / 2^15 (bf16,
+    three) / 2^11 (fp16, three) of its block's maximum; below that the truncation error is < 2^-19 / 2^-22 of the block
+    maximum and never increases a magnitude.  Inf / NaN poison their block."""
     from msq_b200 import _tc
     g = torch.Generator().manual_seed(3)
     Mx, K = 37, 512
-    spread = 15 if dt == torch.bfloat16 else 11
+    spread = {(torch.bfloat16, 2): 12, (torch.bfloat16, 3): 15, (torch.float16, 3): 11}[(dt, T)]
+    floor = 2.0 ** -19 if T == 2 else 2.0 ** -22
     x = torch.randn(Mx, K, generator=g) * torch.exp2(torch.randint(-spread // 2, spread // 2 + 1, (Mx, K), generator=g).float())
     x[0, :32] = 0.0                                        # an all-zero block
     x[1, 5] = 0.0
     x = x.to(dt)
     x[2, 40:48] = torch.tensor([2.0 ** -i for i in range(8)], dtype=dt) * x[2, 40:48].abs().max() + 0    # exact powers of two
-    sa = _tc.split_a16(x.cuda())
-    terms = sa.codes.view(torch.float8_e4m3fn).float().view(3, Mx, K // 32, 32) * torch.exp2(sa.e_in.float()).view(3, Mx, K // 32, 1)
-    rec = terms.sum(0).view(Mx, K)
+
+    def rebuild(t):
+        sa = _tc.split_a16(t.cuda(), terms=T)
+        r, c = t.shape
+        assert sa.shape == (T * r, c) and sa.terms == T
+        terms = sa.codes.view(torch.float8_e4m3fn).float().view(T, r, c // 32, 32) * torch.exp2(sa.e_in.float()).view(T, r, c // 32, 1)
+        return terms.sum(0).view(r, c), sa
+
+    rec, _ = rebuild(x)
     xf = x.float().cuda()
     blockmax = xf.abs().view(Mx, K // 32, 32).amax(-1, keepdim=True).expand(Mx, K // 32, 32).reshape(Mx, K)
     near = xf.abs() * 2.0 ** spread >= blockmax
     assert torch.equal(rec[near], xf[near])
-    assert bool(((rec - xf).abs() <= blockmax * 2.0 ** -22).all())
-    # wide dynamic range inside a block: truncation at 2^-22 of the block maximum, never more
-    y = (torch.randn(8, 256, generator=g) * torch.exp2(torch.randint(-30, 1, (8, 256), generator=g).float())).to(dt).cuda()
-    sb = _tc.split_a16(y)
-    rec = (sb.codes.view(torch.float8_e4m3fn).float().view(3, 8, 8, 32) * torch.exp2(sb.e_in.float()).view(3, 8, 8, 1)).sum(0).view(8, 256)
-    bm = y.float().abs().view(8, 8, 32).amax(-1, keepdim=True).expand(8, 8, 32).reshape(8, 256)
-    assert bool(((rec - y.float()).abs() <= bm * 2.0 ** -22).all()) and bool((rec.abs() <= y.float().abs()).all())
-    z = torch.ones(2, 64, dtype=dt).cuda()
+    assert bool(((rec - xf).abs() <= blockmax * floor).all())
+    # wide dynamic range inside a block: truncation at `floor` of the block maximum, never more, never away from zero
+    y = (torch.randn(8, 256, generator=g) * torch.exp2(torch.randint(-30, 1, (8, 256), generator=g).float())).to(dt)
+    rec, _ = rebuild(y)
+    yf = y.float().cuda()
+    bm = yf.abs().view(8, 8, 32).amax(-1, keepdim=True).expand(8, 8, 32).reshape(8, 256)
+    assert bool(((rec - yf).abs() <= bm * floor).all()) and bool((rec.abs() <= yf.abs()).all())
+    z = torch.ones(2, 64, dtype=dt)
     z[1, 3] = float("inf")
-    sz = _tc.split_a16(z)
-    assert int(sz.e_in[1, 0]) == -128 and int(sz.e_in[3, 0]) == -128 and int(sz.e_in[5, 0]) == -128 and int(sz.e_in[1, 1]) != -128
+    _, sz = rebuild(z)
+    assert all(int(sz.e_in[t * 2 + 1, 0]) == -128 for t in range(T)) and int(sz.e_in[1, 1]) != -128
 
 
 @pytest.mark.timeout(300)
