@@ -318,6 +318,11 @@ int msq_gemm_mxfp8_dense(const unsigned char* xcodes, long long ldx, const signe
  *     o_ptr / o_k / o_dw (may be NULL): CSR of the outlier corrections of an FP4 weight, as in
  *     msq_gemm_mxfp4w_blockscaled, applied by the epilogue warps to the accumulator tile they hold in registers.
  *     K % 128 == 0; w 32-byte aligned.  msq_gemm_mxfp8_tma_tile_tokens reports the token-tile width it will use. */
+/* the sparse part as a pass of its own (every SM works on it): C[m (mod fold_m if > 0), o_n[e]] += dq(x)[m, o_k[e]] * o_dw[e]
+ * for every outlier e (COO triplets) and token m, by atomics, behind a GEMM that ran on the packed codes alone. */
+int msq_sparse_outlier_correct(const unsigned char* xcodes, long long ldx, const signed char* xe, const int* o_n,
+                               const int* o_k, const float* o_dw, int nnz, float* C, long long ldc, int M, int K,
+                               int fold_m, void* stream);
 int msq_tile_scales_ue8m0(const void* scales, int is_int8_exponent, int rows, int K, int rows_per_tile,
                           unsigned char* out, void* stream);
 int msq_gemm_mxfp8_tma_tile_tokens(int M, int N, int K);

@@ -415,6 +415,7 @@ def mx4_sparse_outliers(pw):
         if idx.numel():
             o_ptr[1:] = torch.cumsum(torch.bincount(idx[:, 0], minlength=Nn), 0).to(torch.int32)
         sp = (o_ptr, idx[:, 1].to(torch.int32).contiguous(), dw.float())
+        pw._mx4_sparse_rows = idx[:, 0].to(torch.int32).contiguous()
         if not idx.numel():
             sp = (None, None, None)
     pw._mx4_sparse = sp
@@ -434,6 +435,7 @@ def widen_weight_mx8(pw):
     return wb, wsf
 
 
+N.register("msq_sparse_outlier_correct", _i, [_p, _ll, _p, _p, _p, _p, _i, _p, _ll, _i, _i, _i, _p])
 N.register("msq_tile_scales_ue8m0", _i, [_p, _i, _i, _i, _i, _p, _p])
 N.register("msq_gemm_mxfp8_tma_tile_tokens", _i, [_i, _i, _i])
 N.register("msq_gemm_mxfp8_tma_workspace_bytes", _ll, [_i, _i, _i])
@@ -458,14 +460,16 @@ def tile_scales(scales, rows_per_tile=128):
     return out
 
 
-#: a weight WITH outliers still feeds its packed codes to the TMA-fed kernel, the outliers being the fused sparse epilogue
-#: correction, while it has at most this many outliers per output feature on average.  The correction is a gather of
-#: activation bytes by the four epilogue warps whose latency is exposed once per (outlier, 16 tokens): measured at 8192^2,
-#: 0.85 outliers per row: M = 64: 16.4 -> 26.9 us (producer-widen kernel 51.7), M = 4096: 241 -> 658 us (widened copy 245);
-#: so below the compute-bound sizes up to one per row, at them only a weight without outliers (or one whose exponents
-#: the E4M3 folding cannot represent); denser weights use the widened E4M3 copy / the producer-widen kernel
-MX8_TMA_SPARSE_MAX_PER_ROW = 1.0
-MX8_TMA_SPARSE_MAX_PER_ROW_LARGE_M = 0.0
+#: a weight WITH outliers still feeds its packed codes to the TMA-fed kernel; the outliers are a sparse correction
+#: C[m, n_e] += x[m, k_e] * dw_e applied by a pass of its own behind the GEMM (msq_sparse_outlier_correct: one thread per
+#: (outlier, token), every SM works on it) while outliers x tokens stays below this budget; beyond it the widened E4M3
+#: copy (compute-bound sizes) or the producer-widen kernel.  MX8_TMA_FUSED_SPARSE = True applies the correction inside the
+#: GEMM's epilogue instead (four warps per CTA gather: latency-bound, measured 8192^2, 0.85 outliers per row, M = 256:
+#: 63.8 us against 22.4 us for the weight without outliers).
+MX8_TMA_SPARSE_BUDGET = 4.0e6
+MX8_TMA_SPARSE_BUDGET_LARGE_M = 2.5e5        # from MX8_DENSE_MIN_M rows the widened copy is the alternative: a few microseconds
+MX8_TMA_FUSED_SPARSE = False
+MX8_TMA_SPARSE_MAX_PER_ROW = 1.0            # used when the token count is not known to the caller
 
 
 def mx8_tma_weight(pw, allow_copy=True, sparse_limit=None):
@@ -486,7 +490,7 @@ def mx8_tma_weight(pw, allow_copy=True, sparse_limit=None):
         if nnz <= sparse_limit * Nn or not mx8_weight_ok(pw):
             return op                  # few outliers -- or no other kernel can take this weight's exponents
         if not allow_copy:
-            # below the compute-bound sizes no copy is made: the sparse epilogue up to 4x the limit, beyond that the
+            # below the compute-bound sizes no copy is made: the sparse correction up to 4x the budget, beyond that the
             # producer-widen kernel (whose cost does not depend on the number of outliers)
             return op if nnz <= 4 * sparse_limit * Nn else None
     dense = getattr(pw, "_mx8_dense", None)
@@ -522,17 +526,24 @@ def packed_linear_mx8(xq, pw, bias=None, cache_dense=False):
         # A plain FP4 weight feeds its packed codes; a weight with outliers its widened E4M3 copy -- built (and kept) only
         # in the compute-bound regime or on request, below that the producer-widen kernel reads the packed planes
         op = mx8_tma_weight(pw, allow_copy=cache_dense or dense is not None or M >= MX8_DENSE_MIN_M,
-                            sparse_limit=-1.0 if cache_dense else (MX8_TMA_SPARSE_MAX_PER_ROW_LARGE_M if M >= MX8_DENSE_MIN_M
-                                                                   else None))
+                            sparse_limit=-1.0 if cache_dense else
+                            (MX8_TMA_SPARSE_BUDGET if M < MX8_DENSE_MIN_M else MX8_TMA_SPARSE_BUDGET_LARGE_M) / (float(M) * Nn))
         if op is not None:
             out = torch.empty(M, Nn, dtype=torch.float32, device=pw.codes.device)
             w, ldw, is_fp4, wsf_t, o_ptr, o_k, o_dw = op
+            behind = o_ptr is not None and not MX8_TMA_FUSED_SPARSE
             nbytes = int(N.lib().msq_gemm_mxfp8_tma_workspace_bytes(M, Nn, K))
             ws = _workspace(nbytes, out.device)
             rc = N.lib().msq_gemm_mxfp8_tma(N.ptr(xq.codes), K, N.ptr(xq.e_in), N.ptr(w), ldw, is_fp4, N.ptr(wsf_t),
-                                            N.ptr(o_ptr), N.ptr(o_k), N.ptr(o_dw), N.ptr(out), out.stride(0), M, Nn, K, 0,
+                                            N.ptr(None if behind else o_ptr), N.ptr(None if behind else o_k),
+                                            N.ptr(None if behind else o_dw), N.ptr(out), out.stride(0), M, Nn, K, 0,
                                             N.ptr(ws), nbytes, N.stream_ptr(out.device))
             N.check(rc, "msq_gemm_mxfp8_tma")
+            if behind:
+                rc = N.lib().msq_sparse_outlier_correct(N.ptr(xq.codes), K, N.ptr(xq.e_in), N.ptr(pw._mx4_sparse_rows), N.ptr(o_k),
+                                                        N.ptr(o_dw), int(o_k.numel()), N.ptr(out), out.stride(0), M, K, 0,
+                                                        N.stream_ptr(out.device))
+                N.check(rc, "msq_sparse_outlier_correct")
             if bias is not None:
                 out += bias.float()
             return out.reshape(*xq.shape[:-1], Nn)

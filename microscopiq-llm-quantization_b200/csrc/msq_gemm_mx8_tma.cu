@@ -254,6 +254,25 @@ __global__ void __launch_bounds__(256) k_tile_scales(const uint8_t* __restrict__
   *reinterpret_cast<uint32_t*>(out + (((long long)tile * kblocks + kb) * chunks + (r >> 7)) * 512 + (rr & 31) * 16 + (rr >> 5) * 4) = w;
 }
 
+// sparse outlier correction as a pass of its own behind the GEMM (every SM works on it; inside the GEMM only the four
+// epilogue warps of a CTA can): one thread per (outlier, token), C[m, n_e] += x[m, k_e] * dw_e by atomics
+__global__ void __launch_bounds__(256) k_sparse_outlier_corr(const int* __restrict__ o_n, const int* __restrict__ o_k,
+                                                             const float* __restrict__ o_dw, int nnz, const uint8_t* __restrict__ xcodes,
+                                                             long long ldx, const int8_t* __restrict__ xe, int M, int K, float* C,
+                                                             long long ldc, int fold_m) {
+  // lanes = 32 consecutive outliers (sorted by feature: their atomics for one token fall into a few sectors of C's row),
+  // warps = 8 tokens
+  const int e = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int m = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (e >= nnz || m >= M) return;
+  const int k = __ldg(o_k + e), n = __ldg(o_n + e);
+  const float dw = __ldg(o_dw + e);
+  const int xb = __ldg(xe + (long long)m * (K >> 5) + (k >> 5));
+  const float xs = xb == MSQ_EXP_NAN ? qnan() : pow2i(xb);
+  const float xv = __fmul_rn(decode_elem((uint32_t)__ldg(xcodes + (long long)m * ldx + k), 4, 5), xs);
+  atomicAdd(C + (long long)(fold_m ? m % fold_m : m) * ldc + n, __fmul_rn(xv, dw));
+}
+
 // token-tile width: fewest (waves over the SMs) x (bytes a tile pulls into shared memory) -- the kernel is bound by the
 // L2 -> shared-memory fill, not by the tensor pipe; one accumulator (BN = 256) pays its exposed epilogue
 static void choose_bn(int M, int N, int K, int sms, int& bn, int& nacc) {
@@ -292,6 +311,21 @@ int msq_tile_scales_ue8m0(const void* scales, int is_int8_exponent, int rows, in
   dim3 grid((unsigned)(K / YBK), (unsigned)((rows + rows_per_tile - 1) / rows_per_tile));
   k_tile_scales<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(scales), is_int8_exponent ? 1 : 0, rows,
                                                         K / 32, rows_per_tile, chunks, K / YBK, out);
+  return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+}
+
+// C[m mod fold_m (fold_m = 0: m), o_n[e]] += dq(x)[m, o_k[e]] * o_dw[e] for every outlier e and token m: the sparse part of a
+// linear whose dense part ran on the packed codes (msq_gemm_mxfp8_tma without o_ptr); COO triplets, best sorted by feature
+int msq_sparse_outlier_correct(const unsigned char* xcodes, long long ldx, const signed char* xe, const int* o_n, const int* o_k,
+                               const float* o_dw, int nnz, float* C, long long ldc, int M, int K, int fold_m, void* stream) {
+  msq::DevGuard dev_guard_(xcodes);
+  if (!xcodes || !xe || !C || M <= 0 || K <= 0 || nnz < 0 || fold_m < 0) return MSQ_ERR_BAD_ARG;
+  if (nnz == 0) return MSQ_OK;
+  if (!o_n || !o_k || !o_dw) return MSQ_ERR_BAD_ARG;
+  dim3 grid((unsigned)((nnz + 31) / 32), (unsigned)((M + 7) / 8));
+  if (grid.y > 65535u) return MSQ_ERR_UNSUPPORTED;
+  k_sparse_outlier_corr<<<grid, 256, 0, (cudaStream_t)stream>>>(o_n, o_k, o_dw, nnz, xcodes, ldx, reinterpret_cast<const int8_t*>(xe),
+                                                                M, K, C, ldc, fold_m);
   return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
 }
 

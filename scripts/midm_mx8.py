@@ -34,11 +34,14 @@ for KN in (4096, 8192):
         _tc.MX8_TMA = True
         _tc.MX8_DENSE_MIN_M = 512
         t_new = tm(lambda: _tc.packed_linear_mx8(xq, pwp))
-        _tc.MX8_TMA_SPARSE_MAX_PER_ROW = _tc.MX8_TMA_SPARSE_MAX_PER_ROW_LARGE_M = 1e9
+        _tc.MX8_TMA_SPARSE_BUDGET = _tc.MX8_TMA_SPARSE_BUDGET_LARGE_M = 1e18
         t_sp = tm(lambda: _tc.packed_linear_mx8(xq, pwo))            # FP4 codes + sparse outlier epilogue (no copy)
         t_sp2 = tm(lambda: _tc.packed_linear_mx8(xq, pwo2))          # the same with ~1 outlier per row
+        _tc.MX8_TMA_FUSED_SPARSE = True
+        t_fu2 = tm(lambda: _tc.packed_linear_mx8(xq, pwo2))          # ... applied inside the GEMM's epilogue
+        _tc.MX8_TMA_FUSED_SPARSE = False
         assert getattr(pwo, "_mx8_dense", None) is None
         t_newo = tm(lambda: _tc.packed_linear_mx8(xq, pwo, cache_dense=True))
         pwo._mx8_dense = None
-        print("KN %d M %3d: cuBLAS bf16 %.1f us | producer-widen plain %.1f outl %.1f | TMA-fed (bn %d) FP4 codes %.1f, + sparse outliers (%.3f / row) %.1f (%.2f / row) %.1f, E4M3 copy %.1f" % (
-            KN, M, t_c, t_old, t_oldo, _tc.N.lib().msq_gemm_mxfp8_tma_tile_tokens(M, KN, KN), t_new, float(pwo.outlier_mask().sum()) / KN, t_sp, float(pwo2.outlier_mask().sum()) / KN, t_sp2, t_newo), flush=True)
+        print("KN %d M %3d: cuBLAS bf16 %.1f us | producer-widen plain %.1f outl %.1f | TMA-fed (bn %d) FP4 codes %.1f, + sparse outliers (%.3f / row) %.1f (%.2f / row) %.1f [fused in the epilogue: %.1f], E4M3 copy %.1f" % (
+            KN, M, t_c, t_old, t_oldo, _tc.N.lib().msq_gemm_mxfp8_tma_tile_tokens(M, KN, KN), t_new, float(pwo.outlier_mask().sum()) / KN, t_sp, float(pwo2.outlier_mask().sum()) / KN, t_sp2, t_fu2, t_newo), flush=True)
