@@ -232,6 +232,53 @@ def split_a16(x2, terms=None):
     return sa
 
 
+#: the quantizers' own artefact (row blocks, FP8 outliers in a hi stream) below FUSED_MAX_M rows: re-encode the weight
+#: ONCE, exactly, as K-blocked MX-FP8 (E4M3 bytes + UE8M0 scales, 1.03 B/weight next to the artefact's 0.94) and run the
+#: block-scaled kernels on it, instead of the producer-bound row-block kernel
+ROWBLOCK_VIA_MXFP8 = True
+
+
+def rowblock_mxfp8_operand(pw):
+    """exact K-blocked MX-FP8 form of ANY packed weight [N, K] (K % 32 == 0): (E4M3 bytes [N, K], UE8M0 scales [N, K/32]) with
+    bytes * 2^(scale - 127) (+ pw._mx8_dense_resid: COO remainders of the few elements that are more than ~14 binades
+    below their block's maximum) == pw.dequantize() bit for bit, or None when more than max(64, N) elements are not
+    representable.  Built once (one device-to-host read for the exactness check), kept on the PackedMX as the operand of
+    the block-scaled GEMMs."""
+    hit = getattr(pw, "_mx8_dense", None)
+    if hit is not None:
+        return hit
+    if getattr(pw, "_mx8_dense_failed", False):
+        return None
+    Nn, K = pw.shape
+    if K % 32:
+        return None
+    w = pw.dequantize()                                              # fp32, exact values of the artefact
+    blk = w.view(Nn, K // 32, 32)
+    amax = blk.abs().amax(-1, keepdim=True)
+    # exponent of the block maximum from its bits (frexp) and exact powers of two from bit patterns: the device log2 / exp2
+    # are not exact at the integers.  The block maximum lands in [2^7, 2^8).
+    e = (torch.frexp(amax.clamp_min(2.0 ** -100))[1] - 1 - 7).clamp_(-126, 120).to(torch.int32)
+    p2 = lambda t: ((t + 127) << 23).view(torch.float32)
+    q8 = (blk * p2(-e)).to(torch.float8_e4m3fn)
+    back = q8.float() * p2(e)
+    bad = (back != blk).view(Nn, K)
+    nbad = int(bad.sum())                                            # the one device-to-host read
+    if nbad > max(64, Nn):
+        pw._mx8_dense_failed = True
+        return None
+    pw._mx8_dense_resid = None
+    if nbad:
+        # a handful of elements far below their block's maximum (measured: 7 of 16.7 M on a 4096^2 Gaussian weight, FP8
+        # outliers ~2^18 under the block maximum): their remainders ride along as a sparse correction
+        idx = bad.nonzero()
+        dw = (w - back.view(Nn, K))[bad].contiguous()
+        pw._mx8_dense_resid = (idx[:, 0].to(torch.int32).contiguous(), idx[:, 1].to(torch.int32).contiguous(), dw)
+    wb = q8.view(torch.uint8).reshape(Nn, K).contiguous()
+    wsf = (e + 127).to(torch.uint8).reshape(Nn, K // 32).contiguous()
+    pw._mx8_dense = (wb, wsf)
+    return pw._mx8_dense
+
+
 def packed_linear(x, pw, bias=None):
     """y[..., N] (fp32) = x[..., K] @ dequant(pw)[N, K].T (+ bias) with pw a PackedMX blocked along K
     (block 32).  bf16 activations take one pass; fp16 / fp32 activations are split into exact bf16
@@ -245,7 +292,20 @@ def packed_linear(x, pw, bias=None):
         lead = x.shape[:-1]
         x2 = x.reshape(-1, K)
         out = torch.empty(x2.shape[0], (Nn + 3) // 4 * 4, dtype=torch.float32, device=x.device)[:, :Nn]
-        if rowblock_ok(pw) and x2.shape[0] < FUSED_MAX_M:
+        M = x2.shape[0]
+        if (ROWBLOCK_VIA_MXFP8 and SPLIT_A16 and x2.dtype in SPLIT_A16_TERMS and M < FUSED_MAX_M and K % 128 == 0 and Nn % 4 == 0
+                and rowblock_mxfp8_operand(pw) is not None):
+            # 16-bit activations as block-scaled E4M3 terms x the exact MX-FP8 form of the artefact: block-scaled kernels
+            sa = split_a16(x2)
+            y3 = packed_linear_mx8(sa, pw)
+            if pw._mx8_dense_resid is not None:
+                rn, rk, rdw = pw._mx8_dense_resid
+                rc = N.lib().msq_sparse_outlier_correct(N.ptr(sa.codes), K, N.ptr(sa.e_in), N.ptr(rn), N.ptr(rk), N.ptr(rdw),
+                                                        int(rk.numel()), N.ptr(y3), y3.stride(0), sa.shape[0], K, 0,
+                                                        N.stream_ptr(y3.device))
+                N.check(rc, "msq_sparse_outlier_correct")
+            out = y3.view(sa.terms, M, Nn).sum(0)
+        elif rowblock_ok(pw) and x2.shape[0] < FUSED_MAX_M:
             _packed_linear_rowblock(x2, pw, out)
         else:
             wb = getattr(pw, "_dense_bf16", None)
@@ -564,7 +624,7 @@ def packed_linear_mx8(xq, pw, bias=None, cache_dense=False):
         if bias is not None:
             out += bias.float()
         return out.reshape(*xq.shape[:-1], Nn)
-    if not mx8_weight_ok(pw):
+    if dense is None and not mx8_weight_ok(pw):
         raise NotImplementedError("weight is not eligible for the block-scaled FP8 path")
     out = torch.empty(M, Nn, dtype=torch.float32, device=pw.codes.device)
     if K % 128 == 0 and (dense is not None or cache_dense or M >= MX8_DENSE_MIN_M):

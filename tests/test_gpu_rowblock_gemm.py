@@ -46,10 +46,23 @@ def test_hi_index_matches_the_bitmap(M, N, K, fi, fo, bs):
                                           (1024, 4096, "fp4_e2m1", "fp8_e4m3", 16), (4096, 1024, "int2", "fp4", 16),
                                           (512, 512, "fp4_e2m1", "fp4_e2m1", 32), (384, 640, "fp4_e2m1", "fp8_e4m3", 32)])
 @pytest.mark.parametrize("Mx", [1, 16, 100, 300])
-def test_rowblock_gemm_against_dequantized_weight(M, N, K, fi, fo, bs, Mx):
+@pytest.mark.parametrize("via_mxfp8", [False, True])
+def test_rowblock_gemm_against_dequantized_weight(M, monkeypatch, N, K, fi, fo, bs, Mx, via_mxfp8):
+    """via_mxfp8: the artefact re-encoded once, exactly, as K-blocked MX-FP8 and run on the block-scaled kernels with the
+    bf16 activations as two block-scaled E4M3 terms (K % 128 == 0); else the row-block kernel (k_gemm_rb)"""
     from msq_b200 import _tc
+    monkeypatch.setattr(_tc, "ROWBLOCK_VIA_MXFP8", via_mxfp8)
     pw = M.pack_mx_outlier(weights(N, K, N * 3 + K).cuda(), 8, 8, fi, fo, 2, [0], bs)
     assert _tc.rowblock_ok(pw)
+    if via_mxfp8 and K % 128 == 0:
+        op = _tc.rowblock_mxfp8_operand(pw)
+        assert op is not None                                     # exact by construction (checked inside), and it is:
+        wb, wsf = op
+        w8 = (wb.cpu().view(torch.float8_e4m3fn).float().view(N, K // 32, 32) * torch.exp2(wsf.cpu().float() - 127).view(N, K // 32, 1)).view(N, K)
+        if pw._mx8_dense_resid is not None:                       # elements far below their block's maximum: exact remainders
+            rn, rk, rdw = (t.cpu() for t in pw._mx8_dense_resid)
+            w8[rn.long(), rk.long()] += rdw
+        assert torch.equal(w8, pw.dequantize().cpu())
     g = torch.Generator().manual_seed(Mx)
     x = torch.randn(Mx, K, generator=g).to(torch.bfloat16).cuda()
     y = _tc.packed_linear(x, pw).double().cpu()
@@ -57,6 +70,23 @@ def test_rowblock_gemm_against_dequantized_weight(M, N, K, fi, fo, bs, Mx):
     ref = x.double().cpu() @ Wd.t()
     bound = 4 * K * 2.0 ** -24 * (x.double().cpu().abs() @ Wd.abs().t()) + 1e-30
     assert bool(((y - ref).abs() <= bound).all()), float(((y - ref).abs() / bound).max())
+    assert (getattr(pw, "_mx8_dense", None) is not None) == (via_mxfp8 and K % 128 == 0)
+
+
+def test_rowblock_weight_without_an_exact_mxfp8_form_keeps_the_rowblock_kernel(M):
+    """a 32-block along K whose elements span more binades than E4M3 holds has no exact MX-FP8 form: the conversion
+    reports it (once) and packed_linear stays on the row-block kernel"""
+    from msq_b200 import _tc
+    W = weights(256, 256, 4)
+    W[:, 7::32] *= 2.0 ** 30                                         # every block holds a column 30 binades above its neighbours
+    pw = M.pack_mx_outlier(W.cuda(), 8, 8, "fp4_e2m1", "fp8_e4m3", 2, [0], 16)
+    assert _tc.rowblock_mxfp8_operand(pw) is None and pw._mx8_dense_failed
+    x = torch.randn(8, 256).to(torch.bfloat16).cuda()
+    y = _tc.packed_linear(x, pw).double().cpu()
+    Wd = pw.dequantize().double().cpu()
+    ref = x.double().cpu() @ Wd.t()
+    bound = 4 * 256 * 2.0 ** -24 * (x.double().cpu().abs() @ Wd.abs().t()) + 1e-30
+    assert bool(((y - ref).abs() <= bound).all())
 
 
 def test_rowblock_gemm_other_dtypes_large_m_and_fallback(M):
