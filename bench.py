@@ -269,6 +269,20 @@ def extras(dev, dev_w, nel):
         ms = (_time_ms_device if M <= 256 else _time_ms)(lambda: _tc.packed_linear(x, pw), 10)
         gemm["M%d" % M] = {"ms": ms, "TFLOPs": 2.0 * M * 4096 * 4096 / (ms * 1e-3) / 1e12}
     out["packed_gemm_k4096_n4096"] = gemm
+    # (3b) the artefact the quantizers / GPTQ emit (row blocks of 16 along the output features, FP4 inliers / FP8 outliers,
+    # hi stream), bf16 activations: its exact K-blocked MX-FP8 form on the block-scaled kernels vs the row-block kernel
+    rb = {}
+    pwr = msq_b200.pack_mx_outlier(W, 8, 8, QCFG["in_fmt"], QCFG["out_fmt"], QCFG["std_dev"], [0], QCFG["bs"])
+    rb["exact_mxfp8_form"] = _tc.rowblock_mxfp8_operand(pwr) is not None
+    for M in (16, 256):
+        x = torch.randn(M, 4096, device=dev).to(torch.bfloat16)
+        ms = _time_ms_device(lambda: _tc.packed_linear(x, pwr), 10)
+        _tc.ROWBLOCK_VIA_MXFP8 = False
+        ms_rb = _time_ms_device(lambda: _tc.packed_linear(x, pwr), 10)
+        _tc.ROWBLOCK_VIA_MXFP8 = True
+        rb["M%d" % M] = {"ms": ms, "TFLOPs": 2.0 * M * 4096 * 4096 / (ms * 1e-3) / 1e12, "rowblock_kernel_ms": ms_rb}
+    del pwr
+    out["quantizer_artefact_gemm_k4096_n4096"] = rb
     # (4) same weight on the native block-scaled path (tcgen05 kind::mxf8f6f4), MX-FP8 activations
     mx8 = {}
     if _tc.mx8_weight_ok(pw):
