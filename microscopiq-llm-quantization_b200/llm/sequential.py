@@ -220,7 +220,7 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
     qcfg = dict(REFERENCE_QCFG if qcfg is None else qcfg)
     layers, _, _, _ = decoder_parts(model)
     stats = stats if stats is not None else {}
-    stats.update(hessian_s=0.0, solve_s=0.0, forward_s=0.0, comm_s=0.0, move_s=0.0, linears=0, comm_bytes=0)
+    stats.update(hessian_s=0.0, solve_s=0.0, forward_s=0.0, comm_s=0.0, move_s=0.0, capture_s=0.0, linears=0, comm_bytes=0)
     quantizers = {}
     world, rank = 1, 0
     if D.is_dist():
@@ -271,8 +271,11 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
         mover.finish()
         return quantizers
 
+    t0 = time.perf_counter()
     inps, args, kwargs = capture_layer_inputs(model, batches, dev)
     outs = torch.zeros_like(inps)
+    torch.cuda.synchronize()
+    stats["capture_s"] = stats.get("capture_s", 0.0) + time.perf_counter() - t0      # once per model, not per layer
     nsamples = inps.shape[0]
     for i in range(len(layers)):
         t0 = time.perf_counter()
