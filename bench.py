@@ -195,10 +195,14 @@ def extras(dev, dev_w, nel):
                 N.ptr(pl["e_out"]), N.ptr(pl["bitmap"]), N.ptr(pl["hi"]), N.ptr(pl["seg_cnt"]), None, None, N.ptr(st),
                 C.byref(path), N.stream_ptr(dev))
             assert rc == 0
-    ms = _time_ms(pack_all, 30, warm=10)      # the leg follows the PCIe-bound e2e phase: let the clocks come back up first
+    ms_host = _time_ms(pack_all, 30, warm=10)      # the leg follows the PCIe-bound e2e phase: let the clocks come back up first
+    # seven launches of 40-120 us each behind ~15 us of Python + ctypes per call: device time from CUDA-graph replays
+    # (the event-timed number with the Python launches in the loop is kept beside it)
+    ms = _time_ms_device(pack_all, 10, 5)
     bpe = pbytes / nel
     out["pack"] = {"GBps": nel * (4 + bpe) / (ms * 1e-3) / 1e9, "ms_per_layer": ms, "packed_bytes_per_elem": bpe,
-                   "frac_of_hbm_peak": nel * (4 + bpe) / (ms * 1e-3) / 1e9 / peaks()[0]}
+                   "frac_of_hbm_peak": nel * (4 + bpe) / (ms * 1e-3) / 1e9 / peaks()[0],
+                   "ms_per_layer_with_python_launches": ms_host, "timing": "CUDA-graph replays of the seven launches"}
     del calls
     # (2) GPTQ: Hessians over 128 x 2048 synthetic fp16 tokens + fasterquant for the 7 linears of one layer, the way the
     #     driver runs them: linears fed by the same activations (q/k/v, gate/up) share ONE Hessian and ONE factorization
