@@ -317,6 +317,10 @@ int msq_gemm_mxfp8_dense(const unsigned char* xcodes, long long ldx, const signe
  *     [M, K/32], tiled into `workspace` (msq_gemm_mxfp8_tma_workspace_bytes) by a launch in front of the GEMM.
  *     o_ptr / o_k / o_dw (may be NULL): CSR of the outlier corrections of an FP4 weight, as in
  *     msq_gemm_mxfp4w_blockscaled, applied by the epilogue warps to the accumulator tile they hold in registers.
+ *     terms (1..3): the activations are `terms` stacked slabs of M rows (msq_split_a16_e4m3: row t * M + m) whose
+ *     products are ACCUMULATED into C [M, N] -- the K loop runs over (term, K block) -- so a W4A16 linear needs neither a
+ *     [terms * M, N] result nor a pass that adds its slabs (o_ptr must be NULL then: msq_sparse_outlier_correct with
+ *     fold_m = M applies the corrections).
  *     K % 128 == 0; w 32-byte aligned.  msq_gemm_mxfp8_tma_tile_tokens reports the token-tile width it will use. */
 /* the sparse part as a pass of its own (every SM works on it): C[m (mod fold_m if > 0), o_n[e]] += dq(x)[m, o_k[e]] * o_dw[e]
  * for every outlier e (COO triplets) and token m, by atomics, behind a GEMM that ran on the packed codes alone. */
@@ -329,7 +333,7 @@ int msq_gemm_mxfp8_tma_tile_tokens(int M, int N, int K);
 long long msq_gemm_mxfp8_tma_workspace_bytes(int M, int N, int K);
 int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* w,
                        long long ldw, int w_is_fp4, const unsigned char* wsf_tiled, const int* o_ptr, const int* o_k,
-                       const float* o_dw, float* C, long long ldc, int M, int N, int K, int accumulate,
+                       const float* o_dw, float* C, long long ldc, int M, int N, int K, int terms, int accumulate,
                        void* workspace, long long workspace_bytes, void* stream);
 
 /* W4A16 on the block-scaled tensor-core path: 16-bit activations as a sum of T = 2 or 3 block-scaled E4M3 terms

@@ -215,6 +215,8 @@ class _SplitActs(object):
 #: E4M3 terms per 16-bit activation: 2 hold bf16's 8 significant bits (exact within 2^12 of the block maximum, truncation
 #: at 2^-19 of it below), fp16's 11 bits need 3
 SPLIT_A16_TERMS = {torch.bfloat16: 2, torch.float16: 3}
+#: measured (8192^2, bf16): M = 64: stacked 27.1 us / accumulated 31.2 us; M = 256: 49.7 / 41.6; M = 511: 90.7 / 62.1
+SPLIT_A16_ACCUMULATE_MIN_M = 128
 
 
 def split_a16(x2, terms=None):
@@ -297,14 +299,15 @@ def packed_linear(x, pw, bias=None):
                 and rowblock_mxfp8_operand(pw) is not None):
             # 16-bit activations as block-scaled E4M3 terms x the exact MX-FP8 form of the artefact: block-scaled kernels
             sa = split_a16(x2)
-            y3 = packed_linear_mx8(sa, pw)
+            y3 = packed_linear_mx8(sa, pw, accumulate_terms=M >= SPLIT_A16_ACCUMULATE_MIN_M)
+            folded = y3.shape[0] == M and sa.terms > 1
             if pw._mx8_dense_resid is not None:
                 rn, rk, rdw = pw._mx8_dense_resid
                 rc = N.lib().msq_sparse_outlier_correct(N.ptr(sa.codes), K, N.ptr(sa.e_in), N.ptr(rn), N.ptr(rk), N.ptr(rdw),
-                                                        int(rk.numel()), N.ptr(y3), y3.stride(0), sa.shape[0], K, 0,
-                                                        N.stream_ptr(y3.device))
+                                                        int(rk.numel()), N.ptr(y3), y3.stride(0), sa.shape[0], K,
+                                                        M if folded else 0, N.stream_ptr(y3.device))
                 N.check(rc, "msq_sparse_outlier_correct")
-            out = y3.view(sa.terms, M, Nn).sum(0)
+            out = y3 if folded else y3.view(sa.terms, M, Nn).sum(0)
         elif rowblock_ok(pw) and x2.shape[0] < FUSED_MAX_M:
             _packed_linear_rowblock(x2, pw, out)
         else:
@@ -355,8 +358,10 @@ def packed_linear(x, pw, bias=None):
                                                       N.stream_ptr(out.device))
             N.check(rc, "msq_gemm_mxfp4w_tiled_folded")
         else:
-            y3 = packed_linear_mx8(sa, pw)
-            out = y3.view(sa.terms, M, Nn).sum(0)
+            # from SPLIT_A16_ACCUMULATE_MIN_M rows the slabs are accumulated inside the TMA-fed GEMM (K loop over (term, K
+            # block): no [terms * M, N] result, no pass that adds the slabs); below, stacked slabs give more tiles to fill the SMs
+            y3 = packed_linear_mx8(sa, pw, accumulate_terms=M >= SPLIT_A16_ACCUMULATE_MIN_M)
+            out = y3 if y3.shape[0] == M else y3.view(sa.terms, M, Nn).sum(0)
         if bias is not None:
             out += bias.float()
         return out.reshape(*lead, Nn)
@@ -499,7 +504,7 @@ N.register("msq_sparse_outlier_correct", _i, [_p, _ll, _p, _p, _p, _p, _i, _p, _
 N.register("msq_tile_scales_ue8m0", _i, [_p, _i, _i, _i, _i, _p, _p])
 N.register("msq_gemm_mxfp8_tma_tile_tokens", _i, [_i, _i, _i])
 N.register("msq_gemm_mxfp8_tma_workspace_bytes", _ll, [_i, _i, _i])
-N.register("msq_gemm_mxfp8_tma", _i, [_p, _ll, _p, _p, _ll, _i, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p, _ll, _p])
+N.register("msq_gemm_mxfp8_tma", _i, [_p, _ll, _p, _p, _ll, _i, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _p, _ll, _p])
 
 #: compute-bound sizes (M >= MX8_DENSE_MIN_M): fully TMA-fed kernel (csrc/msq_gemm_mx8_tma.cu)
 MX8_TMA = True
@@ -564,7 +569,7 @@ def mx8_tma_weight(pw, allow_copy=True, sparse_limit=None):
     return (dense[0], K, 0, sf_t[1], None, None, None)
 
 
-def packed_linear_mx8(xq, pw, bias=None, cache_dense=False):
+def packed_linear_mx8(xq, pw, bias=None, cache_dense=False, accumulate_terms=False):
     """y = dq(xq) @ dq(pw).T on tcgen05 kind::mxf8f6f4.block_scale.  xq: PackedMX of the activations
     ([..., K], FP8 E4M3, block 32 along the last axis, no outliers); pw: packed FP4 weight (mx8_weight_ok).
     Routing: M <= 32 -> the packed codes by TMA + sparse outlier epilogue (msq_gemm_mxfp4w_tiled_blockscaled);
@@ -581,7 +586,16 @@ def packed_linear_mx8(xq, pw, bias=None, cache_dense=False):
         M *= s_
     Nn = pw.shape[0]
     dense = getattr(pw, "_mx8_dense", None)
-    if MX8_TMA and M > FP4_TMA_MAX_M and K % 128 == 0 and Nn % 4 == 0:
+    terms = int(getattr(xq, "terms", 1)) if accumulate_terms else 1          # stacked slabs accumulated inside the GEMM
+    if terms > 1:
+        # -> [M, N]; when the TMA-fed kernel cannot take this weight the slabs come back stacked ([terms * M, N])
+        M //= terms
+        if not (MX8_TMA and M * terms > FP4_TMA_MAX_M and K % 128 == 0 and Nn % 4 == 0 and mx8_tma_weight(
+                pw, allow_copy=cache_dense or dense is not None or M >= MX8_DENSE_MIN_M,
+                sparse_limit=-1.0 if cache_dense else
+                (MX8_TMA_SPARSE_BUDGET if M < MX8_DENSE_MIN_M else MX8_TMA_SPARSE_BUDGET_LARGE_M) / (float(M) * Nn)) is not None):
+            return packed_linear_mx8(xq, pw, bias=None, cache_dense=cache_dense)
+    if MX8_TMA and M * terms > FP4_TMA_MAX_M and K % 128 == 0 and Nn % 4 == 0:
         # everything above the decode sizes: both operands and both scale streams by TMA, double-buffered accumulators.
         # A plain FP4 weight feeds its packed codes; a weight with outliers its widened E4M3 copy -- built (and kept) only
         # in the compute-bound regime or on request, below that the producer-widen kernel reads the packed planes
@@ -591,22 +605,22 @@ def packed_linear_mx8(xq, pw, bias=None, cache_dense=False):
         if op is not None:
             out = torch.empty(M, Nn, dtype=torch.float32, device=pw.codes.device)
             w, ldw, is_fp4, wsf_t, o_ptr, o_k, o_dw = op
-            behind = o_ptr is not None and not MX8_TMA_FUSED_SPARSE
+            behind = o_ptr is not None and (terms > 1 or not MX8_TMA_FUSED_SPARSE)
             nbytes = int(N.lib().msq_gemm_mxfp8_tma_workspace_bytes(M, Nn, K))
             ws = _workspace(nbytes, out.device)
             rc = N.lib().msq_gemm_mxfp8_tma(N.ptr(xq.codes), K, N.ptr(xq.e_in), N.ptr(w), ldw, is_fp4, N.ptr(wsf_t),
                                             N.ptr(None if behind else o_ptr), N.ptr(None if behind else o_k),
-                                            N.ptr(None if behind else o_dw), N.ptr(out), out.stride(0), M, Nn, K, 0,
+                                            N.ptr(None if behind else o_dw), N.ptr(out), out.stride(0), M, Nn, K, terms, 0,
                                             N.ptr(ws), nbytes, N.stream_ptr(out.device))
             N.check(rc, "msq_gemm_mxfp8_tma")
             if behind:
                 rc = N.lib().msq_sparse_outlier_correct(N.ptr(xq.codes), K, N.ptr(xq.e_in), N.ptr(pw._mx4_sparse_rows), N.ptr(o_k),
-                                                        N.ptr(o_dw), int(o_k.numel()), N.ptr(out), out.stride(0), M, K, 0,
-                                                        N.stream_ptr(out.device))
+                                                        N.ptr(o_dw), int(o_k.numel()), N.ptr(out), out.stride(0), M * terms, K,
+                                                        M if terms > 1 else 0, N.stream_ptr(out.device))
                 N.check(rc, "msq_sparse_outlier_correct")
             if bias is not None:
                 out += bias.float()
-            return out.reshape(*xq.shape[:-1], Nn)
+            return out if terms > 1 else out.reshape(*xq.shape[:-1], Nn)
     if FP4_TMA and not cache_dense and M <= FP4_TMA_MAX_M and mx4_weight_ok(pw):
         # decode sizes: the packed 4-bit codes are the tensor-core operand (TMA-expanded), outliers = sparse epilogue
         o_ptr, o_k, o_dw = mx4_sparse_outliers(pw)

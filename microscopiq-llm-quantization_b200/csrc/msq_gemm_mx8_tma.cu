@@ -33,6 +33,8 @@ struct YParams {
   const uint8_t* xsf_t;       // activation scales, tiled: chunks (tm, kb)   at (tm * kblocks + kb) * 512 * sfb_chunks
   float* C; long long ldc;
   int M, N, K, bn, nacc, tiles_n, tiles_m, kblocks, sfb_chunks, accumulate, w_fmt, w_tx_bytes, pdl;
+  int terms;                  // the activations are `terms` stacked slabs of M rows (msq_split_a16_e4m3) that are ACCUMULATED:
+                              // the K loop runs terms * kblocks stages, stage (t, kb) = weight tile kb x slab t's tile kb
   // sparse outlier correction fused into the epilogue (FP4 operand whose outlier slots the tensor core reads as
   // q * 2^e_in):  C[m, n] += sum_e x[m, o_k[e]] * o_dw[e]  over the CSR row of feature n; o_ptr NULL = none
   const int* o_ptr; const int* o_k; const float* o_dw;
@@ -113,18 +115,21 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int tn, tm; tile_coords(t, tn, tm);
       const uint8_t* wsf = P.wsf_t + (long long)tn * P.kblocks * 512;
-      const uint8_t* xsf = P.xsf_t + (long long)tm * P.kblocks * 512 * P.sfb_chunks;
-      for (int kb = 0; kb < P.kblocks; ++kb) {
-        tc::mbar_wait(&empty[stage], phase ^ 1);
-        if (tc::elect_one()) {
-          tc::mbar_expect_tx(&full[stage], tx);
-          tc::tma_load_2d(sA + stage * YA_BYTES, &tmW, &full[stage], kb * YBK, tn * YM);
-          tc::tma_load_2d(sB + stage * YB_BYTES, &tmX, &full[stage], kb * YBK, tm * P.bn);
-          bulk_1d(sSF + stage * YSF_BYTES, wsf + (long long)kb * 512, 512, &full[stage]);
-          bulk_1d(sSF + stage * YSF_BYTES + 512, xsf + (long long)kb * 512 * P.sfb_chunks, 512u * (uint32_t)P.sfb_chunks, &full[stage]);
+      for (int term = 0; term < P.terms; ++term) {
+        const uint8_t* xsf = P.xsf_t + ((long long)term * P.tiles_m + tm) * P.kblocks * 512 * P.sfb_chunks;
+        const int xrow = term * P.M + tm * P.bn;
+        for (int kb = 0; kb < P.kblocks; ++kb) {
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+          if (tc::elect_one()) {
+            tc::mbar_expect_tx(&full[stage], tx);
+            tc::tma_load_2d(sA + stage * YA_BYTES, &tmW, &full[stage], kb * YBK, tn * YM);
+            tc::tma_load_2d(sB + stage * YB_BYTES, &tmX, &full[stage], kb * YBK, xrow);
+            bulk_1d(sSF + stage * YSF_BYTES, wsf + (long long)kb * 512, 512, &full[stage]);
+            bulk_1d(sSF + stage * YSF_BYTES + 512, xsf + (long long)kb * 512 * P.sfb_chunks, 512u * (uint32_t)P.sfb_chunks, &full[stage]);
+          }
+          __syncwarp();
+          if (++stage == YST) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == YST) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -142,7 +147,7 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__
       tc::mbar_wait(&acc_empty[as], ((acc_phase >> as) & 1u) ^ 1u);
       tc::tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(as * P.bn);
-      for (int kb = 0; kb < P.kblocks; ++kb) {
+      for (int kb = 0; kb < P.terms * P.kblocks; ++kb) {
         tc::mbar_wait(&full[stage], phase);
         tc::tc_fence_after();
         const uint64_t ad = ad0 + (uint64_t)((uint32_t)stage * a_step), bd = bd0 + (uint64_t)((uint32_t)stage * b_step);
@@ -241,6 +246,9 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__
 __global__ void __launch_bounds__(256) k_tile_scales(const uint8_t* __restrict__ src, int add127, int rows, int kblk32,
                                                      int rows_per_tile, int chunks, int kblocks, uint8_t* __restrict__ out) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // the GEMM behind us waits before it reads `out`
+  // blockIdx.z = slab of `rows` rows (stacked activation terms): each slab is tiled on its own
+  src += (long long)blockIdx.z * rows * kblk32;
+  out += (long long)blockIdx.z * gridDim.y * kblocks * chunks * 512;
   const int kb = blockIdx.x, tile = blockIdx.y;
   const int r = threadIdx.x;
   if (r >= chunks * 128) return;
@@ -301,14 +309,23 @@ using namespace msq;
 
 extern "C" {
 
+static int tile_scales(const void* scales, int is_int8_exponent, int rows, int K, int rows_per_tile, unsigned char* out, int slabs,
+                       void* stream);
+
 int msq_tile_scales_ue8m0(const void* scales, int is_int8_exponent, int rows, int K, int rows_per_tile, unsigned char* out,
                           void* stream) {
+  return tile_scales(scales, is_int8_exponent, rows, K, rows_per_tile, out, 1, stream);
+}
+
+static int tile_scales(const void* scales, int is_int8_exponent, int rows, int K, int rows_per_tile, unsigned char* out, int slabs,
+                       void* stream) {
   msq::DevGuard dev_guard_(scales);
-  if (!scales || !out || rows <= 0 || K <= 0 || rows_per_tile <= 0 || rows_per_tile > 256) return MSQ_ERR_BAD_ARG;
+  if (!scales || !out || rows <= 0 || K <= 0 || rows_per_tile <= 0 || rows_per_tile > 256 || slabs < 1) return MSQ_ERR_BAD_ARG;
   if (K % 128 != 0) return MSQ_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(scales) & 3) || (reinterpret_cast<uintptr_t>(out) & 15)) return MSQ_ERR_ALIGN;
+  if (slabs > 1 && ((long long)rows * (K / 32)) % 4 != 0) return MSQ_ERR_ALIGN;          // every slab starts on a 32-bit word
   const int chunks = (rows_per_tile + 127) / 128;
-  dim3 grid((unsigned)(K / YBK), (unsigned)((rows + rows_per_tile - 1) / rows_per_tile));
+  dim3 grid((unsigned)(K / YBK), (unsigned)((rows + rows_per_tile - 1) / rows_per_tile), (unsigned)slabs);
   k_tile_scales<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(scales), is_int8_exponent ? 1 : 0, rows,
                                                         K / 32, rows_per_tile, chunks, K / YBK, out);
   return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
@@ -337,16 +354,18 @@ int msq_gemm_mxfp8_tma_tile_tokens(int M, int N, int K) {
   return bn;
 }
 
+// bytes for the tiled activation scales of up to three stacked terms
 long long msq_gemm_mxfp8_tma_workspace_bytes(int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   const int bn = msq_gemm_mxfp8_tma_tile_tokens(M, N, K);
   const long long tiles_m = (M + bn - 1) / bn, kblocks = (K + YBK - 1) / YBK, chunks = (bn + 127) / 128;
-  return tiles_m * kblocks * chunks * 512;
+  return 3 * tiles_m * kblocks * chunks * 512;
 }
 
 int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* w, long long ldw,
                        int w_is_fp4, const unsigned char* wsf_tiled, const int* o_ptr, const int* o_k, const float* o_dw, float* C,
-                       long long ldc, int M, int N, int K, int accumulate, void* workspace, long long workspace_bytes, void* stream) {
+                       long long ldc, int M, int N, int K, int terms, int accumulate, void* workspace, long long workspace_bytes,
+                       void* stream) {
   msq::DevGuard dev_guard_(xcodes);
   if (!xcodes || !xe || !w || !wsf_tiled || !C || !workspace || M <= 0 || N <= 0 || K <= 0) return MSQ_ERR_BAD_ARG;
   if (K % 128 != 0) return MSQ_ERR_UNSUPPORTED;
@@ -356,6 +375,7 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
     return MSQ_ERR_ALIGN;
   if (w_is_fp4 && (ldw % 32)) return MSQ_ERR_ALIGN;
   if (o_ptr && (!o_k || !o_dw)) return MSQ_ERR_BAD_ARG;
+  if (terms < 1 || terms > 3 || (terms > 1 && o_ptr)) return MSQ_ERR_BAD_ARG;     // stacked terms: corrections by msq_sparse_outlier_correct
   if (workspace_bytes < msq_gemm_mxfp8_tma_workspace_bytes(M, N, K)) return MSQ_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   int dev = 0, sms = 148;
@@ -365,16 +385,16 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
   memset(&P, 0, sizeof(P));
   choose_bn(M, N, K, sms, P.bn, P.nacc);
   P.wsf_t = wsf_tiled; P.xsf_t = reinterpret_cast<const uint8_t*>(workspace); P.C = C; P.ldc = ldc;
-  P.M = M; P.N = N; P.K = K; P.accumulate = accumulate;
+  P.M = M; P.N = N; P.K = K; P.accumulate = accumulate; P.terms = terms;
   P.o_ptr = o_ptr; P.o_k = o_k; P.o_dw = o_dw; P.xcodes = xcodes; P.ldx = ldx; P.xe = xe;
   P.tiles_n = (N + YM - 1) / YM; P.tiles_m = (M + P.bn - 1) / P.bn; P.kblocks = K / YBK; P.sfb_chunks = (P.bn + 127) / 128;
   P.w_fmt = w_is_fp4 ? 5 : 0;
   // a 16U4_ALIGN16B load reports the bytes it READ to the mbarrier (see msq_gemm_mx8.cu)
   P.w_tx_bytes = w_is_fp4 ? YA_BYTES / 2 : YA_BYTES;
-  int rc = msq_tile_scales_ue8m0(xe, 1, M, K, P.bn, reinterpret_cast<unsigned char*>(workspace), stream);
+  int rc = tile_scales(xe, 1, M, K, P.bn, reinterpret_cast<unsigned char*>(workspace), terms, stream);
   if (rc) return rc;
   CUtensorMap tmX, tmW;
-  rc = make_tmap_2d(&tmX, xcodes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K, ldx, P.bn, YBK);
+  rc = make_tmap_2d(&tmX, xcodes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, (long long)terms * M, K, ldx, P.bn, YBK);
   if (rc) return rc;
   if (w_is_fp4) rc = make_tmap_2d_u4(&tmW, w, N, K, ldw, YM);
   else rc = make_tmap_2d(&tmW, w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, ldw, YM, YBK);
