@@ -272,6 +272,15 @@ def extras(dev, dev_w, nel):
         x = torch.randn(M, 4096, device=dev).to(torch.bfloat16)
         ms = (_time_ms_device if M <= 256 else _time_ms)(lambda: _tc.packed_linear(x, pw), 10)
         gemm["M%d" % M] = {"ms": ms, "TFLOPs": 2.0 * M * 4096 * 4096 / (ms * 1e-3) / 1e12}
+        if M >= 4096:
+            # the same with a dequantized bf16 copy of the weight kept next to the planes (2 B / weight) + kind::f16 GEMM
+            _tc.LARGE_M_WITHOUT_BF16_COPY = False
+            ms2 = _time_ms(lambda: _tc.packed_linear(x, pw), 10)
+            _tc.LARGE_M_WITHOUT_BF16_COPY = True
+            pw._dense_bf16 = None
+            gemm["M%d" % M]["with_bf16_copy_of_the_weight"] = {"ms": ms2, "TFLOPs": 2.0 * M * 4096 * 4096 / (ms2 * 1e-3) / 1e12}
+    gemm["note"] = ("bf16 activations x packed FP4 weight: activations split into two block-scaled E4M3 terms, tcgen05 "
+                    "kind::mxf8f6f4 on the packed codes at every M (no dequantized copy of the weight)")
     out["packed_gemm_k4096_n4096"] = gemm
     # (3b) the artefact the quantizers / GPTQ emit (row blocks of 16 along the output features, FP4 inliers / FP8 outliers,
     # hi stream), bf16 activations: its exact K-blocked MX-FP8 form on the block-scaled kernels vs the row-block kernel
