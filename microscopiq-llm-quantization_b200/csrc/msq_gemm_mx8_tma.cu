@@ -240,6 +240,225 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Two-CTA form (cta_group::2): a cluster of two CTAs owns a tile of 256 weight rows x BN tokens.  Each CTA stages ITS 128
+// weight rows and ITS half of the tokens (BN/2 rows), the MMA -- issued by the leader CTA for both -- reads the halves of the
+// token tile from both CTAs' shared memory: per SM and stage 16 KB + 16 KB land by TMA and are read by the tensor core instead
+// of 16 KB + 32 KB (the one-CTA kernel sits at 107 of the 128 B/clk of shared-memory traffic an SM moves), and the ring is six
+// stages deep.  All loads -- including the scale chunks, through uint32 tensor maps over the tiled scale arrays -- are
+// cp.async.bulk.tensor.cta_group::2 that signal the LEADER's mbarrier; tcgen05.commit multicasts the "stage free" /
+// "accumulator full" arrivals to both CTAs; the epilogue warps of both CTAs arrive on the leader's "accumulator free".
+constexpr int ZST = 6;
+constexpr int ZA_BYTES = YM * YBK, ZB_BYTES = (YMAXN / 2) * YBK, ZSF_BYTES = 512 + 1024;
+constexpr int Z_SMEM = ZST * (ZA_BYTES + ZB_BYTES + ZSF_BYTES) + 1024 + 256;
+static_assert(Z_SMEM <= 227 * 1024, "shared memory");
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// bounded wait: a protocol error traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = tc::smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 6000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          tc::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void cp_sf2(uint32_t tmem_addr, uint64_t desc) {
+  asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(tmem_addr), "l"(desc) : "memory");
+}
+__device__ __forceinline__ void mma_bs2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                        uint32_t tsfa, uint32_t tsfb) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb)
+      : "memory");
+}
+__device__ __forceinline__ void commit2_mc(uint64_t* bar) {       // arrive on `bar` in BOTH CTAs once the MMAs issued so far are done
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   tc::smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                                                           const __grid_constant__ CUtensorMap tmXSF,
+                                                           const __grid_constant__ CUtensorMap tmWSF, const YParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + ZST * ZA_BYTES;
+  uint8_t* sSF = smem + ZST * (ZA_BYTES + ZB_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSF + ZST * ZSF_BYTES);
+  uint64_t* full = bars;                    // used in the leader CTA only
+  uint64_t* empty = bars + ZST;
+  uint64_t* acc_full = bars + 2 * ZST;
+  uint64_t* acc_empty = bars + 2 * ZST + 2;  // used in the leader CTA only (256 arrivals: the epilogue threads of both CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ZST + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int pair = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
+  const int num_tiles = P.tiles_n * P.tiles_m;                 // tiles_n counts 256-row tiles here
+  const int band_tiles = YGROUP * P.tiles_n;
+  auto tile_coords = [&](int t, int& tn, int& tm) {
+    const int band = t / band_tiles;
+    const int first = band * YGROUP;
+    const int rows = min(YGROUP, P.tiles_m - first);
+    const int r = t - band * band_tiles;
+    tn = r / rows;
+    tm = first + (r - tn * rows);
+  };
+
+  if (warp == 0 && lane == 0) {
+    tc::tma_prefetch_desc(&tmX); tc::tma_prefetch_desc(&tmW); tc::tma_prefetch_desc(&tmXSF); tc::tma_prefetch_desc(&tmWSF);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < ZST; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 256); }
+    tc::mbar_fence_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc::tc_fence_before();
+  cluster_sync_all();                       // barrier inits and the allocation are visible in both CTAs
+  tc::tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const int half = P.bn >> 1;
+
+  if (warp == 0) {
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t tx_cta = (uint32_t)(P.w_tx_bytes + half * YBK + 512 + 512 * P.sfb_chunks);
+    if (P.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int t = pair; t < num_tiles; t += npairs) {
+      int tn, tm; tile_coords(t, tn, tm);
+      const int wrow = tn * 2 * YM + (int)rank * YM;
+      const int wsf_row = (tn * 2 + (int)rank) * P.kblocks;
+      for (int term = 0; term < P.terms; ++term) {
+        const int xrow = term * P.M + tm * P.bn + (int)rank * half;
+        const int xsf_row = ((term * P.tiles_m + tm) * P.kblocks) * P.sfb_chunks;
+        for (int kb = 0; kb < P.kblocks; ++kb) {
+          mbar_wait_b(&empty[stage], phase ^ 1);
+          if (tc::elect_one()) {
+            const uint32_t lbar = mapa_u32(tc::smem_u32(&full[stage]), 0);
+            if (rank == 0) tc::mbar_expect_tx(&full[stage], 2u * tx_cta);
+            tma_load_2d_cg2(sA + stage * ZA_BYTES, &tmW, lbar, kb * YBK, wrow);
+            tma_load_2d_cg2(sB + stage * ZB_BYTES, &tmX, lbar, kb * YBK, xrow);
+            tma_load_2d_cg2(sSF + stage * ZSF_BYTES, &tmWSF, lbar, 0, wsf_row + kb);
+            tma_load_2d_cg2(sSF + stage * ZSF_BYTES + 512, &tmXSF, lbar, 0, xsf_row + kb * P.sfb_chunks);
+          }
+          __syncwarp();
+          if (++stage == ZST) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    int stage = 0; uint32_t phase = 0;
+    int as = 0; uint32_t acc_phase = 0;
+    const uint64_t ad0 = tc::make_kmajor_sw128_desc(tc::smem_u32(sA)), bd0 = tc::make_kmajor_sw128_desc(tc::smem_u32(sB));
+    const uint64_t sfd0 = sf_desc(tc::smem_u32(sSF));
+    const uint32_t a_step = (uint32_t)(ZA_BYTES >> 4), b_step = (uint32_t)(ZB_BYTES >> 4), sf_step = (uint32_t)(ZSF_BYTES >> 4);
+    const uint32_t idesc0 = ((uint32_t)P.w_fmt << 7) | ((uint32_t)(P.bn >> 3) << 17) | (1u << 23) | ((uint32_t)((2 * YM) >> 4) << 24);
+    const uint32_t idesc_k = (1u << 4) | (1u << 29);
+    const uint32_t tsfa = tmem_base + (uint32_t)(P.nacc * P.bn), tsfb = tsfa + 4;
+    for (int t = pair; t < num_tiles; t += npairs) {
+      mbar_wait_b(&acc_empty[as], ((acc_phase >> as) & 1u) ^ 1u);
+      tc::tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(as * P.bn);
+      for (int kb = 0; kb < P.terms * P.kblocks; ++kb) {
+        mbar_wait_b(&full[stage], phase);
+        tc::tc_fence_after();
+        const uint64_t ad = ad0 + (uint64_t)((uint32_t)stage * a_step), bd = bd0 + (uint64_t)((uint32_t)stage * b_step);
+        const uint64_t sfd = sfd0 + (uint64_t)((uint32_t)stage * sf_step);
+        if (tc::elect_one()) {
+          cp_sf2(tsfa, sfd);
+          cp_sf2(tsfb, sfd + 32u);
+          if (P.sfb_chunks > 1) cp_sf2(tsfb + 4, sfd + 64u);
+#pragma unroll
+          for (int k = 0; k < YBK / 32; ++k)
+            mma_bs2(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc0 + (uint32_t)k * idesc_k, (kb | k) != 0, tsfa, tsfb);
+          commit2_mc(&empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == ZST) { stage = 0; phase ^= 1; }
+      }
+      if (tc::elect_one()) commit2_mc(&acc_full[as]);
+      __syncwarp();
+      acc_phase ^= 1u << as;
+      if (P.nacc == 2) as ^= 1;
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    int as = 0; uint32_t acc_phase = 0;
+    for (int t = pair; t < num_tiles; t += npairs) {
+      int tn, tm; tile_coords(t, tn, tm);
+      const int n = tn * 2 * YM + (int)rank * YM + q * 32 + lane;
+      const int m0 = tm * P.bn;
+      mbar_wait_b(&acc_full[as], (acc_phase >> as) & 1u);
+      tc::tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * P.bn);
+      float* crow = P.C + (long long)m0 * P.ldc + n;
+      for (int c = 0; c < P.bn; c += 16) {
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(tacc + (uint32_t)c)
+            : "memory");
+        tc::tmem_ld_wait();
+        if (n < P.N) {
+#pragma unroll
+          for (int v = 0; v < 16; ++v) {
+            if (m0 + c + v < P.M) {
+              float* p = crow + (long long)(c + v) * P.ldc;
+              const float val = __uint_as_float(r[v]);
+              *p = P.accumulate ? (*p + val) : val;
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+      arrive_cluster(mapa_u32(tc::smem_u32(&acc_empty[as]), 0));
+      acc_phase ^= 1u << as;
+      if (P.nacc == 2) as ^= 1;
+    }
+  }
+  tc::tc_fence_before();
+  cluster_sync_all();                       // nobody frees tensor memory (or leaves) while the peer still uses the pair
+  if (warp == 2) {
+    tc::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
 // scales [rows, K/32] (int8 shared exponents, or UE8M0 bytes) -> tcgen05.cp chunks: for every (tile of rows_per_tile rows,
 // 128-wide K block) `chunks` = ceil(rows_per_tile / 128) pieces of 512 bytes, byte(r, j) = (r % 32) * 16 + (r / 32) * 4 + j
 // for row r of the piece and 32-block j of the K block; rows outside the matrix get 2^0
@@ -302,6 +521,31 @@ static void choose_bn(int M, int N, int K, int sms, int& bn, int& nacc) {
   }
 }
 
+// tiled scale chunks as a 2-D uint32 tensor: row = one 512-byte chunk
+static int make_tmap_sf(CUtensorMap* out, const void* base, long long rows, int box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return MSQ_ERR_CUDA;
+  cuuint64_t dims[2] = {128u, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {512u};
+  cuuint32_t box[2] = {128u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MSQ_OK : MSQ_ERR_CUDA;
+}
+
+// which kernel and which token-tile width a problem gets (shared by the GEMM and the workspace / tile-width queries)
+static void plan(int M, int N, int K, int sms, int& bn, int& nacc, int& cta2) {
+  // measured (plain FP4 weight, 4096^2 / 8192^2): M = 64: 10.0 / 16.8 us one CTA, 10.6 / 17.0 us pairs; M = 256: 12.8 / 23.1 vs
+  // 11.8 / 19.7; M = 4096: 65.1 / 243.9 vs 55.6 / 201.0 -- pairs from 256 tokens on (MSQ_MX8T_CTA2 = 0 / 1 forces a form)
+  const char* e = getenv("MSQ_MX8T_CTA2");
+  cta2 = e ? (e[0] == '1') : (M >= 256 && N >= 512);
+  if (sms < 2) cta2 = 0;
+  if (cta2) choose_bn(M, ((N + 2 * YM - 1) / (2 * YM)) * YM, K, sms / 2, bn, nacc);       // pairs of CTAs over 256-row tiles
+  else choose_bn(M, N, K, sms, bn, nacc);
+}
+
 }  // namespace
 }  // namespace msq
 
@@ -350,7 +594,8 @@ int msq_gemm_mxfp8_tma_tile_tokens(int M, int N, int K) {
   int dev = 0, sms = 148, bn, nacc;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 148; }
-  choose_bn(M, N, K, sms, bn, nacc);
+  int cta2;
+  plan(M, N, K, sms, bn, nacc, cta2);
   return bn;
 }
 
@@ -359,7 +604,7 @@ long long msq_gemm_mxfp8_tma_workspace_bytes(int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   const int bn = msq_gemm_mxfp8_tma_tile_tokens(M, N, K);
   const long long tiles_m = (M + bn - 1) / bn, kblocks = (K + YBK - 1) / YBK, chunks = (bn + 127) / 128;
-  return 3 * tiles_m * kblocks * chunks * 512;
+  return 3 * tiles_m * kblocks * chunks * 512 + 1024;
 }
 
 int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* w, long long ldw,
@@ -383,7 +628,9 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   YParams P;
   memset(&P, 0, sizeof(P));
-  choose_bn(M, N, K, sms, P.bn, P.nacc);
+  int cta2 = 0;
+  plan(M, N, K, sms, P.bn, P.nacc, cta2);
+  if (o_ptr) { cta2 = 0; choose_bn(M, N, K, sms, P.bn, P.nacc); }       // the fused sparse epilogue lives in the one-CTA kernel
   P.wsf_t = wsf_tiled; P.xsf_t = reinterpret_cast<const uint8_t*>(workspace); P.C = C; P.ldc = ldc;
   P.M = M; P.N = N; P.K = K; P.accumulate = accumulate; P.terms = terms;
   P.o_ptr = o_ptr; P.o_k = o_k; P.o_dw = o_dw; P.xcodes = xcodes; P.ldx = ldx; P.xe = xe;
@@ -399,6 +646,31 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
   if (w_is_fp4) rc = make_tmap_2d_u4(&tmW, w, N, K, ldw, YM);
   else rc = make_tmap_2d(&tmW, w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, ldw, YM, YBK);
   if (rc) return rc;
+  if (cta2) {
+    // cluster of two CTAs per 256-row tile; each CTA loads its half of the token tile
+    P.tiles_n = (N + 2 * YM - 1) / (2 * YM);
+    CUtensorMap tmXh, tmXSF, tmWSF;
+    rc = make_tmap_2d(&tmXh, xcodes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, (long long)terms * M, K, ldx, P.bn / 2, YBK);
+    if (rc) return rc;
+    rc = make_tmap_sf(&tmXSF, workspace, (long long)terms * P.tiles_m * P.kblocks * P.sfb_chunks, P.sfb_chunks);
+    if (rc) return rc;
+    rc = make_tmap_sf(&tmWSF, wsf_tiled, (long long)((N + YM - 1) / YM) * P.kblocks, 1);
+    if (rc) return rc;
+    if (cudaFuncSetAttribute(k_gemm_mx8_tma2, cudaFuncAttributeMaxDynamicSharedMemorySize, Z_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
+    int pairs = P.tiles_n * P.tiles_m;
+    if (pairs > sms / 2) pairs = sms / 2;
+    P.pdl = getenv("MSQ_MX8_NO_PDL") == nullptr ? 1 : 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * pairs)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Z_SMEM; cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = P.pdl ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, k_gemm_mx8_tma2, tmXh, tmW, tmXSF, tmWSF, P) == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+  }
   if (cudaFuncSetAttribute(k_gemm_mx8_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, Y_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
   int grid = P.tiles_n * P.tiles_m;
   if (grid > sms) grid = sms;
