@@ -33,6 +33,7 @@ struct YParams {
   const uint8_t* xsf_t;       // activation scales, tiled: chunks (tm, kb)   at (tm * kblocks + kb) * 512 * sfb_chunks
   float* C; long long ldc;
   int M, N, K, bn, nacc, tiles_n, tiles_m, kblocks, sfb_chunks, accumulate, w_fmt, w_tx_bytes, pdl;
+  int epi_h;                  // two-CTA kernel: epilogue warps per TMEM lane quarter (1 or 2)
   int terms;                  // the activations are `terms` stacked slabs of M rows (msq_split_a16_e4m3) that are ACCUMULATED:
                               // the K loop runs terms * kblocks stages, stage (t, kb) = weight tile kb x slab t's tile kb
   // sparse outlier correction fused into the epilogue (FP4 operand whose outlier slots the tensor core reads as
@@ -305,7 +306,7 @@ __device__ __forceinline__ void arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
-__global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+__global__ void __launch_bounds__(384, 1) k_gemm_mx8_tma2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                                                            const __grid_constant__ CUtensorMap tmXSF,
                                                            const __grid_constant__ CUtensorMap tmWSF, const YParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma2(const __grid_constant_
   uint64_t* full = bars;                    // used in the leader CTA only
   uint64_t* empty = bars + ZST;
   uint64_t* acc_full = bars + 2 * ZST;
-  uint64_t* acc_empty = bars + 2 * ZST + 2;  // used in the leader CTA only (256 arrivals: the epilogue threads of both CTAs)
+  uint64_t* acc_empty = bars + 2 * ZST + 2;  // used in the leader CTA only (512 arrivals: the epilogue threads of both CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ZST + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma2(const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < ZST; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 256); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 256u * (uint32_t)P.epi_h); }
     tc::mbar_fence_init();
   }
   if (warp == 2) {
@@ -415,9 +416,20 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma2(const __grid_constant_
       if (P.nacc == 2) as ^= 1;
     }
   } else if (warp >= 4) {
-    const int q = warp & 3;
+    // ---- epilogue: EIGHT warps, two per TMEM lane quarter taking alternate 16-column chunks; the tcgen05.ld of a warp's
+    // next chunk is in flight while it stores the current one.  With BN = 256 there is one accumulator and the drain is
+    // exposed once per tile (ncu, 8192^3, four warps: tensor pipe 80 % active, the rest is this drain)
+    const int q = warp & 3, h = (warp - 4) >> 2;
     int as = 0; uint32_t acc_phase = 0;
-    for (int t = pair; t < num_tiles; t += npairs) {
+    auto ld16 = [&](uint32_t (&r)[16], uint32_t taddr) {
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(taddr)
+          : "memory");
+    };
+    for (int t = pair; t < num_tiles && h < P.epi_h; t += npairs) {
       int tn, tm; tile_coords(t, tn, tm);
       const int n = tn * 2 * YM + (int)rank * YM + q * 32 + lane;
       const int m0 = tm * P.bn;
@@ -425,15 +437,7 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma2(const __grid_constant_
       tc::tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * P.bn);
       float* crow = P.C + (long long)m0 * P.ldc + n;
-      for (int c = 0; c < P.bn; c += 16) {
-        uint32_t r[16];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-            : "r"(tacc + (uint32_t)c)
-            : "memory");
-        tc::tmem_ld_wait();
+      auto st16 = [&](const uint32_t (&r)[16], int c) {
         if (n < P.N) {
 #pragma unroll
           for (int v = 0; v < 16; ++v) {
@@ -443,6 +447,20 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma2(const __grid_constant_
               *p = P.accumulate ? (*p + val) : val;
             }
           }
+        }
+      };
+      uint32_t ra[16], rb[16];
+      const int half = 16 * P.epi_h;
+      int c = h * 16;
+      if (c < P.bn) ld16(ra, tacc + (uint32_t)c);
+      for (; c < P.bn; c += 2 * half) {
+        tc::tmem_ld_wait();
+        if (c + half < P.bn) ld16(rb, tacc + (uint32_t)(c + half));
+        st16(ra, c);
+        if (c + half < P.bn) {
+          tc::tmem_ld_wait();
+          if (c + 2 * half < P.bn) ld16(ra, tacc + (uint32_t)(c + 2 * half));
+          st16(rb, c + half);
         }
       }
       tc::tc_fence_before();
@@ -660,9 +678,10 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
     int pairs = P.tiles_n * P.tiles_m;
     if (pairs > sms / 2) pairs = sms / 2;
     P.pdl = getenv("MSQ_MX8_NO_PDL") == nullptr ? 1 : 0;
+    P.epi_h = getenv("MSQ_MX8T_EPI4") == nullptr ? 2 : 1;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)(2 * pairs)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Z_SMEM; cfg.stream = s;
+    cfg.gridDim = dim3((unsigned)(2 * pairs)); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = Z_SMEM; cfg.stream = s;
     cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;

@@ -550,6 +550,225 @@ __device__ __forceinline__ BlockOut core_outlier(float (&x)[N], uint32_t (&code)
   return o;
 }
 
+// ---------------------------------------------------------------------------------------------
+// core_outlier_cvt: the packing kernels' block arithmetic for the drivers' own pairing -- fp4_e2m1 inliers, fp8_e4m3
+// outliers, round-to-nearest, 16-element blocks held by one thread (llm/llama.py:130-137 of the reference) -- with the
+// element rounding AND the code done by Blackwell's narrow-format conversion instructions
+// (cvt.rn.satfinite.e2m1x2.f32 / .e4m3x2.f32, two elements each) instead of ~20 fp32 / integer instructions per element.
+//
+// Why the results are the reference's, bit for bit (elemwise_ops.py:47-81,131-167 with saturate_normals, allow_denorm):
+//  * the scaled value v = x * 2^-e (inliers) / x * 2^(e_in - e_out) (outliers) is exact while the shared exponents are
+//    far from the fp32 range limits (checked per block; an fp32-subnormal intermediate only occurs for |v| < 2^-46,
+//    which both roundings send to zero);
+//  * the reference rounds |y| = |v| / quantum to floor(fl(|y| + 0.5)) -- ties away from zero -- and clamps to max_norm;
+//    the hardware rounds to nearest EVEN and saturates to the same max_norm.  Setting the last mantissa bit of x
+//    (x | 1) before the (exact) scaling moves every exact tie just above the tie and changes nothing else: ties have
+//    that bit clear (the format grids are >= 2^20 ulps coarse), no other value can cross or land on one;
+//  * fl(|y| + 0.5) is itself rounded: for exactly one magnitude per format, the fp32 just below half the smallest
+//    subnormal (|y| = 0.5 - 2^-25), the sum rounds up to 1.0 and the reference returns the smallest subnormal where
+//    round-to-nearest gives zero (every other binade adds exactly, or lands where the floor does not change).  That
+//    magnitude is compared for exactly (block-uniform constants) and patched in a branch that real data never takes;
+//  * the reference's code for a value rounded to zero carries no sign (encode_elem): the sign bit of zero-magnitude
+//    codes is cleared (SWAR on the packed words).
+// Everything outside these conditions -- non-finite input, a shared exponent outside [-40, 40] (inliers) / [-80, 80]
+// (outliers) or clamped by the scale width, an all-outlier block, flush-to-zero -- takes core_outlier unchanged.
+// Outputs are the packed words the staging code wants: 4-bit slots of elements 0-7 / 8-15 and the compacted hi nibbles.
+// ---------------------------------------------------------------------------------------------
+struct BlockPk {
+  uint32_t s0, s1;   // slot nibbles of elements 0..7 / 8..15 (element j of a group in nibble j)
+  uint32_t h0, h1;   // compacted hi nibbles of the outliers of each group, first outlier in the lowest nibble
+  uint32_t mask;
+  int e_in, e_out, cnt, st;
+};
+// eight fp32 -> eight E2M1 codes, element j in nibble j
+__device__ __forceinline__ uint32_t cvt8_e2m1(float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
+  uint32_t d;
+  asm("{\n"
+      ".reg .b8 b0, b1, b2, b3;\n"
+      "cvt.rn.satfinite.e2m1x2.f32 b0, %2, %1;\n"
+      "cvt.rn.satfinite.e2m1x2.f32 b1, %4, %3;\n"
+      "cvt.rn.satfinite.e2m1x2.f32 b2, %6, %5;\n"
+      "cvt.rn.satfinite.e2m1x2.f32 b3, %8, %7;\n"
+      "mov.b32 %0, {b0, b1, b2, b3};\n"
+      "}\n"
+      : "=r"(d)
+      : "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4), "f"(a5), "f"(a6), "f"(a7));
+  return d;
+}
+// four fp32 -> four E4M3 codes, element j in byte j
+__device__ __forceinline__ uint32_t cvt4_e4m3(float a0, float a1, float a2, float a3) {
+  uint32_t d;
+  asm("{\n"
+      ".reg .b16 l, h;\n"
+      "cvt.rn.satfinite.e4m3x2.f32 l, %2, %1;\n"
+      "cvt.rn.satfinite.e4m3x2.f32 h, %4, %3;\n"
+      "mov.b32 %0, {l, h};\n"
+      "}\n"
+      : "=r"(d)
+      : "f"(a0), "f"(a1), "f"(a2), "f"(a3));
+  return d;
+}
+// 16 codes (<= 8 bits, low nibble = slot) -> the two slot words
+__device__ __forceinline__ void slots_from_codes16(const uint32_t* c, uint32_t& W0, uint32_t& W1) {
+  // four codes per word by multiply-adds (sums of disjoint bytes), low nibbles kept, adjacent nibbles merged:
+  // byte 0 / byte 2 of t = elements (4j, 4j+1) / (4j+2, 4j+3)
+  uint32_t t[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t w = ((c[4 * j + 3] * 256u + c[4 * j + 2]) * 256u + c[4 * j + 1]) * 256u + c[4 * j];
+    const uint32_t l = w & 0x0F0F0F0Fu;
+    t[j] = l | (l >> 4);
+  }
+  W0 = __byte_perm(t[0], t[1], 0x6420);
+  W1 = __byte_perm(t[2], t[3], 0x6420);
+}
+// bits 0..7 -> nibbles 0..7 (0xF where the bit is set)
+__device__ __forceinline__ uint32_t nibble_mask8(uint32_t m8) {
+  uint32_t x = (m8 * 0x1001u) & 0x000F000Fu;       // bits 0-3 | bits 4-7 at bit 16
+  x = (x * 0x41u) & 0x03030303u;
+  x = (x * 0x9u) & 0x11111111u;
+  return x * 15u;
+}
+
+__device__ __forceinline__ BlockPk core_outlier_cvt(const float (&x)[16], const QCfg& c) {
+  constexpr int N = 16;
+  BlockPk o;
+  o.st = 0;
+  // ---- detector bounds: the statements of core_outlier (same order of fp32 operations)
+  float t[N];
+#pragma unroll
+  for (int i = 0; i + 1 < N; i += 2) t[i] = __fadd_rn(fabsf(x[i]), fabsf(x[i + 1]));
+  const float s = tree_sum_regs2<N, 2>(t);
+  const bool bad = !(s <= 3.402823466e38f);
+  constexpr float inv_bs = 1.0f / (float)N;
+  const float mean = __fmul_rn(s, inv_bs);
+  {
+    const float2 z2 = f2s(c.fzero);
+#pragma unroll
+    for (int i = 0; i < N; i += 4) {
+      const float d0 = __fsub_rn(fabsf(x[i]), mean), d1 = __fsub_rn(fabsf(x[i + 1]), mean);
+      const float d2 = __fsub_rn(fabsf(x[i + 2]), mean), d3 = __fsub_rn(fabsf(x[i + 3]), mean);
+      const float2 a = __ffma2_rn(make_float2(d0, d2), make_float2(d0, d2), z2);
+      const float2 b = __ffma2_rn(make_float2(d1, d3), make_float2(d1, d3), z2);
+      t[i] = a.x; t[i + 2] = a.y; t[i + 1] = b.x; t[i + 3] = b.y;
+    }
+  }
+  const float q = tree_sum_regs2<N>(t);
+  const float sd = __fsqrt_rn(__fmul_rn(q, inv_bs));
+  const float w = __fmul_rn(c.std_dev, sd);
+  const float l = __fsub_rn(mean, w), h = __fadd_rn(mean, w);
+  // ---- mask, the two maxima (|x * (1 - m)|, |x * m| are the magnitudes of quant.py:70-71's products)
+  float mf[N];
+  float m_in = 0.0f, m_out = 0.0f;
+  float2 lo2 = f2s(0.0f);
+#pragma unroll
+  for (int i = 0; i < N; i += 2) {
+    mf[i] = fmaxf(fset_lt(x[i], l), fset_gt(x[i], h));
+    mf[i + 1] = fmaxf(fset_lt(x[i + 1], l), fset_gt(x[i + 1], h));
+    const float2 m = f2(mf[i], mf[i + 1]), xv = f2(x[i], x[i + 1]);
+    lo2 = __ffma2_rn(m, f2((float)(1u << i), (float)(2u << i)), lo2);
+    const float2 nm = __ffma2_rn(m, f2s(-1.0f), f2s(1.0f));
+    const float2 to = __fmul2_rn(xv, m), ti = __fmul2_rn(xv, nm);
+    m_in = fmaxf(m_in, fmaxf(fabsf(ti.x), fabsf(ti.y)));
+    m_out = fmaxf(m_out, fmaxf(fabsf(to.x), fabsf(to.y)));
+  }
+  o.mask = __float2uint_rz(__fadd_rn(lo2.x, lo2.y));
+  o.cnt = __popc(o.mask);
+  // ---- shared exponents exactly as core_outlier; decide whether this block is on the conversion path
+  const int S_in = (1 << (c.sb_in - 1)) - 1, S_out = (1 << (c.sb_out - 1)) - 1;
+  const int U_in = (c.variant == 0 && S_in > 20) ? -20 : -S_in, U_out = (c.variant == 0 && S_out > 20) ? -20 : -S_out;
+  const int er_in = floor_log2_or_min(m_in) - c.fin.emax;
+  o.e_in = clamp_scale_sel(er_in, S_in, U_in);
+  const bool zero_in = (m_in == 0.0f) && (o.mask == 0u);       // nothing but zeros: every code is 0 whatever the scale
+  bool fast = !bad && ((o.e_in == er_in && er_in >= -40 && er_in <= 40) || zero_in);
+  const int e_in = zero_in ? 0 : er_in;
+  // max |t * 2^e_in| = (max |t|) * 2^e_in: scaling by a power of two is monotone (and exact in this range)
+  const int er_out = floor_log2_or_min(__fmul_rn(m_out, pow2i(fast ? e_in : 0))) - c.fout.emax;
+  o.e_out = clamp_scale_sel(er_out, S_out, U_out);
+  fast = fast && (o.mask == 0u || (o.e_out == er_out && er_out >= -80 && er_out <= 80));
+  if (!fast) {
+    float xc[N];
+    uint32_t code[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) xc[i] = x[i];
+    const BlockOut b = core_outlier<N, 1, true, false, true, true>(xc, code, c, nullptr, nullptr);
+    slots_from_codes16(code, o.s0, o.s1);
+    o.h0 = b.hacc[0]; o.h1 = b.hacc[1];
+    o.mask = b.mask; o.e_in = b.e_in; o.e_out = b.e_out; o.cnt = b.cnt; o.st = b.st;
+    return o;
+  }
+  const int e_out = o.mask ? er_out : e_in;
+  const float si = pow2i(-e_in), so = pow2i(e_in - e_out);
+  // the one magnitude per format where fl(|y| + 0.5) rounds up to 1 (see above): half the smallest subnormal minus an ulp
+  const float c_in = __int_as_float(__float_as_int(pow2i(e_in + c.fin.min_exp - (c.fin.bits - 2) - 1)) - 1);
+  const float c_out = __int_as_float(__float_as_int(pow2i(e_out - e_in + c.fout.min_exp - (c.fout.bits - 2) - 1)) - 1);
+  float vi[N], vo[N];
+  bool special = false;
+#pragma unroll
+  for (int i = 0; i < N; i += 2) {
+    special = special || (fabsf(x[i]) == c_in) || (fabsf(x[i]) == c_out) || (fabsf(x[i + 1]) == c_in) || (fabsf(x[i + 1]) == c_out);
+    const float2 xb = f2(__int_as_float(__float_as_int(x[i]) | 1), __int_as_float(__float_as_int(x[i + 1]) | 1));
+    const float2 a = __fmul2_rn(xb, f2s(si)), b = __fmul2_rn(xb, f2s(so));
+    vi[i] = a.x; vi[i + 1] = a.y; vo[i] = b.x; vo[i + 1] = b.y;
+  }
+  uint32_t in0 = cvt8_e2m1(vi[0], vi[1], vi[2], vi[3], vi[4], vi[5], vi[6], vi[7]);
+  uint32_t in1 = cvt8_e2m1(vi[8], vi[9], vi[10], vi[11], vi[12], vi[13], vi[14], vi[15]);
+  uint32_t ow[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) ow[j] = cvt4_e4m3(vo[4 * j], vo[4 * j + 1], vo[4 * j + 2], vo[4 * j + 3]);
+  if (special) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const uint32_t sgn = (uint32_t)__float_as_int(x[i]) >> 31;
+      if (fabsf(x[i]) == c_in) {
+        uint32_t& wd = (i < 8) ? in0 : in1;
+        wd = (wd & ~(0xFu << (4 * (i & 7)))) | ((1u | (sgn << 3)) << (4 * (i & 7)));
+      }
+      if (fabsf(x[i]) == c_out) {
+        uint32_t& wd = ow[i >> 2];
+        wd = (wd & ~(0xFFu << (8 * (i & 3)))) | ((1u | (sgn << 7)) << (8 * (i & 3)));
+      }
+    }
+  }
+  // ---- a zero magnitude carries no sign
+  {
+    const uint32_t a0 = (in0 & 0x77777777u) + 0x77777777u, a1 = (in1 & 0x77777777u) + 0x77777777u;
+    in0 &= (a0 & 0x88888888u) | 0x77777777u;
+    in1 &= (a1 & 0x88888888u) | 0x77777777u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t a = (ow[j] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+      ow[j] &= (a & 0x80808080u) | 0x7F7F7F7Fu;
+    }
+  }
+  // ---- low / high nibbles of the outlier bytes as nibble words, slot select by the mask
+  uint32_t lp[4], hp[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t y4 = ow[j] >> 4, y8 = ow[j] >> 8;
+    lp[j] = (ow[j] & 0x0F0F0F0Fu) | (y4 & 0xF0F0F0F0u);      // byte 0 = low nibbles of elements (0, 1), byte 2 = (2, 3)
+    hp[j] = (y4 & 0x0F0F0F0Fu) | (y8 & 0xF0F0F0F0u);         // same for the high nibbles
+  }
+  const uint32_t nm0 = nibble_mask8(o.mask & 0xFFu), nm1 = nibble_mask8(o.mask >> 8);
+  const uint32_t l0 = __byte_perm(lp[0], lp[1], 0x6420), l1 = __byte_perm(lp[2], lp[3], 0x6420);
+  const uint32_t g0 = __byte_perm(hp[0], hp[1], 0x6420) & nm0, g1 = __byte_perm(hp[2], hp[3], 0x6420) & nm1;
+  o.s0 = (in0 & ~nm0) | (l0 & nm0);
+  o.s1 = (in1 & ~nm1) | (l1 & nm1);
+  // ---- hi nibbles compacted: from the top element down, (acc : next nibble) is funnel-shifted left by 4 for an outlier
+  // and by 0 for an inlier (the shift count is the 4-bit of the element's mask nibble; SHF takes it modulo 32)
+  {
+    const uint32_t a0 = nm0 & 0x44444444u, a1 = nm1 & 0x44444444u;
+    uint32_t acc0 = 0u, acc1 = 0u;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      acc0 = __funnelshift_l(g0 << (4 * (7 - i)), acc0, a0 >> (4 * i));
+      acc1 = __funnelshift_l(g1 << (4 * (7 - i)), acc1, a1 >> (4 * i));
+    }
+    o.h0 = acc0; o.h1 = acc1;
+  }
+  return o;
+}
+
 // cpp/quantize.cuh:88-149 restated: integer-mantissa rounding of one fp32 value.
 __device__ __forceinline__ float qelem_native(float x, int bits, int ebits, float max_norm, int rmode,
                                               bool saturate, bool allow_denorm) {

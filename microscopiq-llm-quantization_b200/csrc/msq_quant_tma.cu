@@ -14,6 +14,7 @@
 // Requirements: cols % 4 == 0 (16-byte global strides), 16-byte aligned bases; otherwise the caller uses k_strided_multi.
 #include "msq_quant_kernels.cuh"
 #include "msq_tc.cuh"
+#include <stdlib.h>
 
 namespace msq {
 
@@ -194,22 +195,9 @@ __device__ __forceinline__ int cons_excl_scan(int v, int* s_warp, int* sum) {
 
 // store_codes4_16 (msq_quant_strided.cu) with the destination in shared memory: cd = the tile's code image, 16 rows of
 // 128 bytes; this warp's 32 columns are bytes [16*warp, 16*warp + 16) of every row
-__device__ __forceinline__ void stage_codes4_16(uint32_t* cd, const uint32_t* c, int lane, int warp) {
+// W0 / W1 = this column's slot nibbles of rows 0-7 / 8-15 (slots_from_codes16)
+__device__ __forceinline__ void stage_slots16(uint32_t* cd, uint32_t W0, uint32_t W1, int lane, int warp) {
   const int g = lane & 7;
-  uint32_t W0, W1;
-  {
-    // four codes (<= 8 bits each) per word by multiply-adds (sums of disjoint bytes), low nibbles kept, adjacent
-    // nibbles merged: byte 0 / byte 2 of t = rows (4j, 4j+1) / (4j+2, 4j+3)
-    uint32_t t[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t w = ((c[4 * j + 3] * 256u + c[4 * j + 2]) * 256u + c[4 * j + 1]) * 256u + c[4 * j];
-      const uint32_t l = w & 0x0F0F0F0Fu;
-      t[j] = l | (l >> 4);
-    }
-    W0 = __byte_perm(t[0], t[1], 0x6420);
-    W1 = __byte_perm(t[2], t[3], 0x6420);
-  }
   {
     const uint32_t r = __shfl_xor_sync(0xffffffffu, (g & 4) ? W0 : W1, 4);
     if (g & 4) W0 = r; else W1 = r;
@@ -231,6 +219,11 @@ __device__ __forceinline__ void stage_codes4_16(uint32_t* cd, const uint32_t* c,
   uint32_t* dst = cd + (2 * g) * 32 + warp * 4 + (lane >> 3);      // 32 words per row
   dst[0] = row_lo;
   dst[32] = row_hi;
+}
+__device__ __forceinline__ void stage_codes4_16(uint32_t* cd, const uint32_t* c, int lane, int warp) {
+  uint32_t W0, W1;
+  slots_from_codes16(c, W0, W1);
+  stage_slots16(cd, W0, W1, lane, warp);
 }
 
 // bitmap of a tile without ballots: the 32 x 16 bit matrix (lane = column, bit = row) is transposed by a 5-stage
@@ -258,7 +251,7 @@ constexpr int TP_NST = 5;      // input ring
 constexpr int TP_NOUT = 3;     // staging buffers of the output planes (a freed buffer is needed one whole tile later)
 constexpr int TP_TW = 256;
 
-template <int BS>
+template <int BS, bool CVT>
 __global__ void __launch_bounds__(TP_TW + 32, 2) k_pack_tma(const __grid_constant__ TmaPackParams P) {
   static_assert(BS == 16, "4-bit slots, 16-row blocks");
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -350,24 +343,30 @@ __global__ void __launch_bounds__(TP_TW + 32, 2) k_pack_tma(const __grid_constan
     mbar_wait_sleep(&full[s], ph);
     const float* tp = tiles + (size_t)s * STAGE_FLOATS + tid;
     float x[BS];
-    uint32_t code[BS];
 #pragma unroll
     for (int i = 0; i < BS; ++i) x[i] = tp[i * TP_TW];
     tc::mbar_arrive(&empty[s]);
-    const BlockOut bo = core_outlier<BS, 1, true, false, true, true>(x, code, P.c, nullptr, nullptr);
+    BlockPk bo;
+    if (CVT) {
+      bo = core_outlier_cvt(x, P.c);
+    } else {
+      uint32_t code[BS];
+      const BlockOut b = core_outlier<BS, 1, true, false, true, true>(x, code, P.c, nullptr, nullptr);
+      slots_from_codes16(code, bo.s0, bo.s1);
+      bo.h0 = b.hacc[0]; bo.h1 = b.hacc[1]; bo.mask = b.mask; bo.e_in = b.e_in; bo.e_out = b.e_out; bo.cnt = b.cnt; bo.st = b.st;
+    }
     st |= bo.st;
     // staging buffer b2 was last used by tile k - TP_NOUT: wait until its stores have read it
     mbar_wait_sleep(&sfree[b2], pf);
     unsigned char* o = outs + (size_t)b2 * OUT_BYTES;
-    stage_codes4_16(reinterpret_cast<uint32_t*>(o), code, lane, warp);
+    stage_slots16(reinterpret_cast<uint32_t*>(o), bo.s0, bo.s1, lane, warp);
     stage_bitmap16(reinterpret_cast<uint32_t*>(o + CD_BYTES) + warp, bo.mask, lane);
     o[CD_BYTES + BM_BYTES + tid] = (unsigned char)(int8_t)bo.e_in;
     o[CD_BYTES + BM_BYTES + EX_BYTES + tid] = (unsigned char)(int8_t)bo.e_out;
     if (hi_w > 0) {
-      // the two 32-bit halves of the block's compacted hi fields (core_outlier<.., HI>), joined by the number of
-      // outliers in the low half
+      // the two 32-bit halves of the block's compacted hi fields, joined by the number of outliers in the low half
       const int sh = __popc(bo.mask & 0xFFu) * hi_w;                       // <= 32
-      s_acc[u * TP_TW + tid] = (unsigned long long)bo.hacc[0] | ((unsigned long long)bo.hacc[1] << sh);
+      s_acc[u * TP_TW + tid] = (unsigned long long)bo.h0 | ((unsigned long long)bo.h1 << sh);
       s_cnt[u * TP_TW + tid] = (unsigned char)bo.cnt;
     }
     fence_proxy_async_smem();
@@ -511,7 +510,12 @@ int launch_pack_tma(const QParams& Q, cudaStream_t stream) {
   P.nseg = (unsigned)((Q.nblocks + MSQ_SEG_BLOCKS - 1) / MSQ_SEG_BLOCKS);
   P.gx = (int)(Q.post / TP_TW);
   magic_div(P.gx, &P.gx_m, &P.gx_k);
-  auto k = k_pack_tma<16>;
+  // the drivers' pairing (fp4_e2m1 inliers, fp8_e4m3 outliers, round to nearest) rounds and encodes by the narrow-format
+  // conversion instructions (core_outlier_cvt); MSQ_PACK_CVT=0 keeps the generic arithmetic for comparison
+  const bool cvt = Q.c.fin.ebits == 2 && Q.c.fin.bits == 3 && Q.c.fin.max_norm == 6.0f && Q.c.fout.ebits == 4 && Q.c.fout.bits == 5 &&
+                   Q.c.fout.max_norm == 448.0f && Q.c.fin.emax == 2 && Q.c.fout.emax == 8 && Q.c.rmode == RD_NEAREST && Q.hi_w == 4 &&
+                   !(getenv("MSQ_PACK_CVT") && getenv("MSQ_PACK_CVT")[0] == '0');
+  auto k = cvt ? k_pack_tma<16, true> : k_pack_tma<16, false>;
   const size_t smem = (size_t)TP_NST * (16 * TP_TW * 4) + TP_NOUT * (16 * (TP_TW / 2) + 16 * (TP_TW / 8) + 2 * TP_TW) +
                       (size_t)MSQ_SEG_BLOCKS * 8 + (size_t)MSQ_SEG_BLOCKS * 16 * 4 / 8 + MSQ_SEG_BLOCKS +
                       (2 * TP_NST + 2 * TP_NOUT) * sizeof(uint64_t) + 8 * sizeof(int) + 64;
