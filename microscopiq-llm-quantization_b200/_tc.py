@@ -514,6 +514,37 @@ N.register("msq_gemm_mxfp8_tma_tile_tokens", _i, [_i, _i, _i])
 N.register("msq_gemm_mxfp8_tma_workspace_bytes", _ll, [_i, _i, _i])
 N.register("msq_gemm_mxfp8_tma", _i, [_p, _ll, _p, _p, _ll, _i, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _p, _ll, _p])
 
+N.register("msq_gemm_mxfp4_tma", _i, [_p, _ll, _p, _p, _ll, _p, _p, _ll, _i, _i, _i, _i, _p, _ll, _p])
+
+
+def packed_linear_mx4(xq, pw, bias=None):
+    """W4A4: y = dq(xq) @ dq(pw).T with BOTH operands as packed FP4 codes on tcgen05 kind::mxf4.block_scale (K = 64 per
+    instruction, twice the rate of kind::mxf8f6f4).  xq: pack_mx(x, 8, 'fp4_e2m1', axes=[-1], block_size=32); pw: a plain
+    FP4 weight packed along K with block 32 (mx4_weight_ok, no outliers).  Replaces F.linear on the two fake-quantized
+    operands of number_system/mx/linear.py:66-91 for a_elem_format = w_elem_format = fp4_e2m1."""
+    from . import _ops
+    Nn, K = pw.shape
+    if xq.shape[-1] != K or xq.block_size != 32 or xq.code_width != 4 or not xq.plain or _ops.fmt4(xq.in_fmt)[:2] != (2, 3):
+        raise NotImplementedError("activations must be MX-FP4 (E2M1) packed along K with block 32")
+    if not (pw.plain and mx4_weight_ok(pw)) or K % 256 != 0:
+        raise NotImplementedError("weight must be a plain MX-FP4 weight packed along K with block 32, K % 256 == 0")
+    M = 1
+    for s_ in xq.shape[:-1]:
+        M *= s_
+    wsf_t = getattr(pw, "_mx4_sf_tiled", None)
+    if wsf_t is None:
+        wsf_t = pw._mx4_sf_tiled = tile_scales(pw.e_in.reshape(Nn, K // 32))
+    out = torch.empty(M, Nn, dtype=torch.float32, device=pw.codes.device)
+    nbytes = int(N.lib().msq_gemm_mxfp8_tma_workspace_bytes(M, Nn, K))
+    ws = _workspace(nbytes, out.device)
+    rc = N.lib().msq_gemm_mxfp4_tma(N.ptr(xq.codes), K // 2, N.ptr(xq.e_in), N.ptr(pw.codes), K // 2, N.ptr(wsf_t), N.ptr(out),
+                                    out.stride(0), M, Nn, K, 0, N.ptr(ws), nbytes, N.stream_ptr(out.device))
+    N.check(rc, "msq_gemm_mxfp4_tma")
+    if bias is not None:
+        out += bias.float()
+    return out.reshape(*xq.shape[:-1], Nn)
+
+
 #: compute-bound sizes (M >= MX8_DENSE_MIN_M): fully TMA-fed kernel (csrc/msq_gemm_mx8_tma.cu)
 MX8_TMA = True
 #: ... with the packed 4-bit codes themselves as the operand when the weight has no outliers (half the L2 -> SMEM bytes)

@@ -24,7 +24,7 @@ namespace msq {
 namespace {
 
 constexpr int YM = 128, YBK = 128, YST = 4, YMAXN = 256, YGROUP = 8;
-constexpr int YA_BYTES = YM * YBK, YB_BYTES = YMAXN * YBK, YSF_BYTES = 512 + 1024;
+constexpr int YA_BYTES = YM * YBK, YB_BYTES = YMAXN * YBK, YSF_BYTES = 1024 + 2048;     // scale chunks of a stage (F4: 256 values of K)
 constexpr int Y_SMEM = YST * (YA_BYTES + YB_BYTES + YSF_BYTES) + 1024 + 256;
 static_assert(Y_SMEM <= 227 * 1024, "shared memory");
 
@@ -69,6 +69,23 @@ __device__ __forceinline__ void mma_bs(uint32_t tmem_d, uint64_t adesc, uint64_t
       : "memory");
 }
 
+// both operands packed FP4 (E2M1, two codes per byte, K-major), one UE8M0 scale per 32 values: K = 64 per instruction, two
+// scale bytes per row and instruction (scale_vec::2X) taken from bytes {0, 1} or {2, 3} of the row's 32-bit cell (sf id 0 / 2)
+__device__ __forceinline__ void mma_f4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                       uint32_t tsfa, uint32_t tsfb) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb)
+      : "memory");
+}
+
+// F4 = true: W4A4 -- the activations are packed FP4 as well (kind::mxf4, twice the tensor rate of kind::mxf8f6f4).  A stage
+// is the same 128 bytes of K per row, i.e. 256 values: two 128-wide scale chunks per operand tile, four K = 64 instructions.
+template <bool F4>
 __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                                                           const YParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -110,7 +127,8 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__
   if (warp == 0) {
     // ---- loads: per stage one weight tile, one activation tile, one + sfb_chunks scale chunks, all on one mbarrier
     int stage = 0; uint32_t phase = 0;
-    const uint32_t tx = (uint32_t)(P.w_tx_bytes + P.bn * YBK + 512 + 512 * P.sfb_chunks);
+    constexpr int KC = F4 ? 2 : 1;                  // 128-wide scale chunks of K per stage
+    const uint32_t tx = (uint32_t)(P.w_tx_bytes + P.bn * YBK + KC * (512 + 512 * P.sfb_chunks));
     // programmatic dependent of k_tile_scales (which releases us at once): everything up to here overlapped it
     if (P.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -119,14 +137,15 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__
       for (int term = 0; term < P.terms; ++term) {
         const uint8_t* xsf = P.xsf_t + ((long long)term * P.tiles_m + tm) * P.kblocks * 512 * P.sfb_chunks;
         const int xrow = term * P.M + tm * P.bn;
-        for (int kb = 0; kb < P.kblocks; ++kb) {
+        for (int kb = 0; kb < P.kblocks / KC; ++kb) {
           tc::mbar_wait(&empty[stage], phase ^ 1);
           if (tc::elect_one()) {
             tc::mbar_expect_tx(&full[stage], tx);
             tc::tma_load_2d(sA + stage * YA_BYTES, &tmW, &full[stage], kb * YBK, tn * YM);
             tc::tma_load_2d(sB + stage * YB_BYTES, &tmX, &full[stage], kb * YBK, xrow);
-            bulk_1d(sSF + stage * YSF_BYTES, wsf + (long long)kb * 512, 512, &full[stage]);
-            bulk_1d(sSF + stage * YSF_BYTES + 512, xsf + (long long)kb * 512 * P.sfb_chunks, 512u * (uint32_t)P.sfb_chunks, &full[stage]);
+            bulk_1d(sSF + stage * YSF_BYTES, wsf + (long long)kb * (512 * KC), 512u * KC, &full[stage]);
+            bulk_1d(sSF + stage * YSF_BYTES + 512 * KC, xsf + (long long)kb * (512 * KC) * P.sfb_chunks,
+                    512u * KC * (uint32_t)P.sfb_chunks, &full[stage]);
           }
           __syncwarp();
           if (++stage == YST) { stage = 0; phase ^= 1; }
@@ -141,25 +160,42 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__
     const uint64_t sfd0 = sf_desc(tc::smem_u32(sSF));
     const uint32_t a_step = (uint32_t)(YA_BYTES >> 4), b_step = (uint32_t)(YB_BYTES >> 4), sf_step = (uint32_t)(YSF_BYTES >> 4);
     // [4,6) b_sf_id  [7,10) A fmt  [10,13) B fmt  [17,23) N>>3  [23] scale fmt (1 = E8M0)  [24,29) M>>4  [29,31) a_sf_id
-    const uint32_t idesc0 = ((uint32_t)P.w_fmt << 7) | ((uint32_t)(P.bn >> 3) << 17) | (1u << 23) | ((uint32_t)(YM >> 4) << 24);
+    // (F4: both formats 1 = E2M1 of kind::mxf4)
+    const uint32_t idesc0 = (F4 ? ((1u << 7) | (1u << 10)) : ((uint32_t)P.w_fmt << 7)) | ((uint32_t)(P.bn >> 3) << 17) | (1u << 23) |
+                            ((uint32_t)(YM >> 4) << 24);
     const uint32_t idesc_k = (1u << 4) | (1u << 29);
-    const uint32_t tsfa = tmem_base + (uint32_t)(P.nacc * P.bn), tsfb = tsfa + 4;
+    // scale-factor columns behind the accumulators: F4 keeps the two K chunks of a stage side by side (A: 4 + 4, B: 8 + 8)
+    const uint32_t tsfa = tmem_base + (uint32_t)(P.nacc * P.bn), tsfb = tsfa + (F4 ? 8 : 4);
+    constexpr int KC = F4 ? 2 : 1;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       tc::mbar_wait(&acc_empty[as], ((acc_phase >> as) & 1u) ^ 1u);
       tc::tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(as * P.bn);
-      for (int kb = 0; kb < P.terms * P.kblocks; ++kb) {
+      for (int kb = 0; kb < P.terms * (P.kblocks / KC); ++kb) {
         tc::mbar_wait(&full[stage], phase);
         tc::tc_fence_after();
         const uint64_t ad = ad0 + (uint64_t)((uint32_t)stage * a_step), bd = bd0 + (uint64_t)((uint32_t)stage * b_step);
         const uint64_t sfd = sfd0 + (uint64_t)((uint32_t)stage * sf_step);
         if (tc::elect_one()) {
-          cp_sf(tsfa, sfd);
-          cp_sf(tsfb, sfd + 32u);
-          if (P.sfb_chunks > 1) cp_sf(tsfb + 4, sfd + 64u);
+          if (F4) {
 #pragma unroll
-          for (int k = 0; k < YBK / 32; ++k)
-            mma_bs(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc0 + (uint32_t)k * idesc_k, (kb | k) != 0, tsfa, tsfb);
+            for (int kc = 0; kc < 2; ++kc) {
+              cp_sf(tsfa + 4u * kc, sfd + 32u * kc);
+              cp_sf(tsfb + 8u * kc, sfd + 64u + 32u * (uint32_t)(kc * P.sfb_chunks));
+              if (P.sfb_chunks > 1) cp_sf(tsfb + 8u * kc + 4u, sfd + 64u + 32u * (uint32_t)(kc * P.sfb_chunks + 1));
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)          // K = 64 each: 32 bytes along the 128-byte row, scale bytes (k & 1) * 2 ..
+              mma_f4(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc0 + (uint32_t)((k & 1) * 2) * idesc_k, (kb | k) != 0,
+                     tsfa + 4u * (uint32_t)(k >> 1), tsfb + 8u * (uint32_t)(k >> 1));
+          } else {
+            cp_sf(tsfa, sfd);
+            cp_sf(tsfb, sfd + 32u);
+            if (P.sfb_chunks > 1) cp_sf(tsfb + 4, sfd + 64u);
+#pragma unroll
+            for (int k = 0; k < YBK / 32; ++k)
+              mma_bs(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc0 + (uint32_t)k * idesc_k, (kb | k) != 0, tsfa, tsfb);
+          }
           tc::umma_commit(&empty[stage]);
         }
         __syncwarp();
@@ -690,7 +726,7 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
     cfg.attrs = at; cfg.numAttrs = P.pdl ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, k_gemm_mx8_tma2, tmXh, tmW, tmXSF, tmWSF, P) == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
   }
-  if (cudaFuncSetAttribute(k_gemm_mx8_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, Y_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
+  if (cudaFuncSetAttribute(k_gemm_mx8_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Y_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
   int grid = P.tiles_n * P.tiles_m;
   if (grid > sms) grid = sms;
   if (getenv("MSQ_MX8_NO_PDL") == nullptr) {
@@ -702,10 +738,60 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_gemm_mx8_tma, tmX, tmW, P) == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+    return cudaLaunchKernelEx(&cfg, k_gemm_mx8_tma<false>, tmX, tmW, P) == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
   }
-  k_gemm_mx8_tma<<<grid, 256, Y_SMEM, s>>>(tmX, tmW, P);
+  k_gemm_mx8_tma<false><<<grid, 256, Y_SMEM, s>>>(tmX, tmW, P);
   return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+}
+
+// W4A4: C[m, n] (+)= sum_k dq(X)[m, k] * dq(W)[n, k] with BOTH operands packed FP4 (E2M1, two codes per byte, low nibble
+// first, K-major) and int8 shared exponents per 32 values of K (activations) / pre-tiled UE8M0 chunks (weight,
+// msq_tile_scales_ue8m0): tcgen05.mma kind::mxf4.block_scale.scale_vec::2X, K = 64 per instruction.  ldx / ldw in BYTES.
+// Workspace as msq_gemm_mxfp8_tma_workspace_bytes(M, N, K).  K % 256 == 0.
+int msq_gemm_mxfp4_tma(const unsigned char* xcodes4, long long ldx, const signed char* xe, const unsigned char* w4, long long ldw,
+                       const unsigned char* wsf_tiled, float* C, long long ldc, int M, int N, int K, int accumulate, void* workspace,
+                       long long workspace_bytes, void* stream) {
+  msq::DevGuard dev_guard_(xcodes4);
+  if (!xcodes4 || !xe || !w4 || !wsf_tiled || !C || !workspace || M <= 0 || N <= 0 || K <= 0) return MSQ_ERR_BAD_ARG;
+  if (K % 256 != 0) return MSQ_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(xe) & 3) || (reinterpret_cast<uintptr_t>(xcodes4) & 15) || (ldx % 16) ||
+      (reinterpret_cast<uintptr_t>(w4) & 15) || (ldw % 16) || (reinterpret_cast<uintptr_t>(wsf_tiled) & 15) ||
+      (reinterpret_cast<uintptr_t>(workspace) & 15))
+    return MSQ_ERR_ALIGN;
+  if (workspace_bytes < msq_gemm_mxfp8_tma_workspace_bytes(M, N, K)) return MSQ_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  YParams P;
+  memset(&P, 0, sizeof(P));
+  // the token-tile width of the workspace query (the tiled activation scales depend on it); the two-CTA plan's width is a
+  // valid one-CTA width as well
+  P.bn = msq_gemm_mxfp8_tma_tile_tokens(M, N, K);
+  P.nacc = P.bn <= 240 ? 2 : 1;
+  P.wsf_t = wsf_tiled; P.xsf_t = reinterpret_cast<const uint8_t*>(workspace); P.C = C; P.ldc = ldc;
+  P.M = M; P.N = N; P.K = K; P.accumulate = accumulate; P.terms = 1;
+  P.tiles_n = (N + YM - 1) / YM; P.tiles_m = (M + P.bn - 1) / P.bn; P.kblocks = K / YBK; P.sfb_chunks = (P.bn + 127) / 128;
+  P.w_tx_bytes = YA_BYTES;
+  int rc = tile_scales(xe, 1, M, K, P.bn, reinterpret_cast<unsigned char*>(workspace), 1, stream);
+  if (rc) return rc;
+  CUtensorMap tmX, tmW;
+  rc = make_tmap_2d(&tmX, xcodes4, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K / 2, ldx, P.bn, YBK);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmW, w4, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K / 2, ldw, YM, YBK);
+  if (rc) return rc;
+  if (cudaFuncSetAttribute(k_gemm_mx8_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Y_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
+  int grid = P.tiles_n * P.tiles_m;
+  if (grid > sms) grid = sms;
+  P.pdl = 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = Y_SMEM; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_gemm_mx8_tma<true>, tmX, tmW, P) == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
 }
 
 }  // extern "C"
