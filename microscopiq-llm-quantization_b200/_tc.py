@@ -517,17 +517,31 @@ N.register("msq_gemm_mxfp8_tma", _i, [_p, _ll, _p, _p, _ll, _i, _p, _p, _p, _p, 
 N.register("msq_gemm_mxfp4_tma", _i, [_p, _ll, _p, _p, _ll, _p, _p, _ll, _i, _i, _i, _i, _p, _ll, _p])
 
 
-def packed_linear_mx4(xq, pw, bias=None):
+#: W4A4 (both operands FP4) runs on kind::mxf4 (msq_gemm_mxfp4_tma); False routes it like any other pairing
+MX4_TMA = True
+
+
+def mx4_pair_ok(pw, K=None):
+    """can this weight be the FP4 operand of the kind::mxf4 kernel?  K-blocked FP4 codes without outliers, K % 256 == 0"""
+    return (MX4_TMA and mx4_weight_ok(pw) and pw.shape[1] % 256 == 0
+            and (pw.plain or mx4_sparse_outliers(pw)[0] is None))
+
+
+def packed_linear_mx4(xq, pw, bias=None, assume_clean=False):
     """W4A4: y = dq(xq) @ dq(pw).T with BOTH operands as packed FP4 codes on tcgen05 kind::mxf4.block_scale (K = 64 per
-    instruction, twice the rate of kind::mxf8f6f4).  xq: pack_mx(x, 8, 'fp4_e2m1', axes=[-1], block_size=32); pw: a plain
-    FP4 weight packed along K with block 32 (mx4_weight_ok, no outliers).  Replaces F.linear on the two fake-quantized
+    instruction, twice the rate of kind::mxf8f6f4).  xq: FP4 (E2M1) activations packed along K with block 32 and no
+    outliers (pack_mx, or pack_mx_outlier with an empty bitmap -- checked here unless assume_clean); pw: an FP4 weight
+    packed along K with block 32, no outliers, K % 256 == 0 (mx4_pair_ok).  Replaces F.linear on the two fake-quantized
     operands of number_system/mx/linear.py:66-91 for a_elem_format = w_elem_format = fp4_e2m1."""
     from . import _ops
     Nn, K = pw.shape
-    if xq.shape[-1] != K or xq.block_size != 32 or xq.code_width != 4 or not xq.plain or _ops.fmt4(xq.in_fmt)[:2] != (2, 3):
+    if (xq.shape[-1] != K or xq.block_size != 32 or xq.code_width != 4 or xq.hi_w != 0 or xq.axis != len(xq.shape) - 1
+            or _ops.fmt4(xq.in_fmt)[:2] != (2, 3)):
         raise NotImplementedError("activations must be MX-FP4 (E2M1) packed along K with block 32")
-    if not (pw.plain and mx4_weight_ok(pw)) or K % 256 != 0:
-        raise NotImplementedError("weight must be a plain MX-FP4 weight packed along K with block 32, K % 256 == 0")
+    if not xq.plain and not assume_clean and bool((xq.bitmap != 0).any()):
+        raise NotImplementedError("activations with outliers of their own cannot feed kind::mxf4")
+    if not mx4_pair_ok(pw):
+        raise NotImplementedError("weight must be an MX-FP4 weight packed along K with block 32, no outliers, K % 256 == 0")
     M = 1
     for s_ in xq.shape[:-1]:
         M *= s_

@@ -44,6 +44,13 @@ def _mx8_activation_ok(x, mx_specs):
             and x.shape[1] // 32 >= 2 and _get_format_params(a)[:2] == (4, 5) and x.dtype == torch.float32)
 
 
+def _mx4_activation_ok(x, mx_specs):
+    from .formats import _get_format_params
+    a = mx_specs["a_elem_format"]
+    return (a is not None and x.dim() == 2 and mx_specs["block_size"] == 32 and x.shape[1] % 256 == 0
+            and _get_format_params(a)[:2] == (2, 3) and x.dtype == torch.float32)
+
+
 def _bf16_exact_activations(mx_specs):
     """are the (fake-quantized) activations exactly representable in bfloat16?  MX element formats with at most 8
     significant bits times a power of two are (fp32 subnormals aside); unquantized activations are when the spec rounds
@@ -69,7 +76,15 @@ def linear_forward(input, weight, bias, mx_specs, packed_weight=None):
         packed_weight = _pack_weight(bf_weight, mx_specs)
     if packed_weight is not None and qis_input.shape[-1] == packed_weight.shape[1]:
         output = None
-        if _mx8_activation_ok(bf_in, mx_specs) and _tc.mx8_weight_ok(packed_weight):
+        if _mx4_activation_ok(bf_in, mx_specs) and _tc.mx4_pair_ok(packed_weight):
+            # W4A4: both operands as packed FP4 codes on kind::mxf4 (twice the tensor rate of the FP8 pairing)
+            sb = mx_specs["scale_bits"] or 4
+            xq = pack_mx_outlier(bf_in, sb, sb, mx_specs["a_elem_format"], mx_specs["a_elem_format"], 5, [1], 32,
+                                 round=mx_specs["round_mx_output"], flush_fp32_subnorms=mx_specs["mx_flush_fp32_subnorms"],
+                                 variant=1)
+            if not bool((xq.bitmap != 0).any()):
+                output = _tc.packed_linear_mx4(xq, packed_weight, assume_clean=True).to(input.dtype)
+        if output is None and _mx8_activation_ok(bf_in, mx_specs) and _tc.mx8_weight_ok(packed_weight):
             # native block-scaled path: needs the activations as MX-FP8 codes with no outliers of their own
             sb = mx_specs["scale_bits"] or 4
             xq = pack_mx_outlier(bf_in, sb, sb, mx_specs["a_elem_format"], mx_specs["a_elem_format"], 5, [1], 32,

@@ -1,0 +1,95 @@
+"""GPU tier: W4A4 on tcgen05.mma kind::mxf4.block_scale (msq_gemm_mxfp4_tma / packed_linear_mx4): both operands packed
+FP4 codes.  Reference = fp64 matmul of the DEQUANTIZED operands (number_system/mx/linear.py:91 multiplies the two
+fake-quantized tensors); products and power-of-two block scales are exact, only fp32 summation order differs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def M():
+    import msq_b200
+    return msq_b200
+
+
+def check(y, x, w):
+    ref = x.double() @ w.double().t()
+    bound = 4 * x.shape[-1] * 2.0 ** -24 * (x.double().abs() @ w.double().abs().t()) + 1e-30
+    bad = ((y.double() - ref).abs() > bound)
+    assert not bool(bad.any()), (int(bad.sum()), float(((y.double() - ref).abs() / bound).max()))
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("Mx,N,K", [(1, 128, 256), (16, 128, 256), (33, 200, 512), (100, 1000, 768), (256, 256, 256),
+                                    (300, 384, 1024), (513, 640, 2048), (1100, 384, 256), (2048, 1024, 512),
+                                    (700, 4096, 4096), (64, 11008, 4096)])
+def test_w4a4_linear(M, Mx, N, K):
+    from msq_b200 import _tc
+    g = torch.Generator().manual_seed(N + K + Mx)
+    W = torch.randn(N, K, generator=g) * 0.02 * torch.logspace(-1, 1, N).unsqueeze(1)
+    x = torch.randn(Mx, K, generator=g) * torch.logspace(-2, 1, Mx).unsqueeze(1)
+    pw = M.pack_mx(W.cuda(), 8, "fp4_e2m1", axes=[1], block_size=32)
+    xq = M.pack_mx(x.cuda(), 8, "fp4_e2m1", axes=[-1], block_size=32)
+    assert _tc.mx4_pair_ok(pw)
+    y = _tc.packed_linear_mx4(xq, pw)
+    assert y.shape == (Mx, N)
+    check(y.cpu(), xq.dequantize().cpu(), pw.dequantize().cpu())
+    # the same operands through the FP8-activation kernel (an FP4 value is an E4M3 value): same sums, other order
+    b = torch.randn(N, generator=g).cuda()
+    yb = _tc.packed_linear_mx4(xq, pw, bias=b)
+    assert torch.allclose(yb, y + b)
+
+
+def test_w4a4_rejects(M):
+    from msq_b200 import _tc
+    g = torch.Generator().manual_seed(5)
+    W = torch.randn(128, 384, generator=g) * 0.02           # K % 256 != 0
+    pw = M.pack_mx(W.cuda(), 8, "fp4_e2m1", axes=[1], block_size=32)
+    xq = M.pack_mx(torch.randn(4, 384, generator=g).cuda(), 8, "fp4_e2m1", axes=[-1], block_size=32)
+    assert not _tc.mx4_pair_ok(pw)
+    with pytest.raises(NotImplementedError):
+        _tc.packed_linear_mx4(xq, pw)
+    W = torch.randn(128, 512, generator=g) * 0.02
+    pw = M.pack_mx(W.cuda(), 8, "fp4_e2m1", axes=[1], block_size=32)
+    x8 = M.pack_mx(torch.randn(4, 512, generator=g).cuda(), 8, "fp8_e4m3", axes=[-1], block_size=32)
+    with pytest.raises(NotImplementedError):                # FP8 activations belong to packed_linear_mx8
+        _tc.packed_linear_mx4(x8, pw)
+    # a weight with outliers of its own is not an mxf4 operand
+    W[3, 5] = 3.0
+    W = W.repeat(1, 4)
+    po = M.pack_mx_outlier(W.cuda(), 8, 8, "fp4_e2m1", "fp4_e2m1", 5, [1], 32, variant=1)
+    if bool((po.bitmap != 0).any()):
+        assert not _tc.mx4_pair_ok(po)
+
+
+@pytest.mark.timeout(300)
+def test_mx_linear_w4a4_route(M):
+    """mx.linear with a_elem_format = w_elem_format = fp4_e2m1 takes the kind::mxf4 kernel and gives the result of the
+    kind::mxf8f6f4 / dequantized routes (linear.py:66-91: F.linear of the fake-quantized operands)"""
+    from msq_b200 import _tc
+    from msq_b200 import mx
+    specs = mx.specs.finalize_mx_specs({"w_elem_format": "fp4_e2m1", "a_elem_format": "fp4_e2m1", "block_size": 32,
+                                        "scale_bits": 8, "bfloat": 0, "custom_cuda": False})
+    g = torch.Generator().manual_seed(11)
+    W = (torch.randn(384, 1024, generator=g) * 0.02).cuda()
+    x = torch.randn(48, 1024, generator=g).cuda()
+    b = torch.randn(384, generator=g).cuda()
+    calls = []
+    orig = _tc.packed_linear_mx4
+
+    def spy(*a, **k):
+        calls.append(1)
+        return orig(*a, **k)
+    _tc.packed_linear_mx4 = spy
+    try:
+        y4 = mx.linear(x, W, b, mx_specs=specs)
+    finally:
+        _tc.packed_linear_mx4 = orig
+    assert calls, "the W4A4 pairing did not reach the kind::mxf4 kernel"
+    _tc.MX4_TMA = False
+    try:
+        y8 = mx.linear(x, W, b, mx_specs=specs)
+    finally:
+        _tc.MX4_TMA = True
+    assert torch.allclose(y4, y8, rtol=1e-5, atol=1e-6 * float(y8.abs().max()))

@@ -144,3 +144,96 @@ def test_multi_segment_roundtrip(M, fi, fo, bs, axis, shape):
     # the oracle on a slice that crosses the first segment boundary
     ref = O.quantize_mx_outlier(W.cpu()[:, :64] if axis == 0 else W.cpu()[:8], 8, 8, fi, fo, 2, axis, bs)
     assert_exact(y[:, :64] if axis == 0 else y[:8], ref, "oracle slice")
+
+
+def _ulp(x, k):
+    return (x.view(torch.int32) + k).view(torch.float32)
+
+
+def _adversarial(kind, L=64, C=256):
+    """inputs aimed at the conversion-instruction core (core_outlier_cvt): exact rounding ties of both formats and their
+    fp32 neighbours, the magnitude below half the smallest subnormal where the reference's fl(|y| + 0.5) rounds up,
+    negative values that round to zero, saturation, zero / constant / all-negative blocks, shared exponents at and
+    beyond the edge of the core's range, non-finite values"""
+    g = torch.Generator().manual_seed(77)
+    if kind == "ties":
+        m = torch.randint(-64, 65, (L, C), generator=g).float() / 16.0
+        j = torch.randint(-12, 6, (L, C), generator=g).float()
+        W = m * torch.exp2(j + torch.randint(-30, 31, (1, C), generator=g).float())
+        d = torch.randint(-1, 2, (L, C), generator=g, dtype=torch.int32)
+        return torch.where(W != 0, (W.view(torch.int32) + d).view(torch.float32), W).contiguous()
+    if kind == "specials":
+        W = torch.randn(L, C, generator=g) * 0.02
+        _, art = O.quantize_mx_outlier(W, 8, 8, "fp4_e2m1", "fp8_e4m3", 2, 0, 16, artefacts=True)
+        e_in = art["e_in"].reshape(L // 16, C).repeat_interleave(16, 0)
+        e_out = art["e_out"].reshape(L // 16, C).repeat_interleave(16, 0)
+        sel = torch.rand(L, C, generator=g)
+        sgn = torch.where(torch.rand(L, C, generator=g) < 0.5, -1.0, 1.0)
+        W = torch.where(sel < 0.05, _ulp(torch.exp2(e_in - 2), -1) * sgn, W)
+        W = torch.where((sel >= 0.05) & (sel < 0.08), torch.exp2(e_in - 2) * sgn, W)
+        W = torch.where((sel >= 0.08) & (sel < 0.11) & (e_out > -100), -_ulp(torch.exp2(e_out - e_in - 10), -1), W)
+        return W.contiguous()
+    if kind == "degenerate":
+        W = torch.randn(L, C, generator=g)
+        W[:, :32] = 0
+        W[:16, 32:64] = 0
+        W[16:32, 64:96] = 1.0
+        W[32:48, 64:96] = -3.0
+        W[:, 96:128] = torch.where(torch.rand(L, 32, generator=g) < 0.5, -1e-9, 1.0)
+        W[:, 128:160] *= torch.exp2(torch.randint(-8, 9, (L, 32), generator=g).float())
+        W[:, 160:192] = -torch.rand(L, 32, generator=g) - 0.5
+        return W.contiguous()
+    if kind == "scales":
+        W = torch.randn(L, C, generator=g)
+        e = torch.cat([torch.randint(-44, -34, (1, C // 4), generator=g), torch.randint(36, 46, (1, C // 4), generator=g),
+                       torch.randint(-120, 110, (1, C // 2), generator=g)], 1).float()
+        W = W * torch.exp2(e)
+        W[:, ::7] *= 2.0 ** 40
+        return torch.nan_to_num(W, posinf=3e38, neginf=-3e38).contiguous()
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["ties", "specials", "degenerate", "scales"])
+def test_pack_conversion_core_vs_oracle(M, kind, monkeypatch):
+    """k_pack_tma<16, CVT> (fp4_e2m1 / fp8_e4m3, nearest: rounding and codes by cvt.rn.satfinite.e2m1x2 / e4m3x2) gives
+    the oracle's mask, exponents and element codes, and the planes of the generic arithmetic, on adversarial inputs"""
+    W = _adversarial(kind)
+    monkeypatch.setenv("MSQ_QUANT_TMA", "1")
+    monkeypatch.delenv("MSQ_PACK_CVT", raising=False)
+    p = M.pack_mx_outlier(W.cuda(), 8, 8, "fp4_e2m1", "fp8_e4m3", 2, [0], 16, check=False)
+    assert p.path == 5
+    monkeypatch.setenv("MSQ_PACK_CVT", "0")
+    r = M.pack_mx_outlier(W.cuda(), 8, 8, "fp4_e2m1", "fp8_e4m3", 2, [0], 16, check=False)
+    assert r.path == 5
+    for name in ("codes", "bitmap", "e_in", "e_out", "seg_cnt"):
+        assert torch.equal(getattr(p, name), getattr(r, name)), name
+    for s in range(p.nseg):
+        nb = (int(p.seg_cnt[s]) * p.hi_w + 7) // 8
+        assert torch.equal(p.hi[s * p.hi_seg_stride: s * p.hi_seg_stride + nb], r.hi[s * p.hi_seg_stride: s * p.hi_seg_stride + nb])
+    assert int(p.status.item()) == int(r.status.item())
+    if kind == "scales":
+        # sums that overflow fp32: the reference asserts (and so does the oracle); the planes are those of the direct-load
+        # kernel (k_strided<.., PACK>, compared with the oracle by the tests above)
+        monkeypatch.setenv("MSQ_QUANT_TMA", "0")
+        d = M.pack_mx_outlier(W.cuda(), 8, 8, "fp4_e2m1", "fp8_e4m3", 2, [0], 16, check=False)
+        assert d.path == 1
+        for name in ("codes", "bitmap", "e_in", "e_out", "seg_cnt"):
+            assert torch.equal(getattr(p, name), getattr(d, name)), name
+        assert int(p.status.item()) == int(d.status.item())
+        return
+    y, art = O.quantize_mx_outlier(W, 8, 8, "fp4_e2m1", "fp8_e4m3", 2, 0, 16, artefacts=True)
+    mask, code = decode_planes(p, M)
+    L, C = W.shape
+    ok = torch.isfinite(y).reshape(L // 16, 16, C).all(1)            # blocks the reference would assert on are NaN in the oracle
+    assert_exact(mask.float()[ok.repeat_interleave(16, 0)], art["mask"][ok.repeat_interleave(16, 0)], "outlier bitmap")
+    assert_exact(p.e_in.view(L // 16, C).float()[ok], art["e_in"].reshape(L // 16, C)[ok], "e_in")
+    q = torch.where(art["mask"].bool(), art["qout"], art["qin"])
+    dec = torch.where(art["mask"].bool(), O.decode_elem(code, "fp8_e4m3"), O.decode_elem(code, "fp4_e2m1"))
+    okE = ok.repeat_interleave(16, 0)
+    assert_exact(dec[okE], q[okE], "element codes")
+    assert_exact(p.dequantize().cpu()[okE], y[okE], "unpack(pack(W))")
+    if kind == "specials":
+        e_in = art["e_in"].reshape(L // 16, C).repeat_interleave(16, 0)
+        hit = (W.abs() == _ulp(torch.exp2(e_in - 2), -1)) & ~art["mask"].bool()
+        assert int(hit.sum()) > 50                    # the patched magnitude really occurs ...
+        assert bool((dec[hit].abs() == 0.5).all())    # ... and rounds UP to the smallest subnormal, as the reference does
