@@ -328,6 +328,26 @@ def extras(dev, dev_w, nel):
         del pw8
         torch.cuda.empty_cache()
     out["blockscaled_mxfp8_gemm_k4096_n4096"] = mx8
+    # (5) W4A4: both operands packed FP4 codes on tcgen05 kind::mxf4.block_scale (msq_gemm_mxfp4_tma)
+    mx4 = {}
+    pw4 = msq_b200.pack_mx(W, 8, "fp4_e2m1", axes=[1], block_size=32)
+    for M in (256, 4096):
+        xq = msq_b200.pack_mx(torch.randn(M, 4096, device=dev), 8, "fp4_e2m1", axes=[-1], block_size=32)
+        ms = _time_ms_device(lambda: _tc.packed_linear_mx4(xq, pw4), 10)
+        mx4["M%d" % M] = {"ms": ms, "TFLOPs": 2.0 * M * 4096 * 4096 / (ms * 1e-3) / 1e12}
+    del pw4
+    W8 = torch.randn(8192, 8192, device=dev) * 0.02
+    pw8 = msq_b200.pack_mx(W8, 8, "fp4_e2m1", axes=[1], block_size=32)
+    del W8
+    xq8 = msq_b200.pack_mx(torch.randn(8192, 8192, device=dev), 8, "fp4_e2m1", axes=[-1], block_size=32)
+    ms = _time_ms(lambda: _tc.packed_linear_mx4(xq8, pw8), 10)
+    tf = 2.0 * 8192.0 ** 3 / (ms * 1e-3) / 1e12
+    mx4["M8192_K8192_N8192"] = {"ms": ms, "TFLOPs": tf, "frac_of_nominal_9000_TFLOPs": tf / 9000.0,
+                                "kernel": "k_gemm_mx8_tma<F4> (kind::mxf4.block_scale.scale_vec::2X, one CTA per 128 x %d tile)"
+                                          % _tc.N.lib().msq_gemm_mxfp8_tma_tile_tokens(8192, 8192, 8192)}
+    del xq8, pw8
+    torch.cuda.empty_cache()
+    out["blockscaled_mxfp4_gemm_w4a4"] = mx4
     return out
 
 

@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__
 // cp.async.bulk.tensor.cta_group::2 that signal the LEADER's mbarrier; tcgen05.commit multicasts the "stage free" /
 // "accumulator full" arrivals to both CTAs; the epilogue warps of both CTAs arrive on the leader's "accumulator free".
 constexpr int ZST = 6;
-constexpr int ZA_BYTES = YM * YBK, ZB_BYTES = (YMAXN / 2) * YBK, ZSF_BYTES = 512 + 1024;
+constexpr int ZA_BYTES = YM * YBK, ZB_BYTES = (YMAXN / 2) * YBK, ZSF_BYTES = 1024 + 2048;
 constexpr int Z_SMEM = ZST * (ZA_BYTES + ZB_BYTES + ZSF_BYTES) + 1024 + 256;
 static_assert(Z_SMEM <= 227 * 1024, "shared memory");
 
@@ -332,6 +332,17 @@ __device__ __forceinline__ void mma_bs2(uint32_t tmem_d, uint64_t adesc, uint64_
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb)
       : "memory");
 }
+__device__ __forceinline__ void mma_f4_2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                         uint32_t tsfa, uint32_t tsfb) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb)
+      : "memory");
+}
 __device__ __forceinline__ void commit2_mc(uint64_t* bar) {       // arrive on `bar` in BOTH CTAs once the MMAs issued so far are done
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                    tc::smem_u32(bar)),
@@ -342,6 +353,7 @@ __device__ __forceinline__ void arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
+template <bool F4>      // F4: both operands packed FP4 on kind::mxf4 (see k_gemm_mx8_tma<true>)
 __global__ void __launch_bounds__(384, 1) k_gemm_mx8_tma2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                                                            const __grid_constant__ CUtensorMap tmXSF,
                                                            const __grid_constant__ CUtensorMap tmWSF, const YParams P) {
@@ -392,7 +404,8 @@ __global__ void __launch_bounds__(384, 1) k_gemm_mx8_tma2(const __grid_constant_
 
   if (warp == 0) {
     int stage = 0; uint32_t phase = 0;
-    const uint32_t tx_cta = (uint32_t)(P.w_tx_bytes + half * YBK + 512 + 512 * P.sfb_chunks);
+    constexpr int KC = F4 ? 2 : 1;
+    const uint32_t tx_cta = (uint32_t)(P.w_tx_bytes + half * YBK + KC * (512 + 512 * P.sfb_chunks));
     if (P.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int t = pair; t < num_tiles; t += npairs) {
       int tn, tm; tile_coords(t, tn, tm);
@@ -401,15 +414,15 @@ __global__ void __launch_bounds__(384, 1) k_gemm_mx8_tma2(const __grid_constant_
       for (int term = 0; term < P.terms; ++term) {
         const int xrow = term * P.M + tm * P.bn + (int)rank * half;
         const int xsf_row = ((term * P.tiles_m + tm) * P.kblocks) * P.sfb_chunks;
-        for (int kb = 0; kb < P.kblocks; ++kb) {
+        for (int kb = 0; kb < P.kblocks / KC; ++kb) {
           mbar_wait_b(&empty[stage], phase ^ 1);
           if (tc::elect_one()) {
             const uint32_t lbar = mapa_u32(tc::smem_u32(&full[stage]), 0);
             if (rank == 0) tc::mbar_expect_tx(&full[stage], 2u * tx_cta);
             tma_load_2d_cg2(sA + stage * ZA_BYTES, &tmW, lbar, kb * YBK, wrow);
             tma_load_2d_cg2(sB + stage * ZB_BYTES, &tmX, lbar, kb * YBK, xrow);
-            tma_load_2d_cg2(sSF + stage * ZSF_BYTES, &tmWSF, lbar, 0, wsf_row + kb);
-            tma_load_2d_cg2(sSF + stage * ZSF_BYTES + 512, &tmXSF, lbar, 0, xsf_row + kb * P.sfb_chunks);
+            tma_load_2d_cg2(sSF + stage * ZSF_BYTES, &tmWSF, lbar, 0, wsf_row + kb * KC);
+            tma_load_2d_cg2(sSF + stage * ZSF_BYTES + 512 * KC, &tmXSF, lbar, 0, xsf_row + kb * KC * P.sfb_chunks);
           }
           __syncwarp();
           if (++stage == ZST) { stage = 0; phase ^= 1; }
@@ -422,25 +435,40 @@ __global__ void __launch_bounds__(384, 1) k_gemm_mx8_tma2(const __grid_constant_
     const uint64_t ad0 = tc::make_kmajor_sw128_desc(tc::smem_u32(sA)), bd0 = tc::make_kmajor_sw128_desc(tc::smem_u32(sB));
     const uint64_t sfd0 = sf_desc(tc::smem_u32(sSF));
     const uint32_t a_step = (uint32_t)(ZA_BYTES >> 4), b_step = (uint32_t)(ZB_BYTES >> 4), sf_step = (uint32_t)(ZSF_BYTES >> 4);
-    const uint32_t idesc0 = ((uint32_t)P.w_fmt << 7) | ((uint32_t)(P.bn >> 3) << 17) | (1u << 23) | ((uint32_t)((2 * YM) >> 4) << 24);
+    const uint32_t idesc0 = (F4 ? ((1u << 7) | (1u << 10)) : ((uint32_t)P.w_fmt << 7)) | ((uint32_t)(P.bn >> 3) << 17) | (1u << 23) |
+                            ((uint32_t)((2 * YM) >> 4) << 24);
     const uint32_t idesc_k = (1u << 4) | (1u << 29);
-    const uint32_t tsfa = tmem_base + (uint32_t)(P.nacc * P.bn), tsfb = tsfa + 4;
+    const uint32_t tsfa = tmem_base + (uint32_t)(P.nacc * P.bn), tsfb = tsfa + (F4 ? 8 : 4);
+    constexpr int KC = F4 ? 2 : 1;
     for (int t = pair; t < num_tiles; t += npairs) {
       mbar_wait_b(&acc_empty[as], ((acc_phase >> as) & 1u) ^ 1u);
       tc::tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(as * P.bn);
-      for (int kb = 0; kb < P.terms * P.kblocks; ++kb) {
+      for (int kb = 0; kb < P.terms * (P.kblocks / KC); ++kb) {
         mbar_wait_b(&full[stage], phase);
         tc::tc_fence_after();
         const uint64_t ad = ad0 + (uint64_t)((uint32_t)stage * a_step), bd = bd0 + (uint64_t)((uint32_t)stage * b_step);
         const uint64_t sfd = sfd0 + (uint64_t)((uint32_t)stage * sf_step);
         if (tc::elect_one()) {
-          cp_sf2(tsfa, sfd);
-          cp_sf2(tsfb, sfd + 32u);
-          if (P.sfb_chunks > 1) cp_sf2(tsfb + 4, sfd + 64u);
+          if (F4) {
 #pragma unroll
-          for (int k = 0; k < YBK / 32; ++k)
-            mma_bs2(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc0 + (uint32_t)k * idesc_k, (kb | k) != 0, tsfa, tsfb);
+            for (int kc = 0; kc < 2; ++kc) {
+              cp_sf2(tsfa + 4u * kc, sfd + 32u * kc);
+              cp_sf2(tsfb + 8u * kc, sfd + 64u + 32u * (uint32_t)(kc * P.sfb_chunks));
+              if (P.sfb_chunks > 1) cp_sf2(tsfb + 8u * kc + 4u, sfd + 64u + 32u * (uint32_t)(kc * P.sfb_chunks + 1));
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_f4_2(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc0 + (uint32_t)((k & 1) * 2) * idesc_k, (kb | k) != 0,
+                       tsfa + 4u * (uint32_t)(k >> 1), tsfb + 8u * (uint32_t)(k >> 1));
+          } else {
+            cp_sf2(tsfa, sfd);
+            cp_sf2(tsfb, sfd + 32u);
+            if (P.sfb_chunks > 1) cp_sf2(tsfb + 4, sfd + 64u);
+#pragma unroll
+            for (int k = 0; k < YBK / 32; ++k)
+              mma_bs2(tacc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc0 + (uint32_t)k * idesc_k, (kb | k) != 0, tsfa, tsfb);
+          }
           commit2_mc(&empty[stage]);
         }
         __syncwarp();
@@ -710,7 +738,7 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
     if (rc) return rc;
     rc = make_tmap_sf(&tmWSF, wsf_tiled, (long long)((N + YM - 1) / YM) * P.kblocks, 1);
     if (rc) return rc;
-    if (cudaFuncSetAttribute(k_gemm_mx8_tma2, cudaFuncAttributeMaxDynamicSharedMemorySize, Z_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
+    if (cudaFuncSetAttribute(k_gemm_mx8_tma2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Z_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
     int pairs = P.tiles_n * P.tiles_m;
     if (pairs > sms / 2) pairs = sms / 2;
     P.pdl = getenv("MSQ_MX8_NO_PDL") == nullptr ? 1 : 0;
@@ -724,7 +752,7 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = P.pdl ? 2 : 1;
-    return cudaLaunchKernelEx(&cfg, k_gemm_mx8_tma2, tmXh, tmW, tmXSF, tmWSF, P) == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+    return cudaLaunchKernelEx(&cfg, k_gemm_mx8_tma2<false>, tmXh, tmW, tmXSF, tmWSF, P) == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
   }
   if (cudaFuncSetAttribute(k_gemm_mx8_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Y_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
   int grid = P.tiles_n * P.tiles_m;
@@ -765,10 +793,8 @@ int msq_gemm_mxfp4_tma(const unsigned char* xcodes4, long long ldx, const signed
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   YParams P;
   memset(&P, 0, sizeof(P));
-  // the token-tile width of the workspace query (the tiled activation scales depend on it); the two-CTA plan's width is a
-  // valid one-CTA width as well
-  P.bn = msq_gemm_mxfp8_tma_tile_tokens(M, N, K);
-  P.nacc = P.bn <= 240 ? 2 : 1;
+  int cta2 = 0;
+  plan(M, N, K, sms, P.bn, P.nacc, cta2);       // same plan as the workspace query (the tiled activation scales depend on bn)
   P.wsf_t = wsf_tiled; P.xsf_t = reinterpret_cast<const uint8_t*>(workspace); P.C = C; P.ldc = ldc;
   P.M = M; P.N = N; P.K = K; P.accumulate = accumulate; P.terms = 1;
   P.tiles_n = (N + YM - 1) / YM; P.tiles_m = (M + P.bn - 1) / P.bn; P.kblocks = K / YBK; P.sfb_chunks = (P.bn + 127) / 128;
@@ -780,6 +806,31 @@ int msq_gemm_mxfp4_tma(const unsigned char* xcodes4, long long ldx, const signed
   if (rc) return rc;
   rc = make_tmap_2d(&tmW, w4, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K / 2, ldw, YM, YBK);
   if (rc) return rc;
+  if (cta2) {
+    P.tiles_n = (N + 2 * YM - 1) / (2 * YM);
+    CUtensorMap tmXh, tmXSF, tmWSF;
+    rc = make_tmap_2d(&tmXh, xcodes4, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K / 2, ldx, P.bn / 2, YBK);
+    if (rc) return rc;
+    rc = make_tmap_sf(&tmXSF, workspace, (long long)P.tiles_m * P.kblocks * P.sfb_chunks, 2 * P.sfb_chunks);
+    if (rc) return rc;
+    rc = make_tmap_sf(&tmWSF, wsf_tiled, (long long)((N + YM - 1) / YM) * P.kblocks, 2);
+    if (rc) return rc;
+    if (cudaFuncSetAttribute(k_gemm_mx8_tma2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Z_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
+    int pairs = P.tiles_n * P.tiles_m;
+    if (pairs > sms / 2) pairs = sms / 2;
+    P.pdl = 1;
+    P.epi_h = 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * pairs)); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = Z_SMEM; cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    return cudaLaunchKernelEx(&cfg, k_gemm_mx8_tma2<true>, tmXh, tmW, tmXSF, tmWSF, P) == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+  }
   if (cudaFuncSetAttribute(k_gemm_mx8_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Y_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
   int grid = P.tiles_n * P.tiles_m;
   if (grid > sms) grid = sms;

@@ -25,19 +25,32 @@ for (M, Nn, K) in shapes:
     x *= torch.exp2(torch.randint(-3, 4, (M, 1), device='cuda', generator=g).float())
     pw = msq_b200.pack_mx(W, 8, 'fp4_e2m1', axes=[1], block_size=32)
     x4 = msq_b200.pack_mx(x, 8, 'fp4_e2m1', axes=[-1], block_size=32)
+    os.environ["MSQ_MX8T_CTA2"] = "0"
+    y1 = _tc.packed_linear_mx4(x4, pw)
+    os.environ["MSQ_MX8T_CTA2"] = "1"
+    y2 = _tc.packed_linear_mx4(x4, pw) if M >= 32 else y1
+    os.environ.pop("MSQ_MX8T_CTA2")
     y = _tc.packed_linear_mx4(x4, pw)
     torch.cuda.synchronize()
+    if not (torch.equal(y1, y2) and (torch.equal(y, y1))):
+        ok = False
+        print("   one-CTA / two-CTA results differ: max abs %g" % float((y1 - y2).abs().max()))
     ref = x4.dequantize().double() @ pw.dequantize().double().t()
     err = float((y.double() - ref).abs().max() / ref.abs().max())
     good = err < 2e-6
     ok = ok and good
     line = "M %5d N %5d K %5d: max rel err vs fp64 matmul of the dequantized operands %.2e %s" % (M, Nn, K, err, "ok" if good else "WRONG")
     if M >= 2048:
+        os.environ["MSQ_MX8T_CTA2"] = "0"
+        t41 = tm(lambda: _tc.packed_linear_mx4(x4, pw))
+        os.environ["MSQ_MX8T_CTA2"] = "1"
         t4 = tm(lambda: _tc.packed_linear_mx4(x4, pw))
+        os.environ.pop("MSQ_MX8T_CTA2")
+        line += " | mxf4 one CTA %.3f ms %.0f TF" % (t41, 2.0 * M * Nn * K / t41 / 1e9)
         x8 = msq_b200.pack_mx(x, 8, 'fp8_e4m3', axes=[-1], block_size=32)
         t8 = tm(lambda: _tc.packed_linear_mx8(x8, pw))
         fl = 2.0 * M * Nn * K
-        line += " | mxf4 %.3f ms %.0f TF | mxf8f6f4 (A8) %.3f ms %.0f TF" % (t4, fl / t4 / 1e9, t8, fl / t8 / 1e9)
+        line += " | two CTAs %.3f ms %.0f TF | mxf8f6f4 (A8) %.3f ms %.0f TF" % (t4, fl / t4 / 1e9, t8, fl / t8 / 1e9)
     print(line, flush=True)
 print("all ok:", ok)
 sys.exit(0 if ok else 1)
