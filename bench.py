@@ -343,8 +343,8 @@ def extras(dev, dev_w, nel):
     ms = _time_ms(lambda: _tc.packed_linear_mx4(xq8, pw8), 10)
     tf = 2.0 * 8192.0 ** 3 / (ms * 1e-3) / 1e12
     mx4["M8192_K8192_N8192"] = {"ms": ms, "TFLOPs": tf, "frac_of_nominal_9000_TFLOPs": tf / 9000.0,
-                                "kernel": "k_gemm_mx8_tma<F4> (kind::mxf4.block_scale.scale_vec::2X, one CTA per 128 x %d tile)"
-                                          % _tc.N.lib().msq_gemm_mxfp8_tma_tile_tokens(8192, 8192, 8192)}
+                                "kernel": "k_gemm_mx8_tma2<F4> (kind::mxf4.block_scale.scale_vec::2X, cta_group::2, 256 x %d tiles)"
+                                          % _tc.N.lib().msq_gemm_mxfp4_tma_tile_tokens(8192, 8192, 8192)}
     del xq8, pw8
     torch.cuda.empty_cache()
     out["blockscaled_mxfp4_gemm_w4a4"] = mx4

@@ -337,10 +337,12 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
                        void* workspace, long long workspace_bytes, void* stream);
 /* W4A4 (replaces F.linear on the two fake-quantized operands of number_system/mx/linear.py:66-91 when a_elem_format and
  * w_elem_format are both fp4_e2m1): BOTH operands packed FP4 (two codes per byte, low nibble = lower k, K-major; ldx / ldw in
- * bytes), activations with int8 shared exponents [M, K/32] (tiled into `workspace` like msq_gemm_mxfp8_tma), weight with
+ * bytes), activations with int8 shared exponents [M, K/32] (tiled into `workspace`, msq_gemm_mxfp4_tma_workspace_bytes), weight with
  * pre-tiled UE8M0 chunks: tcgen05.mma kind::mxf4.block_scale.scale_vec::2X (K = 64 per instruction, twice the tensor rate
  * of kind::mxf8f6f4).  Products and fp32 accumulation as the tensor core does them: equal to the fp32 matmul of the
  * dequantized operands up to summation order.  K % 256 == 0; 16-byte aligned operands and pitches. */
+int msq_gemm_mxfp4_tma_tile_tokens(int M, int N, int K);
+long long msq_gemm_mxfp4_tma_workspace_bytes(int M, int N, int K);
 int msq_gemm_mxfp4_tma(const unsigned char* xcodes4, long long ldx, const signed char* xe, const unsigned char* w4,
                        long long ldw, const unsigned char* wsf_tiled, float* C, long long ldc, int M, int N, int K,
                        int accumulate, void* workspace, long long workspace_bytes, void* stream);

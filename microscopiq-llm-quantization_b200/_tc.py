@@ -514,6 +514,8 @@ N.register("msq_gemm_mxfp8_tma_tile_tokens", _i, [_i, _i, _i])
 N.register("msq_gemm_mxfp8_tma_workspace_bytes", _ll, [_i, _i, _i])
 N.register("msq_gemm_mxfp8_tma", _i, [_p, _ll, _p, _p, _ll, _i, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _p, _ll, _p])
 
+N.register("msq_gemm_mxfp4_tma_tile_tokens", _i, [_i, _i, _i])
+N.register("msq_gemm_mxfp4_tma_workspace_bytes", _ll, [_i, _i, _i])
 N.register("msq_gemm_mxfp4_tma", _i, [_p, _ll, _p, _p, _ll, _p, _p, _ll, _i, _i, _i, _i, _p, _ll, _p])
 
 
@@ -549,7 +551,7 @@ def packed_linear_mx4(xq, pw, bias=None, assume_clean=False):
     if wsf_t is None:
         wsf_t = pw._mx4_sf_tiled = tile_scales(pw.e_in.reshape(Nn, K // 32))
     out = torch.empty(M, Nn, dtype=torch.float32, device=pw.codes.device)
-    nbytes = int(N.lib().msq_gemm_mxfp8_tma_workspace_bytes(M, Nn, K))
+    nbytes = int(N.lib().msq_gemm_mxfp4_tma_workspace_bytes(M, Nn, K))
     ws = _workspace(nbytes, out.device)
     rc = N.lib().msq_gemm_mxfp4_tma(N.ptr(xq.codes), K // 2, N.ptr(xq.e_in), N.ptr(pw.codes), K // 2, N.ptr(wsf_t), N.ptr(out),
                                     out.stride(0), M, Nn, K, 0, N.ptr(ws), nbytes, N.stream_ptr(out.device))

@@ -584,10 +584,10 @@ __global__ void __launch_bounds__(256) k_sparse_outlier_corr(const int* __restri
 
 // token-tile width: fewest (waves over the SMs) x (bytes a tile pulls into shared memory) -- the kernel is bound by the
 // L2 -> shared-memory fill, not by the tensor pipe; one accumulator (BN = 256) pays its exposed epilogue
-static void choose_bn(int M, int N, int K, int sms, int& bn, int& nacc) {
+static void choose_bn(int M, int N, int K, int sms, int& bn, int& nacc, bool f4 = false) {
   if (const char* e = getenv("MSQ_MX8T_BN")) {
     const int v = atoi(e);
-    if (v >= 16 && v <= 256 && v % 16 == 0) { bn = v; nacc = v <= 240 ? 2 : 1; return; }
+    if (v >= 16 && v <= 256 && v % 16 == 0) { bn = v; nacc = v <= 240 ? 2 : 1; return; }      // (A/B switch)
   }
   const int tiles_n = (N + YM - 1) / YM;
   const double kblocks = (K + YBK - 1) / YBK;
@@ -596,6 +596,9 @@ static void choose_bn(int M, int N, int K, int sms, int& bn, int& nacc) {
   const int cand[] = {256, 240, 224, 208, 192, 176, 160, 144, 128, 112, 96, 80, 64, 48, 32, 16};
   for (int c : cand) {
     if (c > 16 && c - 16 >= M) continue;                 // a narrower tile already holds every token
+    // kind::mxf4: a tile's MMAs take half as long, the exposed drain of a single accumulator costs twice as much
+    // (8192^3: 4.66 PFLOP/s at 256, 5.4-5.6 at 240 / 224)
+    if (f4 && c > 240) continue;
     const long long tiles = (long long)tiles_n * ((M + c - 1) / c);
     const double waves = (double)((tiles + sms - 1) / sms);
     const double cost = waves * (kblocks * (YA_BYTES + c * YBK + 4096.0) + (c > 240 ? 135000.0 : 0.0));
@@ -618,14 +621,14 @@ static int make_tmap_sf(CUtensorMap* out, const void* base, long long rows, int 
 }
 
 // which kernel and which token-tile width a problem gets (shared by the GEMM and the workspace / tile-width queries)
-static void plan(int M, int N, int K, int sms, int& bn, int& nacc, int& cta2) {
+static void plan(int M, int N, int K, int sms, int& bn, int& nacc, int& cta2, bool f4 = false) {
   // measured (plain FP4 weight, 4096^2 / 8192^2): M = 64: 10.0 / 16.8 us one CTA, 10.6 / 17.0 us pairs; M = 256: 12.8 / 23.1 vs
   // 11.8 / 19.7; M = 4096: 65.1 / 243.9 vs 55.6 / 201.0 -- pairs from 256 tokens on (MSQ_MX8T_CTA2 = 0 / 1 forces a form)
   const char* e = getenv("MSQ_MX8T_CTA2");
   cta2 = e ? (e[0] == '1') : (M >= 256 && N >= 512);
   if (sms < 2) cta2 = 0;
-  if (cta2) choose_bn(M, ((N + 2 * YM - 1) / (2 * YM)) * YM, K, sms / 2, bn, nacc);       // pairs of CTAs over 256-row tiles
-  else choose_bn(M, N, K, sms, bn, nacc);
+  if (cta2) choose_bn(M, ((N + 2 * YM - 1) / (2 * YM)) * YM, K, sms / 2, bn, nacc, f4);       // pairs of CTAs over 256-row tiles
+  else choose_bn(M, N, K, sms, bn, nacc, f4);
 }
 
 }  // namespace
@@ -679,6 +682,21 @@ int msq_gemm_mxfp8_tma_tile_tokens(int M, int N, int K) {
   int cta2;
   plan(M, N, K, sms, bn, nacc, cta2);
   return bn;
+}
+
+static int tile_tokens(int M, int N, int K, bool f4) {
+  int dev = 0, sms = 148, bn, nacc, cta2;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 148; }
+  plan(M, N, K, sms, bn, nacc, cta2, f4);
+  return bn;
+}
+int msq_gemm_mxfp4_tma_tile_tokens(int M, int N, int K) { return tile_tokens(M, N, K, true); }
+long long msq_gemm_mxfp4_tma_workspace_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  const int bn = tile_tokens(M, N, K, true);
+  const long long tiles_m = (M + bn - 1) / bn, kblocks = (K + YBK - 1) / YBK, chunks = (bn + 127) / 128;
+  return tiles_m * kblocks * chunks * 512 + 1024;
 }
 
 // bytes for the tiled activation scales of up to three stacked terms
@@ -775,7 +793,7 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
 // W4A4: C[m, n] (+)= sum_k dq(X)[m, k] * dq(W)[n, k] with BOTH operands packed FP4 (E2M1, two codes per byte, low nibble
 // first, K-major) and int8 shared exponents per 32 values of K (activations) / pre-tiled UE8M0 chunks (weight,
 // msq_tile_scales_ue8m0): tcgen05.mma kind::mxf4.block_scale.scale_vec::2X, K = 64 per instruction.  ldx / ldw in BYTES.
-// Workspace as msq_gemm_mxfp8_tma_workspace_bytes(M, N, K).  K % 256 == 0.
+// Workspace: msq_gemm_mxfp4_tma_workspace_bytes(M, N, K).  K % 256 == 0.
 int msq_gemm_mxfp4_tma(const unsigned char* xcodes4, long long ldx, const signed char* xe, const unsigned char* w4, long long ldw,
                        const unsigned char* wsf_tiled, float* C, long long ldc, int M, int N, int K, int accumulate, void* workspace,
                        long long workspace_bytes, void* stream) {
@@ -786,7 +804,7 @@ int msq_gemm_mxfp4_tma(const unsigned char* xcodes4, long long ldx, const signed
       (reinterpret_cast<uintptr_t>(w4) & 15) || (ldw % 16) || (reinterpret_cast<uintptr_t>(wsf_tiled) & 15) ||
       (reinterpret_cast<uintptr_t>(workspace) & 15))
     return MSQ_ERR_ALIGN;
-  if (workspace_bytes < msq_gemm_mxfp8_tma_workspace_bytes(M, N, K)) return MSQ_ERR_BAD_ARG;
+  if (workspace_bytes < msq_gemm_mxfp4_tma_workspace_bytes(M, N, K)) return MSQ_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -794,7 +812,7 @@ int msq_gemm_mxfp4_tma(const unsigned char* xcodes4, long long ldx, const signed
   YParams P;
   memset(&P, 0, sizeof(P));
   int cta2 = 0;
-  plan(M, N, K, sms, P.bn, P.nacc, cta2);       // same plan as the workspace query (the tiled activation scales depend on bn)
+  plan(M, N, K, sms, P.bn, P.nacc, cta2, true);       // same plan as the workspace query (the tiled activation scales depend on bn)
   P.wsf_t = wsf_tiled; P.xsf_t = reinterpret_cast<const uint8_t*>(workspace); P.C = C; P.ldc = ldc;
   P.M = M; P.N = N; P.K = K; P.accumulate = accumulate; P.terms = 1;
   P.tiles_n = (N + YM - 1) / YM; P.tiles_m = (M + P.bn - 1) / P.bn; P.kblocks = K / YBK; P.sfb_chunks = (P.bn + 127) / 128;

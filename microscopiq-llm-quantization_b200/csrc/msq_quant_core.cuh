@@ -34,6 +34,9 @@ struct QCfg {
   // "code >> slot width" into a multiply-high
   float mu_i, mu_o;
   unsigned int hi_mulhi;
+  // core_outlier_cvt: |shared exponent| limits of the conversion path (min(40, S_in) / min(80, S_out)) and the clamped
+  // exponents the reference gives a block whose inlier / outlier maximum is zero
+  int cvt_lim_in, cvt_lim_out, e_zero_in, e_zero_out;
 };
 
 // |q| on the format grid times sc lands in fp32's own subnormal / lowest-normal range in such a way that the fp32 bit
@@ -72,6 +75,16 @@ __host__ inline void finish_cfg(QCfg& c) {
     memcpy(&c.mu_i, &one, 4);
     memcpy(&c.mu_o, &mo, 4);
     c.hi_mulhi = 1u << (32 - c.fin.width);
+  }
+  {
+    // floor_log2_or_min(0) = -126; clamp_scale_sel(e, S, U): e < -S -> U, e > S -> NaN marker
+    const int S_in = (1 << (c.sb_in - 1)) - 1, S_out = (1 << (c.sb_out - 1)) - 1;
+    const int U_in = (c.variant == 0 && S_in > 20) ? -20 : -S_in, U_out = (c.variant == 0 && S_out > 20) ? -20 : -S_out;
+    c.cvt_lim_in = S_in < 40 ? S_in : 40;
+    c.cvt_lim_out = S_out < 80 ? S_out : 80;
+    const int z_in = -126 - c.fin.emax, z_out = -126 - c.fout.emax;
+    c.e_zero_in = z_in < -S_in ? U_in : z_in;
+    c.e_zero_out = z_out < -S_out ? U_out : z_out;
   }
 }
 
@@ -217,6 +230,13 @@ __device__ __forceinline__ uint32_t fset_lt_u32(float a, float b) {
 __device__ __forceinline__ float fset_lt(float a, float b) {
   float d;
   asm("set.lt.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+
+// (x < lo) || (x > hi) as 1.0f / 0.0f in TWO logic-pipe instructions (FSETP + FSET with the predicate as third operand)
+__device__ __forceinline__ float fset_outside(float x, float lo, float hi) {
+  float d;
+  asm("{\n.reg .pred p;\nsetp.lt.f32 p, %1, %2;\nset.gt.or.f32.f32 %0, %1, %3, p;\n}\n" : "=f"(d) : "f"(x), "f"(lo), "f"(hi));
   return d;
 }
 
@@ -663,8 +683,8 @@ __device__ __forceinline__ BlockPk core_outlier_cvt(const float (&x)[16], const 
   float2 lo2 = f2s(0.0f);
 #pragma unroll
   for (int i = 0; i < N; i += 2) {
-    mf[i] = fmaxf(fset_lt(x[i], l), fset_gt(x[i], h));
-    mf[i + 1] = fmaxf(fset_lt(x[i + 1], l), fset_gt(x[i + 1], h));
+    mf[i] = fset_outside(x[i], l, h);
+    mf[i + 1] = fset_outside(x[i + 1], l, h);
     const float2 m = f2(mf[i], mf[i + 1]), xv = f2(x[i], x[i + 1]);
     lo2 = __ffma2_rn(m, f2((float)(1u << i), (float)(2u << i)), lo2);
     const float2 nm = __ffma2_rn(m, f2s(-1.0f), f2s(1.0f));
@@ -675,17 +695,18 @@ __device__ __forceinline__ BlockPk core_outlier_cvt(const float (&x)[16], const 
   o.mask = __float2uint_rz(__fadd_rn(lo2.x, lo2.y));
   o.cnt = __popc(o.mask);
   // ---- shared exponents exactly as core_outlier; decide whether this block is on the conversion path
-  const int S_in = (1 << (c.sb_in - 1)) - 1, S_out = (1 << (c.sb_out - 1)) - 1;
-  const int U_in = (c.variant == 0 && S_in > 20) ? -20 : -S_in, U_out = (c.variant == 0 && S_out > 20) ? -20 : -S_out;
-  const int er_in = floor_log2_or_min(m_in) - c.fin.emax;
-  o.e_in = clamp_scale_sel(er_in, S_in, U_in);
+  // ---- shared exponents.  On the conversion path both maxima are fp32 normals well inside the range, so floor(log2) is the
+  // exponent field and the clamp of the scale width cannot bind (range limits c.cvt_lim_* = min(40 / 80, S), finish_cfg);
+  // a block of zeros (padding) and a block without outliers get the clamped "exponent of zero" the reference computes
+  const int er_in = (__float_as_int(m_in) >> 23) - 127 - 2;                     // fp4_e2m1: emax = 2
   const bool zero_in = (m_in == 0.0f) && (o.mask == 0u);       // nothing but zeros: every code is 0 whatever the scale
-  bool fast = !bad && ((o.e_in == er_in && er_in >= -40 && er_in <= 40) || zero_in);
+  bool fast = !bad && ((er_in >= -c.cvt_lim_in && er_in <= c.cvt_lim_in) || zero_in);
   const int e_in = zero_in ? 0 : er_in;
+  o.e_in = zero_in ? c.e_zero_in : er_in;
   // max |t * 2^e_in| = (max |t|) * 2^e_in: scaling by a power of two is monotone (and exact in this range)
-  const int er_out = floor_log2_or_min(__fmul_rn(m_out, pow2i(fast ? e_in : 0))) - c.fout.emax;
-  o.e_out = clamp_scale_sel(er_out, S_out, U_out);
-  fast = fast && (o.mask == 0u || (o.e_out == er_out && er_out >= -80 && er_out <= 80));
+  const int er_out = (__float_as_int(__fmul_rn(m_out, pow2i(fast ? e_in : 0))) >> 23) - 127 - 8;      // fp8_e4m3: emax = 8
+  o.e_out = o.mask == 0u ? c.e_zero_out : er_out;
+  fast = fast && (o.mask == 0u || (er_out >= -c.cvt_lim_out && er_out <= c.cvt_lim_out));
   if (!fast) {
     float xc[N];
     uint32_t code[N];
