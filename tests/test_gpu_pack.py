@@ -237,3 +237,23 @@ def test_pack_conversion_core_vs_oracle(M, kind, monkeypatch):
         hit = (W.abs() == _ulp(torch.exp2(e_in - 2), -1)) & ~art["mask"].bool()
         assert int(hit.sum()) > 50                    # the patched magnitude really occurs ...
         assert bool((dec[hit].abs() == 0.5).all())    # ... and rounds UP to the smallest subnormal, as the reference does
+
+
+@pytest.mark.parametrize("sb", [4, 5, 6])
+@pytest.mark.parametrize("kind", ["ties", "degenerate"])
+def test_pack_conversion_core_narrow_scales(M, kind, sb, monkeypatch):
+    """scale widths whose clamp binds inside the conversion core's exponent range: those blocks must take the generic
+    arithmetic (clamped exponents, overflow status) -- planes and status equal to the generic kernel's"""
+    W = _adversarial(kind).cuda()
+    monkeypatch.setenv("MSQ_QUANT_TMA", "1")
+    monkeypatch.delenv("MSQ_PACK_CVT", raising=False)
+    p = M.pack_mx_outlier(W, sb, sb, "fp4_e2m1", "fp8_e4m3", 2, [0], 16, check=False)
+    monkeypatch.setenv("MSQ_PACK_CVT", "0")
+    r = M.pack_mx_outlier(W, sb, sb, "fp4_e2m1", "fp8_e4m3", 2, [0], 16, check=False)
+    assert p.path == 5 and r.path == 5
+    for name in ("codes", "bitmap", "e_in", "e_out", "seg_cnt"):
+        assert torch.equal(getattr(p, name), getattr(r, name)), name
+    for s in range(p.nseg):
+        nb = (int(p.seg_cnt[s]) * p.hi_w + 7) // 8
+        assert torch.equal(p.hi[s * p.hi_seg_stride: s * p.hi_seg_stride + nb], r.hi[s * p.hi_seg_stride: s * p.hi_seg_stride + nb])
+    assert int(p.status.item()) == int(r.status.item())
