@@ -327,6 +327,10 @@ int msq_gemm_mxfp8_dense(const unsigned char* xcodes, long long ldx, const signe
 int msq_sparse_outlier_correct(const unsigned char* xcodes, long long ldx, const signed char* xe, const int* o_n,
                                const int* o_k, const float* o_dw, int nnz, float* C, long long ldc, int M, int K,
                                int fold_m, void* stream);
+/* the same behind the W4A4 GEMM (msq_gemm_mxfp4_tma): xcodes4 = packed FP4 activations, ldx in bytes */
+int msq_sparse_outlier_correct_fp4(const unsigned char* xcodes4, long long ldx, const signed char* xe, const int* o_n,
+                                   const int* o_k, const float* o_dw, int nnz, float* C, long long ldc, int M, int K,
+                                   int fold_m, void* stream);
 int msq_tile_scales_ue8m0(const void* scales, int is_int8_exponent, int rows, int K, int rows_per_tile,
                           unsigned char* out, void* stream);
 int msq_gemm_mxfp8_tma_tile_tokens(int M, int N, int K);

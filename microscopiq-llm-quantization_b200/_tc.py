@@ -514,6 +514,7 @@ N.register("msq_gemm_mxfp8_tma_tile_tokens", _i, [_i, _i, _i])
 N.register("msq_gemm_mxfp8_tma_workspace_bytes", _ll, [_i, _i, _i])
 N.register("msq_gemm_mxfp8_tma", _i, [_p, _ll, _p, _p, _ll, _i, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _p, _ll, _p])
 
+N.register("msq_sparse_outlier_correct_fp4", _i, [_p, _ll, _p, _p, _p, _p, _i, _p, _ll, _i, _i, _i, _p])
 N.register("msq_gemm_mxfp4_tma_tile_tokens", _i, [_i, _i, _i])
 N.register("msq_gemm_mxfp4_tma_workspace_bytes", _ll, [_i, _i, _i])
 N.register("msq_gemm_mxfp4_tma", _i, [_p, _ll, _p, _p, _ll, _p, _p, _ll, _i, _i, _i, _i, _p, _ll, _p])
@@ -523,10 +524,16 @@ N.register("msq_gemm_mxfp4_tma", _i, [_p, _ll, _p, _p, _ll, _p, _p, _ll, _i, _i,
 MX4_TMA = True
 
 
-def mx4_pair_ok(pw, K=None):
-    """can this weight be the FP4 operand of the kind::mxf4 kernel?  K-blocked FP4 codes without outliers, K % 256 == 0"""
-    return (MX4_TMA and mx4_weight_ok(pw) and pw.shape[1] % 256 == 0
-            and (pw.plain or mx4_sparse_outliers(pw)[0] is None))
+def mx4_pair_ok(pw, M=1):
+    """can this weight be the FP4 operand of the kind::mxf4 kernel for M tokens?  K-blocked FP4 codes (outliers in FP4 as
+    well: they become a sparse correction behind the GEMM while outliers x tokens stays within the budget of the FP8
+    pairing), K % 256 == 0"""
+    if not (MX4_TMA and mx4_weight_ok(pw) and pw.shape[1] % 256 == 0):
+        return False
+    if pw.plain:
+        return True
+    o_k = mx4_sparse_outliers(pw)[1]
+    return o_k is None or o_k.numel() * float(M) <= MX8_TMA_SPARSE_BUDGET
 
 
 def packed_linear_mx4(xq, pw, bias=None, assume_clean=False):
@@ -542,11 +549,11 @@ def packed_linear_mx4(xq, pw, bias=None, assume_clean=False):
         raise NotImplementedError("activations must be MX-FP4 (E2M1) packed along K with block 32")
     if not xq.plain and not assume_clean and bool((xq.bitmap != 0).any()):
         raise NotImplementedError("activations with outliers of their own cannot feed kind::mxf4")
-    if not mx4_pair_ok(pw):
-        raise NotImplementedError("weight must be an MX-FP4 weight packed along K with block 32, no outliers, K % 256 == 0")
     M = 1
     for s_ in xq.shape[:-1]:
         M *= s_
+    if not mx4_pair_ok(pw, M):
+        raise NotImplementedError("weight must be an MX-FP4 weight packed along K with block 32 (few FP4 outliers), K % 256 == 0")
     wsf_t = getattr(pw, "_mx4_sf_tiled", None)
     if wsf_t is None:
         wsf_t = pw._mx4_sf_tiled = tile_scales(pw.e_in.reshape(Nn, K // 32))
@@ -556,6 +563,14 @@ def packed_linear_mx4(xq, pw, bias=None, assume_clean=False):
     rc = N.lib().msq_gemm_mxfp4_tma(N.ptr(xq.codes), K // 2, N.ptr(xq.e_in), N.ptr(pw.codes), K // 2, N.ptr(wsf_t), N.ptr(out),
                                     out.stride(0), M, Nn, K, 0, N.ptr(ws), nbytes, N.stream_ptr(out.device))
     N.check(rc, "msq_gemm_mxfp4_tma")
+    if not pw.plain:
+        o_ptr, o_k, o_dw = mx4_sparse_outliers(pw)
+        if o_k is not None and o_k.numel():
+            # the tensor core read every outlier slot as q * 2^e_in: add x[m, k] * (true value - that) per outlier and token
+            rc = N.lib().msq_sparse_outlier_correct_fp4(N.ptr(xq.codes), K // 2, N.ptr(xq.e_in), N.ptr(pw._mx4_sparse_rows), N.ptr(o_k),
+                                                        N.ptr(o_dw), int(o_k.numel()), N.ptr(out), out.stride(0), M, K, 0,
+                                                        N.stream_ptr(out.device))
+            N.check(rc, "msq_sparse_outlier_correct_fp4")
     if bias is not None:
         out += bias.float()
     return out.reshape(*xq.shape[:-1], Nn)

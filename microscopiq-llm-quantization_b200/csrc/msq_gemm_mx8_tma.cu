@@ -565,6 +565,7 @@ __global__ void __launch_bounds__(256) k_tile_scales(const uint8_t* __restrict__
 
 // sparse outlier correction as a pass of its own behind the GEMM (every SM works on it; inside the GEMM only the four
 // epilogue warps of a CTA can): one thread per (outlier, token), C[m, n_e] += x[m, k_e] * dw_e by atomics
+template <bool X4>      // X4: the activations are packed FP4 codes (two per byte, ldx in bytes) instead of E4M3 bytes
 __global__ void __launch_bounds__(256) k_sparse_outlier_corr(const int* __restrict__ o_n, const int* __restrict__ o_k,
                                                              const float* __restrict__ o_dw, int nnz, const uint8_t* __restrict__ xcodes,
                                                              long long ldx, const int8_t* __restrict__ xe, int M, int K, float* C,
@@ -578,7 +579,10 @@ __global__ void __launch_bounds__(256) k_sparse_outlier_corr(const int* __restri
   const float dw = __ldg(o_dw + e);
   const int xb = __ldg(xe + (long long)m * (K >> 5) + (k >> 5));
   const float xs = xb == MSQ_EXP_NAN ? qnan() : pow2i(xb);
-  const float xv = __fmul_rn(decode_elem((uint32_t)__ldg(xcodes + (long long)m * ldx + k), 4, 5), xs);
+  float xq;
+  if (X4) xq = decode_elem(((uint32_t)__ldg(xcodes + (long long)m * ldx + (k >> 1)) >> ((k & 1) * 4)) & 0xFu, 2, 3);
+  else xq = decode_elem((uint32_t)__ldg(xcodes + (long long)m * ldx + k), 4, 5);
+  const float xv = __fmul_rn(xq, xs);
   atomicAdd(C + (long long)(fold_m ? m % fold_m : m) * ldc + n, __fmul_rn(xv, dw));
 }
 
@@ -662,16 +666,31 @@ static int tile_scales(const void* scales, int is_int8_exponent, int rows, int K
 
 // C[m mod fold_m (fold_m = 0: m), o_n[e]] += dq(x)[m, o_k[e]] * o_dw[e] for every outlier e and token m: the sparse part of a
 // linear whose dense part ran on the packed codes (msq_gemm_mxfp8_tma without o_ptr); COO triplets, best sorted by feature
+static int sparse_correct(bool x4, const unsigned char* xcodes, long long ldx, const signed char* xe, const int* o_n, const int* o_k,
+                          const float* o_dw, int nnz, float* C, long long ldc, int M, int K, int fold_m, void* stream);
 int msq_sparse_outlier_correct(const unsigned char* xcodes, long long ldx, const signed char* xe, const int* o_n, const int* o_k,
                                const float* o_dw, int nnz, float* C, long long ldc, int M, int K, int fold_m, void* stream) {
+  return sparse_correct(false, xcodes, ldx, xe, o_n, o_k, o_dw, nnz, C, ldc, M, K, fold_m, stream);
+}
+// the same behind the W4A4 GEMM: xcodes4 = packed FP4 activations (two codes per byte, low nibble = lower k; ldx in bytes)
+int msq_sparse_outlier_correct_fp4(const unsigned char* xcodes4, long long ldx, const signed char* xe, const int* o_n, const int* o_k,
+                                   const float* o_dw, int nnz, float* C, long long ldc, int M, int K, int fold_m, void* stream) {
+  return sparse_correct(true, xcodes4, ldx, xe, o_n, o_k, o_dw, nnz, C, ldc, M, K, fold_m, stream);
+}
+static int sparse_correct(bool x4, const unsigned char* xcodes, long long ldx, const signed char* xe, const int* o_n, const int* o_k,
+                          const float* o_dw, int nnz, float* C, long long ldc, int M, int K, int fold_m, void* stream) {
   msq::DevGuard dev_guard_(xcodes);
   if (!xcodes || !xe || !C || M <= 0 || K <= 0 || nnz < 0 || fold_m < 0) return MSQ_ERR_BAD_ARG;
   if (nnz == 0) return MSQ_OK;
   if (!o_n || !o_k || !o_dw) return MSQ_ERR_BAD_ARG;
   dim3 grid((unsigned)((nnz + 31) / 32), (unsigned)((M + 7) / 8));
   if (grid.y > 65535u) return MSQ_ERR_UNSUPPORTED;
-  k_sparse_outlier_corr<<<grid, 256, 0, (cudaStream_t)stream>>>(o_n, o_k, o_dw, nnz, xcodes, ldx, reinterpret_cast<const int8_t*>(xe),
-                                                                M, K, C, ldc, fold_m);
+  if (x4)
+    k_sparse_outlier_corr<true><<<grid, 256, 0, (cudaStream_t)stream>>>(o_n, o_k, o_dw, nnz, xcodes, ldx, reinterpret_cast<const int8_t*>(xe),
+                                                                        M, K, C, ldc, fold_m);
+  else
+    k_sparse_outlier_corr<false><<<grid, 256, 0, (cudaStream_t)stream>>>(o_n, o_k, o_dw, nnz, xcodes, ldx, reinterpret_cast<const int8_t*>(xe),
+                                                                         M, K, C, ldc, fold_m);
   return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
 }
 

@@ -76,7 +76,7 @@ def linear_forward(input, weight, bias, mx_specs, packed_weight=None):
         packed_weight = _pack_weight(bf_weight, mx_specs)
     if packed_weight is not None and qis_input.shape[-1] == packed_weight.shape[1]:
         output = None
-        if _mx4_activation_ok(bf_in, mx_specs) and _tc.mx4_pair_ok(packed_weight):
+        if _mx4_activation_ok(bf_in, mx_specs) and _tc.mx4_pair_ok(packed_weight, bf_in.shape[0]):
             # W4A4: both operands as packed FP4 codes on kind::mxf4 (twice the tensor rate of the FP8 pairing)
             sb = mx_specs["scale_bits"] or 4
             xq = pack_mx_outlier(bf_in, sb, sb, mx_specs["a_elem_format"], mx_specs["a_elem_format"], 5, [1], 32,

@@ -55,12 +55,32 @@ def test_w4a4_rejects(M):
     x8 = M.pack_mx(torch.randn(4, 512, generator=g).cuda(), 8, "fp8_e4m3", axes=[-1], block_size=32)
     with pytest.raises(NotImplementedError):                # FP8 activations belong to packed_linear_mx8
         _tc.packed_linear_mx4(x8, pw)
-    # a weight with outliers of its own is not an mxf4 operand
-    W[3, 5] = 3.0
-    W = W.repeat(1, 4)
-    po = M.pack_mx_outlier(W.cuda(), 8, 8, "fp4_e2m1", "fp4_e2m1", 5, [1], 32, variant=1)
-    if bool((po.bitmap != 0).any()):
-        assert not _tc.mx4_pair_ok(po)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("Mx,N,K", [(16, 256, 1024), (300, 384, 2048), (400, 512, 4096)])
+def test_w4a4_weight_with_outliers(M, Mx, N, K):
+    """FP4 outliers of the weight (own shared exponent) = sparse correction behind the kind::mxf4 GEMM
+    (msq_sparse_outlier_correct_fp4); beyond the outliers x tokens budget the pairing is refused"""
+    from msq_b200 import _tc
+    g = torch.Generator().manual_seed(N + K + Mx)
+    W = torch.randn(N, K, generator=g) * 0.02
+    W.view(-1)[torch.randperm(W.numel(), generator=g)[: max(4, W.numel() // 400)]] *= 20
+    x = torch.randn(Mx, K, generator=g) * torch.logspace(-2, 1, Mx).unsqueeze(1)
+    pw = M.pack_mx_outlier(W.cuda(), 8, 8, "fp4_e2m1", "fp4_e2m1", 5, [1], 32, variant=1)
+    assert bool((pw.bitmap != 0).any())
+    xq = M.pack_mx(x.cuda(), 8, "fp4_e2m1", axes=[-1], block_size=32)
+    assert _tc.mx4_pair_ok(pw, Mx)
+    y = _tc.packed_linear_mx4(xq, pw)
+    check(y.cpu(), xq.dequantize().cpu(), pw.dequantize().cpu())
+    old = _tc.MX8_TMA_SPARSE_BUDGET
+    _tc.MX8_TMA_SPARSE_BUDGET = 1.0
+    try:
+        assert not _tc.mx4_pair_ok(pw, Mx)
+        with pytest.raises(NotImplementedError):
+            _tc.packed_linear_mx4(xq, pw)
+    finally:
+        _tc.MX8_TMA_SPARSE_BUDGET = old
 
 
 @pytest.mark.timeout(300)
