@@ -724,10 +724,17 @@ __device__ __forceinline__ BlockPk core_outlier_cvt(const float (&x)[16], const 
   const float c_in = __int_as_float(__float_as_int(pow2i(e_in + c.fin.min_exp - (c.fin.bits - 2) - 1)) - 1);
   const float c_out = __int_as_float(__float_as_int(pow2i(e_out - e_in + c.fout.min_exp - (c.fout.bits - 2) - 1)) - 1);
   float vi[N], vo[N];
-  bool special = false;
+  // any |x| equal to one of the two magnitudes?  (|x| - c_in) * (|x| - c_out) is zero exactly then (both differences are
+  // exact zeros or non-zero, the factors are finite); an underflowing product of two tiny differences only sends the block
+  // through the exact branch below for nothing.  Differences and products on the FMA pipe, one 3-input minimum per pair on
+  // the logic pipe (the pipe that bounds this kernel) instead of four comparisons
+  float pmin = 1.0f;
+  const float2 nci = f2s(-c_in), nco = f2s(-c_out);
 #pragma unroll
   for (int i = 0; i < N; i += 2) {
-    special = special || (fabsf(x[i]) == c_in) || (fabsf(x[i]) == c_out) || (fabsf(x[i + 1]) == c_in) || (fabsf(x[i + 1]) == c_out);
+    const float2 ax = f2(fabsf(x[i]), fabsf(x[i + 1]));
+    const float2 pr = __fmul2_rn(__fadd2_rn(ax, nci), __fadd2_rn(ax, nco));
+    pmin = fminf(pmin, fminf(fabsf(pr.x), fabsf(pr.y)));
     const float2 xb = f2(__int_as_float(__float_as_int(x[i]) | 1), __int_as_float(__float_as_int(x[i + 1]) | 1));
     const float2 a = __fmul2_rn(xb, f2s(si)), b = __fmul2_rn(xb, f2s(so));
     vi[i] = a.x; vi[i + 1] = a.y; vo[i] = b.x; vo[i + 1] = b.y;
@@ -737,7 +744,7 @@ __device__ __forceinline__ BlockPk core_outlier_cvt(const float (&x)[16], const 
   uint32_t ow[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) ow[j] = cvt4_e4m3(vo[4 * j], vo[4 * j + 1], vo[4 * j + 2], vo[4 * j + 3]);
-  if (special) {
+  if (pmin == 0.0f) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       const uint32_t sgn = (uint32_t)__float_as_int(x[i]) >> 31;
