@@ -55,10 +55,21 @@ class LayerMover(object):
     GPU the moves cost 0.035 s per layer through the staging buffer, and the background copies slow the launch-bound
     solves down by more than that (measured: 4 layers 2.30 s without, 2.82 s with overlap)."""
 
-    def __init__(self, layers, dev, enabled=True):
+    def __init__(self, layers, dev, enabled=True, shard=False, gather=None):
+        """shard=True (under torch.distributed, every rank holding the SAME host model): an upload is split over the
+        ranks -- each stages and copies 1/world of the layer's bytes through its own PCIe link and one all-gather over
+        NVLink assembles the layer on every GPU (eight ranks each pushing the whole layer through the one host
+        otherwise contend for the host's memory bandwidth: 0.51 s of a 1.34 s four-layer run on 8 GPUs).  `gather` =
+        all_gather_into_tensor-like callable (tests)."""
         self.layers, self.dev = layers, dev
         self.cuda = dev.type == "cuda"
         self.enabled = enabled and self.cuda
+        self.world, self.rank = 1, 0
+        self.gather = gather
+        if shard and D.is_dist() and not self.enabled:
+            self.world, self.rank = D.dist.get_world_size(), D.dist.get_rank()
+            if gather is None:
+                self.gather = D.dist.all_gather_into_tensor
         self.pending, self.offloads = {}, []
         self.host = {}             # layer index -> {param/buffer name: host tensor} (the original storage)
         self.stage = None
@@ -72,8 +83,55 @@ class LayerMover(object):
             self.stage = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
         return self.stage
 
+    @staticmethod
+    def shard_plan(nbytes_list, world):
+        """byte layout of a sharded upload: tensors at 256-byte aligned offsets of one buffer, the buffer cut into `world`
+        equal chunks (multiples of 256 bytes) -> (offsets, chunk bytes)"""
+        offs, off = [], 0
+        for nb in nbytes_list:
+            offs.append(off)
+            off += (nb + 255) // 256 * 256
+        chunk = ((off + world - 1) // world + 255) // 256 * 256
+        return offs, max(chunk, 256)
+
+    @staticmethod
+    def stage_shard(tensors, offs, lo, hi, stage):
+        """copy the bytes [lo, hi) of the concatenated layout (tensor t at offs[t]) into stage[0 : hi - lo]"""
+        for p, off in zip(tensors, offs):
+            nb = p.numel() * p.element_size()
+            a, b = max(lo, off), min(hi, off + nb)
+            if a < b:
+                src = p.contiguous().reshape(-1).view(torch.uint8)
+                stage[a - lo: b - lo].copy_(src[a - off: b - off])
+
+    def _to_device_sharded(self, i):
+        layer = self.layers[i]
+        named = [(n, p) for n, p in list(layer.named_parameters()) + list(layer.named_buffers()) if p.device != self.dev]
+        if not named:
+            return layer
+        offs, chunk = self.shard_plan([p.numel() * p.element_size() for _, p in named], self.world)
+        lo = self.rank * chunk
+        stage = self._staging(chunk) if self.cuda else torch.empty(chunk, dtype=torch.uint8)
+        self.stage_shard([p.data for _, p in named], offs, lo, lo + chunk, stage)
+        buf = torch.empty(chunk * self.world, dtype=torch.uint8, device=self.dev)
+        mine = buf[lo: lo + chunk]
+        mine.copy_(stage[:chunk], non_blocking=True)
+        self.gather(buf, mine)                                       # NVLink: every rank ends with the whole layer
+        host = {}
+        with torch.no_grad():
+            for (n, p), off in zip(named, offs):
+                nb = p.numel() * p.element_size()
+                host[n] = p.data
+                p.data = buf[off: off + nb].view(p.dtype).reshape(p.shape)
+        if self.cuda:
+            torch.cuda.current_stream(self.dev).synchronize()         # the staging buffer is reused by the next layer
+        self.host[i] = host
+        return layer
+
     def _to_device(self, i):
         layer = self.layers[i]
+        if self.world > 1:
+            return self._to_device_sharded(i)
         if not self.cuda:
             return layer.to(self.dev)
         host = {}
@@ -199,7 +257,7 @@ def _run_layer(layer, x, args, kwargs):
 def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=.01, groupsize=-1, act_order=False,
                         static_groups=False, true_sequential=False, hessian_batch=8, verbose=False, stats=None, overlap_moves=False,
                         share_hessians=True, forward_batch=8, release_cache=False, packed_out=None,
-                        solve_streams_n=3):
+                        solve_streams_n=3, shard_moves=True):
     """llama_sequential / opt_sequential (llm/llama.py:62-173, llm/opt.py:26-128).
     nearest=True is the RTN branch (llm/llama.py:226-253): every linear is replaced by
     quantize_mx_outlier_v1(W) without calibration.  Returns {layer name: quantizer}.
@@ -215,6 +273,8 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
     Hessian + one factorization for linears that receive the same tensor (q/k/v, gate/up).  release_cache: call
     torch.cuda.empty_cache() after every linear like gptq.py:191 (off: the solver workspaces are reused).
     solve_streams_n: side streams the independent column loops of a layer are queued on (0 = one after the other).
+    shard_moves: under torch.distributed every rank uploads 1/world of a layer and an all-gather assembles it
+    (LayerMover; needs the same host model on every rank, which the data-parallel path assumes anyway).
     packed_out: a dict that receives {"layers.<i>.<name>": PackedMX} -- the packed artefact of every linear this rank
     solved on the fused path (packed.save_packed writes them to disk, MXLinear.from_packed runs them)."""
     qcfg = dict(REFERENCE_QCFG if qcfg is None else qcfg)
@@ -229,7 +289,7 @@ def sequential_quantize(model, batches, dev, qcfg=None, nearest=False, percdamp=
         if not nearest:
             assert hi > lo, "fewer calibration batches than ranks"
             batches = batches[lo:hi]
-    mover = LayerMover(layers, dev, overlap_moves)
+    mover = LayerMover(layers, dev, overlap_moves, shard=shard_moves and dev.type == "cuda")
     solve_streams = [torch.cuda.Stream(dev) for _ in range(max(0, solve_streams_n))] if dev.type == "cuda" else []
     if nearest:
         for i in range(len(layers)):

@@ -157,3 +157,46 @@ def test_row_sharded_fasterquant_two_rank_gloo():
     ret = mgr.dict()
     mp.spawn(_rowshard_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert all(ret[r] for r in range(world)), dict(ret)
+
+
+def _mover_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from msq_b200.llm.sequential import LayerMover
+    torch.manual_seed(0)                          # the same host model on every rank
+
+    def mk():
+        return torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.LayerNorm(53), torch.nn.Linear(53, 11, bias=False)).half()
+    layers = [mk(), mk()]
+    want = [{n: p.detach().clone() for n, p in l.named_parameters()} for l in layers]
+
+    def gather(out, mine):                        # gloo: all_gather on a list of views
+        parts = list(out.chunk(world))
+        dist.all_gather(parts, mine.clone())
+    mv = LayerMover(layers, torch.device("cpu"), enabled=False, shard=True, gather=gather)
+    ok = mv.world == world
+    # the two halves of the sharded route on CPU tensors (source and destination are both the host here)
+    for i, layer in enumerate(layers):
+        named = list(layer.named_parameters())
+        offs, chunk = LayerMover.shard_plan([p.numel() * p.element_size() for _, p in named], world)
+        ok = ok and chunk % 256 == 0 and chunk * world >= offs[-1] + named[-1][1].numel() * 2
+        stage = torch.zeros(chunk, dtype=torch.uint8)
+        LayerMover.stage_shard([p.data for _, p in named], offs, rank * chunk, (rank + 1) * chunk, stage)
+        buf = torch.empty(chunk * world, dtype=torch.uint8)
+        gather(buf, stage)
+        for (n, p), off in zip(named, offs):
+            nb = p.numel() * p.element_size()
+            got = buf[off: off + nb].view(p.dtype).reshape(p.shape)
+            ok = ok and torch.equal(got, want[i][n])
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sharded_layer_upload_two_rank_gloo():
+    """LayerMover(shard=True): each rank stages 1/world of a layer's bytes, an all-gather assembles every parameter"""
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_mover_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world)), dict(ret)
