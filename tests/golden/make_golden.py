@@ -207,7 +207,9 @@ def make_linear():
              dict(w_elem_format="fp4", a_elem_format="int4", block_size=128, custom_cuda=False, quantize_backprop=False),
              dict(w_elem_format="fp4_e2m1", a_elem_format="fp8_e4m3", block_size=16, scale_bits=8),
              dict(w_elem_format=None, a_elem_format="fp8_e4m3", block_size=32, scale_bits=8),
-             dict(w_elem_format="int8", a_elem_format=None, block_size=64, scale_bits=8, bfloat=16)]
+             dict(w_elem_format="int8", a_elem_format=None, block_size=64, scale_bits=8, bfloat=16),
+             # W4A4: both operands FP4 -> tcgen05 kind::mxf4 on the B200 path
+             dict(w_elem_format="fp4_e2m1", a_elem_format="fp4_e2m1", block_size=32, scale_bits=8)]
     for n, spec in enumerate(cases):
         g = torch.Generator().manual_seed(800 + n)
         x = torch.randn(64, 256, generator=g)
