@@ -74,6 +74,15 @@ int msq_quantize_mx_f32(const float* in, float* deq, long long pre, long long L,
                         const float* ext_max, unsigned char* codes, signed char* e_shared,
                         int* status, int* host_path, void* stream);
 
+/* The activation side of the block-scaled linears (number_system/mx/linear.py:66-73 quantizes the activations of every
+ * call): [rows, K] fp32 (x_dtype 0), bf16 (1) or fp16 (2) activations, blocks of 32 along K, straight to packed FP4 (E2M1,
+ * elem_is_fp4 != 0) or FP8 (E4M3) codes + int8 shared exponents [rows, K/32].  Arithmetic and planes of
+ * msq_quantize_mx_f32(mode = 1, block 32, round to nearest) bit for bit; one launch, the input read in its own dtype.
+ * ldx in elements, ldc_bytes / lde in bytes; K % 32 == 0, 16-byte aligned rows. */
+int msq_quantize_mx_act(const void* x, int x_dtype, long long ldx, long long rows, int K, int elem_is_fp4,
+                        int scale_bits, int flush_fp32_subnorms, unsigned char* codes, long long ldc_bytes,
+                        signed char* e_shared, long long lde, int* status, void* stream);
+
 /* ---- MX + outlier quantization (the MicroScopiQ quantizer) ----------------------------
  * replaces quantize_mx_outlier_v1        utils/quant.py:147-266   (variant 0)
  *          quantize_mx_outlier_hessian   utils/quant.py:23-146    (variant 0 + blk_cnt)

@@ -81,6 +81,10 @@ class PackedMX(object):
         return out32 if out32 is not None else out16
 
 
+N.register("msq_quantize_mx_act", C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p])
+
+
 def _alloc_planes(x, pre, L, post, bs, fi, fo, plain):
     L_ = N.lib()
     dev = x.device
@@ -133,8 +137,51 @@ def pack_mx_outlier(A, inlier_scale_bits, outlier_scale_bits, inlier_elem_format
     return (p, deq) if want_deq else p
 
 
+#: activations blocked along their last axis go through the dedicated kernel (csrc/msq_quant_act.cu): the input is read
+#: in its own dtype, rounding + codes by the hardware's narrow-format conversions; planes bit-identical to the generic path
+ACT_KERNEL = True
+_ACT_DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+def _pack_mx_act(A, scale_bits, elem_format, flush):
+    from .mx.formats import _get_format_params
+    fp = tuple(_get_format_params(elem_format)[:4])
+    if fp not in ((2, 3, 2, 6.0), (4, 5, 8, 448.0)):
+        return None
+    x = A.detach()
+    N.require_cuda(x, "input")
+    if x.dtype not in _ACT_DTYPES or x.dim() < 1 or x.shape[-1] % 32 or not (1 <= int(scale_bits) <= 8) or x.numel() == 0:
+        return None
+    x = x.contiguous()
+    K = x.shape[-1]
+    rows = x.numel() // K
+    if x.data_ptr() % 16 or (K * x.element_size()) % 16:
+        return None
+    is4 = fp[0] == 2
+    cb = K // 2 if is4 else K
+    dev = x.device
+    codes = torch.empty(rows * cb + 16, dtype=torch.uint8, device=dev)[: rows * cb]
+    e = torch.empty(rows * (K // 32), dtype=torch.int8, device=dev)
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    rc = N.lib().msq_quantize_mx_act(N.ptr(x), _ACT_DTYPES[x.dtype], K, rows, K, int(is4), int(scale_bits), int(bool(flush)),
+                                     N.ptr(codes), cb, N.ptr(e), K // 32, N.ptr(st), N.stream_ptr(dev))
+    if rc == -2:            # MSQ_ERR_UNSUPPORTED: the generic path takes it
+        return None
+    N.check(rc, "msq_quantize_mx_act")
+    nseg = (e.numel() + N.lib().msq_seg_blocks() - 1) // N.lib().msq_seg_blocks()
+    return PackedMX(shape=tuple(x.shape), axis=x.dim() - 1, block_size=32, in_fmt=elem_format, out_fmt=elem_format,
+                    in_scale_bits=scale_bits, out_scale_bits=scale_bits, code_width=4 if is4 else 8, hi_w=0, hi_seg_stride=0,
+                    nseg=nseg, plain=True, path=7, status=st, codes=codes, e_in=e, e_out=None, bitmap=None, hi=None,
+                    seg_cnt=None)
+
+
 def pack_mx(A, scale_bits, elem_format, axes=None, block_size=32, round="nearest", flush_fp32_subnorms=False, mode=1):
     """plain MX quantize + pack (codes + shared exponents); mode 1 = spec arithmetic (exact 2^e divisor)."""
+    if (ACT_KERNEL and mode == 1 and int(block_size) == 32 and round == "nearest" and torch.is_tensor(A) and A.dim() >= 1
+            and _ops._single_axis(axes, A.dim()) == A.dim() - 1):
+        p = _pack_mx_act(A, scale_bits, elem_format, flush_fp32_subnorms)
+        if p is not None:
+            return p
     x = _ops._as_f32(A)
     axis = _ops._single_axis(axes, x.ndim)
     pre, L, post = _ops.geometry(x.shape, axis)
