@@ -348,6 +348,23 @@ def extras(dev, dev_w, nel):
     del xq8, pw8
     torch.cuda.empty_cache()
     out["blockscaled_mxfp4_gemm_w4a4"] = mx4
+    # (6) the activation side of those linears: [M, K] activations -> packed codes + shared exponents (msq_quantize_mx_act),
+    # 8192 x 8192 so that the input does not sit in L2 between replays
+    act = {}
+    peak = 6543.1
+    _pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(_pp):
+        peak = float(json.load(open(_pp)).get("hbm_gbs", peak))
+    for dt, nm in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
+        xa = torch.randn(8192, 8192, device=dev).to(dt)
+        for fmt, wbytes in (("fp4_e2m1", 0.5), ("fp8_e4m3", 1.0)):
+            ms = _time_ms_device(lambda: msq_b200.pack_mx(xa, 8, fmt, axes=[-1], block_size=32), 10)
+            gb = 8192.0 * 8192.0 * (xa.element_size() + wbytes + 1.0 / 32) / (ms * 1e-3) / 1e9
+            act["%s_to_%s" % (nm, fmt)] = {"ms": ms, "GBps": gb, "frac_of_hbm_peak": gb / peak}
+        del xa
+    act["note"] = "8192 x 8192 activations, blocks of 32 along K; algorithmic bytes = input + codes + 1 exponent byte per block"
+    torch.cuda.empty_cache()
+    out["activation_quant"] = act
     return out
 
 

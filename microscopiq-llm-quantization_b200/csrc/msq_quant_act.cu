@@ -5,8 +5,8 @@
 // bit-identical planes (tests/test_gpu_mxops.py), but written for the place it runs: in front of EVERY linear call.
 //
 //  * fp32, bf16 or fp16 input is read as it is (the generic entry point needs an fp32 copy first: two more passes over
-//    the activations), 16 bytes per lane, a block of 32 values = 8 lanes (fp32) or 4 lanes (16-bit) of one warp: every
-//    load instruction of a warp covers 512 contiguous bytes, the block maximum is 3 (2) shuffles;
+//    the activations); a thread owns a whole block of 32 values (no shuffles, the block-level work once per 32 elements,
+//    16- / 32-byte code stores, coalesced exponent bytes);
 //  * element rounding + encoding by cvt.rn.satfinite.e2m1x2.f32 / e4m3x2.f32.  The reference rounds the exact value
 //    half AWAY from zero on the integer mantissa (quantize.cuh:120-131) and saturates to max_norm; the hardware rounds
 //    half to EVEN and saturates to the same max_norm.  Setting the last mantissa bit of x before the exact power-of-two
@@ -28,124 +28,131 @@ struct ActParams {
   signed char* e; long long lde;         // exponents per row
   int* status;
   long long rows; int K;
-  int tasks, cpr; unsigned int cpr_m; int cpr_k;      // warp tasks, tasks per row and its magic divider
+  int tasks, cpr; unsigned int cpr_m; int cpr_k;      // blocks, blocks per row and its magic divider
   int S;                                 // 2^(scale_bits - 1) - 1
   int flush;
 };
 
-template <int DT> struct Elt;            // 0 = fp32, 1 = bf16, 2 = fp16
-template <> struct Elt<0> { static constexpr int EPL = 4; };
-template <> struct Elt<1> { static constexpr int EPL = 8; };
-template <> struct Elt<2> { static constexpr int EPL = 8; };
-
+// 32 values of one block from 128 (fp32) or 64 (16-bit) contiguous bytes
+// 32 bytes per load instruction (one whole sector per lane: with 16-byte loads at a 128-byte lane stride every sector is
+// requested twice and the fp32 path ran at 0.6-0.7 of the copy roofline)
+__device__ __forceinline__ void ldg32(const char* p, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+// 32 values of one block from 128 (fp32) or 64 (16-bit) contiguous bytes
 template <int DT>
-__device__ __forceinline__ void load16(const void* p, float (&v)[Elt<DT>::EPL]) {
-  const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+__device__ __forceinline__ void load_block(const char* p, float (&v)[32]) {
   if (DT == 0) {
-    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
-  } else {
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (DT == 1) {
-        v[2 * i] = __uint_as_float(w[i] << 16);
-        v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
-      } else {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-        v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    for (int j = 0; j < 4; ++j) {
+      uint32_t r[8];
+      ldg32(p + 32 * j, r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[8 * j + i] = __uint_as_float(r[i]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      uint32_t w[8];
+      ldg32(p + 32 * j, w);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (DT == 1) {
+          v[16 * j + 2 * i] = __uint_as_float(w[i] << 16);
+          v[16 * j + 2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+        } else {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+          v[16 * j + 2 * i] = f.x; v[16 * j + 2 * i + 1] = f.y;
+        }
       }
     }
   }
 }
 
-__device__ __forceinline__ uint32_t cvt_e2m1x2(float lo, float hi) {      // byte: lo in the low nibble
+// eight fp32 -> eight E2M1 codes (element j in nibble j) / four fp32 -> four E4M3 codes (element j in byte j)
+__device__ __forceinline__ uint32_t cvt8_e2m1(float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
   uint32_t d;
-  asm("{\n.reg .b8 b;\ncvt.rn.satfinite.e2m1x2.f32 b, %2, %1;\ncvt.u32.u8 %0, b;\n}\n" : "=r"(d) : "f"(lo), "f"(hi));
+  asm("{\n"
+      ".reg .b8 b0, b1, b2, b3;\n"
+      "cvt.rn.satfinite.e2m1x2.f32 b0, %2, %1;\n"
+      "cvt.rn.satfinite.e2m1x2.f32 b1, %4, %3;\n"
+      "cvt.rn.satfinite.e2m1x2.f32 b2, %6, %5;\n"
+      "cvt.rn.satfinite.e2m1x2.f32 b3, %8, %7;\n"
+      "mov.b32 %0, {b0, b1, b2, b3};\n"
+      "}\n"
+      : "=r"(d)
+      : "f"(a0), "f"(a1), "f"(a2), "f"(a3), "f"(a4), "f"(a5), "f"(a6), "f"(a7));
   return d;
 }
-__device__ __forceinline__ uint32_t cvt_e4m3x2(float lo, float hi) {      // 16 bits: lo in the low byte
+__device__ __forceinline__ uint32_t cvt4_e4m3(float a0, float a1, float a2, float a3) {
   uint32_t d;
-  asm("{\n.reg .b16 h;\ncvt.rn.satfinite.e4m3x2.f32 h, %2, %1;\ncvt.u32.u16 %0, h;\n}\n" : "=r"(d) : "f"(lo), "f"(hi));
+  asm("{\n"
+      ".reg .b16 l, h;\n"
+      "cvt.rn.satfinite.e4m3x2.f32 l, %2, %1;\n"
+      "cvt.rn.satfinite.e4m3x2.f32 h, %4, %3;\n"
+      "mov.b32 %0, {l, h};\n"
+      "}\n"
+      : "=r"(d)
+      : "f"(a0), "f"(a1), "f"(a2), "f"(a3));
   return d;
 }
 
-// one 16-byte piece of a block per lane; LPB = lanes per block of 32 values
+// thread = one block of 32 values: no shuffles, the block-level work once per 32 elements, 16- / 32-byte code stores and
+// one exponent byte per lane (consecutive lanes = consecutive blocks of a row).  A lane's loads are 16 bytes at a 128- /
+// 64-byte stride across the warp; the other half of every sector is the next load of the same lane (an L1 hit)
 template <int DT, bool FP4>
 __global__ void __launch_bounds__(256) k_quant_act(const ActParams P) {
-  constexpr int EPL = Elt<DT>::EPL, LPB = 32 / EPL;
   constexpr int EMAX = FP4 ? 2 : 8;
-  const int pieces_per_row = P.K / EPL;
   int st = 0;
-  // a warp task = 32 consecutive pieces (512 bytes) of one row; lanes past the end of the row idle as whole blocks
-  // (pieces_per_row is a multiple of LPB and LPB divides 32), the loop condition is warp-uniform (shuffles inside)
-  const int lane = threadIdx.x & 31;
-  const int nwarps = (int)((gridDim.x * blockDim.x) >> 5);
-  for (int w = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < P.tasks; w += nwarps) {
-    const int row = fast_div(w, P.cpr_m, P.cpr_k);
-    const int pc = (w - row * P.cpr) * 32 + lane;
-    const bool active = pc < pieces_per_row;
-    float v[EPL];
+  const int stride = (int)(gridDim.x * blockDim.x);
+  for (int b = (int)(blockIdx.x * blockDim.x + threadIdx.x); b < P.tasks; b += stride) {
+    const int row = fast_div(b, P.cpr_m, P.cpr_k);
+    const int kb = b - row * P.cpr;
+    float v[32];
+    load_block<DT>(reinterpret_cast<const char*>(P.x) + ((long long)row * P.ldx + (long long)kb * 32) * (DT == 0 ? 4 : 2), v);
+    // exponent field of the block maximum: maximum of the magnitudes' bit patterns (an Inf or NaN gives 255)
+    uint32_t mb = 0;
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) v[i] = 0.0f;
-    if (active) load16<DT>(reinterpret_cast<const char*>(P.x) + ((long long)row * P.ldx + (long long)pc * EPL) * (DT == 0 ? 4 : 2), v);
-    // exponent field of the block maximum = maximum of the exponent fields (255 as soon as one value is Inf / NaN)
-    uint32_t eb = 0;
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) eb = max(eb, ((uint32_t)__float_as_int(v[i]) >> 23) & 0xFFu);
-#pragma unroll
-    for (int o = LPB / 2; o > 0; o >>= 1) eb = max(eb, __shfl_xor_sync(0xffffffffu, eb, o));
+    for (int i = 0; i < 32; i += 2)
+      mb = max(mb, max((uint32_t)__float_as_int(v[i]) & 0x7FFFFFFFu, (uint32_t)__float_as_int(v[i + 1]) & 0x7FFFFFFFu));
     // shared exponent exactly as core_plain mode 1 (shared_exp.cuh:14-53)
-    const int be = (int)eb;                                        // = exponent field of the block maximum (255: Inf / NaN)
+    const int be = (int)(mb >> 23);
     const bool bad = be == 255;
     const bool flush = (be == 0) && P.flush;
     int sh = bad ? 255 : be - EMAX;
     const int ub = sh - 127;
     sh = ub > P.S ? 255 : sh;
-    sh = ub < -P.S ? 127 - P.S : sh;
+    sh = ub < -P.S ? 127 - P.S : sh;              // >= 0 for S <= 127
     const bool dead = sh == 255;
     if (dead) st |= bad ? MSQ_ST_NONFINITE_INPUT : MSQ_ST_EXP_IN_OVERFLOW;
-    // sh < 0 cannot happen for S <= 127 (sh >= 127 - S >= 0)
     const float inv = (flush || dead) ? 0.0f : pow2i(127 - sh);
+    // ties away from zero (quantize.cuh:120-131) = ties to even on x | 1; the power-of-two scaling is exact
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __fmul_rn(__int_as_float(__float_as_int(v[i]) | 1), inv);
+    unsigned char* dst = P.codes + (long long)row * P.ldc + (long long)kb * (FP4 ? 16 : 32);
     if (FP4) {
-      // EPL values -> EPL / 2 bytes
-      uint32_t acc = 0;
+      uint32_t w[4];
 #pragma unroll
-      for (int i = 0; i < EPL; i += 2) {
-        const float a = __fmul_rn(__int_as_float(__float_as_int(v[i]) | 1), inv);
-        const float b = __fmul_rn(__int_as_float(__float_as_int(v[i + 1]) | 1), inv);
-        acc |= cvt_e2m1x2(a, b) << (4 * i);
+      for (int j = 0; j < 4; ++j) {
+        uint32_t a = cvt8_e2m1(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]);
+        a &= (((a & 0x77777777u) + 0x77777777u) & 0x88888888u) | 0x77777777u;        // a zero magnitude carries no sign
+        w[j] = dead ? 0u : a;
       }
-      // a zero magnitude carries no sign
-      const uint32_t nz = ((acc & 0x77777777u) + 0x77777777u) & 0x88888888u;
-      acc &= nz | 0x77777777u;
-      if (dead) acc = 0u;
-      unsigned char* dst = P.codes + (long long)row * P.ldc + (long long)pc * (EPL / 2);
-      if (active) {
-        if (EPL == 8) *reinterpret_cast<uint32_t*>(dst) = acc;
-        else *reinterpret_cast<uint16_t*>(dst) = (uint16_t)acc;
-      }
+      *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
     } else {
-      uint32_t wd[EPL / 4];
+      uint32_t w[8];
 #pragma unroll
-      for (int j = 0; j < EPL / 4; ++j) {
-        uint32_t acc = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i += 2) {
-          const float a = __fmul_rn(__int_as_float(__float_as_int(v[4 * j + i]) | 1), inv);
-          const float b = __fmul_rn(__int_as_float(__float_as_int(v[4 * j + i + 1]) | 1), inv);
-          acc |= cvt_e4m3x2(a, b) << (8 * i);
-        }
-        const uint32_t nz = ((acc & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) & 0x80808080u;
-        acc &= nz | 0x7F7F7F7Fu;
-        wd[j] = dead ? 0u : acc;
+      for (int j = 0; j < 8; ++j) {
+        uint32_t a = cvt4_e4m3(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        a &= (((a & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) & 0x80808080u) | 0x7F7F7F7Fu;
+        w[j] = dead ? 0u : a;
       }
-      unsigned char* dst = P.codes + (long long)row * P.ldc + (long long)pc * EPL;
-      if (active) {
-        if (EPL == 8) *reinterpret_cast<uint2*>(dst) = make_uint2(wd[0], wd[EPL / 4 - 1]);
-        else *reinterpret_cast<uint32_t*>(dst) = wd[0];
-      }
+      *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(dst + 16) = make_uint4(w[4], w[5], w[6], w[7]);
     }
-    if (active && (pc & (LPB - 1)) == 0) P.e[(long long)row * P.lde + pc / LPB] = (signed char)(dead ? MSQ_EXP_NAN : sh - 127);
+    P.e[(long long)row * P.lde + kb] = (signed char)(dead ? MSQ_EXP_NAN : sh - 127);
   }
   if (P.status) {
     st = __reduce_or_sync(0xffffffffu, st);
@@ -155,8 +162,7 @@ __global__ void __launch_bounds__(256) k_quant_act(const ActParams P) {
 
 template <int DT>
 static int launch(ActParams P, bool fp4, cudaStream_t s) {
-  constexpr int EPL = Elt<DT>::EPL;
-  P.cpr = (P.K / EPL + 31) / 32;
+  P.cpr = P.K / 32;                                     // blocks per row
   const long long tasks = P.rows * P.cpr;
   if (tasks >= 0x7fffffffLL) return MSQ_ERR_UNSUPPORTED;
   P.tasks = (int)tasks;
@@ -164,8 +170,8 @@ static int launch(ActParams P, bool fp4, cudaStream_t s) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  long long blocks = (tasks + 7) / 8;                   // 8 warps per CTA
-  const long long cap = (long long)sms * 16;            // a few tasks per warp once the tensor is large
+  long long blocks = (tasks + 255) / 256;
+  const long long cap = (long long)sms * 8;             // one wave of resident CTAs once the tensor is large
   if (blocks > cap) blocks = cap;
   if (fp4) k_quant_act<DT, true><<<(unsigned)blocks, 256, 0, s>>>(P);
   else k_quant_act<DT, false><<<(unsigned)blocks, 256, 0, s>>>(P);
@@ -185,8 +191,8 @@ extern "C" int msq_quantize_mx_act(const void* x, int x_dtype, long long ldx, lo
   if (K % 32 != 0) return MSQ_ERR_UNSUPPORTED;
   if (scale_bits < 1 || scale_bits > 8) return MSQ_ERR_UNSUPPORTED;
   const int esz = x_dtype == 0 ? 4 : 2;
-  if ((reinterpret_cast<uintptr_t>(x) & 15) || ((ldx * esz) & 15) || (reinterpret_cast<uintptr_t>(codes) & 7) ||
-      (ldc_bytes & 7))
+  if ((reinterpret_cast<uintptr_t>(x) & 31) || ((ldx * esz) & 31) || (reinterpret_cast<uintptr_t>(codes) & 15) ||
+      (ldc_bytes & 15))
     return MSQ_ERR_ALIGN;
   if (ldx < K || ldc_bytes < (elem_is_fp4 ? K / 2 : K) || lde < K / 32) return MSQ_ERR_BAD_ARG;
   ActParams P;

@@ -155,7 +155,7 @@ def _pack_mx_act(A, scale_bits, elem_format, flush):
     x = x.contiguous()
     K = x.shape[-1]
     rows = x.numel() // K
-    if x.data_ptr() % 16 or (K * x.element_size()) % 16:
+    if x.data_ptr() % 32 or (K * x.element_size()) % 32:
         return None
     is4 = fp[0] == 2
     cb = K // 2 if is4 else K
