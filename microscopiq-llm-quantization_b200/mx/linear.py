@@ -16,7 +16,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import _tc
-from ..packed import pack_mx_outlier
+from ..packed import pack_mx, pack_mx_outlier
 from .elemwise_ops import quantize_elemwise_op
 from .mx_ops import quantize_mx_outlier_op
 from .specs import apply_mx_specs, mx_assert_test
@@ -133,7 +133,7 @@ class MXLinear(torch.nn.Linear):
         super().__init__(in_features, out_features, bias)
 
     @classmethod
-    def from_packed(cls, pw, bias=None, mx_specs=None, name=None, keep_dense=False):
+    def from_packed(cls, pw, bias=None, mx_specs=None, name=None, keep_dense=False, fast_activations=False):
         """inference module over a packed weight (PackedMX [out_features, in_features], e.g. loaded from an MSQPACK
         checkpoint or emitted by GPTQ / pack_mx_outlier): the stored planes ARE the weight -- nothing is re-quantized,
         the forward multiplies the (MX-quantized) activations with the packed planes on tcgen05.
@@ -154,6 +154,7 @@ class MXLinear(torch.nn.Linear):
         mx_assert_test(specs)
         self.mx_specs = apply_mx_specs(specs)
         self._packed, self._packed_version, self._frozen = pw, None, True
+        self.fast_activations = bool(fast_activations)
         return self
 
     def apply_mx_specs(self, mx_specs):
@@ -178,8 +179,43 @@ class MXLinear(torch.nn.Linear):
             self._packed_version = ver
         return self._packed
 
+    #: serving mode (opt-in; from_packed(..., fast_activations=True) or set on the module): the activations go through
+    #: the one-launch plain-MX activation quantizer (msq_quantize_mx_act: the MX spec's shared-exponent blocks of 32, no
+    #: outlier detection on the ACTIVATIONS) straight into the block-scaled GEMM on the packed weight -- W4A4 on
+    #: kind::mxf4, W4A8 on kind::mxf8f6f4.  linear_forward (the default) keeps the reference's semantics, whose
+    #: activation quantizer (linear.py:66-73) is the outlier-aware one: an across-block statistics pass, the pack, and a
+    #: host check that no activation outlier was found before the same GEMM can run.
+    fast_activations = False
+
+    def _forward_fast(self, inputs):
+        from .formats import _get_format_params
+        pw = self.packed_weight()
+        a = self.mx_specs["a_elem_format"]
+        if pw is None or a is None or not _tc.mx4_weight_ok(pw):
+            return None
+        fp = tuple(_get_format_params(a)[:2])
+        if fp not in ((2, 3), (4, 5)) or inputs.shape[-1] != pw.shape[1] or not inputs.is_cuda:
+            return None
+        x2 = inputs.reshape(-1, inputs.shape[-1])
+        xq = pack_mx(x2, self.mx_specs["scale_bits"] or 8, a, axes=[-1], block_size=32,
+                     flush_fp32_subnorms=self.mx_specs["mx_flush_fp32_subnorms"])
+        try:
+            if fp == (2, 3) and _tc.mx4_pair_ok(pw, x2.shape[0]):
+                y = _tc.packed_linear_mx4(xq, pw, bias=self.bias)
+            elif fp == (4, 5):
+                y = _tc.packed_linear_mx8(xq, pw, bias=self.bias)
+            else:
+                return None
+        except NotImplementedError:          # a weight the block-scaled kernels cannot take: the default route decides
+            return None
+        return y.reshape(*inputs.shape[:-1], pw.shape[0]).to(inputs.dtype)
+
     def forward(self, inputs):
         if self.mx_none:
             return super().forward(inputs)
         with torch.no_grad():
+            if self.fast_activations:
+                y = self._forward_fast(inputs)
+                if y is not None:
+                    return y
             return linear_forward(inputs, self.weight, self.bias, self.mx_specs, packed_weight=self.packed_weight())

@@ -113,3 +113,38 @@ def test_mx_linear_w4a4_route(M):
     finally:
         _tc.MX4_TMA = True
     assert torch.allclose(y4, y8, rtol=1e-5, atol=1e-6 * float(y8.abs().max()))
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("a_fmt", ["fp4_e2m1", "fp8_e4m3"])
+def test_mxlinear_serving_mode(M, a_fmt):
+    """MXLinear.from_packed(..., fast_activations=True): one-launch plain-MX activation quantizer + block-scaled GEMM;
+    result = the fp64 matmul of the dequantized operands (+ bias) within the summation-order bound"""
+    from msq_b200 import _tc
+    g = torch.Generator().manual_seed(21)
+    W = (torch.randn(384, 1024, generator=g) * 0.02).cuda()
+    b = torch.randn(384, generator=g).cuda()
+    x = (torch.randn(3, 50, 1024, generator=g) * 2).cuda()
+    pw = M.pack_mx(W, 8, "fp4_e2m1", axes=[1], block_size=32)
+    lin = M.MXLinear.from_packed(pw, bias=b, mx_specs={"w_elem_format": "fp4_e2m1", "a_elem_format": a_fmt, "block_size": 32,
+                                                        "scale_bits": 8}, fast_activations=True)
+    calls, saved = [], {}
+    for name in ("packed_linear_mx4", "packed_linear_mx8"):
+        saved[name] = getattr(_tc, name)
+
+        def spy(*a, _o=saved[name], _n=name, **k):
+            calls.append(_n)
+            return _o(*a, **k)
+        setattr(_tc, name, spy)
+    try:
+        y = lin(x)
+    finally:
+        for name, fn in saved.items():
+            setattr(_tc, name, fn)
+    assert y.shape == (3, 50, 384)
+    assert calls and calls[0] == ("packed_linear_mx4" if a_fmt == "fp4_e2m1" else "packed_linear_mx8")
+    xq = M.pack_mx(x.reshape(-1, 1024), 8, a_fmt, axes=[-1], block_size=32)
+    check((y.reshape(-1, 384) - b).cpu(), xq.dequantize().cpu(), pw.dequantize().cpu())
+    for bf in (torch.bfloat16, torch.float16):           # 16-bit activations are read as they are
+        yb = lin(x.to(bf))
+        assert yb.dtype == bf and torch.isfinite(yb).all()
