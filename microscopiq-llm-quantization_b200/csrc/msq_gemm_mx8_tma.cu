@@ -602,7 +602,7 @@ static void choose_bn(int M, int N, int K, int sms, int& bn, int& nacc, bool f4 
     if (c > 16 && c - 16 >= M) continue;                 // a narrower tile already holds every token
     // kind::mxf4: a tile's MMAs take half as long, the exposed drain of a single accumulator costs twice as much
     // (8192^3: 4.66 PFLOP/s at 256, 5.4-5.6 at 240 / 224)
-    if (f4 && c > 240) continue;
+    if (f4 && c > 240) continue;                         // (f4 is also set for the two-CTA form of either kind)
     const long long tiles = (long long)tiles_n * ((M + c - 1) / c);
     const double waves = (double)((tiles + sms - 1) / sms);
     const double cost = waves * (kblocks * (YA_BYTES + c * YBK + 4096.0) + (c > 240 ? 135000.0 : 0.0));
@@ -631,7 +631,9 @@ static void plan(int M, int N, int K, int sms, int& bn, int& nacc, int& cta2, bo
   const char* e = getenv("MSQ_MX8T_CTA2");
   cta2 = e ? (e[0] == '1') : (M >= 256 && N >= 512);
   if (sms < 2) cta2 = 0;
-  if (cta2) choose_bn(M, ((N + 2 * YM - 1) / (2 * YM)) * YM, K, sms / 2, bn, nacc, f4);       // pairs of CTAs over 256-row tiles
+  // pairs of CTAs over 256-row tiles; with eight epilogue warps per CTA two accumulators of <= 240 columns beat the single
+  // 256-column one for FP8 activations as well (8192^3: 2.67 vs 2.94-2.98 PFLOP/s, scripts/mx8_bn_sweep.py)
+  if (cta2) choose_bn(M, ((N + 2 * YM - 1) / (2 * YM)) * YM, K, sms / 2, bn, nacc, true);
   else choose_bn(M, N, K, sms, bn, nacc, f4);
 }
 
