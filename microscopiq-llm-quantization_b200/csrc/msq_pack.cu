@@ -7,6 +7,8 @@
 //             block-major order, hi_w bits each, starting at seg * hi_seg_stride
 // unpack(pack(W)) reproduces the reference's dequantized tensor bit for bit (tests/test_gpu_pack.py).
 #include "msq_quant_kernels.cuh"
+#include <stdlib.h>
+#include <cuda_fp16.h>
 
 namespace msq {
 
@@ -18,6 +20,7 @@ struct UParams {
   long long hi_seg_stride; int hi_w;
   float* out_f32; __nv_bfloat16* out_bf16;
   int plain;          // 1: plain MX (no bitmap / outliers)
+  unsigned int post_m, nblk_m; int post_k, nblk_k;      // magic dividers (k_unpack_strided_cvt)
 };
 
 __device__ __forceinline__ float dq_elem(uint32_t code, bool isout, const UParams& P, float s_in, float inv_s_in, float s_out,
@@ -243,6 +246,177 @@ __global__ void __launch_bounds__(256) k_unpack_strided_fast(const UParams P) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// k_unpack_strided_cvt: the strided unpack of the drivers' own pairing (fp4_e2m1 slots, fp8_e4m3 outliers with a
+// 4-bit hi field, 16-row blocks) on packed words.  k_unpack_strided_fast spends 54 instructions per element
+// (ncu: 76 M warp instructions for 45 M elements, ALU pipe 66 %, issue 71 %: instruction-bound at 0.33 of the copy
+// roofline) on per-element table lookups, a popcount + shared-memory load + two shifts per hi field and per-element
+// selects.  Here a thread (= column = one MX block) gathers its 16 slot nibbles and 16 mask bits by funnel shifts
+// (one shift each, no masking), takes the block's hi nibbles as ONE unaligned 64-bit window of the segment stream
+// and deals them to the outlier positions with funnel shifts, and decodes with the hardware conversions
+// (cvt.rn.f16x2.e2m1x2 / e4m3x2, exact: every code value is an fp16 value): the inlier and the outlier decode of
+// an element are both computed (one of them from a zeroed code) and added, so there is no select.
+// Same prologue (segment offsets, hi staging) and the same results, bit for bit, as k_unpack_strided_fast.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 dec2_e2m1(uint32_t byte) {          // two E2M1 codes (low nibble first) -> fp32
+  uint32_t h;
+  asm("{\n.reg .b8 b;\ncvt.u8.u32 b, %1;\ncvt.rn.f16x2.e2m1x2 %0, b;\n}\n" : "=r"(h) : "r"(byte));
+  return __half22float2(*reinterpret_cast<const __half2*>(&h));
+}
+__device__ __forceinline__ float2 dec2_e4m3(uint32_t two_bytes) {     // two E4M3 codes (low byte first) -> fp32
+  uint32_t h;
+  asm("{\n.reg .b16 b;\ncvt.u16.u32 b, %1;\ncvt.rn.f16x2.e4m3x2 %0, b;\n}\n" : "=r"(h) : "r"(two_bytes));
+  return __half22float2(*reinterpret_cast<const __half2*>(&h));
+}
+// 4 nibbles (bits 0..15) -> 4 bytes (nibble j in the low half of byte j)
+__device__ __forceinline__ uint32_t spread4(uint32_t n) {
+  uint32_t x = (n | (n << 8)) & 0x00FF00FFu;
+  return (x | (x << 4)) & 0x0F0F0F0Fu;
+}
+// bits 0..7 -> nibbles 0..7 (0xF where the bit is set)
+__device__ __forceinline__ uint32_t nibble_mask8u(uint32_t m8) {
+  uint32_t x = (m8 * 0x1001u) & 0x000F000Fu;
+  x = (x * 0x41u) & 0x03030303u;
+  x = (x * 0x9u) & 0x11111111u;
+  return x * 15u;
+}
+
+template <bool BF16OUT>      // output type; L % 16 == 0 (no ragged row block: the table kernel takes those)
+__global__ void __launch_bounds__(256) k_unpack_strided_cvt(const UParams P) {
+  constexpr int BS = 16, hw = 4;
+  extern __shared__ uint32_t s_dyn[];
+  __shared__ int s_off[MSQ_SEG_BLOCKS / 32 + 1];
+  uint32_t* s_hi = s_dyn;
+  const int seg = (int)blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int post = (int)P.post;
+  constexpr int NGRP = MSQ_SEG_BLOCKS / 32;
+  // ---- prologue of k_unpack_strided_fast: outliers per group of 32 blocks, exclusive scan, stage the used hi prefix
+  for (int w = threadIdx.x; w < NGRP * BS; w += 256) {
+    const int g = w / BS, i = w % BS;
+    const int t = seg * MSQ_SEG_BLOCKS + g * 32;
+    int cnt = 0;
+    if (t < (int)P.nblocks) {
+      const int pb = t / post, j = t - pb * post;
+      const int p = pb / P.nblk, b = pb - p * P.nblk;
+      if (i < min(BS, P.L - b * BS)) cnt = __popc(__ldg(P.bitmap + (((p * P.L + b * BS + i) * post + j) >> 5)));
+    }
+#pragma unroll
+    for (int o = BS / 2; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (i == 0) s_off[g] = cnt;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int tot;
+    const int ex = warp_excl_scan(s_off[lane], lane, tot);
+    s_off[lane] = ex;
+    if (lane == 0) s_off[NGRP] = tot;
+  }
+  __syncthreads();
+  {
+    const int words = (s_off[NGRP] * hw + 31) >> 5;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.hi + (long long)seg * P.hi_seg_stride);
+    for (int i = threadIdx.x; i < words + 2; i += 256) s_hi[i] = i < words ? __ldg(src + i) : 0u;      // + 2: the window below
+  }
+  __syncthreads();
+  const int cshift = (lane * 4) & 31;
+  const uint32_t* codes32 = reinterpret_cast<const uint32_t*>(P.codes) + ((lane * 4) >> 5);
+  const int cstride = (post >> 5) * 4 * 4;
+  const int bstride = (post >> 5) * 4;
+  const int sb = post * 4;
+#pragma unroll 1
+  for (int sub = 0; sub < MSQ_SEG_BLOCKS / 256; ++sub) {
+    const int t0 = seg * MSQ_SEG_BLOCKS + sub * 256 + (int)threadIdx.x;
+    const bool active = t0 < (int)P.nblocks;
+    int base = 0, b = 0;
+    if (active) {
+      const int pb = fast_div(t0, P.post_m, P.post_k);
+      const int j = t0 - pb * post;
+      const int p = fast_div(pb, P.nblk_m, P.nblk_k); b = pb - p * P.nblk;
+      base = (p * P.L + b * BS) * post + j;
+    }
+    // (an inactive thread -- past the last block -- reads the first row block and stores nothing)
+    const int ei = active ? P.e_in[t0] : 0, eo = active ? P.e_out[t0] : 0;
+    const int row32 = (base - lane) >> 5;
+    const char* cp = reinterpret_cast<const char*>(codes32 + (long long)row32 * 4);
+    const char* bp = reinterpret_cast<const char*>(P.bitmap + row32);
+    // slot nibbles of rows 0-7 / 8-15 and the 16 mask bits: every row shifts its nibble / bit in from the top
+    uint32_t s0 = 0, s1 = 0, mask = 0;
+#pragma unroll
+    for (int i = 0; i < BS; ++i) {
+      const uint32_t cw = __ldg(reinterpret_cast<const uint32_t*>(row_at(cp, cstride, i)));
+      const uint32_t bw = __ldg(reinterpret_cast<const uint32_t*>(row_at(bp, bstride, i)));
+      if (i < 8) s0 = __funnelshift_r(s0, cw >> cshift, 4);
+      else s1 = __funnelshift_r(s1, cw >> cshift, 4);
+      mask = __funnelshift_r(mask, bw >> lane, 1);
+    }
+    if (!active) mask = 0;
+    mask >>= 16;
+    // position of this block's hi nibbles in the segment stream
+    int wt;
+    const int k = s_off[sub * 8 + warp] + warp_excl_scan(__popc(mask), lane, wt);
+    const int bit = k * hw;
+    const uint32_t w0 = s_hi[bit >> 5], w1 = s_hi[(bit >> 5) + 1], w2 = s_hi[(bit >> 5) + 2];
+    uint32_t hlo = __funnelshift_r(w0, w1, bit & 31), hhi = __funnelshift_r(w1, w2, bit & 31);   // 16 nibbles, first outlier lowest
+    // deal them to the outlier positions: element i takes the lowest nibble, the window moves on by 4 bits after an outlier
+    const uint32_t nm0 = nibble_mask8u(mask & 0xFFu), nm1 = nibble_mask8u(mask >> 8);
+    uint32_t h0 = 0, h1 = 0;
+    {
+      const uint32_t a0 = nm0 & 0x44444444u, a1 = nm1 & 0x44444444u;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        h0 = __funnelshift_r(h0, hlo, 4);
+        const uint32_t sh = a0 >> (4 * i);            // 4 for an outlier, 0 for an inlier (SHF takes it modulo 32)
+        hlo = __funnelshift_r(hlo, hhi, sh);
+        hhi >>= (sh & 31u);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        h1 = __funnelshift_r(h1, hlo, 4);
+        const uint32_t sh = a1 >> (4 * i);
+        hlo = __funnelshift_r(hlo, hhi, sh);
+        hhi >>= (sh & 31u);
+      }
+    }
+    h0 &= nm0; h1 &= nm1;
+    const uint32_t in0 = s0 & ~nm0, in1 = s1 & ~nm1;            // inlier slots (outlier positions zeroed: decode 0)
+    const uint32_t lo0 = s0 & nm0, lo1 = s1 & nm1;              // low nibbles of the outlier codes
+    const bool nan_blk = ei == MSQ_EXP_NAN || eo == MSQ_EXP_NAN;
+    const float s_in = pow2i(nan_blk ? 0 : ei), inv_s_in = pow2i(nan_blk ? 0 : -ei), s_out = pow2i(nan_blk ? 0 : eo);
+    float r[BS];
+    const float2 si2 = make_float2(s_in, s_in), so2 = make_float2(s_out, s_out), ii2 = make_float2(inv_s_in, inv_s_in);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {                                // four elements at a time
+      const uint32_t inw = g < 2 ? in0 : in1, low = g < 2 ? lo0 : lo1, hiw = g < 2 ? h0 : h1;
+      const int q = (g & 1) * 16;
+      const uint32_t ob = spread4((low >> q) & 0xFFFFu) | (spread4((hiw >> q) & 0xFFFFu) << 4);     // four E4M3 bytes
+      const float2 i01 = dec2_e2m1((inw >> q) & 0xFFu), i23 = dec2_e2m1((inw >> (q + 8)) & 0xFFu);
+      const float2 o01 = dec2_e4m3(ob & 0xFFFFu), o23 = dec2_e4m3(ob >> 16);
+      // inlier: q * 2^e_in; outlier: (q * 2^e_out) * 2^-e_in (quant.py:136); exactly one of the two terms is non-zero and
+      // the sum of a product and a zero is the reference's "+ 0" (quant.py:140)
+      const float2 a = __fadd2_rn(__fmul2_rn(i01, si2), __fmul2_rn(__fmul2_rn(o01, so2), ii2));
+      const float2 c = __fadd2_rn(__fmul2_rn(i23, si2), __fmul2_rn(__fmul2_rn(o23, so2), ii2));
+      r[4 * g + 0] = a.x; r[4 * g + 1] = a.y; r[4 * g + 2] = c.x; r[4 * g + 3] = c.y;
+    }
+    if (nan_blk) {
+#pragma unroll
+      for (int i = 0; i < BS; ++i) r[i] = qnan();
+    }
+    if (active) {
+      if (!BF16OUT) {
+        float* o = P.out_f32 + base;
+#pragma unroll
+        for (int i = 0; i < BS; ++i) *reinterpret_cast<float*>(const_cast<char*>(row_at(o, sb, i))) = r[i];
+      } else {
+        __nv_bfloat16* o = P.out_bf16 + base;
+#pragma unroll
+        for (int i = 0; i < BS; ++i)
+          *reinterpret_cast<__nv_bfloat16*>(const_cast<char*>(row_at(o, sb >> 1, i))) = __float2bfloat16_rn(r[i]);
+      }
+    }
+  }
+}
+
 // innermost layout: thread = 4 consecutive elements, bs/4 lanes per block
 __global__ void __launch_bounds__(256) k_unpack_inner(const UParams P) {
   extern __shared__ uint32_t s_hi[];
@@ -428,6 +602,8 @@ int msq_unpack_mx(const unsigned char* codes, const signed char* e_in, const sig
   P.hi_w = plain ? 0 : msq_packed_hi_width(in_ebits, in_mbits, out_ebits, out_mbits);
   if (P.hi_w > 0 && !hi) return MSQ_ERR_BAD_ARG;
   P.hi_seg_stride = msq_packed_hi_seg_stride(block_size, P.hi_w);
+  magic_div(post, &P.post_m, &P.post_k);
+  magic_div(P.nblk, &P.nblk_m, &P.nblk_k);
   P.out_f32 = out_f32; P.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   const long long nseg = (P.nblocks + MSQ_SEG_BLOCKS - 1) / MSQ_SEG_BLOCKS;
   const size_t smem = P.hi_w > 0 ? (size_t)P.hi_seg_stride : 0;
@@ -456,6 +632,17 @@ int msq_unpack_mx(const unsigned char* codes, const signed char* e_in, const sig
     else MSQ_PICK_U(8);
 #undef MSQ_PICK_U
     (void)hh;
+    // the drivers' pairing on packed words + hardware decode (MSQ_UNPACK_CVT=0 keeps the table kernel: A/B)
+    const bool cvt = !plain && block_size == 16 && P.hi_w == 4 && P.fin.ebits == 2 && P.fin.bits == 3 && P.fout.ebits == 4 &&
+                     P.fout.bits == 5 && L % 16 == 0 && (out_f32 == nullptr) != (out_bf16 == nullptr) &&
+                     !(getenv("MSQ_UNPACK_CVT") && getenv("MSQ_UNPACK_CVT")[0] == '0');
+    if (cvt) {
+      const size_t smc = smem + 16;
+      void (*kc)(const UParams) = out_f32 ? k_unpack_strided_cvt<false> : k_unpack_strided_cvt<true>;
+      if (smc > 48 * 1024) cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc);
+      kc<<<(unsigned)nseg, 256, smc, s>>>(P);
+      return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
+    }
     if (sm > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     k<<<(unsigned)nseg, 256, sm, s>>>(P);
   } else if (post > 1 && post % 32 == 0 && block_size <= 32) {
