@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(256) k_unpack_strided_cvt(const UParams P) {
   for (int sub = 0; sub < MSQ_SEG_BLOCKS / 256; ++sub) {
     const int t0 = seg * MSQ_SEG_BLOCKS + sub * 256 + (int)threadIdx.x;
     const bool active = t0 < (int)P.nblocks;
-    int base = 0, b = 0;
+    int base = lane, b = 0;                   // inactive (past the last block): column `lane` of the first row block
     if (active) {
       const int pb = fast_div(t0, P.post_m, P.post_k);
       const int j = t0 - pb * post;

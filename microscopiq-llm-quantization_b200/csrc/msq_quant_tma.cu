@@ -251,8 +251,8 @@ constexpr int TP_NST = 5;      // input ring
 constexpr int TP_NOUT = 3;     // staging buffers of the output planes (a freed buffer is needed one whole tile later)
 constexpr int TP_TW = 256;
 
-template <int BS, bool CVT>
-__global__ void __launch_bounds__(TP_TW + 32, 2) k_pack_tma(const __grid_constant__ TmaPackParams P) {
+template <int BS, bool CVT, int NST = TP_NST, int NOUT = TP_NOUT, int MINB = 2>
+__global__ void __launch_bounds__(TP_TW + 32, MINB) k_pack_tma(const __grid_constant__ TmaPackParams P) {
   static_assert(BS == 16, "4-bit slots, 16-row blocks");
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int STAGE_FLOATS = BS * TP_TW;
@@ -260,22 +260,22 @@ __global__ void __launch_bounds__(TP_TW + 32, 2) k_pack_tma(const __grid_constan
   constexpr int CD_BYTES = BS * (TP_TW / 2), BM_BYTES = BS * (TP_TW / 8), EX_BYTES = TP_TW;
   constexpr int OUT_BYTES = CD_BYTES + BM_BYTES + 2 * EX_BYTES;      // staging per tile (3 KB), double-buffered
   float* tiles = reinterpret_cast<float*>(smem_raw);
-  unsigned char* outs = smem_raw + (size_t)TP_NST * STAGE_BYTES;
-  unsigned long long* s_acc = reinterpret_cast<unsigned long long*>(outs + TP_NOUT * OUT_BYTES);
+  unsigned char* outs = smem_raw + (size_t)NST * STAGE_BYTES;
+  unsigned long long* s_acc = reinterpret_cast<unsigned long long*>(outs + NOUT * OUT_BYTES);
   uint32_t* s_hi = reinterpret_cast<uint32_t*>(s_acc + MSQ_SEG_BLOCKS);          // MSQ_SEG_BLOCKS * BS * 4 / 8 bytes max
   unsigned char* s_cnt = reinterpret_cast<unsigned char*>(s_hi + MSQ_SEG_BLOCKS * BS * 4 / 32);
   uint64_t* full = reinterpret_cast<uint64_t*>(s_cnt + MSQ_SEG_BLOCKS);   // producer -> consumers: tile landed
-  uint64_t* empty = full + TP_NST;                                         // consumers -> producer: tile is in registers
-  uint64_t* sdone = empty + TP_NST;                                        // consumers -> producer: staging written
-  uint64_t* sfree = sdone + TP_NOUT;                                       // producer -> consumers: staging read out
-  int* s_warp = reinterpret_cast<int*>(sfree + TP_NOUT);
+  uint64_t* empty = full + NST;                                         // consumers -> producer: tile is in registers
+  uint64_t* sdone = empty + NST;                                        // consumers -> producer: staging written
+  uint64_t* sfree = sdone + NOUT;                                       // producer -> consumers: staging read out
+  int* s_warp = reinterpret_cast<int*>(sfree + NOUT);
   const int tid = (int)threadIdx.x;
   const int hi_w = P.hi_w;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < TP_NST; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], TP_TW); }
+    for (int s = 0; s < NST; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], TP_TW); }
 #pragma unroll
-    for (int s = 0; s < TP_NOUT; ++s) { tc::mbar_init(&sdone[s], TP_TW); tc::mbar_init(&sfree[s], 1); }
+    for (int s = 0; s < NOUT; ++s) { tc::mbar_init(&sdone[s], TP_TW); tc::mbar_init(&sfree[s], 1); }
     tc::mbar_fence_init();
   }
   for (int i = tid; i < MSQ_SEG_BLOCKS * BS * 4 / 32; i += TP_TW + 32) s_hi[i] = 0;
@@ -297,19 +297,19 @@ __global__ void __launch_bounds__(TP_TW + 32, 2) k_pack_tma(const __grid_constan
       auto load = [&](int k) {
         int cx, r0;
         coords(tile_of(k), cx, r0);
-        const int s = k % TP_NST;
+        const int s = k % NST;
         tc::mbar_expect_tx(&full[s], STAGE_BYTES);
         tc::tma_load_2d(tiles + (size_t)s * STAGE_FLOATS, &P.tin, &full[s], cx * TP_TW, r0);
       };
-      const int pre = n_mine < TP_NST ? n_mine : TP_NST;
+      const int pre = n_mine < NST ? n_mine : NST;
       for (int k = 0; k < pre; ++k) load(k);
       int si = 0, so = 0;                    // input stage / staging buffer of tile k
       uint32_t pi = 0, po = 0;               // their phase parities
       for (int k = 0; k < n_mine; ++k) {
         // the input stage is free as soon as every consumer holds its block in registers: refill it right away
-        if (k + TP_NST < n_mine) {
+        if (k + NST < n_mine) {
           mbar_wait_sleep(&empty[si], pi);
-          load(k + TP_NST);
+          load(k + NST);
         }
         mbar_wait_sleep(&sdone[so], po);
         const unsigned int q = tile_of(k);
@@ -323,10 +323,10 @@ __global__ void __launch_bounds__(TP_TW + 32, 2) k_pack_tma(const __grid_constan
         bulk_commit();
         if (k >= 1) {                     // the stores of tile k-1 have left their staging buffer
           bulk_wait_read<1>();
-          tc::mbar_arrive(&sfree[so == 0 ? TP_NOUT - 1 : so - 1]);
+          tc::mbar_arrive(&sfree[so == 0 ? NOUT - 1 : so - 1]);
         }
-        if (++si == TP_NST) { si = 0; pi ^= 1u; }
-        if (++so == TP_NOUT) { so = 0; po ^= 1u; }
+        if (++si == NST) { si = 0; pi ^= 1u; }
+        if (++so == NOUT) { so = 0; po ^= 1u; }
       }
       bulk_wait_all();
     }
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(TP_TW + 32, 2) k_pack_tma(const __grid_constan
       bo.h0 = b.hacc[0]; bo.h1 = b.hacc[1]; bo.mask = b.mask; bo.e_in = b.e_in; bo.e_out = b.e_out; bo.cnt = b.cnt; bo.st = b.st;
     }
     st |= bo.st;
-    // staging buffer b2 was last used by tile k - TP_NOUT: wait until its stores have read it
+    // staging buffer b2 was last used by tile k - NOUT: wait until its stores have read it
     mbar_wait_sleep(&sfree[b2], pf);
     unsigned char* o = outs + (size_t)b2 * OUT_BYTES;
     stage_slots16(reinterpret_cast<uint32_t*>(o), bo.s0, bo.s1, lane, warp);
@@ -371,8 +371,8 @@ __global__ void __launch_bounds__(TP_TW + 32, 2) k_pack_tma(const __grid_constan
     }
     fence_proxy_async_smem();
     tc::mbar_arrive(&sdone[b2]);
-    if (++s == TP_NST) { s = 0; ph ^= 1u; }
-    if (++b2 == TP_NOUT) { b2 = 0; pf ^= 1u; }
+    if (++s == NST) { s = 0; ph ^= 1u; }
+    if (++b2 == NOUT) { b2 = 0; pf ^= 1u; }
 
     if (u == 3 || k == n_mine - 1) {
       const unsigned int sg = first + (unsigned)(k >> 2) * G;
@@ -515,10 +515,13 @@ int launch_pack_tma(const QParams& Q, cudaStream_t stream) {
   const bool cvt = Q.c.fin.ebits == 2 && Q.c.fin.bits == 3 && Q.c.fin.max_norm == 6.0f && Q.c.fout.ebits == 4 && Q.c.fout.bits == 5 &&
                    Q.c.fout.max_norm == 448.0f && Q.c.fin.emax == 2 && Q.c.fout.emax == 8 && Q.c.rmode == RD_NEAREST && Q.hi_w == 4 &&
                    !(getenv("MSQ_PACK_CVT") && getenv("MSQ_PACK_CVT")[0] == '0');
-  auto k = cvt ? k_pack_tma<16, true> : k_pack_tma<16, false>;
-  const size_t smem = (size_t)TP_NST * (16 * TP_TW * 4) + TP_NOUT * (16 * (TP_TW / 2) + 16 * (TP_TW / 8) + 2 * TP_TW) +
+  // MSQ_PACK_OCC3=1 (experiment): three CTAs per SM with a 3-stage ring and two staging buffers
+  const bool occ3 = cvt && getenv("MSQ_PACK_OCC3") && getenv("MSQ_PACK_OCC3")[0] == '1';
+  void (*k)(const TmaPackParams) = cvt ? (occ3 ? k_pack_tma<16, true, 3, 2, 3> : k_pack_tma<16, true>) : k_pack_tma<16, false>;
+  const int nst = occ3 ? 3 : TP_NST, nout = occ3 ? 2 : TP_NOUT;
+  const size_t smem = (size_t)nst * (16 * TP_TW * 4) + nout * (16 * (TP_TW / 2) + 16 * (TP_TW / 8) + 2 * TP_TW) +
                       (size_t)MSQ_SEG_BLOCKS * 8 + (size_t)MSQ_SEG_BLOCKS * 16 * 4 / 8 + MSQ_SEG_BLOCKS +
-                      (2 * TP_NST + 2 * TP_NOUT) * sizeof(uint64_t) + 8 * sizeof(int) + 64;
+                      (2 * nst + 2 * nout) * sizeof(uint64_t) + 8 * sizeof(int) + 64;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -257,3 +257,14 @@ def test_pack_conversion_core_narrow_scales(M, kind, sb, monkeypatch):
         nb = (int(p.seg_cnt[s]) * p.hi_w + 7) // 8
         assert torch.equal(p.hi[s * p.hi_seg_stride: s * p.hi_seg_stride + nb], r.hi[s * p.hi_seg_stride: s * p.hi_seg_stride + nb])
     assert int(p.status.item()) == int(r.status.item())
+
+
+@pytest.mark.parametrize("shape", [(16, 256), (48, 512), (64, 1024), (528, 768)])
+def test_unpack_packed_words_small_and_partial_segments(M, shape):
+    """k_unpack_strided_cvt on tensors smaller than one segment / with a partial last segment (threads past the last
+    block read the first row block and store nothing): unpack(pack(W)) == the oracle, fp32 and bf16"""
+    W = weights(shape[0], shape[1], 5)
+    p = M.pack_mx_outlier(W.cuda(), 8, 8, "fp4_e2m1", "fp8_e4m3", 2, [0], 16)
+    y = O.quantize_mx_outlier(W, 8, 8, "fp4_e2m1", "fp8_e4m3", 2, 0, 16)
+    assert_exact(p.dequantize(), y, "fp32")
+    assert_exact(p.dequantize(torch.bfloat16).float(), y.to(torch.bfloat16).float(), "bf16")
