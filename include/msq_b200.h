@@ -355,6 +355,8 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
  * of kind::mxf8f6f4).  Products and fp32 accumulation as the tensor core does them: equal to the fp32 matmul of the
  * dequantized operands up to summation order.  K % 256 == 0; 16-byte aligned operands and pitches. */
 int msq_gemm_mxfp4_tma_tile_tokens(int M, int N, int K);
+/* K slices (split-K through atomics into a zero-filled C) the plan of the TMA-fed kernels gives a problem; 1 = none */
+int msq_gemm_mx_tma_k_slices(int M, int N, int K, int w4a4);
 long long msq_gemm_mxfp4_tma_workspace_bytes(int M, int N, int K);
 int msq_gemm_mxfp4_tma(const unsigned char* xcodes4, long long ldx, const signed char* xe, const unsigned char* w4,
                        long long ldw, const unsigned char* wsf_tiled, float* C, long long ldc, int M, int N, int K,

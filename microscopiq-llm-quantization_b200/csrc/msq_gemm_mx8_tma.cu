@@ -34,6 +34,7 @@ struct YParams {
   float* C; long long ldc;
   int M, N, K, bn, nacc, tiles_n, tiles_m, kblocks, sfb_chunks, accumulate, w_fmt, w_tx_bytes, pdl;
   int epi_h;                  // two-CTA kernel: epilogue warps per TMEM lane quarter (1 or 2)
+  int ksplit, kb_per;         // one-CTA kernel: K slices per tile and stages per slice (ksplit = 1: no split)
   int terms;                  // the activations are `terms` stacked slabs of M rows (msq_split_a16_e4m3) that are ACCUMULATED:
                               // the K loop runs terms * kblocks stages, stage (t, kb) = weight tile kb x slab t's tile kb
   // sparse outlier correction fused into the epilogue (FP4 operand whose outlier slots the tensor core reads as
@@ -102,6 +103,8 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = P.tiles_n * P.tiles_m;
+  // split-K (token counts whose tiles do not fill the SMs): a work item = (tile, K slice); slices add into C by atomics
+  const int num_items = num_tiles * P.ksplit;
   const int band_tiles = YGROUP * P.tiles_n;
   auto tile_coords = [&](int t, int& tn, int& tm) {
     const int band = t / band_tiles;
@@ -131,13 +134,15 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__
     const uint32_t tx = (uint32_t)(P.w_tx_bytes + P.bn * YBK + KC * (512 + 512 * P.sfb_chunks));
     // programmatic dependent of k_tile_scales (which releases us at once): everything up to here overlapped it
     if (P.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
+      const int t = w / P.ksplit, ks = w - t * P.ksplit;
+      const int kb0 = ks * P.kb_per, kb1 = min(P.kblocks / KC, kb0 + P.kb_per);
       int tn, tm; tile_coords(t, tn, tm);
       const uint8_t* wsf = P.wsf_t + (long long)tn * P.kblocks * 512;
       for (int term = 0; term < P.terms; ++term) {
         const uint8_t* xsf = P.xsf_t + ((long long)term * P.tiles_m + tm) * P.kblocks * 512 * P.sfb_chunks;
         const int xrow = term * P.M + tm * P.bn;
-        for (int kb = 0; kb < P.kblocks / KC; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           tc::mbar_wait(&empty[stage], phase ^ 1);
           if (tc::elect_one()) {
             tc::mbar_expect_tx(&full[stage], tx);
@@ -167,11 +172,13 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__
     // scale-factor columns behind the accumulators: F4 keeps the two K chunks of a stage side by side (A: 4 + 4, B: 8 + 8)
     const uint32_t tsfa = tmem_base + (uint32_t)(P.nacc * P.bn), tsfb = tsfa + (F4 ? 8 : 4);
     constexpr int KC = F4 ? 2 : 1;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
+      const int ks = w % P.ksplit;
+      const int nst = P.terms * (min(P.kblocks / KC, ks * P.kb_per + P.kb_per) - ks * P.kb_per);
       tc::mbar_wait(&acc_empty[as], ((acc_phase >> as) & 1u) ^ 1u);
       tc::tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(as * P.bn);
-      for (int kb = 0; kb < P.terms * (P.kblocks / KC); ++kb) {
+      for (int kb = 0; kb < nst; ++kb) {
         tc::mbar_wait(&full[stage], phase);
         tc::tc_fence_after();
         const uint64_t ad = ad0 + (uint64_t)((uint32_t)stage * a_step), bd = bd0 + (uint64_t)((uint32_t)stage * b_step);
@@ -210,12 +217,13 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__
     // ---- epilogue: TMEM lane = output feature, register = token; one register of a warp = 128 contiguous bytes of C
     const int q = warp & 3;
     int as = 0; uint32_t acc_phase = 0;           // bit `as` = phase of accumulator `as`
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int w = blockIdx.x; w < num_items; w += gridDim.x) {
+      const int t = w / P.ksplit, ks = w - t * P.ksplit;
       int tn, tm; tile_coords(t, tn, tm);
       const int n = tn * YM + q * 32 + lane;
       const int m0 = tm * P.bn;
       int oe0 = 0, oe1 = 0;
-      if (P.o_ptr && n < P.N) { oe0 = __ldg(P.o_ptr + n); oe1 = __ldg(P.o_ptr + n + 1); }
+      if (P.o_ptr && n < P.N && ks == 0) { oe0 = __ldg(P.o_ptr + n); oe1 = __ldg(P.o_ptr + n + 1); }
       tc::mbar_wait(&acc_full[as], (acc_phase >> as) & 1u);
       tc::tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * P.bn);
@@ -258,7 +266,8 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__
             if (m0 + c + v < P.M) {
               float* p = crow + (long long)(c + v) * P.ldc;
               const float val = __uint_as_float(r[v]);
-              *p = P.accumulate ? (*p + val) : val;
+              if (P.ksplit > 1) atomicAdd(p, val);
+              else *p = P.accumulate ? (*p + val) : val;
             }
           }
         }
@@ -625,16 +634,66 @@ static int make_tmap_sf(CUtensorMap* out, const void* base, long long rows, int 
 }
 
 // which kernel and which token-tile width a problem gets (shared by the GEMM and the workspace / tile-width queries)
-static void plan(int M, int N, int K, int sms, int& bn, int& nacc, int& cta2, bool f4 = false) {
+static void plan(int M, int N, int K, int sms, int& bn, int& nacc, int& cta2, bool f4 = false, int* ksplit = nullptr) {
   // measured (plain FP4 weight, 4096^2 / 8192^2): M = 64: 10.0 / 16.8 us one CTA, 10.6 / 17.0 us pairs; M = 256: 12.8 / 23.1 vs
   // 11.8 / 19.7; M = 4096: 65.1 / 243.9 vs 55.6 / 201.0 -- pairs from 256 tokens on (MSQ_MX8T_CTA2 = 0 / 1 forces a form)
   const char* e = getenv("MSQ_MX8T_CTA2");
   cta2 = e ? (e[0] == '1') : (M >= 256 && N >= 512);
   if (sms < 2) cta2 = 0;
+  // split-K for the token counts between the decode sizes and the compute-bound ones, whose tiles leave most SMs idle
+  // (4096^2, M = 256: 32 pairs of CTAs on 148 SMs): one-CTA form, every tile cut into K slices that add into C by atomics
+  // (MSQ_MX8T_KSPLIT=0 switches it off).  Slices of at least 4 stages; used when the tiles fill less than half the SMs
+  const char* ek = getenv("MSQ_MX8T_KSPLIT");
+  int ks = 1, bn_s = 0;
+  // measured (scripts/splitk_ab.py): up to 64 tokens and from 32 stages of K on the slices win (FP8 activations, 4096^2 M = 48:
+  // 10.7 -> 9.0 us, 8192^2: 17.8 -> 13.8 us; kind::mxf4 8192^2: 12.6 -> 11.0 us); from 128 tokens on the zero-fill of C and the
+  // atomics cost more than the narrow tiles (4096^2 M = 256: 12.8 -> 15.7 us), so those keep the plan without slices
+  if (!(ek && ek[0] == '0') && !(e && e[0] == '1') && M <= 64 && K / (f4 ? 2 * YBK : YBK) >= 32) {
+    // the alternative to split-K is what choose_bn does on its own: narrow token tiles (4096^2, M = 64: 16 tokens per tile),
+    // i.e. the weight tile streamed once per token tile.  Same cost model for both: bytes a CTA pulls into shared memory
+    int bn1, nacc1;
+    choose_bn(M, N, K, sms, bn1, nacc1, f4);
+    const int tiles_n = (N + YM - 1) / YM;
+    const int kst = K / (f4 ? 2 * YBK : YBK);                           // stages along K
+    const long long tiles1 = (long long)tiles_n * ((M + bn1 - 1) / bn1);
+    const double cost1 = (double)((tiles1 + sms - 1) / sms) * (kst * (YA_BYTES + bn1 * YBK + 4096.0) + (bn1 > 240 ? 135000.0 : 0.0));
+    double best = 0.85 * cost1;                                          // the slices pay a zero-fill and atomics
+    const int cand[] = {240, 224, 208, 192, 176, 160, 144, 128, 112, 96, 80, 64, 48, 32, 16};
+    for (int c : cand) {
+      if (c > 16 && c - 16 >= M) continue;
+      const long long tiles = (long long)tiles_n * ((M + c - 1) / c);
+      if (tiles * 2 > sms || kst < 8) continue;
+      int k = (int)(sms / tiles);
+      if (k > kst / 4) k = kst / 4;
+      if (k > 16) k = 16;
+      if (ek && ek[0] >= '2' && ek[0] <= '9') k = ek[0] - '0';
+      if (k < 2) continue;
+      const double cost = (double)((kst + k - 1) / k) * (YA_BYTES + c * YBK + 4096.0) + 30000.0;
+      if (cost < best) { best = cost; ks = k; bn_s = c; }
+    }
+  }
+  if (ksplit) *ksplit = ks;
+  if (ks > 1) { cta2 = 0; bn = bn_s; nacc = 2; return; }
   // pairs of CTAs over 256-row tiles; with eight epilogue warps per CTA two accumulators of <= 240 columns beat the single
   // 256-column one for FP8 activations as well (8192^3: 2.67 vs 2.94-2.98 PFLOP/s, scripts/mx8_bn_sweep.py)
   if (cta2) choose_bn(M, ((N + 2 * YM - 1) / (2 * YM)) * YM, K, sms / 2, bn, nacc, true);
   else choose_bn(M, N, K, sms, bn, nacc, f4);
+}
+
+// K slices of the one-CTA kernel: stages per slice, slices recounted so that none is empty; zero-fills C when slices add
+static int setup_split(YParams& P, int ksplit, bool f4, cudaStream_t s) {
+  const int kst = P.kblocks / (f4 ? 2 : 1);
+  P.ksplit = 1; P.kb_per = kst;
+  if (ksplit > 1) {
+    P.kb_per = (kst + ksplit - 1) / ksplit;
+    P.ksplit = (kst + P.kb_per - 1) / P.kb_per;
+  }
+  if (P.ksplit > 1 && !P.accumulate) {
+    cudaError_t e = P.ldc == P.N ? cudaMemsetAsync(P.C, 0, (size_t)P.M * P.N * sizeof(float), s)
+                                 : cudaMemset2DAsync(P.C, (size_t)P.ldc * sizeof(float), 0, (size_t)P.N * sizeof(float), (size_t)P.M, s);
+    if (e != cudaSuccess) return MSQ_ERR_CUDA;
+  }
+  return MSQ_OK;
 }
 
 }  // namespace
@@ -713,6 +772,14 @@ static int tile_tokens(int M, int N, int K, bool f4) {
   return bn;
 }
 int msq_gemm_mxfp4_tma_tile_tokens(int M, int N, int K) { return tile_tokens(M, N, K, true); }
+// K slices the plan gives a problem (1 = no split-K); w4a4 != 0: the kind::mxf4 pairing
+int msq_gemm_mx_tma_k_slices(int M, int N, int K, int w4a4) {
+  int dev = 0, sms = 148, bn, nacc, cta2, ks = 1;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 148; }
+  plan(M, N, K, sms, bn, nacc, cta2, w4a4 != 0, &ks);
+  return ks;
+}
 long long msq_gemm_mxfp4_tma_workspace_bytes(int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   const int bn = tile_tokens(M, N, K, true);
@@ -749,9 +816,9 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   YParams P;
   memset(&P, 0, sizeof(P));
-  int cta2 = 0;
-  plan(M, N, K, sms, P.bn, P.nacc, cta2);
-  if (o_ptr) { cta2 = 0; choose_bn(M, N, K, sms, P.bn, P.nacc); }       // the fused sparse epilogue lives in the one-CTA kernel
+  int cta2 = 0, ksplit = 1;
+  plan(M, N, K, sms, P.bn, P.nacc, cta2, false, &ksplit);
+  if (o_ptr && cta2) { cta2 = 0; choose_bn(M, N, K, sms, P.bn, P.nacc); }       // the fused sparse epilogue lives in the one-CTA kernel
   P.wsf_t = wsf_tiled; P.xsf_t = reinterpret_cast<const uint8_t*>(workspace); P.C = C; P.ldc = ldc;
   P.M = M; P.N = N; P.K = K; P.accumulate = accumulate; P.terms = terms;
   P.o_ptr = o_ptr; P.o_k = o_k; P.o_dw = o_dw; P.xcodes = xcodes; P.ldx = ldx; P.xe = xe;
@@ -759,7 +826,11 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
   P.w_fmt = w_is_fp4 ? 5 : 0;
   // a 16U4_ALIGN16B load reports the bytes it READ to the mbarrier (see msq_gemm_mx8.cu)
   P.w_tx_bytes = w_is_fp4 ? YA_BYTES / 2 : YA_BYTES;
-  int rc = tile_scales(xe, 1, M, K, P.bn, reinterpret_cast<unsigned char*>(workspace), terms, stream);
+  // (the zero-fill of a split-K result goes in front of the scale tiling, so that the GEMM stays the programmatic dependent
+  // of the tiling kernel)
+  int rc = setup_split(P, cta2 ? 1 : ksplit, false, s);
+  if (rc) return rc;
+  rc = tile_scales(xe, 1, M, K, P.bn, reinterpret_cast<unsigned char*>(workspace), terms, stream);
   if (rc) return rc;
   CUtensorMap tmX, tmW;
   rc = make_tmap_2d(&tmX, xcodes, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, (long long)terms * M, K, ldx, P.bn, YBK);
@@ -794,7 +865,7 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
     return cudaLaunchKernelEx(&cfg, k_gemm_mx8_tma2<false>, tmXh, tmW, tmXSF, tmWSF, P) == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
   }
   if (cudaFuncSetAttribute(k_gemm_mx8_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Y_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
-  int grid = P.tiles_n * P.tiles_m;
+  int grid = P.tiles_n * P.tiles_m * P.ksplit;
   if (grid > sms) grid = sms;
   if (getenv("MSQ_MX8_NO_PDL") == nullptr) {
     P.pdl = 1;
@@ -832,13 +903,15 @@ int msq_gemm_mxfp4_tma(const unsigned char* xcodes4, long long ldx, const signed
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   YParams P;
   memset(&P, 0, sizeof(P));
-  int cta2 = 0;
-  plan(M, N, K, sms, P.bn, P.nacc, cta2, true);       // same plan as the workspace query (the tiled activation scales depend on bn)
+  int cta2 = 0, ksplit = 1;
+  plan(M, N, K, sms, P.bn, P.nacc, cta2, true, &ksplit);       // same plan as the workspace query (the tiled activation scales depend on bn)
   P.wsf_t = wsf_tiled; P.xsf_t = reinterpret_cast<const uint8_t*>(workspace); P.C = C; P.ldc = ldc;
   P.M = M; P.N = N; P.K = K; P.accumulate = accumulate; P.terms = 1;
   P.tiles_n = (N + YM - 1) / YM; P.tiles_m = (M + P.bn - 1) / P.bn; P.kblocks = K / YBK; P.sfb_chunks = (P.bn + 127) / 128;
   P.w_tx_bytes = YA_BYTES;
-  int rc = tile_scales(xe, 1, M, K, P.bn, reinterpret_cast<unsigned char*>(workspace), 1, stream);
+  int rc = setup_split(P, cta2 ? 1 : ksplit, true, s);
+  if (rc) return rc;
+  rc = tile_scales(xe, 1, M, K, P.bn, reinterpret_cast<unsigned char*>(workspace), 1, stream);
   if (rc) return rc;
   CUtensorMap tmX, tmW;
   rc = make_tmap_2d(&tmX, xcodes4, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K / 2, ldx, P.bn, YBK);
@@ -871,7 +944,7 @@ int msq_gemm_mxfp4_tma(const unsigned char* xcodes4, long long ldx, const signed
     return cudaLaunchKernelEx(&cfg, k_gemm_mx8_tma2<true>, tmXh, tmW, tmXSF, tmWSF, P) == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
   }
   if (cudaFuncSetAttribute(k_gemm_mx8_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Y_SMEM) != cudaSuccess) return MSQ_ERR_CUDA;
-  int grid = P.tiles_n * P.tiles_m;
+  int grid = P.tiles_n * P.tiles_m * P.ksplit;
   if (grid > sms) grid = sms;
   P.pdl = 1;
   cudaLaunchConfig_t cfg;
