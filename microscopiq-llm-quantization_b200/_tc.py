@@ -515,6 +515,7 @@ N.register("msq_gemm_mxfp8_tma_workspace_bytes", _ll, [_i, _i, _i])
 N.register("msq_gemm_mxfp8_tma", _i, [_p, _ll, _p, _p, _ll, _i, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _p, _ll, _p])
 
 N.register("msq_sparse_outlier_correct_fp4", _i, [_p, _ll, _p, _p, _p, _p, _i, _p, _ll, _i, _i, _i, _p])
+N.register("msq_gemm_mx_tma_k_slices", _i, [_i, _i, _i, _i])
 N.register("msq_gemm_mxfp4_tma_tile_tokens", _i, [_i, _i, _i])
 N.register("msq_gemm_mxfp4_tma_workspace_bytes", _ll, [_i, _i, _i])
 N.register("msq_gemm_mxfp4_tma", _i, [_p, _ll, _p, _p, _ll, _p, _p, _ll, _i, _i, _i, _i, _p, _ll, _p])

@@ -148,3 +148,24 @@ def test_mxlinear_serving_mode(M, a_fmt):
     for bf in (torch.bfloat16, torch.float16):           # 16-bit activations are read as they are
         yb = lin(x.to(bf))
         assert yb.dtype == bf and torch.isfinite(yb).all()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("Mx,N,K", [(48, 512, 4096), (64, 4096, 4096), (33, 384, 8192), (64, 1000, 8192)])
+def test_split_k_between_decode_and_compute_bound_sizes(M, Mx, N, K):
+    """33..64 tokens: the plan cuts every tile into K slices that add into a zero-filled C by atomics (both pairings);
+    result within the summation-order bound, and a second call into the SAME output buffer starts from zero again"""
+    from msq_b200 import _tc
+    g = torch.Generator().manual_seed(N + K + Mx)
+    W = torch.randn(N, K, generator=g) * 0.02
+    x = torch.randn(Mx, K, generator=g) * torch.logspace(-1, 1, Mx).unsqueeze(1)
+    pw = M.pack_mx(W.cuda(), 8, "fp4_e2m1", axes=[1], block_size=32)
+    for fmt, fn, w4a4 in (("fp8_e4m3", _tc.packed_linear_mx8, 0), ("fp4_e2m1", _tc.packed_linear_mx4, 1)):
+        ks = _tc.N.lib().msq_gemm_mx_tma_k_slices(Mx, N, K, w4a4)
+        if K // (256 if w4a4 else 128) >= 32:
+            assert ks > 1, (fmt, ks)
+        xq = M.pack_mx(x.cuda(), 8, fmt, axes=[-1], block_size=32)
+        y = fn(xq, pw)
+        check(y.cpu(), xq.dequantize().cpu(), pw.dequantize().cpu())
+        y2 = fn(xq, pw)
+        check(y2.cpu(), xq.dequantize().cpu(), pw.dequantize().cpu())
