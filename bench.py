@@ -365,6 +365,26 @@ def extras(dev, dev_w, nel):
     act["note"] = "8192 x 8192 activations, blocks of 32 along K; algorithmic bytes = input + codes + 1 exponent byte per block"
     torch.cuda.empty_cache()
     out["activation_quant"] = act
+    # (7) the two together: MXLinear.from_packed(..., fast_activations=True) on bf16 activations (one-launch activation
+    # quantizer + block-scaled GEMM on the packed FP4 weight), device time of the whole forward, next to the bf16 library
+    # linear on the dequantized weight
+    srv = {}
+    pws = msq_b200.pack_mx(W, 8, "fp4_e2m1", axes=[1], block_size=32)
+    wb = pws.dequantize(torch.bfloat16)
+    for a_fmt, nm in (("fp4_e2m1", "w4a4"), ("fp8_e4m3", "w4a8")):
+        lin = msq_b200.MXLinear.from_packed(pws, mx_specs={"w_elem_format": "fp4_e2m1", "a_elem_format": a_fmt, "block_size": 32,
+                                                           "scale_bits": 8}, fast_activations=True)
+        for M in (16, 256, 4096):
+            xs = torch.randn(M, 4096, device=dev).to(torch.bfloat16)
+            ms = _time_ms_device(lambda: lin(xs), 10)
+            srv["%s_M%d" % (nm, M)] = {"ms": ms, "TFLOPs": 2.0 * M * 4096 * 4096 / (ms * 1e-3) / 1e12}
+    for M in (16, 256, 4096):
+        xs = torch.randn(M, 4096, device=dev).to(torch.bfloat16)
+        srv["cublas_bf16_M%d_ms" % M] = _time_ms_device(lambda: torch.nn.functional.linear(xs, wb), 10)
+    srv["note"] = "K = N = 4096, bf16 activations in, bf16 out; activation quantization included in the timed forward"
+    del wb, pws
+    torch.cuda.empty_cache()
+    out["mxlinear_serving_k4096_n4096"] = srv
     return out
 
 
