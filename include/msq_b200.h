@@ -358,6 +358,12 @@ int msq_gemm_mxfp4_tma_tile_tokens(int M, int N, int K);
 /* K slices (split-K through atomics into a zero-filled C) the plan of the TMA-fed kernels gives a problem; 1 = none */
 int msq_gemm_mx_tma_k_slices(int M, int N, int K, int w4a4);
 long long msq_gemm_mxfp4_tma_workspace_bytes(int M, int N, int K);
+/* ..._bf16: the result as bf16 [M, ldc] (rounded once from the fp32 accumulator) for callers that want 16-bit activations
+ * back; own workspace query (no K slices there) */
+long long msq_gemm_mxfp4_tma_bf16_workspace_bytes(int M, int N, int K);
+int msq_gemm_mxfp4_tma_bf16(const unsigned char* xcodes4, long long ldx, const signed char* xe, const unsigned char* w4,
+                            long long ldw, const unsigned char* wsf_tiled, void* C_bf16, long long ldc, int M, int N,
+                            int K, void* workspace, long long workspace_bytes, void* stream);
 int msq_gemm_mxfp4_tma(const unsigned char* xcodes4, long long ldx, const signed char* xe, const unsigned char* w4,
                        long long ldw, const unsigned char* wsf_tiled, float* C, long long ldc, int M, int N, int K,
                        int accumulate, void* workspace, long long workspace_bytes, void* stream);

@@ -516,6 +516,8 @@ N.register("msq_gemm_mxfp8_tma", _i, [_p, _ll, _p, _p, _ll, _i, _p, _p, _p, _p, 
 
 N.register("msq_sparse_outlier_correct_fp4", _i, [_p, _ll, _p, _p, _p, _p, _i, _p, _ll, _i, _i, _i, _p])
 N.register("msq_gemm_mx_tma_k_slices", _i, [_i, _i, _i, _i])
+N.register("msq_gemm_mxfp4_tma_bf16_workspace_bytes", _ll, [_i, _i, _i])
+N.register("msq_gemm_mxfp4_tma_bf16", _i, [_p, _ll, _p, _p, _ll, _p, _p, _ll, _i, _i, _i, _p, _ll, _p])
 N.register("msq_gemm_mxfp4_tma_tile_tokens", _i, [_i, _i, _i])
 N.register("msq_gemm_mxfp4_tma_workspace_bytes", _ll, [_i, _i, _i])
 N.register("msq_gemm_mxfp4_tma", _i, [_p, _ll, _p, _p, _ll, _p, _p, _ll, _i, _i, _i, _i, _p, _ll, _p])
@@ -537,7 +539,7 @@ def mx4_pair_ok(pw, M=1):
     return o_k is None or o_k.numel() * float(M) <= MX8_TMA_SPARSE_BUDGET
 
 
-def packed_linear_mx4(xq, pw, bias=None, assume_clean=False):
+def packed_linear_mx4(xq, pw, bias=None, assume_clean=False, out_dtype=torch.float32):
     """W4A4: y = dq(xq) @ dq(pw).T with BOTH operands as packed FP4 codes on tcgen05 kind::mxf4.block_scale (K = 64 per
     instruction, twice the rate of kind::mxf8f6f4).  xq: FP4 (E2M1) activations packed along K with block 32 and no
     outliers (pack_mx, or pack_mx_outlier with an empty bitmap -- checked here unless assume_clean); pw: an FP4 weight
@@ -558,6 +560,16 @@ def packed_linear_mx4(xq, pw, bias=None, assume_clean=False):
     wsf_t = getattr(pw, "_mx4_sf_tiled", None)
     if wsf_t is None:
         wsf_t = pw._mx4_sf_tiled = tile_scales(pw.e_in.reshape(Nn, K // 32))
+    has_outliers = (not pw.plain) and mx4_sparse_outliers(pw)[1] is not None and mx4_sparse_outliers(pw)[1].numel() > 0
+    if out_dtype == torch.bfloat16 and bias is None and not has_outliers:
+        # the result leaves the epilogue as bf16 (rounded once from the fp32 accumulator): no conversion pass behind the GEMM
+        out = torch.empty(M, Nn, dtype=torch.bfloat16, device=pw.codes.device)
+        nbytes = int(N.lib().msq_gemm_mxfp4_tma_bf16_workspace_bytes(M, Nn, K))
+        ws = _workspace(nbytes, out.device)
+        rc = N.lib().msq_gemm_mxfp4_tma_bf16(N.ptr(xq.codes), K // 2, N.ptr(xq.e_in), N.ptr(pw.codes), K // 2, N.ptr(wsf_t),
+                                             N.ptr(out), out.stride(0), M, Nn, K, N.ptr(ws), nbytes, N.stream_ptr(out.device))
+        N.check(rc, "msq_gemm_mxfp4_tma_bf16")
+        return out.reshape(*xq.shape[:-1], Nn)
     out = torch.empty(M, Nn, dtype=torch.float32, device=pw.codes.device)
     nbytes = int(N.lib().msq_gemm_mxfp4_tma_workspace_bytes(M, Nn, K))
     ws = _workspace(nbytes, out.device)

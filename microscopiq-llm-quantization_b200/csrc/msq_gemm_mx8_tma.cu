@@ -16,6 +16,7 @@
 // Weight operand: dense E4M3 bytes [N, K] (the widened copy, outliers folded: msq_widen_fp4_to_mxfp8), or the packed 4-bit
 // codes themselves (plain FP4 weight; CU_TENSOR_MAP_DATA_TYPE_16U4_ALIGN16B expands 16 codes into a 16-byte chunk).
 #include <stdlib.h>
+#include <cuda_bf16.h>
 #include "msq_api_internal.h"
 #include "msq_common.cuh"
 #include "msq_tc.cuh"
@@ -35,6 +36,7 @@ struct YParams {
   int M, N, K, bn, nacc, tiles_n, tiles_m, kblocks, sfb_chunks, accumulate, w_fmt, w_tx_bytes, pdl;
   int epi_h;                  // two-CTA kernel: epilogue warps per TMEM lane quarter (1 or 2)
   int ksplit, kb_per;         // one-CTA kernel: K slices per tile and stages per slice (ksplit = 1: no split)
+  int c_bf16;                 // C is bf16 [M, ldc] (plain store, no accumulate / split-K) instead of fp32
   int terms;                  // the activations are `terms` stacked slabs of M rows (msq_split_a16_e4m3) that are ACCUMULATED:
                               // the K loop runs terms * kblocks stages, stage (t, kb) = weight tile kb x slab t's tile kb
   // sparse outlier correction fused into the epilogue (FP4 operand whose outlier slots the tensor core reads as
@@ -264,10 +266,14 @@ __global__ void __launch_bounds__(256, 1) k_gemm_mx8_tma(const __grid_constant__
 #pragma unroll
           for (int v = 0; v < 16; ++v) {
             if (m0 + c + v < P.M) {
-              float* p = crow + (long long)(c + v) * P.ldc;
               const float val = __uint_as_float(r[v]);
-              if (P.ksplit > 1) atomicAdd(p, val);
-              else *p = P.accumulate ? (*p + val) : val;
+              if (P.c_bf16) {
+                reinterpret_cast<__nv_bfloat16*>(P.C)[(long long)(m0 + c + v) * P.ldc + n] = __float2bfloat16_rn(val);
+              } else {
+                float* p = crow + (long long)(c + v) * P.ldc;
+                if (P.ksplit > 1) atomicAdd(p, val);
+                else *p = P.accumulate ? (*p + val) : val;
+              }
             }
           }
         }
@@ -515,9 +521,13 @@ __global__ void __launch_bounds__(384, 1) k_gemm_mx8_tma2(const __grid_constant_
 #pragma unroll
           for (int v = 0; v < 16; ++v) {
             if (m0 + c + v < P.M) {
-              float* p = crow + (long long)(c + v) * P.ldc;
               const float val = __uint_as_float(r[v]);
-              *p = P.accumulate ? (*p + val) : val;
+              if (P.c_bf16) {
+                reinterpret_cast<__nv_bfloat16*>(P.C)[(long long)(m0 + c + v) * P.ldc + n] = __float2bfloat16_rn(val);
+              } else {
+                float* p = crow + (long long)(c + v) * P.ldc;
+                *p = P.accumulate ? (*p + val) : val;
+              }
             }
           }
         }
@@ -634,7 +644,8 @@ static int make_tmap_sf(CUtensorMap* out, const void* base, long long rows, int 
 }
 
 // which kernel and which token-tile width a problem gets (shared by the GEMM and the workspace / tile-width queries)
-static void plan(int M, int N, int K, int sms, int& bn, int& nacc, int& cta2, bool f4 = false, int* ksplit = nullptr) {
+static void plan(int M, int N, int K, int sms, int& bn, int& nacc, int& cta2, bool f4 = false, int* ksplit = nullptr,
+                 bool allow_split = true) {
   // measured (plain FP4 weight, 4096^2 / 8192^2): M = 64: 10.0 / 16.8 us one CTA, 10.6 / 17.0 us pairs; M = 256: 12.8 / 23.1 vs
   // 11.8 / 19.7; M = 4096: 65.1 / 243.9 vs 55.6 / 201.0 -- pairs from 256 tokens on (MSQ_MX8T_CTA2 = 0 / 1 forces a form)
   const char* e = getenv("MSQ_MX8T_CTA2");
@@ -648,7 +659,7 @@ static void plan(int M, int N, int K, int sms, int& bn, int& nacc, int& cta2, bo
   // measured (scripts/splitk_ab.py): up to 64 tokens and from 32 stages of K on the slices win (FP8 activations, 4096^2 M = 48:
   // 10.7 -> 9.0 us, 8192^2: 17.8 -> 13.8 us; kind::mxf4 8192^2: 12.6 -> 11.0 us); from 128 tokens on the zero-fill of C and the
   // atomics cost more than the narrow tiles (4096^2 M = 256: 12.8 -> 15.7 us), so those keep the plan without slices
-  if (!(ek && ek[0] == '0') && !(e && e[0] == '1') && M <= 64 && K / (f4 ? 2 * YBK : YBK) >= 32) {
+  if (allow_split && !(ek && ek[0] == '0') && !(e && e[0] == '1') && M <= 64 && K / (f4 ? 2 * YBK : YBK) >= 32) {
     // the alternative to split-K is what choose_bn does on its own: narrow token tiles (4096^2, M = 64: 16 tokens per tile),
     // i.e. the weight tile streamed once per token tile.  Same cost model for both: bytes a CTA pulls into shared memory
     int bn1, nacc1;
@@ -886,9 +897,35 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
 // first, K-major) and int8 shared exponents per 32 values of K (activations) / pre-tiled UE8M0 chunks (weight,
 // msq_tile_scales_ue8m0): tcgen05.mma kind::mxf4.block_scale.scale_vec::2X, K = 64 per instruction.  ldx / ldw in BYTES.
 // Workspace: msq_gemm_mxfp4_tma_workspace_bytes(M, N, K).  K % 256 == 0.
+static int gemm_mxfp4(const unsigned char* xcodes4, long long ldx, const signed char* xe, const unsigned char* w4, long long ldw,
+                      const unsigned char* wsf_tiled, void* Cv, int c_is_bf16, long long ldc, int M, int N, int K, int accumulate,
+                      void* workspace, long long workspace_bytes, void* stream);
 int msq_gemm_mxfp4_tma(const unsigned char* xcodes4, long long ldx, const signed char* xe, const unsigned char* w4, long long ldw,
                        const unsigned char* wsf_tiled, float* C, long long ldc, int M, int N, int K, int accumulate, void* workspace,
                        long long workspace_bytes, void* stream) {
+  return gemm_mxfp4(xcodes4, ldx, xe, w4, ldw, wsf_tiled, C, 0, ldc, M, N, K, accumulate, workspace, workspace_bytes, stream);
+}
+// the same with a bf16 result [M, ldc] (rounded once from the fp32 accumulator; no accumulate, no K slices): saves the
+// conversion pass behind the GEMM when the caller wants 16-bit activations back.  Workspace:
+// msq_gemm_mxfp4_tma_bf16_workspace_bytes (the plan without K slices can pick another token-tile width)
+long long msq_gemm_mxfp4_tma_bf16_workspace_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  int dev = 0, sms = 148, bn, nacc, cta2;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 148; }
+  plan(M, N, K, sms, bn, nacc, cta2, true, nullptr, false);
+  const long long tiles_m = (M + bn - 1) / bn, kblocks = (K + YBK - 1) / YBK, chunks = (bn + 127) / 128;
+  return tiles_m * kblocks * chunks * 512 + 1024;
+}
+int msq_gemm_mxfp4_tma_bf16(const unsigned char* xcodes4, long long ldx, const signed char* xe, const unsigned char* w4, long long ldw,
+                            const unsigned char* wsf_tiled, void* C_bf16, long long ldc, int M, int N, int K, void* workspace,
+                            long long workspace_bytes, void* stream) {
+  return gemm_mxfp4(xcodes4, ldx, xe, w4, ldw, wsf_tiled, C_bf16, 1, ldc, M, N, K, 0, workspace, workspace_bytes, stream);
+}
+static int gemm_mxfp4(const unsigned char* xcodes4, long long ldx, const signed char* xe, const unsigned char* w4, long long ldw,
+                      const unsigned char* wsf_tiled, void* Cv, int c_is_bf16, long long ldc, int M, int N, int K, int accumulate,
+                      void* workspace, long long workspace_bytes, void* stream) {
+  float* C = reinterpret_cast<float*>(Cv);
   msq::DevGuard dev_guard_(xcodes4);
   if (!xcodes4 || !xe || !w4 || !wsf_tiled || !C || !workspace || M <= 0 || N <= 0 || K <= 0) return MSQ_ERR_BAD_ARG;
   if (K % 256 != 0) return MSQ_ERR_UNSUPPORTED;
@@ -896,7 +933,8 @@ int msq_gemm_mxfp4_tma(const unsigned char* xcodes4, long long ldx, const signed
       (reinterpret_cast<uintptr_t>(w4) & 15) || (ldw % 16) || (reinterpret_cast<uintptr_t>(wsf_tiled) & 15) ||
       (reinterpret_cast<uintptr_t>(workspace) & 15))
     return MSQ_ERR_ALIGN;
-  if (workspace_bytes < msq_gemm_mxfp4_tma_workspace_bytes(M, N, K)) return MSQ_ERR_BAD_ARG;
+  if (workspace_bytes < (c_is_bf16 ? msq_gemm_mxfp4_tma_bf16_workspace_bytes(M, N, K) : msq_gemm_mxfp4_tma_workspace_bytes(M, N, K)))
+    return MSQ_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -904,7 +942,8 @@ int msq_gemm_mxfp4_tma(const unsigned char* xcodes4, long long ldx, const signed
   YParams P;
   memset(&P, 0, sizeof(P));
   int cta2 = 0, ksplit = 1;
-  plan(M, N, K, sms, P.bn, P.nacc, cta2, true, &ksplit);       // same plan as the workspace query (the tiled activation scales depend on bn)
+  P.c_bf16 = c_is_bf16 ? 1 : 0;
+  plan(M, N, K, sms, P.bn, P.nacc, cta2, true, &ksplit, !c_is_bf16);       // same plan as the workspace query (the tiled activation scales depend on bn)
   P.wsf_t = wsf_tiled; P.xsf_t = reinterpret_cast<const uint8_t*>(workspace); P.C = C; P.ldc = ldc;
   P.M = M; P.N = N; P.K = K; P.accumulate = accumulate; P.terms = 1;
   P.tiles_n = (N + YM - 1) / YM; P.tiles_m = (M + P.bn - 1) / P.bn; P.kblocks = K / YBK; P.sfb_chunks = (P.bn + 127) / 128;

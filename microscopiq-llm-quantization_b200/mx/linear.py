@@ -201,7 +201,7 @@ class MXLinear(torch.nn.Linear):
                      flush_fp32_subnorms=self.mx_specs["mx_flush_fp32_subnorms"])
         try:
             if fp == (2, 3) and _tc.mx4_pair_ok(pw, x2.shape[0]):
-                y = _tc.packed_linear_mx4(xq, pw, bias=self.bias)
+                y = _tc.packed_linear_mx4(xq, pw, bias=self.bias, out_dtype=inputs.dtype)
             elif fp == (4, 5):
                 y = _tc.packed_linear_mx8(xq, pw, bias=self.bias)
             else:

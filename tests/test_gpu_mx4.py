@@ -169,3 +169,23 @@ def test_split_k_between_decode_and_compute_bound_sizes(M, Mx, N, K):
         check(y.cpu(), xq.dequantize().cpu(), pw.dequantize().cpu())
         y2 = fn(xq, pw)
         check(y2.cpu(), xq.dequantize().cpu(), pw.dequantize().cpu())
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("Mx,N,K", [(5, 128, 256), (48, 512, 8192), (300, 640, 1024), (1000, 1000, 2048)])
+def test_w4a4_bf16_result(M, Mx, N, K):
+    """msq_gemm_mxfp4_tma_bf16: the accumulator leaves the epilogue as bf16 -- the fp32 result rounded once (identical bits
+    where both calls use the same plan; within half a bf16 ulp where the fp32 call splits K)"""
+    from msq_b200 import _tc
+    g = torch.Generator().manual_seed(N + K + Mx)
+    W = torch.randn(N, K, generator=g) * 0.02
+    x = torch.randn(Mx, K, generator=g)
+    pw = M.pack_mx(W.cuda(), 8, "fp4_e2m1", axes=[1], block_size=32)
+    xq = M.pack_mx(x.cuda(), 8, "fp4_e2m1", axes=[-1], block_size=32)
+    y32 = _tc.packed_linear_mx4(xq, pw)
+    y16 = _tc.packed_linear_mx4(xq, pw, out_dtype=torch.bfloat16)
+    assert y16.dtype == torch.bfloat16 and y16.shape == y32.shape
+    if _tc.N.lib().msq_gemm_mx_tma_k_slices(Mx, N, K, 1) == 1:
+        assert torch.equal(y16, y32.to(torch.bfloat16))
+    else:
+        assert float((y16.float() - y32).abs().max()) <= 2.0 ** -8 * float(y32.abs().max())
