@@ -348,6 +348,12 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
                        long long ldw, int w_is_fp4, const unsigned char* wsf_tiled, const int* o_ptr, const int* o_k,
                        const float* o_dw, float* C, long long ldc, int M, int N, int K, int terms, int accumulate,
                        void* workspace, long long workspace_bytes, void* stream);
+/* ..._bf16: one term, the result as bf16 [M, ldc] rounded once from the fp32 accumulator (no accumulate, no fused sparse
+ * epilogue -- apply msq_sparse_outlier_correct to an fp32 result instead --, no K slices); own workspace query */
+long long msq_gemm_mxfp8_tma_bf16_workspace_bytes(int M, int N, int K);
+int msq_gemm_mxfp8_tma_bf16(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* w,
+                            long long ldw, int w_is_fp4, const unsigned char* wsf_tiled, void* C_bf16, long long ldc,
+                            int M, int N, int K, void* workspace, long long workspace_bytes, void* stream);
 /* W4A4 (replaces F.linear on the two fake-quantized operands of number_system/mx/linear.py:66-91 when a_elem_format and
  * w_elem_format are both fp4_e2m1): BOTH operands packed FP4 (two codes per byte, low nibble = lower k, K-major; ldx / ldw in
  * bytes), activations with int8 shared exponents [M, K/32] (tiled into `workspace`, msq_gemm_mxfp4_tma_workspace_bytes), weight with

@@ -516,6 +516,8 @@ N.register("msq_gemm_mxfp8_tma", _i, [_p, _ll, _p, _p, _ll, _i, _p, _p, _p, _p, 
 
 N.register("msq_sparse_outlier_correct_fp4", _i, [_p, _ll, _p, _p, _p, _p, _i, _p, _ll, _i, _i, _i, _p])
 N.register("msq_gemm_mx_tma_k_slices", _i, [_i, _i, _i, _i])
+N.register("msq_gemm_mxfp8_tma_bf16_workspace_bytes", _ll, [_i, _i, _i])
+N.register("msq_gemm_mxfp8_tma_bf16", _i, [_p, _ll, _p, _p, _ll, _i, _p, _p, _ll, _i, _i, _i, _p, _ll, _p])
 N.register("msq_gemm_mxfp4_tma_bf16_workspace_bytes", _ll, [_i, _i, _i])
 N.register("msq_gemm_mxfp4_tma_bf16", _i, [_p, _ll, _p, _p, _ll, _p, _p, _ll, _i, _i, _i, _p, _ll, _p])
 N.register("msq_gemm_mxfp4_tma_tile_tokens", _i, [_i, _i, _i])
@@ -652,7 +654,7 @@ def mx8_tma_weight(pw, allow_copy=True, sparse_limit=None):
     return (dense[0], K, 0, sf_t[1], None, None, None)
 
 
-def packed_linear_mx8(xq, pw, bias=None, cache_dense=False, accumulate_terms=False):
+def packed_linear_mx8(xq, pw, bias=None, cache_dense=False, accumulate_terms=False, out_dtype=torch.float32):
     """y = dq(xq) @ dq(pw).T on tcgen05 kind::mxf8f6f4.block_scale.  xq: PackedMX of the activations
     ([..., K], FP8 E4M3, block 32 along the last axis, no outliers); pw: packed FP4 weight (mx8_weight_ok).
     Routing: M <= 32 -> the packed codes by TMA + sparse outlier epilogue (msq_gemm_mxfp4w_tiled_blockscaled);
@@ -685,6 +687,16 @@ def packed_linear_mx8(xq, pw, bias=None, cache_dense=False, accumulate_terms=Fal
         op = mx8_tma_weight(pw, allow_copy=cache_dense or dense is not None or M >= MX8_DENSE_MIN_M,
                             sparse_limit=-1.0 if cache_dense else
                             (MX8_TMA_SPARSE_BUDGET if M < MX8_DENSE_MIN_M else MX8_TMA_SPARSE_BUDGET_LARGE_M) / (float(M) * Nn))
+        if op is not None and out_dtype == torch.bfloat16 and bias is None and terms == 1 and op[4] is None:
+            # no outliers to correct, one term: the accumulator leaves the epilogue as bf16 (no conversion pass behind the GEMM)
+            w, ldw, is_fp4, wsf_t = op[:4]
+            out = torch.empty(M, Nn, dtype=torch.bfloat16, device=pw.codes.device)
+            nbytes = int(N.lib().msq_gemm_mxfp8_tma_bf16_workspace_bytes(M, Nn, K))
+            ws = _workspace(nbytes, out.device)
+            rc = N.lib().msq_gemm_mxfp8_tma_bf16(N.ptr(xq.codes), K, N.ptr(xq.e_in), N.ptr(w), ldw, is_fp4, N.ptr(wsf_t), N.ptr(out),
+                                                 out.stride(0), M, Nn, K, N.ptr(ws), nbytes, N.stream_ptr(out.device))
+            N.check(rc, "msq_gemm_mxfp8_tma_bf16")
+            return out.reshape(*xq.shape[:-1], Nn)
         if op is not None:
             out = torch.empty(M, Nn, dtype=torch.float32, device=pw.codes.device)
             w, ldw, is_fp4, wsf_t, o_ptr, o_k, o_dw = op

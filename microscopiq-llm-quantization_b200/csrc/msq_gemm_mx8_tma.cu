@@ -806,10 +806,39 @@ long long msq_gemm_mxfp8_tma_workspace_bytes(int M, int N, int K) {
   return 3 * tiles_m * kblocks * chunks * 512 + 1024;
 }
 
+static int gemm_mxfp8(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* w, long long ldw,
+                      int w_is_fp4, const unsigned char* wsf_tiled, const int* o_ptr, const int* o_k, const float* o_dw, void* Cv,
+                      int c_is_bf16, long long ldc, int M, int N, int K, int terms, int accumulate, void* workspace,
+                      long long workspace_bytes, void* stream);
 int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* w, long long ldw,
                        int w_is_fp4, const unsigned char* wsf_tiled, const int* o_ptr, const int* o_k, const float* o_dw, float* C,
                        long long ldc, int M, int N, int K, int terms, int accumulate, void* workspace, long long workspace_bytes,
                        void* stream) {
+  return gemm_mxfp8(xcodes, ldx, xe, w, ldw, w_is_fp4, wsf_tiled, o_ptr, o_k, o_dw, C, 0, ldc, M, N, K, terms, accumulate, workspace,
+                    workspace_bytes, stream);
+}
+// the same with a bf16 result [M, ldc] (one term, no accumulate, no fused sparse epilogue, no K slices); workspace:
+// msq_gemm_mxfp8_tma_bf16_workspace_bytes
+long long msq_gemm_mxfp8_tma_bf16_workspace_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  int dev = 0, sms = 148, bn, nacc, cta2;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 148; }
+  plan(M, N, K, sms, bn, nacc, cta2, false, nullptr, false);
+  const long long tiles_m = (M + bn - 1) / bn, kblocks = (K + YBK - 1) / YBK, chunks = (bn + 127) / 128;
+  return tiles_m * kblocks * chunks * 512 + 1024;
+}
+int msq_gemm_mxfp8_tma_bf16(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* w, long long ldw,
+                            int w_is_fp4, const unsigned char* wsf_tiled, void* C_bf16, long long ldc, int M, int N, int K,
+                            void* workspace, long long workspace_bytes, void* stream) {
+  return gemm_mxfp8(xcodes, ldx, xe, w, ldw, w_is_fp4, wsf_tiled, nullptr, nullptr, nullptr, C_bf16, 1, ldc, M, N, K, 1, 0, workspace,
+                    workspace_bytes, stream);
+}
+static int gemm_mxfp8(const unsigned char* xcodes, long long ldx, const signed char* xe, const unsigned char* w, long long ldw,
+                      int w_is_fp4, const unsigned char* wsf_tiled, const int* o_ptr, const int* o_k, const float* o_dw, void* Cv,
+                      int c_is_bf16, long long ldc, int M, int N, int K, int terms, int accumulate, void* workspace,
+                      long long workspace_bytes, void* stream) {
+  float* C = reinterpret_cast<float*>(Cv);
   msq::DevGuard dev_guard_(xcodes);
   if (!xcodes || !xe || !w || !wsf_tiled || !C || !workspace || M <= 0 || N <= 0 || K <= 0) return MSQ_ERR_BAD_ARG;
   if (K % 128 != 0) return MSQ_ERR_UNSUPPORTED;
@@ -820,7 +849,8 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
   if (w_is_fp4 && (ldw % 32)) return MSQ_ERR_ALIGN;
   if (o_ptr && (!o_k || !o_dw)) return MSQ_ERR_BAD_ARG;
   if (terms < 1 || terms > 3 || (terms > 1 && o_ptr)) return MSQ_ERR_BAD_ARG;     // stacked terms: corrections by msq_sparse_outlier_correct
-  if (workspace_bytes < msq_gemm_mxfp8_tma_workspace_bytes(M, N, K)) return MSQ_ERR_BAD_ARG;
+  if (workspace_bytes < (c_is_bf16 ? msq_gemm_mxfp8_tma_bf16_workspace_bytes(M, N, K) : msq_gemm_mxfp8_tma_workspace_bytes(M, N, K)))
+    return MSQ_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -828,7 +858,8 @@ int msq_gemm_mxfp8_tma(const unsigned char* xcodes, long long ldx, const signed 
   YParams P;
   memset(&P, 0, sizeof(P));
   int cta2 = 0, ksplit = 1;
-  plan(M, N, K, sms, P.bn, P.nacc, cta2, false, &ksplit);
+  P.c_bf16 = c_is_bf16 ? 1 : 0;
+  plan(M, N, K, sms, P.bn, P.nacc, cta2, false, &ksplit, !c_is_bf16);
   if (o_ptr && cta2) { cta2 = 0; choose_bn(M, N, K, sms, P.bn, P.nacc); }       // the fused sparse epilogue lives in the one-CTA kernel
   P.wsf_t = wsf_tiled; P.xsf_t = reinterpret_cast<const uint8_t*>(workspace); P.C = C; P.ldc = ldc;
   P.M = M; P.N = N; P.K = K; P.accumulate = accumulate; P.terms = terms;

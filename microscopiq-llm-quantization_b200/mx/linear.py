@@ -203,7 +203,7 @@ class MXLinear(torch.nn.Linear):
             if fp == (2, 3) and _tc.mx4_pair_ok(pw, x2.shape[0]):
                 y = _tc.packed_linear_mx4(xq, pw, bias=self.bias, out_dtype=inputs.dtype)
             elif fp == (4, 5):
-                y = _tc.packed_linear_mx8(xq, pw, bias=self.bias)
+                y = _tc.packed_linear_mx8(xq, pw, bias=self.bias, out_dtype=inputs.dtype)
             else:
                 return None
         except NotImplementedError:          # a weight the block-scaled kernels cannot take: the default route decides
