@@ -144,3 +144,27 @@ def test_fasterquant_llama_shape_improves_on_rtn(M):
     e_gptq = float(((W.cuda() - Wq) @ Xf.t()).pow(2).sum())
     e_rtn = float(((W.cuda() - rtn) @ Xf.t()).pow(2).sum())
     assert e_gptq < e_rtn
+
+
+@pytest.mark.timeout(300)
+def test_no_prune_variant_vs_oracle(M):
+    """GPTQ(layer, prune=False) = the reference's vlm/gptq.py:130-144 column loop (quantize_mx_outlier_v1 per column, no
+    inlier zeroed afterwards): the fused solver never refuses -- also on the fixture where prune=True must fall back --
+    and its first column block equals the oracle's no-prune loop bit for bit"""
+    z = load_npz("gptq.npz")
+    for n, c in enumerate(load_json("gptq_cases.json")):
+        W, Hinv = z["W_%d" % n], z["Hinv_%d" % n]
+        layer = torch.nn.Linear(W.shape[1], W.shape[0], bias=False).cuda()
+        layer.weight.data = W.clone().cuda()
+        gq = M.GPTQ(layer, prune=False)
+        gq.quantizer = M.MXQuantizer()
+        gq.quantizer.configure(8, 8, c["in_fmt"], c["out_fmt"], axes=[0], block_size=c["bs"])
+        Q, loss = gq._solve_fused(W.cuda().clone(), Hinv.cuda().contiguous())
+        assert Q is not None, n
+        cfg = dict(inlier_scale_bits=8, outlier_scale_bits=8, inlier_elem_format=c["in_fmt"],
+                   outlier_elem_format=c["out_fmt"], block_size=c["bs"])
+        Qo, loss_o, _ = O.fasterquant(W, Hinv, cfg, c["blocksize"], prune=False)
+        b0 = min(c["blocksize"], W.shape[1])
+        assert mismatches(Q[:, :b0], Qo[:, :b0]) == 0, n
+        assert mismatches(Q, Qo) / Q.numel() < 0.01, n          # beyond block 0: fp32 order of the trailing update
+        assert abs(loss - float(loss_o)) <= 1e-2 * float(loss_o), n
