@@ -469,7 +469,12 @@ int launch_strided_tma(int n, const float* const* in, float* const* out, const l
   }
   P.tile_start[n] = (unsigned)total;
   P.total = (unsigned)total;
-  if (bs == 16) return launch_one<16, 256, 3>(P, stream);
+  if (bs == 16) {
+    // MSQ_QUANT_TMA_OCC=2 (A/B): two CTAs per SM instead of three -- measured in bench.py on an uncapped box: 0.851 vs 0.875
+    const char* eo = getenv("MSQ_QUANT_TMA_OCC");
+    if (eo && eo[0] == '2') return launch_one<16, 256, 2>(P, stream);
+    return launch_one<16, 256, 3>(P, stream);
+  }
   if (bs == 32) return launch_one<32, 128, 3>(P, stream);
   return launch_one<8, 256, 4>(P, stream);
 }
