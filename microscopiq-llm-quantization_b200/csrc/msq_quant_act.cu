@@ -171,10 +171,13 @@ static int launch(ActParams P, bool fp4, cudaStream_t s) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   long long blocks = (tasks + 255) / 256;
-  const long long cap = (long long)sms * 8;             // one wave of resident CTAs once the tensor is large
+  // exactly one wave of resident CTAs once the tensor is large (a fixed 8 per SM left a partial second wave)
+  void (*k)(const ActParams) = fp4 ? k_quant_act<DT, true> : k_quant_act<DT, false>;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 256, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 4; }
+  const long long cap = (long long)sms * occ;
   if (blocks > cap) blocks = cap;
-  if (fp4) k_quant_act<DT, true><<<(unsigned)blocks, 256, 0, s>>>(P);
-  else k_quant_act<DT, false><<<(unsigned)blocks, 256, 0, s>>>(P);
+  k<<<(unsigned)blocks, 256, 0, s>>>(P);
   return cudaGetLastError() == cudaSuccess ? MSQ_OK : MSQ_ERR_CUDA;
 }
 
